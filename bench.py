@@ -1,0 +1,390 @@
+"""bench.py -- env-steps/s of the Ofighters hot path on B200 (contract: see README / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+
+A *step* is one lockstep frame of every arena in the batch: scripted-bot actions -> fused arena
+step (K1) -> observation raster (K2) [-> policy forward for the policy workloads], with the
+MAX_TIME=200 episode restart when due.  One process per GPU; arenas are sharded with no data-path
+collective (weak scaling: the per-GPU batch is fixed), NCCL only all-reduces the per-episode stats.
+
+Workloads (BASELINE.json configs):
+    arena4096    configs[1]: 4096 default arenas (7 ships), random bots, step + raster   [default]
+    stress       configs[3]: 16384 arenas x 32 ships, max fire rate, step + raster
+    policy       configs[2]: 65536 arenas, ship 0 policy-driven (conv+dense bi-head forward, bf16)
+    sharded1m    configs[4]: 131072 arenas per GPU, policy forward, per-episode stat all-reduce
+
+Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB memset)
+between steps when the working set is smaller than L2, barrier + synchronize on both sides of the
+timed region, max over ranks.  `--impl reference` times the CPU restatement of the reference
+(oracle/step_c.c, OpenMP over all host cores) on the same workload; the reference itself is pure
+Python under /root/reference and cannot travel to the GPU box.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 0x0F16
+
+WORKLOADS = {
+    # name: (arenas per GPU, ships, bot kind, laser_cap, policy ships, description)
+    "arena4096": dict(n=4096, ships=7, bot="random", lcap=0, policy=0,
+                      desc="configs[1]: 4096 default arenas (400x400, 7 ships), random-action bots, "
+                           "step + observation raster (bit-packed maps)"),
+    "stress": dict(n=16384, ships=32, bot="stress", lcap=32 * 64, policy=0,
+                   desc="configs[3]: 16384 arenas x 32 ships, every ship shoots every frame, step + raster"),
+    "policy": dict(n=65536, ships=7, bot="random", lcap=0, policy=1,
+                   desc="configs[2]: 65536 default arenas, ship 0 driven by the bi-head policy forward (bf16), "
+                        "ships 1-6 random bots"),
+    "sharded1m": dict(n=131072, ships=7, bot="random", lcap=0, policy=1,
+                      desc="configs[4]: 131072 arenas per GPU (1M over 8), policy forward, per-episode stats all-reduce"),
+}
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU with NVML while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksEventReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_arm(wl, steps, warmup, n_cap=4096):
+    """The reference's algorithm on the host cores: oracle/step_c.c (bots + step + raster, OpenMP).
+    Returns (env_steps_per_s, ms_per_step, cores, sample description)."""
+    import numpy as np
+    from oracle.step_c import ArenasC
+    N = min(wl["n"], n_cap)
+    S = wl["ships"]
+    c0 = ArenasC(np.zeros((N, S, 2), np.int32))
+    spawn = c0.random_spawn(SEED, 0)
+    c = ArenasC(spawn, lcap=wl["lcap"] or None)
+    out_t = 0.0
+    t_ep, ep = 0, 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        if t_ep >= 200:
+            ep += 1
+            c.reset(c.random_spawn(SEED, ep))
+            t_ep = 0
+        c.step(c.bot_actions(wl["bot"], SEED, it))
+        c.raster_bits()
+        t_ep += 1
+        if it >= warmup:
+            out_t += time.perf_counter() - t0
+    cores = os.cpu_count() or 1
+    return N * steps / out_t, out_t / steps * 1e3, cores, \
+        "%d arenas x %d frames of bots+step+raster, oracle/step_c.c (gcc -O2 -fopenmp, %d threads)" % (N, steps, cores)
+
+
+def python_port_rate(ships, frames=100):
+    """The pure-Python restatement (same language and structure as the reference) on one core."""
+    import numpy as np
+    from oracle.step_py import ArenaPy
+    from oracle.traces import make_tapes
+    spawn, actions = make_tapes(1, 1, frames, ships, "random")
+    a = ArenaPy(spawn[0])
+    t0 = time.perf_counter()
+    for t in range(frames):
+        a.step(actions[0, t])
+        a.maps()
+    return frames / (time.perf_counter() - t0)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def gpu_arm(args, wl):
+    import torch
+    import torch.distributed as dist
+    from ofighters_b200 import ArenaConfig, BatchedBattleground
+    from ofighters_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N>1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N, S = wl["n"], wl["ships"]
+    steps, warmup = args.steps, max(args.warmup, 3)
+    max_time = 200
+
+    ships = {wl["bot"]: S} if not wl["policy"] else {"QlearnIA": wl["policy"], wl["bot"]: S - wl["policy"]}
+    bg = BatchedBattleground(N, ships=ships, config=ArenaConfig(laser_cap=wl["lcap"]), device=dev, seed=SEED,
+                             arena0=rank * N)
+    policy = None
+    if wl["policy"]:
+        from ofighters_b200.policy import PolicyB200
+        policy = PolicyB200.random_init(device=dev, seed=0)
+    maps = torch.empty((N, 2, 400 * 400 // 32), dtype=torch.int32, device=dev)
+    state_bytes = N * bg.state_stride
+    flush_needed = state_bytes + maps.numel() * 4 < 2 * 126 * 2 ** 20
+    flush_buf = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev) if flush_needed else None
+    launches = [0]
+
+    def one_step():
+        n0 = bg.launch_count
+        if bg.time >= max_time:
+            bg.restart()
+            if world > 1:
+                dist.all_reduce(bg.stats)          # K7: per-episode [score, kills, deaths, shots, ships, arenas]
+        if policy is not None:
+            bg.request_actions()
+            bg.raster("bits", out=maps) if bg.total_steps == 0 else None
+            policy.act(bg, maps)                   # writes ship 0's action rows from the forward's argmax
+            bg.generate_frame()
+        else:
+            bg.frame()
+        bg.raster("bits", out=maps)
+        launches[0] += bg.launch_count - n0 + (policy.launches_per_forward if policy is not None else 0)
+
+    stream = torch.cuda.current_stream(dev)
+    for _ in range(warmup):
+        one_step()
+    torch.cuda.synchronize(dev)
+
+    # ---- timed region: exactly K steps, per-step CUDA events, optional L2 flush between steps
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler.start()
+    launches[0] = 0
+    wall0 = time.perf_counter()
+    for k in range(steps):
+        if flush_buf is not None:
+            flush_buf.zero_()
+        ev[k][0].record(stream)
+        one_step()
+        ev[k][1].record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    bg.check_overflow()
+    value = N * world * steps / (total_ms * 1e-3)
+
+    # ---- dominant kernel alone (raster for the arena workloads), same events + flush
+    roof = kernel_roofline(bg, maps, flush_buf, wl, dev)
+
+    # ---- end-to-end through the public API with HOST buffers
+    e2e = e2e_arm(bg, maps, wl, dev, min(steps, 400), world)
+
+    out = {
+        "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster%s)" %
+                  (" + policy fwd" if wl["policy"] else ""),
+        "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 laser physics / i32 ship state / u32 bit maps" + (" / bf16 policy" if wl["policy"] else ""),
+        "data": "synthetic (Philox-seeded spawns and bot actions)",
+        "config": {"workload": args.workload, "desc": wl["desc"], "arenas_per_gpu": N, "arenas_total": N * world,
+                   "ships_per_arena": S, "ship_steps_per_s": value * S, "map_format": "bits u32[N,2,5000]",
+                   "episode": "restart every 200 frames inside the timed region",
+                   "l2": ("flushed between steps (256 MiB memset, outside the per-step events)" if flush_needed
+                          else "working set %.0f MB > L2" % ((state_bytes + maps.numel() * 4) / 1e6)),
+                   "wall_s_timed_region": wall},
+        "gpu_launches": launches[0], "clocks": clocks, "e2e": e2e, "roofline": roof,
+    }
+    if rank == 0:
+        if world == 1:
+            v, ms, cores, sample = cpu_arm(wl, 100, 5)
+            try:
+                py = python_port_rate(S)
+            except Exception:
+                py = None
+            out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                   "sample": sample, "python_port_env_steps_per_s_1core": py}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(bg, maps, flush_buf, wl, dev, iters=50):
+    """Dominant kernel of the arena workloads = the raster (it writes >95 % of the step's bytes).
+    achieved = algorithmic bytes (the tensor it must produce: N * 2 * W*H/8) / mean launch time."""
+    import torch
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    stream = torch.cuda.current_stream(dev)
+    res = {}
+    for name, fn, nbytes in (("k_raster", lambda: bg.raster("bits", out=maps), maps.numel() * 4),
+                             ("k_step", lambda: bg.generate_frame(), bg.algorithmic_step_bytes)):
+        ts = []
+        for _ in range(iters):
+            if flush_buf is not None:
+                flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nb = nbytes() if callable(nbytes) else nbytes
+            a.record(stream)
+            fn()
+            b.record(stream)
+            ts.append((a, b, nb))
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b, _ in ts) / iters
+        nb = sum(x[2] for x in ts) / iters
+        res[name] = {"us": ms * 1e3, "bytes": nb, "gbs": nb / (ms * 1e-3) / 1e9}
+    dom = "k_raster"
+    return {"bound": "hbm", "kernel": dom, "achieved": res[dom]["gbs"], "peak": peak, "unit": "GB/s",
+            "frac": res[dom]["gbs"] / peak,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+            "traffic": None, "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
+            "other_kernels": {"k_step": res["k_step"]}}
+
+
+def e2e_arm(bg, maps, wl, dev, steps, world):
+    """Same metric through BatchedBattleground with HOST buffers: every step the host bot's action
+    tensor is copied from pinned memory, the step + raster run, and the per-ship observation heads
+    (what a host bot is shown, incl. its reward) are read back.  Maps stay in HBM for the policy."""
+    import numpy as np
+    import torch
+    N, S = bg.n_arenas, bg.ships_number
+    rng = np.random.Generator(np.random.PCG64(7))
+    T = 64
+    kind = rng.integers(0, 3, size=(T, N, S), dtype=np.int16)
+    newp = rng.integers(0, 401, size=(T, N, S, 2), dtype=np.int16)
+    act_host = torch.empty((N, S, 4), dtype=torch.int16).pin_memory()
+    obs_host = torch.empty((N, S, 8), dtype=torch.float32).pin_memory()
+    act_np, obs_np = act_host.numpy(), obs_host.numpy()
+    obs_host.copy_(bg.obs_vec)
+    torch.cuda.synchronize(dev)
+
+    def host_step(k):
+        t = k % T
+        if wl["bot"] == "stress":
+            act_np[..., 0] = 1
+            act_np[..., 1] = kind[t] & 1
+            act_np[..., 2:] = np.minimum(newp[t], 399)
+        else:                                               # agents/agent.py:123-133 on the host
+            act_np[..., 0] = kind[t] == 0
+            act_np[..., 1] = kind[t] == 1
+            rep = (kind[t] == 2)[..., None]
+            act_np[..., 2:] = np.where(rep, newp[t], obs_np[..., 2:4].astype(np.int16))
+        if bg.time >= 200:
+            bg.restart()
+        bg.step_host(act_host, obs_host)                    # H2D actions, K1, D2H obs heads (synchronises)
+        bg.raster("bits", out=maps)
+
+    for k in range(3):
+        host_step(k)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(steps):
+        host_step(k)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    return {"value": N * world * steps / dt, "unit": "env-steps/s", "h2d_bytes_per_step": act_host.numel() * 2,
+            "d2h_bytes_per_step": obs_host.numel() * 4, "steps": steps,
+            "what": "pinned host actions -> H2D -> step -> raster (maps stay in HBM) -> D2H obs heads; host-side "
+                    "random bot (numpy) inside the timed region; wall clock"}
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--workload", default="arena4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        steps = min(args.steps, 400)
+        v, ms, cores, sample = cpu_arm(wl, steps, min(max(args.warmup, 3), 10))
+        print(json.dumps({
+            "impl": "reference", "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster)",
+            "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 laser physics / i32 ship state / u32 bit maps", "data": "synthetic (Philox-seeded)",
+            "config": {"workload": args.workload, "desc": wl["desc"],
+                       "note": "CPU restatement of the reference's algorithm (the reference is pure Python under "
+                               "/root/reference and is absent on the GPU box); policy forward not included"},
+            "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    gpu_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,129 @@
+/* ofb.h -- C ABI of libofb.so: the B200 (sm_100a) drop-in for Ofighters' data-parallel hot path.
+ *
+ * The reference (Chthi/Ofighters) is pure Python and has no FFI of its own; this header declares
+ * the entry points a Python binding of that path needs, each citing the reference interface it
+ * replaces (paths under /root/reference/ofighters).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error (OFB_E_*); the message of the last error
+ *     on the calling thread is ofb_last_error().
+ *   - every pointer marked "dev" is DEVICE memory owned by the caller; the handle owns only its
+ *     arena state allocated at create time.  Nothing is allocated on the step path.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All calls are
+ *     asynchronous on that stream unless stated otherwise.
+ *   - a handle is bound to one device and is not thread-safe.  There is no CPU fallback: without
+ *     a CUDA device ofb_create fails with OFB_E_CUDA.
+ *
+ * Tensor formats
+ *   actions   int16 [N, S, 4] = (shoot, thrust, pointing_x, pointing_y)     lib/action.py:12-56
+ *   obs_vec   float [N, S, 8] = (reward, can_shoot=1, pointing_x, pointing_y, W, H, x, y)
+ *                                                                            lib/observation.py:113-123
+ *   spawn     int32 [N, S, 2] = (x, y), 0..W / 0..H inclusive                lib/battleground.py:114
+ *   maps      OFB_MAP_BITS : uint32 [N, 2, W*H/32], bit (y*W + x) LSB-first, ch0 ships, ch1 lasers
+ *             OFB_MAP_BF16 : bf16   [N, H, W, 2]  (NHWC, the Keras input of qlearnIA_V2.py:208)
+ *             OFB_MAP_U8   : uint8  [N, H, W, 2]
+ */
+#ifndef OFB_H
+#define OFB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OFB_ABI_VERSION 1
+
+enum {
+    OFB_OK = 0,
+    OFB_E_ARG = -1,      /* bad argument */
+    OFB_E_CUDA = -2,     /* CUDA runtime error (message in ofb_last_error) */
+    OFB_E_NOMEM = -3,
+    OFB_E_STATE = -4     /* e.g. laser-slot overflow detected */
+};
+
+enum { OFB_MAP_BITS = 0, OFB_MAP_BF16 = 1, OFB_MAP_U8 = 2 };
+
+/* scripted bots of agents/agent.py:99-155 (+ the stress distribution of SURVEY 8(d) config 4) */
+enum { OFB_BOT_IDLE = 0, OFB_BOT_RANDOM = 1, OFB_BOT_TURRET = 2, OFB_BOT_RUNNER = 3,
+       OFB_BOT_THRUST = 4, OFB_BOT_SHOOT = 5, OFB_BOT_STRESS = 6,
+       OFB_BOT_EXTERNAL = 255 /* leave the ship's action row untouched (policy / host bot) */ };
+
+/* Arena constants; defaults = the reference's module constants (SURVEY section 5 "config"). */
+typedef struct ofb_config {
+    int32_t n_ships;        /* ships per arena, 1..32          lib/ofighters.py:53 (7)       */
+    int32_t laser_cap;      /* laser slots per arena, 0 = auto (max(128, 16*n_ships))         */
+    int32_t width, height;  /* lib/observation.py:10-11 (400, 400); width*height % 32 == 0    */
+    int32_t max_time;       /* lib/ofighters.py:59 (200) -- informational, host enforces it   */
+    int32_t reward_kill, reward_death, reward_aim, reward_trajectory;  /* qlearnIA_V2.py:39-44 */
+    int32_t reserved[7];
+} ofb_config;
+
+typedef struct ofb_arenas ofb_arenas;   /* opaque: N arenas' struct-of-arrays state on one GPU */
+
+/* Flat views for export / import (all dev pointers, any may be NULL to skip). */
+typedef struct ofb_state_view {
+    int32_t *time, *n_lasers, *kills, *deaths, *shots, *overflow, *episode, *near_ties;  /* [N]   */
+    int32_t *ship_x, *ship_y, *ship_px, *ship_py, *ship_hull, *ship_reward,
+            *ship_score, *ship_steps;                                                     /* [N,S] */
+    uint8_t *ship_alive;                                                                  /* [N,S] */
+    double  *laser_x, *laser_y, *laser_dx, *laser_dy;                                     /* [N,L] */
+    uint8_t *laser_owner, *laser_destroyed;                                               /* [N,L] */
+} ofb_state_view;
+
+int         ofb_abi_version(void);
+const char *ofb_last_error(void);
+void        ofb_default_config(ofb_config *cfg);
+
+/* Battleground.__init__ for N arenas (lib/battleground.py:13-106): ships placed at spawn[N,S,2]
+ * (dev, int32), pointing = own position, hull 1, flying, no lasers, time 0. */
+int ofb_create(const ofb_config *cfg, int64_t n_arenas, int device, const int32_t *spawn_dev,
+               void *stream, ofb_arenas **out);
+int ofb_destroy(ofb_arenas *h);
+int ofb_laser_cap(const ofb_arenas *h);
+int64_t ofb_state_stride(const ofb_arenas *h);   /* bytes of HBM per arena (for sizing) */
+
+/* Battleground.restart + Ship.reset + Agent.reset (lib/battleground.py:108-117, lib/ship.py:92-106,
+ * agents/agent.py:59-64) for the arenas with mask[a] != 0 (mask NULL = all).  Before zeroing, the
+ * episode's [sum score, kills, deaths, shots, ships, arenas] are added into stats_dev[6] (int64,
+ * may be NULL) -- the payload of the per-episode all-reduce. */
+int ofb_reset(ofb_arenas *h, const uint8_t *mask_dev, const int32_t *spawn_dev, int64_t *stats_dev,
+              void *stream);
+
+/* Battleground.generate_frame(actions) (lib/battleground.py:153-160) preceded by the score fold of
+ * Agent.step (agents/agent.py:66-74) and the destroyed-laser pruning of the Tk controller
+ * (lib/ofighters.py:704-707).  If obs_out_dev != NULL the per-ship observation head of the NEXT
+ * request_actions() is written there (float [N,S,8]). */
+int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *stream);
+
+/* Same step driven from HOST buffers (a host-side bot loop calling Battleground.frame,
+ * lib/battleground.py:163-166): actions_host int16 [N,S,4] is copied to the device, the step runs,
+ * and the next observation heads are copied back to obs_host float [N,S,8] (may be NULL).  Both
+ * host buffers should be pinned; the call is asynchronous on `stream` -- synchronise before reading. */
+int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream);
+
+/* Observation.analyse_ship head for every ship (lib/observation.py:101-123). */
+int ofb_obs_vec(const ofb_arenas *h, float *out_dev, void *stream);
+
+/* Observation.analyse_battleground (lib/observation.py:79-95): ship_map / laser_map of every arena. */
+int ofb_raster(const ofb_arenas *h, void *out_dev, int format, void *stream);
+
+/* Scripted bots (agents/agent.py:99-155): counter-based Philox4x32-10 keyed by (seed; global arena
+ * id = arena0 + a, ship, step).  kinds_dev (uint8 [S], may be NULL) gives one bot kind per ship
+ * index like the reference's ships={"behavior": n} map (lib/battleground.py:21-28,79-81);
+ * when NULL every ship uses bot_kind. */
+int ofb_bot_actions(const ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed,
+                    int64_t arena0, uint32_t step, int16_t *actions_dev, void *stream);
+/* randint(0, W) x randint(0, H) spawn draws of lib/battleground.py:79-81,114. */
+int ofb_random_spawn(int64_t n_arenas, int n_ships, int width, int height, uint64_t seed, int64_t arena0,
+                     uint32_t episode, int32_t *spawn_dev, void *stream);
+
+int ofb_state_export(const ofb_arenas *h, const ofb_state_view *view, void *stream);
+int ofb_state_import(ofb_arenas *h, const ofb_state_view *view, void *stream);
+
+/* ---- policy forward (agents/qlearnIA_V2.py:123-235), see ofb_policy.h ---- */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OFB_H */

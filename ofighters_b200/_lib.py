@@ -1,0 +1,82 @@
+"""ctypes binding of libofb.so (include/ofb.h).  No torch types cross this boundary: tensors
+are passed as raw device pointers, streams as ``cudaStream_t`` integers.
+
+The library is built in-tree by ``ofighters_b200.build``; if it is missing the import of the
+product path fails loudly -- there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+from . import build as _build
+
+OFB_MAP_BITS, OFB_MAP_BF16, OFB_MAP_U8 = 0, 1, 2
+BOT_KINDS = {"idle": 0, "random": 1, "turret": 2, "runner": 3, "thrust": 4, "shoot": 5, "stress": 6,
+             "external": 255}
+
+
+class OfbConfig(C.Structure):
+    _fields_ = [("n_ships", C.c_int32), ("laser_cap", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+                ("max_time", C.c_int32), ("reward_kill", C.c_int32), ("reward_death", C.c_int32),
+                ("reward_aim", C.c_int32), ("reward_trajectory", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+STATE_VIEW_FIELDS = ["time", "n_lasers", "kills", "deaths", "shots", "overflow", "episode", "near_ties",
+                     "ship_x", "ship_y", "ship_px", "ship_py", "ship_hull", "ship_reward", "ship_score",
+                     "ship_steps", "ship_alive", "laser_x", "laser_y", "laser_dx", "laser_dy",
+                     "laser_owner", "laser_destroyed"]
+
+
+class OfbStateView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in STATE_VIEW_FIELDS]
+
+
+class OfbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        raise OfbError("libofb.so not built (%s); run `python -m ofighters_b200.build` -- "
+                       "there is no CPU fallback" % path)
+    lib = C.CDLL(path)
+    vp, i64, u64, u32, i32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_uint32, C.c_int
+    lib.ofb_abi_version.restype = i32
+    lib.ofb_last_error.restype = C.c_char_p
+    lib.ofb_default_config.argtypes = [C.POINTER(OfbConfig)]
+    lib.ofb_default_config.restype = None
+    lib.ofb_create.argtypes = [C.POINTER(OfbConfig), i64, i32, vp, vp, C.POINTER(vp)]
+    lib.ofb_destroy.argtypes = [vp]
+    lib.ofb_laser_cap.argtypes = [vp]
+    lib.ofb_state_stride.argtypes = [vp]
+    lib.ofb_state_stride.restype = i64
+    lib.ofb_step_host.argtypes = [vp, vp, vp, vp]
+    lib.ofb_reset.argtypes = [vp, vp, vp, vp, vp]
+    lib.ofb_step.argtypes = [vp, vp, vp, vp]
+    lib.ofb_obs_vec.argtypes = [vp, vp, vp]
+    lib.ofb_raster.argtypes = [vp, vp, i32, vp]
+    lib.ofb_bot_actions.argtypes = [vp, i32, vp, u64, i64, u32, vp, vp]
+    lib.ofb_random_spawn.argtypes = [i64, i32, i32, i32, u64, i64, u32, vp, vp]
+    lib.ofb_state_export.argtypes = [vp, C.POINTER(OfbStateView), vp]
+    lib.ofb_state_import.argtypes = [vp, C.POINTER(OfbStateView), vp]
+    for name in ("ofb_create", "ofb_destroy", "ofb_laser_cap", "ofb_reset", "ofb_step", "ofb_step_host", "ofb_obs_vec", "ofb_raster",
+                 "ofb_bot_actions", "ofb_random_spawn", "ofb_state_export", "ofb_state_import"):
+        getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc < 0:
+        raise OfbError("libofb error %d: %s" % (rc, load().ofb_last_error().decode()))
+    return rc

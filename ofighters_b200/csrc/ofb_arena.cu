@@ -1,0 +1,363 @@
+// Handle management + the small arena kernels: create/reset (Battleground.__init__/restart),
+// observation head, scripted bots, state export/import.  Compiled with -fmad=false.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "ofb_common.cuh"
+
+// ---------------------------------------------------------------- error plumbing
+static thread_local char g_err[512] = "";
+void ofb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *ofb_last_error(void) { return g_err; }
+extern "C" int ofb_abi_version(void) { return OFB_ABI_VERSION; }
+
+extern "C" void ofb_default_config(ofb_config *c) {
+    memset(c, 0, sizeof(*c));
+    c->n_ships = 7;            // lib/ofighters.py:53
+    c->laser_cap = 0;
+    c->width = 400;            // lib/observation.py:10-11
+    c->height = 400;
+    c->max_time = 200;         // lib/ofighters.py:59
+    c->reward_kill = 0;        // agents/qlearnIA_V2.py:39-44
+    c->reward_death = 0;
+    c->reward_aim = 2;
+    c->reward_trajectory = 1;
+}
+
+// ---------------------------------------------------------------- init / reset
+// One thread per (arena, ship slot SP); thread 0 of the arena also writes the header.
+__global__ void k_init(char *state, ArenaLayout lay, const int32_t *spawn, long long n_arenas) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long a = t / lay.SP;
+    int i = (int)(t % lay.SP);
+    if (a >= n_arenas) return;
+    char *base = state + a * (long long)lay.stride;
+    int *ship = reinterpret_cast<int *>(base + lay.off_ship);
+    if (i == 0) {
+        int *hdr = reinterpret_cast<int *>(base);
+        for (int k = 0; k < 8; k++) hdr[k] = 0;
+    }
+    int x = 0, y = 0, fl = 0;
+    if (i < lay.S) {
+        x = spawn[(a * lay.S + i) * 2];
+        y = spawn[(a * lay.S + i) * 2 + 1];
+        fl = 1 | (1 << 8);                                   // flying, hull 1 (lib/ship.py:45,55)
+    }
+    ship[SF_X * lay.SP + i] = x;
+    ship[SF_Y * lay.SP + i] = y;
+    ship[SF_PX * lay.SP + i] = x;                            // pointing = own position (lib/ship.py:52)
+    ship[SF_PY * lay.SP + i] = y;
+    ship[SF_REWARD * lay.SP + i] = 0;
+    ship[SF_SCORE * lay.SP + i] = 0;
+    ship[SF_STEPS * lay.SP + i] = 0;
+    ship[SF_FLAGS * lay.SP + i] = fl;
+}
+
+// Battleground.restart (lib/battleground.py:108-117) + Ship.reset (lib/ship.py:92-106) +
+// Agent.reset (agents/agent.py:59-64).  One warp per arena; the episode's statistics are
+// warp-reduced, then block-reduced in shared memory, then one atomicAdd per block and stat.
+__global__ void __launch_bounds__(256)
+k_reset(char *state, ArenaLayout lay, const uint8_t *mask, const int32_t *spawn,
+        unsigned long long *stats, long long n_arenas) {
+    __shared__ long long s_acc[6];
+    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool ok = a < n_arenas && (!mask || mask[a]);
+    long long acc_score = 0;
+    int k = 0, d = 0, sh = 0;
+    if (ok) {
+        char *base = state + a * (long long)lay.stride;
+        int *hdr = reinterpret_cast<int *>(base);
+        int *ship = reinterpret_cast<int *>(base + lay.off_ship);
+        if (lane < lay.S) {
+            const int SP = lay.SP;
+            acc_score = ship[SF_SCORE * SP + lane];          // scores.append(score)
+            const int ox = ship[SF_X * SP + lane], oy = ship[SF_Y * SP + lane];
+            const int nx = spawn[(a * lay.S + lane) * 2], ny = spawn[(a * lay.S + lane) * 2 + 1];
+            ship[SF_PX * SP + lane] = ox;                    // pointing = OLD position
+            ship[SF_PY * SP + lane] = oy;
+            ship[SF_X * SP + lane] = nx ? nx : ox;           // "x or self.body.x": 0 keeps old
+            ship[SF_Y * SP + lane] = ny ? ny : oy;
+            ship[SF_SCORE * SP + lane] = 0;
+            ship[SF_STEPS * SP + lane] = 0;
+            ship[SF_FLAGS * SP + lane] |= 1;                 // flying again; hull NOT restored
+            // pending reward survives the reset (agents/agent.py:59-64)
+        }
+        k = hdr[HDR_KILLS]; d = hdr[HDR_DEATHS]; sh = hdr[HDR_SHOTS];
+    }
+    __syncwarp();
+    if (ok && lane == 0) {
+        int *hdr = reinterpret_cast<int *>(state + a * (long long)lay.stride);
+        hdr[HDR_TIME] = 0; hdr[HDR_NLASERS] = 0; hdr[HDR_KILLS] = 0; hdr[HDR_DEATHS] = 0;
+        hdr[HDR_SHOTS] = 0; hdr[HDR_EPISODE] += 1;
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc_score += __shfl_xor_sync(0xffffffffu, acc_score, o);
+        if (lane == 0 && ok) {
+            atomicAdd((unsigned long long *)&s_acc[0], (unsigned long long)acc_score);
+            atomicAdd((unsigned long long *)&s_acc[1], (unsigned long long)k);
+            atomicAdd((unsigned long long *)&s_acc[2], (unsigned long long)d);
+            atomicAdd((unsigned long long *)&s_acc[3], (unsigned long long)sh);
+            atomicAdd((unsigned long long *)&s_acc[4], (unsigned long long)lay.S);
+            atomicAdd((unsigned long long *)&s_acc[5], 1ull);
+        }
+        __syncthreads();
+        if (threadIdx.x < 6 && s_acc[threadIdx.x] != 0)
+            atomicAdd(&stats[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
+    }
+}
+
+// ---------------------------------------------------------------- observation head
+__global__ void k_obs_vec(const char *state, ArenaLayout lay, float4 *out, long long n_ships_total) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ships_total) return;
+    long long a = t / lay.S;
+    int i = (int)(t % lay.S);
+    const int *ship = reinterpret_cast<const int *>(state + a * (long long)lay.stride + lay.off_ship);
+    const int SP = lay.SP;
+    out[t * 2] = make_float4((float)ship[SF_REWARD * SP + i], 1.0f, (float)ship[SF_PX * SP + i],
+                             (float)ship[SF_PY * SP + i]);
+    out[t * 2 + 1] = make_float4((float)lay.W, (float)lay.H, (float)ship[SF_X * SP + i], (float)ship[SF_Y * SP + i]);
+}
+
+// ---------------------------------------------------------------- scripted bots
+__global__ void k_bot_actions(const char *state, ArenaLayout lay, int kind, const uint8_t *kinds, uint64_t seed,
+                              long long arena0, uint32_t step, int2 *actions, long long n_ships_total) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ships_total) return;
+    long long a = t / lay.S;
+    int i = (int)(t % lay.S);
+    if (kinds) kind = kinds[i];
+    if (kind == OFB_BOT_EXTERNAL) return;                     // row is written by someone else (policy, host bot)
+    const int *ship = reinterpret_cast<const int *>(state + a * (long long)lay.stride + lay.off_ship);
+    uint32_t c[4] = {(uint32_t)(arena0 + a), (uint32_t)i, step, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    int shoot = 0, thrust = 0, px = ship[SF_PX * lay.SP + i], py = ship[SF_PY * lay.SP + i];
+    const int rx = (int)mulhi32(c[1], (uint32_t)lay.W + 1), ry = (int)mulhi32(c[2], (uint32_t)lay.H + 1);
+    switch (kind) {
+    case OFB_BOT_RANDOM: {                                    // agents/agent.py:123-133
+        uint32_t k = mulhi32(c[0], 3u);
+        shoot = k == 0; thrust = k == 1;
+        if (k == 2) { px = rx; py = ry; }
+    } break;
+    case OFB_BOT_TURRET:                                      // agents/agent.py:136-144
+        shoot = mulhi32(c[0], 10u) < 8;
+        if (mulhi32(c[3], 10u) < 3) { px = rx; py = ry; }
+        break;
+    case OFB_BOT_RUNNER:                                      // agents/agent.py:147-155
+        thrust = mulhi32(c[0], 10u) < 9;
+        if (mulhi32(c[3], 10u) < 1) { px = rx; py = ry; }
+        break;
+    case OFB_BOT_THRUST: thrust = 1; break;                   // agents/agent.py:107-112
+    case OFB_BOT_SHOOT: shoot = 1; break;                     // agents/agent.py:115-120
+    case OFB_BOT_STRESS:                                      // agents/qlearnIA_V2.py:317-321, shoot forced
+        shoot = 1; thrust = (int)(c[0] & 1u);
+        px = (int)mulhi32(c[1], (uint32_t)lay.W); py = (int)mulhi32(c[2], (uint32_t)lay.H);
+        break;
+    default: break;                                           // idle: agents/agent.py:99-104
+    }
+    actions[t] = make_int2((shoot & 0xffff) | (thrust << 16), (px & 0xffff) | (py << 16));
+}
+
+__global__ void k_random_spawn(int S, int W, int H, uint64_t seed, long long arena0, uint32_t episode, int2 *spawn,
+                               long long n_ships_total) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_ships_total) return;
+    uint32_t c[4] = {(uint32_t)(arena0 + t / S), (uint32_t)(t % S), episode, 1u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    spawn[t] = make_int2((int)mulhi32(c[0], (uint32_t)W + 1), (int)mulhi32(c[1], (uint32_t)H + 1));
+}
+
+// ---------------------------------------------------------------- export / import
+template <bool IMPORT>
+__global__ void k_xfer(char *state, ArenaLayout lay, ofb_state_view v, long long n_arenas) {
+    const long long a = blockIdx.x;
+    if (a >= n_arenas) return;
+    char *base = state + a * (long long)lay.stride;
+    int *hdr = reinterpret_cast<int *>(base);
+    int *ship = reinterpret_cast<int *>(base + lay.off_ship);
+    double *lx = reinterpret_cast<double *>(base + lay.off_lx);
+    double *ly = reinterpret_cast<double *>(base + lay.off_ly);
+    double *ldx = reinterpret_cast<double *>(base + lay.off_ldx);
+    double *ldy = reinterpret_cast<double *>(base + lay.off_ldy);
+    unsigned *lmeta = reinterpret_cast<unsigned *>(base + lay.off_lmeta);
+    const int S = lay.S, SP = lay.SP, L = lay.L;
+    int32_t *hv[8] = {v.time, v.n_lasers, v.kills, v.deaths, v.shots, v.overflow, v.episode, v.near_ties};
+    if (threadIdx.x < 8 && hv[threadIdx.x]) {
+        if (IMPORT) hdr[threadIdx.x] = hv[threadIdx.x][a];
+        else hv[threadIdx.x][a] = hdr[threadIdx.x];
+    }
+    int32_t *sv[7] = {v.ship_x, v.ship_y, v.ship_px, v.ship_py, v.ship_reward, v.ship_score, v.ship_steps};
+    for (int i = threadIdx.x; i < S; i += blockDim.x) {
+        for (int f = 0; f < 7; f++)
+            if (sv[f]) {
+                if (IMPORT) ship[f * SP + i] = sv[f][a * S + i];
+                else sv[f][a * S + i] = ship[f * SP + i];
+            }
+        if (IMPORT) {
+            if (v.ship_alive && v.ship_hull)
+                ship[SF_FLAGS * SP + i] = (v.ship_alive[a * S + i] ? 1 : 0) | (v.ship_hull[a * S + i] << 8);
+        } else {
+            const int fl = ship[SF_FLAGS * SP + i];
+            if (v.ship_alive) v.ship_alive[a * S + i] = fl & 1;
+            if (v.ship_hull) v.ship_hull[a * S + i] = fl >> 8;
+        }
+    }
+    for (int k = threadIdx.x; k < L; k += blockDim.x) {
+        const long long o = a * L + k;
+        if (IMPORT) {
+            if (v.laser_x) lx[k] = v.laser_x[o];
+            if (v.laser_y) ly[k] = v.laser_y[o];
+            if (v.laser_dx) ldx[k] = v.laser_dx[o];
+            if (v.laser_dy) ldy[k] = v.laser_dy[o];
+            if (v.laser_owner && v.laser_destroyed)
+                lmeta[k] = (unsigned)v.laser_owner[o] | (v.laser_destroyed[o] ? 0x100u : 0u);
+        } else {
+            const bool live = k < hdr[HDR_NLASERS];
+            const unsigned m = live ? lmeta[k] : 0u;
+            if (v.laser_x) v.laser_x[o] = live ? lx[k] : 0.0;
+            if (v.laser_y) v.laser_y[o] = live ? ly[k] : 0.0;
+            if (v.laser_dx) v.laser_dx[o] = live ? ldx[k] : 0.0;
+            if (v.laser_dy) v.laser_dy[o] = live ? ldy[k] : 0.0;
+            if (v.laser_owner) v.laser_owner[o] = (uint8_t)(m & 0xffu);
+            if (v.laser_destroyed) v.laser_destroyed[o] = (uint8_t)((m >> 8) & 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- C ABI
+static inline unsigned nblocks(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+extern "C" int ofb_create(const ofb_config *cfg, int64_t n_arenas, int device, const int32_t *spawn_dev,
+                          void *stream, ofb_arenas **out) {
+    if (!cfg || !out || !spawn_dev || n_arenas <= 0) { ofb_set_error("ofb_create: bad argument"); return OFB_E_ARG; }
+    ofb_config c = *cfg;
+    if (c.n_ships < 1 || c.n_ships > 32) { ofb_set_error("ofb_create: n_ships must be 1..32"); return OFB_E_ARG; }
+    if (c.width < 32 || c.height < 1 || c.width > 16384 || c.height > 16384 || (c.width * c.height) % 128 != 0) {
+        ofb_set_error("ofb_create: width*height must be a multiple of 128 and fit int16 coordinates");
+        return OFB_E_ARG;
+    }
+    if (c.laser_cap <= 0) c.laser_cap = c.n_ships * 16 > 128 ? c.n_ships * 16 : 128;
+    c.laser_cap = (c.laser_cap + 31) & ~31;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        ofb_set_error("ofb_create: no CUDA device (libofb has no CPU fallback)");
+        return OFB_E_CUDA;
+    }
+    OFB_CUDA_CHECK(cudaSetDevice(device));
+    ofb_arenas *h = new (std::nothrow) ofb_arenas();
+    if (!h) return OFB_E_NOMEM;
+    h->cfg = c;
+    h->lay = make_layout(c);
+    h->n_arenas = n_arenas;
+    h->device = device;
+    h->state = nullptr;
+    cudaError_t e = cudaMalloc(&h->state, (size_t)n_arenas * h->lay.stride);
+    if (e != cudaSuccess) {
+        ofb_set_error("ofb_create: cudaMalloc(%zu) failed: %s", (size_t)n_arenas * h->lay.stride, cudaGetErrorString(e));
+        delete h;
+        return OFB_E_NOMEM;
+    }
+    h->stage_actions = nullptr;
+    h->stage_obs = nullptr;
+    const size_t n_ship = (size_t)n_arenas * c.n_ships;
+    if (cudaMalloc(&h->stage_actions, n_ship * 4 * sizeof(int16_t)) != cudaSuccess ||
+        cudaMalloc(&h->stage_obs, n_ship * 8 * sizeof(float)) != cudaSuccess) {
+        ofb_set_error("ofb_create: cudaMalloc of the host-staging buffers failed");
+        cudaFree(h->stage_actions);
+        cudaFree(h->state);
+        delete h;
+        return OFB_E_NOMEM;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nt = n_arenas * h->lay.SP;
+    k_init<<<nblocks(nt, 256), 256, 0, st>>>(h->state, h->lay, spawn_dev, n_arenas);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        ofb_set_error("ofb_create: init kernel failed: %s", cudaGetErrorString(e));
+        cudaFree(h->stage_actions);
+        cudaFree(h->stage_obs);
+        cudaFree(h->state);
+        delete h;
+        return OFB_E_CUDA;
+    }
+    *out = h;
+    return OFB_OK;
+}
+
+extern "C" int ofb_destroy(ofb_arenas *h) {
+    if (!h) return OFB_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->stage_actions);
+    cudaFree(h->stage_obs);
+    cudaFree(h->state);
+    delete h;
+    return OFB_OK;
+}
+
+extern "C" int ofb_laser_cap(const ofb_arenas *h) { return h ? h->lay.L : OFB_E_ARG; }
+extern "C" int64_t ofb_state_stride(const ofb_arenas *h) { return h ? (int64_t)h->lay.stride : OFB_E_ARG; }
+
+extern "C" int ofb_reset(ofb_arenas *h, const uint8_t *mask_dev, const int32_t *spawn_dev, int64_t *stats_dev,
+                         void *stream) {
+    if (!h || !spawn_dev) { ofb_set_error("ofb_reset: null argument"); return OFB_E_ARG; }
+    k_reset<<<nblocks(h->n_arenas * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        h->state, h->lay, mask_dev, spawn_dev, reinterpret_cast<unsigned long long *>(stats_dev), h->n_arenas);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_obs_vec(const ofb_arenas *h, float *out_dev, void *stream) {
+    if (!h || !out_dev) { ofb_set_error("ofb_obs_vec: null argument"); return OFB_E_ARG; }
+    const long long nt = h->n_arenas * h->lay.S;
+    k_obs_vec<<<nblocks(nt, 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->lay, reinterpret_cast<float4 *>(out_dev), nt);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_bot_actions(const ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed,
+                               int64_t arena0, uint32_t step, int16_t *actions_dev, void *stream) {
+    if (!h || !actions_dev || bot_kind < 0 || (bot_kind > OFB_BOT_STRESS && bot_kind != OFB_BOT_EXTERNAL)) {
+        ofb_set_error("ofb_bot_actions: bad argument");
+        return OFB_E_ARG;
+    }
+    const long long nt = h->n_arenas * h->lay.S;
+    k_bot_actions<<<nblocks(nt, 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->lay, bot_kind, kinds_dev, seed, arena0, step,
+                                                                       reinterpret_cast<int2 *>(actions_dev), nt);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_random_spawn(int64_t n_arenas, int n_ships, int width, int height, uint64_t seed, int64_t arena0,
+                                uint32_t episode, int32_t *spawn_dev, void *stream) {
+    if (!spawn_dev || n_arenas <= 0 || n_ships < 1) { ofb_set_error("ofb_random_spawn: bad argument"); return OFB_E_ARG; }
+    const long long nt = n_arenas * n_ships;
+    k_random_spawn<<<nblocks(nt, 256), 256, 0, (cudaStream_t)stream>>>(n_ships, width, height, seed, arena0, episode,
+                                                                        reinterpret_cast<int2 *>(spawn_dev), nt);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_state_export(const ofb_arenas *h, const ofb_state_view *view, void *stream) {
+    if (!h || !view) { ofb_set_error("ofb_state_export: null argument"); return OFB_E_ARG; }
+    k_xfer<false><<<(unsigned)h->n_arenas, 128, 0, (cudaStream_t)stream>>>(h->state, h->lay, *view, h->n_arenas);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_state_import(ofb_arenas *h, const ofb_state_view *view, void *stream) {
+    if (!h || !view) { ofb_set_error("ofb_state_import: null argument"); return OFB_E_ARG; }
+    k_xfer<true><<<(unsigned)h->n_arenas, 128, 0, (cudaStream_t)stream>>>(h->state, h->lay, *view, h->n_arenas);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}

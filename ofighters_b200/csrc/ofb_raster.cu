@@ -1,0 +1,147 @@
+// K2 -- observation raster for sm_100a (compiled with -fmad=false).
+//
+// Restates Observation.analyse_battleground (lib/observation.py:79-95): ship_map gets a radius-8
+// disk per playable ship, laser_map a radius-2 disk per laser in the list (just-destroyed and
+// off-map ones included), both indexed [row = y, col = x]; the disk is skimage.draw.disk as
+// called by Circle.binary_draw (lib/form.py:222-228):
+//     ul = ceil(c - R), lr = floor(c + R) clipped to the map, sc = c - ul,
+//     pixel (i, j) of the box set iff ((i - sc_r)/R)^2 + ((j - sc_c)/R)^2 < 1   (fp64, strict).
+// R is 8 or 2, so the divisions are exact scalings and the test is dr*dr + dc*dc < R*R with
+// dr = fl(i - fl(c - ul)).  Ship centres are integers -> the same test in int32.
+//
+// One CTA per arena.  Both bitmaps (W*H/8 bytes each) are composed in shared memory with
+// atomicOr, then leave the SM either as one TMA bulk store (OFB_MAP_BITS, 40 000 B / arena) or
+// expanded to the dense NHWC bf16 / u8 tensor Keras' predict() takes (qlearnIA_V2.py:208).
+#include <cuda_bf16.h>
+#include "ofb_common.cuh"
+
+__device__ __forceinline__ void set_bit_range(uint32_t *bits, unsigned b0, unsigned b1) {
+    const unsigned w0 = b0 >> 5, w1 = b1 >> 5;
+    const uint32_t lo = ~0u << (b0 & 31u), hi = (2u << (b1 & 31u)) - 1u;
+    if (w0 == w1) atomicOr(&bits[w0], lo & hi);
+    else {
+        atomicOr(&bits[w0], lo);
+        for (unsigned w = w0 + 1; w < w1; w++) atomicOr(&bits[w], ~0u);
+        atomicOr(&bits[w1], hi);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_raster(const char *__restrict__ state, const ArenaLayout lay, void *__restrict__ out, int format,
+         long long n_arenas) {
+    extern __shared__ __align__(128) uint32_t bits[];      // [2][words]
+    const int W = lay.W, H = lay.H;
+    const int words = (W * H) >> 5;
+    const long long a = blockIdx.x;
+    const char *base = state + a * (long long)lay.stride;
+    const int *hdr = reinterpret_cast<const int *>(base);
+    const int *ship = reinterpret_cast<const int *>(base + lay.off_ship);
+    const double *lx = reinterpret_cast<const double *>(base + lay.off_lx);
+    const double *ly = reinterpret_cast<const double *>(base + lay.off_ly);
+
+    const int n = hdr[HDR_NLASERS];
+    {
+        uint4 *b4 = reinterpret_cast<uint4 *>(bits);
+        for (int i = threadIdx.x; i < (2 * words) / 4; i += blockDim.x) b4[i] = make_uint4(0, 0, 0, 0);
+    }
+    __syncthreads();
+
+    // ships: one thread per (ship, row)
+    const int rows = 2 * OFB_R_SHIP - 1;
+    for (int t = threadIdx.x; t < lay.S * rows; t += blockDim.x) {
+        const int i = t / rows, dr = t % rows - (OFB_R_SHIP - 1);
+        if (!(ship[SF_FLAGS * lay.SP + i] & 1)) continue;
+        const int cx = ship[SF_X * lay.SP + i], y = ship[SF_Y * lay.SP + i] + dr;
+        if (y < 0 || y >= H) continue;
+        int hw = -1;
+        for (int dc = 0; dc < OFB_R_SHIP; dc++)
+            if (dr * dr + dc * dc < OFB_R_SHIP * OFB_R_SHIP) hw = dc;
+        const int c0 = max(0, cx - hw), c1 = min(W - 1, cx + hw);
+        if (hw >= 0 && c0 <= c1) set_bit_range(bits, (unsigned)(y * W + c0), (unsigned)(y * W + c1));
+    }
+    // lasers: one thread per laser, <= 5x5 candidate pixels in fp64
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double cx = lx[k], cy = ly[k], R = (double)OFB_R_LASER;
+        long long ulr = (long long)ceil(__dsub_rn(cy, R)), ulc = (long long)ceil(__dsub_rn(cx, R));
+        long long lrr = (long long)floor(__dadd_rn(cy, R)), lrc = (long long)floor(__dadd_rn(cx, R));
+        ulr = ulr < 0 ? 0 : ulr;
+        ulc = ulc < 0 ? 0 : ulc;
+        lrr = lrr > H - 1 ? H - 1 : lrr;
+        lrc = lrc > W - 1 ? W - 1 : lrc;
+        const double scr = __dsub_rn(cy, (double)ulr), scc = __dsub_rn(cx, (double)ulc);
+        for (long long i = 0; i <= lrr - ulr; i++) {
+            const double dr = __dsub_rn((double)i, scr);
+            const double dr2 = __dmul_rn(dr, dr);
+            for (long long j = 0; j <= lrc - ulc; j++) {
+                const double dc = __dsub_rn((double)j, scc);
+                if (__dadd_rn(dr2, __dmul_rn(dc, dc)) < R * R) {
+                    const unsigned b = (unsigned)((ulr + i) * W + (ulc + j));
+                    atomicOr(&bits[words + (b >> 5)], 1u << (b & 31u));
+                }
+            }
+        }
+    }
+
+    if (format == OFB_MAP_BITS) {
+        // generic-proxy writes -> visible to the async proxy, then one TMA bulk store per arena
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned bytes = (unsigned)(2 * words * 4);
+            char *dst = reinterpret_cast<char *>(out) + a * (long long)bytes;
+            const unsigned src = (unsigned)__cvta_generic_to_shared(bits);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        return;
+    }
+    __syncthreads();
+    const uint32_t *sm = bits, *lm = bits + words;
+    if (format == OFB_MAP_BF16) {
+        // 4 pixels x 2 channels x bf16 = 16 B per store; bf16(1.0) = 0x3F80
+        uint4 *o = reinterpret_cast<uint4 *>(out) + a * (long long)(W * H / 4);
+        for (int q = threadIdx.x; q < W * H / 4; q += blockDim.x) {
+            const unsigned p = (unsigned)q * 4u;
+            const uint32_t s4 = (sm[p >> 5] >> (p & 31u)) & 0xfu, l4 = (lm[p >> 5] >> (p & 31u)) & 0xfu;
+            uint4 v;
+            v.x = ((s4 & 1u) ? 0x3F80u : 0u) | ((l4 & 1u) ? 0x3F800000u : 0u);
+            v.y = ((s4 & 2u) ? 0x3F80u : 0u) | ((l4 & 2u) ? 0x3F800000u : 0u);
+            v.z = ((s4 & 4u) ? 0x3F80u : 0u) | ((l4 & 4u) ? 0x3F800000u : 0u);
+            v.w = ((s4 & 8u) ? 0x3F80u : 0u) | ((l4 & 8u) ? 0x3F800000u : 0u);
+            __stcs(&o[q], v);
+        }
+    } else {
+        // 8 pixels x 2 channels x u8 = 16 B per store
+        uint4 *o = reinterpret_cast<uint4 *>(out) + a * (long long)(W * H / 8);
+        for (int q = threadIdx.x; q < W * H / 8; q += blockDim.x) {
+            const unsigned p = (unsigned)q * 8u;
+            const uint32_t s8 = (sm[p >> 5] >> (p & 31u)) & 0xffu, l8 = (lm[p >> 5] >> (p & 31u)) & 0xffu;
+            uint32_t r[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t sa = (s8 >> (2 * j)) & 1u, la = (l8 >> (2 * j)) & 1u;
+                const uint32_t sb = (s8 >> (2 * j + 1)) & 1u, lb = (l8 >> (2 * j + 1)) & 1u;
+                r[j] = sa | (la << 8) | (sb << 16) | (lb << 24);
+            }
+            __stcs(&o[q], make_uint4(r[0], r[1], r[2], r[3]));
+        }
+    }
+}
+
+extern "C" int ofb_raster(const ofb_arenas *h, void *out_dev, int format, void *stream) {
+    if (!h || !out_dev || format < OFB_MAP_BITS || format > OFB_MAP_U8) {
+        ofb_set_error("ofb_raster: bad argument");
+        return OFB_E_ARG;
+    }
+    const size_t smem = (size_t)(h->lay.W * h->lay.H / 32) * 2 * sizeof(uint32_t);
+    static thread_local size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    k_raster<<<(unsigned)h->n_arenas, 256, smem, (cudaStream_t)stream>>>(h->state, h->lay, out_dev, format, h->n_arenas);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}

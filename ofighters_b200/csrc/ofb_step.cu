@@ -1,0 +1,314 @@
+// K1 -- fused arena step for sm_100a (compiled with -fmad=false: every fp64 op is an IEEE rn op,
+// which is what makes laser positions / hit tests / thrust truncation bit-identical to CPython).
+//
+// Restates Battleground.generate_frame + Agent.step's score fold + the Tk controller's laser
+// pruning (reference: lib/battleground.py:153-160, lib/laser.py:36-62, lib/ship.py:127-230,303-339,
+// agents/agent.py:66-74, lib/ofighters.py:704-707; rules A1-A4/A7 of SURVEY.md Appendix A).
+//
+// Mapping: one LPA-lane tile (LPA = 8/16/32 >= ships per arena) steps one arena, 32/LPA arenas per
+// warp.  In the laser phase a lane owns a laser slot; in the ship phase lane i owns ship i.  The
+// reference's sequential semantics are recovered with ballots:
+//   * lasers are kept as a dense list in append order, so "lowest lane of the lowest chunk" ==
+//     "first laser in list order": a ship alive at frame start dies to the first colliding laser,
+//     and later lasers pass through it (laser.py:52-62);
+//   * ship i's shoot-rewards read ships j<i after their thrust and j>i before it (ship.py:158-177
+//     inside the loop of battleground.py:159-160).
+#include "ofb_common.cuh"
+
+#define FULL 0xffffffffu
+
+// largest double whose correctly rounded sqrt is <= 10.0 (collide: distance <= r_laser + r_ship)
+#define D2_HIT_MAX 0x1.9000000000001p+6
+
+// ---- enemy_on_trajectory (lib/ship.py:179-210) ------------------------------------------------
+// Reference formula, evaluated with the device's fp64 libm.  Only reached for geometrically
+// borderline pairs (see on_trajectory below); counted in hdr[HDR_NEARTIES].
+__device__ __noinline__ bool on_trajectory_formula(int ux, int uy, int vx, int vy) {
+    const double PI = 3.141592653589793, TWO_PI = 6.283185307179586;
+    double shooting = atan2((double)uy, (double)ux) + PI;
+    if (shooting == 0.0) return false;
+    double target = atan2((double)vy, (double)vx) + PI;
+    if (target == 0.0) return false;
+    long long vv = (long long)vx * vx + (long long)vy * vy;
+    double d = __dsqrt_rn((double)vv);
+    double ang = (d == 0.0) ? TWO_PI : atan(__ddiv_rn(8.0, d));
+    double s1 = target + ang, s2 = target - ang;
+    double sup = fmod(s1, TWO_PI);              // s1 >= 0
+    double inf = fmod(s2, TWO_PI);
+    if (inf != 0.0) { if (inf < 0.0) inf += TWO_PI; } else inf = 0.0;   // CPython float_rem
+    return inf <= shooting && shooting <= sup;
+}
+
+// Exact integer form of the same predicate away from its decision boundaries:
+//   touch  <=>  angle(u, v) <= atan(8/|v|)   and the cone [t-a, t+a] does not straddle 0/2pi
+// with u = pointing - me, v = enemy - me.  cos^2 of both sides are rationals of the integer
+// coordinates, so the comparison is exact in int64; pairs within 1e-10 rad of a boundary (where
+// the reference's outcome is decided by libm rounding) fall back to the formula.
+__device__ __forceinline__ bool on_trajectory(int ux, int uy, int vx, int vy, int &near_ties) {
+    long long uu = (long long)ux * ux + (long long)uy * uy;
+    long long vv = (long long)vx * vx + (long long)vy * vy;
+    // enemy on my own pixel: target = pi, cone half-angle = 2*pi, sup = inf = pi exactly in fp64
+    // (3*pi is representable) -> touch iff the shot angle is exactly pi, i.e. along +x.
+    if (vv == 0) return uy == 0 && ux > 0;
+    long long dot = (long long)ux * vx + (long long)uy * vy;
+    if (dot <= 0) return false;                       // angle >= pi/2 > atan(8/d)
+    long long diff = dot * dot * (vv + 64) - uu * vv * vv;
+    double scale = (double)uu * (double)vv * (double)(vv + 64);
+    bool near = fabs((double)diff) <= 1e-10 * scale;
+    if (!near && diff < 0) return false;
+    if (!near) {
+        if (vx >= 0) return true;                     // cone axis >= pi/2 away from the 0/2pi seam
+        long long lw = (long long)vx * vx * (vv + 64) - vv * vv;
+        double sw = (double)vv * (double)(vv + 64);
+        if (fabs((double)lw) > 1e-10 * sw) return lw <= 0;
+    }
+    near_ties++;
+    return on_trajectory_formula(ux, uy, vx, vy);
+}
+
+template <int LPA>
+__global__ void __launch_bounds__(128)
+k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions,
+       float4 *__restrict__ obs_out, long long n_arenas) {
+    constexpr int APW = 32 / LPA;
+    constexpr unsigned GM = (LPA == 32) ? 0xffffffffu : ((1u << LPA) - 1u);
+    const int lane = threadIdx.x & 31;
+    const int g = lane / LPA, gl = lane % LPA;
+    const unsigned gshift = g * LPA;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long arena = warp_global * APW + g;
+    const bool ok = arena < n_arenas;
+    const int S = lay.S, SP = lay.SP, L = lay.L;
+    char *base = state + (ok ? arena : 0) * (long long)lay.stride;
+    int *hdr = reinterpret_cast<int *>(base);
+    int *ship = reinterpret_cast<int *>(base + lay.off_ship);
+    double *lx = reinterpret_cast<double *>(base + lay.off_lx);
+    double *ly = reinterpret_cast<double *>(base + lay.off_ly);
+    double *ldx = reinterpret_cast<double *>(base + lay.off_ldx);
+    double *ldy = reinterpret_cast<double *>(base + lay.off_ldy);
+    unsigned *lmeta = reinterpret_cast<unsigned *>(base + lay.off_lmeta);
+
+    // ---- load header (tile lanes 0..7) and ship state (tile lane i = ship i) ----
+    int hv = (ok && gl < 8) ? hdr[gl] : 0;
+    int time = __shfl_sync(FULL, hv, gshift + HDR_TIME);
+    int n = __shfl_sync(FULL, hv, gshift + HDR_NLASERS);
+    int kills = __shfl_sync(FULL, hv, gshift + HDR_KILLS);
+    int deaths = __shfl_sync(FULL, hv, gshift + HDR_DEATHS);
+    int shots = __shfl_sync(FULL, hv, gshift + HDR_SHOTS);
+    int overflow = __shfl_sync(FULL, hv, gshift + HDR_OVERFLOW);
+    int near_ties = 0;
+
+    const bool is_ship = ok && gl < S;
+    int sx = 0, sy = 0, spx = 0, spy = 0, rew = 0, score = 0, steps = 0, flags = 0;
+    int2 act = make_int2(0, 0);
+    if (is_ship) {
+        sx = ship[SF_X * SP + gl];
+        sy = ship[SF_Y * SP + gl];
+        spx = ship[SF_PX * SP + gl];
+        spy = ship[SF_PY * SP + gl];
+        rew = ship[SF_REWARD * SP + gl];
+        score = ship[SF_SCORE * SP + gl];
+        steps = ship[SF_STEPS * SP + gl];
+        flags = ship[SF_FLAGS * SP + gl];
+        act = actions[arena * S + gl];
+    }
+    bool alive = (flags & 1) != 0;
+    int hull = flags >> 8;
+
+    // ---- A1: score fold, dead ships included (agents/agent.py:66-74, lib/ship.py:260-262) ----
+    steps += 1;
+    score += rew;
+    rew = 0;
+    // ---- A2 ----
+    time += 1;
+
+    // ---- A3 + A7: lasers in list order; entries destroyed last frame are dropped on load ----
+    unsigned alive_bits = (__ballot_sync(FULL, alive) >> gshift) & GM;
+    int iters = (n + LPA - 1) / LPA;
+    iters = __reduce_max_sync(FULL, iters);
+    int w = 0;                                           // compaction write cursor
+    for (int it = 0; it < iters; it++) {
+        const int k = it * LPA + gl;
+        bool live = ok && k < n;
+        unsigned meta = 0;
+        double x = 0.0, y = 0.0, dx = 0.0, dy = 0.0;
+        if (live) {
+            meta = lmeta[k];
+            live = !(meta & 0x100u);
+        }
+        if (live) {
+            x = lx[k]; y = ly[k]; dx = ldx[k]; dy = ldy[k];
+            x = __dadd_rn(x, dx);                        // lib/laser.py:46-47
+            y = __dadd_rn(y, dy);
+        }
+        bool hit_any = false;
+        for (int s = 0; s < S; s++) {
+            const double ex = __dsub_rn(x, (double)__shfl_sync(FULL, sx, gshift + s));
+            const double ey = __dsub_rn(y, (double)__shfl_sync(FULL, sy, gshift + s));
+            const double d2 = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
+            const bool hit = live && ((alive_bits >> s) & 1u) && d2 <= D2_HIT_MAX;
+            const unsigned b = (__ballot_sync(FULL, hit) >> gshift) & GM;
+            const int killer = b ? (__ffs(b) - 1) : 0;
+            if (lay.r_kill != 0) {
+                const int own = __shfl_sync(FULL, (int)(meta & 0xffu), gshift + killer);
+                if (b && gl == own) rew += lay.r_kill;   // lib/laser.py:57
+            }
+            if (b) {
+                if (gl == killer) hit_any = true;
+                alive_bits &= ~(1u << s);
+                kills += 1;                              // event (1, t)
+                deaths += 1;                             // event (10, t): hull 1, never restored
+                if (gl == s) {                           // lib/ship.py:127-131,225-230
+                    hull -= 1;
+                    alive = false;
+                    rew += lay.r_death;
+                }
+            }
+        }
+        const bool destroyed = live && (hit_any || x < 0.0 || y < 0.0 || x >= (double)lay.W || y >= (double)lay.H);
+        const unsigned lv = (__ballot_sync(FULL, live) >> gshift) & GM;
+        const int pos = w + __popc(lv & ((1u << gl) - 1u));
+        if (live) {
+            lx[pos] = x;
+            ly[pos] = y;
+            lmeta[pos] = (meta & 0xffu) | (destroyed ? 0x100u : 0u);
+            if (pos != k) { ldx[pos] = dx; ldy[pos] = dy; }
+        }
+        w += __popc(lv);
+    }
+
+    // ---- A4: ships in index order (lib/ship.py:303-339) ----
+    const int old_x = sx, old_y = sy;
+    bool shooter = false;
+    double nlx = 0.0, nly = 0.0, ndx = 0.0, ndy = 0.0;
+    if (is_ship && alive) {
+        const int a_shoot = (short)(act.x & 0xffff), a_thrust = (short)(act.x >> 16);
+        spx = (short)(act.y & 0xffff);
+        spy = (short)(act.y >> 16);
+        if (a_thrust) {                                  // lib/ship.py:213-222
+            const int dX = spx - sx, dY = spy - sy;
+            const int d2 = dX * dX + dY * dY;
+            if (d2 != 0) {
+                const double dist = __dsqrt_rn((double)d2);
+                const double mx = __ddiv_rn((double)(dX * OFB_SHIP_SPEED), dist);
+                const double my = __ddiv_rn((double)(dY * OFB_SHIP_SPEED), dist);
+                int nx = (int)__dadd_rn((double)sx, mx);
+                int ny = (int)__dadd_rn((double)sy, my);
+                sx = min(lay.W - 1, max(0, nx));
+                sy = min(lay.H - 1, max(0, ny));
+            }
+        }
+        if (a_shoot) {                                   // lib/ship.py:134-156, lib/form.py:159-188
+            const int dX = spx - sx, dY = spy - sy;
+            const int d2 = dX * dX + dY * dY;
+            if (d2 != 0) {
+                const double dist = __dsqrt_rn((double)d2);
+                const int in_r = OFB_R_SHIP + OFB_R_LASER;
+                const int px0 = (int)__dadd_rn((double)sx, __ddiv_rn((double)(dX * in_r), dist));
+                const int py0 = (int)__dadd_rn((double)sy, __ddiv_rn((double)(dY * in_r), dist));
+                int fx = px0, fy = py0;
+                if (d2 <= in_r * in_r) { fx = sx; fy = sy; }       // lib/ship.py:147-148
+                const int fX = spx - fx, fY = spy - fy;            // lib/laser.py:39-45
+                const int f2 = fX * fX + fY * fY;
+                if (f2 != 0) {
+                    const double fd = __dsqrt_rn((double)f2);
+                    ndx = __ddiv_rn((double)(fX * OFB_LASER_SPEED), fd);
+                    ndy = __ddiv_rn((double)(fY * OFB_LASER_SPEED), fd);
+                }
+                nlx = (double)px0;
+                nly = (double)py0;
+                shooter = true;
+            }
+        }
+    }
+    // shoot rewards: enemies j<i are seen after their move, j>i before it
+    {
+        const unsigned alive_now = (__ballot_sync(FULL, alive) >> gshift) & GM;
+        bool aimed = false, traj = false;
+        for (int j = 0; j < S; j++) {
+            const int jnx = __shfl_sync(FULL, sx, gshift + j), jny = __shfl_sync(FULL, sy, gshift + j);
+            const int jox = __shfl_sync(FULL, old_x, gshift + j), joy = __shfl_sync(FULL, old_y, gshift + j);
+            if (shooter && j != gl && ((alive_now >> j) & 1u)) {
+                const int ox = j < gl ? jnx : jox, oy = j < gl ? jny : joy;
+                const int ax = ox - spx, ay = oy - spy;
+                if (ax * ax + ay * ay <= OFB_R_SHIP * OFB_R_SHIP) aimed = true;     // lib/ship.py:165-169
+                if (!traj && on_trajectory(spx - sx, spy - sy, ox - sx, oy - sy, near_ties)) traj = true;
+            }
+        }
+        if (aimed) rew += lay.r_aim;
+        if (traj) rew += lay.r_traj;
+    }
+    // append the new lasers in ship order (lib/ship.py:151)
+    {
+        const unsigned sh = (__ballot_sync(FULL, shooter) >> gshift) & GM;
+        const int slot = w + __popc(sh & ((1u << gl) - 1u));
+        if (shooter && slot < L) {
+            lx[slot] = nlx; ly[slot] = nly; ldx[slot] = ndx; ldy[slot] = ndy;
+            lmeta[slot] = (unsigned)gl;
+        }
+        const int want = w + __popc(sh);
+        shots += __popc(sh);
+        overflow += max(0, want - L);
+        n = min(want, L);
+    }
+    int nt = near_ties;
+#pragma unroll
+    for (int o = LPA / 2; o > 0; o >>= 1) nt += __shfl_xor_sync(FULL, nt, o);
+
+    // ---- store ----
+    if (is_ship) {
+        ship[SF_X * SP + gl] = sx;
+        ship[SF_Y * SP + gl] = sy;
+        ship[SF_PX * SP + gl] = spx;
+        ship[SF_PY * SP + gl] = spy;
+        ship[SF_REWARD * SP + gl] = rew;
+        ship[SF_SCORE * SP + gl] = score;
+        ship[SF_STEPS * SP + gl] = steps;
+        ship[SF_FLAGS * SP + gl] = (alive ? 1 : 0) | (hull << 8);
+        if (obs_out) {                                   // lib/observation.py:113-123
+            float4 *o = obs_out + (arena * S + gl) * 2;
+            o[0] = make_float4((float)rew, 1.0f, (float)spx, (float)spy);
+            o[1] = make_float4((float)lay.W, (float)lay.H, (float)sx, (float)sy);
+        }
+    }
+    if (ok && gl == 0) {
+        int4 *h4 = reinterpret_cast<int4 *>(hdr);
+        h4[0] = make_int4(time, n, kills, deaths);
+        h4[1] = make_int4(shots, overflow, hdr[HDR_EPISODE], hdr[HDR_NEARTIES] + nt);
+    }
+}
+
+static inline int lpa_for(int S) { return S <= 8 ? 8 : (S <= 16 ? 16 : 32); }
+
+extern "C" int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *stream) {
+    if (!h || !actions_dev) { ofb_set_error("ofb_step: null argument"); return OFB_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int lpa = lpa_for(h->lay.S);
+    const int apw = 32 / lpa;
+    const int threads = 128;
+    const long long warps = (h->n_arenas + apw - 1) / apw;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    if (blocks == 0) return OFB_OK;
+    const int2 *act = reinterpret_cast<const int2 *>(actions_dev);
+    float4 *obs = reinterpret_cast<float4 *>(obs_out_dev);
+    if (lpa == 8) k_step<8><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas);
+    else if (lpa == 16) k_step<16><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas);
+    else k_step<32><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+// Host-buffer form of ofb_step: the drop-in call for a host-side bot loop (Battleground.frame with
+// Python bots).  actions_host / obs_host should be pinned; everything is asynchronous on `stream`.
+extern "C" int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream) {
+    if (!h || !actions_host) { ofb_set_error("ofb_step_host: null argument"); return OFB_E_ARG; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_ship = (size_t)h->n_arenas * h->lay.S;
+    OFB_CUDA_CHECK(cudaMemcpyAsync(h->stage_actions, actions_host, n_ship * 4 * sizeof(int16_t),
+                                   cudaMemcpyHostToDevice, st));
+    int rc = ofb_step(h, h->stage_actions, obs_host ? h->stage_obs : nullptr, st);
+    if (rc != OFB_OK) return rc;
+    if (obs_host)
+        OFB_CUDA_CHECK(cudaMemcpyAsync(obs_host, h->stage_obs, n_ship * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    return OFB_OK;
+}
