@@ -50,7 +50,7 @@ def test_cuda_path_matches_c_restatement_on_device_bots(N, S, kind, T):
     seed = 0xC0FFEE + N
     c0 = ArenasC(np.zeros((N, S, 2), np.int32))
     spawn = c0.random_spawn(seed, 0, arena0=1000)
-    g = GpuEngine(spawn, seed=seed, arena0=1000)
+    g = GpuEngine(spawn, lcap=64 * S if kind in ("turret", "shoot") else 0, seed=seed, arena0=1000)
     bg = g.bg
     c = ArenasC(spawn, lcap=bg.laser_cap)
     # device-side spawn draws must equal the oracle's
