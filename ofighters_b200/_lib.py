@@ -30,6 +30,22 @@ class OfbStateView(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in STATE_VIEW_FIELDS]
 
 
+class OfbConvWeights(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("kernel", "bias", "gamma", "beta", "mean", "var")]
+
+
+class OfbDenseWeights(C.Structure):
+    _fields_ = [("kernel", C.c_void_p), ("bias", C.c_void_p)]
+
+
+class OfbPolicyWeights(C.Structure):
+    _fields_ = [("conv", OfbConvWeights * 4), ("dense1", OfbDenseWeights), ("dense2", OfbDenseWeights),
+                ("output1", OfbDenseWeights), ("updense1", OfbDenseWeights), ("upconv", OfbConvWeights * 4)]
+
+
+ENGINE_TENSOR, ENGINE_CUDA_CORE = 0, 1
+
+
 class OfbError(RuntimeError):
     pass
 
@@ -69,6 +85,16 @@ def load():
     lib.ofb_random_spawn.argtypes = [i64, i32, i32, i32, u64, i64, u32, vp, vp]
     lib.ofb_state_export.argtypes = [vp, C.POINTER(OfbStateView), vp]
     lib.ofb_state_import.argtypes = [vp, C.POINTER(OfbStateView), vp]
+    lib.ofb_policy_create.argtypes = [C.POINTER(OfbPolicyWeights), i32, i32, C.POINTER(vp)]
+    lib.ofb_policy_destroy.argtypes = [vp]
+    lib.ofb_policy_set_engine.argtypes = [vp, i32]
+    lib.ofb_policy_forward.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
+    lib.ofb_policy_write_actions.argtypes = [vp, vp, i64, i32, vp, i32, C.c_float, u64, i64, u32, vp, vp]
+    lib.ofb_policy_pack_image.argtypes = [vp, i32, i64, vp, vp]
+    lib.ofb_policy_debug_tap.argtypes = [vp, i32, i64, vp, vp]
+    for name in ("ofb_policy_create", "ofb_policy_destroy", "ofb_policy_set_engine", "ofb_policy_forward",
+                 "ofb_policy_write_actions", "ofb_policy_pack_image", "ofb_policy_debug_tap"):
+        getattr(lib, name).restype = i32
     for name in ("ofb_create", "ofb_destroy", "ofb_laser_cap", "ofb_reset", "ofb_step", "ofb_step_host", "ofb_obs_vec", "ofb_raster",
                  "ofb_bot_actions", "ofb_random_spawn", "ofb_state_export", "ofb_state_import"):
         getattr(lib, name).restype = i32

@@ -23,11 +23,14 @@ UNITS = [
     ("ofb_arena.cu", ["-fmad=false"]),
     ("ofb_step.cu", ["-fmad=false"]),
     ("ofb_raster.cu", ["-fmad=false"]),
+    ("ofb_policy.cu", []),
+    ("ofb_policy_tc.cu", []),
 ]
 
 
 def _deps():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "ofb.h")]
+    inc = os.path.join(HERE, "..", "include")
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, f) for f in os.listdir(inc)]
 
 
 def build(force=False, verbose=False):

@@ -1,0 +1,651 @@
+// Policy forward of the bi-head pointer model (agents/qlearnIA_V2.py:123-235): handle, weight
+// folding, orchestration, and the CUDA-core engine.  The tensor-core (tcgen05) kernels of the
+// product path live in ofb_policy_tc.cu; both engines share ofb_policy_dev.cuh.
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+#include "ofb_common.cuh"
+#include "ofb_policy_dev.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// host-side folding (BN into conv, bilinear x2 into 4 output phases) and upload
+// ------------------------------------------------------------------------------------------------
+static void fold_conv(const ofb_conv_weights &c, int cin, int cout, std::vector<float> &w, std::vector<float> &b) {
+    w.assign((size_t)9 * cin * cout, 0.f);
+    b.assign(cout, 0.f);
+    for (int co = 0; co < cout; co++) {
+        float s = 1.f, sh = c.bias ? c.bias[co] : 0.f;
+        if (c.gamma) {                                        // BatchNormalization, eps = 1e-3 (Keras default)
+            s = c.gamma[co] / std::sqrt(c.var[co] + 1e-3f);
+            sh = (sh - c.mean[co]) * s + c.beta[co];
+        }
+        b[co] = sh;
+        for (int t = 0; t < 9; t++)
+            for (int ci = 0; ci < cin; ci++) w[((size_t)t * cin + ci) * cout + co] = c.kernel[((size_t)t * cin + ci) * cout + co] * s;
+    }
+}
+
+// [9][cin][cout] fp32 -> UMMA B-operand image [10 taps][npad][8 cin] bf16 (K-major rows of 16 B)
+static std::vector<__nv_bfloat16> pack_taps(const std::vector<float> &w, int cin, int cout, int npad) {
+    std::vector<__nv_bfloat16> o((size_t)POL_TAPS * npad * 8, __float2bfloat16(0.f));
+    for (int t = 0; t < 9; t++)
+        for (int ci = 0; ci < cin; ci++)
+            for (int co = 0; co < cout; co++) o[((size_t)t * npad + co) * 8 + ci] = __float2bfloat16(w[((size_t)t * cin + ci) * cout + co]);
+    return o;
+}
+
+// coefficient of L[i+u-1] in U[2i + a + d - 1]  (TF2 half-pixel bilinear x2), a = phase, d = conv tap
+static const float PHASE_C[2][3][3] = {
+    {{0.75f, 0.25f, 0.f}, {0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}},
+    {{0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}, {0.f, 0.25f, 0.75f}}};
+
+// [9][cin][cout] -> phase-folded [10][npad][8]: n = (a*2+b)*cout + co, low-res tap (u, v)
+static std::vector<__nv_bfloat16> pack_phase(const std::vector<float> &w, int cin, int cout, int npad) {
+    std::vector<__nv_bfloat16> o((size_t)POL_TAPS * npad * 8, __float2bfloat16(0.f));
+    for (int a = 0; a < 2; a++)
+        for (int b = 0; b < 2; b++)
+            for (int u = 0; u < 3; u++)
+                for (int v = 0; v < 3; v++)
+                    for (int ci = 0; ci < cin; ci++)
+                        for (int co = 0; co < cout; co++) {
+                            double s = 0.0;
+                            for (int dy = 0; dy < 3; dy++)
+                                for (int dx = 0; dx < 3; dx++)
+                                    s += (double)w[((size_t)(dy * 3 + dx) * cin + ci) * cout + co] * PHASE_C[a][dy][u] * PHASE_C[b][dx][v];
+                            o[((size_t)(u * 3 + v) * npad + (a * 2 + b) * cout + co) * 8 + ci] = __float2bfloat16((float)s);
+                        }
+    return o;
+}
+
+struct Uploader {
+    std::vector<char> host;
+    std::vector<std::pair<void **, size_t>> fix;
+    template <class T> void add(T **dst, const T *src, size_t n) {
+        size_t off = (host.size() + 255) & ~(size_t)255;
+        host.resize(off + n * sizeof(T));
+        memcpy(host.data() + off, src, n * sizeof(T));
+        fix.push_back({reinterpret_cast<void **>(dst), off});
+    }
+    template <class T> void add(T **dst, const std::vector<T> &v) { add(dst, v.data(), v.size()); }
+};
+
+extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int max_ships, ofb_policy **out) {
+    if (!wh || !out) { ofb_set_error("ofb_policy_create: null argument"); return OFB_E_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        ofb_set_error("ofb_policy_create: no CUDA device (libofb has no CPU fallback)");
+        return OFB_E_CUDA;
+    }
+    OFB_CUDA_CHECK(cudaSetDevice(device));
+    if (max_ships <= 0) max_ships = 1024;
+    ofb_policy *p = new (std::nothrow) ofb_policy();
+    if (!p) return OFB_E_NOMEM;
+    memset(p, 0, sizeof(*p));
+    p->device = device;
+    p->max_ships = max_ships;
+    p->engine = OFB_ENGINE_TENSOR;
+
+    Uploader up;
+    PolicyDev &d = p->w;
+    std::vector<float> w, b;
+    // trunk
+    fold_conv(wh->conv[0], 2, 8, w, b);
+    up.add(&d.c1_w, w); up.add(&d.c1_b, b);
+    for (int l = 0; l < 3; l++) {
+        fold_conv(wh->conv[l + 1], 8, 8, w, b);
+        b.resize(16, 0.f);
+        up.add(&d.cw[l], pack_taps(w, 8, 8, 16));
+        up.add(&d.cb[l], b);
+    }
+    // dense1: rows 0..7 = vector slice (fp32), rows 8..5007 = flat slice (bf16)
+    {
+        const float *k = wh->dense1.kernel;
+        up.add(&d.d1_wv, k, 8 * 100);
+        std::vector<__nv_bfloat16> wf((size_t)POL_FLAT * 100), wt((size_t)128 * POL_FLAT_PITCH, __float2bfloat16(0.f));
+        for (int i = 0; i < POL_FLAT; i++)
+            for (int j = 0; j < 100; j++) {
+                wf[(size_t)i * 100 + j] = __float2bfloat16(k[(size_t)(8 + i) * 100 + j]);
+                wt[(size_t)j * POL_FLAT_PITCH + i] = wf[(size_t)i * 100 + j];
+            }
+        up.add(&d.d1_wf, wf); up.add(&d.d1_wt, wt);
+        up.add(&d.d1_b, wh->dense1.bias, 100);
+    }
+    up.add(&d.d2_w, wh->dense2.kernel, 100 * 50); up.add(&d.d2_b, wh->dense2.bias, 50);
+    up.add(&d.o1_w, wh->output1.kernel, 50 * 2); up.add(&d.o1_b, wh->output1.bias, 2);
+    up.add(&d.ud_w, wh->updense1.kernel, 100 * 625); up.add(&d.ud_b, wh->updense1.bias, 625);
+    fold_conv(wh->upconv[0], 1, 2, w, b); up.add(&d.u1_w, w); up.add(&d.u1_b, b);
+    fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b);
+    fold_conv(wh->upconv[2], 4, 8, w, b);
+    up.add(&d.u3_w, w); up.add(&d.u3_b, b);
+    up.add(&d.u3_pw, pack_phase(w, 4, 8, 32));
+    { std::vector<float> pb(32); for (int n = 0; n < 32; n++) pb[n] = b[n % 8]; up.add(&d.u3_pb, pb); }
+    fold_conv(wh->upconv[3], 8, 1, w, b);
+    up.add(&d.u4_w, w); up.add(&d.u4_b, b);
+    up.add(&d.u4_pw, pack_phase(w, 8, 1, 16));
+    { std::vector<float> pb(16, 0.f); for (int n = 0; n < 4; n++) pb[n] = b[0]; up.add(&d.u4_pb, pb); }
+
+    cudaError_t e = cudaMalloc(&p->arena_blob, up.host.size());
+    if (e == cudaSuccess) e = cudaMemcpy(p->arena_blob, up.host.data(), up.host.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        ofb_set_error("ofb_policy_create: weight upload failed: %s", cudaGetErrorString(e));
+        cudaFree(p->arena_blob); delete p; return OFB_E_CUDA;
+    }
+    for (auto &f : up.fix) *f.first = static_cast<char *>(p->arena_blob) + f.second;
+
+    // workspace
+    const size_t C = (size_t)max_ships;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_p1 = take(C * 200 * 200 * 8 * 2), o_p2 = take(C * 100 * 100 * 8 * 2), o_p3 = take(C * 50 * 50 * 8 * 2);
+    const size_t o_fl = take(C * POL_FLAT_PITCH * 2), o_hf = take(C * 100 * 4);
+    const size_t o_u2 = take(C * 100 * 100 * 8 * 2), o_u3 = take(C * 200 * 200 * 8 * 2);
+    const size_t o_av = take(C * AMAX_PARTS * 4), o_ai = take(C * AMAX_PARTS * 4);
+    e = cudaMalloc(&p->work_blob, off);
+    if (e != cudaSuccess) {
+        ofb_set_error("ofb_policy_create: cudaMalloc(workspace %zu bytes for %d ships) failed: %s", off, max_ships, cudaGetErrorString(e));
+        cudaFree(p->arena_blob); delete p; return OFB_E_NOMEM;
+    }
+    char *wb = static_cast<char *>(p->work_blob);
+    cudaMemset(wb + o_fl, 0, C * POL_FLAT_PITCH * 2);            // K padding of dense1 must read as zero
+    cudaMemset(wb + o_u2, 0, C * 100 * 100 * 8 * 2);             // channels 4..7 of up2 stay zero
+    p->ws.pool1 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p1);
+    p->ws.pool2 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p2);
+    p->ws.pool3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p3);
+    p->ws.flat = reinterpret_cast<__nv_bfloat16 *>(wb + o_fl);
+    p->ws.hflat = reinterpret_cast<float *>(wb + o_hf);
+    p->ws.up2 = reinterpret_cast<__nv_bfloat16 *>(wb + o_u2);
+    p->ws.up3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_u3);
+    p->ws.amax_val = reinterpret_cast<float *>(wb + o_av);
+    p->ws.amax_idx = reinterpret_cast<int *>(wb + o_ai);
+    OFB_CUDA_CHECK(cudaDeviceSynchronize());
+    *out = p;
+    return OFB_OK;
+}
+
+extern "C" int ofb_policy_destroy(ofb_policy *p) {
+    if (!p) return OFB_OK;
+    cudaSetDevice(p->device);
+    cudaFree(p->arena_blob);
+    cudaFree(p->work_blob);
+    delete p;
+    return OFB_OK;
+}
+
+extern "C" int ofb_policy_set_engine(ofb_policy *p, int engine) {
+    if (!p || (engine != OFB_ENGINE_TENSOR && engine != OFB_ENGINE_CUDA_CORE)) {
+        ofb_set_error("ofb_policy_set_engine: bad argument");
+        return OFB_E_ARG;
+    }
+    p->engine = engine;
+    return OFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// CUDA-core engine
+// ------------------------------------------------------------------------------------------------
+// conv1 + BN + ReLU + pool straight from the bit maps: one thread per pooled pixel.
+__global__ void __launch_bounds__(256)
+k_trunk1_cc(const uint32_t *__restrict__ maps, PolicyDev w, __nv_bfloat16 *__restrict__ out) {
+    __shared__ float sw[144], sb[8];
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) sw[i] = w.c1_w[i];
+    if (threadIdx.x < 8) sb[threadIdx.x] = w.c1_b[threadIdx.x];
+    __syncthreads();
+    const int a = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= 200 * 200) return;
+    const int py = p / 200, px = p % 200;
+    const uint32_t *sm = maps + (size_t)a * 2 * POL_WORDS, *lm = sm + POL_WORDS;
+    const uint32_t ps = conv1_patch(sm, py, px), pl = conv1_patch(lm, py, px);
+    float v[8];
+    if ((ps | pl) == 0) {
+#pragma unroll
+        for (int co = 0; co < 8; co++) v[co] = fmaxf(sb[co], 0.f);
+    } else conv1_pool_pixel(ps, pl, sw, sb, v);
+    *reinterpret_cast<uint4 *>(out + ((size_t)a * 40000 + p) * 8) = pack_bf8(v);
+}
+
+// generic 8 -> 8 conv3x3 'same' + bias + ReLU + 2x2 max-pool, NHWC bf16; one thread per pooled pixel
+__global__ void __launch_bounds__(128)
+k_conv_pool_cc(const __nv_bfloat16 *__restrict__ in, const __nv_bfloat16 *__restrict__ wt, const float *__restrict__ bias,
+               __nv_bfloat16 *__restrict__ out, int hin, long long out_item_stride) {
+    __shared__ float sw[9 * 8 * 8];                             // [tap][cout][cin]
+    __shared__ float sb[8];
+    for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) {
+        const int t = i / 64, co = (i / 8) % 8, ci = i % 8;
+        sw[i] = bf2f(wt[((size_t)t * 16 + co) * 8 + ci]);
+    }
+    if (threadIdx.x < 8) sb[threadIdx.x] = bias[threadIdx.x];
+    __syncthreads();
+    const int ho = hin / 2;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= ho * ho) return;
+    const int py = p / ho, px = p % ho;
+    const __nv_bfloat16 *src = in + (size_t)blockIdx.y * hin * hin * 8;
+    float acc[4][8];
+#pragma unroll
+    for (int q = 0; q < 4; q++)
+#pragma unroll
+        for (int co = 0; co < 8; co++) acc[q][co] = sb[co];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int y = 2 * py - 1 + r;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int x = 2 * px - 1 + c;
+            if (y < 0 || y >= hin || x < 0 || x >= hin) continue;
+            float v[8];
+            unpack_bf8(*reinterpret_cast<const uint4 *>(src + ((size_t)y * hin + x) * 8), v);
+#pragma unroll
+            for (int i = 0; i < 2; i++)
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    const int dy = r - i, dx = c - j;
+                    if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
+                    const float *wp = sw + (dy * 3 + dx) * 64;
+#pragma unroll
+                    for (int co = 0; co < 8; co++) {
+                        float s = acc[i * 2 + j][co];
+#pragma unroll
+                        for (int ci = 0; ci < 8; ci++) s += v[ci] * wp[co * 8 + ci];
+                        acc[i * 2 + j][co] = s;
+                    }
+                }
+        }
+    }
+    float o[8];
+#pragma unroll
+    for (int co = 0; co < 8; co++)
+        o[co] = fmaxf(fmaxf(fmaxf(acc[0][co], acc[1][co]), fmaxf(acc[2][co], acc[3][co])), 0.f);
+    *reinterpret_cast<uint4 *>(out + (size_t)blockIdx.y * out_item_stride + (size_t)p * 8) = pack_bf8(o);
+}
+
+// dense1, flat slice: hflat[a][j] = sum_k flat[a][k] * Wf[k][j]   (8 arenas per block)
+__global__ void __launch_bounds__(128)
+k_dense1_cc(const __nv_bfloat16 *__restrict__ flat, const __nv_bfloat16 *__restrict__ wf, float *__restrict__ hflat, int n_items) {
+    constexpr int KT = 1000;
+    __shared__ float sf[8][KT];
+    const int a0 = blockIdx.x * 8, j = threadIdx.x;
+    float acc[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) acc[a] = 0.f;
+    for (int k0 = 0; k0 < POL_FLAT; k0 += KT) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < 8 * KT; i += blockDim.x) {
+            const int a = i / KT, k = i % KT;
+            sf[a][k] = (a0 + a < n_items) ? bf2f(flat[(size_t)(a0 + a) * POL_FLAT_PITCH + k0 + k]) : 0.f;
+        }
+        __syncthreads();
+        if (j < 100) {
+            for (int k = 0; k < KT; k++) {
+                const float wv = bf2f(wf[(size_t)(k0 + k) * 100 + j]);
+#pragma unroll
+                for (int a = 0; a < 8; a++) acc[a] += sf[a][k] * wv;
+            }
+        }
+    }
+    if (j < 100)
+        for (int a = 0; a < 8; a++)
+            if (a0 + a < n_items) hflat[(size_t)(a0 + a) * 100 + j] = acc[a];
+}
+
+// Everything between dense1's flat part and upconv3, per ship, in fp32 on CUDA cores:
+// dense1 (vector slice + bias + ReLU), dense2, output1 (+ argmax), updense1, upconv1, upconv2.
+#define HEADS_SMEM_FLOATS (128 + 64 + 640 + 2500 + 5000 + 20000)
+__global__ void __launch_bounds__(256)
+k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, float *__restrict__ act_out,
+        int *__restrict__ iaction_out, __nv_bfloat16 *__restrict__ up2_out) {
+    extern __shared__ float sm[];
+    float *h = sm, *d2 = h + 128, *u = d2 + 64, *U1 = u + 640, *a1 = U1 + 2500, *U2 = a1 + 5000;
+    const int s = blockIdx.x, arena = s / ships_per_arena, tid = threadIdx.x, nt = blockDim.x;
+    // dense1: [vector(8), flat(5000)] -> 100, ReLU      (qlearnIA_V2.py:154-155)
+    if (tid < 100) {
+        float acc = w.d1_b[tid];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc += vec[(size_t)s * 8 + i] * w.d1_wv[i * 100 + tid];
+        acc += hflat[(size_t)arena * 100 + tid];
+        h[tid] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    // dense2 100 -> 50 ReLU (:158); updense1 100 -> 625 ReLU (:163)
+    for (int j = tid; j < 50 + 625; j += nt) {
+        if (j < 50) {
+            float acc = w.d2_b[j];
+            for (int i = 0; i < 100; i++) acc += h[i] * w.d2_w[i * 50 + j];
+            d2[j] = fmaxf(acc, 0.f);
+        } else {
+            const int q = j - 50;
+            float acc = w.ud_b[q];
+            for (int i = 0; i < 100; i++) acc += h[i] * w.ud_w[i * 625 + q];
+            u[q] = fmaxf(acc, 0.f);
+        }
+    }
+    __syncthreads();
+    // output1 50 -> 2 linear (:160) and its argmax (:218, ties -> lowest index)
+    if (tid == 0) {
+        float a0 = w.o1_b[0], a1v = w.o1_b[1];
+        for (int i = 0; i < 50; i++) { a0 += d2[i] * w.o1_w[i * 2]; a1v += d2[i] * w.o1_w[i * 2 + 1]; }
+        if (act_out) { act_out[(size_t)s * 2] = a0; act_out[(size_t)s * 2 + 1] = a1v; }
+        if (iaction_out) iaction_out[s] = a1v > a0 ? 1 : 0;
+    }
+    // upsampling1: 25x25 -> 50x50 bilinear (:166)
+    for (int p = tid; p < 2500; p += nt) {
+        const int Y = p / 50, X = p % 50;
+        int yl, yh, xl, xh; float wyl, wyh, wxl, wxh;
+        bil_tap(Y, 25, yl, yh, wyl, wyh);
+        bil_tap(X, 25, xl, xh, wxl, wxh);
+        U1[p] = wyl * (wxl * u[yl * 25 + xl] + wxh * u[yl * 25 + xh]) + wyh * (wxl * u[yh * 25 + xl] + wxh * u[yh * 25 + xh]);
+    }
+    __syncthreads();
+    // upconv1 1 -> 2 + BN + ReLU (:167-169)
+    for (int p = tid; p < 2500; p += nt) {
+        const int y = p / 50, x = p % 50;
+        float c0 = w.u1_b[0], c1 = w.u1_b[1];
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+                const int yy = y + dy - 1, xx = x + dx - 1;
+                if (yy < 0 || yy >= 50 || xx < 0 || xx >= 50) continue;
+                const float v = U1[yy * 50 + xx];
+                c0 += v * w.u1_w[(dy * 3 + dx) * 2];
+                c1 += v * w.u1_w[(dy * 3 + dx) * 2 + 1];
+            }
+        a1[p * 2] = fmaxf(c0, 0.f);
+        a1[p * 2 + 1] = fmaxf(c1, 0.f);
+    }
+    __syncthreads();
+    // upsampling2: 50x50x2 -> 100x100x2 (:172)
+    for (int p = tid; p < 10000; p += nt) {
+        const int Y = p / 100, X = p % 100;
+        int yl, yh, xl, xh; float wyl, wyh, wxl, wxh;
+        bil_tap(Y, 50, yl, yh, wyl, wyh);
+        bil_tap(X, 50, xl, xh, wxl, wxh);
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+            U2[p * 2 + c] = wyl * (wxl * a1[(yl * 50 + xl) * 2 + c] + wxh * a1[(yl * 50 + xh) * 2 + c]) +
+                            wyh * (wxl * a1[(yh * 50 + xl) * 2 + c] + wxh * a1[(yh * 50 + xh) * 2 + c]);
+    }
+    __syncthreads();
+    // upconv2 2 -> 4 + BN + ReLU (:173-175) -> bf16 NHWC with channels padded to 8
+    __nv_bfloat16 *dst = up2_out + (size_t)s * 100 * 100 * 8;
+    for (int p = tid; p < 10000; p += nt) {
+        const int y = p / 100, x = p % 100;
+        float c[4] = {w.u2_b[0], w.u2_b[1], w.u2_b[2], w.u2_b[3]};
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+                const int yy = y + dy - 1, xx = x + dx - 1;
+                if (yy < 0 || yy >= 100 || xx < 0 || xx >= 100) continue;
+                const float v0 = U2[(yy * 100 + xx) * 2], v1 = U2[(yy * 100 + xx) * 2 + 1];
+                const float *wp = w.u2_w + (dy * 3 + dx) * 8;
+#pragma unroll
+                for (int co = 0; co < 4; co++) c[co] += v0 * wp[co] + v1 * wp[4 + co];
+            }
+        *reinterpret_cast<uint2 *>(dst + (size_t)p * 8) =
+            make_uint2(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)));
+    }
+}
+
+// upconv3 (bilinear x2 folded into 4 phases) 4 -> 8 + BN + ReLU: one thread per low-res pixel
+__global__ void __launch_bounds__(128)
+k_up3_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, __nv_bfloat16 *__restrict__ out) {
+    __shared__ float sw[9 * 32 * 4];                            // [tap][n][cin<4]
+    __shared__ float sb[32], rw[9 * 4 * 8], rb[8];
+    for (int i = threadIdx.x; i < 9 * 32 * 4; i += blockDim.x) sw[i] = bf2f(w.u3_pw[(size_t)(i / 4) * 8 + (i % 4)]);
+    for (int i = threadIdx.x; i < 9 * 4 * 8; i += blockDim.x) rw[i] = w.u3_w[i];
+    if (threadIdx.x < 32) sb[threadIdx.x] = w.u3_pb[threadIdx.x];
+    if (threadIdx.x < 8) rb[threadIdx.x] = w.u3_b[threadIdx.x];
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= 100 * 100) return;
+    const int i = p / 100, j = p % 100;
+    const __nv_bfloat16 *L = in + (size_t)blockIdx.y * 100 * 100 * 8;
+    __nv_bfloat16 *dst = out + (size_t)blockIdx.y * 200 * 200 * 8;
+    float acc[32];
+#pragma unroll
+    for (int n = 0; n < 32; n++) acc[n] = sb[n];
+#pragma unroll
+    for (int u = 0; u < 3; u++)
+#pragma unroll
+        for (int v = 0; v < 3; v++) {
+            const int yy = min(max(i + u - 1, 0), 99), xx = min(max(j + v - 1, 0), 99);
+            float x[8];
+            unpack_bf8(*reinterpret_cast<const uint4 *>(L + ((size_t)yy * 100 + xx) * 8), x);
+            const float *wp = sw + (u * 3 + v) * 128;
+#pragma unroll
+            for (int n = 0; n < 32; n++)
+#pragma unroll
+                for (int ci = 0; ci < 4; ci++) acc[n] += x[ci] * wp[n * 4 + ci];
+        }
+#pragma unroll
+    for (int ph = 0; ph < 4; ph++) {
+        const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
+        float o[8];
+        if (Y == 0 || Y == 199 || X == 0 || X == 199) up_ring_pixel<4, 8>(L, 100, Y, X, rw, rb, o);
+        else {
+#pragma unroll
+            for (int co = 0; co < 8; co++) o[co] = acc[ph * 8 + co];
+        }
+#pragma unroll
+        for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
+        *reinterpret_cast<uint4 *>(dst + ((size_t)Y * 200 + X) * 8) = pack_bf8(o);
+    }
+}
+
+// upconv4 (phase-folded) 8 -> 1, linear, + per-block argmax partials; optional dense map
+__global__ void __launch_bounds__(256)
+k_up4_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, float *__restrict__ ptr_out, float *__restrict__ amax_val,
+         int *__restrict__ amax_idx) {
+    __shared__ float sw[9 * 4 * 8], rw[72], sv[8];
+    __shared__ int si[8];
+    for (int i = threadIdx.x; i < 9 * 4 * 8; i += blockDim.x) sw[i] = bf2f(w.u4_pw[(size_t)((i / 32) * 16 + (i / 8) % 4) * 8 + (i % 8)]);
+    for (int i = threadIdx.x; i < 72; i += blockDim.x) rw[i] = w.u4_w[i];
+    __syncthreads();
+    const float pb = w.u4_pb[0], rb = w.u4_b[0];
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const __nv_bfloat16 *L = in + (size_t)blockIdx.y * 200 * 200 * 8;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    if (p < 200 * 200) {
+        const int i = p / 200, j = p % 200;
+        float acc[4] = {pb, pb, pb, pb};
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+#pragma unroll
+            for (int v = 0; v < 3; v++) {
+                const int yy = min(max(i + u - 1, 0), 199), xx = min(max(j + v - 1, 0), 199);
+                float x[8];
+                unpack_bf8(*reinterpret_cast<const uint4 *>(L + ((size_t)yy * 200 + xx) * 8), x);
+                const float *wp = sw + (u * 3 + v) * 32;
+#pragma unroll
+                for (int ph = 0; ph < 4; ph++)
+#pragma unroll
+                    for (int ci = 0; ci < 8; ci++) acc[ph] += x[ci] * wp[ph * 8 + ci];
+            }
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) {
+            const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
+            float o = acc[ph];
+            if (Y == 0 || Y == 399 || X == 0 || X == 399) up_ring_pixel<8, 1>(L, 200, Y, X, rw, &rb, &o);
+            const int idx = Y * 400 + X;
+            if (ptr_out) ptr_out[(size_t)blockIdx.y * 160000 + idx] = o;
+            if (amax_better(o, idx, bv, bi)) { bv = o; bi = idx; }
+        }
+    }
+    amax_warp(bv, bi);
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = bv; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        bv = threadIdx.x < 8 ? sv[threadIdx.x] : -INFINITY;
+        bi = threadIdx.x < 8 ? si[threadIdx.x] : 0x7fffffff;
+        amax_warp(bv, bi);
+        if (threadIdx.x == 0) {
+            amax_val[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = bv;
+            amax_idx[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = bi;
+        }
+    }
+}
+
+// final argmax over the per-block partials: one warp per ship; (x, y) = (k % 400, k / 400)
+__global__ void k_argmax_final(const float *__restrict__ val, const int *__restrict__ idx, int parts, int n_ships, int *__restrict__ xy) {
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= n_ships) return;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < parts; k += 32) {
+        const float v = val[(size_t)s * parts + k];
+        const int i = idx[(size_t)s * parts + k];
+        if (amax_better(v, i, bv, bi)) { bv = v; bi = i; }
+    }
+    amax_warp(bv, bi);
+    if (lane == 0) { xy[s * 2] = bi % POL_W; xy[s * 2 + 1] = bi / POL_W; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// orchestration
+// ------------------------------------------------------------------------------------------------
+static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, int A, int P, float *act, float *ptr, int32_t *iact,
+                         int32_t *xy, cudaStream_t st) {
+    const PolicyDev &w = p->w;
+    PolicyWork &ws = p->ws;
+    const int S = A * P;
+    const bool tc = p->engine == OFB_ENGINE_TENSOR;
+    int rc;
+    if (tc) {
+        if ((rc = pol_tc_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc;
+        if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc;
+        if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc;
+        if ((rc = pol_tc_dense1(p, ws.flat, ws.hflat, A, st)) != OFB_OK) return rc;
+    } else {
+        k_trunk1_cc<<<dim3((40000 + 255) / 256, A), 256, 0, st>>>(maps, w, ws.pool1);
+        k_conv_pool_cc<<<dim3((10000 + 127) / 128, A), 128, 0, st>>>(ws.pool1, w.cw[0], w.cb[0], ws.pool2, 200, 100 * 100 * 8);
+        k_conv_pool_cc<<<dim3((2500 + 127) / 128, A), 128, 0, st>>>(ws.pool2, w.cw[1], w.cb[1], ws.pool3, 100, 50 * 50 * 8);
+        k_conv_pool_cc<<<dim3((625 + 127) / 128, A), 128, 0, st>>>(ws.pool3, w.cw[2], w.cb[2], ws.flat, 50, POL_FLAT_PITCH);
+        k_dense1_cc<<<(A + 7) / 8, 128, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
+    }
+    k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2);
+    if (!xy && !ptr) { OFB_CUDA_CHECK(cudaGetLastError()); return OFB_OK; }
+    int parts;
+    if (tc) {
+        if ((rc = pol_tc_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc;
+        if ((rc = pol_tc_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc;
+        parts = AMAX_PARTS;
+    } else {
+        k_up3_cc<<<dim3((10000 + 127) / 128, S), 128, 0, st>>>(ws.up2, w, ws.up3);
+        parts = (40000 + 255) / 256;
+        k_up4_cc<<<dim3(parts, S), 256, 0, st>>>(ws.up3, w, ptr, ws.amax_val, ws.amax_idx);
+    }
+    if (xy) k_argmax_final<<<(S * 32 + 127) / 128, 128, 0, st>>>(ws.amax_val, ws.amax_idx, parts, S, xy);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_policy_forward(ofb_policy *p, const uint32_t *maps, const float *vec, int64_t n_arenas, int P, float *act,
+                                  float *ptr, int32_t *iact, int32_t *xy, void *stream) {
+    if (!p || !maps || !vec || n_arenas < 0 || P < 1 || P > p->max_ships) {
+        ofb_set_error("ofb_policy_forward: bad argument");
+        return OFB_E_ARG;
+    }
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(HEADS_SMEM_FLOATS * sizeof(float))));
+        attr_set = true;
+    }
+    const int64_t chunk = p->max_ships / P;                     // arenas per chunk
+    for (int64_t a0 = 0; a0 < n_arenas; a0 += chunk) {
+        const int A = (int)((n_arenas - a0) < chunk ? (n_arenas - a0) : chunk);
+        const int64_t s0 = a0 * P;
+        int rc = forward_chunk(p, maps + a0 * 2 * POL_WORDS, vec + s0 * 8, A, P, act ? act + s0 * 2 : nullptr,
+                               ptr ? ptr + s0 * 160000 : nullptr, iact ? iact + s0 : nullptr, xy ? xy + s0 * 2 : nullptr,
+                               (cudaStream_t)stream);
+        if (rc != OFB_OK) return rc;
+    }
+    return OFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// action vector of QlearnIA.play (+ eps-greedy random_play), image packing, debug taps
+// ------------------------------------------------------------------------------------------------
+__global__ void k_write_actions(const int *__restrict__ iact, const int *__restrict__ xy, long long n_rows, int P,
+                                const int *__restrict__ ship_index, int S, float eps, uint64_t seed, long long arena0, uint32_t step,
+                                int2 *__restrict__ actions) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const long long a = r / P;
+    const int ship = ship_index[r % P];
+    int ia = iact[r], x = xy[r * 2], y = xy[r * 2 + 1];
+    if (eps > 0.f) {
+        uint32_t c[4] = {(uint32_t)(arena0 + a), (uint32_t)ship, step, 2u};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        if ((float)(c[0] >> 8) * (1.0f / 16777216.0f) <= eps) {     // np.random.rand() <= epsilon  (:201)
+            ia = (int)(c[1] & 1u);                                   // random.randint(0, action_size - 1)
+            x = (int)mulhi32(c[2], POL_W);                           // randint(0, DEFAULT_WIDTH - 1)
+            y = (int)mulhi32(c[3], POL_W);
+        }
+    }
+    const int shoot = ia == 0, thrust = ia == 1;                     // act_vector[iaction] = 1   (:449)
+    actions[a * S + ship] = make_int2(shoot | (thrust << 16), (x & 0xffff) | (y << 16));
+}
+
+extern "C" int ofb_policy_write_actions(const int32_t *iact, const int32_t *xy, int64_t n_arenas, int P, const int32_t *ship_index,
+                                        int S, float eps, uint64_t seed, int64_t arena0, uint32_t step, int16_t *actions,
+                                        void *stream) {
+    if (!iact || !xy || !ship_index || !actions || P < 1 || S < P) { ofb_set_error("ofb_policy_write_actions: bad argument"); return OFB_E_ARG; }
+    const long long n = n_arenas * P;
+    if (n == 0) return OFB_OK;
+    k_write_actions<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(iact, xy, n, P, ship_index, S, eps, seed, arena0, step,
+                                                                                  reinterpret_cast<int2 *>(actions));
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+template <class T>
+__global__ void k_pack_image(const T *__restrict__ img, long long n_words, uint32_t *__restrict__ maps) {
+    const long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // word index over [B][5000]
+    if (wi >= n_words) return;
+    const long long b = wi / POL_WORDS;
+    const int w = (int)(wi % POL_WORDS);
+    const T *src = img + ((size_t)b * 160000 + (size_t)w * 32) * 2;
+    uint32_t s = 0, l = 0;
+    for (int k = 0; k < 32; k++) {
+        if (src[k * 2] != T(0)) s |= 1u << k;
+        if (src[k * 2 + 1] != T(0)) l |= 1u << k;
+    }
+    maps[(size_t)b * 2 * POL_WORDS + w] = s;
+    maps[(size_t)b * 2 * POL_WORDS + POL_WORDS + w] = l;
+}
+
+extern "C" int ofb_policy_pack_image(const void *img, int fmt, int64_t n, uint32_t *maps, void *stream) {
+    if (!img || !maps || n < 0) { ofb_set_error("ofb_policy_pack_image: bad argument"); return OFB_E_ARG; }
+    const long long nw = n * POL_WORDS;
+    if (nw == 0) return OFB_OK;
+    const unsigned blocks = (unsigned)((nw + 255) / 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (fmt == OFB_MAP_U8) k_pack_image<uint8_t><<<blocks, 256, 0, st>>>(static_cast<const uint8_t *>(img), nw, maps);
+    else if (fmt == OFB_MAP_BF16) k_pack_image<uint16_t><<<blocks, 256, 0, st>>>(static_cast<const uint16_t *>(img), nw, maps);
+    else if (fmt == 3) k_pack_image<float><<<blocks, 256, 0, st>>>(static_cast<const float *>(img), nw, maps);
+    else { ofb_set_error("ofb_policy_pack_image: unknown format %d", fmt); return OFB_E_ARG; }
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_policy_debug_tap(ofb_policy *p, int which, int64_t n_items, void *dst_dev, void *stream) {
+    if (!p || !dst_dev || n_items < 0 || n_items > p->max_ships) { ofb_set_error("ofb_policy_debug_tap: bad argument"); return OFB_E_ARG; }
+    const void *src;
+    size_t stride;
+    switch (which) {
+    case 0: src = p->ws.pool1; stride = 200 * 200 * 8 * 2; break;
+    case 1: src = p->ws.pool2; stride = 100 * 100 * 8 * 2; break;
+    case 2: src = p->ws.pool3; stride = 50 * 50 * 8 * 2; break;
+    case 3: src = p->ws.flat; stride = POL_FLAT_PITCH * 2; break;
+    case 4: src = p->ws.hflat; stride = 100 * 4; break;
+    case 5: src = p->ws.up2; stride = 100 * 100 * 8 * 2; break;
+    case 6: src = p->ws.up3; stride = 200 * 200 * 8 * 2; break;
+    default: ofb_set_error("ofb_policy_debug_tap: unknown tap %d", which); return OFB_E_ARG;
+    }
+    OFB_CUDA_CHECK(cudaMemcpyAsync(dst_dev, src, stride * (size_t)n_items, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return OFB_OK;
+}

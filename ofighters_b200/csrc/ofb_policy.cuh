@@ -1,0 +1,74 @@
+// Internal definitions of the policy forward (see include/ofb_policy.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ofb.h"
+#include "../../include/ofb_policy.h"
+
+#define POL_W 400
+#define POL_WORDS 5000           // W*H/32 words per bit map
+#define POL_TAPS 10              // 9 taps + 1 zero tap (K = 10 * 8 = 80 = 5 UMMA K-steps)
+#define POL_FLAT 5000            // 25*25*8
+#define POL_FLAT_PITCH 5120      // padded K of dense1's flat part (zeros beyond 5000)
+
+// Device-side weights, BN already folded (see fold_weights in ofb_policy.cu).
+struct PolicyDev {
+    // trunk
+    float *c1_w;              // [9][2][8]  (tap, cin, cout)  fp32
+    float *c1_b;              // [8]
+    __nv_bfloat16 *cw[3];     // conv2..4: [10][16][8] (tap, n = cout padded to 16, cin)  bf16
+    float *cb[3];             // [16]
+    // dense1
+    float *d1_wv;             // [8][100]     vector slice, fp32 (values up to 400 are not bf16-exact)
+    __nv_bfloat16 *d1_wf;     // [5000][100]  flat slice, (k, n)  -- CUDA-core engine
+    __nv_bfloat16 *d1_wt;     // [128][5120]  flat slice transposed + zero padded (n, k) -- tensor engine
+    float *d1_b;              // [100]
+    // heads
+    float *d2_w, *d2_b;       // [100][50], [50]
+    float *o1_w, *o1_b;       // [50][2], [2]
+    float *ud_w, *ud_b;       // [100][625], [625]
+    float *u1_w, *u1_b;       // upconv1 [9][1][2], [2]
+    float *u2_w, *u2_b;       // upconv2 [9][2][4], [4]
+    // upconv3 / upconv4: bilinear x2 folded into 4 output phases on the low-res grid
+    float *u3_w, *u3_b;       // [9][4][8], [8]   un-phased fp32 (ring pixels)
+    __nv_bfloat16 *u3_pw;     // [10][32][8]      (tap, n = phase*8 + cout, cin padded to 8)
+    float *u3_pb;             // [32]
+    float *u4_w, *u4_b;       // [9][8][1], [1]
+    __nv_bfloat16 *u4_pw;     // [10][16][8]      (tap, n = phase (4 used), cin)
+    float *u4_pb;             // [16]
+};
+
+struct PolicyWork {
+    __nv_bfloat16 *pool1;     // [Ca][200*200*8]
+    __nv_bfloat16 *pool2;     // [Ca][100*100*8]
+    __nv_bfloat16 *pool3;     // [Ca][50*50*8]
+    __nv_bfloat16 *flat;      // [Ca][5120]
+    float *hflat;             // [Ca][100]   dense1 flat-part pre-activation
+    __nv_bfloat16 *up2;       // [Cs][100*100*8]
+    __nv_bfloat16 *up3;       // [Cs][200*200*8]
+    float *amax_val;          // [Cs][AMAX_PARTS]
+    int *amax_idx;            // [Cs][AMAX_PARTS]
+};
+#define AMAX_PARTS 160
+
+struct ofb_policy {
+    int device;
+    int max_ships;
+    int engine;
+    PolicyDev w;
+    PolicyWork ws;
+    void *arena_blob;         // single allocation holding all weights
+    void *work_blob;          // single allocation holding the workspace
+};
+
+void ofb_set_error(const char *fmt, ...);
+
+// tensor-core (tcgen05) kernels, ofb_policy_tc.cu
+int pol_tc_conv_pool(const ofb_policy *p, int layer, const __nv_bfloat16 *in, __nv_bfloat16 *out, int hin, int n_items,
+                     long long out_item_stride, cudaStream_t st);
+int pol_tc_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
+int pol_tc_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
+int pol_tc_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
+               cudaStream_t st);
+int pol_tc_dense1(const ofb_policy *p, const __nv_bfloat16 *flat, float *hflat, int n_items, cudaStream_t st);

@@ -1,0 +1,158 @@
+"""Parity of the CUDA policy forward (through the C ABI) with the torch-fp32 oracle -- B200 box.
+
+Tolerances (stated here, used below): activations travel as bf16 between layers and the tensor-core
+contractions take bf16 operands, so against the all-fp32 oracle every tapped tensor must agree to
+  max|x - ref| <= 2.5e-2 * max|ref|        (bf16 has 8 significant bits; ~6 rounding points deep)
+while the two engines of the library (tensor cores vs CUDA cores, same bf16 operands, different
+fp32 summation order) must agree to 2e-3 * max|ref|.  Discrete outputs: iaction equal unless the two
+action values are within tolerance of each other; the decoded pointer must be a near-argmax of the
+oracle's map (ref[xy] >= max(ref) - tol).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TOL_ORACLE = 2.5e-2
+TOL_ENGINES = 2e-3
+
+
+def _scene(n_arenas, frames=30, ships=7, seed=11):
+    from ofighters_b200 import BatchedBattleground
+    bg = BatchedBattleground(n_arenas, ships={"random": ships}, seed=seed)
+    for _ in range(frames):
+        bg.frame()
+    return bg, bg.raster("bits")
+
+
+def _dense_image(maps):
+    b = maps.cpu().numpy().view(np.uint32)
+    d = np.unpackbits(b.view(np.uint8).reshape(b.shape[0], 2, -1), axis=2, bitorder="little")
+    return torch.from_numpy(d.reshape(b.shape[0], 2, 400, 400).transpose(0, 2, 3, 1).astype(np.float32))
+
+
+def _relerr(x, ref):
+    x, ref = x.float().cpu(), ref.float().cpu()
+    return float((x - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+
+
+def _nhwc(t):           # oracle NCHW -> NHWC
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.fixture(scope="module")
+def setup():
+    from oracle import policy_torch as po
+    from ofighters_b200.policy import PolicyB200
+    w = po.init_weights(5, randomize_bn=True)
+    pol = PolicyB200(w, max_ships=16)
+    bg, maps = _scene(6)
+    img = _dense_image(maps)
+    vec = bg.obs_vec[:, 0, :].contiguous()
+    act, ptr, inter = po.forward(w, img, vec.cpu(), return_intermediates=True)
+    return dict(po=po, pol=pol, w=w, bg=bg, maps=maps, img=img, vec=vec, act=act, ptr=ptr, inter=inter)
+
+
+@pytest.mark.parametrize("engine", ["cuda_core", "tensor"])
+def test_forward_matches_oracle(setup, engine):
+    s = setup
+    pol = s["pol"]
+    pol.set_engine(engine)
+    r = pol.forward(s["maps"], s["vec"], 1, want_ptr=True)
+    torch.cuda.synchronize()
+    n = s["maps"].shape[0]
+    taps = {}
+    if engine == "cuda_core":
+        taps["pool1"] = pol.debug_tap(0, n, (200, 200, 8))
+    taps["pool2"] = pol.debug_tap(1, n, (100, 100, 8))
+    taps["pool3"] = pol.debug_tap(2, n, (50, 50, 8))
+    taps["pool4"] = pol.debug_tap(3, n, (25, 25, 8))
+    taps["up3"] = pol.debug_tap(6, n, (200, 200, 8))
+    up2 = pol.debug_tap(5, n, (100, 100, 8))
+    assert float(up2[..., 4:].abs().max()) == 0.0            # channel padding stays zero
+    errs = {k: _relerr(v, _nhwc(s["inter"][k])) for k, v in taps.items()}
+    errs["up2"] = _relerr(up2[..., :4], _nhwc(s["inter"]["up2"]))
+    errs["act"] = _relerr(r["act"], s["act"])
+    errs["ptr"] = _relerr(r["ptr"], s["ptr"])
+    print(engine, {k: "%.2e" % v for k, v in errs.items()})
+    bad = {k: v for k, v in errs.items() if not v <= TOL_ORACLE}
+    assert not bad, bad
+    # discrete outputs
+    ia_ref, xy_ref = s["po"].decode(s["act"], s["ptr"])
+    tol_a = TOL_ORACLE * float(s["act"].abs().max())
+    for b in range(n):
+        if abs(float(s["act"][b, 0] - s["act"][b, 1])) > 2 * tol_a:
+            assert int(r["iaction"][b]) == int(ia_ref[b])
+        x, y = (int(v) for v in r["xy"][b])
+        tol_p = TOL_ORACLE * float(s["ptr"][b].abs().max())
+        assert float(s["ptr"][b, y, x]) >= float(s["ptr"][b].max()) - 2 * tol_p
+    # the fused decode equals np.argmax of the library's own dense map (first max wins, (x, y) = (col, row))
+    k = torch.argmax(r["ptr"].reshape(n, -1), dim=1).cpu()
+    assert torch.equal(r["xy"].cpu().long(), torch.stack([k % 400, k // 400], dim=1))
+    assert torch.equal(r["iaction"].cpu().long(), torch.argmax(r["act"], dim=1).cpu())
+
+
+def test_engines_agree_tightly(setup):
+    s = setup
+    pol = s["pol"]
+    n = s["maps"].shape[0]
+    out = {}
+    for engine in ("cuda_core", "tensor"):
+        pol.set_engine(engine)
+        r = pol.forward(s["maps"], s["vec"], 1, want_ptr=True)
+        out[engine] = dict(act=r["act"].clone(), ptr=r["ptr"].clone(), pool2=pol.debug_tap(1, n, (100, 100, 8)).clone(),
+                           pool3=pol.debug_tap(2, n, (50, 50, 8)).clone(), pool4=pol.debug_tap(3, n, (25, 25, 8)).clone(),
+                           up3=pol.debug_tap(6, n, (200, 200, 8)).clone())
+    errs = {k: _relerr(out["tensor"][k], out["cuda_core"][k]) for k in out["tensor"]}
+    print({k: "%.2e" % v for k, v in errs.items()})
+    # bf16 storage can flip one ulp (2^-8 relative) where the fp32 sums differ in the last bits
+    assert all(v <= 8e-3 for v in errs.values()), errs
+    assert errs["act"] <= TOL_ENGINES and errs["ptr"] <= 5e-3, errs
+
+
+def test_multi_ship_and_chunking(setup):
+    """P policy ships per arena share the trunk; chunked calls equal one-shot calls."""
+    from ofighters_b200.policy import PolicyB200
+    s = setup
+    pol_small = PolicyB200(s["w"], max_ships=4)              # forces 3 chunks of 2 arenas x 2 ships
+    pol_small.set_engine("cuda_core")
+    vec2 = s["bg"].obs_vec[:, :2, :].contiguous().reshape(-1, 8)
+    a = pol_small.forward(s["maps"], vec2, 2, want_ptr=False)
+    s["pol"].set_engine("cuda_core")
+    b = s["pol"].forward(s["maps"], vec2, 2, want_ptr=False)
+    assert torch.equal(a["xy"], b["xy"]) and torch.equal(a["act"], b["act"])
+    # ship 0 of each arena equals the P=1 result
+    c = s["pol"].forward(s["maps"], s["vec"], 1)
+    assert torch.equal(b["act"][0::2], c["act"]) and torch.equal(b["xy"][0::2], c["xy"])
+
+
+def test_predict_interface_and_action_rows(setup):
+    s = setup
+    pol = s["pol"]
+    pol.set_engine("cuda_core")
+    act, ptr = pol.predict([s["img"][:2], s["vec"][:2].cpu()])
+    assert tuple(act.shape) == (2, 2) and tuple(ptr.shape) == (2, 400, 400, 1)
+    assert tuple(pol.ptr_values.shape) == (400, 400) and tuple(pol.act_values.shape) == (2,)
+    r = pol.forward(s["maps"][:2], s["vec"][:2], 1, want_ptr=True)
+    assert torch.equal(ptr[..., 0], r["ptr"]) and torch.equal(act, r["act"])
+    # bits <-> dense image packing is lossless for u8 / bf16 / f32 inputs
+    for dt in (torch.uint8, torch.bfloat16, torch.float32):
+        assert torch.equal(pol.pack_image(s["img"].to(dt)), s["maps"])
+    with pytest.raises(Exception, match="Invalid image input"):
+        pol.predict([torch.zeros(1, 400, 399, 2), torch.zeros(1, 8)])
+    # QlearnIA.play's action vector, written into ship 6's rows of a 6+1 arena
+    from ofighters_b200 import BatchedBattleground
+    bg = BatchedBattleground(4, ships={"idle": 6, "QlearnIA": 1}, seed=3)
+    maps = bg.raster("bits")
+    iact, xy = pol.act(bg, maps)
+    torch.cuda.synchronize()
+    rows = bg.actions[:, 6, :].cpu().long()
+    assert torch.equal(rows[:, 0], (iact.cpu() == 0).long()) and torch.equal(rows[:, 1], (iact.cpu() == 1).long())
+    assert torch.equal(rows[:, 2:], xy.cpu().long())
+    assert int(bg.actions[:, :6, :2].abs().sum()) == 0
+    bg.frame()                                               # idle bots leave the policy rows alone ("external")
+    # eps = 1: every policy ship plays random_play's distribution
+    pol.act(bg, maps, epsilon=1.0)
+    rows = bg.actions[:, 6, :].cpu().long()
+    assert ((rows[:, 0] + rows[:, 1]) == 1).all() and (rows[:, 2:] >= 0).all() and (rows[:, 2:] < 400).all()
