@@ -517,7 +517,7 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
         if ((rc = pol_tc_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc;
         if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc;
         if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc;
-        if ((rc = pol_tc_dense1(p, ws.flat, ws.hflat, A, st)) != OFB_OK) return rc;
+        k_dense1_cc<<<(A + 7) / 8, 128, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
     } else {
         k_trunk1_cc<<<dim3((40000 + 255) / 256, A), 256, 0, st>>>(maps, w, ws.pool1);
         k_conv_pool_cc<<<dim3((10000 + 127) / 128, A), 128, 0, st>>>(ws.pool1, w.cw[0], w.cb[0], ws.pool2, 200, 100 * 100 * 8);
@@ -531,7 +531,7 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     if (tc) {
         if ((rc = pol_tc_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc;
         if ((rc = pol_tc_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc;
-        parts = AMAX_PARTS;
+        parts = pol_tc_up4_parts();
     } else {
         k_up3_cc<<<dim3((10000 + 127) / 128, S), 128, 0, st>>>(ws.up2, w, ws.up3);
         parts = (40000 + 255) / 256;

@@ -71,4 +71,4 @@ int pol_tc_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out
 int pol_tc_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 int pol_tc_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st);
-int pol_tc_dense1(const ofb_policy *p, const __nv_bfloat16 *flat, float *hflat, int n_items, cudaStream_t st);
+int pol_tc_up4_parts();

@@ -1,10 +1,392 @@
-// Tensor-core (tcgen05 / TMEM) kernels of the policy forward -- placeholder until they land.
+// Tensor-core engine of the policy forward: 3x3 convolutions as tcgen05 "shifted GEMMs" (sm_100a).
+//
+// Activations are NHWC bf16 with 8 channels = one 16-byte row of a UMMA core matrix per pixel.  A CTA
+// stages a strip of the input image in shared memory as a LINEAR pixel array with pitch P (one or two
+// halo pixels per row) and never builds an im2col matrix: for the tile of 128 consecutive output
+// positions q = 128 t .. 128 t + 127, tap (dy, dx) of the 3x3 stencil is the same array shifted by
+// dy*P + dx pixels, so the A operand of every tcgen05.mma is just a shared-memory descriptor
+// (K-major, no swizzle: 8 pixels x 16 B = one core matrix, SBO = 128 B between 8-pixel groups,
+// LBO = distance between the two taps that make up one K = 16 step).  Nine taps + one zero tap =
+// five MMAs (M = 128, N = 16 or 32, K = 16) per tile, accumulated in TMEM; the 128 threads then read
+// their accumulator row with tcgen05.ld and run the fused epilogue:
+//   conv2/3/4 : + bias, ReLU, bf16 -> smem stage -> 2x2 max-pool -> HBM
+//   upconv3   : bilinear x2 folded into 4 output phases (N = 4 x 8): + bias, ReLU -> 4 pixels of HBM
+//   upconv4   : 4 phases of the single output channel: + bias -> running argmax (+ optional dense map)
+// conv1 never touches HBM: its pooled output is generated straight into conv2's shared-memory strip
+// from the bit maps (background constant + exact evaluation near set bits).
+// Double-buffered TMEM accumulators let the MMAs of tile t+1 run under the epilogue of tile t.
 #include "ofb_common.cuh"
 #include "ofb_policy_dev.cuh"
 
-#define NOT_YET(name) do { ofb_set_error(name ": tensor engine not built yet"); return OFB_E_STATE; } while (0)
-int pol_tc_conv_pool(const ofb_policy *, int, const __nv_bfloat16 *, __nv_bfloat16 *, int, int, long long, cudaStream_t) { NOT_YET("conv_pool"); }
-int pol_tc_trunk12(const ofb_policy *, const uint32_t *, __nv_bfloat16 *, int, cudaStream_t) { NOT_YET("trunk12"); }
-int pol_tc_up3(const ofb_policy *, const __nv_bfloat16 *, __nv_bfloat16 *, int, cudaStream_t) { NOT_YET("up3"); }
-int pol_tc_up4(const ofb_policy *, const __nv_bfloat16 *, float *, float *, int *, int, cudaStream_t) { NOT_YET("up4"); }
-int pol_tc_dense1(const ofb_policy *, const __nv_bfloat16 *, float *, int, cudaStream_t) { NOT_YET("dense1"); }
+enum { M_CONV_GMEM = 0, M_CONV_BITS = 1, M_UP3 = 2, M_UP4 = 3 };
+#define TC_R 10                       // image rows per strip (all layer heights are multiples of 10)
+
+struct TcArgs {
+    const void *in;                   // bf16 [item][H][H][8], or uint32 bit maps [item][2][5000]
+    const __nv_bfloat16 *wt;          // [10][N][8] B-operand image
+    const float *bias;                // [N]
+    const float *aux_w, *aux_b;       // conv1 fp32 weights (BITS) / un-phased fp32 weights (ring of UP3, UP4)
+    __nv_bfloat16 *out;               // pooled / upsampled activations
+    float *ptr_out;                   // UP4: optional dense map [item][400][400]
+    float *amax_val;                  // UP4: [item][gridDim.x]
+    int *amax_idx;
+    long long in_item_stride, out_item_stride;   // in elements
+    int H;                            // input height = width (conv resolution)
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        if (++spins > (1u << 24)) __trap();              // a lost arrival must fail loudly, not hang the GPU
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start / LBO / SBO in
+// 16-byte units, version 1 (Blackwell), layout type 0.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t start16, uint32_t lbo16, uint32_t sbo16) {
+    return (uint64_t)(start16 & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) | (1ull << 46);
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128
+__host__ __device__ constexpr uint32_t instr_desc(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// shared-memory plan of one CTA (host and device agree through this)
+struct TcPlan {
+    int P, tiles, sin_pixels;
+    unsigned off_sin, off_stage, off_aux, off_bar, total;
+};
+__host__ __device__ inline TcPlan tc_plan(int mode, int N, int H) {
+    TcPlan p;
+    p.P = H + ((mode == M_UP3 || mode == M_UP4) ? 2 : 1);
+    p.tiles = (TC_R * p.P + 127) / 128;
+    p.sin_pixels = 128 * p.tiles + 2 * p.P + 8;
+    p.off_sin = (unsigned)((POL_TAPS * N * 16 + 127) & ~127);
+    p.off_stage = p.off_sin + (unsigned)p.sin_pixels * 16;
+    const unsigned stage = (mode == M_CONV_GMEM || mode == M_CONV_BITS) ? (unsigned)p.tiles * 128 * 16 : 0;
+    p.off_aux = p.off_stage + stage;
+    p.off_bar = p.off_aux + 1280;                       // aux: up to 320 floats (conv1 / ring weights + bias)
+    p.total = p.off_bar + 32;
+    return p;
+}
+
+template <int MODE, int N>
+__global__ void __launch_bounds__(128)
+k_tc_conv(const TcArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr bool REPL = (MODE == M_UP3 || MODE == M_UP4);
+    constexpr bool POOL = (MODE == M_CONV_GMEM || MODE == M_CONV_BITS);
+    constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : 64;
+    const int W = a.H;
+    const TcPlan pl = tc_plan(MODE, N, W);
+    const int P = pl.P, T = pl.tiles;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int item = blockIdx.y, y0 = blockIdx.x * TC_R;
+
+    uint4 *sw = reinterpret_cast<uint4 *>(smem);
+    uint4 *sin = reinterpret_cast<uint4 *>(smem + pl.off_sin);
+    uint4 *stage = reinterpret_cast<uint4 *>(smem + pl.off_stage);
+    float *aux = reinterpret_cast<float *>(smem + pl.off_aux);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + pl.off_bar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + pl.off_bar + 16);
+
+    // ---- one-time setup: TMEM, barriers, weights
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    if (tid == 32) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.wt);
+        for (int i = tid; i < POL_TAPS * N; i += 128) sw[i] = src[i];
+    }
+    if (MODE == M_CONV_BITS) {
+        for (int i = tid; i < 152; i += 128) aux[i] = i < 144 ? a.aux_w[i] : a.aux_b[i - 144];
+    } else if (MODE == M_UP3) {
+        for (int i = tid; i < 9 * 4 * 8 + 8; i += 128) aux[i] = i < 288 ? a.aux_w[i] : a.aux_b[i - 288];
+    } else if (MODE == M_UP4) {
+        for (int i = tid; i < 73; i += 128) aux[i] = i < 72 ? a.aux_w[i] : a.aux_b[0];
+    }
+    float biasr[POOL ? 8 : (MODE == M_UP3 ? 32 : 4)];
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(biasr) / sizeof(float)); i++) biasr[i] = a.bias[i];
+
+    // ---- stage the input strip: rows y0-1 .. y0+R, columns -1 .. W (halo pixels zero or replicated)
+    const int rows_in = TC_R + 2;
+    if (MODE == M_CONV_BITS) __syncthreads();            // aux (conv1 weights) is read below
+    if (MODE == M_CONV_BITS) {
+        const uint32_t *smap = reinterpret_cast<const uint32_t *>(a.in) + (size_t)item * 2 * POL_WORDS;
+        const uint32_t *lmap = smap + POL_WORDS;
+        float bg[8];
+#pragma unroll
+        for (int co = 0; co < 8; co++) bg[co] = fmaxf(aux[144 + co], 0.f);
+        const uint4 bgq = pack_bf8(bg);
+        const int groups = W / 8;                        // 8 pooled pixels per work item
+        for (int g = tid; g < rows_in * groups; g += 128) {
+            const int ry = g / groups, gx = g % groups, py = y0 - 1 + ry;
+            uint4 *dst = sin + ry * P + 1 + gx * 8;
+            if (py < 0 || py >= W) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) dst[k] = make_uint4(0, 0, 0, 0);
+                continue;
+            }
+            // 18 map columns 16 gx - 1 .. 16 gx + 16 of the 4 map rows 2 py - 1 .. 2 py + 2
+            uint32_t rs[4], rl[4], any = 0;
+            uint32_t colmask = 0x3FFFFu;
+            if (gx == 0) colmask &= ~1u;
+            if (gx == groups - 1) colmask &= ~(1u << 17);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int r = 2 * py - 1 + i;
+                rs[i] = rl[i] = 0;
+                if (r >= 0 && r < POL_W) {
+                    int b = r * POL_W + 16 * gx - 1;
+                    const int sh = b < 0 ? 1 : 0;
+                    b = max(b, 0);
+                    const int wd = b >> 5, wd1 = min(wd + 1, POL_WORDS - 1);
+                    rs[i] = (__funnelshift_r(smap[wd], smap[wd1], b & 31) << sh) & colmask;
+                    rl[i] = (__funnelshift_r(lmap[wd], lmap[wd1], b & 31) << sh) & colmask;
+                }
+                any |= rs[i] | rl[i];
+            }
+            if (!any) {
+#pragma unroll
+                for (int k = 0; k < 8; k++) dst[k] = bgq;
+                continue;
+            }
+            for (int k = 0; k < 8; k++) {
+                uint32_t ps = 0, pq = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    ps |= ((rs[i] >> (2 * k)) & 0xFu) << (4 * i);
+                    pq |= ((rl[i] >> (2 * k)) & 0xFu) << (4 * i);
+                }
+                if ((ps | pq) == 0) { dst[k] = bgq; continue; }
+                float v[8];
+                conv1_pool_pixel(ps, pq, aux, aux + 144, v);
+                dst[k] = pack_bf8(v);
+            }
+        }
+        for (int ry = tid; ry < rows_in; ry += 128) sin[ry * P] = make_uint4(0, 0, 0, 0);    // shared halo column
+    } else {
+        const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.in) + (size_t)item * a.in_item_stride);
+        for (int i = tid; i < rows_in * P; i += 128) {
+            const int ry = i / P, c = i % P;
+            int y = y0 - 1 + ry, x = c - 1;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (REPL) {
+                y = min(max(y, 0), W - 1);
+                x = min(max(x, 0), W - 1);
+                v = src[(size_t)y * W + x];
+            } else if (y >= 0 && y < W && x >= 0 && x < W) v = src[(size_t)y * W + x];
+            sin[i] = v;
+        }
+    }
+    for (int i = rows_in * P + tid; i < pl.sin_pixels; i += 128) sin[i] = make_uint4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- descriptors
+    constexpr uint32_t IDESC = instr_desc(N);
+    const uint32_t sin16 = smem_u32(sin) >> 4, sw16 = smem_u32(sw) >> 4;
+    auto issue_tile = [&](int t) {
+        const uint32_t d = tmem_base + (uint32_t)((t & 1) * N);
+#pragma unroll
+        for (int j = 0; j < 5; j++) {
+            const int t0 = 2 * j, t1 = 2 * j + 1;
+            const int off0 = (t0 / 3) * P + (t0 % 3);
+            const int off1 = t1 < 9 ? (t1 / 3) * P + (t1 % 3) : off0 + 1;     // tap 9: zero weights
+            const uint64_t ad = smem_desc(sin16 + (uint32_t)(128 * t + off0), (uint32_t)(off1 - off0), 8);
+            const uint64_t bd = smem_desc(sw16 + (uint32_t)(t0 * N), (uint32_t)N, 8);
+            tc_mma(d, ad, bd, IDESC, j > 0 ? 1u : 0u);
+        }
+        tc_commit(&bars[t & 1]);
+    };
+
+    float best_v = -INFINITY;
+    int best_i = 0x7fffffff;
+    if (tid == 0) issue_tile(0);
+    for (int t = 0; t < T; t++) {
+        if (tid == 0 && t + 1 < T) issue_tile(t + 1);
+        mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((t & 1) * N);
+        const int q = 128 * t + tid;
+        if (POOL) {
+            uint32_t r[8];
+            tc_ld8(taddr, r);
+            tc_wait_ld();
+            float v[8];
+#pragma unroll
+            for (int co = 0; co < 8; co++) v[co] = fmaxf(__uint_as_float(r[co]) + biasr[co], 0.f);
+            stage[q] = pack_bf8(v);
+        } else if (MODE == M_UP3) {
+            uint32_t r[32];
+            tc_ld8(taddr, r); tc_ld8(taddr + 8, r + 8); tc_ld8(taddr + 16, r + 16); tc_ld8(taddr + 24, r + 24);
+            tc_wait_ld();
+            const int rr = q / P, c = q % P;
+            if (rr < TC_R && c < W) {
+                const int i = y0 + rr, j = c;
+                const __nv_bfloat16 *L = reinterpret_cast<const __nv_bfloat16 *>(a.in) + (size_t)item * a.in_item_stride;
+                __nv_bfloat16 *dst = a.out + (size_t)item * a.out_item_stride;
+#pragma unroll
+                for (int ph = 0; ph < 4; ph++) {
+                    const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
+                    float o[8];
+                    if (Y == 0 || Y == 2 * W - 1 || X == 0 || X == 2 * W - 1) up_ring_pixel<4, 8>(L, W, Y, X, aux, aux + 288, o);
+                    else {
+#pragma unroll
+                        for (int co = 0; co < 8; co++) o[co] = __uint_as_float(r[ph * 8 + co]) + biasr[ph * 8 + co];
+                    }
+#pragma unroll
+                    for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
+                    *reinterpret_cast<uint4 *>(dst + ((size_t)Y * 2 * W + X) * 8) = pack_bf8(o);
+                }
+            }
+        } else {    // M_UP4
+            uint32_t r[4];
+            tc_ld4(taddr, r);
+            tc_wait_ld();
+            const int rr = q / P, c = q % P;
+            if (rr < TC_R && c < W) {
+                const int i = y0 + rr, j = c;
+                const __nv_bfloat16 *L = reinterpret_cast<const __nv_bfloat16 *>(a.in) + (size_t)item * a.in_item_stride;
+#pragma unroll
+                for (int ph = 0; ph < 4; ph++) {
+                    const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
+                    float o = __uint_as_float(r[ph]) + biasr[ph];
+                    if (Y == 0 || Y == 2 * W - 1 || X == 0 || X == 2 * W - 1) up_ring_pixel<8, 1>(L, W, Y, X, aux, aux + 72, &o);
+                    const int idx = Y * 2 * W + X;
+                    if (a.ptr_out) a.ptr_out[(size_t)item * 4 * W * W + idx] = o;
+                    if (amax_better(o, idx, best_v, best_i)) { best_v = o; best_i = idx; }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                 // buffer t&1 is free again, stage rows are visible
+        tc_fence_after();
+    }
+
+    if (POOL) {
+        const int wo = W / 2;
+        __nv_bfloat16 *dst = a.out + (size_t)item * a.out_item_stride;
+        for (int pp = tid; pp < (TC_R / 2) * wo; pp += 128) {
+            const int pr = pp / wo, pc = pp % wo;
+            const uint4 q0 = stage[(2 * pr) * P + 2 * pc], q1 = stage[(2 * pr) * P + 2 * pc + 1];
+            const uint4 q2 = stage[(2 * pr + 1) * P + 2 * pc], q3 = stage[(2 * pr + 1) * P + 2 * pc + 1];
+            uint4 o;
+            const uint32_t *p0 = &q0.x, *p1 = &q1.x, *p2 = &q2.x, *p3 = &q3.x;
+            uint32_t *po = &o.x;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                __nv_bfloat162 m = __hmax2(__hmax2(*reinterpret_cast<const __nv_bfloat162 *>(p0 + k), *reinterpret_cast<const __nv_bfloat162 *>(p1 + k)),
+                                           __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(p2 + k), *reinterpret_cast<const __nv_bfloat162 *>(p3 + k)));
+                po[k] = *reinterpret_cast<uint32_t *>(&m);
+            }
+            *reinterpret_cast<uint4 *>(dst + ((size_t)(y0 / 2 + pr) * wo + pc) * 8) = o;
+        }
+    }
+    if (MODE == M_UP4) {
+        float *sv = aux + 128;
+        int *si = reinterpret_cast<int *>(aux + 136);
+        amax_warp(best_v, best_i);
+        if ((tid & 31) == 0) { sv[warp] = best_v; si[warp] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int k = 1; k < 4; k++)
+                if (amax_better(sv[k], si[k], best_v, best_i)) { best_v = sv[k]; best_i = si[k]; }
+            a.amax_val[(size_t)item * gridDim.x + blockIdx.x] = best_v;
+            a.amax_idx[(size_t)item * gridDim.x + blockIdx.x] = best_i;
+        }
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+}
+
+// ---------------------------------------------------------------- host launchers
+template <int MODE, int N>
+static int launch(const TcArgs &a, int n_items, cudaStream_t st) {
+    const TcPlan pl = tc_plan(MODE, N, a.H);
+    static thread_local unsigned configured = 0;
+    if (pl.total > configured) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tc_conv<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
+        configured = pl.total;
+    }
+    if (n_items == 0) return OFB_OK;
+    k_tc_conv<MODE, N><<<dim3(a.H / TC_R, n_items), 128, pl.total, st>>>(a);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+int pol_tc_conv_pool(const ofb_policy *p, int layer, const __nv_bfloat16 *in, __nv_bfloat16 *out, int hin, int n_items,
+                     long long out_item_stride, cudaStream_t st) {
+    TcArgs a = {};
+    a.in = in; a.wt = p->w.cw[layer]; a.bias = p->w.cb[layer]; a.out = out;
+    a.in_item_stride = (long long)hin * hin * 8; a.out_item_stride = out_item_stride; a.H = hin;
+    return launch<M_CONV_GMEM, 16>(a, n_items, st);
+}
+
+int pol_tc_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
+    TcArgs a = {};
+    a.in = maps; a.wt = p->w.cw[0]; a.bias = p->w.cb[0]; a.aux_w = p->w.c1_w; a.aux_b = p->w.c1_b; a.out = out;
+    a.out_item_stride = 100 * 100 * 8; a.H = 200;
+    return launch<M_CONV_BITS, 16>(a, n_items, st);
+}
+
+int pol_tc_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
+    TcArgs a = {};
+    a.in = in; a.wt = p->w.u3_pw; a.bias = p->w.u3_pb; a.aux_w = p->w.u3_w; a.aux_b = p->w.u3_b; a.out = out;
+    a.in_item_stride = 100 * 100 * 8; a.out_item_stride = 200 * 200 * 8; a.H = 100;
+    return launch<M_UP3, 32>(a, n_items, st);
+}
+
+int pol_tc_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
+               cudaStream_t st) {
+    TcArgs a = {};
+    a.in = in; a.wt = p->w.u4_pw; a.bias = p->w.u4_pb; a.aux_w = p->w.u4_w; a.aux_b = p->w.u4_b;
+    a.ptr_out = ptr_out; a.amax_val = amax_val; a.amax_idx = amax_idx;
+    a.in_item_stride = 200 * 200 * 8; a.H = 200;
+    return launch<M_UP4, 16>(a, n_items, st);
+}
+
+int pol_tc_up4_parts() { return 200 / TC_R; }
