@@ -93,6 +93,18 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     // trunk
     fold_conv(wh->conv[0], 2, 8, w, b);
     up.add(&d.c1_w, w); up.add(&d.c1_b, b);
+    {
+        std::vector<float> lut((size_t)2 * 512 * 8, 0.f);
+        for (int ch = 0; ch < 2; ch++)
+            for (int pat = 0; pat < 512; pat++)
+                for (int co = 0; co < 8; co++) {
+                    float s = 0.f;
+                    for (int t = 0; t < 9; t++)
+                        if ((pat >> t) & 1) s += w[((size_t)t * 2 + ch) * 8 + co];
+                    lut[((size_t)ch * 512 + pat) * 8 + co] = s;
+                }
+        up.add(&d.c1_lut, lut);
+    }
     for (int l = 0; l < 3; l++) {
         fold_conv(wh->conv[l + 1], 8, 8, w, b);
         b.resize(16, 0.f);
@@ -188,8 +200,7 @@ extern "C" int ofb_policy_set_engine(ofb_policy *p, int engine) {
 // conv1 + BN + ReLU + pool straight from the bit maps: one thread per pooled pixel.
 __global__ void __launch_bounds__(256)
 k_trunk1_cc(const uint32_t *__restrict__ maps, PolicyDev w, __nv_bfloat16 *__restrict__ out) {
-    __shared__ float sw[144], sb[8];
-    for (int i = threadIdx.x; i < 144; i += blockDim.x) sw[i] = w.c1_w[i];
+    __shared__ float sb[8];
     if (threadIdx.x < 8) sb[threadIdx.x] = w.c1_b[threadIdx.x];
     __syncthreads();
     const int a = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -201,7 +212,7 @@ k_trunk1_cc(const uint32_t *__restrict__ maps, PolicyDev w, __nv_bfloat16 *__res
     if ((ps | pl) == 0) {
 #pragma unroll
         for (int co = 0; co < 8; co++) v[co] = fmaxf(sb[co], 0.f);
-    } else conv1_pool_pixel(ps, pl, sw, sb, v);
+    } else conv1_pool_pixel(ps, pl, w.c1_lut, sb, v);
     *reinterpret_cast<uint4 *>(out + ((size_t)a * 40000 + p) * 8) = pack_bf8(v);
 }
 
@@ -260,33 +271,51 @@ k_conv_pool_cc(const __nv_bfloat16 *__restrict__ in, const __nv_bfloat16 *__rest
     *reinterpret_cast<uint4 *>(out + (size_t)blockIdx.y * out_item_stride + (size_t)p * 8) = pack_bf8(o);
 }
 
-// dense1, flat slice: hflat[a][j] = sum_k flat[a][k] * Wf[k][j]   (8 arenas per block)
-__global__ void __launch_bounds__(128)
+// dense1, flat slice: hflat[a][j] = sum_k flat[a][k] * Wf[k][j].  4 arenas per block; 256 threads =
+// 128 output lanes (100 used) x 2 halves of every K tile, halves summed through shared memory.
+#define D1_ARENAS 4
+__global__ void __launch_bounds__(256)
 k_dense1_cc(const __nv_bfloat16 *__restrict__ flat, const __nv_bfloat16 *__restrict__ wf, float *__restrict__ hflat, int n_items) {
     constexpr int KT = 1000;
-    __shared__ float sf[8][KT];
-    const int a0 = blockIdx.x * 8, j = threadIdx.x;
-    float acc[8];
+    __shared__ __align__(16) float sf[D1_ARENAS][KT];
+    __shared__ float red[D1_ARENAS][128];
+    const int a0 = blockIdx.x * D1_ARENAS, j = threadIdx.x & 127, kh = threadIdx.x >> 7;
+    float acc[D1_ARENAS];
 #pragma unroll
-    for (int a = 0; a < 8; a++) acc[a] = 0.f;
+    for (int a = 0; a < D1_ARENAS; a++) acc[a] = 0.f;
     for (int k0 = 0; k0 < POL_FLAT; k0 += KT) {
         __syncthreads();
-        for (int i = threadIdx.x; i < 8 * KT; i += blockDim.x) {
+        for (int i = threadIdx.x; i < D1_ARENAS * KT; i += blockDim.x) {
             const int a = i / KT, k = i % KT;
             sf[a][k] = (a0 + a < n_items) ? bf2f(flat[(size_t)(a0 + a) * POL_FLAT_PITCH + k0 + k]) : 0.f;
         }
         __syncthreads();
         if (j < 100) {
-            for (int k = 0; k < KT; k++) {
-                const float wv = bf2f(wf[(size_t)(k0 + k) * 100 + j]);
+            const int kb = kh * (KT / 2);
+#pragma unroll 2
+            for (int k = kb; k < kb + KT / 2; k += 4) {
+                float wv[4];
 #pragma unroll
-                for (int a = 0; a < 8; a++) acc[a] += sf[a][k] * wv;
+                for (int q = 0; q < 4; q++) wv[q] = bf2f(wf[(size_t)(k0 + k + q) * 100 + j]);
+#pragma unroll
+                for (int a = 0; a < D1_ARENAS; a++) {
+                    const float4 f = *reinterpret_cast<const float4 *>(&sf[a][k]);
+                    acc[a] += f.x * wv[0];
+                    acc[a] += f.y * wv[1];
+                    acc[a] += f.z * wv[2];
+                    acc[a] += f.w * wv[3];
+                }
             }
         }
     }
-    if (j < 100)
-        for (int a = 0; a < 8; a++)
-            if (a0 + a < n_items) hflat[(size_t)(a0 + a) * 100 + j] = acc[a];
+    if (kh == 1) {
+#pragma unroll
+        for (int a = 0; a < D1_ARENAS; a++) red[a][j] = acc[a];
+    }
+    __syncthreads();
+    if (kh == 0 && j < 100)
+        for (int a = 0; a < D1_ARENAS; a++)
+            if (a0 + a < n_items) hflat[(size_t)(a0 + a) * 100 + j] = acc[a] + red[a][j];
 }
 
 // Everything between dense1's flat part and upconv3, per ship, in fp32 on CUDA cores:
@@ -392,11 +421,10 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
 __global__ void __launch_bounds__(128)
 k_up3_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, __nv_bfloat16 *__restrict__ out) {
     __shared__ float sw[9 * 32 * 4];                            // [tap][n][cin<4]
-    __shared__ float sb[32], rw[9 * 4 * 8], rb[8];
+    __shared__ float sb[32], rw[9 * 4 * 8];
     for (int i = threadIdx.x; i < 9 * 32 * 4; i += blockDim.x) sw[i] = bf2f(w.u3_pw[(size_t)(i / 4) * 8 + (i % 4)]);
     for (int i = threadIdx.x; i < 9 * 4 * 8; i += blockDim.x) rw[i] = w.u3_w[i];
     if (threadIdx.x < 32) sb[threadIdx.x] = w.u3_pb[threadIdx.x];
-    if (threadIdx.x < 8) rb[threadIdx.x] = w.u3_b[threadIdx.x];
     __syncthreads();
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= 100 * 100) return;
@@ -423,11 +451,9 @@ k_up3_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, __nv_bfloat16 *__res
     for (int ph = 0; ph < 4; ph++) {
         const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
         float o[8];
-        if (Y == 0 || Y == 199 || X == 0 || X == 199) up_ring_pixel<4, 8>(L, 100, Y, X, rw, rb, o);
-        else {
 #pragma unroll
-            for (int co = 0; co < 8; co++) o[co] = acc[ph * 8 + co];
-        }
+        for (int co = 0; co < 8; co++) o[co] = acc[ph * 8 + co];
+        if (Y == 0 || Y == 199 || X == 0 || X == 199) up_ring_correct<4, 8>(GlobalImage{L, 100}, 100, Y, X, rw, o);
 #pragma unroll
         for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
         *reinterpret_cast<uint4 *>(dst + ((size_t)Y * 200 + X) * 8) = pack_bf8(o);
@@ -443,7 +469,7 @@ k_up4_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, float *__restrict__ 
     for (int i = threadIdx.x; i < 9 * 4 * 8; i += blockDim.x) sw[i] = bf2f(w.u4_pw[(size_t)((i / 32) * 16 + (i / 8) % 4) * 8 + (i % 8)]);
     for (int i = threadIdx.x; i < 72; i += blockDim.x) rw[i] = w.u4_w[i];
     __syncthreads();
-    const float pb = w.u4_pb[0], rb = w.u4_b[0];
+    const float pb = w.u4_pb[0];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const __nv_bfloat16 *L = in + (size_t)blockIdx.y * 200 * 200 * 8;
     float bv = -INFINITY;
@@ -468,7 +494,7 @@ k_up4_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, float *__restrict__ 
         for (int ph = 0; ph < 4; ph++) {
             const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
             float o = acc[ph];
-            if (Y == 0 || Y == 399 || X == 0 || X == 399) up_ring_pixel<8, 1>(L, 200, Y, X, rw, &rb, &o);
+            if (Y == 0 || Y == 399 || X == 0 || X == 399) up_ring_correct<8, 1>(GlobalImage{L, 200}, 200, Y, X, rw, &o);
             const int idx = Y * 400 + X;
             if (ptr_out) ptr_out[(size_t)blockIdx.y * 160000 + idx] = o;
             if (amax_better(o, idx, bv, bi)) { bv = o; bi = idx; }
@@ -517,13 +543,13 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
         if ((rc = pol_tc_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc;
         if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc;
         if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc;
-        k_dense1_cc<<<(A + 7) / 8, 128, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
+        k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
     } else {
         k_trunk1_cc<<<dim3((40000 + 255) / 256, A), 256, 0, st>>>(maps, w, ws.pool1);
         k_conv_pool_cc<<<dim3((10000 + 127) / 128, A), 128, 0, st>>>(ws.pool1, w.cw[0], w.cb[0], ws.pool2, 200, 100 * 100 * 8);
         k_conv_pool_cc<<<dim3((2500 + 127) / 128, A), 128, 0, st>>>(ws.pool2, w.cw[1], w.cb[1], ws.pool3, 100, 50 * 50 * 8);
         k_conv_pool_cc<<<dim3((625 + 127) / 128, A), 128, 0, st>>>(ws.pool3, w.cw[2], w.cb[2], ws.flat, 50, POL_FLAT_PITCH);
-        k_dense1_cc<<<(A + 7) / 8, 128, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
+        k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
     }
     k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2);
     if (!xy && !ptr) { OFB_CUDA_CHECK(cudaGetLastError()); return OFB_OK; }

@@ -17,6 +17,7 @@ struct PolicyDev {
     // trunk
     float *c1_w;              // [9][2][8]  (tap, cin, cout)  fp32
     float *c1_b;              // [8]
+    float *c1_lut;            // [2][512][8] sums of c1_w over the set taps of a 9-bit stencil pattern
     __nv_bfloat16 *cw[3];     // conv2..4: [10][16][8] (tap, n = cout padded to 16, cin)  bf16
     float *cb[3];             // [16]
     // dense1

@@ -45,10 +45,14 @@ __device__ __forceinline__ uint32_t conv1_patch(const uint32_t *__restrict__ m, 
     return p;
 }
 
-// conv1 (3x3 'same', 2 -> 8, BN folded) + ReLU + 2x2 max-pool for one pooled pixel whose patch is
-// (ps, pl).  w = [9][2][8] fp32, b = [8].  Accumulation order: bias, then taps 0..8, ship channel
-// before laser channel.
-__device__ __forceinline__ void conv1_pool_pixel(uint32_t ps, uint32_t pl, const float *__restrict__ w,
+// conv1 (3x3 'same', 2 -> 8, BN folded) + ReLU + 2x2 max-pool for one pooled pixel whose 4x4 patch is
+// (ps, pl).  The input is binary, so the 3x3 x 1-channel stencil is a 9-bit pattern: lut[ch][pattern][co]
+// holds sum_{set taps} w[tap][ch][co] (fp32, summed in tap order on the host) and a conv output is
+// bias + lut[ship][pattern_s] + lut[laser][pattern_l].
+__device__ __forceinline__ uint32_t conv1_pattern(uint32_t p, int i, int j) {
+    return ((p >> (4 * i + j)) & 7u) | (((p >> (4 * (i + 1) + j)) & 7u) << 3) | (((p >> (4 * (i + 2) + j)) & 7u) << 6);
+}
+__device__ __forceinline__ void conv1_pool_pixel(uint32_t ps, uint32_t pl, const float *__restrict__ lut,
                                                  const float *__restrict__ b, float *out) {
 #pragma unroll
     for (int co = 0; co < 8; co++) out[co] = 0.0f;             // ReLU output >= 0
@@ -56,25 +60,13 @@ __device__ __forceinline__ void conv1_pool_pixel(uint32_t ps, uint32_t pl, const
     for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            float acc[8];
+            const float4 *ls = reinterpret_cast<const float4 *>(lut + (size_t)conv1_pattern(ps, i, j) * 8);
+            const float4 *ll = reinterpret_cast<const float4 *>(lut + (size_t)(512 + conv1_pattern(pl, i, j)) * 8);
+            const float4 s0 = __ldg(ls), s1 = __ldg(ls + 1), l0 = __ldg(ll), l1 = __ldg(ll + 1);
+            const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
-            for (int co = 0; co < 8; co++) acc[co] = b[co];
-#pragma unroll
-            for (int dy = 0; dy < 3; dy++)
-#pragma unroll
-                for (int dx = 0; dx < 3; dx++) {
-                    const int bit = 4 * (i + dy) + (j + dx), tap = dy * 3 + dx;
-                    if ((ps >> bit) & 1u) {
-#pragma unroll
-                        for (int co = 0; co < 8; co++) acc[co] += w[(tap * 2 + 0) * 8 + co];
-                    }
-                    if ((pl >> bit) & 1u) {
-#pragma unroll
-                        for (int co = 0; co < 8; co++) acc[co] += w[(tap * 2 + 1) * 8 + co];
-                    }
-                }
-#pragma unroll
-            for (int co = 0; co < 8; co++) out[co] = fmaxf(out[co], acc[co]);
+            for (int co = 0; co < 8; co++) out[co] = fmaxf(out[co], (b[co] + sv[co]) + lv[co]);
         }
 }
 
@@ -86,40 +78,55 @@ __device__ __forceinline__ void bil_tap(int Y, int n, int &lo, int &hi, float &w
     else { lo = max(i - 1, 0); hi = i; wlo = 0.25f; whi = 0.75f; }
 }
 
-// One output pixel (Y, X) of [bilinear x2 -> conv3x3 'same' (zero pad)] straight from the definition,
-// input L = [n][n][8] bf16 (CIN real channels), weights w = [9][CIN][COUT] fp32, bias [COUT].
-// Used for the 1-pixel border ring, where the zero padding of the upsampled map breaks the
-// phase-folded form.
-template <int CIN, int COUT>
-__device__ __forceinline__ void up_ring_pixel(const __nv_bfloat16 *__restrict__ L, int n, int Y, int X,
-                                              const float *__restrict__ w, const float *__restrict__ b, float *out) {
-#pragma unroll
-    for (int co = 0; co < COUT; co++) out[co] = b[co];
+// Border ring of [bilinear x2 -> conv3x3 'same'] in the phase-folded form.  The folded weights assume
+// the upsampled map continues past its border (replicate-extended low-res input), whereas the
+// convolution zero-pads it: for the output pixels on the 1-pixel ring, the contribution of the taps
+// that fall outside [0, 2n) must be taken back out:
+//     out_true = out_folded - sum_{(dy,dx) out of range} w[dy][dx] . U~[Y+dy-1][X+dx-1]
+// with U~ the same half-pixel interpolation evaluated on the replicate-extended input.
+// `L(y, x)` returns the 8 bf16 channels of low-res pixel (y, x) for y, x in [-1, n] (replicated).
+__device__ __forceinline__ void bil_tap_ext(int Y, int &lo, int &hi, float &wlo, float &whi) {
+    const int i = Y >> 1;                                   // arithmetic shift: -1 -> -1
+    if (Y & 1) { lo = i; hi = i + 1; wlo = 0.75f; whi = 0.25f; }
+    else { lo = i - 1; hi = i; wlo = 0.25f; whi = 0.75f; }
+}
+
+template <int CIN, int COUT, class Acc>
+__device__ __forceinline__ void up_ring_correct(const Acc &L, int n, int Y, int X, const float *__restrict__ w, float *v) {
     for (int dy = 0; dy < 3; dy++) {
         const int YY = Y + dy - 1;
-        if (YY < 0 || YY >= 2 * n) continue;
-        int ylo, yhi; float wyl, wyh;
-        bil_tap(YY, n, ylo, yhi, wyl, wyh);
         for (int dx = 0; dx < 3; dx++) {
             const int XX = X + dx - 1;
-            if (XX < 0 || XX >= 2 * n) continue;
-            int xlo, xhi; float wxl, wxh;
-            bil_tap(XX, n, xlo, xhi, wxl, wxh);
+            if (YY >= 0 && YY < 2 * n && XX >= 0 && XX < 2 * n) continue;
+            int ylo, yhi, xlo, xhi; float wyl, wyh, wxl, wxh;
+            bil_tap_ext(YY, ylo, yhi, wyl, wyh);
+            bil_tap_ext(XX, xlo, xhi, wxl, wxh);
             float a[8], c[8], d[8], e[8];
-            unpack_bf8(*reinterpret_cast<const uint4 *>(L + ((size_t)ylo * n + xlo) * 8), a);
-            unpack_bf8(*reinterpret_cast<const uint4 *>(L + ((size_t)ylo * n + xhi) * 8), c);
-            unpack_bf8(*reinterpret_cast<const uint4 *>(L + ((size_t)yhi * n + xlo) * 8), d);
-            unpack_bf8(*reinterpret_cast<const uint4 *>(L + ((size_t)yhi * n + xhi) * 8), e);
+            unpack_bf8(L(ylo, xlo), a);
+            unpack_bf8(L(ylo, xhi), c);
+            unpack_bf8(L(yhi, xlo), d);
+            unpack_bf8(L(yhi, xhi), e);
             const int tap = dy * 3 + dx;
 #pragma unroll
             for (int ci = 0; ci < CIN; ci++) {
                 const float u = wyl * (wxl * a[ci] + wxh * c[ci]) + wyh * (wxl * d[ci] + wxh * e[ci]);
 #pragma unroll
-                for (int co = 0; co < COUT; co++) out[co] += u * w[(tap * CIN + ci) * COUT + co];
+                for (int co = 0; co < COUT; co++) v[co] -= u * w[(tap * CIN + ci) * COUT + co];
             }
         }
     }
 }
+
+// accessor over a dense [n][n][8] bf16 image in global memory, replicate-clamped
+struct GlobalImage {
+    const __nv_bfloat16 *p;
+    int n;
+    __device__ __forceinline__ uint4 operator()(int y, int x) const {
+        y = min(max(y, 0), n - 1);
+        x = min(max(x, 0), n - 1);
+        return *reinterpret_cast<const uint4 *>(p + ((size_t)y * n + x) * 8);
+    }
+};
 
 // argmax ordering of np.argmax on the flat C-order map: larger value wins, ties -> lower index.
 __device__ __forceinline__ bool amax_better(float v, int i, float bv, int bi) { return v > bv || (v == bv && i < bi); }

@@ -94,11 +94,23 @@ __host__ __device__ inline TcPlan tc_plan(int mode, int N, int H) {
     p.sin_pixels = 128 * p.tiles + 2 * p.P + 8;
     p.off_sin = (unsigned)((POL_TAPS * N * 16 + 127) & ~127);
     p.off_stage = p.off_sin + (unsigned)p.sin_pixels * 16;
-    const unsigned stage = (mode == M_CONV_GMEM || mode == M_CONV_BITS) ? (unsigned)p.tiles * 128 * 16 : 0;
+    const unsigned stage = (mode == M_CONV_GMEM || mode == M_CONV_BITS) ? (unsigned)p.tiles * 128 * 16
+                                                                         : (unsigned)(4 * TC_R + 4 * H) * (mode == M_UP3 ? 32 : 4);   // ring buffer
     p.off_aux = p.off_stage + stage;
     p.off_bar = p.off_aux + 1280;                       // aux: up to 320 floats (conv1 / ring weights + bias)
     p.total = p.off_bar + 32;
     return p;
+}
+
+// low-res strip in shared memory as an image accessor (rows y0-1 .. y0+R, cols -1 .. W, replicated halo)
+struct StripImage {
+    const uint4 *sin;
+    int P, y0;
+    __device__ __forceinline__ uint4 operator()(int y, int x) const { return sin[(y - y0 + 1) * P + x + 1]; }
+};
+// slot of a ring pixel in the strip's ring buffer: left column, right column, then the top / bottom row by X
+__device__ __forceinline__ int ring_slot(int y_local, int X, int Wo) {
+    return X == 0 ? y_local : (X == Wo - 1 ? 2 * TC_R + y_local : 4 * TC_R + X);
 }
 
 template <int MODE, int N>
@@ -117,6 +129,7 @@ k_tc_conv(const TcArgs a) {
     uint4 *sw = reinterpret_cast<uint4 *>(smem);
     uint4 *sin = reinterpret_cast<uint4 *>(smem + pl.off_sin);
     uint4 *stage = reinterpret_cast<uint4 *>(smem + pl.off_stage);
+    float *ring = reinterpret_cast<float *>(smem + pl.off_stage);     // UP modes reuse the stage region
     float *aux = reinterpret_cast<float *>(smem + pl.off_aux);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + pl.off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + pl.off_bar + 16);
@@ -136,11 +149,11 @@ k_tc_conv(const TcArgs a) {
         for (int i = tid; i < POL_TAPS * N; i += 128) sw[i] = src[i];
     }
     if (MODE == M_CONV_BITS) {
-        for (int i = tid; i < 152; i += 128) aux[i] = i < 144 ? a.aux_w[i] : a.aux_b[i - 144];
+        if (tid < 8) aux[tid] = a.aux_b[tid];            // conv1 bias; its pattern LUT (a.aux_w) stays in global/L1
     } else if (MODE == M_UP3) {
-        for (int i = tid; i < 9 * 4 * 8 + 8; i += 128) aux[i] = i < 288 ? a.aux_w[i] : a.aux_b[i - 288];
+        for (int i = tid; i < 9 * 4 * 8; i += 128) aux[i] = a.aux_w[i];
     } else if (MODE == M_UP4) {
-        for (int i = tid; i < 73; i += 128) aux[i] = i < 72 ? a.aux_w[i] : a.aux_b[0];
+        for (int i = tid; i < 72; i += 128) aux[i] = a.aux_w[i];
     }
     float biasr[POOL ? 8 : (MODE == M_UP3 ? 32 : 4)];
 #pragma unroll
@@ -154,7 +167,7 @@ k_tc_conv(const TcArgs a) {
         const uint32_t *lmap = smap + POL_WORDS;
         float bg[8];
 #pragma unroll
-        for (int co = 0; co < 8; co++) bg[co] = fmaxf(aux[144 + co], 0.f);
+        for (int co = 0; co < 8; co++) bg[co] = fmaxf(aux[co], 0.f);
         const uint4 bgq = pack_bf8(bg);
         const int groups = W / 8;                        // 8 pooled pixels per work item
         for (int g = tid; g < rows_in * groups; g += 128) {
@@ -198,7 +211,7 @@ k_tc_conv(const TcArgs a) {
                 }
                 if ((ps | pq) == 0) { dst[k] = bgq; continue; }
                 float v[8];
-                conv1_pool_pixel(ps, pq, aux, aux + 144, v);
+                conv1_pool_pixel(ps, pq, a.aux_w, aux, v);
                 dst[k] = pack_bf8(v);
             }
         }
@@ -265,16 +278,18 @@ k_tc_conv(const TcArgs a) {
             const int rr = q / P, c = q % P;
             if (rr < TC_R && c < W) {
                 const int i = y0 + rr, j = c;
-                const __nv_bfloat16 *L = reinterpret_cast<const __nv_bfloat16 *>(a.in) + (size_t)item * a.in_item_stride;
                 __nv_bfloat16 *dst = a.out + (size_t)item * a.out_item_stride;
 #pragma unroll
                 for (int ph = 0; ph < 4; ph++) {
                     const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
                     float o[8];
-                    if (Y == 0 || Y == 2 * W - 1 || X == 0 || X == 2 * W - 1) up_ring_pixel<4, 8>(L, W, Y, X, aux, aux + 288, o);
-                    else {
 #pragma unroll
-                        for (int co = 0; co < 8; co++) o[co] = __uint_as_float(r[ph * 8 + co]) + biasr[ph * 8 + co];
+                    for (int co = 0; co < 8; co++) o[co] = __uint_as_float(r[ph * 8 + co]) + biasr[ph * 8 + co];
+                    if (Y == 0 || Y == 2 * W - 1 || X == 0 || X == 2 * W - 1) {      // ring: corrected after the tile loop
+                        float *rb = ring + 8 * ring_slot(Y - 2 * y0, X, 2 * W);
+#pragma unroll
+                        for (int co = 0; co < 8; co++) rb[co] = o[co];
+                        continue;
                     }
 #pragma unroll
                     for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
@@ -288,12 +303,11 @@ k_tc_conv(const TcArgs a) {
             const int rr = q / P, c = q % P;
             if (rr < TC_R && c < W) {
                 const int i = y0 + rr, j = c;
-                const __nv_bfloat16 *L = reinterpret_cast<const __nv_bfloat16 *>(a.in) + (size_t)item * a.in_item_stride;
 #pragma unroll
                 for (int ph = 0; ph < 4; ph++) {
                     const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
                     float o = __uint_as_float(r[ph]) + biasr[ph];
-                    if (Y == 0 || Y == 2 * W - 1 || X == 0 || X == 2 * W - 1) up_ring_pixel<8, 1>(L, W, Y, X, aux, aux + 72, &o);
+                    if (Y == 0 || Y == 2 * W - 1 || X == 0 || X == 2 * W - 1) { ring[ring_slot(Y - 2 * y0, X, 2 * W)] = o; continue; }
                     const int idx = Y * 2 * W + X;
                     if (a.ptr_out) a.ptr_out[(size_t)item * 4 * W * W + idx] = o;
                     if (amax_better(o, idx, best_v, best_i)) { best_v = o; best_i = idx; }
@@ -305,6 +319,37 @@ k_tc_conv(const TcArgs a) {
         tc_fence_after();
     }
 
+    if (REPL) {
+        // border ring: take the out-of-range taps back out of the folded result, then consume the pixel
+        const int Wo = 2 * W, nslots = 4 * TC_R + Wo;
+        const bool first = blockIdx.x == 0, last = blockIdx.x == gridDim.x - 1;
+        const StripImage Ls{sin, P, y0};
+        for (int slot = tid; slot < nslots; slot += 128) {
+            int Y, X;
+            if (slot < 2 * TC_R) { Y = 2 * y0 + slot; X = 0; }
+            else if (slot < 4 * TC_R) { Y = 2 * y0 + slot - 2 * TC_R; X = Wo - 1; }
+            else {
+                X = slot - 4 * TC_R;
+                if (!(first || last) || X == 0 || X == Wo - 1) continue;
+                Y = first ? 0 : Wo - 1;
+            }
+            if (MODE == M_UP3) {
+                float o[8];
+#pragma unroll
+                for (int co = 0; co < 8; co++) o[co] = ring[8 * slot + co];
+                up_ring_correct<4, 8>(Ls, W, Y, X, aux, o);
+#pragma unroll
+                for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
+                *reinterpret_cast<uint4 *>(a.out + (size_t)item * a.out_item_stride + ((size_t)Y * Wo + X) * 8) = pack_bf8(o);
+            } else {
+                float o = ring[slot];
+                up_ring_correct<8, 1>(Ls, W, Y, X, aux, &o);
+                const int idx = Y * Wo + X;
+                if (a.ptr_out) a.ptr_out[(size_t)item * Wo * Wo + idx] = o;
+                if (amax_better(o, idx, best_v, best_i)) { best_v = o; best_i = idx; }
+            }
+        }
+    }
     if (POOL) {
         const int wo = W / 2;
         __nv_bfloat16 *dst = a.out + (size_t)item * a.out_item_stride;
@@ -368,7 +413,7 @@ int pol_tc_conv_pool(const ofb_policy *p, int layer, const __nv_bfloat16 *in, __
 
 int pol_tc_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
     TcArgs a = {};
-    a.in = maps; a.wt = p->w.cw[0]; a.bias = p->w.cb[0]; a.aux_w = p->w.c1_w; a.aux_b = p->w.c1_b; a.out = out;
+    a.in = maps; a.wt = p->w.cw[0]; a.bias = p->w.cb[0]; a.aux_w = p->w.c1_lut; a.aux_b = p->w.c1_b; a.out = out;
     a.out_item_stride = 100 * 100 * 8; a.H = 200;
     return launch<M_CONV_BITS, 16>(a, n_items, st);
 }

@@ -1,0 +1,40 @@
+"""Policy forward timings (CUDA events): python scripts/pbench.py [n_arenas] [engine ...]"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ofighters_b200 import BatchedBattleground  # noqa: E402
+from ofighters_b200.policy import PolicyB200  # noqa: E402
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+    engines = sys.argv[2:] or ["tensor", "cuda_core"]
+    bg = BatchedBattleground(n, ships={"random": 7}, seed=5)
+    for _ in range(30):
+        bg.frame()
+    maps = bg.raster("bits")
+    vec = bg.obs_vec[:, 0, :].contiguous()
+    pol = PolicyB200.random_init(device=bg.device, seed=0, max_ships=1024)
+    for eng in engines:
+        pol.set_engine(eng)
+        for _ in range(2):
+            pol.forward_argmax(maps, vec)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        iters = 3
+        a.record()
+        for _ in range(iters):
+            pol.forward_argmax(maps, vec)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / iters
+        print(json.dumps({"engine": eng, "n_arenas": n, "ms_per_forward_batch": ms, "forwards_per_s": n / ms * 1e3,
+                          "dense_equiv_TFLOPs": n * 155.3e6 / (ms * 1e-3) / 1e12}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
