@@ -176,28 +176,30 @@ def gpu_arm(args, wl):
     policy = None
     if wl["policy"]:
         from ofighters_b200.policy import PolicyB200
-        policy = PolicyB200.random_init(device=dev, seed=0)
+        policy = PolicyB200.random_init(device=dev, seed=0, max_ships=8192)
     maps = torch.empty((N, 2, 400 * 400 // 32), dtype=torch.int32, device=dev)
+    bg.raster("bits", out=maps)
     state_bytes = N * bg.state_stride
     flush_needed = state_bytes + maps.numel() * 4 < 2 * 126 * 2 ** 20
     flush_buf = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev) if flush_needed else None
     launches = [0]
 
     def one_step():
-        n0 = bg.launch_count
+        n0 = bg.launch_count + (policy.launch_count if policy is not None else 0)
         if bg.time >= max_time:
             bg.restart()
             if world > 1:
                 dist.all_reduce(bg.stats)          # K7: per-episode [score, kills, deaths, shots, ships, arenas]
+            if policy is not None:
+                bg.raster("bits", out=maps)        # Battleground.restart builds a fresh Observation
         if policy is not None:
-            bg.request_actions()
-            bg.raster("bits", out=maps) if bg.total_steps == 0 else None
-            policy.act(bg, maps)                   # writes ship 0's action rows from the forward's argmax
+            bg.request_actions()                   # scripted bots fill their rows; policy rows are "external"
+            policy.act(bg, maps)                   # forward on the current maps -> the policy ship's action row
             bg.generate_frame()
         else:
             bg.frame()
         bg.raster("bits", out=maps)
-        launches[0] += bg.launch_count - n0 + (policy.launches_per_forward if policy is not None else 0)
+        launches[0] += bg.launch_count + (policy.launch_count if policy is not None else 0) - n0
 
     stream = torch.cuda.current_stream(dev)
     for _ in range(warmup):
@@ -234,10 +236,10 @@ def gpu_arm(args, wl):
     value = N * world * steps / (total_ms * 1e-3)
 
     # ---- dominant kernel alone (raster for the arena workloads), same events + flush
-    roof = kernel_roofline(bg, maps, flush_buf, wl, dev)
+    roof = kernel_roofline(bg, maps, flush_buf, wl, dev, policy)
 
     # ---- end-to-end through the public API with HOST buffers
-    e2e = e2e_arm(bg, maps, wl, dev, min(steps, 400), world)
+    e2e = e2e_arm(bg, maps, wl, dev, min(steps, 400 if policy is None else 20), world, policy)
 
     out = {
         "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster%s)" %
@@ -268,9 +270,12 @@ def gpu_arm(args, wl):
         dist.destroy_process_group()
 
 
-def kernel_roofline(bg, maps, flush_buf, wl, dev, iters=50):
-    """Dominant kernel of the arena workloads = the raster (it writes >95 % of the step's bytes).
-    achieved = algorithmic bytes (the tensor it must produce: N * 2 * W*H/8) / mean launch time."""
+def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
+    """Dominant kernel of the arena workloads = the raster (it writes >95 % of the step's bytes):
+    achieved = algorithmic bytes (the tensor it must produce: N * 2 * W*H/8) / mean launch time.
+    Policy workloads: the dominant kernel is the phase-folded upconv4 + argmax (tcgen05); achieved =
+    its algorithmic FLOPs (2 * 400*400*72 per ship, Appendix B) / its mean launch time, against the
+    measured bf16 tensor peak; the whole forward is reported beside it in dense-equivalent FLOPs."""
     import torch
     peaks = {}
     try:
@@ -280,6 +285,28 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, iters=50):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     stream = torch.cuda.current_stream(dev)
+    if policy is not None:
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        vec = bg.obs_vec[:, 0, :].contiguous()
+        policy.profile(True)
+        for _ in range(3):
+            policy.forward_argmax(maps, vec)
+        prof = policy.profile(False)                      # {layer: ms per forward of the whole batch}
+        n = bg.n_arenas
+        fl = {"trunk12": 2 * (23.04e6 + 23.04e6), "conv3": 2 * 5.76e6, "conv4": 2 * 1.44e6, "dense1": 2 * 0.5e6,
+              "heads": 2 * (5.1e3 + 62.5e3 + 45e3 + 720e3 + 800), "up3": 2 * 11.52e6, "up4": 2 * 11.52e6, "argmax": 0.0}
+        layers = {k: {"ms": v, "alg_tflops": fl.get(k, 0.0) * n / (v * 1e-3) / 1e12 if v > 0 else None}
+                  for k, v in prof.items()}
+        dom = max(prof, key=prof.get)
+        total = sum(prof.values())
+        return {"bound": "tensor", "kernel": "k_tc_conv<%s>" % dom, "achieved": layers[dom]["alg_tflops"], "peak": tpeak,
+                "unit": "TFLOP/s", "frac": layers[dom]["alg_tflops"] / tpeak,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM loop)" if peaks else "fallback",
+                "traffic": None, "us_per_launch": prof[dom] * 1e3 / max(1, -(-n // policy.max_ships)),
+                "whole_forward": {"ms": total, "forwards_per_s": n / (total * 1e-3),
+                                  "dense_equiv_tflops": 155.3e6 * n / (total * 1e-3) / 1e12,
+                                  "frac_of_peak": 155.3e6 * n / (total * 1e-3) / 1e12 / tpeak},
+                "layers": layers}
     res = {}
     for name, fn, nbytes in (("k_raster", lambda: bg.raster("bits", out=maps), maps.numel() * 4),
                              ("k_step", lambda: bg.generate_frame(), bg.algorithmic_step_bytes)):
@@ -305,7 +332,7 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, iters=50):
             "other_kernels": {"k_step": res["k_step"]}}
 
 
-def e2e_arm(bg, maps, wl, dev, steps, world):
+def e2e_arm(bg, maps, wl, dev, steps, world, policy=None):
     """Same metric through BatchedBattleground with HOST buffers: every step the host bot's action
     tensor is copied from pinned memory, the step + raster run, and the per-ship observation heads
     (what a host bot is shown, incl. its reward) are read back.  Maps stay in HBM for the policy."""
@@ -335,7 +362,16 @@ def e2e_arm(bg, maps, wl, dev, steps, world):
             act_np[..., 2:] = np.where(rep, newp[t], obs_np[..., 2:4].astype(np.int16))
         if bg.time >= 200:
             bg.restart()
-        bg.step_host(act_host, obs_host)                    # H2D actions, K1, D2H obs heads (synchronises)
+            if policy is not None:
+                bg.raster("bits", out=maps)
+        if policy is None:
+            bg.step_host(act_host, obs_host)                # H2D actions, K1, D2H obs heads (synchronises)
+        else:
+            bg.actions.copy_(act_host, non_blocking=True)   # host bots' rows
+            policy.act(bg, maps)                            # policy ship's row from the forward
+            bg.generate_frame()
+            obs_host.copy_(bg.obs_vec, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
         bg.raster("bits", out=maps)
 
     for k in range(3):

@@ -84,6 +84,11 @@ int ofb_policy_write_actions(const int32_t *iaction_dev, const int32_t *xy_dev, 
  * predict([img, vec]) callers that hold Keras-style images.  A pixel is set iff it is non-zero. */
 int ofb_policy_pack_image(const void *img_dev, int fmt, int64_t n, uint32_t *maps_bits_dev, void *stream);
 
+/* Per-layer device times (measurement aid): enable = 1 brackets every kernel of the following forward
+ * calls with CUDA events; enable = 0 stops, synchronises and writes the accumulated milliseconds per
+ * layer to ms_out[8] = (trunk12, conv3, conv4, dense1, heads, up3, up4, argmax). */
+int ofb_policy_profile(ofb_policy *p, int enable, float *ms_out);
+
 /* Debug / validation tap: copies the first n_items entries of an intermediate activation of the
  * LAST forward call's first chunk into dst_dev (device, n_items * stride elements).
  * which (stride in elements): 0 pool1 [200,200,8] (320000, cuda-core engine only), 1 pool2 [100,100,8]

@@ -92,6 +92,8 @@ def load():
     lib.ofb_policy_write_actions.argtypes = [vp, vp, i64, i32, vp, i32, C.c_float, u64, i64, u32, vp, vp]
     lib.ofb_policy_pack_image.argtypes = [vp, i32, i64, vp, vp]
     lib.ofb_policy_debug_tap.argtypes = [vp, i32, i64, vp, vp]
+    lib.ofb_policy_profile.argtypes = [vp, i32, vp]
+    lib.ofb_policy_profile.restype = i32
     for name in ("ofb_policy_create", "ofb_policy_destroy", "ofb_policy_set_engine", "ofb_policy_forward",
                  "ofb_policy_write_actions", "ofb_policy_pack_image", "ofb_policy_debug_tap"):
         getattr(lib, name).restype = i32

@@ -8,6 +8,9 @@
 #include "ofb_common.cuh"
 #include "ofb_policy_dev.cuh"
 
+struct ProfEvent { cudaEvent_t a, b; int layer; };
+enum { L_TRUNK12 = 0, L_CONV3, L_CONV4, L_DENSE1, L_HEADS, L_UP3, L_UP4, L_ARGMAX, L_COUNT };
+
 // ------------------------------------------------------------------------------------------------
 // host-side folding (BN into conv, bilinear x2 into 4 output phases) and upload
 // ------------------------------------------------------------------------------------------------
@@ -86,6 +89,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     p->device = device;
     p->max_ships = max_ships;
     p->engine = OFB_ENGINE_TENSOR;
+    p->prof = new std::vector<ProfEvent>();
 
     Uploader up;
     PolicyDev &d = p->w;
@@ -181,7 +185,32 @@ extern "C" int ofb_policy_destroy(ofb_policy *p) {
     cudaSetDevice(p->device);
     cudaFree(p->arena_blob);
     cudaFree(p->work_blob);
+    if (p->prof) {
+        for (auto &e : *static_cast<std::vector<ProfEvent> *>(p->prof)) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+        delete static_cast<std::vector<ProfEvent> *>(p->prof);
+    }
     delete p;
+    return OFB_OK;
+}
+
+// Per-layer device times: enable = 1 starts collecting (CUDA events around every kernel of forward);
+// enable = 0 stops, synchronises and returns the accumulated milliseconds per layer in ms_out[8]
+// (trunk12, conv3, conv4, dense1, heads, up3, up4, argmax) together with the number of forward calls' chunks.
+extern "C" int ofb_policy_profile(ofb_policy *p, int enable, float *ms_out) {
+    if (!p) { ofb_set_error("ofb_policy_profile: null handle"); return OFB_E_ARG; }
+    auto *v = static_cast<std::vector<ProfEvent> *>(p->prof);
+    if (enable) { p->profiling = 1; return OFB_OK; }
+    p->profiling = 0;
+    OFB_CUDA_CHECK(cudaDeviceSynchronize());
+    float acc[L_COUNT] = {0};
+    for (auto &e : *v) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e.a, e.b);
+        acc[e.layer] += ms;
+        cudaEventDestroy(e.a); cudaEventDestroy(e.b);
+    }
+    v->clear();
+    if (ms_out) for (int i = 0; i < L_COUNT; i++) ms_out[i] = acc[i];
     return OFB_OK;
 }
 
@@ -532,6 +561,18 @@ __global__ void k_argmax_final(const float *__restrict__ val, const int *__restr
 // ------------------------------------------------------------------------------------------------
 // orchestration
 // ------------------------------------------------------------------------------------------------
+struct ProfScope {
+    ofb_policy *p; cudaStream_t st; cudaEvent_t a; int layer;
+    ProfScope(ofb_policy *p_, int layer_, cudaStream_t st_) : p(p_), st(st_), a(nullptr), layer(layer_) {
+        if (p->profiling) { cudaEventCreate(&a); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (p->profiling) {
+            cudaEvent_t b; cudaEventCreate(&b); cudaEventRecord(b, st);
+            static_cast<std::vector<ProfEvent> *>(p->prof)->push_back({a, b, layer});
+        }
+    }
+};
 static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, int A, int P, float *act, float *ptr, int32_t *iact,
                          int32_t *xy, cudaStream_t st) {
     const PolicyDev &w = p->w;
@@ -540,30 +581,34 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     const bool tc = p->engine == OFB_ENGINE_TENSOR;
     int rc;
     if (tc) {
-        if ((rc = pol_tc_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc;
-        if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc;
-        if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc;
-        k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
+        { ProfScope ps(p, L_TRUNK12, st); if ((rc = pol_tc_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc; }
+        { ProfScope ps(p, L_CONV3, st); if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc; }
+        { ProfScope ps(p, L_CONV4, st); if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc; }
     } else {
-        k_trunk1_cc<<<dim3((40000 + 255) / 256, A), 256, 0, st>>>(maps, w, ws.pool1);
-        k_conv_pool_cc<<<dim3((10000 + 127) / 128, A), 128, 0, st>>>(ws.pool1, w.cw[0], w.cb[0], ws.pool2, 200, 100 * 100 * 8);
-        k_conv_pool_cc<<<dim3((2500 + 127) / 128, A), 128, 0, st>>>(ws.pool2, w.cw[1], w.cb[1], ws.pool3, 100, 50 * 50 * 8);
-        k_conv_pool_cc<<<dim3((625 + 127) / 128, A), 128, 0, st>>>(ws.pool3, w.cw[2], w.cb[2], ws.flat, 50, POL_FLAT_PITCH);
-        k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A);
+        { ProfScope ps(p, L_TRUNK12, st);
+          k_trunk1_cc<<<dim3((40000 + 255) / 256, A), 256, 0, st>>>(maps, w, ws.pool1);
+          k_conv_pool_cc<<<dim3((10000 + 127) / 128, A), 128, 0, st>>>(ws.pool1, w.cw[0], w.cb[0], ws.pool2, 200, 100 * 100 * 8); }
+        { ProfScope ps(p, L_CONV3, st);
+          k_conv_pool_cc<<<dim3((2500 + 127) / 128, A), 128, 0, st>>>(ws.pool2, w.cw[1], w.cb[1], ws.pool3, 100, 50 * 50 * 8); }
+        { ProfScope ps(p, L_CONV4, st);
+          k_conv_pool_cc<<<dim3((625 + 127) / 128, A), 128, 0, st>>>(ws.pool3, w.cw[2], w.cb[2], ws.flat, 50, POL_FLAT_PITCH); }
     }
-    k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2);
+    { ProfScope ps(p, L_DENSE1, st);
+      k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A); }
+    { ProfScope ps(p, L_HEADS, st);
+      k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2); }
     if (!xy && !ptr) { OFB_CUDA_CHECK(cudaGetLastError()); return OFB_OK; }
     int parts;
     if (tc) {
-        if ((rc = pol_tc_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc;
-        if ((rc = pol_tc_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc;
+        { ProfScope ps(p, L_UP3, st); if ((rc = pol_tc_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc; }
+        { ProfScope ps(p, L_UP4, st); if ((rc = pol_tc_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc; }
         parts = pol_tc_up4_parts();
     } else {
-        k_up3_cc<<<dim3((10000 + 127) / 128, S), 128, 0, st>>>(ws.up2, w, ws.up3);
+        { ProfScope ps(p, L_UP3, st); k_up3_cc<<<dim3((10000 + 127) / 128, S), 128, 0, st>>>(ws.up2, w, ws.up3); }
         parts = (40000 + 255) / 256;
-        k_up4_cc<<<dim3(parts, S), 256, 0, st>>>(ws.up3, w, ptr, ws.amax_val, ws.amax_idx);
+        { ProfScope ps(p, L_UP4, st); k_up4_cc<<<dim3(parts, S), 256, 0, st>>>(ws.up3, w, ptr, ws.amax_val, ws.amax_idx); }
     }
-    if (xy) k_argmax_final<<<(S * 32 + 127) / 128, 128, 0, st>>>(ws.amax_val, ws.amax_idx, parts, S, xy);
+    if (xy) { ProfScope ps(p, L_ARGMAX, st); k_argmax_final<<<(S * 32 + 127) / 128, 128, 0, st>>>(ws.amax_val, ws.amax_idx, parts, S, xy); }
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

@@ -59,6 +59,8 @@ struct ofb_policy {
     int engine;
     PolicyDev w;
     PolicyWork ws;
+    int profiling;            // when set, forward brackets every kernel with CUDA events
+    void *prof;               // std::vector<ProfEvent>*
     void *arena_blob;         // single allocation holding all weights
     void *work_blob;          // single allocation holding the workspace
 };

@@ -56,7 +56,7 @@ def _ptr(t):
 
 
 class PolicyB200:
-    launches_per_forward = 9      # kernels one chunk of a forward launches (tensor engine)
+    KERNELS_PER_CHUNK = 8         # trunk12, conv3, conv4, dense1, heads, up3, up4, argmax
 
     def __init__(self, weights, device=None, max_ships=1024):
         if not torch.cuda.is_available():
@@ -66,6 +66,7 @@ class PolicyB200:
         self._lib = _lib.load()
         self.max_ships = int(max_ships)
         self._h = None
+        self.launch_count = 0         # kernels of libofb launched by this object so far
         self.act_values = None        # Trainer.act_values / ptr_values of the last predict (qlearnIA_V2.py:214-215)
         self.ptr_values = None
         self.load_weights(weights)
@@ -109,6 +110,20 @@ class PolicyB200:
         """"tensor" (tcgen05, default) or "cuda_core" (same arithmetic on CUDA cores; validation twin)."""
         _lib.check(self._lib.ofb_policy_set_engine(self._h, {"tensor": 0, "cuda_core": 1}[name]))
 
+    LAYERS = ("trunk12", "conv3", "conv4", "dense1", "heads", "up3", "up4", "argmax")
+
+    def profile(self, enable):
+        """enable=True: start bracketing every kernel with CUDA events.  enable=False: stop and return
+        {layer: milliseconds per forward call} averaged over the calls made in between."""
+        if enable:
+            self._prof_calls = 0
+            _lib.check(self._lib.ofb_policy_profile(self._h, 1, None))
+            return None
+        ms = (C.c_float * 8)()
+        _lib.check(self._lib.ofb_policy_profile(self._h, 0, ms))
+        calls = max(1, getattr(self, "_prof_calls", 1))
+        return {k: float(ms[i]) / calls for i, k in enumerate(self.LAYERS)}
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
@@ -138,6 +153,9 @@ class PolicyB200:
         xy = torch.empty((n, 2), dtype=torch.int32, device=self.device) if want_argmax else None
         _lib.check(self._lib.ofb_policy_forward(self._h, _ptr(maps_bits), _ptr(vec), A, ships_per_arena, _ptr(act),
                                                 _ptr(ptr), _ptr(iact), _ptr(xy), self._stream()))
+        self._prof_calls = getattr(self, "_prof_calls", 0) + 1
+        per_chunk = max(1, self.max_ships // ships_per_arena)
+        self.launch_count += self.KERNELS_PER_CHUNK * ((A + per_chunk - 1) // per_chunk)
         return {"act": act, "ptr": ptr, "iaction": iact, "xy": xy}
 
     def forward_argmax(self, maps_bits, vec, ships_per_arena=1):
@@ -190,6 +208,7 @@ class PolicyB200:
         _lib.check(self._lib.ofb_policy_write_actions(_ptr(iact), _ptr(xy), bg.n_arenas, P, _ptr(idx), bg.ships_number,
                                                       float(epsilon), bg.seed, bg.arena0, bg.total_steps, _ptr(bg.actions),
                                                       self._stream()))
+        self.launch_count += 1
         return iact, xy
 
     _TAP_STRIDE = {0: 320000, 1: 80000, 2: 20000, 3: 5120, 4: 100, 5: 80000, 6: 320000}
