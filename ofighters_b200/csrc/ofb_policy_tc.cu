@@ -14,12 +14,16 @@
 //   upconv4   : 4 phases of the single output channel: + bias -> running argmax (+ optional dense map)
 // conv1 never touches HBM: its pooled output is generated straight into conv2's shared-memory strip
 // from the bit maps (background constant + exact evaluation near set bits).
-// Double-buffered TMEM accumulators let the MMAs of tile t+1 run under the epilogue of tile t.
+// The input rows reach shared memory as bulk asynchronous copies (cp.async.bulk + mbarrier); a ring of 8
+// TMEM accumulators keeps at least 4 tiles of MMAs queued while the four warps drain completed tiles.
 #include "ofb_common.cuh"
 #include "ofb_policy_dev.cuh"
 
 enum { M_CONV_GMEM = 0, M_CONV_BITS = 1, M_UP3 = 2, M_UP4 = 3 };
 #define TC_R 10                       // image rows per strip (all layer heights are multiples of 10)
+#define TC_NT 256                     // threads per CTA: two warps per TMEM lane quarter, draining alternate tiles
+#define TC_RING 8                     // TMEM accumulators (tiles in flight) per CTA
+#define TC_BITS_WORDS 352             // words of one bit map staged per strip: 27 rows x 50 B + alignment slack
 
 struct TcArgs {
     const void *in;                   // bf16 [item][H][H][8], or uint32 bit maps [item][2][5000]
@@ -49,6 +53,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bulk asynchronous copy global -> shared (TMA-class, no tensor map), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -94,11 +107,12 @@ __host__ __device__ inline TcPlan tc_plan(int mode, int N, int H) {
     p.sin_pixels = 128 * p.tiles + 2 * p.P + 8;
     p.off_sin = (unsigned)((POL_TAPS * N * 16 + 127) & ~127);
     p.off_stage = p.off_sin + (unsigned)p.sin_pixels * 16;
-    const unsigned stage = (mode == M_CONV_GMEM || mode == M_CONV_BITS) ? (unsigned)p.tiles * 128 * 16
+    const unsigned stage = (mode == M_CONV_GMEM || mode == M_CONV_BITS) ? (unsigned)(TC_R * p.P) * 16      // (BITS: also holds the bit rows first)
                                                                          : (unsigned)(4 * TC_R + 4 * H) * (mode == M_UP3 ? 32 : 4);   // ring buffer
     p.off_aux = p.off_stage + stage;
-    p.off_bar = p.off_aux + 1280;                       // aux: up to 320 floats (conv1 / ring weights + bias)
-    p.total = p.off_bar + 32;
+    // aux: ring weights (<= 288 floats) + argmax scratch, or conv1 bias + the strip's bit rows of both maps
+    p.off_bar = p.off_aux + (mode == M_CONV_BITS ? 64 : 1280);
+    p.total = p.off_bar + (TC_RING + 1) * 8 + 16;       // accumulator-ring mbarriers + load barrier + TMEM slot
     return p;
 }
 
@@ -114,12 +128,11 @@ __device__ __forceinline__ int ring_slot(int y_local, int X, int Wo) {
 }
 
 template <int MODE, int N>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(TC_NT)
 k_tc_conv(const TcArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr bool REPL = (MODE == M_UP3 || MODE == M_UP4);
     constexpr bool POOL = (MODE == M_CONV_GMEM || MODE == M_CONV_BITS);
-    constexpr uint32_t TMEM_COLS = (2 * N <= 32) ? 32 : 64;
     const int W = a.H;
     const TcPlan pl = tc_plan(MODE, N, W);
     const int P = pl.P, T = pl.tiles;
@@ -132,50 +145,91 @@ k_tc_conv(const TcArgs a) {
     float *ring = reinterpret_cast<float *>(smem + pl.off_stage);     // UP modes reuse the stage region
     float *aux = reinterpret_cast<float *>(smem + pl.off_aux);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + pl.off_bar);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + pl.off_bar + 16);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + pl.off_bar + (TC_RING + 1) * 8);
 
-    // ---- one-time setup: TMEM, barriers, weights
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-    }
-    if (tid == 32) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+    // ---- one-time setup: barriers, bulk copies of the input rows, weights
+    uint64_t *lbar = &bars[TC_RING];                     // completion of the bulk (TMA-class) row copies
+    const int rows_in = TC_R + 2;
+    const uint8_t *in_item = reinterpret_cast<const uint8_t *>(a.in) +
+                             (MODE == M_CONV_BITS ? (size_t)item * 2 * POL_WORDS * 4 : (size_t)item * a.in_item_stride * 2);
+    uint32_t *sbits = reinterpret_cast<uint32_t *>(smem + pl.off_stage);  // BITS: 2 x TC_BITS_WORDS words of the two maps (dead before the epilogue)
+    int bits_w0 = 0;                                     // first map word held in sbits
+    if (MODE == M_CONV_BITS) {
+        const int r0 = max(2 * y0 - 3, 0), r1 = min(2 * (y0 + TC_R) + 2, POL_W - 1);
+        bits_w0 = ((r0 * 50) & ~15) >> 2;                // rows are 50 B; bulk copies move 16 B units
+        if (tid == 32) {
+            const int b0 = bits_w0 * 4, b1 = min(((r1 + 1) * 50 + 15 + 16) & ~15, POL_WORDS * 4);
+            for (int t = 0; t <= TC_RING; t++) mbar_init(&bars[t], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            mbar_expect_tx(lbar, 2u * (uint32_t)(b1 - b0));
+            bulk_g2s(sbits, in_item + b0, (uint32_t)(b1 - b0), lbar);
+            bulk_g2s(sbits + TC_BITS_WORDS, in_item + POL_WORDS * 4 + b0, (uint32_t)(b1 - b0), lbar);
+        }
+    } else if (tid == 32) {
+        for (int t = 0; t <= TC_RING; t++) mbar_init(&bars[t], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        int nrows = 0;
+        for (int ry = 0; ry < rows_in; ry++) {
+            const int y = y0 - 1 + ry;
+            nrows += (REPL || (y >= 0 && y < W)) ? 1 : 0;
+        }
+        mbar_expect_tx(lbar, (uint32_t)(nrows * W * 16));
+        for (int ry = 0; ry < rows_in; ry++) {
+            int y = y0 - 1 + ry;
+            if (!REPL && (y < 0 || y >= W)) continue;
+            y = min(max(y, 0), W - 1);
+            bulk_g2s(sin + ry * P + 1, in_item + (size_t)y * W * 16, (uint32_t)(W * 16), lbar);
+        }
     }
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.wt);
-        for (int i = tid; i < POL_TAPS * N; i += 128) sw[i] = src[i];
+        for (int i = tid; i < POL_TAPS * N; i += TC_NT) sw[i] = src[i];
     }
     if (MODE == M_CONV_BITS) {
         if (tid < 8) aux[tid] = a.aux_b[tid];            // conv1 bias; its pattern LUT (a.aux_w) stays in global/L1
     } else if (MODE == M_UP3) {
-        for (int i = tid; i < 9 * 4 * 8; i += 128) aux[i] = a.aux_w[i];
+        for (int i = tid; i < 9 * 4 * 8; i += TC_NT) aux[i] = a.aux_w[i];
     } else if (MODE == M_UP4) {
-        for (int i = tid; i < 72; i += 128) aux[i] = a.aux_w[i];
+        for (int i = tid; i < 72; i += TC_NT) aux[i] = a.aux_w[i];
     }
     float biasr[POOL ? 8 : (MODE == M_UP3 ? 32 : 4)];
 #pragma unroll
     for (int i = 0; i < (int)(sizeof(biasr) / sizeof(float)); i++) biasr[i] = a.bias[i];
 
-    // ---- stage the input strip: rows y0-1 .. y0+R, columns -1 .. W (halo pixels zero or replicated)
-    const int rows_in = TC_R + 2;
-    if (MODE == M_CONV_BITS) __syncthreads();            // aux (conv1 weights) is read below
+    // ---- halo pixels, out-of-image rows and the tail (generic stores; the rows themselves arrive by bulk copy)
+    if (MODE != M_CONV_BITS) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(in_item);
+        for (int i = tid; i < rows_in * 2; i += TC_NT) {
+            const int ry = i >> 1, right = i & 1;
+            const int y = min(max(y0 - 1 + ry, 0), W - 1);
+            if (REPL) sin[ry * P + (right ? P - 1 : 0)] = src[(size_t)y * W + (right ? W - 1 : 0)];
+            else if (!right) sin[ry * P] = make_uint4(0, 0, 0, 0);
+        }
+        if (!REPL)
+            for (int ry = 0; ry < rows_in; ry += rows_in - 1) {           // only the first / last staged row can be outside
+                const int y = y0 - 1 + ry;
+                if (y >= 0 && y < W) continue;
+                for (int c = tid; c < W; c += TC_NT) sin[ry * P + 1 + c] = make_uint4(0, 0, 0, 0);
+            }
+    }
+    for (int i = rows_in * P + tid; i < pl.sin_pixels; i += TC_NT) sin[i] = make_uint4(0, 0, 0, 0);
+
     if (MODE == M_CONV_BITS) {
-        const uint32_t *smap = reinterpret_cast<const uint32_t *>(a.in) + (size_t)item * 2 * POL_WORDS;
-        const uint32_t *lmap = smap + POL_WORDS;
+        __syncthreads();                                 // barrier init + aux visible
+        mbar_wait(lbar, 0);                              // bit rows have landed
+        const uint32_t *smap = sbits - bits_w0, *lmap = sbits + TC_BITS_WORDS - bits_w0;
         float bg[8];
 #pragma unroll
         for (int co = 0; co < 8; co++) bg[co] = fmaxf(aux[co], 0.f);
         const uint4 bgq = pack_bf8(bg);
         const int groups = W / 8;                        // 8 pooled pixels per work item
-        for (int g = tid; g < rows_in * groups; g += 128) {
+        for (int g = tid; g < rows_in * groups; g += TC_NT) {
             const int ry = g / groups, gx = g % groups, py = y0 - 1 + ry;
             uint4 *dst = sin + ry * P + 1 + gx * 8;
+            const int rot = tid & 7;                     // rotate the store order: 8 lanes hit 8 different bank groups
             if (py < 0 || py >= W) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) dst[k] = make_uint4(0, 0, 0, 0);
+                for (int k = 0; k < 8; k++) dst[(k + rot) & 7] = make_uint4(0, 0, 0, 0);
                 continue;
             }
             // 18 map columns 16 gx - 1 .. 16 gx + 16 of the 4 map rows 2 py - 1 .. 2 py + 2
@@ -191,18 +245,19 @@ k_tc_conv(const TcArgs a) {
                     int b = r * POL_W + 16 * gx - 1;
                     const int sh = b < 0 ? 1 : 0;
                     b = max(b, 0);
-                    const int wd = b >> 5, wd1 = min(wd + 1, POL_WORDS - 1);
-                    rs[i] = (__funnelshift_r(smap[wd], smap[wd1], b & 31) << sh) & colmask;
-                    rl[i] = (__funnelshift_r(lmap[wd], lmap[wd1], b & 31) << sh) & colmask;
+                    const int wd = b >> 5;
+                    rs[i] = (__funnelshift_r(smap[wd], smap[wd + 1], b & 31) << sh) & colmask;
+                    rl[i] = (__funnelshift_r(lmap[wd], lmap[wd + 1], b & 31) << sh) & colmask;
                 }
                 any |= rs[i] | rl[i];
             }
             if (!any) {
 #pragma unroll
-                for (int k = 0; k < 8; k++) dst[k] = bgq;
+                for (int k = 0; k < 8; k++) dst[(k + rot) & 7] = bgq;
                 continue;
             }
-            for (int k = 0; k < 8; k++) {
+            for (int kk = 0; kk < 8; kk++) {
+                const int k = (kk + rot) & 7;
                 uint32_t ps = 0, pq = 0;
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
@@ -215,33 +270,28 @@ k_tc_conv(const TcArgs a) {
                 dst[k] = pack_bf8(v);
             }
         }
-        for (int ry = tid; ry < rows_in; ry += 128) sin[ry * P] = make_uint4(0, 0, 0, 0);    // shared halo column
-    } else {
-        const uint4 *src = reinterpret_cast<const uint4 *>(reinterpret_cast<const __nv_bfloat16 *>(a.in) + (size_t)item * a.in_item_stride);
-        for (int i = tid; i < rows_in * P; i += 128) {
-            const int ry = i / P, c = i % P;
-            int y = y0 - 1 + ry, x = c - 1;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (REPL) {
-                y = min(max(y, 0), W - 1);
-                x = min(max(x, 0), W - 1);
-                v = src[(size_t)y * W + x];
-            } else if (y >= 0 && y < W && x >= 0 && x < W) v = src[(size_t)y * W + x];
-            sin[i] = v;
-        }
+        for (int ry = tid; ry < rows_in; ry += TC_NT) sin[ry * P] = make_uint4(0, 0, 0, 0);    // shared halo column
     }
-    for (int i = rows_in * P + tid; i < pl.sin_pixels; i += 128) sin[i] = make_uint4(0, 0, 0, 0);
+    // ---- TMEM: a ring of TC_RING accumulators of N columns each (allocated late so that a CTA waiting for
+    //      columns has already staged its strip)
+    uint32_t TMEM_COLS = 32;
+    while (TMEM_COLS < (uint32_t)(min(T, TC_RING) * N)) TMEM_COLS <<= 1;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    if (MODE != M_CONV_BITS) mbar_wait(lbar, 0);         // bulk-copied rows have landed (acquire for every thread)
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- descriptors
     constexpr uint32_t IDESC = instr_desc(N);
     const uint32_t sin16 = smem_u32(sin) >> 4, sw16 = smem_u32(sw) >> 4;
     auto issue_tile = [&](int t) {
-        const uint32_t d = tmem_base + (uint32_t)((t & 1) * N);
+        const uint32_t d = tmem_base + (uint32_t)((t % TC_RING) * N);
 #pragma unroll
         for (int j = 0; j < 5; j++) {
             const int t0 = 2 * j, t1 = 2 * j + 1;
@@ -251,18 +301,28 @@ k_tc_conv(const TcArgs a) {
             const uint64_t bd = smem_desc(sw16 + (uint32_t)(t0 * N), (uint32_t)N, 8);
             tc_mma(d, ad, bd, IDESC, j > 0 ? 1u : 0u);
         }
-        tc_commit(&bars[t & 1]);
+        tc_commit(&bars[t % TC_RING]);
     };
 
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
-    if (tid == 0) issue_tile(0);
+    // all MMAs of the first TC_RING tiles are queued at once; after every TC_RING/2 drained tiles the freed
+    // accumulators are refilled, so the tensor pipe always has at least TC_RING/2 tiles of work queued
+    if (tid == 0)
+        for (int t = 0; t < min(T, TC_RING); t++) issue_tile(t);
     for (int t = 0; t < T; t++) {
-        if (tid == 0 && t + 1 < T) issue_tile(t + 1);
-        mbar_wait(&bars[t & 1], (uint32_t)((t >> 1) & 1));
+        if (t > 0 && (t % (TC_RING / 2)) == 0 && t + TC_RING / 2 < T) {
+            tc_fence_before();
+            __syncthreads();                             // tiles t - TC_RING/2 .. t - 1 are drained by every warp
+            tc_fence_after();
+            if (tid == 0)
+                for (int u = t + TC_RING / 2; u < min(T, t + TC_RING); u++) issue_tile(u);
+        }
+        if ((t & 1) != (warp >> 2)) continue;            // warps 0-3 drain even tiles, warps 4-7 odd tiles
+        mbar_wait(&bars[t % TC_RING], (uint32_t)((t / TC_RING) & 1));
         tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((t & 1) * N);
-        const int q = 128 * t + tid;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((t % TC_RING) * N);
+        const int q = 128 * t + (tid & 127);
         if (POOL) {
             uint32_t r[8];
             tc_ld8(taddr, r);
@@ -270,7 +330,7 @@ k_tc_conv(const TcArgs a) {
             float v[8];
 #pragma unroll
             for (int co = 0; co < 8; co++) v[co] = fmaxf(__uint_as_float(r[co]) + biasr[co], 0.f);
-            stage[q] = pack_bf8(v);
+            if (q < TC_R * P) stage[q] = pack_bf8(v);
         } else if (MODE == M_UP3) {
             uint32_t r[32];
             tc_ld8(taddr, r); tc_ld8(taddr + 8, r + 8); tc_ld8(taddr + 16, r + 16); tc_ld8(taddr + 24, r + 24);
@@ -314,17 +374,16 @@ k_tc_conv(const TcArgs a) {
                 }
             }
         }
-        tc_fence_before();
-        __syncthreads();                                 // buffer t&1 is free again, stage rows are visible
-        tc_fence_after();
     }
+    tc_fence_before();
+    __syncthreads();                                     // stage rows / ring values are visible to every thread
 
     if (REPL) {
         // border ring: take the out-of-range taps back out of the folded result, then consume the pixel
         const int Wo = 2 * W, nslots = 4 * TC_R + Wo;
         const bool first = blockIdx.x == 0, last = blockIdx.x == gridDim.x - 1;
         const StripImage Ls{sin, P, y0};
-        for (int slot = tid; slot < nslots; slot += 128) {
+        for (int slot = tid; slot < nslots; slot += TC_NT) {
             int Y, X;
             if (slot < 2 * TC_R) { Y = 2 * y0 + slot; X = 0; }
             else if (slot < 4 * TC_R) { Y = 2 * y0 + slot - 2 * TC_R; X = Wo - 1; }
@@ -353,7 +412,7 @@ k_tc_conv(const TcArgs a) {
     if (POOL) {
         const int wo = W / 2;
         __nv_bfloat16 *dst = a.out + (size_t)item * a.out_item_stride;
-        for (int pp = tid; pp < (TC_R / 2) * wo; pp += 128) {
+        for (int pp = tid; pp < (TC_R / 2) * wo; pp += TC_NT) {
             const int pr = pp / wo, pc = pp % wo;
             const uint4 q0 = stage[(2 * pr) * P + 2 * pc], q1 = stage[(2 * pr) * P + 2 * pc + 1];
             const uint4 q2 = stage[(2 * pr + 1) * P + 2 * pc], q3 = stage[(2 * pr + 1) * P + 2 * pc + 1];
@@ -376,7 +435,7 @@ k_tc_conv(const TcArgs a) {
         if ((tid & 31) == 0) { sv[warp] = best_v; si[warp] = best_i; }
         __syncthreads();
         if (tid == 0) {
-            for (int k = 1; k < 4; k++)
+            for (int k = 1; k < TC_NT / 32; k++)
                 if (amax_better(sv[k], si[k], best_v, best_i)) { best_v = sv[k]; best_i = si[k]; }
             a.amax_val[(size_t)item * gridDim.x + blockIdx.x] = best_v;
             a.amax_idx[(size_t)item * gridDim.x + blockIdx.x] = best_i;
@@ -398,7 +457,7 @@ static int launch(const TcArgs &a, int n_items, cudaStream_t st) {
         configured = pl.total;
     }
     if (n_items == 0) return OFB_OK;
-    k_tc_conv<MODE, N><<<dim3(a.H / TC_R, n_items), 128, pl.total, st>>>(a);
+    k_tc_conv<MODE, N><<<dim3(a.H / TC_R, n_items), TC_NT, pl.total, st>>>(a);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

@@ -18,7 +18,7 @@ def main():
         bg.frame()
     maps = bg.raster("bits")
     vec = bg.obs_vec[:, 0, :].contiguous()
-    pol = PolicyB200.random_init(device=bg.device, seed=0, max_ships=1024)
+    pol = PolicyB200.random_init(device=bg.device, seed=0, max_ships=int(os.environ.get('OFB_MAX_SHIPS', '4096')))
     for eng in engines:
         pol.set_engine(eng)
         for _ in range(2):
@@ -32,7 +32,10 @@ def main():
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / iters
-        print(json.dumps({"engine": eng, "n_arenas": n, "ms_per_forward_batch": ms, "forwards_per_s": n / ms * 1e3,
+        pol.profile(True)
+        pol.forward_argmax(maps, vec)
+        prof = pol.profile(False)
+        print(json.dumps({"engine": eng, "layers_ms": {k: round(v, 3) for k, v in prof.items()}, "n_arenas": n, "ms_per_forward_batch": ms, "forwards_per_s": n / ms * 1e3,
                           "dense_equiv_TFLOPs": n * 155.3e6 / (ms * 1e-3) / 1e12}), flush=True)
 
 
