@@ -91,30 +91,41 @@ __device__ __forceinline__ void bil_tap_ext(int Y, int &lo, int &hi, float &wlo,
     else { lo = i - 1; hi = i; wlo = 0.25f; whi = 0.75f; }
 }
 
+// contribution of ONE out-of-range tap (dy, dx) of output pixel (Y, X): acc[co] += w[dy][dx][:, co] . U~[Y+dy-1][X+dx-1]
+template <int CIN, int COUT, class Acc>
+__device__ __forceinline__ void up_ring_tap(const Acc &L, int Y, int X, int dy, int dx, const float *__restrict__ w, float *acc) {
+    int ylo, yhi, xlo, xhi; float wyl, wyh, wxl, wxh;
+    bil_tap_ext(Y + dy - 1, ylo, yhi, wyl, wyh);
+    bil_tap_ext(X + dx - 1, xlo, xhi, wxl, wxh);
+    float a[8], c[8], d[8], e[8];
+    unpack_bf8(L(ylo, xlo), a);
+    unpack_bf8(L(ylo, xhi), c);
+    unpack_bf8(L(yhi, xlo), d);
+    unpack_bf8(L(yhi, xhi), e);
+    const int tap = dy * 3 + dx;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ci++) {
+        const float u = wyl * (wxl * a[ci] + wxh * c[ci]) + wyh * (wxl * d[ci] + wxh * e[ci]);
+#pragma unroll
+        for (int co = 0; co < COUT; co++) acc[co] += u * w[(tap * CIN + ci) * COUT + co];
+    }
+}
+
 template <int CIN, int COUT, class Acc>
 __device__ __forceinline__ void up_ring_correct(const Acc &L, int n, int Y, int X, const float *__restrict__ w, float *v) {
+    float acc[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; co++) acc[co] = 0.f;
     for (int dy = 0; dy < 3; dy++) {
         const int YY = Y + dy - 1;
         for (int dx = 0; dx < 3; dx++) {
             const int XX = X + dx - 1;
             if (YY >= 0 && YY < 2 * n && XX >= 0 && XX < 2 * n) continue;
-            int ylo, yhi, xlo, xhi; float wyl, wyh, wxl, wxh;
-            bil_tap_ext(YY, ylo, yhi, wyl, wyh);
-            bil_tap_ext(XX, xlo, xhi, wxl, wxh);
-            float a[8], c[8], d[8], e[8];
-            unpack_bf8(L(ylo, xlo), a);
-            unpack_bf8(L(ylo, xhi), c);
-            unpack_bf8(L(yhi, xlo), d);
-            unpack_bf8(L(yhi, xhi), e);
-            const int tap = dy * 3 + dx;
-#pragma unroll
-            for (int ci = 0; ci < CIN; ci++) {
-                const float u = wyl * (wxl * a[ci] + wxh * c[ci]) + wyh * (wxl * d[ci] + wxh * e[ci]);
-#pragma unroll
-                for (int co = 0; co < COUT; co++) v[co] -= u * w[(tap * CIN + ci) * COUT + co];
-            }
+            up_ring_tap<CIN, COUT>(L, Y, X, dy, dx, w, acc);
         }
     }
+#pragma unroll
+    for (int co = 0; co < COUT; co++) v[co] -= acc[co];
 }
 
 // accessor over a dense [n][n][8] bf16 image in global memory, replicate-clamped

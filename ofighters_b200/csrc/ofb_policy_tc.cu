@@ -36,6 +36,7 @@ struct TcArgs {
     int *amax_idx;
     long long in_item_stride, out_item_stride;   // in elements
     int H;                            // input height = width (conv resolution)
+    long long *dbg;                   // optional: clock64 stamps of CTA (1, 0) at the phase boundaries
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -147,12 +148,16 @@ k_tc_conv(const TcArgs a) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + pl.off_bar);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + pl.off_bar + (TC_RING + 1) * 8);
 
+#define TC_STAMP(k) do { if (a.dbg && tid == 0 && blockIdx.x == 1 && blockIdx.y == 0) a.dbg[k] = clock64(); } while (0)
+    TC_STAMP(0);
     // ---- one-time setup: barriers, bulk copies of the input rows, weights
     uint64_t *lbar = &bars[TC_RING];                     // completion of the bulk (TMA-class) row copies
     const int rows_in = TC_R + 2;
     const uint8_t *in_item = reinterpret_cast<const uint8_t *>(a.in) +
                              (MODE == M_CONV_BITS ? (size_t)item * 2 * POL_WORDS * 4 : (size_t)item * a.in_item_stride * 2);
     uint32_t *sbits = reinterpret_cast<uint32_t *>(smem + pl.off_stage);  // BITS: 2 x TC_BITS_WORDS words of the two maps (dead before the epilogue)
+    uint2 *wl = reinterpret_cast<uint2 *>(smem + pl.off_stage + 2 * TC_BITS_WORDS * 4);   // BITS: work list (patch, sin index)
+    int *wl_count = reinterpret_cast<int *>(aux + 8);
     int bits_w0 = 0;                                     // first map word held in sbits
     if (MODE == M_CONV_BITS) {
         const int r0 = max(2 * y0 - 3, 0), r1 = min(2 * (y0 + TC_R) + 2, POL_W - 1);
@@ -187,6 +192,7 @@ k_tc_conv(const TcArgs a) {
     }
     if (MODE == M_CONV_BITS) {
         if (tid < 8) aux[tid] = a.aux_b[tid];            // conv1 bias; its pattern LUT (a.aux_w) stays in global/L1
+        if (tid == 8) *wl_count = 0;
     } else if (MODE == M_UP3) {
         for (int i = tid; i < 9 * 4 * 8; i += TC_NT) aux[i] = a.aux_w[i];
     } else if (MODE == M_UP4) {
@@ -216,7 +222,9 @@ k_tc_conv(const TcArgs a) {
 
     if (MODE == M_CONV_BITS) {
         __syncthreads();                                 // barrier init + aux visible
+        TC_STAMP(1);
         mbar_wait(lbar, 0);                              // bit rows have landed
+        TC_STAMP(2);
         const uint32_t *smap = sbits - bits_w0, *lmap = sbits + TC_BITS_WORDS - bits_w0;
         float bg[8];
 #pragma unroll
@@ -256,6 +264,8 @@ k_tc_conv(const TcArgs a) {
                 for (int k = 0; k < 8; k++) dst[(k + rot) & 7] = bgq;
                 continue;
             }
+            // pixels that see a set bit go to a work list, so that the (rare, heavier) exact evaluations are
+            // spread over all threads afterwards instead of serialising in the few threads that met them
             for (int kk = 0; kk < 8; kk++) {
                 const int k = (kk + rot) & 7;
                 uint32_t ps = 0, pq = 0;
@@ -265,13 +275,23 @@ k_tc_conv(const TcArgs a) {
                     pq |= ((rl[i] >> (2 * k)) & 0xFu) << (4 * i);
                 }
                 if ((ps | pq) == 0) { dst[k] = bgq; continue; }
+                const int slot = atomicAdd(wl_count, 1);
+                wl[slot] = make_uint2(ps | (pq << 16), (uint32_t)(ry * P + 1 + gx * 8 + k));
+            }
+        }
+        __syncthreads();
+        {
+            const int n_work = *wl_count;
+            for (int i = tid; i < n_work; i += TC_NT) {
+                const uint2 e = wl[i];
                 float v[8];
-                conv1_pool_pixel(ps, pq, a.aux_w, aux, v);
-                dst[k] = pack_bf8(v);
+                conv1_pool_pixel(e.x & 0xFFFFu, e.x >> 16, a.aux_w, aux, v);
+                sin[e.y] = pack_bf8(v);
             }
         }
         for (int ry = tid; ry < rows_in; ry += TC_NT) sin[ry * P] = make_uint4(0, 0, 0, 0);    // shared halo column
     }
+    TC_STAMP(3);
     // ---- TMEM: a ring of TC_RING accumulators of N columns each (allocated late so that a CTA waiting for
     //      columns has already staged its strip)
     uint32_t TMEM_COLS = 32;
@@ -284,8 +304,10 @@ k_tc_conv(const TcArgs a) {
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    TC_STAMP(4);
     if (MODE != M_CONV_BITS) mbar_wait(lbar, 0);         // bulk-copied rows have landed (acquire for every thread)
     const uint32_t tmem_base = *tmem_slot;
+    TC_STAMP(5);
 
     // ---- descriptors
     constexpr uint32_t IDESC = instr_desc(N);
@@ -310,6 +332,7 @@ k_tc_conv(const TcArgs a) {
     // accumulators are refilled, so the tensor pipe always has at least TC_RING/2 tiles of work queued
     if (tid == 0)
         for (int t = 0; t < min(T, TC_RING); t++) issue_tile(t);
+    TC_STAMP(6);
     for (int t = 0; t < T; t++) {
         if (t > 0 && (t % (TC_RING / 2)) == 0 && t + TC_RING / 2 < T) {
             tc_fence_before();
@@ -375,37 +398,61 @@ k_tc_conv(const TcArgs a) {
             }
         }
     }
+    TC_STAMP(7);
     tc_fence_before();
     __syncthreads();                                     // stage rows / ring values are visible to every thread
+    TC_STAMP(8);
 
     if (REPL) {
-        // border ring: take the out-of-range taps back out of the folded result, then consume the pixel
+        // border ring: take the out-of-range taps back out of the folded result, then consume the pixel.
+        // Four lanes per ring pixel: lanes 0..2 evaluate one out-of-range tap each (lane 0 also the two extra
+        // taps of a corner), summed in lane order by shuffles.
+        constexpr int CIN = (MODE == M_UP3) ? 4 : 8, COUT = (MODE == M_UP3) ? 8 : 1;
         const int Wo = 2 * W, nslots = 4 * TC_R + Wo;
         const bool first = blockIdx.x == 0, last = blockIdx.x == gridDim.x - 1;
         const StripImage Ls{sin, P, y0};
-        for (int slot = tid; slot < nslots; slot += TC_NT) {
-            int Y, X;
+        for (int base = 0; base < nslots * 4; base += TC_NT) {
+            const int itm = base + tid, slot = itm >> 2, j = itm & 3;
+            int Y = 0, X = 0;
+            bool valid = slot < nslots;
             if (slot < 2 * TC_R) { Y = 2 * y0 + slot; X = 0; }
             else if (slot < 4 * TC_R) { Y = 2 * y0 + slot - 2 * TC_R; X = Wo - 1; }
             else {
                 X = slot - 4 * TC_R;
-                if (!(first || last) || X == 0 || X == Wo - 1) continue;
+                valid = valid && (first || last) && X != 0 && X != Wo - 1;
                 Y = first ? 0 : Wo - 1;
             }
+            float acc[COUT];
+#pragma unroll
+            for (int co = 0; co < COUT; co++) acc[co] = 0.f;
+            if (valid && j < 3) {
+                const bool xedge = (X == 0 || X == Wo - 1), yedge = (Y == 0 || Y == Wo - 1);
+                const int dxe = X == 0 ? 0 : 2, dye = Y == 0 ? 0 : 2;
+                if (xedge) up_ring_tap<CIN, COUT>(Ls, Y, X, j, dxe, aux, acc);
+                else up_ring_tap<CIN, COUT>(Ls, Y, X, dye, j, aux, acc);
+                if (xedge && yedge && j == 0)                       // corner: the two remaining taps of the edge row
+                    for (int dx = 0; dx < 3; dx++)
+                        if (dx != dxe) up_ring_tap<CIN, COUT>(Ls, Y, X, dye, dx, aux, acc);
+            }
+            float o[COUT];
+#pragma unroll
+            for (int co = 0; co < COUT; co++) {
+                const float t1 = __shfl_down_sync(0xffffffffu, acc[co], 1), t2 = __shfl_down_sync(0xffffffffu, acc[co], 2);
+                o[co] = (acc[co] + t1) + t2;
+            }
+            if (!valid || j != 0) continue;
             if (MODE == M_UP3) {
-                float o[8];
 #pragma unroll
-                for (int co = 0; co < 8; co++) o[co] = ring[8 * slot + co];
-                up_ring_correct<4, 8>(Ls, W, Y, X, aux, o);
+                for (int co = 0; co < COUT; co++) o[co] = fmaxf(ring[COUT * slot + co] - o[co], 0.f);
+                float o8[8];
 #pragma unroll
-                for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
-                *reinterpret_cast<uint4 *>(a.out + (size_t)item * a.out_item_stride + ((size_t)Y * Wo + X) * 8) = pack_bf8(o);
+                for (int co = 0; co < 8; co++) o8[co] = o[co % COUT];
+                *reinterpret_cast<uint4 *>(a.out + (size_t)item * a.out_item_stride + ((size_t)Y * Wo + X) * 8) = pack_bf8(o8);
             } else {
-                float o = ring[slot];
-                up_ring_correct<8, 1>(Ls, W, Y, X, aux, &o);
+                const float v = ring[slot] - o[0];
                 const int idx = Y * Wo + X;
-                if (a.ptr_out) a.ptr_out[(size_t)item * Wo * Wo + idx] = o;
-                if (amax_better(o, idx, best_v, best_i)) { best_v = o; best_i = idx; }
+                if (a.ptr_out) a.ptr_out[(size_t)item * Wo * Wo + idx] = v;
+                if (amax_better(v, idx, best_v, best_i)) { best_v = v; best_i = idx; }
             }
         }
     }
@@ -442,12 +489,17 @@ k_tc_conv(const TcArgs a) {
         }
     }
     // ---- teardown
+    TC_STAMP(9);
     tc_fence_before();
     __syncthreads();
+    TC_STAMP(10);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
 }
 
 // ---------------------------------------------------------------- host launchers
+static long long *g_tc_dbg = nullptr;                    // device buffer of 4 x 16 stamps (mode-major), see ofb_policy_tc_debug
+extern "C" int ofb_policy_tc_debug(long long *dev_buf) { g_tc_dbg = dev_buf; return OFB_OK; }
+
 template <int MODE, int N>
 static int launch(const TcArgs &a, int n_items, cudaStream_t st) {
     const TcPlan pl = tc_plan(MODE, N, a.H);
@@ -457,7 +509,9 @@ static int launch(const TcArgs &a, int n_items, cudaStream_t st) {
         configured = pl.total;
     }
     if (n_items == 0) return OFB_OK;
-    k_tc_conv<MODE, N><<<dim3(a.H / TC_R, n_items), TC_NT, pl.total, st>>>(a);
+    TcArgs b = a;
+    b.dbg = g_tc_dbg ? g_tc_dbg + 16 * MODE : nullptr;
+    k_tc_conv<MODE, N><<<dim3(a.H / TC_R, n_items), TC_NT, pl.total, st>>>(b);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

@@ -19,6 +19,22 @@ def main():
     maps = bg.raster("bits")
     vec = bg.obs_vec[:, 0, :].contiguous()
     pol = PolicyB200.random_init(device=bg.device, seed=0, max_ships=int(os.environ.get('OFB_MAX_SHIPS', '4096')))
+    if os.environ.get("OFB_TC_DEBUG"):
+        import ctypes
+        from ofighters_b200 import _lib
+        dbg = torch.zeros(64, dtype=torch.int64, device=bg.device)
+        lib = _lib.load()
+        lib.ofb_policy_tc_debug.argtypes = [ctypes.c_void_p]
+        lib.ofb_policy_tc_debug(ctypes.c_void_p(dbg.data_ptr()))
+        pol.set_engine("tensor")
+        pol.forward_argmax(maps, vec)
+        pol.forward_argmax(maps, vec)
+        torch.cuda.synchronize()
+        d = dbg.cpu().reshape(4, 16)
+        for m, name in enumerate(["conv_gmem", "trunk12", "up3", "up4"]):
+            st = d[m, :11].tolist()
+            print(name, "phase cycles:", [st[i + 1] - st[i] if st[i + 1] and st[i] else None for i in range(10)], "total", st[10] - st[0])
+        lib.ofb_policy_tc_debug(None)
     for eng in engines:
         pol.set_engine(eng)
         for _ in range(2):
