@@ -43,9 +43,9 @@ static const float PHASE_C[2][3][3] = {
     {{0.75f, 0.25f, 0.f}, {0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}},
     {{0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}, {0.f, 0.25f, 0.75f}}};
 
-// [9][cin][cout] -> phase-folded [10][npad][8]: n = (a*2+b)*cout + co, low-res tap (u, v)
-static std::vector<__nv_bfloat16> pack_phase(const std::vector<float> &w, int cin, int cout, int npad) {
-    std::vector<__nv_bfloat16> o((size_t)POL_TAPS * npad * 8, __float2bfloat16(0.f));
+// [9][cin][cout] -> bilinear-x2 phase-folded fp32 [9 (u, v)][cin][4 * cout], column = (a*2+b)*cout + co
+static std::vector<float> fold_phase(const std::vector<float> &w, int cin, int cout) {
+    std::vector<float> o((size_t)9 * cin * 4 * cout, 0.f);
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 2; b++)
             for (int u = 0; u < 3; u++)
@@ -56,8 +56,20 @@ static std::vector<__nv_bfloat16> pack_phase(const std::vector<float> &w, int ci
                             for (int dy = 0; dy < 3; dy++)
                                 for (int dx = 0; dx < 3; dx++)
                                     s += (double)w[((size_t)(dy * 3 + dx) * cin + ci) * cout + co] * PHASE_C[a][dy][u] * PHASE_C[b][dx][v];
-                            o[((size_t)(u * 3 + v) * npad + (a * 2 + b) * cout + co) * 8 + ci] = __float2bfloat16((float)s);
+                            o[((size_t)(u * 3 + v) * cin + ci) * 4 * cout + (a * 2 + b) * cout + co] = (float)s;
                         }
+    return o;
+}
+
+// [9 (dy, dx)][cin][cout] fp32 -> tensor-engine B image [4 dy][nn][8 cin] bf16 with n = dx * nc + co:
+// the dx taps are folded into the N dimension (summed again in the epilogue), dy into K.
+static std::vector<__nv_bfloat16> pack_dyfold(const std::vector<float> &w, int cin, int cout, int nc, int nn) {
+    std::vector<__nv_bfloat16> o((size_t)4 * nn * 8, __float2bfloat16(0.f));
+    for (int dy = 0; dy < 3; dy++)
+        for (int dx = 0; dx < 3; dx++)
+            for (int ci = 0; ci < cin; ci++)
+                for (int co = 0; co < cout; co++)
+                    o[((size_t)dy * nn + dx * nc + co) * 8 + ci] = __float2bfloat16(w[((size_t)(dy * 3 + dx) * cin + ci) * cout + co]);
     return o;
 }
 
@@ -113,6 +125,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
         fold_conv(wh->conv[l + 1], 8, 8, w, b);
         b.resize(16, 0.f);
         up.add(&d.cw[l], pack_taps(w, 8, 8, 16));
+        up.add(&d.cw2[l], pack_dyfold(w, 8, 8, 8, 32));
         up.add(&d.cb[l], b);
     }
     // dense1: rows 0..7 = vector slice (fp32), rows 8..5007 = flat slice (bf16)
@@ -135,11 +148,15 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b);
     fold_conv(wh->upconv[2], 4, 8, w, b);
     up.add(&d.u3_w, w); up.add(&d.u3_b, b);
-    up.add(&d.u3_pw, pack_phase(w, 4, 8, 32));
+    { const std::vector<float> pf = fold_phase(w, 4, 8);
+      up.add(&d.u3_pw, pack_taps(pf, 4, 32, 32));
+      up.add(&d.u3_pw2, pack_dyfold(pf, 4, 32, 32, 96)); }
     { std::vector<float> pb(32); for (int n = 0; n < 32; n++) pb[n] = b[n % 8]; up.add(&d.u3_pb, pb); }
     fold_conv(wh->upconv[3], 8, 1, w, b);
     up.add(&d.u4_w, w); up.add(&d.u4_b, b);
-    up.add(&d.u4_pw, pack_phase(w, 8, 1, 16));
+    { const std::vector<float> pf = fold_phase(w, 8, 1);
+      up.add(&d.u4_pw, pack_taps(pf, 8, 4, 16));
+      up.add(&d.u4_pw2, pack_dyfold(pf, 8, 4, 4, 16)); }
     { std::vector<float> pb(16, 0.f); for (int n = 0; n < 4; n++) pb[n] = b[0]; up.add(&d.u4_pb, pb); }
 
     cudaError_t e = cudaMalloc(&p->arena_blob, up.host.size());

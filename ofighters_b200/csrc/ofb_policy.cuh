@@ -20,6 +20,7 @@ struct PolicyDev {
     float *c1_lut;            // [2][512][8] sums of c1_w over the set taps of a 9-bit stencil pattern
     __nv_bfloat16 *cw[3];     // conv2..4: [10][16][8] (tap, n = cout padded to 16, cin)  bf16
     float *cb[3];             // [16]
+    __nv_bfloat16 *cw2[3];    // conv2..4 for the tensor engine: [4 dy][32 n = dx*8 + cout][8 cin] (dy 3 and n >= 24 zero)
     // dense1
     float *d1_wv;             // [8][100]     vector slice, fp32 (values up to 400 are not bf16-exact)
     __nv_bfloat16 *d1_wf;     // [5000][100]  flat slice, (k, n)  -- CUDA-core engine
@@ -35,9 +36,11 @@ struct PolicyDev {
     float *u3_w, *u3_b;       // [9][4][8], [8]   un-phased fp32 (ring pixels)
     __nv_bfloat16 *u3_pw;     // [10][32][8]      (tap, n = phase*8 + cout, cin padded to 8)
     float *u3_pb;             // [32]
+    __nv_bfloat16 *u3_pw2;    // tensor engine: [4 u][96 n = v*32 + phase*8 + cout][8 cin]
     float *u4_w, *u4_b;       // [9][8][1], [1]
     __nv_bfloat16 *u4_pw;     // [10][16][8]      (tap, n = phase (4 used), cin)
     float *u4_pb;             // [16]
+    __nv_bfloat16 *u4_pw2;    // tensor engine: [4 u][16 n = v*4 + phase][8 cin]
 };
 
 struct PolicyWork {

@@ -14,14 +14,18 @@
 //   upconv4   : 4 phases of the single output channel: + bias -> running argmax (+ optional dense map)
 // conv1 never touches HBM: its pooled output is generated straight into conv2's shared-memory strip
 // from the bit maps (background constant + exact evaluation near set bits).
-// The input rows reach shared memory as bulk asynchronous copies (cp.async.bulk + mbarrier); a ring of 8
-// TMEM accumulators keeps at least 4 tiles of MMAs queued while the four warps drain completed tiles.
+// The input rows reach shared memory as bulk asynchronous copies (cp.async.bulk + mbarrier).  A dedicated
+// warp issues the MMAs into a ring of 8 TMEM accumulators (full / empty mbarriers per accumulator) while
+// eight warps drain completed tiles.  Measured on B200: these kernels are bound by instruction issue and by
+// the tensor pipe's shared-memory operand reads (~75 cycles per M=128 x K=16 A tile whatever N is), not by
+// its math; folding the dx taps into N (2 MMAs per tile instead of 5) was tried and lost to its heavier
+// epilogue (shuffles + lane-quarter exchange) -- see DESIGN.md section 5.
 #include "ofb_common.cuh"
 #include "ofb_policy_dev.cuh"
 
 enum { M_CONV_GMEM = 0, M_CONV_BITS = 1, M_UP3 = 2, M_UP4 = 3 };
 #define TC_R 10                       // image rows per strip (all layer heights are multiples of 10)
-#define TC_NT 256                     // threads per CTA: two warps per TMEM lane quarter, draining alternate tiles
+#define TC_NT 288                     // threads per CTA: 8 draining warps (two per TMEM lane quarter) + 1 MMA-issuer warp
 #define TC_RING 8                     // TMEM accumulators (tiles in flight) per CTA
 #define TC_BITS_WORDS 352             // words of one bit map staged per strip: 27 rows x 50 B + alignment slack
 
@@ -54,6 +58,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
             "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -113,7 +120,7 @@ __host__ __device__ inline TcPlan tc_plan(int mode, int N, int H) {
     p.off_aux = p.off_stage + stage;
     // aux: ring weights (<= 288 floats) + argmax scratch, or conv1 bias + the strip's bit rows of both maps
     p.off_bar = p.off_aux + (mode == M_CONV_BITS ? 64 : 1280);
-    p.total = p.off_bar + (TC_RING + 1) * 8 + 16;       // accumulator-ring mbarriers + load barrier + TMEM slot
+    p.total = p.off_bar + (2 * TC_RING + 1) * 8 + 16;   // full[RING] + load + empty[RING] mbarriers, TMEM slot
     return p;
 }
 
@@ -146,7 +153,8 @@ k_tc_conv(const TcArgs a) {
     float *ring = reinterpret_cast<float *>(smem + pl.off_stage);     // UP modes reuse the stage region
     float *aux = reinterpret_cast<float *>(smem + pl.off_aux);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + pl.off_bar);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + pl.off_bar + (TC_RING + 1) * 8);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + pl.off_bar + (2 * TC_RING + 1) * 8);
+    uint64_t *ebars = bars + TC_RING + 1;                 // accumulator b drained by its 4 warps -> may be overwritten
 
 #define TC_STAMP(k) do { if (a.dbg && tid == 0 && blockIdx.x == 1 && blockIdx.y == 0) a.dbg[k] = clock64(); } while (0)
     TC_STAMP(0);
@@ -164,14 +172,14 @@ k_tc_conv(const TcArgs a) {
         bits_w0 = ((r0 * 50) & ~15) >> 2;                // rows are 50 B; bulk copies move 16 B units
         if (tid == 32) {
             const int b0 = bits_w0 * 4, b1 = min(((r1 + 1) * 50 + 15 + 16) & ~15, POL_WORDS * 4);
-            for (int t = 0; t <= TC_RING; t++) mbar_init(&bars[t], 1);
+            for (int t = 0; t <= 2 * TC_RING; t++) mbar_init(&bars[t], t > TC_RING ? 4 : 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             mbar_expect_tx(lbar, 2u * (uint32_t)(b1 - b0));
             bulk_g2s(sbits, in_item + b0, (uint32_t)(b1 - b0), lbar);
             bulk_g2s(sbits + TC_BITS_WORDS, in_item + POL_WORDS * 4 + b0, (uint32_t)(b1 - b0), lbar);
         }
     } else if (tid == 32) {
-        for (int t = 0; t <= TC_RING; t++) mbar_init(&bars[t], 1);
+        for (int t = 0; t <= 2 * TC_RING; t++) mbar_init(&bars[t], t > TC_RING ? 4 : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         int nrows = 0;
         for (int ry = 0; ry < rows_in; ry++) {
@@ -328,20 +336,22 @@ k_tc_conv(const TcArgs a) {
 
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
-    // all MMAs of the first TC_RING tiles are queued at once; after every TC_RING/2 drained tiles the freed
-    // accumulators are refilled, so the tensor pipe always has at least TC_RING/2 tiles of work queued
-    if (tid == 0)
-        for (int t = 0; t < min(T, TC_RING); t++) issue_tile(t);
+    // warp 8 = MMA issuer: queues tile t as soon as accumulator t % TC_RING has been drained (empty barrier);
+    // warps 0-7 = drain: warps 0-3 take even tiles, warps 4-7 odd tiles, one TMEM lane quarter each
+    if (warp == 8) {
+        if ((tid & 31) == 0)
+            for (int t = 0; t < T; t++) {
+                if (t >= TC_RING) {
+                    mbar_wait(&ebars[t % TC_RING], (uint32_t)(((t / TC_RING) - 1) & 1));
+                    tc_fence_after();
+                }
+                issue_tile(t);
+            }
+        __syncwarp();
+    }
     TC_STAMP(6);
-    for (int t = 0; t < T; t++) {
-        if (t > 0 && (t % (TC_RING / 2)) == 0 && t + TC_RING / 2 < T) {
-            tc_fence_before();
-            __syncthreads();                             // tiles t - TC_RING/2 .. t - 1 are drained by every warp
-            tc_fence_after();
-            if (tid == 0)
-                for (int u = t + TC_RING / 2; u < min(T, t + TC_RING); u++) issue_tile(u);
-        }
-        if ((t & 1) != (warp >> 2)) continue;            // warps 0-3 drain even tiles, warps 4-7 odd tiles
+    for (int t = 0; t < T && warp < 8; t++) {
+        if ((t & 1) != (warp >> 2)) continue;
         mbar_wait(&bars[t % TC_RING], (uint32_t)((t / TC_RING) & 1));
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((t % TC_RING) * N);
@@ -397,6 +407,9 @@ k_tc_conv(const TcArgs a) {
                 }
             }
         }
+        tc_fence_before();                               // this warp's TMEM reads of the tile are complete
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&ebars[t % TC_RING]);
     }
     TC_STAMP(7);
     tc_fence_before();
@@ -477,7 +490,7 @@ k_tc_conv(const TcArgs a) {
     }
     if (MODE == M_UP4) {
         float *sv = aux + 128;
-        int *si = reinterpret_cast<int *>(aux + 136);
+        int *si = reinterpret_cast<int *>(aux + 144);
         amax_warp(best_v, best_i);
         if ((tid & 31) == 0) { sv[warp] = best_v; si[warp] = best_i; }
         __syncthreads();
