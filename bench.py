@@ -154,7 +154,7 @@ def gpu_arm(args, wl):
     import torch
     import torch.distributed as dist
     from ofighters_b200 import ArenaConfig, BatchedBattleground
-    from ofighters_b200 import _lib
+    from ofighters_b200 import _lib, sharding  # noqa: F401
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -189,7 +189,7 @@ def gpu_arm(args, wl):
         if bg.time >= max_time:
             bg.restart()
             if world > 1:
-                dist.all_reduce(bg.stats)          # K7: per-episode [score, kills, deaths, shots, ships, arenas]
+                sharding.reduce_episode_stats(bg.stats)   # K7: per-episode [score, kills, deaths, shots, ships, arenas]
             if policy is not None:
                 bg.raster("bits", out=maps)        # Battleground.restart builds a fresh Observation
         if policy is not None:

@@ -132,3 +132,28 @@ def test_errors_are_loud():
         bg.generate_frame(torch.zeros((4, 3, 5), dtype=torch.int16, device=bg.device))
     with pytest.raises(Exception):
         BatchedBattleground(4, ships=33)
+
+
+def test_sharded_arenas_equal_the_unsharded_run():
+    """Arena-level sharding: slices keyed by global arena id reproduce the whole batch."""
+    from ofighters_b200 import BatchedBattleground
+    from ofighters_b200.sharding import shard_range
+    N, T = 101, 45
+    whole = BatchedBattleground(N, ships={"random": 7}, seed=77)
+    parts = []
+    for r in range(3):
+        lo, hi = shard_range(N, r, 3)
+        parts.append(BatchedBattleground(hi - lo, ships={"random": 7}, seed=77, arena0=lo))
+    for t in range(T):
+        whole.frame()
+        for p in parts:
+            p.frame()
+    whole.restart()
+    for p in parts:
+        p.restart()
+    w = whole.state()
+    ps = [p.state() for p in parts]
+    for k in ("ship_x", "ship_y", "ship_px", "ship_py", "ship_alive", "ship_reward", "ship_score", "n_lasers", "kills"):
+        assert torch.equal(torch.cat([q[k] for q in ps]), w[k]), k
+    assert torch.equal(sum(p.stats for p in parts), whole.stats)
+    assert torch.equal(torch.cat([p.raster("bits") for p in parts]), whole.raster("bits"))
