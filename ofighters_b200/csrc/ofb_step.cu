@@ -44,7 +44,7 @@ __device__ __noinline__ bool on_trajectory_formula(int ux, int uy, int vx, int v
 // with u = pointing - me, v = enemy - me.  cos^2 of both sides are rationals of the integer
 // coordinates, so the comparison is exact in int64; pairs within 1e-10 rad of a boundary (where
 // the reference's outcome is decided by libm rounding) fall back to the formula.
-__device__ __forceinline__ bool on_trajectory(int ux, int uy, int vx, int vy, int &near_ties) {
+__device__ __noinline__ bool on_trajectory(int ux, int uy, int vx, int vy, int &near_ties) {
     long long uu = (long long)ux * ux + (long long)uy * uy;
     long long vv = (long long)vx * vx + (long long)vy * vy;
     // enemy on my own pixel: target = pi, cone half-angle = 2*pi, sup = inf = pi exactly in fp64
@@ -67,7 +67,7 @@ __device__ __forceinline__ bool on_trajectory(int ux, int uy, int vx, int vy, in
 }
 
 template <int LPA>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions,
        float4 *__restrict__ obs_out, long long n_arenas) {
     constexpr int APW = 32 / LPA;
@@ -75,6 +75,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     const int lane = threadIdx.x & 31;
     const int g = lane / LPA, gl = lane % LPA;
     const unsigned gshift = g * LPA;
+    const unsigned tmask = GM << gshift;                 // lanes of this arena's tile
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long arena = warp_global * APW + g;
     const bool ok = arena < n_arenas;
@@ -88,16 +89,9 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     double *ldy = reinterpret_cast<double *>(base + lay.off_ldy);
     unsigned *lmeta = reinterpret_cast<unsigned *>(base + lay.off_lmeta);
 
-    // ---- load header (tile lanes 0..7) and ship state (tile lane i = ship i) ----
+    // ---- issue every load of the first round trip at once: header, ships, actions and -- speculatively,
+    //      before the laser count is known -- the first LPA laser slots (they always exist: L >= 32)
     int hv = (ok && gl < 8) ? hdr[gl] : 0;
-    int time = __shfl_sync(FULL, hv, gshift + HDR_TIME);
-    int n = __shfl_sync(FULL, hv, gshift + HDR_NLASERS);
-    int kills = __shfl_sync(FULL, hv, gshift + HDR_KILLS);
-    int deaths = __shfl_sync(FULL, hv, gshift + HDR_DEATHS);
-    int shots = __shfl_sync(FULL, hv, gshift + HDR_SHOTS);
-    int overflow = __shfl_sync(FULL, hv, gshift + HDR_OVERFLOW);
-    int near_ties = 0;
-
     const bool is_ship = ok && gl < S;
     int sx = 0, sy = 0, spx = 0, spy = 0, rew = 0, score = 0, steps = 0, flags = 0;
     int2 act = make_int2(0, 0);
@@ -112,6 +106,19 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         flags = ship[SF_FLAGS * SP + gl];
         act = actions[arena * S + gl];
     }
+    unsigned p_meta = 0x100u;
+    double p_x = 0.0, p_y = 0.0, p_dx = 0.0, p_dy = 0.0;
+    if (ok) { p_meta = lmeta[gl]; p_x = lx[gl]; p_y = ly[gl]; p_dx = ldx[gl]; p_dy = ldy[gl]; }
+
+    int time = __shfl_sync(FULL, hv, gshift + HDR_TIME);
+    int n = __shfl_sync(FULL, hv, gshift + HDR_NLASERS);
+    int kills = __shfl_sync(FULL, hv, gshift + HDR_KILLS);
+    int deaths = __shfl_sync(FULL, hv, gshift + HDR_DEATHS);
+    int shots = __shfl_sync(FULL, hv, gshift + HDR_SHOTS);
+    int overflow = __shfl_sync(FULL, hv, gshift + HDR_OVERFLOW);
+    const int episode = __shfl_sync(FULL, hv, gshift + HDR_EPISODE);
+    const int near0 = __shfl_sync(FULL, hv, gshift + HDR_NEARTIES);
+    int near_ties = 0;
     bool alive = (flags & 1) != 0;
     int hull = flags >> 8;
 
@@ -123,46 +130,62 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     time += 1;
 
     // ---- A3 + A7: lasers in list order; entries destroyed last frame are dropped on load ----
+    // A ship alive at frame start dies to the FIRST laser (list order) that collides with it, and only
+    // that laser explodes on it (lib/laser.py:52-62).  Collisions are rare, so each lane first builds
+    // the bit mask of ships its laser touches -- float box pre-filter, then the exact fp64 distance the
+    // reference computes -- and the ballots that recover the list order run only when a mask is non-zero.
+    const float fsx = (float)sx, fsy = (float)sy;
     unsigned alive_bits = (__ballot_sync(FULL, alive) >> gshift) & GM;
     int iters = (n + LPA - 1) / LPA;
     iters = __reduce_max_sync(FULL, iters);
     int w = 0;                                           // compaction write cursor
     for (int it = 0; it < iters; it++) {
         const int k = it * LPA + gl;
-        bool live = ok && k < n;
-        unsigned meta = 0;
-        double x = 0.0, y = 0.0, dx = 0.0, dy = 0.0;
-        if (live) {
-            meta = lmeta[k];
-            live = !(meta & 0x100u);
+        const unsigned meta = p_meta;
+        double x = p_x, y = p_y;
+        const double dx = p_dx, dy = p_dy;
+        const bool live = ok && k < n && !(meta & 0x100u);
+        {   // prefetch the next chunk while this one is processed
+            const int kn = k + LPA;
+            if (ok && kn < n) { p_meta = lmeta[kn]; p_x = lx[kn]; p_y = ly[kn]; p_dx = ldx[kn]; p_dy = ldy[kn]; }
+            else p_meta = 0x100u;
         }
         if (live) {
-            x = lx[k]; y = ly[k]; dx = ldx[k]; dy = ldy[k];
             x = __dadd_rn(x, dx);                        // lib/laser.py:46-47
             y = __dadd_rn(y, dy);
         }
-        bool hit_any = false;
+        const float fx = (float)x, fy = (float)y;
+        unsigned hm = 0;
         for (int s = 0; s < S; s++) {
-            const double ex = __dsub_rn(x, (double)__shfl_sync(FULL, sx, gshift + s));
-            const double ey = __dsub_rn(y, (double)__shfl_sync(FULL, sy, gshift + s));
-            const double d2 = __dadd_rn(__dmul_rn(ex, ex), __dmul_rn(ey, ey));
-            const bool hit = live && ((alive_bits >> s) & 1u) && d2 <= D2_HIT_MAX;
-            const unsigned b = (__ballot_sync(FULL, hit) >> gshift) & GM;
-            const int killer = b ? (__ffs(b) - 1) : 0;
+            const float ex = fx - __shfl_sync(FULL, fsx, gshift + s);
+            const float ey = fy - __shfl_sync(FULL, fsy, gshift + s);
+            if (fabsf(ex) <= 10.5f && fabsf(ey) <= 10.5f) hm |= 1u << s;      // superset of the radius-10 disk
+        }
+        hm = live ? (hm & alive_bits) : 0u;
+        bool hit_any = false;
+        unsigned cand = __reduce_or_sync(tmask, hm);
+        while (cand) {                                   // ships some laser of this chunk may touch (rare)
+            const int s = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const double ddx = __dsub_rn(x, (double)__shfl_sync(tmask, sx, gshift + s));
+            const double ddy = __dsub_rn(y, (double)__shfl_sync(tmask, sy, gshift + s));
+            const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+            const bool hit = ((hm >> s) & 1u) && d2 <= D2_HIT_MAX;
+            const unsigned b = (__ballot_sync(tmask, hit) >> gshift) & GM;
+            if (!b) continue;
+            const int killer = __ffs(b) - 1;
             if (lay.r_kill != 0) {
-                const int own = __shfl_sync(FULL, (int)(meta & 0xffu), gshift + killer);
-                if (b && gl == own) rew += lay.r_kill;   // lib/laser.py:57
+                const int own = __shfl_sync(tmask, (int)(meta & 0xffu), gshift + killer);
+                if (gl == own) rew += lay.r_kill;        // lib/laser.py:57
             }
-            if (b) {
-                if (gl == killer) hit_any = true;
-                alive_bits &= ~(1u << s);
-                kills += 1;                              // event (1, t)
-                deaths += 1;                             // event (10, t): hull 1, never restored
-                if (gl == s) {                           // lib/ship.py:127-131,225-230
-                    hull -= 1;
-                    alive = false;
-                    rew += lay.r_death;
-                }
+            if (gl == killer) hit_any = true;
+            alive_bits &= ~(1u << s);
+            kills += 1;                                  // event (1, t)
+            deaths += 1;                                 // event (10, t): hull 1, never restored
+            if (gl == s) {                               // lib/ship.py:127-131,225-230
+                hull -= 1;
+                alive = false;
+                rew += lay.r_death;
             }
         }
         const bool destroyed = live && (hit_any || x < 0.0 || y < 0.0 || x >= (double)lay.W || y >= (double)lay.H);
@@ -224,23 +247,24 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     // shoot rewards: enemies j<i are seen after their move, j>i before it
     {
         const unsigned alive_now = (__ballot_sync(FULL, alive) >> gshift) & GM;
+        const unsigned any_shooter = __ballot_sync(FULL, shooter) & tmask;
         bool aimed = false, traj = false;
-        for (int j = 0; j < S; j++) {
-            const int jnx = __shfl_sync(FULL, sx, gshift + j), jny = __shfl_sync(FULL, sy, gshift + j);
-            const int jox = __shfl_sync(FULL, old_x, gshift + j), joy = __shfl_sync(FULL, old_y, gshift + j);
-            if (shooter && j != gl && ((alive_now >> j) & 1u)) {
-                const int ox = j < gl ? jnx : jox, oy = j < gl ? jny : joy;
-                const int ax = ox - spx, ay = oy - spy;
-                if (ax * ax + ay * ay <= OFB_R_SHIP * OFB_R_SHIP) aimed = true;     // lib/ship.py:165-169
-                if (!traj && on_trajectory(spx - sx, spy - sy, ox - sx, oy - sy, near_ties)) traj = true;
+        if (any_shooter) {
+            for (int j = 0; j < S; j++) {
+                const int jnx = __shfl_sync(tmask, sx, gshift + j), jny = __shfl_sync(tmask, sy, gshift + j);
+                const int jox = __shfl_sync(tmask, old_x, gshift + j), joy = __shfl_sync(tmask, old_y, gshift + j);
+                if (shooter && j != gl && ((alive_now >> j) & 1u)) {
+                    const int ox = j < gl ? jnx : jox, oy = j < gl ? jny : joy;
+                    const int ax = ox - spx, ay = oy - spy;
+                    if (ax * ax + ay * ay <= OFB_R_SHIP * OFB_R_SHIP) aimed = true;     // lib/ship.py:165-169
+                    if (!traj && on_trajectory(spx - sx, spy - sy, ox - sx, oy - sy, near_ties)) traj = true;
+                }
             }
         }
         if (aimed) rew += lay.r_aim;
         if (traj) rew += lay.r_traj;
-    }
-    // append the new lasers in ship order (lib/ship.py:151)
-    {
-        const unsigned sh = (__ballot_sync(FULL, shooter) >> gshift) & GM;
+        // append the new lasers in ship order (lib/ship.py:151)
+        const unsigned sh = any_shooter >> gshift;
         const int slot = w + __popc(sh & ((1u << gl) - 1u));
         if (shooter && slot < L) {
             lx[slot] = nlx; ly[slot] = nly; ldx[slot] = ndx; ldy[slot] = ndy;
@@ -251,9 +275,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         overflow += max(0, want - L);
         n = min(want, L);
     }
-    int nt = near_ties;
-#pragma unroll
-    for (int o = LPA / 2; o > 0; o >>= 1) nt += __shfl_xor_sync(FULL, nt, o);
+    int nt = __reduce_add_sync(tmask, near_ties);
 
     // ---- store ----
     if (is_ship) {
@@ -274,16 +296,22 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     if (ok && gl == 0) {
         int4 *h4 = reinterpret_cast<int4 *>(hdr);
         h4[0] = make_int4(time, n, kills, deaths);
-        h4[1] = make_int4(shots, overflow, hdr[HDR_EPISODE], hdr[HDR_NEARTIES] + nt);
+        h4[1] = make_int4(shots, overflow, episode, near0 + nt);
     }
 }
 
-static inline int lpa_for(int S) { return S <= 8 ? 8 : (S <= 16 ? 16 : 32); }
+// lanes per arena: the smallest tile that holds the ships, widened while the batch is too small to fill the GPU
+// (more lanes = more lasers per pass and more warps in flight)
+static inline int lpa_for(int S, long long n_arenas) {
+    int lpa = S <= 8 ? 8 : (S <= 16 ? 16 : 32);
+    while (lpa < 32 && n_arenas * lpa / 32 < 148 * 32) lpa *= 2;
+    return lpa;
+}
 
 extern "C" int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *stream) {
     if (!h || !actions_dev) { ofb_set_error("ofb_step: null argument"); return OFB_E_ARG; }
     cudaStream_t st = (cudaStream_t)stream;
-    const int lpa = lpa_for(h->lay.S);
+    const int lpa = lpa_for(h->lay.S, h->n_arenas);
     const int apw = 32 / lpa;
     const int threads = 128;
     const long long warps = (h->n_arenas + apw - 1) / apw;
