@@ -193,11 +193,8 @@ def gpu_arm(args, wl):
             if policy is not None:
                 bg.raster("bits", out=maps)        # Battleground.restart builds a fresh Observation
         if policy is not None:
-            bg.request_actions()                   # scripted bots fill their rows; policy rows are "external"
-            policy.act(bg, maps)                   # forward on the current maps -> the policy ship's action row
-            bg.generate_frame()
-        else:
-            bg.frame()
+            policy.act(bg, maps)                   # forward on the current maps -> the policy ship's ("external") action row
+        bg.frame()                                 # scripted bots + step in one launch
         bg.raster("bits", out=maps)
         launches[0] += bg.launch_count + (policy.launch_count if policy is not None else 0) - n0
 

@@ -114,6 +114,13 @@ int ofb_raster(const ofb_arenas *h, void *out_dev, int format, void *stream);
  * when NULL every ship uses bot_kind. */
 int ofb_bot_actions(const ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed,
                     int64_t arena0, uint32_t step, int16_t *actions_dev, void *stream);
+/* request_actions + generate_frame in one launch (Battleground.frame, lib/battleground.py:163-166, with the
+ * scripted bots of agents/agent.py): every ship whose kind is not OFB_BOT_EXTERNAL draws its action inside the
+ * step kernel (same Philox counters as ofb_bot_actions, so results are identical to the two-call form);
+ * external ships read their row from actions_dev (may be NULL when no ship is external). */
+int ofb_step_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed, int64_t arena0, uint32_t step,
+                  const int16_t *actions_dev, float *obs_out_dev, void *stream);
+
 /* randint(0, W) x randint(0, H) spawn draws of lib/battleground.py:79-81,114. */
 int ofb_random_spawn(int64_t n_arenas, int n_ships, int width, int height, uint64_t seed, int64_t arena0,
                      uint32_t episode, int32_t *spawn_dev, void *stream);

@@ -77,6 +77,8 @@ def load():
     lib.ofb_state_stride.argtypes = [vp]
     lib.ofb_state_stride.restype = i64
     lib.ofb_step_host.argtypes = [vp, vp, vp, vp]
+    lib.ofb_step_bots.argtypes = [vp, i32, vp, u64, i64, u32, vp, vp, vp]
+    lib.ofb_step_bots.restype = i32
     lib.ofb_reset.argtypes = [vp, vp, vp, vp, vp]
     lib.ofb_step.argtypes = [vp, vp, vp, vp]
     lib.ofb_obs_vec.argtypes = [vp, vp, vp]

@@ -43,10 +43,13 @@ class ScriptedBots:
         self.seed = int(seed)
         self._kinds_dev = None
 
-    def play_batch(self, obs_vec, bg):
+    def _ensure_kinds(self, bg):
         if self._kinds_dev is None:
             self._kinds_dev = torch.tensor([_lib.BOT_KINDS[k] for k in self.kinds], dtype=torch.uint8,
                                            device=bg.device)
+
+    def play_batch(self, obs_vec, bg):
+        self._ensure_kinds(bg)
         _lib.check(bg._lib.ofb_bot_actions(bg._h, 0, _ptr(self._kinds_dev), self.seed, bg.arena0,
                                            bg.total_steps, _ptr(bg.actions), bg._stream()))
         bg.launch_count += 1
@@ -203,7 +206,18 @@ class BatchedBattleground:
 
     def frame(self):
         """lib/battleground.py:163-166; the raster (absolute_state) is produced on demand by
-        ``raster()`` / consumed directly by the policy."""
+        ``raster()`` / consumed directly by the policy.  With the built-in device bots the
+        request_actions + generate_frame pair is one fused launch (ofb_step_bots): non-external ships
+        draw their action inside the step kernel, external ships (policy, host bots) use the rows
+        already present in ``self.actions``."""
+        if isinstance(self.bot, ScriptedBots):
+            self.bot._ensure_kinds(self)
+            _lib.check(self._lib.ofb_step_bots(self._h, 0, _ptr(self.bot._kinds_dev), self.bot.seed, self.arena0,
+                                               self.total_steps, _ptr(self.actions), _ptr(self.obs_vec), self._stream()))
+            self.launch_count += 1
+            self.time += 1
+            self.total_steps += 1
+            return
         self.actions = self.request_actions()
         self.generate_frame(self.actions)
 

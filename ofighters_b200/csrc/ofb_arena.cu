@@ -139,33 +139,7 @@ __global__ void k_bot_actions(const char *state, ArenaLayout lay, int kind, cons
     if (kinds) kind = kinds[i];
     if (kind == OFB_BOT_EXTERNAL) return;                     // row is written by someone else (policy, host bot)
     const int *ship = reinterpret_cast<const int *>(state + a * (long long)lay.stride + lay.off_ship);
-    uint32_t c[4] = {(uint32_t)(arena0 + a), (uint32_t)i, step, 0u};
-    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    int shoot = 0, thrust = 0, px = ship[SF_PX * lay.SP + i], py = ship[SF_PY * lay.SP + i];
-    const int rx = (int)mulhi32(c[1], (uint32_t)lay.W + 1), ry = (int)mulhi32(c[2], (uint32_t)lay.H + 1);
-    switch (kind) {
-    case OFB_BOT_RANDOM: {                                    // agents/agent.py:123-133
-        uint32_t k = mulhi32(c[0], 3u);
-        shoot = k == 0; thrust = k == 1;
-        if (k == 2) { px = rx; py = ry; }
-    } break;
-    case OFB_BOT_TURRET:                                      // agents/agent.py:136-144
-        shoot = mulhi32(c[0], 10u) < 8;
-        if (mulhi32(c[3], 10u) < 3) { px = rx; py = ry; }
-        break;
-    case OFB_BOT_RUNNER:                                      // agents/agent.py:147-155
-        thrust = mulhi32(c[0], 10u) < 9;
-        if (mulhi32(c[3], 10u) < 1) { px = rx; py = ry; }
-        break;
-    case OFB_BOT_THRUST: thrust = 1; break;                   // agents/agent.py:107-112
-    case OFB_BOT_SHOOT: shoot = 1; break;                     // agents/agent.py:115-120
-    case OFB_BOT_STRESS:                                      // agents/qlearnIA_V2.py:317-321, shoot forced
-        shoot = 1; thrust = (int)(c[0] & 1u);
-        px = (int)mulhi32(c[1], (uint32_t)lay.W); py = (int)mulhi32(c[2], (uint32_t)lay.H);
-        break;
-    default: break;                                           // idle: agents/agent.py:99-104
-    }
-    actions[t] = make_int2((shoot & 0xffff) | (thrust << 16), (px & 0xffff) | (py << 16));
+    actions[t] = bot_action(kind, seed, arena0 + a, i, step, ship[SF_PX * lay.SP + i], ship[SF_PY * lay.SP + i], lay.W, lay.H);
 }
 
 __global__ void k_random_spawn(int S, int W, int H, uint64_t seed, long long arena0, uint32_t episode, int2 *spawn,

@@ -77,6 +77,40 @@ __host__ __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) {
     return (uint32_t)(((uint64_t)a * b) >> 32);
 }
 
+// Scripted bots of agents/agent.py:99-155 (+ the stress distribution of SURVEY 8(d) config 4): the action row
+// (shoot | thrust << 16, px | py << 16) of ship `ship` of global arena `arena` at frame `step`; (px, py) is the
+// ship's current pointing, kept unless the bot re-points.  Shared by k_bot_actions and the fused step kernel.
+__device__ __forceinline__ int2 bot_action(int kind, uint64_t seed, long long arena, int ship, uint32_t step, int px, int py,
+                                           int W, int H) {
+    uint32_t c[4] = {(uint32_t)arena, (uint32_t)ship, step, 0u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    int shoot = 0, thrust = 0;
+    const int rx = (int)mulhi32(c[1], (uint32_t)W + 1), ry = (int)mulhi32(c[2], (uint32_t)H + 1);
+    switch (kind) {
+    case OFB_BOT_RANDOM: {                                    // agents/agent.py:123-133
+        const uint32_t k = mulhi32(c[0], 3u);
+        shoot = k == 0; thrust = k == 1;
+        if (k == 2) { px = rx; py = ry; }
+    } break;
+    case OFB_BOT_TURRET:                                      // agents/agent.py:136-144
+        shoot = mulhi32(c[0], 10u) < 8;
+        if (mulhi32(c[3], 10u) < 3) { px = rx; py = ry; }
+        break;
+    case OFB_BOT_RUNNER:                                      // agents/agent.py:147-155
+        thrust = mulhi32(c[0], 10u) < 9;
+        if (mulhi32(c[3], 10u) < 1) { px = rx; py = ry; }
+        break;
+    case OFB_BOT_THRUST: thrust = 1; break;                   // agents/agent.py:107-112
+    case OFB_BOT_SHOOT: shoot = 1; break;                     // agents/agent.py:115-120
+    case OFB_BOT_STRESS:                                      // agents/qlearnIA_V2.py:317-321, shoot forced
+        shoot = 1; thrust = (int)(c[0] & 1u);
+        px = (int)mulhi32(c[1], (uint32_t)W); py = (int)mulhi32(c[2], (uint32_t)H);
+        break;
+    default: break;                                           // idle: agents/agent.py:99-104
+    }
+    return make_int2((shoot & 0xffff) | (thrust << 16), (px & 0xffff) | (py << 16));
+}
+
 void ofb_set_error(const char *fmt, ...);
 #define OFB_CUDA_CHECK(expr)                                                              \
     do {                                                                                  \

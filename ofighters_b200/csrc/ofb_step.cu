@@ -66,10 +66,18 @@ __device__ __noinline__ bool on_trajectory(int ux, int uy, int vx, int vy, int &
     return on_trajectory_formula(ux, uy, vx, vy);
 }
 
+struct BotSpec {
+    int enabled, kind;
+    const uint8_t *kinds;
+    uint64_t seed;
+    long long arena0;
+    uint32_t step;
+};
+
 template <int LPA>
 __global__ void __launch_bounds__(128, 8)
 k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions,
-       float4 *__restrict__ obs_out, long long n_arenas) {
+       float4 *__restrict__ obs_out, long long n_arenas, const BotSpec bots) {
     constexpr int APW = 32 / LPA;
     constexpr unsigned GM = (LPA == 32) ? 0xffffffffu : ((1u << LPA) - 1u);
     const int lane = threadIdx.x & 31;
@@ -104,7 +112,11 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         score = ship[SF_SCORE * SP + gl];
         steps = ship[SF_STEPS * SP + gl];
         flags = ship[SF_FLAGS * SP + gl];
-        act = actions[arena * S + gl];
+        // scripted bots fused in front of the step: the action is drawn in registers (same Philox counters as
+        // k_bot_actions); ships of kind "external" (policy / host bots) read their row from `actions`
+        const int kind = bots.enabled ? (bots.kinds ? bots.kinds[gl] : bots.kind) : OFB_BOT_EXTERNAL;
+        if (kind == OFB_BOT_EXTERNAL) act = actions[arena * S + gl];
+        else act = bot_action(kind, bots.seed, bots.arena0 + arena, gl, bots.step, spx, spy, lay.W, lay.H);
     }
     unsigned p_meta = 0x100u;
     double p_x = 0.0, p_y = 0.0, p_dx = 0.0, p_dy = 0.0;
@@ -308,8 +320,7 @@ static inline int lpa_for(int S, long long n_arenas) {
     return lpa;
 }
 
-extern "C" int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *stream) {
-    if (!h || !actions_dev) { ofb_set_error("ofb_step: null argument"); return OFB_E_ARG; }
+static int launch_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, const BotSpec &bots, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int lpa = lpa_for(h->lay.S, h->n_arenas);
     const int apw = 32 / lpa;
@@ -319,11 +330,31 @@ extern "C" int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_ou
     if (blocks == 0) return OFB_OK;
     const int2 *act = reinterpret_cast<const int2 *>(actions_dev);
     float4 *obs = reinterpret_cast<float4 *>(obs_out_dev);
-    if (lpa == 8) k_step<8><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas);
-    else if (lpa == 16) k_step<16><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas);
-    else k_step<32><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas);
+    if (lpa == 8) k_step<8><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots);
+    else if (lpa == 16) k_step<16><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots);
+    else k_step<32><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
+}
+
+extern "C" int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *stream) {
+    if (!h || !actions_dev) { ofb_set_error("ofb_step: null argument"); return OFB_E_ARG; }
+    BotSpec none = {};
+    return launch_step(h, actions_dev, obs_out_dev, none, stream);
+}
+
+extern "C" int ofb_step_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed, int64_t arena0, uint32_t step,
+                             const int16_t *actions_dev, float *obs_out_dev, void *stream) {
+    if (!h || bot_kind < 0 || (bot_kind > OFB_BOT_STRESS && bot_kind != OFB_BOT_EXTERNAL)) {
+        ofb_set_error("ofb_step_bots: bad argument");
+        return OFB_E_ARG;
+    }
+    if (!actions_dev && (kinds_dev || bot_kind == OFB_BOT_EXTERNAL)) {
+        ofb_set_error("ofb_step_bots: ships of kind 'external' need an actions buffer");
+        return OFB_E_ARG;
+    }
+    BotSpec b = {1, bot_kind, kinds_dev, seed, (long long)arena0, step};
+    return launch_step(h, actions_dev, obs_out_dev, b, stream);
 }
 
 // Host-buffer form of ofb_step: the drop-in call for a host-side bot loop (Battleground.frame with
