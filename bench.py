@@ -106,6 +106,31 @@ def physical_gpu_index(local_rank):
     return local_rank
 
 
+# ----------------------------------------------------------------------------- L2 flush
+class L2Flush:
+    """Evicts the working set from the 126 MB L2 between timed iterations: a 256 MiB memset (the write the
+    timing rules ask for) followed by a 256 MiB read of a second buffer.  The read pass matters: L2 is
+    write-back, so a bare memset leaves ~100 MB of DIRTY lines behind and their write-back would be charged
+    to the next timed kernel (measured: see profiles/r01_flush_study.md)."""
+
+    def __init__(self, dev, mode="write+read"):
+        import torch
+        self.mode = mode
+        self.w = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+        self.r = torch.zeros(64 * 2 ** 20, dtype=torch.float32, device=dev) if mode == "write+read" else None
+        self.acc = torch.empty((), dtype=torch.float32, device=dev)
+        self.torch = torch
+
+    def __call__(self):
+        self.w.zero_()
+        if self.r is not None:
+            self.torch.sum(self.r, dim=0, out=self.acc)
+
+    def describe(self):
+        return "flushed between steps (256 MiB memset%s, outside the per-step events)" % (
+            " + 256 MiB read so no dirty lines remain" if self.r is not None else "")
+
+
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_arm(wl, steps, warmup, n_cap=4096):
     """The reference's algorithm on the host cores: oracle/step_c.c (bots + step + raster, OpenMP).
@@ -181,7 +206,7 @@ def gpu_arm(args, wl):
     bg.raster("bits", out=maps)
     state_bytes = N * bg.state_stride
     flush_needed = state_bytes + maps.numel() * 4 < 2 * 126 * 2 ** 20
-    flush_buf = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev) if flush_needed else None
+    flush_buf = L2Flush(dev, args.flush) if flush_needed else None
     launches = [0]
 
     def one_step():
@@ -214,7 +239,7 @@ def gpu_arm(args, wl):
     wall0 = time.perf_counter()
     for k in range(steps):
         if flush_buf is not None:
-            flush_buf.zero_()
+            flush_buf()
         ev[k][0].record(stream)
         one_step()
         ev[k][1].record(stream)
@@ -236,7 +261,11 @@ def gpu_arm(args, wl):
     roof = kernel_roofline(bg, maps, flush_buf, wl, dev, policy)
 
     # ---- end-to-end through the public API with HOST buffers
-    e2e = e2e_arm(bg, maps, wl, dev, min(steps, 400 if policy is None else 20), world, policy)
+    def make_bg():
+        return BatchedBattleground(N, ships=ships, config=ArenaConfig(laser_cap=wl["lcap"]), device=dev, seed=SEED,
+                                   arena0=rank * N)
+
+    e2e = e2e_arm(bg, maps, wl, dev, min(steps, 400 if policy is None else 20), world, policy, make_bg)
 
     out = {
         "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster%s)" %
@@ -248,7 +277,7 @@ def gpu_arm(args, wl):
         "config": {"workload": args.workload, "desc": wl["desc"], "arenas_per_gpu": N, "arenas_total": N * world,
                    "ships_per_arena": S, "ship_steps_per_s": value * S, "map_format": "bits u32[N,2,5000]",
                    "episode": "restart every 200 frames inside the timed region",
-                   "l2": ("flushed between steps (256 MiB memset, outside the per-step events)" if flush_needed
+                   "l2": (flush_buf.describe() if flush_needed
                           else "working set %.0f MB > L2" % ((state_bytes + maps.numel() * 4) / 1e6)),
                    "wall_s_timed_region": wall},
         "gpu_launches": launches[0], "clocks": clocks, "e2e": e2e, "roofline": roof,
@@ -310,7 +339,7 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
         ts = []
         for _ in range(iters):
             if flush_buf is not None:
-                flush_buf.zero_()
+                flush_buf()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             nb = nbytes() if callable(nbytes) else nbytes
             a.record(stream)
@@ -329,13 +358,32 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
             "other_kernels": {"k_step": res["k_step"]}}
 
 
-def e2e_arm(bg, maps, wl, dev, steps, world, policy=None):
-    """Same metric through BatchedBattleground with HOST buffers: every step the host bot's action
-    tensor is copied from pinned memory, the step + raster run, and the per-ship observation heads
-    (what a host bot is shown, incl. its reward) are read back.  Maps stay in HBM for the policy."""
+def _max_over_ranks(dt, world, dev):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    return dt
+
+
+def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
+    """Same metric through BatchedBattleground with HOST buffers, wall clock, max over ranks.
+
+    Arena workloads -- headline `value`: replay of a HOST-resident action tape (the reference's record/replay
+    use, lib/record.py:32-39, and the parity mode of the tests): every frame the frame's int16 [N,S,4] actions
+    are copied from pinned host memory, step + raster run, and the float32 [N,S,8] observation heads (what every
+    bot is shown next, incl. its reward) are copied back to pinned host memory.  The copies are pipelined
+    against the kernels of neighbouring frames (ofb_step_host_async).  `closed_loop`: a host-side numpy bot
+    that reads frame k's observations before it sends frame k+1 (synchronous ofb_step_host; the numpy bot's
+    CPU time is inside the timed region).  Policy workloads: closed loop only (the forward dominates)."""
     import numpy as np
     import torch
     N, S = bg.n_arenas, bg.ships_number
+    out = {"unit": "env-steps/s", "h2d_bytes_per_step": N * S * 4 * 2, "d2h_bytes_per_step": N * S * 8 * 4}
+
+    # ---------------- closed loop (host numpy bot inside the timed region)
     rng = np.random.Generator(np.random.PCG64(7))
     T = 64
     kind = rng.integers(0, 3, size=(T, N, S), dtype=np.int16)
@@ -371,23 +419,67 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None):
             torch.cuda.current_stream(dev).synchronize()
         bg.raster("bits", out=maps)
 
+    cl_steps = min(steps, 100 if policy is None else 20)
     for k in range(3):
         host_step(k)
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
-    for k in range(steps):
+    for k in range(cl_steps):
         host_step(k)
     torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    if world > 1:
-        import torch.distributed as dist
-        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
-    return {"value": N * world * steps / dt, "unit": "env-steps/s", "h2d_bytes_per_step": act_host.numel() * 2,
-            "d2h_bytes_per_step": obs_host.numel() * 4, "steps": steps,
-            "what": "pinned host actions -> H2D -> step -> raster (maps stay in HBM) -> D2H obs heads; host-side "
-                    "random bot (numpy) inside the timed region; wall clock"}
+    dt = _max_over_ranks(time.perf_counter() - t0, world, dev)
+    closed = {"value": N * world * cl_steps / dt, "steps": cl_steps,
+              "what": "host numpy bot reads frame k's obs heads before sending frame k+1: pinned actions -> H2D -> "
+                      "step -> D2H obs heads -> sync -> raster (maps stay in HBM)%s; bot CPU time inside the timed "
+                      "region; wall clock" % (" -> policy forward" if policy is not None else "")}
+    if policy is not None or make_bg is None:
+        out.update(value=closed["value"], steps=cl_steps, what=closed["what"])
+        return out
+
+    # ---------------- action-tape replay, pipelined
+    # the tape: what the device bots of this workload play on a twin of the batch (same seed -> same episode)
+    steps = max(10, min(steps, (512 * 2 ** 20) // (N * S * 8)))     # keep the pinned tape under 512 MiB
+    twin = make_bg()
+    tape = torch.empty((steps + 3, N, S, 4), dtype=torch.int16).pin_memory()
+    for k in range(steps + 3):
+        if twin.time >= 200:
+            twin.restart()
+        tape[k].copy_(twin.request_actions())
+        twin.generate_frame()
+    want = {k: v.cpu() for k, v in twin.state(("ship_x", "ship_y", "ship_score", "ship_alive", "n_lasers", "kills")).items()}
+    del twin
+    rep = make_bg()
+    obs2 = [torch.empty((N, S, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
+
+    def tape_step(k):
+        if rep.time >= 200:
+            rep.restart()
+        rep.step_host(tape[k], obs2[k & 1], wait=False)     # queue H2D(k) | step(k) | D2H(k) on three streams
+        rep.raster("bits", out=maps)
+
+    for k in range(3):
+        tape_step(k)
+    rep.wait_host()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(3, steps + 3):
+        tape_step(k)
+    rep.wait_host()
+    torch.cuda.synchronize(dev)
+    dt = _max_over_ranks(time.perf_counter() - t0, world, dev)
+    got = {k: v.cpu() for k, v in rep.state(tuple(want)).items()}
+    same = all(torch.equal(got[k], want[k]) for k in want)
+    if not same:
+        raise SystemExit("e2e: the tape replay diverged from the device-bot run it was recorded from")
+    last = obs2[(steps + 2) & 1]
+    if not bool(torch.isfinite(last).all()):
+        raise SystemExit("e2e: observation heads did not arrive")
+    out.update(value=N * world * steps / dt, steps=steps, closed_loop=closed, replay_matches_device_run=same,
+               what="action-tape replay: pinned host int16[N,S,4] -> H2D -> step -> raster (maps stay in HBM) -> D2H of "
+                    "the float32[N,S,8] obs heads into pinned host memory, every frame; copies on their own streams "
+                    "overlap neighbouring frames' kernels (ofb_step_host_async); final state checked against the "
+                    "device-bot run the tape was recorded from; wall clock")
+    return out
 
 
 # ----------------------------------------------------------------------------- main
@@ -398,6 +490,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="arena4096", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
+                    help="L2 flush between timed steps when the working set is L2-sized")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -102,6 +102,13 @@ int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void
  * host buffers should be pinned; the call is asynchronous on `stream` -- synchronise before reading. */
 int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream);
 
+/* Pipelined form of ofb_step_host for a loop that feeds one action batch per frame (a recorded action tape, or a
+ * host bot that does not need frame k's observations before sending frame k+1): the H2D copy of the next frame
+ * and the D2H copy of the previous frame's observation heads run on streams owned by the handle and overlap the
+ * kernels on `stream`.  obs_host is valid, and actions_host reusable, after ofb_host_wait(). */
+int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream);
+int ofb_host_wait(ofb_arenas *h);
+
 /* Observation.analyse_ship head for every ship (lib/observation.py:101-123). */
 int ofb_obs_vec(const ofb_arenas *h, float *out_dev, void *stream);
 

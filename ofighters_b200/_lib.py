@@ -77,6 +77,8 @@ def load():
     lib.ofb_state_stride.argtypes = [vp]
     lib.ofb_state_stride.restype = i64
     lib.ofb_step_host.argtypes = [vp, vp, vp, vp]
+    lib.ofb_step_host_async.argtypes = [vp, vp, vp, vp]
+    lib.ofb_host_wait.argtypes = [vp]
     lib.ofb_step_bots.argtypes = [vp, i32, vp, u64, i64, u32, vp, vp, vp]
     lib.ofb_step_bots.restype = i32
     lib.ofb_reset.argtypes = [vp, vp, vp, vp, vp]
@@ -99,7 +101,7 @@ def load():
     for name in ("ofb_policy_create", "ofb_policy_destroy", "ofb_policy_set_engine", "ofb_policy_forward",
                  "ofb_policy_write_actions", "ofb_policy_pack_image", "ofb_policy_debug_tap"):
         getattr(lib, name).restype = i32
-    for name in ("ofb_create", "ofb_destroy", "ofb_laser_cap", "ofb_reset", "ofb_step", "ofb_step_host", "ofb_obs_vec", "ofb_raster",
+    for name in ("ofb_create", "ofb_destroy", "ofb_laser_cap", "ofb_reset", "ofb_step", "ofb_step_host", "ofb_step_host_async", "ofb_host_wait", "ofb_obs_vec", "ofb_raster",
                  "ofb_bot_actions", "ofb_random_spawn", "ofb_state_export", "ofb_state_import"):
         getattr(lib, name).restype = i32
     _lib = lib

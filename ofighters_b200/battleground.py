@@ -178,11 +178,14 @@ class BatchedBattleground:
         self.time += 1
         self.total_steps += 1
 
-    def step_host(self, actions_host, obs_host=None):
+    def step_host(self, actions_host, obs_host=None, wait=True):
         """``generate_frame`` for a host-side bot loop: ``actions_host`` int16 [N,S,4] and
-        ``obs_host`` float32 [N,S,8] are (pinned) HOST tensors; the copies ride the same stream as
+        ``obs_host`` float32 [N,S,8] are (pinned) HOST tensors -- the batched form of one
+        ``Battleground.frame()`` with Python bots.  ``wait=True``: the copies ride the same stream as
         the step (ofb_step_host) and the call returns once ``obs_host`` holds the next observation
-        heads -- the batched form of one ``Battleground.frame()`` with Python bots."""
+        heads.  ``wait=False``: pipelined (ofb_step_host_async) -- the call only queues the frame; the
+        H2D / D2H copies overlap the kernels of neighbouring frames, ``obs_host`` is valid after
+        ``wait_host()``.  Meant for replaying an action tape (lib/record.py) or open-loop bots."""
         if actions_host.dtype != torch.int16 or tuple(actions_host.shape) != (self.n_arenas, self.ships_number, 4) \
                 or actions_host.is_cuda or not actions_host.is_contiguous():
             raise Exception("Invalid actions : expected a contiguous host int16 tensor of shape {}.".format(
@@ -191,13 +194,18 @@ class BatchedBattleground:
                                      or tuple(obs_host.shape) != (self.n_arenas, self.ships_number, 8)):
             raise Exception("Invalid observation buffer : expected host float32 {}.".format(
                 (self.n_arenas, self.ships_number, 8)))
-        _lib.check(self._lib.ofb_step_host(self._h, C.c_void_p(actions_host.data_ptr()),
-                                           C.c_void_p(obs_host.data_ptr()) if obs_host is not None else None,
-                                           self._stream()))
+        fn = self._lib.ofb_step_host if wait else self._lib.ofb_step_host_async
+        _lib.check(fn(self._h, C.c_void_p(actions_host.data_ptr()),
+                      C.c_void_p(obs_host.data_ptr()) if obs_host is not None else None, self._stream()))
         self.launch_count += 1
         self.time += 1
         self.total_steps += 1
-        torch.cuda.current_stream(self.device).synchronize()
+        if wait:
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def wait_host(self):
+        """Block until the copies queued by ``step_host(..., wait=False)`` have completed."""
+        _lib.check(self._lib.ofb_host_wait(self._h))
 
     def algorithmic_step_bytes(self):
         """SURVEY 8(d) byte model of one K1 launch: 88 B per ship + 64 B per live laser."""

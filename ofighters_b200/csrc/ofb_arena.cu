@@ -244,6 +244,8 @@ extern "C" int ofb_create(const ofb_config *cfg, int64_t n_arenas, int device, c
     }
     h->stage_actions = nullptr;
     h->stage_obs = nullptr;
+    h->pipe_ready = 0;
+    h->host_seq = 0;
     const size_t n_ship = (size_t)n_arenas * c.n_ships;
     if (cudaMalloc(&h->stage_actions, n_ship * 4 * sizeof(int16_t)) != cudaSuccess ||
         cudaMalloc(&h->stage_obs, n_ship * 8 * sizeof(float)) != cudaSuccess) {
@@ -269,9 +271,41 @@ extern "C" int ofb_create(const ofb_config *cfg, int64_t n_arenas, int device, c
     return OFB_OK;
 }
 
+// streams, events and double-buffered staging of the pipelined host frame; created on first use
+int ofb_pipe_init(ofb_arenas *h) {
+    if (h->pipe_ready) return OFB_OK;
+    const size_t n_ship = (size_t)h->n_arenas * h->lay.S;
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
+    for (int i = 0; i < 2; i++) {
+        OFB_CUDA_CHECK(cudaMalloc(&h->pipe_actions[i], n_ship * 4 * sizeof(int16_t)));
+        OFB_CUDA_CHECK(cudaMalloc(&h->pipe_obs[i], n_ship * 8 * sizeof(float)));
+        OFB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        OFB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming));
+        OFB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
+    }
+    OFB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+    OFB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+    h->host_seq = 0;
+    h->pipe_ready = 1;
+    return OFB_OK;
+}
+
 extern "C" int ofb_destroy(ofb_arenas *h) {
     if (!h) return OFB_OK;
     cudaSetDevice(h->device);
+    if (h->pipe_ready) {
+        cudaStreamSynchronize(h->s_h2d);
+        cudaStreamSynchronize(h->s_d2h);
+        for (int i = 0; i < 2; i++) {
+            cudaFree(h->pipe_actions[i]);
+            cudaFree(h->pipe_obs[i]);
+            cudaEventDestroy(h->ev_h2d[i]);
+            cudaEventDestroy(h->ev_step[i]);
+            cudaEventDestroy(h->ev_d2h[i]);
+        }
+        cudaStreamDestroy(h->s_h2d);
+        cudaStreamDestroy(h->s_d2h);
+    }
     cudaFree(h->stage_actions);
     cudaFree(h->stage_obs);
     cudaFree(h->state);

@@ -39,6 +39,13 @@ struct ofb_arenas {
     char *state;      // n_arenas * stride bytes
     int16_t *stage_actions;   // [N,S,4] device staging for ofb_step_host
     float *stage_obs;         // [N,S,8]
+    // pipelined host frames (ofb_step_host_async): double-buffered staging, one stream per copy direction
+    int16_t *pipe_actions[2];
+    float *pipe_obs[2];
+    cudaStream_t s_h2d, s_d2h;
+    cudaEvent_t ev_h2d[2], ev_step[2], ev_d2h[2];
+    unsigned long long host_seq;
+    int pipe_ready;
 };
 
 static inline ArenaLayout make_layout(const ofb_config &c) {

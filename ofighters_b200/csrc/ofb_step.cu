@@ -371,3 +371,44 @@ extern "C" int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *
         OFB_CUDA_CHECK(cudaMemcpyAsync(obs_host, h->stage_obs, n_ship * 8 * sizeof(float), cudaMemcpyDeviceToHost, st));
     return OFB_OK;
 }
+
+// Pipelined form of ofb_step_host for a host loop that replays / produces one action batch per frame: the
+// H2D copy of frame k+1 and the D2H copy of frame k's observation heads run on their own streams, so both PCIe
+// directions overlap the kernels of `stream` (step k, raster k).  Staging is double-buffered:
+//   s_h2d : [wait step k-2] actions_host -> pipe_actions[k&1]
+//   stream: [wait h2d k] [wait d2h k-2] step k (reads pipe_actions[k&1], writes pipe_obs[k&1])
+//   s_d2h : [wait step k] pipe_obs[k&1] -> obs_host
+// obs_host is valid after ofb_host_wait(); actions_host may be reused after the same call (or after the next
+// ofb_step_host_async returns two frames later).
+int ofb_pipe_init(ofb_arenas *h);
+extern "C" int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream) {
+    if (!h || !actions_host) { ofb_set_error("ofb_step_host_async: null argument"); return OFB_E_ARG; }
+    int rc = ofb_pipe_init(h);
+    if (rc != OFB_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t n_ship = (size_t)h->n_arenas * h->lay.S;
+    const int i = (int)(h->host_seq & 1ull);
+    if (h->host_seq >= 2) OFB_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_step[i], 0));    // step k-2 has read pipe_actions[i]
+    OFB_CUDA_CHECK(cudaMemcpyAsync(h->pipe_actions[i], actions_host, n_ship * 4 * sizeof(int16_t), cudaMemcpyHostToDevice, h->s_h2d));
+    OFB_CUDA_CHECK(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
+    OFB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_h2d[i], 0));
+    if (obs_host && h->host_seq >= 2) OFB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_d2h[i], 0));   // pipe_obs[i] has left
+    rc = ofb_step(h, h->pipe_actions[i], obs_host ? h->pipe_obs[i] : nullptr, st);
+    if (rc != OFB_OK) return rc;
+    OFB_CUDA_CHECK(cudaEventRecord(h->ev_step[i], st));
+    if (obs_host) {
+        OFB_CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_step[i], 0));
+        OFB_CUDA_CHECK(cudaMemcpyAsync(obs_host, h->pipe_obs[i], n_ship * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+    }
+    OFB_CUDA_CHECK(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
+    h->host_seq++;
+    return OFB_OK;
+}
+
+// Block until every copy queued by ofb_step_host_async has completed (obs_host readable, actions_host reusable).
+extern "C" int ofb_host_wait(ofb_arenas *h) {
+    if (!h) { ofb_set_error("ofb_host_wait: null argument"); return OFB_E_ARG; }
+    if (!h->pipe_ready || h->host_seq == 0) return OFB_OK;
+    OFB_CUDA_CHECK(cudaEventSynchronize(h->ev_d2h[(h->host_seq - 1) & 1ull]));
+    return OFB_OK;
+}

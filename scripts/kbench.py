@@ -18,7 +18,7 @@ def timeit(fn, flush, iters=30):
     evs = []
     for _ in range(iters):
         if flush is not None:
-            flush.zero_()
+            flush()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(st)
         fn()
@@ -34,7 +34,8 @@ def run(N, S, bot, lcap, warm_frames):
     maps = torch.empty((N, 2, 5000), dtype=torch.int32, device=bg.device)
     for _ in range(warm_frames):
         bg.frame()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=bg.device)
+    from bench import L2Flush
+    flush = L2Flush(bg.device, FLUSH_MODE)
     live = int(bg.state(("n_lasers",))["n_lasers"].sum().item())
     step_bytes = 88 * N * S + 64 * live
     t_bot = timeit(lambda: bg.request_actions(), flush)
@@ -42,7 +43,7 @@ def run(N, S, bot, lcap, warm_frames):
     t_step_hot = timeit(lambda: bg.generate_frame(), None)
     t_ras = timeit(lambda: bg.raster("bits", out=maps), flush)
     t_frame = timeit(lambda: (bg.frame(), bg.raster("bits", out=maps)), flush)
-    out = {"N": N, "S": S, "bot": bot, "live_lasers_per_arena": live / N, "stride": bg.state_stride,
+    out = {"flush": FLUSH_MODE, "N": N, "S": S, "bot": bot, "live_lasers_per_arena": live / N, "stride": bg.state_stride,
            "us": {"bots": t_bot, "step_cold": t_step, "step_hot_l2": t_step_hot, "raster": t_ras, "frame+raster": t_frame},
            "step_alg_GBs": step_bytes / t_step / 1e3, "step_frac": step_bytes / t_step / 1e3 / PEAK,
            "raster_alg_GBs": N * 40000 / t_ras / 1e3, "raster_frac": N * 40000 / t_ras / 1e3 / PEAK,
@@ -52,8 +53,13 @@ def run(N, S, bot, lcap, warm_frames):
     torch.cuda.empty_cache()
 
 
+FLUSH_MODE = "write+read"
+
 if __name__ == "__main__":
-    Ns = [int(a) for a in sys.argv[1:]] or [4096, 65536, 131072]
+    args = sys.argv[1:]
+    if args and args[0].startswith("--flush="):
+        FLUSH_MODE = args.pop(0).split("=", 1)[1]
+    Ns = [int(a) for a in args] or [4096, 65536, 131072]
     for N in Ns:
         run(N, 7, "random", 0, 40)
     run(16384, 32, "stress", 2048, 12)

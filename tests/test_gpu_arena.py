@@ -157,3 +157,34 @@ def test_sharded_arenas_equal_the_unsharded_run():
         assert torch.equal(torch.cat([q[k] for q in ps]), w[k]), k
     assert torch.equal(sum(p.stats for p in parts), whole.stats)
     assert torch.equal(torch.cat([p.raster("bits") for p in parts]), whole.raster("bits"))
+
+
+@pytest.mark.parametrize("wait", [True, False], ids=["sync", "pipelined"])
+def test_host_tape_replay_matches_c_restatement(wait):
+    """ofb_step_host / ofb_step_host_async: a HOST action tape replayed frame by frame gives the oracle's state,
+    and every frame's observation heads land in the host buffer they were queued for."""
+    from oracle.step_c import ArenasC
+    GpuEngine = _gpu()
+    N, S, T = 211, 7, 60
+    c = ArenasC(np.zeros((N, S, 2), np.int32))
+    spawn = c.random_spawn(21, 0)
+    g = GpuEngine(spawn)
+    bg = g.bg
+    c = ArenasC(spawn, lcap=bg.laser_cap)
+    tape = torch.empty((T, N, S, 4), dtype=torch.int16).pin_memory()
+    obs = torch.full((T, N, S, 8), float("nan"), dtype=torch.float32).pin_memory()
+    want_obs = np.empty((T, N, S, 8), np.float32)
+    for t in range(T):
+        a = c.bot_actions("random", 21, t)
+        tape[t].copy_(torch.from_numpy(a))
+        c.step(a)
+        want_obs[t] = c.obs_vec()
+    maps = None
+    for t in range(T):
+        bg.step_host(tape[t], obs[t], wait=wait)
+        maps = bg.raster("bits", out=maps)
+    bg.wait_host()
+    torch.cuda.synchronize()
+    _compare_states(g, c, "after host tape")
+    assert np.array_equal(obs.numpy(), want_obs)
+    assert np.array_equal(maps.cpu().numpy().view(np.uint32), c.raster_bits())
