@@ -38,25 +38,22 @@ __global__ void k_init(char *state, ArenaLayout lay, const int32_t *spawn, long 
     int i = (int)(t % lay.SP);
     if (a >= n_arenas) return;
     char *base = state + a * (long long)lay.stride;
-    int *ship = reinterpret_cast<int *>(base + lay.off_ship);
+    uint4 *ship = reinterpret_cast<uint4 *>(base + lay.off_ship);
     if (i == 0) {
-        int *hdr = reinterpret_cast<int *>(base);
-        for (int k = 0; k < 8; k++) hdr[k] = 0;
+        int4 *hdr = reinterpret_cast<int4 *>(base);
+        hdr[0] = make_int4(0, 0, 0, 0);
+        hdr[1] = make_int4(0, 0, 0, 0);
     }
-    int x = 0, y = 0, fl = 0;
+    ShipRec r = {};
     if (i < lay.S) {
-        x = spawn[(a * lay.S + i) * 2];
-        y = spawn[(a * lay.S + i) * 2 + 1];
-        fl = 1 | (1 << 8);                                   // flying, hull 1 (lib/ship.py:45,55)
+        r.x = spawn[(a * lay.S + i) * 2];
+        r.y = spawn[(a * lay.S + i) * 2 + 1];
+        r.px = r.x;                                          // pointing = own position (lib/ship.py:52)
+        r.py = r.y;
+        r.hull = 1;                                          // flying, hull 1 (lib/ship.py:45,55)
+        r.alive = true;
     }
-    ship[SF_X * lay.SP + i] = x;
-    ship[SF_Y * lay.SP + i] = y;
-    ship[SF_PX * lay.SP + i] = x;                            // pointing = own position (lib/ship.py:52)
-    ship[SF_PY * lay.SP + i] = y;
-    ship[SF_REWARD * lay.SP + i] = 0;
-    ship[SF_SCORE * lay.SP + i] = 0;
-    ship[SF_STEPS * lay.SP + i] = 0;
-    ship[SF_FLAGS * lay.SP + i] = fl;
+    ship[i] = ship_pack(r);
 }
 
 // Battleground.restart (lib/battleground.py:108-117) + Ship.reset (lib/ship.py:92-106) +
@@ -76,20 +73,19 @@ k_reset(char *state, ArenaLayout lay, const uint8_t *mask, const int32_t *spawn,
     if (ok) {
         char *base = state + a * (long long)lay.stride;
         int *hdr = reinterpret_cast<int *>(base);
-        int *ship = reinterpret_cast<int *>(base + lay.off_ship);
+        uint4 *ship = reinterpret_cast<uint4 *>(base + lay.off_ship);
         if (lane < lay.S) {
-            const int SP = lay.SP;
-            acc_score = ship[SF_SCORE * SP + lane];          // scores.append(score)
-            const int ox = ship[SF_X * SP + lane], oy = ship[SF_Y * SP + lane];
+            ShipRec r = ship_unpack(ship[lane]);
+            acc_score = r.score;                             // scores.append(score)
             const int nx = spawn[(a * lay.S + lane) * 2], ny = spawn[(a * lay.S + lane) * 2 + 1];
-            ship[SF_PX * SP + lane] = ox;                    // pointing = OLD position
-            ship[SF_PY * SP + lane] = oy;
-            ship[SF_X * SP + lane] = nx ? nx : ox;           // "x or self.body.x": 0 keeps old
-            ship[SF_Y * SP + lane] = ny ? ny : oy;
-            ship[SF_SCORE * SP + lane] = 0;
-            ship[SF_STEPS * SP + lane] = 0;
-            ship[SF_FLAGS * SP + lane] |= 1;                 // flying again; hull NOT restored
+            r.px = r.x;                                      // pointing = OLD position
+            r.py = r.y;
+            r.x = nx ? nx : r.x;                             // "x or self.body.x": 0 keeps old
+            r.y = ny ? ny : r.y;
+            r.score = 0;
+            r.alive = true;                                  // flying again; hull NOT restored
             // pending reward survives the reset (agents/agent.py:59-64)
+            ship[lane] = ship_pack(r);
         }
         k = hdr[HDR_KILLS]; d = hdr[HDR_DEATHS]; sh = hdr[HDR_SHOTS];
     }
@@ -122,11 +118,9 @@ __global__ void k_obs_vec(const char *state, ArenaLayout lay, float4 *out, long 
     if (t >= n_ships_total) return;
     long long a = t / lay.S;
     int i = (int)(t % lay.S);
-    const int *ship = reinterpret_cast<const int *>(state + a * (long long)lay.stride + lay.off_ship);
-    const int SP = lay.SP;
-    out[t * 2] = make_float4((float)ship[SF_REWARD * SP + i], 1.0f, (float)ship[SF_PX * SP + i],
-                             (float)ship[SF_PY * SP + i]);
-    out[t * 2 + 1] = make_float4((float)lay.W, (float)lay.H, (float)ship[SF_X * SP + i], (float)ship[SF_Y * SP + i]);
+    const ShipRec r = ship_unpack(reinterpret_cast<const uint4 *>(state + a * (long long)lay.stride + lay.off_ship)[i]);
+    out[t * 2] = make_float4((float)r.reward, 1.0f, (float)r.px, (float)r.py);
+    out[t * 2 + 1] = make_float4((float)lay.W, (float)lay.H, (float)r.x, (float)r.y);
 }
 
 // ---------------------------------------------------------------- scripted bots
@@ -138,8 +132,8 @@ __global__ void k_bot_actions(const char *state, ArenaLayout lay, int kind, cons
     int i = (int)(t % lay.S);
     if (kinds) kind = kinds[i];
     if (kind == OFB_BOT_EXTERNAL) return;                     // row is written by someone else (policy, host bot)
-    const int *ship = reinterpret_cast<const int *>(state + a * (long long)lay.stride + lay.off_ship);
-    actions[t] = bot_action(kind, seed, arena0 + a, i, step, ship[SF_PX * lay.SP + i], ship[SF_PY * lay.SP + i], lay.W, lay.H);
+    const ShipRec r = ship_unpack(reinterpret_cast<const uint4 *>(state + a * (long long)lay.stride + lay.off_ship)[i]);
+    actions[t] = bot_action(kind, seed, arena0 + a, i, step, r.px, r.py, lay.W, lay.H);
 }
 
 __global__ void k_random_spawn(int S, int W, int H, uint64_t seed, long long arena0, uint32_t episode, int2 *spawn,
@@ -158,50 +152,56 @@ __global__ void k_xfer(char *state, ArenaLayout lay, ofb_state_view v, long long
     if (a >= n_arenas) return;
     char *base = state + a * (long long)lay.stride;
     int *hdr = reinterpret_cast<int *>(base);
-    int *ship = reinterpret_cast<int *>(base + lay.off_ship);
-    double *lx = reinterpret_cast<double *>(base + lay.off_lx);
-    double *ly = reinterpret_cast<double *>(base + lay.off_ly);
-    double *ldx = reinterpret_cast<double *>(base + lay.off_ldx);
-    double *ldy = reinterpret_cast<double *>(base + lay.off_ldy);
-    unsigned *lmeta = reinterpret_cast<unsigned *>(base + lay.off_lmeta);
-    const int S = lay.S, SP = lay.SP, L = lay.L;
+    uint4 *ship = reinterpret_cast<uint4 *>(base + lay.off_ship);
+    const int S = lay.S, L = lay.L;
     int32_t *hv[8] = {v.time, v.n_lasers, v.kills, v.deaths, v.shots, v.overflow, v.episode, v.near_ties};
     if (threadIdx.x < 8 && hv[threadIdx.x]) {
         if (IMPORT) hdr[threadIdx.x] = hv[threadIdx.x][a];
         else hv[threadIdx.x][a] = hdr[threadIdx.x];
     }
-    int32_t *sv[7] = {v.ship_x, v.ship_y, v.ship_px, v.ship_py, v.ship_reward, v.ship_score, v.ship_steps};
     for (int i = threadIdx.x; i < S; i += blockDim.x) {
-        for (int f = 0; f < 7; f++)
-            if (sv[f]) {
-                if (IMPORT) ship[f * SP + i] = sv[f][a * S + i];
-                else sv[f][a * S + i] = ship[f * SP + i];
-            }
+        const long long o = a * S + i;
+        ShipRec r = ship_unpack(ship[i]);
         if (IMPORT) {
-            if (v.ship_alive && v.ship_hull)
-                ship[SF_FLAGS * SP + i] = (v.ship_alive[a * S + i] ? 1 : 0) | (v.ship_hull[a * S + i] << 8);
+            if (v.ship_x) r.x = v.ship_x[o];
+            if (v.ship_y) r.y = v.ship_y[o];
+            if (v.ship_px) r.px = v.ship_px[o];
+            if (v.ship_py) r.py = v.ship_py[o];
+            if (v.ship_reward) r.reward = v.ship_reward[o];
+            if (v.ship_score) r.score = v.ship_score[o];
+            if (v.ship_hull) r.hull = v.ship_hull[o];
+            if (v.ship_alive) r.alive = v.ship_alive[o] != 0;
+            ship[i] = ship_pack(r);                          // ship_steps is derived (= time) and ignored on import
         } else {
-            const int fl = ship[SF_FLAGS * SP + i];
-            if (v.ship_alive) v.ship_alive[a * S + i] = fl & 1;
-            if (v.ship_hull) v.ship_hull[a * S + i] = fl >> 8;
+            if (v.ship_x) v.ship_x[o] = r.x;
+            if (v.ship_y) v.ship_y[o] = r.y;
+            if (v.ship_px) v.ship_px[o] = r.px;
+            if (v.ship_py) v.ship_py[o] = r.py;
+            if (v.ship_reward) v.ship_reward[o] = r.reward;
+            if (v.ship_score) v.ship_score[o] = r.score;
+            if (v.ship_steps) v.ship_steps[o] = hdr[HDR_TIME];       // agent.steps == battleground.time (see ofb_common.cuh)
+            if (v.ship_hull) v.ship_hull[o] = r.hull;
+            if (v.ship_alive) v.ship_alive[o] = r.alive ? 1 : 0;
         }
     }
     for (int k = threadIdx.x; k < L; k += blockDim.x) {
         const long long o = a * L + k;
+        double *lx = reinterpret_cast<double *>(base + laser_off(lay.off_laser, k));
+        unsigned *lm = reinterpret_cast<unsigned *>(base + laser_meta_off(lay.off_laser, k));
         if (IMPORT) {
-            if (v.laser_x) lx[k] = v.laser_x[o];
-            if (v.laser_y) ly[k] = v.laser_y[o];
-            if (v.laser_dx) ldx[k] = v.laser_dx[o];
-            if (v.laser_dy) ldy[k] = v.laser_dy[o];
+            if (v.laser_x) lx[0] = v.laser_x[o];
+            if (v.laser_y) lx[OFB_G_Y / 8] = v.laser_y[o];
+            if (v.laser_dx) lx[OFB_G_DX / 8] = v.laser_dx[o];
+            if (v.laser_dy) lx[OFB_G_DY / 8] = v.laser_dy[o];
             if (v.laser_owner && v.laser_destroyed)
-                lmeta[k] = (unsigned)v.laser_owner[o] | (v.laser_destroyed[o] ? 0x100u : 0u);
+                *lm = (unsigned)v.laser_owner[o] | (v.laser_destroyed[o] ? 0x100u : 0u);
         } else {
             const bool live = k < hdr[HDR_NLASERS];
-            const unsigned m = live ? lmeta[k] : 0u;
-            if (v.laser_x) v.laser_x[o] = live ? lx[k] : 0.0;
-            if (v.laser_y) v.laser_y[o] = live ? ly[k] : 0.0;
-            if (v.laser_dx) v.laser_dx[o] = live ? ldx[k] : 0.0;
-            if (v.laser_dy) v.laser_dy[o] = live ? ldy[k] : 0.0;
+            const unsigned m = live ? *lm : 0u;
+            if (v.laser_x) v.laser_x[o] = live ? lx[0] : 0.0;
+            if (v.laser_y) v.laser_y[o] = live ? lx[OFB_G_Y / 8] : 0.0;
+            if (v.laser_dx) v.laser_dx[o] = live ? lx[OFB_G_DX / 8] : 0.0;
+            if (v.laser_dy) v.laser_dy[o] = live ? lx[OFB_G_DY / 8] : 0.0;
             if (v.laser_owner) v.laser_owner[o] = (uint8_t)(m & 0xffu);
             if (v.laser_destroyed) v.laser_destroyed[o] = (uint8_t)((m >> 8) & 1u);
         }
@@ -220,6 +220,9 @@ extern "C" int ofb_create(const ofb_config *cfg, int64_t n_arenas, int device, c
         ofb_set_error("ofb_create: width*height must be a multiple of 128 and fit int16 coordinates");
         return OFB_E_ARG;
     }
+    const int rw[4] = {c.reward_kill, c.reward_death, c.reward_aim, c.reward_trajectory};
+    for (int i = 0; i < 4; i++)
+        if (rw[i] < -500 || rw[i] > 500) { ofb_set_error("ofb_create: rewards must be within +-500 (pending reward is a 16-bit field)"); return OFB_E_ARG; }
     if (c.laser_cap <= 0) c.laser_cap = c.n_ships * 16 > 128 ? c.n_ships * 16 : 128;
     c.laser_cap = (c.laser_cap + 31) & ~31;
     int ndev = 0;

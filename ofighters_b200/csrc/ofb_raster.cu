@@ -35,9 +35,7 @@ k_raster(const char *__restrict__ state, const ArenaLayout lay, void *__restrict
     const long long a = blockIdx.x;
     const char *base = state + a * (long long)lay.stride;
     const int *hdr = reinterpret_cast<const int *>(base);
-    const int *ship = reinterpret_cast<const int *>(base + lay.off_ship);
-    const double *lx = reinterpret_cast<const double *>(base + lay.off_lx);
-    const double *ly = reinterpret_cast<const double *>(base + lay.off_ly);
+    const uint4 *ship = reinterpret_cast<const uint4 *>(base + lay.off_ship);
 
     const int n = hdr[HDR_NLASERS];
     {
@@ -50,8 +48,9 @@ k_raster(const char *__restrict__ state, const ArenaLayout lay, void *__restrict
     const int rows = 2 * OFB_R_SHIP - 1;
     for (int t = threadIdx.x; t < lay.S * rows; t += blockDim.x) {
         const int i = t / rows, dr = t % rows - (OFB_R_SHIP - 1);
-        if (!(ship[SF_FLAGS * lay.SP + i] & 1)) continue;
-        const int cx = ship[SF_X * lay.SP + i], y = ship[SF_Y * lay.SP + i] + dr;
+        const unsigned sxy = ship[i].x;                      // x | y << 16 | alive << 31
+        if (!(sxy >> 31)) continue;
+        const int cx = (int)(sxy & 0xffffu), y = (int)((sxy >> 16) & 0x7fffu) + dr;
         if (y < 0 || y >= H) continue;
         int hw = -1;
         for (int dc = 0; dc < OFB_R_SHIP; dc++)
@@ -61,7 +60,8 @@ k_raster(const char *__restrict__ state, const ArenaLayout lay, void *__restrict
     }
     // lasers: one thread per laser, <= 5x5 candidate pixels in fp64
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const double cx = lx[k], cy = ly[k], R = (double)OFB_R_LASER;
+        const double *lp = reinterpret_cast<const double *>(base + laser_off(lay.off_laser, k));
+        const double cx = lp[0], cy = lp[OFB_G_Y / 8], R = (double)OFB_R_LASER;
         long long ulr = (long long)ceil(__dsub_rn(cy, R)), ulc = (long long)ceil(__dsub_rn(cx, R));
         long long lrr = (long long)floor(__dadd_rn(cy, R)), lrc = (long long)floor(__dadd_rn(cx, R));
         ulr = ulr < 0 ? 0 : ulr;

@@ -74,68 +74,136 @@ struct BotSpec {
     uint32_t step;
 };
 
+// ---- mbarrier / bulk-copy wrappers (TMA-class copies without a tensor map) ----
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        if (++spins > (1u << 24)) __trap();              // a lost arrival must fail loudly, not hang the GPU
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#define STEP_THREADS 128
+#define STEP_BAR_BYTES 128               // 4 warp mbarriers in front of the tiles
+
+// One LPA-lane tile per arena.  The arena's header, ships and the LIVE prefix of its laser list reach shared memory
+// as bulk asynchronous copies counted on the warp's mbarrier:
+//   phase 0        header + ships + the first C0 = LPA/4 laser groups (issued before anything is known about the arena)
+//   phase 1        the remaining live groups of the first CH = LPA groups, issued as soon as n_lasers has landed and
+//                  overlapped with the first two chunk iterations
+//   phase p + 1    pass p >= 1 (more than 8 * LPA live lasers: rare), same buffer
+// Everything the loop reads comes from the shared-memory snapshot; results go straight to HBM (only the fields that
+// changed: x, y, meta of live lasers; dx, dy only for entries the compaction moved), so a tile never waits on a global
+// load inside the loop and the in-place compaction cannot race with its own reads.
 template <int LPA>
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(STEP_THREADS, 5)
 k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions,
-       float4 *__restrict__ obs_out, long long n_arenas, const BotSpec bots) {
+       float4 *__restrict__ obs_out, long long n_arenas, const BotSpec bots, const int tile_bytes) {
+    extern __shared__ __align__(128) unsigned char smem[];
     constexpr int APW = 32 / LPA;
+    constexpr int CH = LPA;                              // laser groups staged per pass = 8 chunk iterations
+    constexpr int C0 = LPA / 4;                          // groups copied with the header = 2 chunk iterations
     constexpr unsigned GM = (LPA == 32) ? 0xffffffffu : ((1u << LPA) - 1u);
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LPA, gl = lane % LPA;
     const unsigned gshift = g * LPA;
     const unsigned tmask = GM << gshift;                 // lanes of this arena's tile
     const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long arena = warp_global * APW + g;
     const bool ok = arena < n_arenas;
-    const int S = lay.S, SP = lay.SP, L = lay.L;
+    const bool leader = gl == 0;
+    const int S = lay.S, L = lay.L, off_l = lay.off_laser;
     char *base = state + (ok ? arena : 0) * (long long)lay.stride;
-    int *hdr = reinterpret_cast<int *>(base);
-    int *ship = reinterpret_cast<int *>(base + lay.off_ship);
-    double *lx = reinterpret_cast<double *>(base + lay.off_lx);
-    double *ly = reinterpret_cast<double *>(base + lay.off_ly);
-    double *ldx = reinterpret_cast<double *>(base + lay.off_ldx);
-    double *ldy = reinterpret_cast<double *>(base + lay.off_ldy);
-    unsigned *lmeta = reinterpret_cast<unsigned *>(base + lay.off_lmeta);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem) + warp;
+    unsigned char *tb = smem + STEP_BAR_BYTES + (warp * APW + g) * tile_bytes;
+    const int G_cap = L >> 3;
 
-    // ---- issue every load of the first round trip at once: header, ships, actions and -- speculatively,
-    //      before the laser count is known -- the first LPA laser slots (they always exist: L >= 32)
-    int hv = (ok && gl < 8) ? hdr[gl] : 0;
-    const bool is_ship = ok && gl < S;
-    int sx = 0, sy = 0, spx = 0, spy = 0, rew = 0, score = 0, steps = 0, flags = 0;
-    int2 act = make_int2(0, 0);
-    if (is_ship) {
-        sx = ship[SF_X * SP + gl];
-        sy = ship[SF_Y * SP + gl];
-        spx = ship[SF_PX * SP + gl];
-        spy = ship[SF_PY * SP + gl];
-        rew = ship[SF_REWARD * SP + gl];
-        score = ship[SF_SCORE * SP + gl];
-        steps = ship[SF_STEPS * SP + gl];
-        flags = ship[SF_FLAGS * SP + gl];
-        // scripted bots fused in front of the step: the action is drawn in registers (same Philox counters as
-        // k_bot_actions); ships of kind "external" (policy / host bots) read their row from `actions`
-        const int kind = bots.enabled ? (bots.kinds ? bots.kinds[gl] : bots.kind) : OFB_BOT_EXTERNAL;
-        if (kind == OFB_BOT_EXTERNAL) act = actions[arena * S + gl];
-        else act = bot_action(kind, bots.seed, bots.arena0 + arena, gl, bots.step, spx, spy, lay.W, lay.H);
+    if (lane == 0) {
+        mbar_init(mbar, APW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    unsigned p_meta = 0x100u;
-    double p_x = 0.0, p_y = 0.0, p_dx = 0.0, p_dy = 0.0;
-    if (ok) { p_meta = lmeta[gl]; p_x = lx[gl]; p_y = ly[gl]; p_dx = ldx[gl]; p_dy = ldy[gl]; }
+    __syncwarp();
+    if (leader) {
+        if (ok) {
+            const unsigned bytes0 = (unsigned)(off_l + OFB_GROUP_BYTES * min(C0, G_cap));
+            mbar_expect_tx(mbar, bytes0);
+            bulk_g2s(tb, base, bytes0, mbar);
+        } else mbar_arrive(mbar);
+    }
 
-    int time = __shfl_sync(FULL, hv, gshift + HDR_TIME);
-    int n = __shfl_sync(FULL, hv, gshift + HDR_NLASERS);
-    int kills = __shfl_sync(FULL, hv, gshift + HDR_KILLS);
-    int deaths = __shfl_sync(FULL, hv, gshift + HDR_DEATHS);
-    int shots = __shfl_sync(FULL, hv, gshift + HDR_SHOTS);
-    int overflow = __shfl_sync(FULL, hv, gshift + HDR_OVERFLOW);
-    const int episode = __shfl_sync(FULL, hv, gshift + HDR_EPISODE);
-    const int near0 = __shfl_sync(FULL, hv, gshift + HDR_NEARTIES);
+    // ---- while the state is in flight: the action row, or the scripted bot's random words (they need nothing from the
+    //      arena; the kind byte is loaded first and interpreted after the Philox rounds)
+    const bool is_ship = ok && gl < S;
+    int2 act = make_int2(0, 0);
+    BotDraw draw = {};
+    int kind = OFB_BOT_EXTERNAL;
+    if (is_ship) {
+        if (bots.enabled) {
+            kind = bots.kinds ? (int)__ldg(bots.kinds + gl) : bots.kind;
+            const uint4 rnd = bot_random(bots.seed, bots.arena0 + arena, gl, bots.step);
+            if (kind != OFB_BOT_EXTERNAL) draw = bot_interpret(kind, rnd, lay.W, lay.H);
+        }
+        if (kind == OFB_BOT_EXTERNAL) act = actions[arena * S + gl];
+    }
+
+    mbar_wait(mbar, 0);
+    int time = 0, n = 0, kills = 0, deaths = 0, shots = 0, overflow = 0, episode = 0, near0 = 0;
+    if (ok) {
+        const int4 h0 = reinterpret_cast<const int4 *>(tb)[0], h1 = reinterpret_cast<const int4 *>(tb)[1];
+        time = h0.x; n = h0.y; kills = h0.z; deaths = h0.w;
+        shots = h1.x; overflow = h1.y; episode = h1.z; near0 = h1.w;
+    }
+    const int G_live = min((n + 7) >> 3, G_cap);
+    if (leader) {
+        const int hi = min(G_live, CH);
+        if (ok && hi > C0) {
+            const unsigned bytes1 = (unsigned)(OFB_GROUP_BYTES * (hi - C0));
+            mbar_expect_tx(mbar, bytes1);
+            bulk_g2s(tb + off_l + OFB_GROUP_BYTES * C0, base + off_l + OFB_GROUP_BYTES * C0, bytes1, mbar);
+        } else mbar_arrive(mbar);
+    }
+    ShipRec me = {};
+    if (is_ship) me = ship_unpack(reinterpret_cast<const uint4 *>(tb + lay.off_ship)[gl]);
+    int sx = me.x, sy = me.y, spx = me.px, spy = me.py, rew = me.reward, score = me.score, hull = me.hull;
+    bool alive = me.alive;
+    if (is_ship && kind != OFB_BOT_EXTERNAL) act = bot_apply(draw, spx, spy);
     int near_ties = 0;
-    bool alive = (flags & 1) != 0;
-    int hull = flags >> 8;
+
+    // centres of the ships that are alive at frame start, compacted, as floats for the box pre-filter; kept with their ship
+    // indices in the (now consumed) ship region of the tile
+    float2 *spos = reinterpret_cast<float2 *>(tb + lay.off_ship);
+    unsigned char *sid = tb + lay.off_ship + 8 * lay.SP;
+    const unsigned alive_bits = (__ballot_sync(FULL, alive) >> gshift) & GM;
+    const int n_alive = __popc(alive_bits);
+    unsigned alive_c = n_alive >= 32 ? 0xffffffffu : ((1u << n_alive) - 1u);      // by compact index
+    const int na_max = __reduce_max_sync(FULL, n_alive);
+    __syncwarp();
+    if (alive) {
+        const int r = __popc(alive_bits & ((1u << gl) - 1u));
+        spos[r] = make_float2((float)sx, (float)sy);
+        sid[r] = (unsigned char)gl;
+    }
+    __syncwarp();
 
     // ---- A1: score fold, dead ships included (agents/agent.py:66-74, lib/ship.py:260-262) ----
-    steps += 1;
     score += rew;
     rew = 0;
     // ---- A2 ----
@@ -146,68 +214,85 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     // that laser explodes on it (lib/laser.py:52-62).  Collisions are rare, so each lane first builds
     // the bit mask of ships its laser touches -- float box pre-filter, then the exact fp64 distance the
     // reference computes -- and the ballots that recover the list order run only when a mask is non-zero.
-    const float fsx = (float)sx, fsy = (float)sy;
-    unsigned alive_bits = (__ballot_sync(FULL, alive) >> gshift) & GM;
     int iters = (n + LPA - 1) / LPA;
     iters = __reduce_max_sync(FULL, iters);
     int w = 0;                                           // compaction write cursor
     for (int it = 0; it < iters; it++) {
-        const int k = it * LPA + gl;
-        const unsigned meta = p_meta;
-        double x = p_x, y = p_y;
-        const double dx = p_dx, dy = p_dy;
-        const bool live = ok && k < n && !(meta & 0x100u);
-        {   // prefetch the next chunk while this one is processed
-            const int kn = k + LPA;
-            if (ok && kn < n) { p_meta = lmeta[kn]; p_x = lx[kn]; p_y = ly[kn]; p_dx = ldx[kn]; p_dy = ldy[kn]; }
-            else p_meta = 0x100u;
+        const int pit = it & 7;                          // chunk iteration within the pass
+        if (it == 2) mbar_wait(mbar, 1);
+        else if (pit == 0 && it > 0) {                   // pass p: restage groups [p * CH, (p + 1) * CH)
+            const int p = it >> 3;
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (leader) {
+                const int lo = p * CH, hi = min(G_live, lo + CH);
+                if (ok && hi > lo) {
+                    const unsigned bytes = (unsigned)(OFB_GROUP_BYTES * (hi - lo));
+                    mbar_expect_tx(mbar, bytes);
+                    bulk_g2s(tb + off_l, base + off_l + OFB_GROUP_BYTES * lo, bytes, mbar);
+                } else mbar_arrive(mbar);
+            }
+            mbar_wait(mbar, (uint32_t)((p + 1) & 1));
         }
+        const int k = it * LPA + gl;
+        const unsigned char *lp = tb + off_l + ((pit * LPA + gl) >> 3) * OFB_GROUP_BYTES + (gl & 7) * 8;
+        const unsigned meta = *reinterpret_cast<const unsigned *>(lp + OFB_G_META - (gl & 7) * 4);
+        double x = *reinterpret_cast<const double *>(lp), y = *reinterpret_cast<const double *>(lp + OFB_G_Y);
+        const double dx = *reinterpret_cast<const double *>(lp + OFB_G_DX), dy = *reinterpret_cast<const double *>(lp + OFB_G_DY);
+        const bool live = ok && k < n && !(meta & 0x100u);
         if (live) {
             x = __dadd_rn(x, dx);                        // lib/laser.py:46-47
             y = __dadd_rn(y, dy);
         }
         const float fx = (float)x, fy = (float)y;
         unsigned hm = 0;
-        for (int s = 0; s < S; s++) {
-            const float ex = fx - __shfl_sync(FULL, fsx, gshift + s);
-            const float ey = fy - __shfl_sync(FULL, fsy, gshift + s);
-            if (fabsf(ex) <= 10.5f && fabsf(ey) <= 10.5f) hm |= 1u << s;      // superset of the radius-10 disk
+        for (int j = 0; j < na_max; j++) {               // entries beyond this tile's n_alive are masked by alive_c
+            const float2 c = spos[j];
+            const float m = fmaxf(fabsf(fx - c.x), fabsf(fy - c.y));
+            hm |= (m <= 10.5f ? 1u : 0u) << j;           // superset of the radius-10 disk
         }
-        hm = live ? (hm & alive_bits) : 0u;
+        hm = live ? (hm & alive_c) : 0u;
         bool hit_any = false;
-        unsigned cand = __reduce_or_sync(tmask, hm);
-        while (cand) {                                   // ships some laser of this chunk may touch (rare)
-            const int s = __ffs(cand) - 1;
-            cand &= cand - 1;
-            const double ddx = __dsub_rn(x, (double)__shfl_sync(tmask, sx, gshift + s));
-            const double ddy = __dsub_rn(y, (double)__shfl_sync(tmask, sy, gshift + s));
-            const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
-            const bool hit = ((hm >> s) & 1u) && d2 <= D2_HIT_MAX;
-            const unsigned b = (__ballot_sync(tmask, hit) >> gshift) & GM;
-            if (!b) continue;
-            const int killer = __ffs(b) - 1;
-            if (lay.r_kill != 0) {
-                const int own = __shfl_sync(tmask, (int)(meta & 0xffu), gshift + killer);
-                if (gl == own) rew += lay.r_kill;        // lib/laser.py:57
-            }
-            if (gl == killer) hit_any = true;
-            alive_bits &= ~(1u << s);
-            kills += 1;                                  // event (1, t)
-            deaths += 1;                                 // event (10, t): hull 1, never restored
-            if (gl == s) {                               // lib/ship.py:127-131,225-230
-                hull -= 1;
-                alive = false;
-                rew += lay.r_death;
+        if (__ballot_sync(FULL, hm != 0u) & tmask) {     // some laser of this tile's chunk may touch a ship (rare)
+            unsigned cand = __reduce_or_sync(tmask, hm);
+            while (cand) {
+                const int j = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int s = sid[j];
+                const double ddx = __dsub_rn(x, (double)__shfl_sync(tmask, sx, gshift + s));
+                const double ddy = __dsub_rn(y, (double)__shfl_sync(tmask, sy, gshift + s));
+                const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
+                const bool hit = ((hm >> j) & 1u) && d2 <= D2_HIT_MAX;
+                const unsigned b = (__ballot_sync(tmask, hit) >> gshift) & GM;
+                if (!b) continue;
+                const int killer = __ffs(b) - 1;
+                if (lay.r_kill != 0) {
+                    const int own = __shfl_sync(tmask, (int)(meta & 0xffu), gshift + killer);
+                    if (gl == own) rew += lay.r_kill;    // lib/laser.py:57
+                }
+                if (gl == killer) hit_any = true;
+                alive_c &= ~(1u << j);
+                kills += 1;                              // event (1, t)
+                deaths += 1;                             // event (10, t): hull 1, never restored
+                if (gl == s) {                           // lib/ship.py:127-131,225-230
+                    hull -= 1;
+                    alive = false;
+                    rew += lay.r_death;
+                }
             }
         }
         const bool destroyed = live && (hit_any || x < 0.0 || y < 0.0 || x >= (double)lay.W || y >= (double)lay.H);
         const unsigned lv = (__ballot_sync(FULL, live) >> gshift) & GM;
         const int pos = w + __popc(lv & ((1u << gl) - 1u));
         if (live) {
-            lx[pos] = x;
-            ly[pos] = y;
-            lmeta[pos] = (meta & 0xffu) | (destroyed ? 0x100u : 0u);
-            if (pos != k) { ldx[pos] = dx; ldy[pos] = dy; }
+            char *gp = base + laser_off(off_l, pos);
+            *reinterpret_cast<double *>(gp) = x;
+            *reinterpret_cast<double *>(gp + OFB_G_Y) = y;
+            *reinterpret_cast<unsigned *>(base + laser_meta_off(off_l, pos)) = (meta & 0xffu) | (destroyed ? 0x100u : 0u);
+            if (pos != k) {
+                *reinterpret_cast<double *>(gp + OFB_G_DX) = dx;
+                *reinterpret_cast<double *>(gp + OFB_G_DY) = dy;
+            }
         }
         w += __popc(lv);
     }
@@ -279,8 +364,12 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         const unsigned sh = any_shooter >> gshift;
         const int slot = w + __popc(sh & ((1u << gl) - 1u));
         if (shooter && slot < L) {
-            lx[slot] = nlx; ly[slot] = nly; ldx[slot] = ndx; ldy[slot] = ndy;
-            lmeta[slot] = (unsigned)gl;
+            char *gp = base + laser_off(off_l, slot);
+            *reinterpret_cast<double *>(gp) = nlx;
+            *reinterpret_cast<double *>(gp + OFB_G_Y) = nly;
+            *reinterpret_cast<double *>(gp + OFB_G_DX) = ndx;
+            *reinterpret_cast<double *>(gp + OFB_G_DY) = ndy;
+            *reinterpret_cast<unsigned *>(base + laser_meta_off(off_l, slot)) = (unsigned)gl;
         }
         const int want = w + __popc(sh);
         shots += __popc(sh);
@@ -291,22 +380,17 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
 
     // ---- store ----
     if (is_ship) {
-        ship[SF_X * SP + gl] = sx;
-        ship[SF_Y * SP + gl] = sy;
-        ship[SF_PX * SP + gl] = spx;
-        ship[SF_PY * SP + gl] = spy;
-        ship[SF_REWARD * SP + gl] = rew;
-        ship[SF_SCORE * SP + gl] = score;
-        ship[SF_STEPS * SP + gl] = steps;
-        ship[SF_FLAGS * SP + gl] = (alive ? 1 : 0) | (hull << 8);
+        ShipRec o;
+        o.x = sx; o.y = sy; o.px = spx; o.py = spy; o.score = score; o.reward = rew; o.hull = hull; o.alive = alive;
+        reinterpret_cast<uint4 *>(base + lay.off_ship)[gl] = ship_pack(o);
         if (obs_out) {                                   // lib/observation.py:113-123
-            float4 *o = obs_out + (arena * S + gl) * 2;
-            o[0] = make_float4((float)rew, 1.0f, (float)spx, (float)spy);
-            o[1] = make_float4((float)lay.W, (float)lay.H, (float)sx, (float)sy);
+            float4 *ob = obs_out + (arena * S + gl) * 2;
+            ob[0] = make_float4((float)rew, 1.0f, (float)spx, (float)spy);
+            ob[1] = make_float4((float)lay.W, (float)lay.H, (float)sx, (float)sy);
         }
     }
-    if (ok && gl == 0) {
-        int4 *h4 = reinterpret_cast<int4 *>(hdr);
+    if (ok && leader) {
+        int4 *h4 = reinterpret_cast<int4 *>(base);
         h4[0] = make_int4(time, n, kills, deaths);
         h4[1] = make_int4(shots, overflow, episode, near0 + nt);
     }
@@ -320,21 +404,38 @@ static inline int lpa_for(int S, long long n_arenas) {
     return lpa;
 }
 
+// shared-memory image of one arena tile: the arena block's prefix (header, ships, CH = lpa laser groups), padded so that
+// consecutive tiles start 64 B apart modulo the 128-byte bank period
+static inline int step_tile_bytes(const ArenaLayout &lay, int lpa) {
+    return ((lay.off_laser + OFB_GROUP_BYTES * lpa + 127) & ~127) + 64;
+}
+
+template <int LPA>
+static int launch_step_t(ofb_arenas *h, const int2 *act, float4 *obs, const BotSpec &bots, cudaStream_t st) {
+    const int apw = 32 / LPA;
+    const long long warps = (h->n_arenas + apw - 1) / apw;
+    const long long blocks = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
+    if (blocks == 0) return OFB_OK;
+    const int tile = step_tile_bytes(h->lay, LPA);
+    const int smem = STEP_BAR_BYTES + (STEP_THREADS / 32) * apw * tile;
+    static thread_local int configured = 0;
+    if (smem > configured) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_step<LPA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    k_step<LPA><<<(unsigned)blocks, STEP_THREADS, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots, tile);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
 static int launch_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, const BotSpec &bots, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     const int lpa = lpa_for(h->lay.S, h->n_arenas);
-    const int apw = 32 / lpa;
-    const int threads = 128;
-    const long long warps = (h->n_arenas + apw - 1) / apw;
-    const long long blocks = (warps * 32 + threads - 1) / threads;
-    if (blocks == 0) return OFB_OK;
     const int2 *act = reinterpret_cast<const int2 *>(actions_dev);
     float4 *obs = reinterpret_cast<float4 *>(obs_out_dev);
-    if (lpa == 8) k_step<8><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots);
-    else if (lpa == 16) k_step<16><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots);
-    else k_step<32><<<(unsigned)blocks, threads, 0, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots);
-    OFB_CUDA_CHECK(cudaGetLastError());
-    return OFB_OK;
+    if (lpa == 8) return launch_step_t<8>(h, act, obs, bots, st);
+    if (lpa == 16) return launch_step_t<16>(h, act, obs, bots, st);
+    return launch_step_t<32>(h, act, obs, bots, st);
 }
 
 extern "C" int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *stream) {
