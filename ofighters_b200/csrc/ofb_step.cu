@@ -113,14 +113,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
 // Everything the loop reads comes from the shared-memory snapshot; results go straight to HBM (only the fields that
 // changed: x, y, meta of live lasers; dx, dy only for entries the compaction moved), so a tile never waits on a global
 // load inside the loop and the in-place compaction cannot race with its own reads.
-template <int LPA>
-__global__ void __launch_bounds__(STEP_THREADS, 5)
+template <int LPA, int PIT, int MINB>
+__global__ void __launch_bounds__(STEP_THREADS, MINB)
 k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions,
        float4 *__restrict__ obs_out, long long n_arenas, const BotSpec bots, const int tile_bytes) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int APW = 32 / LPA;
-    constexpr int CH = LPA;                              // laser groups staged per pass = 8 chunk iterations
+    constexpr int CH = PIT * LPA / 8;                    // laser groups staged per pass = PIT chunk iterations
     constexpr int C0 = LPA / 4;                          // groups copied with the header = 2 chunk iterations
+    static_assert(PIT > 2, "the second copy is awaited before chunk iteration 2");
     constexpr unsigned GM = (LPA == 32) ? 0xffffffffu : ((1u << LPA) - 1u);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane / LPA, gl = lane % LPA;
@@ -165,12 +166,8 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     }
 
     mbar_wait(mbar, 0);
-    int time = 0, n = 0, kills = 0, deaths = 0, shots = 0, overflow = 0, episode = 0, near0 = 0;
-    if (ok) {
-        const int4 h0 = reinterpret_cast<const int4 *>(tb)[0], h1 = reinterpret_cast<const int4 *>(tb)[1];
-        time = h0.x; n = h0.y; kills = h0.z; deaths = h0.w;
-        shots = h1.x; overflow = h1.y; episode = h1.z; near0 = h1.w;
-    }
+    int n = ok ? reinterpret_cast<const int *>(tb)[HDR_NLASERS] : 0;     // the other header words are re-read at the end
+    int dk = 0;                                          // kills (= deaths: hull is 1 and never restored) of this frame
     const int G_live = min((n + 7) >> 3, G_cap);
     if (leader) {
         const int hi = min(G_live, CH);
@@ -180,17 +177,22 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
             bulk_g2s(tb + off_l + OFB_GROUP_BYTES * C0, base + off_l + OFB_GROUP_BYTES * C0, bytes1, mbar);
         } else mbar_arrive(mbar);
     }
-    ShipRec me = {};
-    if (is_ship) me = ship_unpack(reinterpret_cast<const uint4 *>(tb + lay.off_ship)[gl]);
-    int sx = me.x, sy = me.y, spx = me.px, spy = me.py, rew = me.reward, score = me.score, hull = me.hull;
-    bool alive = me.alive;
-    if (is_ship && kind != OFB_BOT_EXTERNAL) act = bot_apply(draw, spx, spy);
+    // the ship record stays in the tile; the loop only carries what it can change (alive, pending reward)
+    const uint4 *srec = reinterpret_cast<const uint4 *>(tb + lay.off_ship);
+    bool alive = false;
+    int rew = 0;                                         // reward earned this frame (the old pending reward folds into the score)
+    {
+        ShipRec me = {};
+        if (is_ship) me = ship_unpack(srec[gl]);
+        alive = me.alive;
+        if (is_ship && kind != OFB_BOT_EXTERNAL) act = bot_apply(draw, me.px, me.py);
+    }
     int near_ties = 0;
 
     // centres of the ships that are alive at frame start, compacted, as floats for the box pre-filter; kept with their ship
     // indices in the (now consumed) ship region of the tile
-    float2 *spos = reinterpret_cast<float2 *>(tb + lay.off_ship);
-    unsigned char *sid = tb + lay.off_ship + 8 * lay.SP;
+    float2 *spos = reinterpret_cast<float2 *>(tb + off_l + CH * OFB_GROUP_BYTES);      // scratch behind the staged groups
+    unsigned char *sid = reinterpret_cast<unsigned char *>(spos) + 8 * lay.SP;
     const unsigned alive_bits = (__ballot_sync(FULL, alive) >> gshift) & GM;
     const int n_alive = __popc(alive_bits);
     unsigned alive_c = n_alive >= 32 ? 0xffffffffu : ((1u << n_alive) - 1u);      // by compact index
@@ -198,16 +200,11 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     __syncwarp();
     if (alive) {
         const int r = __popc(alive_bits & ((1u << gl) - 1u));
-        spos[r] = make_float2((float)sx, (float)sy);
+        const unsigned xy = srec[gl].x;
+        spos[r] = make_float2((float)(xy & 0xffffu), (float)((xy >> 16) & 0x7fffu));
         sid[r] = (unsigned char)gl;
     }
     __syncwarp();
-
-    // ---- A1: score fold, dead ships included (agents/agent.py:66-74, lib/ship.py:260-262) ----
-    score += rew;
-    rew = 0;
-    // ---- A2 ----
-    time += 1;
 
     // ---- A3 + A7: lasers in list order; entries destroyed last frame are dropped on load ----
     // A ship alive at frame start dies to the FIRST laser (list order) that collides with it, and only
@@ -218,10 +215,10 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     iters = __reduce_max_sync(FULL, iters);
     int w = 0;                                           // compaction write cursor
     for (int it = 0; it < iters; it++) {
-        const int pit = it & 7;                          // chunk iteration within the pass
+        const int pit = it % PIT;                        // chunk iteration within the pass
         if (it == 2) mbar_wait(mbar, 1);
         else if (pit == 0 && it > 0) {                   // pass p: restage groups [p * CH, (p + 1) * CH)
-            const int p = it >> 3;
+            const int p = it / PIT;
             __syncwarp();
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             if (leader) {
@@ -259,8 +256,9 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
                 const int j = __ffs(cand) - 1;
                 cand &= cand - 1;
                 const int s = sid[j];
-                const double ddx = __dsub_rn(x, (double)__shfl_sync(tmask, sx, gshift + s));
-                const double ddy = __dsub_rn(y, (double)__shfl_sync(tmask, sy, gshift + s));
+                const unsigned sxy = srec[s].x;
+                const double ddx = __dsub_rn(x, (double)(int)(sxy & 0xffffu));
+                const double ddy = __dsub_rn(y, (double)(int)((sxy >> 16) & 0x7fffu));
                 const double d2 = __dadd_rn(__dmul_rn(ddx, ddx), __dmul_rn(ddy, ddy));
                 const bool hit = ((hm >> j) & 1u) && d2 <= D2_HIT_MAX;
                 const unsigned b = (__ballot_sync(tmask, hit) >> gshift) & GM;
@@ -272,10 +270,8 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
                 }
                 if (gl == killer) hit_any = true;
                 alive_c &= ~(1u << j);
-                kills += 1;                              // event (1, t)
-                deaths += 1;                             // event (10, t): hull 1, never restored
-                if (gl == s) {                           // lib/ship.py:127-131,225-230
-                    hull -= 1;
+                dk += 1;                                 // events (1, t) and (10, t)
+                if (gl == s) {                           // lib/ship.py:127-131,225-230: hull -= 1 <= 0 -> destroyed
                     alive = false;
                     rew += lay.r_death;
                 }
@@ -296,6 +292,13 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         }
         w += __popc(lv);
     }
+
+    // ---- the ship record again (A1: score fold, dead ships included -- agents/agent.py:66-74, lib/ship.py:260-262) ----
+    ShipRec me = {};
+    if (is_ship) me = ship_unpack(srec[gl]);
+    int sx = me.x, sy = me.y, spx = me.px, spy = me.py;
+    const int score = me.score + me.reward;
+    const int hull = me.hull - ((me.alive && !alive) ? 1 : 0);
 
     // ---- A4: ships in index order (lib/ship.py:303-339) ----
     const int old_x = sx, old_y = sy;
@@ -342,6 +345,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         }
     }
     // shoot rewards: enemies j<i are seen after their move, j>i before it
+    int n_shots = 0, n_over = 0;
     {
         const unsigned alive_now = (__ballot_sync(FULL, alive) >> gshift) & GM;
         const unsigned any_shooter = __ballot_sync(FULL, shooter) & tmask;
@@ -372,8 +376,8 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
             *reinterpret_cast<unsigned *>(base + laser_meta_off(off_l, slot)) = (unsigned)gl;
         }
         const int want = w + __popc(sh);
-        shots += __popc(sh);
-        overflow += max(0, want - L);
+        n_shots = __popc(sh);
+        n_over = max(0, want - L);
         n = min(want, L);
     }
     int nt = __reduce_add_sync(tmask, near_ties);
@@ -389,10 +393,11 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
             ob[1] = make_float4((float)lay.W, (float)lay.H, (float)sx, (float)sy);
         }
     }
-    if (ok && leader) {
+    if (ok && leader) {                                  // A2: time += 1
+        const int4 h0 = reinterpret_cast<const int4 *>(tb)[0], h1 = reinterpret_cast<const int4 *>(tb)[1];
         int4 *h4 = reinterpret_cast<int4 *>(base);
-        h4[0] = make_int4(time, n, kills, deaths);
-        h4[1] = make_int4(shots, overflow, episode, near0 + nt);
+        h4[0] = make_int4(h0.x + 1, n, h0.z + dk, h0.w + dk);
+        h4[1] = make_int4(h1.x + n_shots, h1.y + n_over, h1.z, h1.w + nt);
     }
 }
 
@@ -400,30 +405,32 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
 // (more lanes = more lasers per pass and more warps in flight)
 static inline int lpa_for(int S, long long n_arenas) {
     int lpa = S <= 8 ? 8 : (S <= 16 ? 16 : 32);
-    while (lpa < 32 && n_arenas * lpa / 32 < 148 * 32) lpa *= 2;
+    while (lpa < 32 && n_arenas * lpa / 32 < 148 * 12) lpa *= 2;
     return lpa;
 }
 
-// shared-memory image of one arena tile: the arena block's prefix (header, ships, CH = lpa laser groups), padded so that
-// consecutive tiles start 64 B apart modulo the 128-byte bank period
-static inline int step_tile_bytes(const ArenaLayout &lay, int lpa) {
-    return ((lay.off_laser + OFB_GROUP_BYTES * lpa + 127) & ~127) + 64;
+// shared-memory image of one arena tile: the arena block's prefix (header, ships, PIT * lpa / 8 laser groups) followed
+// by the scratch of the compacted ship centres (8 + 1 bytes per ship), sized so that consecutive tiles start 64 B apart
+// modulo the 128-byte bank period (two tiles' 64-byte group rows then never share a bank)
+static inline int step_tile_bytes(const ArenaLayout &lay, int lpa, int pit) {
+    const int raw = lay.off_laser + OFB_GROUP_BYTES * (pit * lpa / 8) + 9 * lay.SP;
+    return ((raw + 63) & ~127) + 64;                     // smallest size >= raw that is 64 modulo 128
 }
 
-template <int LPA>
+template <int LPA, int PIT, int MINB>
 static int launch_step_t(ofb_arenas *h, const int2 *act, float4 *obs, const BotSpec &bots, cudaStream_t st) {
     const int apw = 32 / LPA;
     const long long warps = (h->n_arenas + apw - 1) / apw;
     const long long blocks = (warps * 32 + STEP_THREADS - 1) / STEP_THREADS;
     if (blocks == 0) return OFB_OK;
-    const int tile = step_tile_bytes(h->lay, LPA);
+    const int tile = step_tile_bytes(h->lay, LPA, PIT);
     const int smem = STEP_BAR_BYTES + (STEP_THREADS / 32) * apw * tile;
     static thread_local int configured = 0;
     if (smem > configured) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_step<LPA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_step<LPA, PIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    k_step<LPA><<<(unsigned)blocks, STEP_THREADS, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots, tile);
+    k_step<LPA, PIT, MINB><<<(unsigned)blocks, STEP_THREADS, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots, tile);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }
@@ -433,9 +440,11 @@ static int launch_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out
     const int lpa = lpa_for(h->lay.S, h->n_arenas);
     const int2 *act = reinterpret_cast<const int2 *>(actions_dev);
     float4 *obs = reinterpret_cast<float4 *>(obs_out_dev);
-    if (lpa == 8) return launch_step_t<8>(h, act, obs, bots, st);
-    if (lpa == 16) return launch_step_t<16>(h, act, obs, bots, st);
-    return launch_step_t<32>(h, act, obs, bots, st);
+    // 6 chunk iterations (48 lasers at 8 lanes per arena) staged per pass, 7 CTAs = 28 warps per SM: measured best of
+    // (8 iterations, 5 CTAs), (6, 7), (5, 8) on B200 -- profiles/r01_step_tuning.md
+    if (lpa == 8) return launch_step_t<8, 6, 7>(h, act, obs, bots, st);
+    if (lpa == 16) return launch_step_t<16, 6, 7>(h, act, obs, bots, st);
+    return launch_step_t<32, 6, 7>(h, act, obs, bots, st);
 }
 
 extern "C" int ofb_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *stream) {
