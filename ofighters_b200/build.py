@@ -25,6 +25,7 @@ UNITS = [
     ("ofb_raster.cu", ["-fmad=false"]),
     ("ofb_policy.cu", []),
     ("ofb_policy_tc.cu", []),
+    ("ofb_policy_tz.cu", []),
 ]
 
 

@@ -73,6 +73,31 @@ static std::vector<__nv_bfloat16> pack_dyfold(const std::vector<float> &w, int c
     return o;
 }
 
+// phase-folded fp32 [9 (u, v)][cin][coutp] -> block-Toeplitz B operand [3 u][nks][2 chunks][B * coutp n][8 cin] bf16 for
+// blocks of B pixels: n = xo * coutp + c, chunk of pixel offset p (input x = B xb + p - 1) carries tap v = p - xo.
+// K-step pairs: (1, 0), (2, 3), ..., (B - 2, B - 1), (B + 1, B)  -- see ofb_policy_tz.cu
+static std::vector<__nv_bfloat16> pack_toeplitz(const std::vector<float> &pf, int cin, int coutp, int B) {
+    const int nks = (B + 2) / 2, N = B * coutp;
+    std::vector<__nv_bfloat16> o((size_t)3 * nks * 2 * N * 8, __float2bfloat16(0.f));
+    for (int u = 0; u < 3; u++)
+        for (int ks = 0; ks < nks; ks++)
+            for (int c = 0; c < 2; c++) {
+                int pix;
+                if (ks == 0) pix = c == 0 ? 1 : 0;
+                else if (ks == nks - 1) pix = c == 0 ? B + 1 : B;
+                else pix = 2 * ks + c;
+                for (int xo = 0; xo < B; xo++) {
+                    const int v = pix - xo;
+                    if (v < 0 || v > 2) continue;
+                    for (int cc = 0; cc < coutp; cc++)
+                        for (int ci = 0; ci < cin; ci++)
+                            o[((((size_t)u * nks + ks) * 2 + c) * N + xo * coutp + cc) * 8 + ci] =
+                                __float2bfloat16(pf[((size_t)(u * 3 + v) * cin + ci) * coutp + cc]);
+                }
+            }
+    return o;
+}
+
 struct Uploader {
     std::vector<char> host;
     std::vector<std::pair<void **, size_t>> fix;
@@ -156,7 +181,9 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     up.add(&d.u4_w, w); up.add(&d.u4_b, b);
     { const std::vector<float> pf = fold_phase(w, 8, 1);
       up.add(&d.u4_pw, pack_taps(pf, 8, 4, 16));
-      up.add(&d.u4_pw2, pack_dyfold(pf, 8, 4, 4, 16)); }
+      up.add(&d.u4_pw2, pack_dyfold(pf, 8, 4, 4, 16));
+      up.add(&d.u4_tz, pack_toeplitz(pf, 8, 4, 8)); }
+    p->u4_bias = b[0];
     { std::vector<float> pb(16, 0.f); for (int n = 0; n < 4; n++) pb[n] = b[0]; up.add(&d.u4_pb, pb); }
 
     cudaError_t e = cudaMalloc(&p->arena_blob, up.host.size());
@@ -173,7 +200,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
     const size_t o_p1 = take(C * 200 * 200 * 8 * 2), o_p2 = take(C * 100 * 100 * 8 * 2), o_p3 = take(C * 50 * 50 * 8 * 2);
     const size_t o_fl = take(C * POL_FLAT_PITCH * 2), o_hf = take(C * 100 * 4);
-    const size_t o_u2 = take(C * 100 * 100 * 8 * 2), o_u3 = take(C * 200 * 200 * 8 * 2);
+    const size_t o_u2 = take(C * 100 * 100 * 8 * 2), o_u3 = take(C * POL_UP3_ITEM * 2);
     const size_t o_av = take(C * AMAX_PARTS * 4), o_ai = take(C * AMAX_PARTS * 4);
     e = cudaMalloc(&p->work_blob, off);
     if (e != cudaSuccess) {
@@ -618,8 +645,8 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     int parts;
     if (tc) {
         { ProfScope ps(p, L_UP3, st); if ((rc = pol_tc_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc; }
-        { ProfScope ps(p, L_UP4, st); if ((rc = pol_tc_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc; }
-        parts = pol_tc_up4_parts();
+        { ProfScope ps(p, L_UP4, st); if ((rc = pol_tz_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc; }
+        parts = pol_tz_up4_parts();
     } else {
         { ProfScope ps(p, L_UP3, st); k_up3_cc<<<dim3((10000 + 127) / 128, S), 128, 0, st>>>(ws.up2, w, ws.up3); }
         parts = (40000 + 255) / 256;
@@ -720,8 +747,24 @@ extern "C" int ofb_policy_pack_image(const void *img, int fmt, int64_t n, uint32
     return OFB_OK;
 }
 
+// plane layout [item][8][200][26][8] (ofb_policy_tz.cu) -> NHWC [item][200][200][8]
+__global__ void k_plane200_to_nhwc(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long n_pixels) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pixels) return;
+    const long long item = t / 40000;
+    const int p = (int)(t % 40000), Y = p / 200, X = p % 200;
+    *reinterpret_cast<uint4 *>(dst + t * 8) = *reinterpret_cast<const uint4 *>(src + item * POL_UP3_ITEM + pol_plane200_off(Y, X));
+}
+
 extern "C" int ofb_policy_debug_tap(ofb_policy *p, int which, int64_t n_items, void *dst_dev, void *stream) {
     if (!p || !dst_dev || n_items < 0 || n_items > p->max_ships) { ofb_set_error("ofb_policy_debug_tap: bad argument"); return OFB_E_ARG; }
+    if (which == 6 && p->engine == OFB_ENGINE_TENSOR) {          // the tensor engine keeps upconv3's output in plane layout
+        const long long np = n_items * 40000;
+        if (np) k_plane200_to_nhwc<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            p->ws.up3, static_cast<__nv_bfloat16 *>(dst_dev), np);
+        OFB_CUDA_CHECK(cudaGetLastError());
+        return OFB_OK;
+    }
     const void *src;
     size_t stride;
     switch (which) {

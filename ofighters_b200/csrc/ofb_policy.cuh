@@ -41,6 +41,7 @@ struct PolicyDev {
     __nv_bfloat16 *u4_pw;     // [10][16][8]      (tap, n = phase (4 used), cin)
     float *u4_pb;             // [16]
     __nv_bfloat16 *u4_pw2;    // tensor engine: [4 u][16 n = v*4 + phase][8 cin]
+    __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
 };
 
 struct PolicyWork {
@@ -50,16 +51,18 @@ struct PolicyWork {
     __nv_bfloat16 *flat;      // [Ca][5120]
     float *hflat;             // [Ca][100]   dense1 flat-part pre-activation
     __nv_bfloat16 *up2;       // [Cs][100*100*8]
-    __nv_bfloat16 *up3;       // [Cs][200*200*8]
+    __nv_bfloat16 *up3;       // [Cs][POL_UP3_ITEM]: tensor engine = plane layout [8][200][26][8], CUDA-core engine = NHWC [200][200][8]
     float *amax_val;          // [Cs][AMAX_PARTS]
     int *amax_idx;            // [Cs][AMAX_PARTS]
 };
 #define AMAX_PARTS 160
+#define POL_UP3_ITEM (8 * 200 * 26 * 8)   // elements of one upconv3 output in plane layout (>= 200*200*8)
 
 struct ofb_policy {
     int device;
     int max_ships;
     int engine;
+    float u4_bias;            // upconv4's (single) bias, host copy
     PolicyDev w;
     PolicyWork ws;
     int profiling;            // when set, forward brackets every kernel with CUDA events
@@ -78,3 +81,9 @@ int pol_tc_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out,
 int pol_tc_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st);
 int pol_tc_up4_parts();
+// block-Toeplitz kernels, ofb_policy_tz.cu
+int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
+               cudaStream_t st);
+int pol_tz_up4_parts();
+// element offset of pixel (Y, X) of a 200 x 200 x 8 image in plane layout (ofb_policy_tz.cu)
+__host__ __device__ __forceinline__ int pol_plane200_off(int Y, int X) { return (((X & 7) * 200 + Y) * 26 + (X >> 3) + 1) * 8; }

@@ -22,6 +22,7 @@
 // epilogue (shuffles + lane-quarter exchange) -- see DESIGN.md section 5.
 #include "ofb_common.cuh"
 #include "ofb_policy_dev.cuh"
+#include "ofb_tc_ptx.cuh"
 
 enum { M_CONV_GMEM = 0, M_CONV_BITS = 1, M_UP3 = 2, M_UP4 = 3 };
 #define TC_R 10                       // image rows per strip (all layer heights are multiples of 10)
@@ -42,66 +43,6 @@ struct TcArgs {
     int H;                            // input height = width (conv resolution)
     long long *dbg;                   // optional: clock64 stamps of CTA (1, 0) at the phase boundaries
 };
-
-// ---------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    uint32_t done, spins = 0;
-    do {
-        if (++spins > (1u << 24)) __trap();              // a lost arrival must fail loudly, not hang the GPU
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// bulk asynchronous copy global -> shared (TMA-class, no tensor map), completion counted on an mbarrier
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld4(uint32_t taddr, uint32_t *r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t *r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start / LBO / SBO in
-// 16-byte units, version 1 (Blackwell), layout type 0.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t start16, uint32_t lbo16, uint32_t sbo16) {
-    return (uint64_t)(start16 & 0x3FFFu) | ((uint64_t)(lbo16 & 0x3FFFu) << 16) | ((uint64_t)(sbo16 & 0x3FFFu) << 32) | (1ull << 46);
-}
-// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M = 128
-__host__ __device__ constexpr uint32_t instr_desc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
 
 // shared-memory plan of one CTA (host and device agree through this)
 struct TcPlan {
@@ -386,7 +327,7 @@ k_tc_conv(const TcArgs a) {
                     }
 #pragma unroll
                     for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
-                    *reinterpret_cast<uint4 *>(dst + ((size_t)Y * 2 * W + X) * 8) = pack_bf8(o);
+                    *reinterpret_cast<uint4 *>(dst + pol_plane200_off(Y, X)) = pack_bf8(o);      // plane layout for k_tz_up4
                 }
             }
         } else {    // M_UP4
@@ -460,7 +401,7 @@ k_tc_conv(const TcArgs a) {
                 float o8[8];
 #pragma unroll
                 for (int co = 0; co < 8; co++) o8[co] = o[co % COUT];
-                *reinterpret_cast<uint4 *>(a.out + (size_t)item * a.out_item_stride + ((size_t)Y * Wo + X) * 8) = pack_bf8(o8);
+                *reinterpret_cast<uint4 *>(a.out + (size_t)item * a.out_item_stride + pol_plane200_off(Y, X)) = pack_bf8(o8);
             } else {
                 const float v = ring[slot] - o[0];
                 const int idx = Y * Wo + X;
@@ -547,7 +488,7 @@ int pol_tc_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out
 int pol_tc_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
     TcArgs a = {};
     a.in = in; a.wt = p->w.u3_pw; a.bias = p->w.u3_pb; a.aux_w = p->w.u3_w; a.aux_b = p->w.u3_b; a.out = out;
-    a.in_item_stride = 100 * 100 * 8; a.out_item_stride = 200 * 200 * 8; a.H = 100;
+    a.in_item_stride = 100 * 100 * 8; a.out_item_stride = POL_UP3_ITEM; a.H = 100;
     return launch<M_UP3, 32>(a, n_items, st);
 }
 

@@ -35,6 +35,20 @@ def main():
             st = d[m, :11].tolist()
             print(name, "phase cycles:", [st[i + 1] - st[i] if st[i + 1] and st[i] else None for i in range(10)], "total", st[10] - st[0], "| first-ring MMAs:", int(d[m, 12] - d[m, 11]), "| tile2 drain: wait %d pass1 %d bar %d pass2 %d" % tuple(int(d[m, k + 1] - d[m, k]) for k in (13, 14, 15, 16)))
         lib.ofb_policy_tc_debug(None)
+    if os.environ.get("OFB_TZ_DEBUG"):
+        import ctypes
+        from ofighters_b200 import _lib
+        dbg = torch.zeros(16, dtype=torch.int64, device=bg.device)
+        lib = _lib.load()
+        lib.ofb_policy_tz_debug.argtypes = [ctypes.c_void_p]
+        lib.ofb_policy_tz_debug(ctypes.c_void_p(dbg.data_ptr()))
+        pol.set_engine("tensor")
+        pol.forward_argmax(maps, vec)
+        pol.forward_argmax(maps, vec)
+        torch.cuda.synchronize()
+        st = dbg.cpu().tolist()
+        print("tz_up4 stamps (cycles since start):", [x - st[0] if x else None for x in st[:13]])
+        lib.ofb_policy_tz_debug(None)
     for eng in engines:
         pol.set_engine(eng)
         for _ in range(2):
