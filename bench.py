@@ -135,8 +135,15 @@ class L2Flush:
 def cpu_arm(wl, steps, warmup, n_cap=4096):
     """The reference's algorithm on the host cores: oracle/step_c.c (bots + step + raster, OpenMP).
     Returns (env_steps_per_s, ms_per_step, cores, sample description)."""
+    import ctypes
     import numpy as np
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    os.environ["OMP_NUM_THREADS"] = str(cores)          # torchrun exports OMP_NUM_THREADS=1: the CPU arm uses every core
     from oracle.step_c import ArenasC
+    try:
+        ctypes.CDLL("libgomp.so.1").omp_set_num_threads(cores)   # in case the OpenMP runtime was initialised already
+    except OSError:
+        pass
     N = min(wl["n"], n_cap)
     S = wl["ships"]
     c0 = ArenasC(np.zeros((N, S, 2), np.int32))
@@ -155,7 +162,6 @@ def cpu_arm(wl, steps, warmup, n_cap=4096):
         t_ep += 1
         if it >= warmup:
             out_t += time.perf_counter() - t0
-    cores = os.cpu_count() or 1
     return N * steps / out_t, out_t / steps * 1e3, cores, \
         "%d arenas x %d frames of bots+step+raster, oracle/step_c.c (gcc -O2 -fopenmp, %d threads)" % (N, steps, cores)
 
@@ -337,6 +343,8 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
     for name, fn, nbytes in (("k_raster", lambda: bg.raster("bits", out=maps), maps.numel() * 4),
                              ("k_step", lambda: bg.generate_frame(), bg.algorithmic_step_bytes)):
         ts = []
+        for _ in range(5):                                # warm-up (module load, clocks)
+            fn()
         for _ in range(iters):
             if flush_buf is not None:
                 flush_buf()
