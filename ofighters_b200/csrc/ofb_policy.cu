@@ -175,7 +175,8 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     up.add(&d.u3_w, w); up.add(&d.u3_b, b);
     { const std::vector<float> pf = fold_phase(w, 4, 8);
       up.add(&d.u3_pw, pack_taps(pf, 4, 32, 32));
-      up.add(&d.u3_pw2, pack_dyfold(pf, 4, 32, 32, 96)); }
+      up.add(&d.u3_pw2, pack_dyfold(pf, 4, 32, 32, 96));
+      up.add(&d.u3_tz, pack_toeplitz(pf, 4, 32, 4)); }
     { std::vector<float> pb(32); for (int n = 0; n < 32; n++) pb[n] = b[n % 8]; up.add(&d.u3_pb, pb); }
     fold_conv(wh->upconv[3], 8, 1, w, b);
     up.add(&d.u4_w, w); up.add(&d.u4_b, b);
@@ -200,7 +201,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
     const size_t o_p1 = take(C * 200 * 200 * 8 * 2), o_p2 = take(C * 100 * 100 * 8 * 2), o_p3 = take(C * 50 * 50 * 8 * 2);
     const size_t o_fl = take(C * POL_FLAT_PITCH * 2), o_hf = take(C * 100 * 4);
-    const size_t o_u2 = take(C * 100 * 100 * 8 * 2), o_u3 = take(C * POL_UP3_ITEM * 2);
+    const size_t o_u2 = take(C * POL_UP2_ITEM * 2), o_u3 = take(C * POL_UP3_ITEM * 2);
     const size_t o_av = take(C * AMAX_PARTS * 4), o_ai = take(C * AMAX_PARTS * 4);
     e = cudaMalloc(&p->work_blob, off);
     if (e != cudaSuccess) {
@@ -209,7 +210,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     }
     char *wb = static_cast<char *>(p->work_blob);
     cudaMemset(wb + o_fl, 0, C * POL_FLAT_PITCH * 2);            // K padding of dense1 must read as zero
-    cudaMemset(wb + o_u2, 0, C * 100 * 100 * 8 * 2);             // channels 4..7 of up2 stay zero
+    cudaMemset(wb + o_u2, 0, C * POL_UP2_ITEM * 2);              // channels 4..7 of up2 stay zero
     p->ws.pool1 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p1);
     p->ws.pool2 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p2);
     p->ws.pool3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p3);
@@ -396,7 +397,7 @@ k_dense1_cc(const __nv_bfloat16 *__restrict__ flat, const __nv_bfloat16 *__restr
 #define HEADS_SMEM_FLOATS (128 + 64 + 640 + 2500 + 5000 + 20000)
 __global__ void __launch_bounds__(256)
 k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, float *__restrict__ act_out,
-        int *__restrict__ iaction_out, __nv_bfloat16 *__restrict__ up2_out) {
+        int *__restrict__ iaction_out, __nv_bfloat16 *__restrict__ up2_out, int plane_layout) {
     extern __shared__ float sm[];
     float *h = sm, *d2 = h + 128, *u = d2 + 64, *U1 = u + 640, *a1 = U1 + 2500, *U2 = a1 + 5000;
     const int s = blockIdx.x, arena = s / ships_per_arena, tid = threadIdx.x, nt = blockDim.x;
@@ -470,7 +471,7 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
     }
     __syncthreads();
     // upconv2 2 -> 4 + BN + ReLU (:173-175) -> bf16 NHWC with channels padded to 8
-    __nv_bfloat16 *dst = up2_out + (size_t)s * 100 * 100 * 8;
+    __nv_bfloat16 *dst = up2_out + (size_t)s * POL_UP2_ITEM;   // tensor engine: de-interleaved by x mod 4 for k_tz_up3
     for (int p = tid; p < 10000; p += nt) {
         const int y = p / 100, x = p % 100;
         float c[4] = {w.u2_b[0], w.u2_b[1], w.u2_b[2], w.u2_b[3]};
@@ -485,7 +486,7 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
 #pragma unroll
                 for (int co = 0; co < 4; co++) c[co] += v0 * wp[co] + v1 * wp[4 + co];
             }
-        *reinterpret_cast<uint2 *>(dst + (size_t)p * 8) =
+        *reinterpret_cast<uint2 *>(dst + (plane_layout ? pol_plane100_off(y, x) : p * 8)) =
             make_uint2(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)));
     }
 }
@@ -502,8 +503,8 @@ k_up3_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, __nv_bfloat16 *__res
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= 100 * 100) return;
     const int i = p / 100, j = p % 100;
-    const __nv_bfloat16 *L = in + (size_t)blockIdx.y * 100 * 100 * 8;
-    __nv_bfloat16 *dst = out + (size_t)blockIdx.y * 200 * 200 * 8;
+    const __nv_bfloat16 *L = in + (size_t)blockIdx.y * POL_UP2_ITEM;
+    __nv_bfloat16 *dst = out + (size_t)blockIdx.y * POL_UP3_ITEM;
     float acc[32];
 #pragma unroll
     for (int n = 0; n < 32; n++) acc[n] = sb[n];
@@ -544,7 +545,7 @@ k_up4_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, float *__restrict__ 
     __syncthreads();
     const float pb = w.u4_pb[0];
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const __nv_bfloat16 *L = in + (size_t)blockIdx.y * 200 * 200 * 8;
+    const __nv_bfloat16 *L = in + (size_t)blockIdx.y * POL_UP3_ITEM;
     float bv = -INFINITY;
     int bi = 0x7fffffff;
     if (p < 200 * 200) {
@@ -640,11 +641,11 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     { ProfScope ps(p, L_DENSE1, st);
       k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A); }
     { ProfScope ps(p, L_HEADS, st);
-      k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2); }
+      k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2, tc ? 1 : 0); }
     if (!xy && !ptr) { OFB_CUDA_CHECK(cudaGetLastError()); return OFB_OK; }
     int parts;
     if (tc) {
-        { ProfScope ps(p, L_UP3, st); if ((rc = pol_tc_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc; }
+        { ProfScope ps(p, L_UP3, st); if ((rc = pol_tz_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc; }
         { ProfScope ps(p, L_UP4, st); if ((rc = pol_tz_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc; }
         parts = pol_tz_up4_parts();
     } else {
@@ -756,8 +757,23 @@ __global__ void k_plane200_to_nhwc(const __nv_bfloat16 *__restrict__ src, __nv_b
     *reinterpret_cast<uint4 *>(dst + t * 8) = *reinterpret_cast<const uint4 *>(src + item * POL_UP3_ITEM + pol_plane200_off(Y, X));
 }
 
+__global__ void k_plane100_to_nhwc(const __nv_bfloat16 *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long n_pixels) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pixels) return;
+    const long long item = t / 10000;
+    const int p = (int)(t % 10000), y = p / 100, x = p % 100;
+    *reinterpret_cast<uint4 *>(dst + t * 8) = *reinterpret_cast<const uint4 *>(src + item * POL_UP2_ITEM + pol_plane100_off(y, x));
+}
+
 extern "C" int ofb_policy_debug_tap(ofb_policy *p, int which, int64_t n_items, void *dst_dev, void *stream) {
     if (!p || !dst_dev || n_items < 0 || n_items > p->max_ships) { ofb_set_error("ofb_policy_debug_tap: bad argument"); return OFB_E_ARG; }
+    if (which == 5 && p->engine == OFB_ENGINE_TENSOR) {          // ... and upconv2's in the 4-plane layout
+        const long long np = n_items * 10000;
+        if (np) k_plane100_to_nhwc<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            p->ws.up2, static_cast<__nv_bfloat16 *>(dst_dev), np);
+        OFB_CUDA_CHECK(cudaGetLastError());
+        return OFB_OK;
+    }
     if (which == 6 && p->engine == OFB_ENGINE_TENSOR) {          // the tensor engine keeps upconv3's output in plane layout
         const long long np = n_items * 40000;
         if (np) k_plane200_to_nhwc<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
@@ -766,17 +782,19 @@ extern "C" int ofb_policy_debug_tap(ofb_policy *p, int which, int64_t n_items, v
         return OFB_OK;
     }
     const void *src;
-    size_t stride;
+    size_t stride, pitch = 0;                                   // pitch: distance between items in the workspace when it is not `stride`
     switch (which) {
     case 0: src = p->ws.pool1; stride = 200 * 200 * 8 * 2; break;
     case 1: src = p->ws.pool2; stride = 100 * 100 * 8 * 2; break;
     case 2: src = p->ws.pool3; stride = 50 * 50 * 8 * 2; break;
     case 3: src = p->ws.flat; stride = POL_FLAT_PITCH * 2; break;
     case 4: src = p->ws.hflat; stride = 100 * 4; break;
-    case 5: src = p->ws.up2; stride = 100 * 100 * 8 * 2; break;
-    case 6: src = p->ws.up3; stride = 200 * 200 * 8 * 2; break;
+    case 5: src = p->ws.up2; stride = 100 * 100 * 8 * 2; pitch = POL_UP2_ITEM * 2; break;
+    case 6: src = p->ws.up3; stride = 200 * 200 * 8 * 2; pitch = POL_UP3_ITEM * 2; break;
     default: ofb_set_error("ofb_policy_debug_tap: unknown tap %d", which); return OFB_E_ARG;
     }
-    OFB_CUDA_CHECK(cudaMemcpyAsync(dst_dev, src, stride * (size_t)n_items, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    if (n_items == 0) return OFB_OK;
+    OFB_CUDA_CHECK(cudaMemcpy2DAsync(dst_dev, stride, src, pitch ? pitch : stride, stride, (size_t)n_items, cudaMemcpyDeviceToDevice,
+                                     (cudaStream_t)stream));
     return OFB_OK;
 }

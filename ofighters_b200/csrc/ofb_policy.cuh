@@ -41,6 +41,7 @@ struct PolicyDev {
     __nv_bfloat16 *u4_pw;     // [10][16][8]      (tap, n = phase (4 used), cin)
     float *u4_pb;             // [16]
     __nv_bfloat16 *u4_pw2;    // tensor engine: [4 u][16 n = v*4 + phase][8 cin]
+    __nv_bfloat16 *u3_tz;     // block-Toeplitz B operand of upconv3: [3 u][3 k-steps][2 chunks][128 n = xo*32 + phase*8 + cout][8 cin]
     __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
 };
 
@@ -50,12 +51,13 @@ struct PolicyWork {
     __nv_bfloat16 *pool3;     // [Ca][50*50*8]
     __nv_bfloat16 *flat;      // [Ca][5120]
     float *hflat;             // [Ca][100]   dense1 flat-part pre-activation
-    __nv_bfloat16 *up2;       // [Cs][100*100*8]
+    __nv_bfloat16 *up2;       // [Cs][POL_UP2_ITEM]: tensor engine = plane layout [4][100][26][8], CUDA-core engine = NHWC [100][100][8]
     __nv_bfloat16 *up3;       // [Cs][POL_UP3_ITEM]: tensor engine = plane layout [8][200][26][8], CUDA-core engine = NHWC [200][200][8]
     float *amax_val;          // [Cs][AMAX_PARTS]
     int *amax_idx;            // [Cs][AMAX_PARTS]
 };
 #define AMAX_PARTS 160
+#define POL_UP2_ITEM (4 * 100 * 26 * 8)   // elements of one upconv2 output in plane layout (>= 100*100*8)
 #define POL_UP3_ITEM (8 * 200 * 26 * 8)   // elements of one upconv3 output in plane layout (>= 200*200*8)
 
 struct ofb_policy {
@@ -85,5 +87,8 @@ int pol_tc_up4_parts();
 int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st);
 int pol_tz_up4_parts();
+int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
+// element offset of pixel (y, x) of a 100 x 100 x 8 image in plane layout (4 planes of x mod 4)
+__host__ __device__ __forceinline__ int pol_plane100_off(int y, int x) { return (((x & 3) * 100 + y) * 26 + (x >> 2) + 1) * 8; }
 // element offset of pixel (Y, X) of a 200 x 200 x 8 image in plane layout (ofb_policy_tz.cu)
 __host__ __device__ __forceinline__ int pol_plane200_off(int Y, int X) { return (((X & 7) * 200 + Y) * 26 + (X >> 3) + 1) * 8; }

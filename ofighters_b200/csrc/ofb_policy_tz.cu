@@ -26,9 +26,10 @@
 
 #define TZ4_H 200                     // input grid of upconv4
 #define TZ4_P 26                      // slots per plane row: 25 blocks + 1 halo
-#define TZ4_R 19                      // rows per strip: 19 * 26 = 494 M rows = 4 tiles of 128
-#define TZ4_T 4
-#define TZ4_PS 576                    // slots per plane in shared memory: (R + 2) * P + 2 + tile overrun, rounded to 8
+#define TZ4_R 14                      // rows per strip: 14 * 26 = 364 M rows = 3 tiles of 128
+#define TZ4_T 3
+#define TZ4_PS 440                    // slots per plane in shared memory: (R + 2) * P + 2 + tile overrun (20), rounded to 8
+#define TZ4_NST 3                     // stages of the strip buffer / TMEM accumulators (two in flight while one is computed: ~110 KB per SM)
 #define TZ4_N 32
 #define TZ4_NT 160                    // 4 draining warps (one per TMEM lane quarter) + 1 producer / MMA-issuer warp
 #define TZ4_STRIPS ((TZ4_H + TZ4_R - 1) / TZ4_R)
@@ -44,13 +45,24 @@ struct Tz4Args {
     long long *dbg;                   // optional: clock64 stamps of CTA (5, 0) at the phase boundaries
 };
 
+#define TZ4_NG 3                      // draining groups of 4 warps; group g owns stage g (TZ4_NG == TZ4_NST)
+#define TZ4_NTP (32 * (4 * TZ4_NG + 1 + TZ4_T))                   // persistent kernel: 2 groups of 4 draining warps (one per stage) + TMA producer warp + MMA / halo warp
+#define TZ4_ABYTES (8 * TZ4_PS * 16)
+#define TZ4_WBYTES (3 * 5 * 2 * TZ4_N * 16)
+#define TZ4_RING (4 * TZ4_R + 400)    // floats: 2R left, 2R right, 400 top / bottom
+#define TZ4_SCR (2 * (TZ4_R + 2) * 3 + 202 * 3 + 2)   // ring-correction scratch: column dots, row dots
+
 struct Tz4Smem {
-    static constexpr unsigned off_w = 0;                                   // 3 * 5 * 2 * 32 * 16 B
-    static constexpr unsigned off_a = 15360;
-    static constexpr unsigned off_ring = off_a + 8 * TZ4_PS * 16;          // floats: 2R left, 2R right, 400 top/bottom
-    static constexpr unsigned off_aux = off_ring + (4 * TZ4_R + 400) * 4;  // 72 ring weights + argmax scratch
-    static constexpr unsigned off_bar = (off_aux + (72 + 16) * 4 + 15) & ~15u;
-    static constexpr unsigned total = off_bar + (TZ4_T + 1) * 8 + 16;
+    static constexpr unsigned off_w = 0;
+    static constexpr unsigned off_a = TZ4_WBYTES;                          // TZ4_NST stages
+    static constexpr unsigned off_ring = off_a + TZ4_NST * TZ4_ABYTES;     // one per draining group
+    static constexpr unsigned off_corr = off_ring + TZ4_NG * TZ4_RING * 4; // one per draining group: ring corrections
+    static constexpr unsigned off_scr = off_corr + TZ4_NG * TZ4_RING * 4;  // one per draining group
+    static constexpr unsigned off_aux = off_scr + TZ4_NG * TZ4_SCR * 4;    // 72 ring weights + argmax scratch (16 floats per group)
+    static constexpr unsigned off_bar = (off_aux + (72 + 16 * TZ4_NG) * 4 + 15) & ~15u;
+    // barriers: wbar, full_a[NST], a_empty[NST], halo[NST], halo2[NST], tmem_empty[NST], acc_full[NST][T]
+    static constexpr unsigned n_bar = 1 + 5 * TZ4_NST + TZ4_NST * TZ4_T;
+    static constexpr unsigned total = off_bar + n_bar * 8 + 16;
 };
 
 // plane-layout strip in shared memory as an image accessor: rows y0-1 .. y0+R, cols -1 .. 200 (halos filled)
@@ -60,200 +72,533 @@ struct PlaneStrip4 {
     __device__ __forceinline__ uint4 operator()(int y, int x) const { return pl[(x & 7) * TZ4_PS + (y - y0 + 1) * TZ4_P + (x >> 3) + 1]; }
 };
 
-__global__ void __launch_bounds__(TZ4_NT)
-k_tz_up4(const Tz4Args a) {
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int item = blockIdx.y, y0 = blockIdx.x * TZ4_R;
-    const int rows_valid = min(TZ4_R, TZ4_H - y0);
-    uint4 *sw = reinterpret_cast<uint4 *>(smem + Tz4Smem::off_w);
-    uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz4Smem::off_a);
-    float *ring = reinterpret_cast<float *>(smem + Tz4Smem::off_ring);
-    float *aux = reinterpret_cast<float *>(smem + Tz4Smem::off_aux);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Tz4Smem::off_bar);      // full[T], load
-    uint64_t *lbar = &bars[TZ4_T];
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Tz4Smem::off_bar + (TZ4_T + 1) * 8);
-#define TZ_STAMP(k, who) do { if (a.dbg && tid == (who) && blockIdx.x == 5 && blockIdx.y == 0) a.dbg[k] = clock64(); } while (0)
-    TZ_STAMP(0, 0);
+__device__ __forceinline__ void named_sync_128(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-    // ---- producer: barriers + bulk copies of the strip's rows, one run of rows per plane (+ a replicated row at the
-    //      top / bottom of the image)
-    if (tid == 128) {
-        for (int t = 0; t <= TZ4_T; t++) mbar_init(&bars[t], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const int ylo = max(y0 - 1, 0), yhi = min(y0 + TZ4_R, TZ4_H - 1);
-        const uint32_t run = (uint32_t)(yhi - ylo + 1) * TZ4_P * 16;
-        const bool top = y0 == 0, bot = y0 + TZ4_R > TZ4_H - 1;                // a halo row outside the image is needed
-        mbar_expect_tx(lbar, 8u * (run + (top ? TZ4_P * 16 : 0) + (bot ? TZ4_P * 16 : 0)) + 3 * 5 * 2 * TZ4_N * 16 + 72 * 4);
-        bulk_g2s(sw, a.wt, 3 * 5 * 2 * TZ4_N * 16, lbar);                      // weights ride the same barrier
-        bulk_g2s(aux, a.ring_w, 72 * 4, lbar);
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.in) + (size_t)item * (8 * TZ4_H * TZ4_P * 16);
-        for (int q = 0; q < 8; q++) {
-            const uint8_t *pq = src + (size_t)q * TZ4_H * TZ4_P * 16;
-            uint4 *dq = sa + q * TZ4_PS;
-            bulk_g2s(dq + (ylo - (y0 - 1)) * TZ4_P, pq + (size_t)ylo * TZ4_P * 16, run, lbar);
-            if (top) bulk_g2s(dq, pq, TZ4_P * 16, lbar);                                                  // row -1 := row 0
-            if (bot) bulk_g2s(dq + (TZ4_H - (y0 - 1)) * TZ4_P, pq + (size_t)(TZ4_H - 1) * TZ4_P * 16, TZ4_P * 16, lbar);   // row 200 := row 199
+// The 32 accumulator columns of one M row (y_local, block xb) of upconv4 -> biased values with the hi-res border pixels
+// masked out (-inf); when `ring` is given the masked values are parked there for the ring pass (column slots own the
+// corners).  Column n = xo * 4 + a * 2 + b is output pixel (2 i + a, 16 xb + 2 xo + b).
+__device__ __forceinline__ void up4_row_values(const uint32_t *r, float bias, int xb, int yl, int i, float *ring, float *v) {
+    const float NINF = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 32; n++) v[n] = __uint_as_float(r[n]) + bias;
+    if (xb == 0) {
+        if (ring) { ring[2 * yl] = v[0]; ring[2 * yl + 1] = v[2]; }
+        v[0] = NINF; v[2] = NINF;
+    }
+    if (xb == 24) {
+        if (ring) { ring[2 * TZ4_R + 2 * yl] = v[29]; ring[2 * TZ4_R + 2 * yl + 1] = v[31]; }
+        v[29] = NINF; v[31] = NINF;
+    }
+    if (i == 0 || i == TZ4_H - 1) {
+        const int ph_a = i == 0 ? 0 : 1;
+#pragma unroll
+        for (int rem = 0; rem < 16; rem++) {
+            const int X = 16 * xb + rem;
+            if (X == 0 || X == 2 * TZ4_H - 1) continue;
+            if (ph_a == 0) { if (ring) ring[4 * TZ4_R + X] = v[(rem >> 1) * 4 + (rem & 1)]; v[(rem >> 1) * 4 + (rem & 1)] = NINF; }
+            else { if (ring) ring[4 * TZ4_R + X] = v[(rem >> 1) * 4 + 2 + (rem & 1)]; v[(rem >> 1) * 4 + 2 + (rem & 1)] = NINF; }
         }
     }
+}
+
+// Persistent, warp-specialised: one CTA per SM walks the (item, strip) work list with two stages of everything --
+//   warp 4 (producer)  : bulk copies of strip k + 1 while strip k is computed            full_a[s] / a_empty[s]
+//   warp 5 (MMA)       : halo slots, then 4 tiles x 15 MMAs into TMEM stage s             halo[s], acc_full[s][t] / tmem_empty[s]
+//   warps 0-11 (drain) : group g = warps 4g..4g+3 owns stage g (every third strip): TMEM -> registers -> masked max,
+//                        border ring, argmax partial.  The index of the maximum is recovered by re-reading the one tile
+//                        that holds it, so the per-tile work is branch-free.
+static_assert(TZ4_NG == TZ4_NST, "group g drains stage g");
+__global__ void __launch_bounds__(TZ4_NTP, 1)
+k_tz_up4(const Tz4Args a, const int n_work) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint4 *sw = reinterpret_cast<uint4 *>(smem + Tz4Smem::off_w);
+    float *aux = reinterpret_cast<float *>(smem + Tz4Smem::off_aux);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Tz4Smem::off_bar);
+    uint64_t *wbar = bars, *full_a = bars + 1, *a_empty = full_a + TZ4_NST, *halo = a_empty + TZ4_NST, *halo2 = halo + TZ4_NST,
+             *tmem_empty = halo2 + TZ4_NST, *acc_full = tmem_empty + TZ4_NST;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Tz4Smem::off_bar + Tz4Smem::n_bar * 8);
+#define TZ_STAMP(k, who) do { if (a.dbg && tid == (who) && blockIdx.x == 5) a.dbg[k] = clock64(); } while (0)
+    // per-work stamps of CTA 5: dbg[16 + 8 * k + j] for the CTA's k-th work item (k < 14)
+#define TZ_STAMPK(k, j) do { if (a.dbg && blockIdx.x == 5 && (k) < 14) a.dbg[16 + 8 * (k) + (j)] = clock64(); } while (0)
+    TZ_STAMP(0, 0);
+
+    if (tid == 0) {
+        mbar_init(wbar, 1);
+        for (int s = 0; s < TZ4_NST; s++) {
+            mbar_init(&full_a[s], 1);
+            mbar_init(&a_empty[s], 4 + TZ4_T);             // 4 draining warps (ring corrections read) + the MMA warps (tcgen05.commit)
+            mbar_init(&halo[s], 1);
+            mbar_init(&halo2[s], 1);                       // released once, awaited by the other MMA warps
+            mbar_init(&tmem_empty[s], 4);
+            for (int t = 0; t < TZ4_T; t++) mbar_init(&acc_full[s * TZ4_T + t], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    __syncthreads();                                     // barrier init visible
-    TZ_STAMP(1, 0);
-    mbar_wait(lbar, 0);                                  // rows have landed (acquire for every thread)
-    TZ_STAMP(2, 0);
-    // ---- halos: x = -1 := x = 0 (plane 7 slot 0 of the row), x = 200 := x = 199 (plane 0 slot 0 of the next row)
-    for (int i = tid; i < 2 * (TZ4_R + 2); i += TZ4_NT) {
-        const int r = i >> 1;
-        if (i & 1) sa[0 * TZ4_PS + (r + 1) * TZ4_P] = sa[7 * TZ4_PS + r * TZ4_P + 25];
-        else sa[7 * TZ4_PS + r * TZ4_P] = sa[0 * TZ4_PS + r * TZ4_P + 1];
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    TZ_STAMP(3, 0);
 
-    float best_v = -INFINITY;
-    int best_i = 0x7fffffff;
-    if (warp == 4) {
-        // ---- MMA issuer: 4 tiles x (3 vertical taps x 5 K-steps), every tile has its own TMEM accumulator
+    if (warp == 4 * TZ4_NG) {
+        // ------------------------------------------------------------ producer
         if (lane == 0) {
-            constexpr uint32_t IDESC = instr_desc(TZ4_N);
-            const uint32_t sa16 = smem_u32(sa) >> 4, sw16 = smem_u32(sw) >> 4;
-            for (int t = 0; t < TZ4_T; t++) {
-                const uint32_t d = tmem_base + (uint32_t)(t * TZ4_N);
-#pragma unroll
-                for (int u = 0; u < 3; u++)
-#pragma unroll
-                    for (int ks = 0; ks < 5; ks++) {
-                        // first / second K-chunk of the step: (plane, slot offset); see the header comment
-                        const int q0 = ks == 0 || ks == 4 ? 0 : 2 * ks - 1, o0 = ks == 4 ? 2 : 1;
-                        const uint32_t lbo = (ks == 0 || ks == 4) ? 7u * TZ4_PS - 1u : (uint32_t)TZ4_PS;
-                        const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ4_PS + u * TZ4_P + 128 * t + o0), lbo, 8);
-                        const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 5 + ks) * 2 * TZ4_N), TZ4_N, 8);
-                        tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
-                    }
-                tc_commit(&bars[t]);
+            mbar_expect_tx(wbar, TZ4_WBYTES + 72 * 4);
+            bulk_g2s(sw, a.wt, TZ4_WBYTES, wbar);
+            bulk_g2s(aux, a.ring_w, 72 * 4, wbar);
+            int k = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
+                const int s = k % TZ4_NST, item = w / TZ4_STRIPS, y0 = (w % TZ4_STRIPS) * TZ4_R;
+                if (k >= TZ4_NST) mbar_wait(&a_empty[s], (uint32_t)((k / TZ4_NST - 1) & 1));
+                TZ_STAMPK(k, 0);                                           // loads issued
+                uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz4Smem::off_a + s * TZ4_ABYTES);
+                const int ylo = max(y0 - 1, 0), yhi = min(y0 + TZ4_R, TZ4_H - 1);
+                const uint32_t run = (uint32_t)(yhi - ylo + 1) * TZ4_P * 16;
+                const bool top = y0 == 0, bot = y0 + TZ4_R > TZ4_H - 1;        // a halo row outside the image is needed
+                mbar_expect_tx(&full_a[s], 8u * (run + (top ? TZ4_P * 16 : 0) + (bot ? TZ4_P * 16 : 0)));
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(a.in) + (size_t)item * (8 * TZ4_H * TZ4_P * 16);
+                for (int q = 0; q < 8; q++) {
+                    const uint8_t *pq = src + (size_t)q * TZ4_H * TZ4_P * 16;
+                    uint4 *dq = sa + q * TZ4_PS;
+                    bulk_g2s(dq + (ylo - (y0 - 1)) * TZ4_P, pq + (size_t)ylo * TZ4_P * 16, run, &full_a[s]);
+                    if (top) bulk_g2s(dq, pq, TZ4_P * 16, &full_a[s]);                                         // row -1 := row 0
+                    if (bot) bulk_g2s(dq + (TZ4_H - (y0 - 1)) * TZ4_P, pq + (size_t)(TZ4_H - 1) * TZ4_P * 16, TZ4_P * 16, &full_a[s]);
+                }
             }
-            TZ_STAMP(4, 128);
         }
         __syncwarp();
+    } else if (warp > 4 * TZ4_NG) {
+        // ------------------------------------------------------------ halo slots + MMA issue.  A single thread issues an
+        // MMA every ~75 cycles (descriptor moves to uniform registers), far slower than the pipe retires these small
+        // MMAs, so one warp per tile issues: warp 9 also fixes the halo slots first.
+        mbar_wait(wbar, 0);
+        constexpr uint32_t IDESC = instr_desc(TZ4_N);
+        const uint32_t sw16 = smem_u32(sw) >> 4;
+        const int half = warp - 4 * TZ4_NG - 1;            // tile issued by this warp
+        int k = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
+            const int s = k % TZ4_NST;
+            const uint32_t par = (uint32_t)((k / TZ4_NST) & 1);
+            uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz4Smem::off_a + s * TZ4_ABYTES);
+            if (half == 0) {
+                mbar_wait(&full_a[s], par);
+                if (lane == 0) TZ_STAMPK(k, 1);                            // loads landed
+                // x = -1 := x = 0 (plane 7 slot 0 of the row), x = 200 := x = 199 (plane 0 slot 0 of the next row)
+                for (int i = lane; i < 2 * (TZ4_R + 2); i += 32) {
+                    const int r = i >> 1;
+                    if (i & 1) sa[0 * TZ4_PS + (r + 1) * TZ4_P] = sa[7 * TZ4_PS + r * TZ4_P + 25];
+                    else sa[7 * TZ4_PS + r * TZ4_P] = sa[0 * TZ4_PS + r * TZ4_P + 1];
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&halo[s]); mbar_arrive(&halo2[s]); }   // ring pass of the draining warps / second issuer
+            } else {
+                mbar_wait(&halo2[s], par);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            if (lane == 0) {
+                if (k >= TZ4_NST) { mbar_wait(&tmem_empty[s], par ^ 1u); tc_fence_after(); }
+                if (half == 0) TZ_STAMPK(k, 2);                            // MMA issue starts
+                const uint32_t sa16 = smem_u32(sa) >> 4;
+                for (int t = half; t < half + 1; t++) {              // warp 9 + t issues tile t
+                    const uint32_t d = tmem_base + (uint32_t)((s * TZ4_T + t) * TZ4_N);
+#pragma unroll
+                    for (int u = 0; u < 3; u++)
+#pragma unroll
+                        for (int ks = 0; ks < 5; ks++) {
+                            // first / second K-chunk of the step: (plane, slot offset); see the header comment
+                            const int q0 = ks == 0 || ks == 4 ? 0 : 2 * ks - 1, o0 = ks == 4 ? 2 : 1;
+                            const uint32_t lbo = (ks == 0 || ks == 4) ? 7u * TZ4_PS - 1u : (uint32_t)TZ4_PS;
+                            const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ4_PS + u * TZ4_P + 128 * t + o0), lbo, 8);
+                            const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 5 + ks) * 2 * TZ4_N), TZ4_N, 8);
+                            tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
+                        }
+                    tc_commit(&acc_full[s * TZ4_T + t]);
+                }
+                tc_commit(&a_empty[s]);                                    // the strip buffer is free once these MMAs have read it
+                if (half == 0) TZ_STAMPK(k, 3);                            // MMA issue done
+            }
+            __syncwarp();
+        }
     } else {
-        // ---- drain: thread = M row (y_local, block) of the tile; 32 columns = 8 pixels x 4 phases
-        for (int t = 0; t < TZ4_T; t++) {
-            mbar_wait(&bars[t], 0);
-            tc_fence_after();
-            TZ_STAMP(5 + t, 0);
-            uint32_t r[32];
-            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * TZ4_N), r);
-            tc_wait_ld();
-            const int m = 128 * t + tid, yl = m / TZ4_P, xb = m - yl * TZ4_P;
-            if (yl >= rows_valid || xb >= 25) continue;
-            const int i = y0 + yl;
-            float v[32];
+        // ------------------------------------------------------------ drain: thread = M row (y_local, block) of the tile
+        mbar_wait(wbar, 0);                               // ring weights
+        const int grp = warp >> 2, gt = tid & 127, gw = warp & 3;     // group g drains every other work item
+        float *ring = reinterpret_cast<float *>(smem + Tz4Smem::off_ring) + grp * TZ4_RING;
+        float *sv = aux + 72 + 16 * grp;                  // per group: 4 warp maxima, then 4 (value, index) pairs
+        int *si = reinterpret_cast<int *>(sv + 8);
+        int k = grp;
+        for (int w = blockIdx.x + grp * gridDim.x; w < n_work; w += TZ4_NG * gridDim.x, k += TZ4_NG) {
+            const int s = k % TZ4_NST, item = w / TZ4_STRIPS, strip = w % TZ4_STRIPS, y0 = strip * TZ4_R;
+            const uint32_t par = (uint32_t)((k / TZ4_NST) & 1);
+            const int rows_valid = min(TZ4_R, TZ4_H - y0);
+            const uint4 *sa = reinterpret_cast<const uint4 *>(smem + Tz4Smem::off_a + s * TZ4_ABYTES);
+            const uint32_t tm = tmem_base + ((uint32_t)(gw * 32) << 16) + (uint32_t)(s * TZ4_T * TZ4_N);
+            float *corr = reinterpret_cast<float *>(smem + Tz4Smem::off_corr) + grp * TZ4_RING;
+            constexpr int Wo = 2 * TZ4_H;
+            const bool first = strip == 0, last = strip == TZ4_STRIPS - 1;
+            const int nslots = 4 * TZ4_R + ((first || last) ? Wo : 0);             // only the first / last strip own a border row
+            // ---- border ring, part 1 (while the MMAs run): the contribution of the taps that fall outside the image, per
+            //      ring pixel (4 lanes per pixel: lanes 0..2 evaluate one out-of-range tap each, lane 0 also the two extra
+            //      taps of a corner).  It needs the staged strip only, so the strip buffer is released right after it.
+            mbar_wait(&halo[s], par);                     // strip + halo slots are in place (acquire)
+            {
+                // Every out-of-range tap of a border-COLUMN pixel sits in column -1 (or 400) of the extended upsampled map,
+                // which is a vertical blend of low-res column 0 (199) alone: cdots[side][row][dy] = w[dy][edge dx] . L[row][edge],
+                // then 6 terms per ring pixel.  Likewise a border-ROW pixel (first / last strip) only sees the vertical blend of
+                // low-res rows -1/0 (199/200): rdots[x][dx] = w[edge dy][dx] . blend[x], 6 terms per pixel.  Corner pixels live
+                // in the column slots and add the two row taps that are not in their column.
+                float *cdots = reinterpret_cast<float *>(smem + Tz4Smem::off_scr) + grp * TZ4_SCR, *rdots = cdots + 2 * (TZ4_R + 2) * 3;
+                const int dye = first ? 0 : 2, Yedge = first ? 0 : Wo - 1;
+                int rlo = 0, rhi = 0; float rwl = 0.f, rwh = 0.f;
+                bil_tap_ext(Yedge + dye - 1, rlo, rhi, rwl, rwh);
+                if (gt < 2 * (TZ4_R + 2) * 3) {
+                    const int side = gt / ((TZ4_R + 2) * 3), rem = gt % ((TZ4_R + 2) * 3), r = rem / 3, dy = rem % 3;
+                    float x[8];
+                    unpack_bf8(sa[(side ? 7 : 0) * TZ4_PS + r * TZ4_P + (side ? 25 : 1)], x);
+                    const float *wp = aux + (dy * 3 + (side ? 2 : 0)) * 8;
+                    float d = 0.f;
 #pragma unroll
-            for (int n = 0; n < 32; n++) v[n] = __uint_as_float(r[n]) + a.bias;
-            // ring pixels (hi-res border) leave through the ring buffer and are corrected after the tile loop; here they
-            // are masked out with -inf so that every thread takes the same branch-free path.  Column slots own the corners.
-            const float NINF = -INFINITY;
-            if (xb == 0) { ring[2 * yl] = v[0]; ring[2 * yl + 1] = v[2]; v[0] = NINF; v[2] = NINF; }
-            if (xb == 24) { ring[2 * TZ4_R + 2 * yl] = v[29]; ring[2 * TZ4_R + 2 * yl + 1] = v[31]; v[29] = NINF; v[31] = NINF; }
-            if (i == 0 || i == TZ4_H - 1) {
-                const int ph_a = i == 0 ? 0 : 1;
+                    for (int ci = 0; ci < 8; ci++) d += x[ci] * wp[ci];
+                    cdots[gt] = d;
+                }
+                if (first || last) {
+                    const PlaneStrip4 Ls{sa, y0};
+                    for (int q = gt; q < 202 * 3; q += 128) {
+                        const int x = q / 3 - 1, dx = q % 3;
+                        float lo[8], hi[8];
+                        unpack_bf8(Ls(rlo, x), lo);
+                        unpack_bf8(Ls(rhi, x), hi);
+                        const float *wp = aux + (dye * 3 + dx) * 8;
+                        float d = 0.f;
 #pragma unroll
-                for (int rem = 0; rem < 16; rem++) {
-                    const int X = 16 * xb + rem;
-                    if (X == 0 || X == 2 * TZ4_H - 1) continue;
-                    if (ph_a == 0) { ring[4 * TZ4_R + X] = v[(rem >> 1) * 4 + (rem & 1)]; v[(rem >> 1) * 4 + (rem & 1)] = NINF; }
-                    else { ring[4 * TZ4_R + X] = v[(rem >> 1) * 4 + 2 + (rem & 1)]; v[(rem >> 1) * 4 + 2 + (rem & 1)] = NINF; }
+                        for (int ci = 0; ci < 8; ci++) d += (rwl * lo[ci] + rwh * hi[ci]) * wp[ci];
+                        rdots[q] = d;
+                    }
+                }
+                named_sync_128(1 + 2 * TZ4_NG + grp);
+                for (int slot = gt; slot < nslots; slot += 128) {
+                    float c = 0.f;
+                    if (slot < 4 * TZ4_R) {
+                        const int side = slot / (2 * TZ4_R), Yl = slot % (2 * TZ4_R), Y = 2 * y0 + Yl;
+                        const float *ds = cdots + side * (TZ4_R + 2) * 3;
+#pragma unroll
+                        for (int dy = 0; dy < 3; dy++) {
+                            int lo, hi; float wlo, whi;
+                            bil_tap_ext(Y + dy - 1, lo, hi, wlo, whi);
+                            c += wlo * ds[(lo - y0 + 1) * 3 + dy] + whi * ds[(hi - y0 + 1) * 3 + dy];
+                        }
+                        if ((first || last) && Y == Yedge) {        // corner: the two taps of the border row outside its column
+                            const int X = side ? Wo - 1 : 0;
+#pragma unroll
+                            for (int dx = 0; dx < 3; dx++) {
+                                if (dx == (side ? 2 : 0)) continue;
+                                int lo, hi; float wlo, whi;
+                                bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                                c += wlo * rdots[(lo + 1) * 3 + dx] + whi * rdots[(hi + 1) * 3 + dx];
+                            }
+                        }
+                    } else {
+                        const int X = slot - 4 * TZ4_R;
+#pragma unroll
+                        for (int dx = 0; dx < 3; dx++) {
+                            int lo, hi; float wlo, whi;
+                            bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                            c += wlo * rdots[(lo + 1) * 3 + dx] + whi * rdots[(hi + 1) * 3 + dx];
+                        }
+                    }
+                    corr[slot] = c;
                 }
             }
-            if (a.ptr_out) {                              // optional dense map (predict()'s second output); ring pixels follow later
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_empty[s]);      // this warp is done with stage s of the strip buffer
+            if (gt == 0) TZ_STAMPK(k, 4);                 // ring corrections done
+            float best_v = -INFINITY;
+            int bt = 0;
+            for (int t = 0; t < TZ4_T; t++) {
+                mbar_wait(&acc_full[s * TZ4_T + t], par);
+                tc_fence_after();
+                uint32_t r[32];
+                tc_ld32(tm + (uint32_t)(t * TZ4_N), r);
+                tc_wait_ld();
+                const int m = 128 * t + gt, yl = m / TZ4_P, xb = m - yl * TZ4_P;
+                if (yl >= rows_valid || xb >= 25) continue;
+                const int i = y0 + yl;
+                float v[32];
+                up4_row_values(r, a.bias, xb, yl, i, ring, v);
+                if (a.ptr_out) {                          // optional dense map (predict()'s second output); ring pixels follow later
 #pragma unroll
-                for (int n = 0; n < 32; n++)
-                    if (v[n] != NINF)
-                        a.ptr_out[(size_t)item * 4 * TZ4_H * TZ4_H + (2 * i + ((n >> 1) & 1)) * 2 * TZ4_H + 16 * xb + 2 * (n >> 2) + (n & 1)] = v[n];
-            }
-            float mx = v[0];
-#pragma unroll
-            for (int n = 1; n < 32; n++) mx = fmaxf(mx, v[n]);
-            if (mx >= best_v) {                           // rare after the first tiles: locate the first maximum in C order
-                int idx = 0x7fffffff;
-#pragma unroll
-                for (int n = 31; n >= 0; n--) {           // descending C order within the thread: the last match is the lowest index
-                    const int ph_a = (n >> 4) & 1, rem = n & 15;                 // order: a, then xo, then b
-                    const int nn = (rem >> 1) * 4 + ph_a * 2 + (rem & 1);
-                    if (v[nn] == mx) idx = (2 * i + ph_a) * 2 * TZ4_H + 16 * xb + rem;
+                    for (int n = 0; n < 32; n++)
+                        if (v[n] != -INFINITY)
+                            a.ptr_out[(size_t)item * 4 * TZ4_H * TZ4_H + (2 * i + ((n >> 1) & 1)) * 2 * TZ4_H + 16 * xb + 2 * (n >> 2) + (n & 1)] = v[n];
                 }
-                if (amax_better(mx, idx, best_v, best_i)) { best_v = mx; best_i = idx; }
+#pragma unroll
+                for (int h = 16; h > 0; h >>= 1)          // tree maximum
+#pragma unroll
+                    for (int n = 0; n < h; n++) v[n] = fmaxf(v[n], v[n + h]);
+                if (v[0] > best_v) { best_v = v[0]; bt = t; }          // strict: the earliest tile (lowest indices) keeps a tie
             }
-        }
-    }
-    TZ_STAMP(9, 0);
-    tc_fence_before();
-    __syncthreads();                                     // ring values are visible to every thread
-    TZ_STAMP(10, 0);
+            if (gt == 0) TZ_STAMPK(k, 5);                 // tiles drained
+            // ---- maximum of the strip's interior, then its first index in C order: only the thread(s) that hold the
+            //      maximum look at their 32 values again (TMEM stage s is still intact)
+            float wv = best_v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wv = fmaxf(wv, __shfl_xor_sync(0xffffffffu, wv, o));
+            if (lane == 0) sv[gw] = wv;
+            named_sync_128(1 + grp);                      // warp maxima, ring values and ring corrections of all four warps are visible
+            const float V = fmaxf(fmaxf(sv[0], sv[1]), fmaxf(sv[2], sv[3]));
+            const bool cand = best_v == V && V > -INFINITY;
+            int best_i = 0x7fffffff;
+            unsigned bal = __ballot_sync(0xffffffffu, cand);
+            while (bal) {
+                const int tt = __shfl_sync(0xffffffffu, bt, __ffs(bal) - 1);
+                uint32_t r[32];
+                tc_ld32(tm + (uint32_t)(tt * TZ4_N), r);
+                tc_wait_ld();
+                const bool mine = cand && bt == tt;
+                if (mine) {
+                    const int m = 128 * tt + gt, yl = m / TZ4_P, xb = m - yl * TZ4_P, i = y0 + yl;
+                    float v[32];
+                    up4_row_values(r, a.bias, xb, yl, i, nullptr, v);
+#pragma unroll
+                    for (int n = 31; n >= 0; n--) {       // descending C order within the thread: the last match is the lowest index
+                        const int ph_a = (n >> 4) & 1, rem = n & 15;             // order: a, then xo, then b
+                        if (v[(rem >> 1) * 4 + ph_a * 2 + (rem & 1)] == V) best_i = (2 * i + ph_a) * 2 * TZ4_H + 16 * xb + rem;
+                    }
+                }
+                bal &= ~__ballot_sync(0xffffffffu, mine);
+            }
+            best_v = cand ? V : -INFINITY;
+            tc_fence_before();                            // this warp's TMEM reads of stage s are complete
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[s]);
 
-    // ---- border ring: take the out-of-range taps back out of the folded result (4 lanes per ring pixel: lanes 0..2
-    //      evaluate one out-of-range tap each, lane 0 also the two extra taps of a corner), then consume the pixel
-    {
-        constexpr int Wo = 2 * TZ4_H;
-        const bool first = blockIdx.x == 0, last = blockIdx.x == gridDim.x - 1;
-        const int nslots = 4 * TZ4_R + ((first || last) ? Wo : 0);             // only the first / last strip own a border row
-        const PlaneStrip4 Ls{sa, y0};
-        for (int base = 0; base < nslots * 4; base += TZ4_NT) {
-            const int itm = base + tid, slot = itm >> 2, j = itm & 3;
-            int Y = 0, X = 0;
-            bool valid = slot < nslots;
-            if (slot < 2 * TZ4_R) { Y = 2 * y0 + slot; X = 0; valid = valid && slot < 2 * rows_valid; }
-            else if (slot < 4 * TZ4_R) { Y = 2 * y0 + slot - 2 * TZ4_R; X = Wo - 1; valid = valid && slot - 2 * TZ4_R < 2 * rows_valid; }
-            else {
-                X = slot - 4 * TZ4_R;
-                valid = valid && (first || last) && X != 0 && X != Wo - 1;
-                Y = first ? 0 : Wo - 1;
+            // ---- border ring, part 2: folded value - out-of-range taps = the true (zero-padded) convolution
+            for (int slot = gt; slot < nslots; slot += 128) {
+                int Y, X;
+                bool valid = true;
+                if (slot < 2 * TZ4_R) { Y = 2 * y0 + slot; X = 0; valid = slot < 2 * rows_valid; }
+                else if (slot < 4 * TZ4_R) { Y = 2 * y0 + slot - 2 * TZ4_R; X = Wo - 1; valid = slot - 2 * TZ4_R < 2 * rows_valid; }
+                else { X = slot - 4 * TZ4_R; valid = X != 0 && X != Wo - 1; Y = first ? 0 : Wo - 1; }
+                if (!valid) continue;
+                const float val = ring[slot] - corr[slot];
+                const int idx = Y * Wo + X;
+                if (a.ptr_out) a.ptr_out[(size_t)item * Wo * Wo + idx] = val;
+                if (amax_better(val, idx, best_v, best_i)) { best_v = val; best_i = idx; }
             }
-            // a strip that is both first and last does not exist (11 strips); the top row belongs to the first, the bottom to the last
-            float acc = 0.f;
-            if (valid && j < 3) {
-                const bool xedge = (X == 0 || X == Wo - 1), yedge = (Y == 0 || Y == Wo - 1);
-                const int dxe = X == 0 ? 0 : 2, dye = Y == 0 ? 0 : 2;
-                if (xedge) up_ring_tap<8, 1>(Ls, Y, X, j, dxe, aux, &acc);
-                else up_ring_tap<8, 1>(Ls, Y, X, dye, j, aux, &acc);
-                if (xedge && yedge && j == 0)                       // corner: the two remaining taps of the edge row
-                    for (int dx = 0; dx < 3; dx++)
-                        if (dx != dxe) up_ring_tap<8, 1>(Ls, Y, X, dye, dx, aux, &acc);
+            amax_warp(best_v, best_i);
+            if (lane == 0) { sv[4 + gw] = best_v; si[4 + gw] = best_i; }
+            named_sync_128(1 + TZ4_NG + grp);
+            if (gt == 0) {
+                for (int q = 1; q < 4; q++)
+                    if (amax_better(sv[4 + q], si[4 + q], best_v, best_i)) { best_v = sv[4 + q]; best_i = si[4 + q]; }
+                a.amax_val[(size_t)item * TZ4_STRIPS + strip] = best_v;
+                a.amax_idx[(size_t)item * TZ4_STRIPS + strip] = best_i;
+                TZ_STAMPK(k, 6);                          // work item finished
             }
-            const float t1 = __shfl_down_sync(0xffffffffu, acc, 1), t2 = __shfl_down_sync(0xffffffffu, acc, 2);
-            const float corr = (acc + t1) + t2;
-            if (!valid || j != 0) continue;
-            const float val = ring[slot] - corr;
-            const int idx = Y * Wo + X;
-            if (a.ptr_out) a.ptr_out[(size_t)item * Wo * Wo + idx] = val;
-            if (amax_better(val, idx, best_v, best_i)) { best_v = val; best_i = idx; }
-        }
-    }
-    TZ_STAMP(11, 0);
-    {
-        float *sv = aux + 72;
-        int *si = reinterpret_cast<int *>(aux + 80);
-        amax_warp(best_v, best_i);
-        if (lane == 0) { sv[warp] = best_v; si[warp] = best_i; }
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 1; k < TZ4_NT / 32; k++)
-                if (amax_better(sv[k], si[k], best_v, best_i)) { best_v = sv[k]; best_i = si[k]; }
-            a.amax_val[(size_t)item * gridDim.x + blockIdx.x] = best_v;
-            a.amax_idx[(size_t)item * gridDim.x + blockIdx.x] = best_i;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     TZ_STAMP(12, 0);
+}
+
+// ================================================================================================
+// k_tz_up3: upsampling3 + upconv3 + BN + ReLU (qlearnIA_V2.py:178-181), 100 x 100 x 4 -> 200 x 200 x 8.
+// Same scheme with blocks of B = 4 pixels: the input (upconv2's output, written by k_heads) is de-interleaved by
+// x mod 4 into 4 planes of P = 26 slots per row; K = 6 pixel chunks (3 K-steps), N = 4 px x 4 phases x 8 channels = 128.
+// A strip is 9 rows = 234 M rows = 2 tiles x 9 MMAs.  The epilogue thread owns 4 low-res pixels = 8 x 2 output pixels
+// and writes them straight in k_tz_up4's plane layout (its 8 x-values are exactly the 8 planes of one block).
+// ================================================================================================
+#define TZ3_H 100
+#define TZ3_P 26
+#define TZ3_R 9
+#define TZ3_T 2
+#define TZ3_PS 312                    // (R + 2) * P + 2 + tile overrun (256 - 234), rounded to 8
+#define TZ3_N 128
+#define TZ3_NT 160
+#define TZ3_STRIPS ((TZ3_H + TZ3_R - 1) / TZ3_R)
+#define TZ3_WBYTES (3 * 3 * 2 * TZ3_N * 16)
+
+struct Tz3Args {
+    const __nv_bfloat16 *in;          // plane layout [item][4][100][26][8] (channels 4..7 zero)
+    const __nv_bfloat16 *wt;          // B operand [3 dy][3 k-steps][2 chunks][128 n][8 cin]
+    const float *bias;                // [32] = bias[co] per phase
+    const float *ring_w;              // un-phased fp32 weights [9][4][8]
+    __nv_bfloat16 *out;               // plane layout [item][8][200][26][8]
+};
+
+struct Tz3Smem {
+    static constexpr unsigned off_w = 0;
+    static constexpr unsigned off_a = TZ3_WBYTES;
+    static constexpr unsigned off_ring = off_a + 4 * TZ3_PS * 16;              // 8 floats per ring pixel: 2R left, 2R right, 200 top/bottom
+    static constexpr unsigned off_aux = off_ring + (4 * TZ3_R + 200) * 32;     // 288 ring weights
+    static constexpr unsigned off_bar = off_aux + 288 * 4;
+    static constexpr unsigned total = off_bar + (TZ3_T + 1) * 8 + 16;
+};
+
+struct PlaneStrip3 {
+    const uint4 *pl;
+    int y0;
+    __device__ __forceinline__ uint4 operator()(int y, int x) const { return pl[(x & 3) * TZ3_PS + (y - y0 + 1) * TZ3_P + (x >> 2) + 1]; }
+};
+
+__global__ void __launch_bounds__(TZ3_NT)
+k_tz_up3(const Tz3Args a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int item = blockIdx.y, y0 = blockIdx.x * TZ3_R;
+    const int rows_valid = min(TZ3_R, TZ3_H - y0);
+    uint4 *sw = reinterpret_cast<uint4 *>(smem + Tz3Smem::off_w);
+    uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz3Smem::off_a);
+    float *ring = reinterpret_cast<float *>(smem + Tz3Smem::off_ring);
+    float *aux = reinterpret_cast<float *>(smem + Tz3Smem::off_aux);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Tz3Smem::off_bar);
+    uint64_t *lbar = &bars[TZ3_T];
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Tz3Smem::off_bar + (TZ3_T + 1) * 8);
+
+    if (tid == 128) {
+        for (int t = 0; t <= TZ3_T; t++) mbar_init(&bars[t], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int ylo = max(y0 - 1, 0), yhi = min(y0 + TZ3_R, TZ3_H - 1);
+        const uint32_t run = (uint32_t)(yhi - ylo + 1) * TZ3_P * 16;
+        const bool top = y0 == 0, bot = y0 + TZ3_R > TZ3_H - 1;
+        mbar_expect_tx(lbar, 4u * (run + (top ? TZ3_P * 16 : 0) + (bot ? TZ3_P * 16 : 0)) + TZ3_WBYTES + 288 * 4);
+        bulk_g2s(sw, a.wt, TZ3_WBYTES, lbar);
+        bulk_g2s(aux, a.ring_w, 288 * 4, lbar);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.in) + (size_t)item * (4 * TZ3_H * TZ3_P * 16);
+        for (int q = 0; q < 4; q++) {
+            const uint8_t *pq = src + (size_t)q * TZ3_H * TZ3_P * 16;
+            uint4 *dq = sa + q * TZ3_PS;
+            bulk_g2s(dq + (ylo - (y0 - 1)) * TZ3_P, pq + (size_t)ylo * TZ3_P * 16, run, lbar);
+            if (top) bulk_g2s(dq, pq, TZ3_P * 16, lbar);
+            if (bot) bulk_g2s(dq + (TZ3_H - (y0 - 1)) * TZ3_P, pq + (size_t)(TZ3_H - 1) * TZ3_P * 16, TZ3_P * 16, lbar);
+        }
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    float biasr[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) biasr[i] = a.bias[i];
+    __syncthreads();
+    mbar_wait(lbar, 0);
+    for (int i = tid; i < 2 * (TZ3_R + 2); i += TZ3_NT) {
+        const int r = i >> 1;
+        if (i & 1) sa[0 * TZ3_PS + (r + 1) * TZ3_P] = sa[3 * TZ3_PS + r * TZ3_P + 25];     // x = 100 := x = 99
+        else sa[3 * TZ3_PS + r * TZ3_P] = sa[0 * TZ3_PS + r * TZ3_P + 1];                 // x = -1 := x = 0
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    __nv_bfloat16 *dst = a.out + (size_t)item * POL_UP3_ITEM;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            constexpr uint32_t IDESC = instr_desc(TZ3_N);
+            const uint32_t sa16 = smem_u32(sa) >> 4, sw16 = smem_u32(sw) >> 4;
+            for (int t = 0; t < TZ3_T; t++) {
+                const uint32_t d = tmem_base + (uint32_t)(t * TZ3_N);
+#pragma unroll
+                for (int u = 0; u < 3; u++)
+#pragma unroll
+                    for (int ks = 0; ks < 3; ks++) {
+                        const int q0 = ks == 1 ? 1 : 0, o0 = ks == 2 ? 2 : 1;
+                        const uint32_t lbo = ks == 1 ? (uint32_t)TZ3_PS : 3u * TZ3_PS - 1u;
+                        const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ3_PS + u * TZ3_P + 128 * t + o0), lbo, 8);
+                        const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 3 + ks) * 2 * TZ3_N), TZ3_N, 8);
+                        tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
+                    }
+                tc_commit(&bars[t]);
+            }
+        }
+        __syncwarp();
+    } else {
+        for (int t = 0; t < TZ3_T; t++) {
+            mbar_wait(&bars[t], 0);
+            tc_fence_after();
+            const int m = 128 * t + tid, yl = m / TZ3_P, xb = m - yl * TZ3_P;
+            const bool valid = yl < rows_valid && xb < 25;
+            const int i = y0 + yl;
+#pragma unroll
+            for (int xo = 0; xo < 4; xo++) {              // 32 columns = the 4 phases x 8 channels of low-res pixel 4 xb + xo
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * TZ3_N + xo * 32), r);
+                tc_wait_ld();
+                if (!valid) continue;
+#pragma unroll
+                for (int ph = 0; ph < 4; ph++) {
+                    const int Y = 2 * i + (ph >> 1), X = 8 * xb + 2 * xo + (ph & 1);
+                    float o[8];
+#pragma unroll
+                    for (int co = 0; co < 8; co++) o[co] = __uint_as_float(r[ph * 8 + co]) + biasr[ph * 8 + co];
+                    if (Y == 0 || Y == 2 * TZ3_H - 1 || X == 0 || X == 2 * TZ3_H - 1) {          // ring: corrected after the tile loop
+                        float *rb = ring + 8 * (X == 0 ? Y - 2 * y0 : (X == 2 * TZ3_H - 1 ? 2 * TZ3_R + Y - 2 * y0 : 4 * TZ3_R + X));
+#pragma unroll
+                        for (int co = 0; co < 8; co++) rb[co] = o[co];
+                        continue;
+                    }
+#pragma unroll
+                    for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
+                    *reinterpret_cast<uint4 *>(dst + pol_plane200_off(Y, X)) = pack_bf8(o);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+
+    {   // border ring (see k_tz_up4): 4 lanes per ring pixel, 8 channels each
+        constexpr int Wo = 2 * TZ3_H;
+        const bool first = blockIdx.x == 0, last = blockIdx.x == gridDim.x - 1;
+        const int nslots = 4 * TZ3_R + ((first || last) ? Wo : 0);
+        const PlaneStrip3 Ls{sa, y0};
+        for (int base = 0; base < nslots * 4; base += TZ3_NT) {
+            const int itm = base + tid, slot = itm >> 2, j = itm & 3;
+            int Y = 0, X = 0;
+            bool valid = slot < nslots;
+            if (slot < 2 * TZ3_R) { Y = 2 * y0 + slot; X = 0; valid = valid && slot < 2 * rows_valid; }
+            else if (slot < 4 * TZ3_R) { Y = 2 * y0 + slot - 2 * TZ3_R; X = Wo - 1; valid = valid && slot - 2 * TZ3_R < 2 * rows_valid; }
+            else {
+                X = slot - 4 * TZ3_R;
+                valid = valid && X != 0 && X != Wo - 1;
+                Y = first ? 0 : Wo - 1;
+            }
+            float acc[8];
+#pragma unroll
+            for (int co = 0; co < 8; co++) acc[co] = 0.f;
+            if (valid && j < 3) {
+                const bool xedge = (X == 0 || X == Wo - 1), yedge = (Y == 0 || Y == Wo - 1);
+                const int dxe = X == 0 ? 0 : 2, dye = Y == 0 ? 0 : 2;
+                if (xedge) up_ring_tap<4, 8>(Ls, Y, X, j, dxe, aux, acc);
+                else up_ring_tap<4, 8>(Ls, Y, X, dye, j, aux, acc);
+                if (xedge && yedge && j == 0)
+                    for (int dx = 0; dx < 3; dx++)
+                        if (dx != dxe) up_ring_tap<4, 8>(Ls, Y, X, dye, dx, aux, acc);
+            }
+            float o[8];
+#pragma unroll
+            for (int co = 0; co < 8; co++) {
+                const float t1 = __shfl_down_sync(0xffffffffu, acc[co], 1), t2 = __shfl_down_sync(0xffffffffu, acc[co], 2);
+                o[co] = (acc[co] + t1) + t2;
+            }
+            if (!valid || j != 0) continue;
+#pragma unroll
+            for (int co = 0; co < 8; co++) o[co] = fmaxf(ring[8 * slot + co] - o[co], 0.f);
+            *reinterpret_cast<uint4 *>(dst + pol_plane200_off(Y, X)) = pack_bf8(o);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
 }
 
 // ---------------------------------------------------------------- host side
@@ -262,19 +607,34 @@ extern "C" int ofb_policy_tz_debug(long long *dev_buf) { g_tz_dbg = dev_buf; ret
 
 int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st) {
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local int n_sm = 0;
+    if (!n_sm) {
         OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tz_up4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tz4Smem::total));
-        configured = true;
+        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
     }
     if (n_items == 0) return OFB_OK;
     Tz4Args a = {};
     a.in = in; a.wt = p->w.u4_tz; a.ring_w = p->w.u4_w; a.bias = p->u4_bias;
     a.ptr_out = ptr_out; a.amax_val = amax_val; a.amax_idx = amax_idx;
     a.dbg = g_tz_dbg;
-    k_tz_up4<<<dim3(TZ4_STRIPS, n_items), TZ4_NT, Tz4Smem::total, st>>>(a);
+    const int n_work = n_items * TZ4_STRIPS;
+    k_tz_up4<<<n_work < n_sm ? n_work : n_sm, TZ4_NTP, Tz4Smem::total, st>>>(a, n_work);     // one persistent CTA per SM
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }
 
 int pol_tz_up4_parts() { return TZ4_STRIPS; }
+
+int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
+    static thread_local bool configured = false;
+    if (!configured) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tz_up3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tz3Smem::total));
+        configured = true;
+    }
+    if (n_items == 0) return OFB_OK;
+    Tz3Args a = {};
+    a.in = in; a.wt = p->w.u3_tz; a.bias = p->w.u3_pb; a.ring_w = p->w.u3_w; a.out = out;
+    k_tz_up3<<<dim3(TZ3_STRIPS, n_items), TZ3_NT, Tz3Smem::total, st>>>(a);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}

@@ -38,7 +38,7 @@ def main():
     if os.environ.get("OFB_TZ_DEBUG"):
         import ctypes
         from ofighters_b200 import _lib
-        dbg = torch.zeros(16, dtype=torch.int64, device=bg.device)
+        dbg = torch.zeros(16 + 8 * 14, dtype=torch.int64, device=bg.device)
         lib = _lib.load()
         lib.ofb_policy_tz_debug.argtypes = [ctypes.c_void_p]
         lib.ofb_policy_tz_debug(ctypes.c_void_p(dbg.data_ptr()))
@@ -48,6 +48,9 @@ def main():
         torch.cuda.synchronize()
         st = dbg.cpu().tolist()
         print("tz_up4 stamps (cycles since start):", [x - st[0] if x else None for x in st[:13]])
+        for k in range(14):
+            row = st[16 + 8 * k: 16 + 8 * k + 7]
+            print("  work %2d: issue %s landed %s mma0 %s mma1 %s corr %s drained %s done %s" % ((k,) + tuple(x - st[0] if x else None for x in row)))
         lib.ofb_policy_tz_debug(None)
     for eng in engines:
         pol.set_engine(eng)
