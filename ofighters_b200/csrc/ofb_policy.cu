@@ -150,6 +150,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
         fold_conv(wh->conv[l + 1], 8, 8, w, b);
         b.resize(16, 0.f);
         up.add(&d.cw[l], pack_taps(w, 8, 8, 16));
+        if (l == 0) up.add(&d.c2_tz, pack_toeplitz(w, 8, 8, 8));
         up.add(&d.cw2[l], pack_dyfold(w, 8, 8, 8, 32));
         up.add(&d.cb[l], b);
     }
@@ -626,7 +627,7 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     const bool tc = p->engine == OFB_ENGINE_TENSOR;
     int rc;
     if (tc) {
-        { ProfScope ps(p, L_TRUNK12, st); if ((rc = pol_tc_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc; }
+        { ProfScope ps(p, L_TRUNK12, st); if ((rc = pol_tz_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc; }
         { ProfScope ps(p, L_CONV3, st); if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc; }
         { ProfScope ps(p, L_CONV4, st); if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc; }
     } else {

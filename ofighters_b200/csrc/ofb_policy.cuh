@@ -41,6 +41,7 @@ struct PolicyDev {
     __nv_bfloat16 *u4_pw;     // [10][16][8]      (tap, n = phase (4 used), cin)
     float *u4_pb;             // [16]
     __nv_bfloat16 *u4_pw2;    // tensor engine: [4 u][16 n = v*4 + phase][8 cin]
+    __nv_bfloat16 *c2_tz;     // block-Toeplitz B operand of conv2: [3 u][5 k-steps][2 chunks][64 n = xo*8 + cout][8 cin]
     __nv_bfloat16 *u3_tz;     // block-Toeplitz B operand of upconv3: [3 u][3 k-steps][2 chunks][128 n = xo*32 + phase*8 + cout][8 cin]
     __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
 };
@@ -87,6 +88,7 @@ int pol_tc_up4_parts();
 int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st);
 int pol_tz_up4_parts();
+int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 // element offset of pixel (y, x) of a 100 x 100 x 8 image in plane layout (4 planes of x mod 4)
 __host__ __device__ __forceinline__ int pol_plane100_off(int y, int x) { return (((x & 3) * 100 + y) * 26 + (x >> 2) + 1) * 8; }

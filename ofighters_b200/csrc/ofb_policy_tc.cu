@@ -261,7 +261,10 @@ k_tc_conv(const TcArgs a) {
     // ---- descriptors
     constexpr uint32_t IDESC = instr_desc(N);
     const uint32_t sin16 = smem_u32(sin) >> 4, sw16 = smem_u32(sw) >> 4;
-    auto issue_tile = [&](int t) {
+    // called by the whole (converged) issuer warp: the descriptors are warp-uniform values, one elected lane issues.
+    // (Issuing from inside an `if (lane == 0)` region costs ~80 cycles per MMA in register -> uniform-register moves;
+    // this form issues back to back and leaves the tensor pipe's operand reads, ~39 cycles per MMA, as the limit.)
+    auto issue_tile = [&](int t, bool leader) {
         const uint32_t d = tmem_base + (uint32_t)((t % TC_RING) * N);
 #pragma unroll
         for (int j = 0; j < 5; j++) {
@@ -270,9 +273,9 @@ k_tc_conv(const TcArgs a) {
             const int off1 = t1 < 9 ? (t1 / 3) * P + (t1 % 3) : off0 + 1;     // tap 9: zero weights
             const uint64_t ad = smem_desc(sin16 + (uint32_t)(128 * t + off0), (uint32_t)(off1 - off0), 8);
             const uint64_t bd = smem_desc(sw16 + (uint32_t)(t0 * N), (uint32_t)N, 8);
-            tc_mma(d, ad, bd, IDESC, j > 0 ? 1u : 0u);
+            if (leader) tc_mma(d, ad, bd, IDESC, j > 0 ? 1u : 0u);
         }
-        tc_commit(&bars[t % TC_RING]);
+        if (leader) tc_commit(&bars[t % TC_RING]);
     };
 
     float best_v = -INFINITY;
@@ -280,14 +283,14 @@ k_tc_conv(const TcArgs a) {
     // warp 8 = MMA issuer: queues tile t as soon as accumulator t % TC_RING has been drained (empty barrier);
     // warps 0-7 = drain: warps 0-3 take even tiles, warps 4-7 odd tiles, one TMEM lane quarter each
     if (warp == 8) {
-        if ((tid & 31) == 0)
-            for (int t = 0; t < T; t++) {
-                if (t >= TC_RING) {
-                    mbar_wait(&ebars[t % TC_RING], (uint32_t)(((t / TC_RING) - 1) & 1));
-                    tc_fence_after();
-                }
-                issue_tile(t);
+        const bool leader = elect_one();
+        for (int t = 0; t < T; t++) {
+            if (t >= TC_RING) {
+                mbar_wait(&ebars[t % TC_RING], (uint32_t)(((t / TC_RING) - 1) & 1));
+                tc_fence_after();
             }
+            issue_tile(t, leader);
+        }
         __syncwarp();
     }
     TC_STAMP(6);

@@ -200,27 +200,30 @@ k_tz_up4(const Tz4Args a, const int n_work) {
                 mbar_wait(&halo2[s], par);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             }
-            if (lane == 0) {
-                if (k >= TZ4_NST) { mbar_wait(&tmem_empty[s], par ^ 1u); tc_fence_after(); }
-                if (half == 0) TZ_STAMPK(k, 2);                            // MMA issue starts
+            // the whole warp stays converged so that the descriptors are warp-uniform values; one elected lane issues
+            if (k >= TZ4_NST) { mbar_wait(&tmem_empty[s], par ^ 1u); tc_fence_after(); }
+            if (half == 0 && lane == 0) TZ_STAMPK(k, 2);                   // MMA issue starts
+            {
+                const bool leader = elect_one();
                 const uint32_t sa16 = smem_u32(sa) >> 4;
-                for (int t = half; t < half + 1; t++) {              // warp 9 + t issues tile t
-                    const uint32_t d = tmem_base + (uint32_t)((s * TZ4_T + t) * TZ4_N);
+                const int t = half;                                        // warp 4 NG + 1 + t issues tile t
+                const uint32_t d = tmem_base + (uint32_t)((s * TZ4_T + t) * TZ4_N);
 #pragma unroll
-                    for (int u = 0; u < 3; u++)
+                for (int u = 0; u < 3; u++)
 #pragma unroll
-                        for (int ks = 0; ks < 5; ks++) {
-                            // first / second K-chunk of the step: (plane, slot offset); see the header comment
-                            const int q0 = ks == 0 || ks == 4 ? 0 : 2 * ks - 1, o0 = ks == 4 ? 2 : 1;
-                            const uint32_t lbo = (ks == 0 || ks == 4) ? 7u * TZ4_PS - 1u : (uint32_t)TZ4_PS;
-                            const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ4_PS + u * TZ4_P + 128 * t + o0), lbo, 8);
-                            const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 5 + ks) * 2 * TZ4_N), TZ4_N, 8);
-                            tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
-                        }
+                    for (int ks = 0; ks < 5; ks++) {
+                        // first / second K-chunk of the step: (plane, slot offset); see the header comment
+                        const int q0 = ks == 0 || ks == 4 ? 0 : 2 * ks - 1, o0 = ks == 4 ? 2 : 1;
+                        const uint32_t lbo = (ks == 0 || ks == 4) ? 7u * TZ4_PS - 1u : (uint32_t)TZ4_PS;
+                        const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ4_PS + u * TZ4_P + 128 * t + o0), lbo, 8);
+                        const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 5 + ks) * 2 * TZ4_N), TZ4_N, 8);
+                        if (leader) tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
+                    }
+                if (leader) {
                     tc_commit(&acc_full[s * TZ4_T + t]);
+                    tc_commit(&a_empty[s]);                                // the strip buffer is free once these MMAs have read it
                 }
-                tc_commit(&a_empty[s]);                                    // the strip buffer is free once these MMAs have read it
-                if (half == 0) TZ_STAMPK(k, 3);                            // MMA issue done
+                if (half == 0 && lane == 0) TZ_STAMPK(k, 3);               // MMA issue done
             }
             __syncwarp();
         }
@@ -635,6 +638,300 @@ int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out,
     Tz3Args a = {};
     a.in = in; a.wt = p->w.u3_tz; a.bias = p->w.u3_pb; a.ring_w = p->w.u3_w; a.out = out;
     k_tz_up3<<<dim3(TZ3_STRIPS, n_items), TZ3_NT, Tz3Smem::total, st>>>(a);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+// ================================================================================================
+// k_tz_trunk12: conv1 + BN + ReLU + pool (from the bit maps) -> conv2 + BN + ReLU + pool (qlearnIA_V2.py:129-139),
+// 400 x 400 x 2 bits -> 100 x 100 x 8, persistent and warp-specialised like k_tz_up4.
+//
+// conv1's pooled output is a constant vector ("background") wherever the 4 x 4 map patch under a pooled pixel holds no
+// set bit -- ~96 % of an arena -- so the strip buffers are kept FILLED with the background between work items: the
+// producer warps only scan the strip's bit rows, evaluate the dirty pixels exactly (9-bit stencil pattern LUT, as in the
+// pixel-linear kernel) and put the background back after the MMAs have read the strip.  conv2 is the block-Toeplitz GEMM
+// (N = 8 px x 8 channels = 64, 15 MMAs per tile); the draining warps pool along x in registers (their 8 pixels are 4
+// pooling pairs) and along y through a shared-memory stage.
+// ================================================================================================
+#define TZ2_H 200                     // conv2 grid
+#define TZ2_P 26
+#define TZ2_R 14                      // conv2 rows per strip (even: 7 pooled rows); 14 * 26 = 364 M rows = 3 tiles
+#define TZ2_T 3
+#define TZ2_PS 440
+#define TZ2_N 64
+#define TZ2_NST 2                     // stages = draining groups
+#define TZ2_STRIPS ((TZ2_H + TZ2_R - 1) / TZ2_R)
+#define TZ2_NTP (32 * (4 * TZ2_NST + 4 + TZ2_T))      // 8 draining + 4 producer + 3 MMA warps
+#define TZ2_ABYTES (8 * TZ2_PS * 16)
+#define TZ2_WBYTES (3 * 5 * 2 * TZ2_N * 16)
+#define TZ2_BITW 456                  // words of one staged bit map: (2 R + 6) rows x 50 B + alignment slack
+#define TZ2_WL ((TZ2_R + 2) * TZ2_H)  // dirty-pixel list capacity = every pixel of the strip
+#define TZ2_STG 384                   // M rows of the pooling stage
+
+struct Tz2Args {
+    const uint32_t *maps;             // [item][2][5000]
+    const __nv_bfloat16 *wt;          // conv2 block-Toeplitz B operand [3][5][2][64][8]
+    const float *bias;                // conv2 bias [8]
+    const float *c1_lut, *c1_b;       // conv1 pattern LUT [2][512][8], bias [8]
+    __nv_bfloat16 *out;               // pool2 NHWC [item][100][100][8]
+    long long *dbg;
+};
+
+struct Tz2Smem {
+    static constexpr unsigned off_w = 0;
+    static constexpr unsigned off_a = TZ2_WBYTES;
+    static constexpr unsigned off_bits = off_a + TZ2_NST * TZ2_ABYTES;                 // [stage][2 maps][BITW]
+    static constexpr unsigned off_wl = off_bits + TZ2_NST * 2 * TZ2_BITW * 4;           // [stage][WL] ushort
+    static constexpr unsigned off_stg = (off_wl + TZ2_NST * TZ2_WL * 2 + 15) & ~15u;    // [group][STG][4] uint4
+    static constexpr unsigned off_misc = off_stg + TZ2_NST * TZ2_STG * 64;              // counters, biases
+    static constexpr unsigned off_bar = off_misc + 128;
+    // barriers: wbar, bits_full[NST], full_a[NST], a_empty[NST], tmem_empty[NST], acc_full[NST][T]
+    static constexpr unsigned n_bar = 1 + 4 * TZ2_NST + TZ2_NST * TZ2_T;
+    static constexpr unsigned total = off_bar + n_bar * 8 + 16;
+};
+
+__device__ __forceinline__ void named_sync_n(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__global__ void __launch_bounds__(TZ2_NTP, 1)
+k_tz_trunk12(const Tz2Args a, const int n_work) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint4 *sw = reinterpret_cast<uint4 *>(smem + Tz2Smem::off_w);
+    int *misc = reinterpret_cast<int *>(smem + Tz2Smem::off_misc);          // [0..1] dirty counts per stage
+    float *sbias = reinterpret_cast<float *>(misc + 8);                      // conv1 bias [8], conv2 bias [8]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Tz2Smem::off_bar);
+    uint64_t *wbar = bars, *bits_full = bars + 1, *full_a = bits_full + TZ2_NST, *a_empty = full_a + TZ2_NST,
+             *tmem_empty = a_empty + TZ2_NST, *acc_full = tmem_empty + TZ2_NST;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Tz2Smem::off_bar + Tz2Smem::n_bar * 8);
+
+    if (tid == 0) {
+        mbar_init(wbar, 1);
+        for (int s = 0; s < TZ2_NST; s++) {
+            mbar_init(&bits_full[s], 1);
+            mbar_init(&full_a[s], 4);                      // the 4 producer warps
+            mbar_init(&a_empty[s], TZ2_T);                 // the MMA warps (tcgen05.commit)
+            mbar_init(&tmem_empty[s], 4);                  // the 4 warps of the draining group
+            for (int t = 0; t < TZ2_T; t++) mbar_init(&acc_full[s * TZ2_T + t], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 16) sbias[tid] = tid < 8 ? a.c1_b[tid] : a.bias[tid - 8];
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp >= 4 * TZ2_NST && warp < 4 * TZ2_NST + 4) {
+        // ------------------------------------------------------------ producer group (128 threads)
+        const int pt = tid - 128 * TZ2_NST;
+        float bg[8];
+#pragma unroll
+        for (int co = 0; co < 8; co++) bg[co] = fmaxf(sbias[co], 0.f);
+        const uint4 bgq = pack_bf8(bg), zq = make_uint4(0, 0, 0, 0);
+        // both stages start clean: background everywhere, zeros in the x halo slots (slot 0 of planes 0 and 7)
+        for (int i = pt; i < TZ2_NST * 8 * TZ2_PS; i += 128) {
+            const int q = (i / TZ2_PS) % 8, t = (i % TZ2_PS) % TZ2_P;
+            reinterpret_cast<uint4 *>(smem + Tz2Smem::off_a)[i] = ((q == 0 || q == 7) && t == 0) ? zq : bgq;
+        }
+        auto issue_bits = [&](int k, int w) {               // one thread: stage the bit rows of work item w
+            const int s = k & 1, item = w / TZ2_STRIPS, y0 = (w % TZ2_STRIPS) * TZ2_R;
+            const int r0 = max(2 * y0 - 3, 0), r1 = min(2 * (y0 + TZ2_R) + 2, POL_W - 1);
+            const int b0 = (r0 * 50) & ~15, b1 = min(((r1 + 1) * 50 + 15 + 16) & ~15, POL_WORDS * 4);
+            uint32_t *sb = reinterpret_cast<uint32_t *>(smem + Tz2Smem::off_bits) + s * 2 * TZ2_BITW;
+            const uint8_t *src = reinterpret_cast<const uint8_t *>(a.maps) + (size_t)item * 2 * POL_WORDS * 4;
+            mbar_expect_tx(&bits_full[s], 2u * (uint32_t)(b1 - b0));
+            bulk_g2s(sb, src + b0, (uint32_t)(b1 - b0), &bits_full[s]);
+            bulk_g2s(sb + TZ2_BITW, src + POL_WORDS * 4 + b0, (uint32_t)(b1 - b0), &bits_full[s]);
+        };
+        if (pt == 0) {
+            mbar_expect_tx(wbar, TZ2_WBYTES);
+            bulk_g2s(sw, a.wt, TZ2_WBYTES, wbar);
+            if (blockIdx.x < n_work) issue_bits(0, blockIdx.x);
+        }
+        named_sync_n(1, 128);
+        int k = 0, prev_y0[TZ2_NST] = {-1000, -1000};
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
+            const int s = k & 1, y0 = (w % TZ2_STRIPS) * TZ2_R;
+            const uint32_t par = (uint32_t)((k >> 1) & 1);
+            uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz2Smem::off_a + s * TZ2_ABYTES);
+            unsigned short *wl = reinterpret_cast<unsigned short *>(smem + Tz2Smem::off_wl) + s * TZ2_WL;
+            const uint32_t *sb = reinterpret_cast<const uint32_t *>(smem + Tz2Smem::off_bits) + s * 2 * TZ2_BITW;
+            if (k >= 2) {
+                // ---- the MMAs of the previous item in this stage are done: put the background back
+                mbar_wait(&a_empty[s], par ^ 1u);
+                const int n_old = misc[s];
+                for (int i = pt; i < n_old; i += 128) {
+                    const int e = wl[i], r = e / TZ2_H, px = e % TZ2_H;
+                    sa[(px & 7) * TZ2_PS + r * TZ2_P + (px >> 3) + 1] = bgq;
+                }
+                const int zr = prev_y0[s] == 0 ? 0 : (prev_y0[s] + TZ2_R >= TZ2_H ? TZ2_H - (prev_y0[s] - 1) : -1);
+                if (zr >= 0)
+                    for (int i = pt; i < 8 * 25; i += 128) sa[(i / 25) * TZ2_PS + zr * TZ2_P + (i % 25) + 1] = bgq;
+            }
+            prev_y0[s] = y0;
+            named_sync_n(1, 128);                          // every producer thread has left the previous item
+            if (pt == 0) {
+                misc[s] = 0;
+                if (w + gridDim.x < n_work) issue_bits(k + 1, w + gridDim.x);               // prefetch the next item's bit rows
+            }
+            mbar_wait(&bits_full[s], par);
+            named_sync_n(1, 128);
+            // ---- scan: pooled pixels whose 4 x 4 map patch holds a set bit
+            const int r0 = max(2 * y0 - 3, 0), bits_w0 = ((r0 * 50) & ~15) >> 2;
+            const uint32_t *smap = sb - bits_w0, *lmap = sb + TZ2_BITW - bits_w0;
+            constexpr int groups = TZ2_H / 8;
+            for (int g = pt; g < (TZ2_R + 2) * groups; g += 128) {
+                const int r = g / groups, gx = g % groups, py = y0 - 1 + r;
+                if (py < 0 || py >= TZ2_H) continue;
+                // 18 map columns 16 gx - 1 .. 16 gx + 16 of the 4 map rows 2 py - 1 .. 2 py + 2
+                uint32_t rs[4], any = 0, colmask = 0x3FFFFu;
+                if (gx == 0) colmask &= ~1u;
+                if (gx == groups - 1) colmask &= ~(1u << 17);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int rr = 2 * py - 1 + i;
+                    rs[i] = 0;
+                    if (rr >= 0 && rr < POL_W) {
+                        int b = rr * POL_W + 16 * gx - 1;
+                        const int sh = b < 0 ? 1 : 0;
+                        b = max(b, 0);
+                        const int wd = b >> 5;
+                        rs[i] = ((__funnelshift_r(smap[wd], smap[wd + 1], b & 31) | __funnelshift_r(lmap[wd], lmap[wd + 1], b & 31)) << sh) & colmask;
+                    }
+                    any |= rs[i];
+                }
+                if (!any) continue;
+                const uint32_t orr = rs[0] | rs[1] | rs[2] | rs[3];
+#pragma unroll
+                for (int kk = 0; kk < 8; kk++)
+                    if ((orr >> (2 * kk)) & 0xFu) wl[atomicAdd(&misc[s], 1)] = (unsigned short)(r * TZ2_H + gx * 8 + kk);
+            }
+            named_sync_n(1, 128);
+            // ---- exact conv1 + pool for the dirty pixels; zero rows outside the image (conv2's padding)
+            {
+                const int n_new = misc[s];
+                for (int i = pt; i < n_new; i += 128) {
+                    const int e = wl[i], r = e / TZ2_H, px = e % TZ2_H, py = y0 - 1 + r;
+                    float v[8];
+                    conv1_pool_pixel(conv1_patch(smap, py, px), conv1_patch(lmap, py, px), a.c1_lut, sbias, v);
+                    sa[(px & 7) * TZ2_PS + r * TZ2_P + (px >> 3) + 1] = pack_bf8(v);
+                }
+                const int zr = y0 == 0 ? 0 : (y0 + TZ2_R >= TZ2_H ? TZ2_H - (y0 - 1) : -1);
+                if (zr >= 0)
+                    for (int i = pt; i < 8 * 25; i += 128) sa[(i / 25) * TZ2_PS + zr * TZ2_P + (i % 25) + 1] = zq;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_a[s]);
+        }
+    } else if (warp >= 4 * TZ2_NST + 4) {
+        // ------------------------------------------------------------ MMA warps: one tile each, converged, elected lane issues
+        mbar_wait(wbar, 0);
+        constexpr uint32_t IDESC = instr_desc(TZ2_N);
+        const uint32_t sw16 = smem_u32(sw) >> 4;
+        const int t = warp - (4 * TZ2_NST + 4);
+        const bool leader = elect_one();
+        int k = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
+            const int s = k & 1;
+            const uint32_t par = (uint32_t)((k >> 1) & 1);
+            mbar_wait(&full_a[s], par);
+            if (k >= 2) mbar_wait(&tmem_empty[s], par ^ 1u);
+            tc_fence_after();
+            const uint32_t sa16 = smem_u32(smem + Tz2Smem::off_a + s * TZ2_ABYTES) >> 4;
+            const uint32_t d = tmem_base + (uint32_t)((s * TZ2_T + t) * TZ2_N);
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+#pragma unroll
+                for (int ks = 0; ks < 5; ks++) {
+                    const int q0 = ks == 0 || ks == 4 ? 0 : 2 * ks - 1, o0 = ks == 4 ? 2 : 1;
+                    const uint32_t lbo = (ks == 0 || ks == 4) ? 7u * TZ2_PS - 1u : (uint32_t)TZ2_PS;
+                    const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ2_PS + u * TZ2_P + 128 * t + o0), lbo, 8);
+                    const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 5 + ks) * 2 * TZ2_N), TZ2_N, 8);
+                    if (leader) tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
+                }
+            if (leader) {
+                tc_commit(&acc_full[s * TZ2_T + t]);
+                tc_commit(&a_empty[s]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ------------------------------------------------------------ draining groups: bias + ReLU + 2 x 2 max-pool
+        const int grp = warp >> 2, gt = tid & 127, gw = warp & 3, s = grp;
+        uint4 *stg = reinterpret_cast<uint4 *>(smem + Tz2Smem::off_stg) + grp * TZ2_STG * 4;
+        float b2[8];
+#pragma unroll
+        for (int co = 0; co < 8; co++) b2[co] = sbias[8 + co];
+        int k = grp;
+        for (int w = blockIdx.x + grp * gridDim.x; w < n_work; w += TZ2_NST * gridDim.x, k += TZ2_NST) {
+            const int item = w / TZ2_STRIPS, y0 = (w % TZ2_STRIPS) * TZ2_R;
+            const uint32_t par = (uint32_t)((k >> 1) & 1);
+            const int rows_valid = min(TZ2_R, TZ2_H - y0);
+            for (int t = 0; t < TZ2_T; t++) {
+                mbar_wait(&acc_full[s * TZ2_T + t], par);
+                tc_fence_after();
+                const int m = 128 * t + gt, yl = m / TZ2_P, xb = m - yl * TZ2_P;
+                const bool valid = yl < rows_valid && xb < 25;
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {            // 32 columns = pixels 4 hh .. 4 hh + 3 of the block, 8 channels each
+                    uint32_t r[32];
+                    tc_ld32(tmem_base + ((uint32_t)(gw * 32) << 16) + (uint32_t)((s * TZ2_T + t) * TZ2_N + hh * 32), r);
+                    tc_wait_ld();
+                    if (!valid) continue;
+#pragma unroll
+                    for (int j = 0; j < 2; j++) {           // pooling pair (x even, x odd): relu(max(.) + bias), then bf16
+                        float o[8];
+#pragma unroll
+                        for (int co = 0; co < 8; co++)
+                            o[co] = fmaxf(fmaxf(__uint_as_float(r[(2 * j) * 8 + co]), __uint_as_float(r[(2 * j + 1) * 8 + co])) + b2[co], 0.f);
+                        stg[m * 4 + hh * 2 + j] = pack_bf8(o);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[s]);
+            named_sync_n(2 + grp, 128);
+            // ---- pooling along y and the NHWC store of the strip's rows_valid / 2 output rows
+            __nv_bfloat16 *dst = a.out + (size_t)item * (100 * 100 * 8) + (size_t)(y0 / 2) * 100 * 8;
+            for (int idx = gt; idx < (rows_valid / 2) * 100; idx += 128) {
+                const int pr = idx / 100, X = idx % 100, xb = X >> 2, j = X & 3;
+                const uint4 q0 = stg[((2 * pr) * TZ2_P + xb) * 4 + j], q1 = stg[((2 * pr + 1) * TZ2_P + xb) * 4 + j];
+                uint4 o;
+                const uint32_t *p0 = &q0.x, *p1 = &q1.x;
+                uint32_t *po = &o.x;
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    __nv_bfloat162 mm = __hmax2(*reinterpret_cast<const __nv_bfloat162 *>(p0 + c), *reinterpret_cast<const __nv_bfloat162 *>(p1 + c));
+                    po[c] = *reinterpret_cast<uint32_t *>(&mm);
+                }
+                *reinterpret_cast<uint4 *>(dst + (size_t)idx * 8) = o;
+            }
+            named_sync_n(2 + grp, 128);                    // the stage may be overwritten by the group's next item
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+}
+
+int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
+    static thread_local int n_sm = 0;
+    if (!n_sm) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tz_trunk12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tz2Smem::total));
+        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
+    }
+    if (n_items == 0) return OFB_OK;
+    Tz2Args a = {};
+    a.maps = maps; a.wt = p->w.c2_tz; a.bias = p->w.cb[0]; a.c1_lut = p->w.c1_lut; a.c1_b = p->w.c1_b; a.out = out;
+    a.dbg = g_tz_dbg;
+    const int n_work = n_items * TZ2_STRIPS;
+    k_tz_trunk12<<<n_work < n_sm ? n_work : n_sm, TZ2_NTP, Tz2Smem::total, st>>>(a, n_work);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

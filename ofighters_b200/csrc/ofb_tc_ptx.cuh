@@ -75,3 +75,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t *r) {
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+
+// one lane of a converged warp (elect.sync): lets a warp keep its descriptor arithmetic warp-uniform (uniform datapath)
+// and predicate only the single-thread tcgen05 instructions
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
