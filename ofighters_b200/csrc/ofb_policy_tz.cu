@@ -661,7 +661,9 @@ int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out,
 #define TZ2_N 64
 #define TZ2_NST 2                     // stages = draining groups
 #define TZ2_STRIPS ((TZ2_H + TZ2_R - 1) / TZ2_R)
-#define TZ2_NTP (32 * (4 * TZ2_NST + 4 + TZ2_T))      // 8 draining + 4 producer + 3 MMA warps
+#define TZ2_NPW 8                     // producer warps
+#define TZ2_NPT (32 * TZ2_NPW)
+#define TZ2_NTP (32 * (4 * TZ2_NST + TZ2_NPW + TZ2_T))      // 8 draining + 8 producer + 3 MMA warps
 #define TZ2_ABYTES (8 * TZ2_PS * 16)
 #define TZ2_WBYTES (3 * 5 * 2 * TZ2_N * 16)
 #define TZ2_BITW 456                  // words of one staged bit map: (2 R + 6) rows x 50 B + alignment slack
@@ -708,7 +710,7 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
         mbar_init(wbar, 1);
         for (int s = 0; s < TZ2_NST; s++) {
             mbar_init(&bits_full[s], 1);
-            mbar_init(&full_a[s], 4);                      // the 4 producer warps
+            mbar_init(&full_a[s], TZ2_NPW);                // the producer warps
             mbar_init(&a_empty[s], TZ2_T);                 // the MMA warps (tcgen05.commit)
             mbar_init(&tmem_empty[s], 4);                  // the 4 warps of the draining group
             for (int t = 0; t < TZ2_T; t++) mbar_init(&acc_full[s * TZ2_T + t], 1);
@@ -725,15 +727,15 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp >= 4 * TZ2_NST && warp < 4 * TZ2_NST + 4) {
-        // ------------------------------------------------------------ producer group (128 threads)
+    if (warp >= 4 * TZ2_NST && warp < 4 * TZ2_NST + TZ2_NPW) {
+        // ------------------------------------------------------------ producer group
         const int pt = tid - 128 * TZ2_NST;
         float bg[8];
 #pragma unroll
         for (int co = 0; co < 8; co++) bg[co] = fmaxf(sbias[co], 0.f);
         const uint4 bgq = pack_bf8(bg), zq = make_uint4(0, 0, 0, 0);
         // both stages start clean: background everywhere, zeros in the x halo slots (slot 0 of planes 0 and 7)
-        for (int i = pt; i < TZ2_NST * 8 * TZ2_PS; i += 128) {
+        for (int i = pt; i < TZ2_NST * 8 * TZ2_PS; i += TZ2_NPT) {
             const int q = (i / TZ2_PS) % 8, t = (i % TZ2_PS) % TZ2_P;
             reinterpret_cast<uint4 *>(smem + Tz2Smem::off_a)[i] = ((q == 0 || q == 7) && t == 0) ? zq : bgq;
         }
@@ -752,7 +754,7 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
             bulk_g2s(sw, a.wt, TZ2_WBYTES, wbar);
             if (blockIdx.x < n_work) issue_bits(0, blockIdx.x);
         }
-        named_sync_n(1, 128);
+        named_sync_n(1, TZ2_NPT);
         int k = 0, prev_y0[TZ2_NST] = {-1000, -1000};
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
             const int s = k & 1, y0 = (w % TZ2_STRIPS) * TZ2_R;
@@ -764,27 +766,27 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
                 // ---- the MMAs of the previous item in this stage are done: put the background back
                 mbar_wait(&a_empty[s], par ^ 1u);
                 const int n_old = misc[s];
-                for (int i = pt; i < n_old; i += 128) {
+                for (int i = pt; i < n_old; i += TZ2_NPT) {
                     const int e = wl[i], r = e / TZ2_H, px = e % TZ2_H;
                     sa[(px & 7) * TZ2_PS + r * TZ2_P + (px >> 3) + 1] = bgq;
                 }
                 const int zr = prev_y0[s] == 0 ? 0 : (prev_y0[s] + TZ2_R >= TZ2_H ? TZ2_H - (prev_y0[s] - 1) : -1);
                 if (zr >= 0)
-                    for (int i = pt; i < 8 * 25; i += 128) sa[(i / 25) * TZ2_PS + zr * TZ2_P + (i % 25) + 1] = bgq;
+                    for (int i = pt; i < 8 * 25; i += TZ2_NPT) sa[(i / 25) * TZ2_PS + zr * TZ2_P + (i % 25) + 1] = bgq;
             }
             prev_y0[s] = y0;
-            named_sync_n(1, 128);                          // every producer thread has left the previous item
+            named_sync_n(1, TZ2_NPT);                          // every producer thread has left the previous item
             if (pt == 0) {
                 misc[s] = 0;
                 if (w + gridDim.x < n_work) issue_bits(k + 1, w + gridDim.x);               // prefetch the next item's bit rows
             }
             mbar_wait(&bits_full[s], par);
-            named_sync_n(1, 128);
+            named_sync_n(1, TZ2_NPT);
             // ---- scan: pooled pixels whose 4 x 4 map patch holds a set bit
             const int r0 = max(2 * y0 - 3, 0), bits_w0 = ((r0 * 50) & ~15) >> 2;
             const uint32_t *smap = sb - bits_w0, *lmap = sb + TZ2_BITW - bits_w0;
             constexpr int groups = TZ2_H / 8;
-            for (int g = pt; g < (TZ2_R + 2) * groups; g += 128) {
+            for (int g = pt; g < (TZ2_R + 2) * groups; g += TZ2_NPT) {
                 const int r = g / groups, gx = g % groups, py = y0 - 1 + r;
                 if (py < 0 || py >= TZ2_H) continue;
                 // 18 map columns 16 gx - 1 .. 16 gx + 16 of the 4 map rows 2 py - 1 .. 2 py + 2
@@ -810,11 +812,11 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
                 for (int kk = 0; kk < 8; kk++)
                     if ((orr >> (2 * kk)) & 0xFu) wl[atomicAdd(&misc[s], 1)] = (unsigned short)(r * TZ2_H + gx * 8 + kk);
             }
-            named_sync_n(1, 128);
+            named_sync_n(1, TZ2_NPT);
             // ---- exact conv1 + pool for the dirty pixels; zero rows outside the image (conv2's padding)
             {
                 const int n_new = misc[s];
-                for (int i = pt; i < n_new; i += 128) {
+                for (int i = pt; i < n_new; i += TZ2_NPT) {
                     const int e = wl[i], r = e / TZ2_H, px = e % TZ2_H, py = y0 - 1 + r;
                     float v[8];
                     conv1_pool_pixel(conv1_patch(smap, py, px), conv1_patch(lmap, py, px), a.c1_lut, sbias, v);
@@ -822,18 +824,18 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
                 }
                 const int zr = y0 == 0 ? 0 : (y0 + TZ2_R >= TZ2_H ? TZ2_H - (y0 - 1) : -1);
                 if (zr >= 0)
-                    for (int i = pt; i < 8 * 25; i += 128) sa[(i / 25) * TZ2_PS + zr * TZ2_P + (i % 25) + 1] = zq;
+                    for (int i = pt; i < 8 * 25; i += TZ2_NPT) sa[(i / 25) * TZ2_PS + zr * TZ2_P + (i % 25) + 1] = zq;
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
             __syncwarp();
             if (lane == 0) mbar_arrive(&full_a[s]);
         }
-    } else if (warp >= 4 * TZ2_NST + 4) {
+    } else if (warp >= 4 * TZ2_NST + TZ2_NPW) {
         // ------------------------------------------------------------ MMA warps: one tile each, converged, elected lane issues
         mbar_wait(wbar, 0);
         constexpr uint32_t IDESC = instr_desc(TZ2_N);
         const uint32_t sw16 = smem_u32(sw) >> 4;
-        const int t = warp - (4 * TZ2_NST + 4);
+        const int t = warp - (4 * TZ2_NST + TZ2_NPW);
         const bool leader = elect_one();
         int k = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {

@@ -46,6 +46,10 @@ def main():
         pol.forward_argmax(maps, vec)
         pol.forward_argmax(maps, vec)
         torch.cuda.synchronize()
+        if os.environ.get("OFB_TZ_DEBUG") == "trunk":
+            dbg.zero_()
+            pol.forward(maps[:8192], vec[:8192], want_act=False, want_argmax=False)     # trunk + heads only
+            torch.cuda.synchronize()
         st = dbg.cpu().tolist()
         print("tz_up4 stamps (cycles since start):", [x - st[0] if x else None for x in st[:13]])
         for k in range(14):
