@@ -487,8 +487,12 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
 #pragma unroll
                 for (int co = 0; co < 4; co++) c[co] += v0 * wp[co] + v1 * wp[4 + co];
             }
-        *reinterpret_cast<uint2 *>(dst + (plane_layout ? pol_plane100_off(y, x) : p * 8)) =
-            make_uint2(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)));
+        // full 16-byte pixels (channels 4..7 = 0) and, in the plane layout, the row's halo slot too: partial 32-byte
+        // sectors would turn into read-modify-writes in DRAM
+        __nv_bfloat16 *q = dst + (plane_layout ? pol_plane100_off(y, x) : p * 8);
+        *reinterpret_cast<uint4 *>(q) =
+            make_uint4(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)), 0u, 0u);
+        if (plane_layout && x < 4) *reinterpret_cast<uint4 *>(q - 8) = make_uint4(0u, 0u, 0u, 0u);
     }
 }
 

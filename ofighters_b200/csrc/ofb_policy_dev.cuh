@@ -9,6 +9,15 @@ __device__ __forceinline__ uint32_t pack_bf2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&t);
 }
+// max(x, 0) and round-to-nearest bf16 of two floats in one instruction (a -> low half, b -> high half)
+__device__ __forceinline__ uint32_t pack_relu_bf2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ uint4 pack_relu_bf8(const float *v) {
+    return make_uint4(pack_relu_bf2(v[0], v[1]), pack_relu_bf2(v[2], v[3]), pack_relu_bf2(v[4], v[5]), pack_relu_bf2(v[6], v[7]));
+}
 __device__ __forceinline__ uint4 pack_bf8(const float *v) {
     return make_uint4(pack_bf2(v[0], v[1]), pack_bf2(v[2], v[3]), pack_bf2(v[4], v[5]), pack_bf2(v[6], v[7]));
 }

@@ -424,9 +424,13 @@ k_tz_up4(const Tz4Args a, const int n_work) {
 #define TZ3_T 2
 #define TZ3_PS 312                    // (R + 2) * P + 2 + tile overrun (256 - 234), rounded to 8
 #define TZ3_N 128
-#define TZ3_NT 160
+#define TZ3_NST 2                     // stages = draining groups (2 x 2 tiles x 128 columns = all of TMEM)
+#define TZ3_NTP (32 * (4 * TZ3_NST + 1 + TZ3_T + TZ3_NST))     // draining groups, producer, MMA warps, one ring warp per stage
 #define TZ3_STRIPS ((TZ3_H + TZ3_R - 1) / TZ3_R)
 #define TZ3_WBYTES (3 * 3 * 2 * TZ3_N * 16)
+#define TZ3_ABYTES (4 * TZ3_PS * 16)
+#define TZ3_RING (4 * TZ3_R + 200)    // ring pixels of a strip: 2R left, 2R right, 200 top / bottom; 8 floats each
+#define TZ3_SCR ((2 * (TZ3_R + 2) * 3 + 102 * 3) * 8)
 
 struct Tz3Args {
     const __nv_bfloat16 *in;          // plane layout [item][4][100][26][8] (channels 4..7 zero)
@@ -434,15 +438,21 @@ struct Tz3Args {
     const float *bias;                // [32] = bias[co] per phase
     const float *ring_w;              // un-phased fp32 weights [9][4][8]
     __nv_bfloat16 *out;               // plane layout [item][8][200][26][8]
+    long long *dbg;                   // optional per-work clock stamps of CTA 5
 };
 
 struct Tz3Smem {
     static constexpr unsigned off_w = 0;
     static constexpr unsigned off_a = TZ3_WBYTES;
-    static constexpr unsigned off_ring = off_a + 4 * TZ3_PS * 16;              // 8 floats per ring pixel: 2R left, 2R right, 200 top/bottom
-    static constexpr unsigned off_aux = off_ring + (4 * TZ3_R + 200) * 32;     // 288 ring weights
+    static constexpr unsigned off_ring = off_a + TZ3_NST * TZ3_ABYTES;             // per group
+    static constexpr unsigned off_corr = off_ring + TZ3_NST * TZ3_RING * 32;        // per group
+    static constexpr unsigned off_scr = off_corr + TZ3_NST * TZ3_RING * 32;         // per group: column / row dots
+    static constexpr unsigned off_aux = off_scr + TZ3_NST * TZ3_SCR * 4;            // 288 ring weights
     static constexpr unsigned off_bar = off_aux + 288 * 4;
-    static constexpr unsigned total = off_bar + (TZ3_T + 1) * 8 + 16;
+    // barriers: wbar, full_a[NST], a_empty[NST], halo[NST], halo2[NST], tmem_empty[NST], acc_full[NST][T]
+    // ... ring_full[NST], ring_free[NST]
+    static constexpr unsigned n_bar = 1 + 7 * TZ3_NST + TZ3_NST * TZ3_T;
+    static constexpr unsigned total = off_bar + n_bar * 8 + 16;
 };
 
 struct PlaneStrip3 {
@@ -451,160 +461,304 @@ struct PlaneStrip3 {
     __device__ __forceinline__ uint4 operator()(int y, int x) const { return pl[(x & 3) * TZ3_PS + (y - y0 + 1) * TZ3_P + (x >> 2) + 1]; }
 };
 
-__global__ void __launch_bounds__(TZ3_NT)
-k_tz_up3(const Tz3Args a) {
+// Persistent and warp-specialised like k_tz_up4: warp 8 = bulk-copy producer, warps 9-10 = one MMA warp per tile (warp 9
+// also fills the halo slots), warps 0-7 = two draining groups (group g owns stage g) that add bias, apply ReLU and store
+// bf16 pixels in k_tz_up4's plane layout; the border ring is corrected with the separable form (column / row dots).
+__global__ void __launch_bounds__(TZ3_NTP, 1)
+k_tz_up3(const Tz3Args a, const int n_work) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int item = blockIdx.y, y0 = blockIdx.x * TZ3_R;
-    const int rows_valid = min(TZ3_R, TZ3_H - y0);
     uint4 *sw = reinterpret_cast<uint4 *>(smem + Tz3Smem::off_w);
-    uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz3Smem::off_a);
-    float *ring = reinterpret_cast<float *>(smem + Tz3Smem::off_ring);
     float *aux = reinterpret_cast<float *>(smem + Tz3Smem::off_aux);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Tz3Smem::off_bar);
-    uint64_t *lbar = &bars[TZ3_T];
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Tz3Smem::off_bar + (TZ3_T + 1) * 8);
+    uint64_t *wbar = bars, *full_a = bars + 1, *a_empty = full_a + TZ3_NST, *halo = a_empty + TZ3_NST, *halo2 = halo + TZ3_NST,
+             *tmem_empty = halo2 + TZ3_NST, *acc_full = tmem_empty + TZ3_NST, *ring_full = acc_full + TZ3_NST * TZ3_T,
+             *ring_free = ring_full + TZ3_NST;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Tz3Smem::off_bar + Tz3Smem::n_bar * 8);
 
-    if (tid == 128) {
-        for (int t = 0; t <= TZ3_T; t++) mbar_init(&bars[t], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const int ylo = max(y0 - 1, 0), yhi = min(y0 + TZ3_R, TZ3_H - 1);
-        const uint32_t run = (uint32_t)(yhi - ylo + 1) * TZ3_P * 16;
-        const bool top = y0 == 0, bot = y0 + TZ3_R > TZ3_H - 1;
-        mbar_expect_tx(lbar, 4u * (run + (top ? TZ3_P * 16 : 0) + (bot ? TZ3_P * 16 : 0)) + TZ3_WBYTES + 288 * 4);
-        bulk_g2s(sw, a.wt, TZ3_WBYTES, lbar);
-        bulk_g2s(aux, a.ring_w, 288 * 4, lbar);
-        const uint8_t *src = reinterpret_cast<const uint8_t *>(a.in) + (size_t)item * (4 * TZ3_H * TZ3_P * 16);
-        for (int q = 0; q < 4; q++) {
-            const uint8_t *pq = src + (size_t)q * TZ3_H * TZ3_P * 16;
-            uint4 *dq = sa + q * TZ3_PS;
-            bulk_g2s(dq + (ylo - (y0 - 1)) * TZ3_P, pq + (size_t)ylo * TZ3_P * 16, run, lbar);
-            if (top) bulk_g2s(dq, pq, TZ3_P * 16, lbar);
-            if (bot) bulk_g2s(dq + (TZ3_H - (y0 - 1)) * TZ3_P, pq + (size_t)(TZ3_H - 1) * TZ3_P * 16, TZ3_P * 16, lbar);
+    if (tid == 0) {
+        mbar_init(wbar, 1);
+        for (int s = 0; s < TZ3_NST; s++) {
+            mbar_init(&full_a[s], 1);
+            mbar_init(&a_empty[s], 1 + TZ3_T);             // the ring warp (its corrections read the strip) + the MMA warps
+            mbar_init(&ring_full[s], 4);                   // the draining warps have parked their ring pixels
+            mbar_init(&ring_free[s], 1);                   // the ring warp has consumed them
+            mbar_init(&halo[s], 1);
+            mbar_init(&halo2[s], 1);
+            mbar_init(&tmem_empty[s], 4);
+            for (int t = 0; t < TZ3_T; t++) mbar_init(&acc_full[s * TZ3_T + t], 1);
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    float biasr[32];
-#pragma unroll
-    for (int i = 0; i < 32; i++) biasr[i] = a.bias[i];
-    __syncthreads();
-    mbar_wait(lbar, 0);
-    for (int i = tid; i < 2 * (TZ3_R + 2); i += TZ3_NT) {
-        const int r = i >> 1;
-        if (i & 1) sa[0 * TZ3_PS + (r + 1) * TZ3_P] = sa[3 * TZ3_PS + r * TZ3_P + 25];     // x = 100 := x = 99
-        else sa[3 * TZ3_PS + r * TZ3_P] = sa[0 * TZ3_PS + r * TZ3_P + 1];                 // x = -1 := x = 0
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    __nv_bfloat16 *dst = a.out + (size_t)item * POL_UP3_ITEM;
 
-    if (warp == 4) {
+    if (warp == 4 * TZ3_NST) {
+        // ------------------------------------------------------------ producer
         if (lane == 0) {
-            constexpr uint32_t IDESC = instr_desc(TZ3_N);
-            const uint32_t sa16 = smem_u32(sa) >> 4, sw16 = smem_u32(sw) >> 4;
-            for (int t = 0; t < TZ3_T; t++) {
-                const uint32_t d = tmem_base + (uint32_t)(t * TZ3_N);
-#pragma unroll
-                for (int u = 0; u < 3; u++)
-#pragma unroll
-                    for (int ks = 0; ks < 3; ks++) {
-                        const int q0 = ks == 1 ? 1 : 0, o0 = ks == 2 ? 2 : 1;
-                        const uint32_t lbo = ks == 1 ? (uint32_t)TZ3_PS : 3u * TZ3_PS - 1u;
-                        const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ3_PS + u * TZ3_P + 128 * t + o0), lbo, 8);
-                        const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 3 + ks) * 2 * TZ3_N), TZ3_N, 8);
-                        tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
-                    }
-                tc_commit(&bars[t]);
-            }
-        }
-        __syncwarp();
-    } else {
-        for (int t = 0; t < TZ3_T; t++) {
-            mbar_wait(&bars[t], 0);
-            tc_fence_after();
-            const int m = 128 * t + tid, yl = m / TZ3_P, xb = m - yl * TZ3_P;
-            const bool valid = yl < rows_valid && xb < 25;
-            const int i = y0 + yl;
-#pragma unroll
-            for (int xo = 0; xo < 4; xo++) {              // 32 columns = the 4 phases x 8 channels of low-res pixel 4 xb + xo
-                uint32_t r[32];
-                tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * TZ3_N + xo * 32), r);
-                tc_wait_ld();
-                if (!valid) continue;
-#pragma unroll
-                for (int ph = 0; ph < 4; ph++) {
-                    const int Y = 2 * i + (ph >> 1), X = 8 * xb + 2 * xo + (ph & 1);
-                    float o[8];
-#pragma unroll
-                    for (int co = 0; co < 8; co++) o[co] = __uint_as_float(r[ph * 8 + co]) + biasr[ph * 8 + co];
-                    if (Y == 0 || Y == 2 * TZ3_H - 1 || X == 0 || X == 2 * TZ3_H - 1) {          // ring: corrected after the tile loop
-                        float *rb = ring + 8 * (X == 0 ? Y - 2 * y0 : (X == 2 * TZ3_H - 1 ? 2 * TZ3_R + Y - 2 * y0 : 4 * TZ3_R + X));
-#pragma unroll
-                        for (int co = 0; co < 8; co++) rb[co] = o[co];
-                        continue;
-                    }
-#pragma unroll
-                    for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
-                    *reinterpret_cast<uint4 *>(dst + pol_plane200_off(Y, X)) = pack_bf8(o);
+            mbar_expect_tx(wbar, TZ3_WBYTES + 288 * 4);
+            bulk_g2s(sw, a.wt, TZ3_WBYTES, wbar);
+            bulk_g2s(aux, a.ring_w, 288 * 4, wbar);
+            int k = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
+                const int s = k % TZ3_NST, item = w / TZ3_STRIPS, y0 = (w % TZ3_STRIPS) * TZ3_R;
+                if (k >= TZ3_NST) mbar_wait(&a_empty[s], (uint32_t)((k / TZ3_NST - 1) & 1));
+                uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz3Smem::off_a + s * TZ3_ABYTES);
+                const int ylo = max(y0 - 1, 0), yhi = min(y0 + TZ3_R, TZ3_H - 1);
+                const uint32_t run = (uint32_t)(yhi - ylo + 1) * TZ3_P * 16;
+                const bool top = y0 == 0, bot = y0 + TZ3_R > TZ3_H - 1;
+                mbar_expect_tx(&full_a[s], 4u * (run + (top ? TZ3_P * 16 : 0) + (bot ? TZ3_P * 16 : 0)));
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(a.in) + (size_t)item * (4 * TZ3_H * TZ3_P * 16);
+                for (int q = 0; q < 4; q++) {
+                    const uint8_t *pq = src + (size_t)q * TZ3_H * TZ3_P * 16;
+                    uint4 *dq = sa + q * TZ3_PS;
+                    bulk_g2s(dq + (ylo - (y0 - 1)) * TZ3_P, pq + (size_t)ylo * TZ3_P * 16, run, &full_a[s]);
+                    if (top) bulk_g2s(dq, pq, TZ3_P * 16, &full_a[s]);
+                    if (bot) bulk_g2s(dq + (TZ3_H - (y0 - 1)) * TZ3_P, pq + (size_t)(TZ3_H - 1) * TZ3_P * 16, TZ3_P * 16, &full_a[s]);
                 }
             }
         }
-    }
-    tc_fence_before();
-    __syncthreads();
-
-    {   // border ring (see k_tz_up4): 4 lanes per ring pixel, 8 channels each
+        __syncwarp();
+    } else if (warp > 4 * TZ3_NST && warp <= 4 * TZ3_NST + TZ3_T) {
+        // ------------------------------------------------------------ halo slots + MMA issue (one converged warp per tile)
+        mbar_wait(wbar, 0);
+        constexpr uint32_t IDESC = instr_desc(TZ3_N);
+        const uint32_t sw16 = smem_u32(sw) >> 4;
+        const int t = warp - 4 * TZ3_NST - 1;
+        const bool leader = elect_one();
+        int k = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
+            const int s = k % TZ3_NST;
+            const uint32_t par = (uint32_t)((k / TZ3_NST) & 1);
+            uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz3Smem::off_a + s * TZ3_ABYTES);
+            if (t == 0) {
+                mbar_wait(&full_a[s], par);
+                for (int i = lane; i < 2 * (TZ3_R + 2); i += 32) {
+                    const int r = i >> 1;
+                    if (i & 1) sa[0 * TZ3_PS + (r + 1) * TZ3_P] = sa[3 * TZ3_PS + r * TZ3_P + 25];     // x = 100 := x = 99
+                    else sa[3 * TZ3_PS + r * TZ3_P] = sa[0 * TZ3_PS + r * TZ3_P + 1];                 // x = -1 := x = 0
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) { mbar_arrive(&halo[s]); mbar_arrive(&halo2[s]); }
+            } else {
+                mbar_wait(&halo2[s], par);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            }
+            if (k >= TZ3_NST) { mbar_wait(&tmem_empty[s], par ^ 1u); tc_fence_after(); }
+            const uint32_t sa16 = smem_u32(sa) >> 4;
+            const uint32_t d = tmem_base + (uint32_t)((s * TZ3_T + t) * TZ3_N);
+#pragma unroll
+            for (int u = 0; u < 3; u++)
+#pragma unroll
+                for (int ks = 0; ks < 3; ks++) {
+                    const int q0 = ks == 1 ? 1 : 0, o0 = ks == 2 ? 2 : 1;
+                    const uint32_t lbo = ks == 1 ? (uint32_t)TZ3_PS : 3u * TZ3_PS - 1u;
+                    const uint64_t ad = smem_desc(sa16 + (uint32_t)(q0 * TZ3_PS + u * TZ3_P + 128 * t + o0), lbo, 8);
+                    const uint64_t bd = smem_desc(sw16 + (uint32_t)((u * 3 + ks) * 2 * TZ3_N), TZ3_N, 8);
+                    if (leader) tc_mma(d, ad, bd, IDESC, (u | ks) ? 1u : 0u);
+                }
+            if (leader) {
+                tc_commit(&acc_full[s * TZ3_T + t]);
+                tc_commit(&a_empty[s]);
+                if (t == 0) TZ_STAMPK(k, 6);
+            }
+            __syncwarp();
+        }
+    } else if (warp > 4 * TZ3_NST + TZ3_T) {
+        // ------------------------------------------------------------ ring warps: warp (4 NST + T + 1 + s) owns the border ring
+        // of stage s.  Part 1 (while the MMAs run): the out-of-range taps of every ring pixel in the separable form (see
+        // k_tz_up4); part 2 (once the draining group has parked the folded values): folded - taps, ReLU, store again.
+        mbar_wait(wbar, 0);                               // ring weights
+        const int s = warp - (4 * TZ3_NST + TZ3_T + 1);
+        const uint4 *sa = reinterpret_cast<const uint4 *>(smem + Tz3Smem::off_a + s * TZ3_ABYTES);
+        const float *ring = reinterpret_cast<const float *>(smem + Tz3Smem::off_ring) + s * TZ3_RING * 8;
+        float *corr = reinterpret_cast<float *>(smem + Tz3Smem::off_corr) + s * TZ3_RING * 8;
+        float *cdots = reinterpret_cast<float *>(smem + Tz3Smem::off_scr) + s * TZ3_SCR, *rdots = cdots + 2 * (TZ3_R + 2) * 3 * 8;
         constexpr int Wo = 2 * TZ3_H;
-        const bool first = blockIdx.x == 0, last = blockIdx.x == gridDim.x - 1;
-        const int nslots = 4 * TZ3_R + ((first || last) ? Wo : 0);
-        const PlaneStrip3 Ls{sa, y0};
-        for (int base = 0; base < nslots * 4; base += TZ3_NT) {
-            const int itm = base + tid, slot = itm >> 2, j = itm & 3;
-            int Y = 0, X = 0;
-            bool valid = slot < nslots;
-            if (slot < 2 * TZ3_R) { Y = 2 * y0 + slot; X = 0; valid = valid && slot < 2 * rows_valid; }
-            else if (slot < 4 * TZ3_R) { Y = 2 * y0 + slot - 2 * TZ3_R; X = Wo - 1; valid = valid && slot - 2 * TZ3_R < 2 * rows_valid; }
-            else {
-                X = slot - 4 * TZ3_R;
-                valid = valid && X != 0 && X != Wo - 1;
-                Y = first ? 0 : Wo - 1;
-            }
-            float acc[8];
+        int k = s;
+        for (int w = blockIdx.x + s * gridDim.x; w < n_work; w += TZ3_NST * gridDim.x, k += TZ3_NST) {
+            const int item = w / TZ3_STRIPS, strip = w % TZ3_STRIPS, y0 = strip * TZ3_R;
+            const uint32_t par = (uint32_t)((k / TZ3_NST) & 1);
+            const int rows_valid = min(TZ3_R, TZ3_H - y0);
+            const bool first = strip == 0, last = strip == TZ3_STRIPS - 1;
+            const int nslots = 4 * TZ3_R + ((first || last) ? Wo : 0);
+            __nv_bfloat16 *dst = a.out + (size_t)item * POL_UP3_ITEM;
+            mbar_wait(&halo[s], par);
+            const int dye = first ? 0 : 2, Yedge = first ? 0 : Wo - 1;
+            int rlo = 0, rhi = 0; float rwl = 0.f, rwh = 0.f;
+            bil_tap_ext(Yedge + dye - 1, rlo, rhi, rwl, rwh);
+            for (int q = lane; q < 2 * (TZ3_R + 2) * 3; q += 32) {
+                const int side = q / ((TZ3_R + 2) * 3), rem = q % ((TZ3_R + 2) * 3), r = rem / 3, dy = rem % 3;
+                float x[8], d[8];
+                unpack_bf8(sa[(side ? 3 : 0) * TZ3_PS + r * TZ3_P + (side ? 25 : 1)], x);
+                const float *wp = aux + (dy * 3 + (side ? 2 : 0)) * 32;
 #pragma unroll
-            for (int co = 0; co < 8; co++) acc[co] = 0.f;
-            if (valid && j < 3) {
-                const bool xedge = (X == 0 || X == Wo - 1), yedge = (Y == 0 || Y == Wo - 1);
-                const int dxe = X == 0 ? 0 : 2, dye = Y == 0 ? 0 : 2;
-                if (xedge) up_ring_tap<4, 8>(Ls, Y, X, j, dxe, aux, acc);
-                else up_ring_tap<4, 8>(Ls, Y, X, dye, j, aux, acc);
-                if (xedge && yedge && j == 0)
-                    for (int dx = 0; dx < 3; dx++)
-                        if (dx != dxe) up_ring_tap<4, 8>(Ls, Y, X, dye, dx, aux, acc);
-            }
-            float o[8];
+                for (int co = 0; co < 8; co++) d[co] = 0.f;
 #pragma unroll
-            for (int co = 0; co < 8; co++) {
-                const float t1 = __shfl_down_sync(0xffffffffu, acc[co], 1), t2 = __shfl_down_sync(0xffffffffu, acc[co], 2);
-                o[co] = (acc[co] + t1) + t2;
-            }
-            if (!valid || j != 0) continue;
+                for (int ci = 0; ci < 4; ci++)
 #pragma unroll
-            for (int co = 0; co < 8; co++) o[co] = fmaxf(ring[8 * slot + co] - o[co], 0.f);
-            *reinterpret_cast<uint4 *>(dst + pol_plane200_off(Y, X)) = pack_bf8(o);
+                    for (int co = 0; co < 8; co++) d[co] += x[ci] * wp[ci * 8 + co];
+#pragma unroll
+                for (int co = 0; co < 8; co++) cdots[q * 8 + co] = d[co];
+            }
+            if (first || last) {
+                const PlaneStrip3 Ls{sa, y0};
+                for (int q = lane; q < 102 * 3; q += 32) {
+                    const int x = q / 3 - 1, dx = q % 3;
+                    float lo[8], hi[8], d[8];
+                    unpack_bf8(Ls(rlo, x), lo);
+                    unpack_bf8(Ls(rhi, x), hi);
+                    const float *wp = aux + (dye * 3 + dx) * 32;
+#pragma unroll
+                    for (int co = 0; co < 8; co++) d[co] = 0.f;
+#pragma unroll
+                    for (int ci = 0; ci < 4; ci++) {
+                        const float u = rwl * lo[ci] + rwh * hi[ci];
+#pragma unroll
+                        for (int co = 0; co < 8; co++) d[co] += u * wp[ci * 8 + co];
+                    }
+#pragma unroll
+                    for (int co = 0; co < 8; co++) rdots[q * 8 + co] = d[co];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_empty[s]);      // the strip buffer is no longer read by this warp
+            for (int slot = lane; slot < nslots; slot += 32) {
+                float c[8];
+#pragma unroll
+                for (int co = 0; co < 8; co++) c[co] = 0.f;
+                if (slot < 4 * TZ3_R) {
+                    const int side = slot / (2 * TZ3_R), Yl = slot % (2 * TZ3_R), Y = 2 * y0 + Yl;
+                    const float *ds = cdots + side * (TZ3_R + 2) * 3 * 8;
+#pragma unroll
+                    for (int dy = 0; dy < 3; dy++) {
+                        int lo, hi; float wlo, whi;
+                        bil_tap_ext(Y + dy - 1, lo, hi, wlo, whi);
+                        const float *dl = ds + ((lo - y0 + 1) * 3 + dy) * 8, *dh = ds + ((hi - y0 + 1) * 3 + dy) * 8;
+#pragma unroll
+                        for (int co = 0; co < 8; co++) c[co] += wlo * dl[co] + whi * dh[co];
+                    }
+                    if ((first || last) && Y == Yedge) {        // corner: the two taps of the border row outside its column
+                        const int X = side ? Wo - 1 : 0;
+                        for (int dx = 0; dx < 3; dx++) {
+                            if (dx == (side ? 2 : 0)) continue;
+                            int lo, hi; float wlo, whi;
+                            bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                            const float *dl = rdots + ((lo + 1) * 3 + dx) * 8, *dh = rdots + ((hi + 1) * 3 + dx) * 8;
+#pragma unroll
+                            for (int co = 0; co < 8; co++) c[co] += wlo * dl[co] + whi * dh[co];
+                        }
+                    }
+                } else {
+                    const int X = slot - 4 * TZ3_R;
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++) {
+                        int lo, hi; float wlo, whi;
+                        bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                        const float *dl = rdots + ((lo + 1) * 3 + dx) * 8, *dh = rdots + ((hi + 1) * 3 + dx) * 8;
+#pragma unroll
+                        for (int co = 0; co < 8; co++) c[co] += wlo * dl[co] + whi * dh[co];
+                    }
+                }
+#pragma unroll
+                for (int co = 0; co < 8; co++) corr[slot * 8 + co] = c[co];
+            }
+            __syncwarp();
+            mbar_wait(&ring_full[s], par);                // the draining group has parked (and stored, uncorrected) the ring pixels
+            for (int slot = lane; slot < nslots; slot += 32) {
+                int Y, X;
+                bool valid = true;
+                if (slot < 2 * TZ3_R) { Y = 2 * y0 + slot; X = 0; valid = slot < 2 * rows_valid; }
+                else if (slot < 4 * TZ3_R) { Y = 2 * y0 + slot - 2 * TZ3_R; X = Wo - 1; valid = slot - 2 * TZ3_R < 2 * rows_valid; }
+                else { X = slot - 4 * TZ3_R; valid = X != 0 && X != Wo - 1; Y = first ? 0 : Wo - 1; }
+                if (!valid) continue;
+                float o[8];
+#pragma unroll
+                for (int co = 0; co < 8; co++) o[co] = ring[slot * 8 + co] - corr[slot * 8 + co];
+                *reinterpret_cast<uint4 *>(dst + pol_plane200_off(Y, X)) = pack_relu_bf8(o);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring_free[s]);
+        }
+    } else {
+        // ------------------------------------------------------------ draining groups: bias + ReLU + bf16, straight to HBM in
+        // k_tz_up4's plane layout.  Every pixel is stored; the pixels of the border ring are also parked (pre-activation) for
+        // the stage's ring warp, which stores them again, corrected, after this group's stores (mbarrier release / acquire).
+        const int grp = warp >> 2, gt = tid & 127, gw = warp & 3, s = grp;
+        float *ring = reinterpret_cast<float *>(smem + Tz3Smem::off_ring) + grp * TZ3_RING * 8;
+        float biasr[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) biasr[i] = a.bias[i];
+        constexpr int Wo = 2 * TZ3_H;
+        int k = grp;
+        for (int w = blockIdx.x + grp * gridDim.x; w < n_work; w += TZ3_NST * gridDim.x, k += TZ3_NST) {
+            const int item = w / TZ3_STRIPS, strip = w % TZ3_STRIPS, y0 = strip * TZ3_R;
+            const uint32_t par = (uint32_t)((k / TZ3_NST) & 1);
+            const int rows_valid = min(TZ3_R, TZ3_H - y0);
+            __nv_bfloat16 *dst = a.out + (size_t)item * POL_UP3_ITEM;
+            if (gt == 0) TZ_STAMPK(k, 0);
+            if (k >= TZ3_NST) mbar_wait(&ring_free[s], par ^ 1u);        // the ring scratch of the previous item has been consumed
+            for (int t = 0; t < TZ3_T; t++) {
+                mbar_wait(&acc_full[s * TZ3_T + t], par);
+                tc_fence_after();
+                if (gt == 0) TZ_STAMPK(k, 2 + t);
+                const int m = 128 * t + gt, yl = m / TZ3_P, xb = m - yl * TZ3_P;
+                const bool valid = yl < rows_valid && xb < 25;
+                const int i = y0 + yl;
+                const bool edge = xb == 0 || xb == 24 || i == 0 || i == TZ3_H - 1;     // owns pixels of the border ring
+                // pixel (Y = 2 i + a, X = 8 xb + 2 xo + b) lives in plane 2 xo + b at slot Y * 26 + xb + 1: one base per thread,
+                // compile-time offsets per (xo, a, b)
+                __nv_bfloat16 *pix = dst + ((2 * i) * 26 + xb + 1) * 8;
+                const uint32_t tm = tmem_base + ((uint32_t)(gw * 32) << 16) + (uint32_t)((s * TZ3_T + t) * TZ3_N);
+                uint32_t ra[32], rb[32];                  // two TMEM loads in flight: pixel xo is processed while xo + 1 arrives
+                tc_ld32(tm, ra);
+#pragma unroll
+                for (int xo = 0; xo < 4; xo++) {          // 32 columns = the 4 phases x 8 channels of low-res pixel 4 xb + xo
+                    uint32_t *r = (xo & 1) ? rb : ra;
+                    tc_wait_ld();
+                    if (xo < 3) tc_ld32(tm + (uint32_t)((xo + 1) * 32), (xo & 1) ? ra : rb);
+                    if (!valid) continue;
+#pragma unroll
+                    for (int ph = 0; ph < 4; ph++) {
+                        float o[8];
+#pragma unroll
+                        for (int co = 0; co < 8; co++) o[co] = __uint_as_float(r[ph * 8 + co]) + biasr[ph * 8 + co];
+                        *reinterpret_cast<uint4 *>(pix + ((2 * xo + (ph & 1)) * 200 + (ph >> 1)) * 26 * 8) = pack_relu_bf8(o);
+                        if (edge) {
+                            // the row's halo slot is never read from HBM, but leaving it unwritten would make the row's first
+                            // 32-byte sector a partial write (read-modify-write in DRAM)
+                            if (xb == 0) *reinterpret_cast<uint4 *>(pix - 8 + ((2 * xo + (ph & 1)) * 200 + (ph >> 1)) * 26 * 8) = make_uint4(0, 0, 0, 0);
+                            const int Y = 2 * i + (ph >> 1), X = 8 * xb + 2 * xo + (ph & 1);
+                            if (Y == 0 || Y == Wo - 1 || X == 0 || X == Wo - 1) {
+                                float *rbp = ring + 8 * (X == 0 ? Y - 2 * y0 : (X == Wo - 1 ? 2 * TZ3_R + Y - 2 * y0 : 4 * TZ3_R + X));
+#pragma unroll
+                                for (int co = 0; co < 8; co++) rbp[co] = o[co];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&tmem_empty[s]); mbar_arrive(&ring_full[s]); }
+            if (gt == 0) TZ_STAMPK(k, 4);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 // ---------------------------------------------------------------- host side
+static long long *g_tz_dbg3 = nullptr;                   // per-work stamps of k_tz_up3 (OFB_TZ_DEBUG=up3)
+extern "C" int ofb_policy_tz_debug3(long long *dev_buf) { g_tz_dbg3 = dev_buf; return OFB_OK; }
 static long long *g_tz_dbg = nullptr;                    // device buffer of 16 stamps, see ofb_policy_tz_debug
 extern "C" int ofb_policy_tz_debug(long long *dev_buf) { g_tz_dbg = dev_buf; return OFB_OK; }
 
@@ -629,15 +783,17 @@ int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, flo
 int pol_tz_up4_parts() { return TZ4_STRIPS; }
 
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
-    static thread_local bool configured = false;
-    if (!configured) {
+    static thread_local int n_sm = 0;
+    if (!n_sm) {
         OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tz_up3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tz3Smem::total));
-        configured = true;
+        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
     }
     if (n_items == 0) return OFB_OK;
     Tz3Args a = {};
     a.in = in; a.wt = p->w.u3_tz; a.bias = p->w.u3_pb; a.ring_w = p->w.u3_w; a.out = out;
-    k_tz_up3<<<dim3(TZ3_STRIPS, n_items), TZ3_NT, Tz3Smem::total, st>>>(a);
+    a.dbg = g_tz_dbg3;
+    const int n_work = n_items * TZ3_STRIPS;
+    k_tz_up3<<<n_work < n_sm ? n_work : n_sm, TZ3_NTP, Tz3Smem::total, st>>>(a, n_work);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

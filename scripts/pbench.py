@@ -41,7 +41,11 @@ def main():
         dbg = torch.zeros(16 + 8 * 14, dtype=torch.int64, device=bg.device)
         lib = _lib.load()
         lib.ofb_policy_tz_debug.argtypes = [ctypes.c_void_p]
-        lib.ofb_policy_tz_debug(ctypes.c_void_p(dbg.data_ptr()))
+        lib.ofb_policy_tz_debug3.argtypes = [ctypes.c_void_p]
+        if os.environ.get("OFB_TZ_DEBUG") == "up3":
+            lib.ofb_policy_tz_debug3(ctypes.c_void_p(dbg.data_ptr()))
+        else:
+            lib.ofb_policy_tz_debug(ctypes.c_void_p(dbg.data_ptr()))
         pol.set_engine("tensor")
         pol.forward_argmax(maps, vec)
         pol.forward_argmax(maps, vec)
@@ -54,8 +58,10 @@ def main():
         print("tz_up4 stamps (cycles since start):", [x - st[0] if x else None for x in st[:13]])
         for k in range(14):
             row = st[16 + 8 * k: 16 + 8 * k + 7]
-            print("  work %2d: issue %s landed %s mma0 %s mma1 %s corr %s drained %s done %s" % ((k,) + tuple(x - st[0] if x else None for x in row)))
+            base = st[0] or st[16]
+            print("  work %2d: j0 %s j1 %s j2 %s j3 %s j4 %s j5 %s j6 %s" % ((k,) + tuple(x - base if x else None for x in row)))
         lib.ofb_policy_tz_debug(None)
+        lib.ofb_policy_tz_debug3(None)
     for eng in engines:
         pol.set_engine(eng)
         for _ in range(2):
