@@ -170,8 +170,8 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     up.add(&d.d2_w, wh->dense2.kernel, 100 * 50); up.add(&d.d2_b, wh->dense2.bias, 50);
     up.add(&d.o1_w, wh->output1.kernel, 50 * 2); up.add(&d.o1_b, wh->output1.bias, 2);
     up.add(&d.ud_w, wh->updense1.kernel, 100 * 625); up.add(&d.ud_b, wh->updense1.bias, 625);
-    fold_conv(wh->upconv[0], 1, 2, w, b); up.add(&d.u1_w, w); up.add(&d.u1_b, b);
-    fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b);
+    fold_conv(wh->upconv[0], 1, 2, w, b); up.add(&d.u1_w, w); up.add(&d.u1_b, b); up.add(&d.u1_pw, fold_phase(w, 1, 2));
+    fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b); up.add(&d.u2_pw, fold_phase(w, 2, 4));
     fold_conv(wh->upconv[2], 4, 8, w, b);
     up.add(&d.u3_w, w); up.add(&d.u3_b, b);
     { const std::vector<float> pf = fold_phase(w, 4, 8);
@@ -393,15 +393,57 @@ k_dense1_cc(const __nv_bfloat16 *__restrict__ flat, const __nv_bfloat16 *__restr
             if (a0 + a < n_items) hflat[(size_t)(a0 + a) * 100 + j] = acc[a] + red[a][j];
 }
 
+// 16-byte shared-memory load the compiler may not hoist out of a loop
+__device__ __forceinline__ float4 lds128_volatile(const float *p) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+
+// Border-ring correction of a phase-folded [bilinear x2 -> conv3x3 'same'] for an fp32 [n][n][CIN] source in shared memory
+// (see up_ring_correct in ofb_policy_dev.cuh): v[co] -= sum over the taps outside [0, 2n) of w[dy][dx][:, co] . U~.
+template <int CIN, int COUT>
+__device__ __forceinline__ void ring_correct_f32(const float *__restrict__ src, int n, int Y, int X, const float *__restrict__ w, float *v) {
+    for (int dy = 0; dy < 3; dy++) {
+        const int YY = Y + dy - 1;
+        for (int dx = 0; dx < 3; dx++) {
+            const int XX = X + dx - 1;
+            if (YY >= 0 && YY < 2 * n && XX >= 0 && XX < 2 * n) continue;
+            int ylo, yhi, xlo, xhi; float wyl, wyh, wxl, wxh;
+            bil_tap_ext(YY, ylo, yhi, wyl, wyh);
+            bil_tap_ext(XX, xlo, xhi, wxl, wxh);
+            ylo = min(max(ylo, 0), n - 1); yhi = min(max(yhi, 0), n - 1);
+            xlo = min(max(xlo, 0), n - 1); xhi = min(max(xhi, 0), n - 1);
+#pragma unroll
+            for (int ci = 0; ci < CIN; ci++) {
+                const float u = wyl * (wxl * src[(ylo * n + xlo) * CIN + ci] + wxh * src[(ylo * n + xhi) * CIN + ci]) +
+                                wyh * (wxl * src[(yhi * n + xlo) * CIN + ci] + wxh * src[(yhi * n + xhi) * CIN + ci]);
+#pragma unroll
+                for (int co = 0; co < COUT; co++) v[co] -= u * w[((dy * 3 + dx) * CIN + ci) * COUT + co];
+            }
+        }
+    }
+}
+
 // Everything between dense1's flat part and upconv3, per ship, in fp32 on CUDA cores:
-// dense1 (vector slice + bias + ReLU), dense2, output1 (+ argmax), updense1, upconv1, upconv2.
-#define HEADS_SMEM_FLOATS (128 + 64 + 640 + 2500 + 5000 + 20000)
-__global__ void __launch_bounds__(256)
+// dense1 (vector slice + bias + ReLU), dense2, output1 (+ argmax), updense1, upsampling1 + upconv1, upsampling2 + upconv2.
+// The two small up-convolutions run in the phase-folded form on their low-res grids (25 x 25 and 50 x 50), so no upsampled
+// map is materialised and the block needs ~26 KB of shared memory (8 blocks per SM instead of 2).
+#define HEADS_SMEM_FLOATS (128 + 64 + 640 + 5000 + 80 + 304 + 32 + 80)
+__global__ void __launch_bounds__(256, 3)
 k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, float *__restrict__ act_out,
         int *__restrict__ iaction_out, __nv_bfloat16 *__restrict__ up2_out, int plane_layout) {
-    extern __shared__ float sm[];
-    float *h = sm, *d2 = h + 128, *u = d2 + 64, *U1 = u + 640, *a1 = U1 + 2500, *U2 = a1 + 5000;
+    extern __shared__ __align__(16) float sm[];
+    float *h = sm, *d2 = h + 128, *u = d2 + 64, *a1 = u + 640, *w1p = a1 + 5000, *w2p = w1p + 80, *w1r = w2p + 304, *w2r = w1r + 32;
     const int s = blockIdx.x, arena = s / ships_per_arena, tid = threadIdx.x, nt = blockDim.x;
+    // folded weights: upconv1 [9][1][8] (+ un-phased [9][1][2] for the ring), upconv2 [9][2][16] (+ [9][2][4]), biases
+    for (int i = tid; i < 72; i += nt) w1p[i] = w.u1_pw[i];
+    for (int i = tid; i < 288; i += nt) w2p[i] = w.u2_pw[i];
+    if (tid < 18) w1r[tid] = w.u1_w[tid];
+    for (int i = tid; i < 72; i += nt) w2r[i] = w.u2_w[i];
+    if (tid < 2) w1p[72 + tid] = w.u1_b[tid];
+    if (tid < 4) w2p[288 + tid] = w.u2_b[tid];
     // dense1: [vector(8), flat(5000)] -> 100, ReLU      (qlearnIA_V2.py:154-155)
     if (tid < 100) {
         float acc = w.d1_b[tid];
@@ -420,6 +462,7 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         } else {
             const int q = j - 50;
             float acc = w.ud_b[q];
+#pragma unroll 10
             for (int i = 0; i < 100; i++) acc += h[i] * w.ud_w[i * 625 + q];
             u[q] = fmaxf(acc, 0.f);
         }
@@ -432,68 +475,100 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         if (act_out) { act_out[(size_t)s * 2] = a0; act_out[(size_t)s * 2 + 1] = a1v; }
         if (iaction_out) iaction_out[s] = a1v > a0 ? 1 : 0;
     }
-    // upsampling1: 25x25 -> 50x50 bilinear (:166)
-    for (int p = tid; p < 2500; p += nt) {
-        const int Y = p / 50, X = p % 50;
-        int yl, yh, xl, xh; float wyl, wyh, wxl, wxh;
-        bil_tap(Y, 25, yl, yh, wyl, wyh);
-        bil_tap(X, 25, xl, xh, wxl, wxh);
-        U1[p] = wyl * (wxl * u[yl * 25 + xl] + wxh * u[yl * 25 + xh]) + wyh * (wxl * u[yh * 25 + xl] + wxh * u[yh * 25 + xh]);
-    }
-    __syncthreads();
-    // upconv1 1 -> 2 + BN + ReLU (:167-169)
-    for (int p = tid; p < 2500; p += nt) {
-        const int y = p / 50, x = p % 50;
-        float c0 = w.u1_b[0], c1 = w.u1_b[1];
+    // upsampling1 + upconv1 1 -> 2 + BN + ReLU (:166-169): one thread per pixel of the 25 x 25 grid, 4 phases x 2 channels
+    for (int p = tid; p < 625; p += nt) {
+        const int i = p / 25, j = p % 25;
+        float acc[8];
 #pragma unroll
-        for (int dy = 0; dy < 3; dy++)
+        for (int n = 0; n < 8; n++) acc[n] = w1p[72 + (n & 1)];
 #pragma unroll
-            for (int dx = 0; dx < 3; dx++) {
-                const int yy = y + dy - 1, xx = x + dx - 1;
-                if (yy < 0 || yy >= 50 || xx < 0 || xx >= 50) continue;
-                const float v = U1[yy * 50 + xx];
-                c0 += v * w.u1_w[(dy * 3 + dx) * 2];
-                c1 += v * w.u1_w[(dy * 3 + dx) * 2 + 1];
+        for (int uu = 0; uu < 3; uu++)
+#pragma unroll
+            for (int vv = 0; vv < 3; vv++) {
+                const float x = u[min(max(i + uu - 1, 0), 24) * 25 + min(max(j + vv - 1, 0), 24)];
+#pragma unroll
+                for (int n = 0; n < 8; n++) acc[n] += x * w1p[(uu * 3 + vv) * 8 + n];
             }
-        a1[p * 2] = fmaxf(c0, 0.f);
-        a1[p * 2 + 1] = fmaxf(c1, 0.f);
-    }
-    __syncthreads();
-    // upsampling2: 50x50x2 -> 100x100x2 (:172)
-    for (int p = tid; p < 10000; p += nt) {
-        const int Y = p / 100, X = p % 100;
-        int yl, yh, xl, xh; float wyl, wyh, wxl, wxh;
-        bil_tap(Y, 50, yl, yh, wyl, wyh);
-        bil_tap(X, 50, xl, xh, wxl, wxh);
 #pragma unroll
-        for (int c = 0; c < 2; c++)
-            U2[p * 2 + c] = wyl * (wxl * a1[(yl * 50 + xl) * 2 + c] + wxh * a1[(yl * 50 + xh) * 2 + c]) +
-                            wyh * (wxl * a1[(yh * 50 + xl) * 2 + c] + wxh * a1[(yh * 50 + xh) * 2 + c]);
+        for (int ph = 0; ph < 4; ph++) {
+            const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
+            if (Y == 0 || Y == 49 || X == 0 || X == 49) continue;        // border ring: second loop
+            a1[(Y * 50 + X) * 2] = fmaxf(acc[ph * 2], 0.f);
+            a1[(Y * 50 + X) * 2 + 1] = fmaxf(acc[ph * 2 + 1], 0.f);
+        }
+    }
+#pragma unroll 1
+    for (int rp = tid; rp < 4 * 49; rp += nt) {                          // the 196 pixels of the border ring, with the correction
+        const int side = rp / 49, q = rp % 49;
+        const int Y = side == 0 ? 0 : (side == 1 ? 49 : (side == 2 ? q + 1 : q)), X = side == 0 ? q : (side == 1 ? q + 1 : (side == 2 ? 0 : 49));
+        const int i = Y >> 1, j = X >> 1, ph = (Y & 1) * 2 + (X & 1);
+        float o[2] = {w1p[72], w1p[73]};
+        for (int t = 0; t < 9; t++) {
+            const float x = u[min(max(i + t / 3 - 1, 0), 24) * 25 + min(max(j + t % 3 - 1, 0), 24)];
+            o[0] += x * w1p[t * 8 + ph * 2];
+            o[1] += x * w1p[t * 8 + ph * 2 + 1];
+        }
+        ring_correct_f32<1, 2>(u, 25, Y, X, w1r, o);
+        a1[(Y * 50 + X) * 2] = fmaxf(o[0], 0.f);
+        a1[(Y * 50 + X) * 2 + 1] = fmaxf(o[1], 0.f);
     }
     __syncthreads();
-    // upconv2 2 -> 4 + BN + ReLU (:173-175) -> bf16 NHWC with channels padded to 8
+    // upsampling2 + upconv2 2 -> 4 + BN + ReLU (:172-175): one thread per pixel of the 50 x 50 grid, 4 phases x 4 channels
+    // -> bf16 with channels padded to 8
     __nv_bfloat16 *dst = up2_out + (size_t)s * POL_UP2_ITEM;   // tensor engine: de-interleaved by x mod 4 for k_tz_up3
-    for (int p = tid; p < 10000; p += nt) {
-        const int y = p / 100, x = p % 100;
-        float c[4] = {w.u2_b[0], w.u2_b[1], w.u2_b[2], w.u2_b[3]};
+    for (int p = tid; p < 2500; p += nt) {
+        const int i = p / 50, j = p % 50;
+        float acc[16];
 #pragma unroll
-        for (int dy = 0; dy < 3; dy++)
+        for (int n = 0; n < 16; n++) acc[n] = w2p[288 + (n & 3)];
 #pragma unroll
-            for (int dx = 0; dx < 3; dx++) {
-                const int yy = y + dy - 1, xx = x + dx - 1;
-                if (yy < 0 || yy >= 100 || xx < 0 || xx >= 100) continue;
-                const float v0 = U2[(yy * 100 + xx) * 2], v1 = U2[(yy * 100 + xx) * 2 + 1];
-                const float *wp = w.u2_w + (dy * 3 + dx) * 8;
+        for (int uu = 0; uu < 3; uu++)
 #pragma unroll
-                for (int co = 0; co < 4; co++) c[co] += v0 * wp[co] + v1 * wp[4 + co];
+            for (int vv = 0; vv < 3; vv++) {
+                const float2 x = *reinterpret_cast<const float2 *>(a1 + (min(max(i + uu - 1, 0), 49) * 50 + min(max(j + vv - 1, 0), 49)) * 2);
+                // volatile: keeps the 288 loop-invariant weights in shared memory instead of (spilled) registers
+                const float *wp = w2p + (uu * 3 + vv) * 32;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float4 wa = lds128_volatile(wp + 4 * q), wb = lds128_volatile(wp + 16 + 4 * q);
+                    acc[q * 4 + 0] += x.x * wa.x + x.y * wb.x;
+                    acc[q * 4 + 1] += x.x * wa.y + x.y * wb.y;
+                    acc[q * 4 + 2] += x.x * wa.z + x.y * wb.z;
+                    acc[q * 4 + 3] += x.x * wa.w + x.y * wb.w;
+                }
             }
-        // full 16-byte pixels (channels 4..7 = 0) and, in the plane layout, the row's halo slot too: partial 32-byte
-        // sectors would turn into read-modify-writes in DRAM
-        __nv_bfloat16 *q = dst + (plane_layout ? pol_plane100_off(y, x) : p * 8);
-        *reinterpret_cast<uint4 *>(q) =
-            make_uint4(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)), 0u, 0u);
-        if (plane_layout && x < 4) *reinterpret_cast<uint4 *>(q - 8) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+        for (int ph = 0; ph < 4; ph++) {
+            const int y = 2 * i + (ph >> 1), x = 2 * j + (ph & 1);
+            if (y == 0 || y == 99 || x == 0 || x == 99) continue;        // border ring: second loop
+            // full 16-byte pixels (channels 4..7 = 0): partial 32-byte sectors would turn into read-modify-writes in DRAM
+            *reinterpret_cast<uint4 *>(dst + (plane_layout ? pol_plane100_off(y, x) : (y * 100 + x) * 8)) =
+                make_uint4(pack_bf2(fmaxf(acc[ph * 4], 0.f), fmaxf(acc[ph * 4 + 1], 0.f)),
+                           pack_bf2(fmaxf(acc[ph * 4 + 2], 0.f), fmaxf(acc[ph * 4 + 3], 0.f)), 0u, 0u);
+        }
     }
+#pragma unroll 1
+    for (int rp = tid; rp < 4 * 99; rp += nt) {                          // the 396 pixels of the border ring, with the correction
+        const int side = rp / 99, q = rp % 99;
+        const int y = side == 0 ? 0 : (side == 1 ? 99 : (side == 2 ? q + 1 : q)), x = side == 0 ? q : (side == 1 ? q + 1 : (side == 2 ? 0 : 99));
+        const int i = y >> 1, j = x >> 1, ph = (y & 1) * 2 + (x & 1);
+        float c[4] = {w2p[288], w2p[289], w2p[290], w2p[291]};
+        for (int t = 0; t < 9; t++) {
+            const float2 v = *reinterpret_cast<const float2 *>(a1 + (min(max(i + t / 3 - 1, 0), 49) * 50 + min(max(j + t % 3 - 1, 0), 49)) * 2);
+            const float4 wa = *reinterpret_cast<const float4 *>(w2p + t * 32 + ph * 4), wb = *reinterpret_cast<const float4 *>(w2p + t * 32 + 16 + ph * 4);
+            c[0] += v.x * wa.x + v.y * wb.x;
+            c[1] += v.x * wa.y + v.y * wb.y;
+            c[2] += v.x * wa.z + v.y * wb.z;
+            c[3] += v.x * wa.w + v.y * wb.w;
+        }
+        ring_correct_f32<2, 4>(a1, 50, y, x, w2r, c);
+        __nv_bfloat16 *q16 = dst + (plane_layout ? pol_plane100_off(y, x) : (y * 100 + x) * 8);
+        *reinterpret_cast<uint4 *>(q16) = make_uint4(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)), 0u, 0u);
+        if (plane_layout && x == 0) *reinterpret_cast<uint4 *>(q16 - 8) = make_uint4(0u, 0u, 0u, 0u);     // the row's halo slot
+    }
+    if (plane_layout)                                                    // halo slots of planes 1..3 (x = 1..3 are interior pixels)
+        for (int rp = tid; rp < 3 * 100; rp += nt)
+            *reinterpret_cast<uint4 *>(dst + pol_plane100_off(rp % 100, 1 + rp / 100) - 8) = make_uint4(0u, 0u, 0u, 0u);
 }
 
 // upconv3 (bilinear x2 folded into 4 phases) 4 -> 8 + BN + ReLU: one thread per low-res pixel
