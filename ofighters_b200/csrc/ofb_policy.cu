@@ -719,7 +719,8 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
           k_conv_pool_cc<<<dim3((625 + 127) / 128, A), 128, 0, st>>>(ws.pool3, w.cw[2], w.cb[2], ws.flat, 50, POL_FLAT_PITCH); }
     }
     { ProfScope ps(p, L_DENSE1, st);
-      k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A); }
+      if (tc) { if ((rc = pol_tc_dense1(p, ws.flat, ws.hflat, A, st)) != OFB_OK) return rc; }
+      else k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A); }
     { ProfScope ps(p, L_HEADS, st);
       k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2, tc ? 1 : 0); }
     if (!xy && !ptr) { OFB_CUDA_CHECK(cudaGetLastError()); return OFB_OK; }

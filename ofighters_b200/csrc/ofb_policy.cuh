@@ -89,6 +89,7 @@ int pol_tc_up4_parts();
 int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st);
 int pol_tz_up4_parts();
+int pol_tc_dense1(const ofb_policy *p, const __nv_bfloat16 *flat, float *hflat, int n_items, cudaStream_t st);
 int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 // element offset of pixel (y, x) of a 100 x 100 x 8 image in plane layout (4 planes of x mod 4)

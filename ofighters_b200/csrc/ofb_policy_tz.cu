@@ -1093,3 +1093,119 @@ int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }
+
+// ================================================================================================
+// k_tc_dense1: the flat slice of dense1 (qlearnIA_V2.py:154-155) as a plain tcgen05 GEMM,
+//     hflat[arena][n] = sum_k flat[arena][k] * W[n][k],   M = 128 arenas per CTA, N = 128 (100 used), K = 5120.
+// Both operands are K-major in HBM ([row][5120] bf16).  Eight loader warps move K = 64 slabs into shared memory with
+// coalesced 16-byte loads, storing them as UMMA core matrices [k/8][row][16 B] (LBO = one k-chunk plane, padded by 16 B
+// so that the 8 chunks of a row fall into different banks); one converged warp issues 4 MMAs per slab.
+// ================================================================================================
+#define D1_K POL_FLAT_PITCH           // 5120
+#define D1_SLAB 64                    // K per stage
+#define D1_NSLAB (D1_K / D1_SLAB)     // 80
+#define D1_PLANE (128 * 16 + 16)      // bytes of one k-chunk plane (128 rows x 16 B + pad)
+#define D1_OPBYTES (8 * D1_PLANE)     // one operand slab
+#define D1_NST 4
+#define D1_NT (32 * 9)                // 8 loader warps + 1 MMA warp
+
+__global__ void __launch_bounds__(D1_NT, 1)
+k_tc_dense1(const __nv_bfloat16 *__restrict__ flat, const __nv_bfloat16 *__restrict__ wt, float *__restrict__ hflat, int n_items) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + D1_NST * 2 * D1_OPBYTES);     // full[NST], empty[NST], done
+    uint64_t *full = bars, *empty = bars + D1_NST, *done = bars + 2 * D1_NST;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * D1_NST + 1);
+    const int a0 = blockIdx.x * 128;
+    if (tid == 0) {
+        for (int s = 0; s < D1_NST; s++) { mbar_init(&full[s], 8); mbar_init(&empty[s], 1); }
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ---- loaders: thread -> (row, k-chunk) pieces of 16 B; 8 consecutive threads read 128 contiguous bytes of one row
+        const int kc = tid & 7, r0 = tid >> 3;             // rows r0, r0 + 32, r0 + 64, r0 + 96
+        for (int sl = 0; sl < D1_NSLAB; sl++) {
+            const int s = sl % D1_NST;
+            if (sl >= D1_NST) mbar_wait(&empty[s], (uint32_t)((sl / D1_NST - 1) & 1));
+            uint8_t *sA = smem + s * 2 * D1_OPBYTES, *sB = sA + D1_OPBYTES;
+            uint4 va[4], vb[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int row = r0 + 32 * i;
+                va[i] = (a0 + row < n_items) ? *reinterpret_cast<const uint4 *>(flat + (size_t)(a0 + row) * D1_K + sl * D1_SLAB + kc * 8)
+                                             : make_uint4(0, 0, 0, 0);
+                vb[i] = *reinterpret_cast<const uint4 *>(wt + (size_t)row * D1_K + sl * D1_SLAB + kc * 8);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int row = r0 + 32 * i;
+                *reinterpret_cast<uint4 *>(sA + kc * D1_PLANE + row * 16) = va[i];
+                *reinterpret_cast<uint4 *>(sB + kc * D1_PLANE + row * 16) = vb[i];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+        }
+        // ---- epilogue: warps 0-3 read the accumulator (lane quarter = warp), thread = arena
+        if (warp < 4) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const int arena = a0 + tid;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), r);
+                tc_wait_ld();
+                if (arena < n_items)
+#pragma unroll
+                    for (int n = 0; n < 32; n++)
+                        if (c * 32 + n < 100) hflat[(size_t)arena * 100 + c * 32 + n] = __uint_as_float(r[n]);
+            }
+        }
+    } else {
+        // ---- MMA warp (converged, elected lane issues)
+        constexpr uint32_t IDESC = instr_desc(128);
+        const bool leader = elect_one();
+        for (int sl = 0; sl < D1_NSLAB; sl++) {
+            const int s = sl % D1_NST;
+            mbar_wait(&full[s], (uint32_t)((sl / D1_NST) & 1));
+            tc_fence_after();
+            const uint32_t a16 = smem_u32(smem + s * 2 * D1_OPBYTES) >> 4, b16 = a16 + D1_OPBYTES / 16;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint64_t ad = smem_desc(a16 + (uint32_t)(2 * j * (D1_PLANE / 16)), D1_PLANE / 16, 8);
+                const uint64_t bd = smem_desc(b16 + (uint32_t)(2 * j * (D1_PLANE / 16)), D1_PLANE / 16, 8);
+                if (leader) tc_mma(tmem_base, ad, bd, IDESC, (sl | j) ? 1u : 0u);
+            }
+            if (leader) tc_commit(&empty[s]);
+        }
+        if (leader) tc_commit(done);
+        __syncwarp();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
+}
+
+int pol_tc_dense1(const ofb_policy *p, const __nv_bfloat16 *flat, float *hflat, int n_items, cudaStream_t st) {
+    const int smem = D1_NST * 2 * D1_OPBYTES + (2 * D1_NST + 1) * 8 + 16;
+    static thread_local bool configured = false;
+    if (!configured) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tc_dense1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    if (n_items == 0) return OFB_OK;
+    k_tc_dense1<<<(n_items + 127) / 128, D1_NT, smem, st>>>(flat, p->w.d1_wt, hflat, n_items);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
