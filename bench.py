@@ -331,10 +331,14 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
                   for k, v in prof.items()}
         dom = max(prof, key=prof.get)
         total = sum(prof.values())
-        return {"bound": "tensor", "kernel": "k_tc_conv<%s>" % dom, "achieved": layers[dom]["alg_tflops"], "peak": tpeak,
+        kname = {"trunk12": "k_tz_trunk12 (conv1 from bits + block-Toeplitz conv2 + pools)", "conv3": "k_tc_conv_pool", "conv4": "k_tc_conv_pool",
+                 "dense1": "k_tc_dense1", "heads": "k_heads", "up3": "k_tz_up3", "up4": "k_tz_up4", "argmax": "k_argmax_final"}
+        return {"bound": "tensor", "kernel": kname.get(dom, dom), "achieved": layers[dom]["alg_tflops"], "peak": tpeak,
                 "unit": "TFLOP/s", "frac": layers[dom]["alg_tflops"] / tpeak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM loop)" if peaks else "fallback",
                 "traffic": None, "us_per_launch": prof[dom] * 1e3 / max(1, -(-n // policy.max_ships)),
+                "note": "algorithmic FLOPs of the layer (Appendix B MACs x 2) / its device time; these layers have 8 or fewer "
+                        "channels, so the tensor pipe is bound by operand reads and the kernels by HBM / epilogue, not by math",
                 "whole_forward": {"ms": total, "forwards_per_s": n / (total * 1e-3),
                                   "dense_equiv_tflops": 155.3e6 * n / (total * 1e-3) / 1e12,
                                   "frac_of_peak": 155.3e6 * n / (total * 1e-3) / 1e12 / tpeak},

@@ -61,18 +61,6 @@ static std::vector<float> fold_phase(const std::vector<float> &w, int cin, int c
     return o;
 }
 
-// [9 (dy, dx)][cin][cout] fp32 -> tensor-engine B image [4 dy][nn][8 cin] bf16 with n = dx * nc + co:
-// the dx taps are folded into the N dimension (summed again in the epilogue), dy into K.
-static std::vector<__nv_bfloat16> pack_dyfold(const std::vector<float> &w, int cin, int cout, int nc, int nn) {
-    std::vector<__nv_bfloat16> o((size_t)4 * nn * 8, __float2bfloat16(0.f));
-    for (int dy = 0; dy < 3; dy++)
-        for (int dx = 0; dx < 3; dx++)
-            for (int ci = 0; ci < cin; ci++)
-                for (int co = 0; co < cout; co++)
-                    o[((size_t)dy * nn + dx * nc + co) * 8 + ci] = __float2bfloat16(w[((size_t)(dy * 3 + dx) * cin + ci) * cout + co]);
-    return o;
-}
-
 // phase-folded fp32 [9 (u, v)][cin][coutp] -> block-Toeplitz B operand [3 u][nks][2 chunks][B * coutp n][8 cin] bf16 for
 // blocks of B pixels: n = xo * coutp + c, chunk of pixel offset p (input x = B xb + p - 1) carries tap v = p - xo.
 // K-step pairs: (1, 0), (2, 3), ..., (B - 2, B - 1), (B + 1, B)  -- see ofb_policy_tz.cu
@@ -151,7 +139,6 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
         b.resize(16, 0.f);
         up.add(&d.cw[l], pack_taps(w, 8, 8, 16));
         if (l == 0) up.add(&d.c2_tz, pack_toeplitz(w, 8, 8, 8));
-        up.add(&d.cw2[l], pack_dyfold(w, 8, 8, 8, 32));
         up.add(&d.cb[l], b);
     }
     // dense1: rows 0..7 = vector slice (fp32), rows 8..5007 = flat slice (bf16)
@@ -176,14 +163,12 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     up.add(&d.u3_w, w); up.add(&d.u3_b, b);
     { const std::vector<float> pf = fold_phase(w, 4, 8);
       up.add(&d.u3_pw, pack_taps(pf, 4, 32, 32));
-      up.add(&d.u3_pw2, pack_dyfold(pf, 4, 32, 32, 96));
       up.add(&d.u3_tz, pack_toeplitz(pf, 4, 32, 4)); }
     { std::vector<float> pb(32); for (int n = 0; n < 32; n++) pb[n] = b[n % 8]; up.add(&d.u3_pb, pb); }
     fold_conv(wh->upconv[3], 8, 1, w, b);
     up.add(&d.u4_w, w); up.add(&d.u4_b, b);
     { const std::vector<float> pf = fold_phase(w, 8, 1);
       up.add(&d.u4_pw, pack_taps(pf, 8, 4, 16));
-      up.add(&d.u4_pw2, pack_dyfold(pf, 8, 4, 4, 16));
       up.add(&d.u4_tz, pack_toeplitz(pf, 8, 4, 8)); }
     p->u4_bias = b[0];
     { std::vector<float> pb(16, 0.f); for (int n = 0; n < 4; n++) pb[n] = b[0]; up.add(&d.u4_pb, pb); }

@@ -20,7 +20,6 @@ struct PolicyDev {
     float *c1_lut;            // [2][512][8] sums of c1_w over the set taps of a 9-bit stencil pattern
     __nv_bfloat16 *cw[3];     // conv2..4: [10][16][8] (tap, n = cout padded to 16, cin)  bf16
     float *cb[3];             // [16]
-    __nv_bfloat16 *cw2[3];    // conv2..4 for the tensor engine: [4 dy][32 n = dx*8 + cout][8 cin] (dy 3 and n >= 24 zero)
     // dense1
     float *d1_wv;             // [8][100]     vector slice, fp32 (values up to 400 are not bf16-exact)
     __nv_bfloat16 *d1_wf;     // [5000][100]  flat slice, (k, n)  -- CUDA-core engine
@@ -37,11 +36,9 @@ struct PolicyDev {
     float *u3_w, *u3_b;       // [9][4][8], [8]   un-phased fp32 (ring pixels)
     __nv_bfloat16 *u3_pw;     // [10][32][8]      (tap, n = phase*8 + cout, cin padded to 8)
     float *u3_pb;             // [32]
-    __nv_bfloat16 *u3_pw2;    // tensor engine: [4 u][96 n = v*32 + phase*8 + cout][8 cin]
     float *u4_w, *u4_b;       // [9][8][1], [1]
     __nv_bfloat16 *u4_pw;     // [10][16][8]      (tap, n = phase (4 used), cin)
     float *u4_pb;             // [16]
-    __nv_bfloat16 *u4_pw2;    // tensor engine: [4 u][16 n = v*4 + phase][8 cin]
     __nv_bfloat16 *c2_tz;     // block-Toeplitz B operand of conv2: [3 u][5 k-steps][2 chunks][64 n = xo*8 + cout][8 cin]
     __nv_bfloat16 *u3_tz;     // block-Toeplitz B operand of upconv3: [3 u][3 k-steps][2 chunks][128 n = xo*32 + phase*8 + cout][8 cin]
     __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
@@ -80,11 +77,6 @@ void ofb_set_error(const char *fmt, ...);
 // tensor-core (tcgen05) kernels, ofb_policy_tc.cu
 int pol_tc_conv_pool(const ofb_policy *p, int layer, const __nv_bfloat16 *in, __nv_bfloat16 *out, int hin, int n_items,
                      long long out_item_stride, cudaStream_t st);
-int pol_tc_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
-int pol_tc_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
-int pol_tc_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
-               cudaStream_t st);
-int pol_tc_up4_parts();
 // block-Toeplitz kernels, ofb_policy_tz.cu
 int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st);

@@ -19,22 +19,6 @@ def main():
     maps = bg.raster("bits")
     vec = bg.obs_vec[:, 0, :].contiguous()
     pol = PolicyB200.random_init(device=bg.device, seed=0, max_ships=int(os.environ.get('OFB_MAX_SHIPS', '4096')))
-    if os.environ.get("OFB_TC_DEBUG"):
-        import ctypes
-        from ofighters_b200 import _lib
-        dbg = torch.zeros(128, dtype=torch.int64, device=bg.device)
-        lib = _lib.load()
-        lib.ofb_policy_tc_debug.argtypes = [ctypes.c_void_p]
-        lib.ofb_policy_tc_debug(ctypes.c_void_p(dbg.data_ptr()))
-        pol.set_engine("tensor")
-        pol.forward_argmax(maps, vec)
-        pol.forward_argmax(maps, vec)
-        torch.cuda.synchronize()
-        d = dbg.cpu().reshape(4, 32)
-        for m, name in enumerate(["conv_gmem", "trunk12", "up3", "up4"]):
-            st = d[m, :11].tolist()
-            print(name, "phase cycles:", [st[i + 1] - st[i] if st[i + 1] and st[i] else None for i in range(10)], "total", st[10] - st[0], "| first-ring MMAs:", int(d[m, 12] - d[m, 11]), "| tile2 drain: wait %d pass1 %d bar %d pass2 %d" % tuple(int(d[m, k + 1] - d[m, k]) for k in (13, 14, 15, 16)))
-        lib.ofb_policy_tc_debug(None)
     if os.environ.get("OFB_TZ_DEBUG"):
         import ctypes
         from ofighters_b200 import _lib
