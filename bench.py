@@ -302,6 +302,15 @@ def gpu_arm(args, wl):
         dist.destroy_process_group()
 
 
+def _ncu_traffic():
+    """DRAM bytes per launch of the dominant kernels, from the committed `ncu --set full` captures (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
 def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
     """Dominant kernel of the arena workloads = the raster (it writes >95 % of the step's bytes):
     achieved = algorithmic bytes (the tensor it must produce: N * 2 * W*H/8) / mean launch time.
@@ -331,12 +340,15 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
                   for k, v in prof.items()}
         dom = max(prof, key=prof.get)
         total = sum(prof.values())
+        per_item = _ncu_traffic().get("policy_per_item", {})
         kname = {"trunk12": "k_tz_trunk12 (conv1 from bits + block-Toeplitz conv2 + pools)", "conv3": "k_tc_conv_pool", "conv4": "k_tc_conv_pool",
                  "dense1": "k_tc_dense1", "heads": "k_heads", "up3": "k_tz_up3", "up4": "k_tz_up4", "argmax": "k_argmax_final"}
         return {"bound": "tensor", "kernel": kname.get(dom, dom), "achieved": layers[dom]["alg_tflops"], "peak": tpeak,
                 "unit": "TFLOP/s", "frac": layers[dom]["alg_tflops"] / tpeak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM loop)" if peaks else "fallback",
-                "traffic": None, "us_per_launch": prof[dom] * 1e3 / max(1, -(-n // policy.max_ships)),
+                "traffic": (per_item[kname.get(dom, dom).split(" ")[0]] * min(n, policy.max_ships)
+                            if kname.get(dom, dom).split(" ")[0] in per_item else None),
+                "us_per_launch": prof[dom] * 1e3 / max(1, -(-n // policy.max_ships)),
                 "note": "algorithmic FLOPs of the layer (Appendix B MACs x 2) / its device time; these layers have 8 or fewer "
                         "channels, so the tensor pipe is bound by operand reads and the kernels by HBM / epilogue, not by math",
                 "whole_forward": {"ms": total, "forwards_per_s": n / (total * 1e-3),
@@ -363,10 +375,13 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
         nb = sum(x[2] for x in ts) / iters
         res[name] = {"us": ms * 1e3, "bytes": nb, "gbs": nb / (ms * 1e-3) / 1e9}
     dom = "k_raster"
+    tr = _ncu_traffic().get("arena%d" % bg.n_arenas, {}) if bg.ships_number == 7 else {}
     return {"bound": "hbm", "kernel": dom, "achieved": res[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": res[dom]["gbs"] / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
-            "traffic": None, "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
+            "traffic": tr.get(dom),
+            "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_ncu_full_*): below the algorithmic bytes because "
+                            "the last ~50 MB of the maps are still dirty in the 126 MB L2 when the kernel ends", "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
             "other_kernels": {"k_step": res["k_step"]}}
 
 

@@ -12,10 +12,10 @@
  * asynchronous on `stream`, no CPU fallback.  The handle owns the folded weights and a workspace
  * for the intermediate activations (sized at create time; nothing is allocated by forward).
  *
- * Arithmetic: BatchNormalization (inference, eps 1e-3) is folded into the conv weights; conv2-4
- * and upconv3-4 run as bf16 x bf16 -> fp32 tensor-core contractions (tcgen05) with bf16
- * activations between layers; conv1 (binary input), the 8-value vector slice of dense1, dense2,
- * output1, updense1, upconv1 and upconv2 stay in fp32.  Bilinear x2 upsampling uses TF2 half-pixel
+ * Arithmetic: BatchNormalization (inference, eps 1e-3) is folded into the conv weights; conv2-4,
+ * the 5000-wide flat slice of dense1 and upconv3-4 run as bf16 x bf16 -> fp32 tensor-core
+ * contractions (tcgen05) with bf16 activations between layers; conv1 (binary input), the 8-value
+ * vector slice of dense1, dense2, output1, updense1, upconv1 and upconv2 stay in fp32.  Bilinear x2 upsampling uses TF2 half-pixel
  * centres with edge clamp.
  */
 #ifndef OFB_POLICY_H
