@@ -817,8 +817,8 @@ int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out,
 #define TZ2_N 64
 #define TZ2_NST 2                     // stages = draining groups
 #define TZ2_STRIPS ((TZ2_H + TZ2_R - 1) / TZ2_R)
-#define TZ2_NPW 8                     // producer warps
-#define TZ2_NPT (32 * TZ2_NPW)
+#define TZ2_NPW 8                     // producer warps: two groups of 4, group g owns stage g (every other work item)
+#define TZ2_NPT 128                   // threads of one producer group
 #define TZ2_NTP (32 * (4 * TZ2_NST + TZ2_NPW + TZ2_T))      // 8 draining + 8 producer + 3 MMA warps
 #define TZ2_ABYTES (8 * TZ2_PS * 16)
 #define TZ2_WBYTES (3 * 5 * 2 * TZ2_N * 16)
@@ -839,12 +839,12 @@ struct Tz2Smem {
     static constexpr unsigned off_w = 0;
     static constexpr unsigned off_a = TZ2_WBYTES;
     static constexpr unsigned off_bits = off_a + TZ2_NST * TZ2_ABYTES;                 // [stage][2 maps][BITW]
-    static constexpr unsigned off_wl = off_bits + TZ2_NST * 2 * TZ2_BITW * 4;           // [stage][WL] ushort
+    static constexpr unsigned off_wl = off_bits + TZ2_NST * 2 * 2 * TZ2_BITW * 4;       // [stage][WL] ushort   (bits: [stage][2 buffers][2 maps][BITW])
     static constexpr unsigned off_stg = (off_wl + TZ2_NST * TZ2_WL * 2 + 15) & ~15u;    // [group][STG][4] uint4
     static constexpr unsigned off_misc = off_stg + TZ2_NST * TZ2_STG * 64;              // counters, biases
     static constexpr unsigned off_bar = off_misc + 128;
-    // barriers: wbar, bits_full[NST], full_a[NST], a_empty[NST], tmem_empty[NST], acc_full[NST][T]
-    static constexpr unsigned n_bar = 1 + 4 * TZ2_NST + TZ2_NST * TZ2_T;
+    // barriers: wbar, bits_full[NST][2 buffers] (the second half of the array), full_a[NST], a_empty[NST], tmem_empty[NST], acc_full[NST][T]
+    static constexpr unsigned n_bar = 1 + 5 * TZ2_NST + TZ2_NST * TZ2_T;
     static constexpr unsigned total = off_bar + n_bar * 8 + 16;
 };
 
@@ -859,14 +859,15 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
     float *sbias = reinterpret_cast<float *>(misc + 8);                      // conv1 bias [8], conv2 bias [8]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Tz2Smem::off_bar);
     uint64_t *wbar = bars, *bits_full = bars + 1, *full_a = bits_full + TZ2_NST, *a_empty = full_a + TZ2_NST,
-             *tmem_empty = a_empty + TZ2_NST, *acc_full = tmem_empty + TZ2_NST;
+             *tmem_empty = a_empty + TZ2_NST, *acc_full = tmem_empty + TZ2_NST, *bits_full2 = acc_full + TZ2_NST * TZ2_T;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + Tz2Smem::off_bar + Tz2Smem::n_bar * 8);
 
     if (tid == 0) {
         mbar_init(wbar, 1);
         for (int s = 0; s < TZ2_NST; s++) {
             mbar_init(&bits_full[s], 1);
-            mbar_init(&full_a[s], TZ2_NPW);                // the producer warps
+            mbar_init(&bits_full2[s], 1);
+            mbar_init(&full_a[s], 4);                      // the 4 warps of the stage's producer group
             mbar_init(&a_empty[s], TZ2_T);                 // the MMA warps (tcgen05.commit)
             mbar_init(&tmem_empty[s], 4);                  // the 4 warps of the draining group
             for (int t = 0; t < TZ2_T; t++) mbar_init(&acc_full[s * TZ2_T + t], 1);
@@ -884,41 +885,45 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= 4 * TZ2_NST && warp < 4 * TZ2_NST + TZ2_NPW) {
-        // ------------------------------------------------------------ producer group
-        const int pt = tid - 128 * TZ2_NST;
+        // ------------------------------------------------------------ producer groups: group g = 4 warps owns stage g
+        const int pg = (warp - 4 * TZ2_NST) >> 2, pt = (tid - 128 * TZ2_NST) & 127, s = pg;
         float bg[8];
 #pragma unroll
         for (int co = 0; co < 8; co++) bg[co] = fmaxf(sbias[co], 0.f);
         const uint4 bgq = pack_bf8(bg), zq = make_uint4(0, 0, 0, 0);
-        // both stages start clean: background everywhere, zeros in the x halo slots (slot 0 of planes 0 and 7)
-        for (int i = pt; i < TZ2_NST * 8 * TZ2_PS; i += TZ2_NPT) {
-            const int q = (i / TZ2_PS) % 8, t = (i % TZ2_PS) % TZ2_P;
-            reinterpret_cast<uint4 *>(smem + Tz2Smem::off_a)[i] = ((q == 0 || q == 7) && t == 0) ? zq : bgq;
+        uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz2Smem::off_a + s * TZ2_ABYTES);
+        unsigned short *wl = reinterpret_cast<unsigned short *>(smem + Tz2Smem::off_wl) + s * TZ2_WL;
+        // the stage starts clean: background everywhere, zeros in the x halo slots (slot 0 of planes 0 and 7)
+        for (int i = pt; i < 8 * TZ2_PS; i += TZ2_NPT) {
+            const int q = i / TZ2_PS, t = (i % TZ2_PS) % TZ2_P;
+            sa[i] = ((q == 0 || q == 7) && t == 0) ? zq : bgq;
         }
-        auto issue_bits = [&](int k, int w) {               // one thread: stage the bit rows of work item w
-            const int s = k & 1, item = w / TZ2_STRIPS, y0 = (w % TZ2_STRIPS) * TZ2_R;
+        auto issue_bits = [&](int j, int w) {               // one thread: stage the bit rows of the group's j-th work item w
+            const int item = w / TZ2_STRIPS, y0 = (w % TZ2_STRIPS) * TZ2_R;
             const int r0 = max(2 * y0 - 3, 0), r1 = min(2 * (y0 + TZ2_R) + 2, POL_W - 1);
             const int b0 = (r0 * 50) & ~15, b1 = min(((r1 + 1) * 50 + 15 + 16) & ~15, POL_WORDS * 4);
-            uint32_t *sb = reinterpret_cast<uint32_t *>(smem + Tz2Smem::off_bits) + s * 2 * TZ2_BITW;
+            uint32_t *sb = reinterpret_cast<uint32_t *>(smem + Tz2Smem::off_bits) + (s * 2 + (j & 1)) * 2 * TZ2_BITW;
+            uint64_t *bar = (j & 1) ? &bits_full2[s] : &bits_full[s];
             const uint8_t *src = reinterpret_cast<const uint8_t *>(a.maps) + (size_t)item * 2 * POL_WORDS * 4;
-            mbar_expect_tx(&bits_full[s], 2u * (uint32_t)(b1 - b0));
-            bulk_g2s(sb, src + b0, (uint32_t)(b1 - b0), &bits_full[s]);
-            bulk_g2s(sb + TZ2_BITW, src + POL_WORDS * 4 + b0, (uint32_t)(b1 - b0), &bits_full[s]);
+            mbar_expect_tx(bar, 2u * (uint32_t)(b1 - b0));
+            bulk_g2s(sb, src + b0, (uint32_t)(b1 - b0), bar);
+            bulk_g2s(sb + TZ2_BITW, src + POL_WORDS * 4 + b0, (uint32_t)(b1 - b0), bar);
         };
+        const int wstep = TZ2_NST * gridDim.x;
         if (pt == 0) {
-            mbar_expect_tx(wbar, TZ2_WBYTES);
-            bulk_g2s(sw, a.wt, TZ2_WBYTES, wbar);
-            if (blockIdx.x < n_work) issue_bits(0, blockIdx.x);
+            if (pg == 0) {
+                mbar_expect_tx(wbar, TZ2_WBYTES);
+                bulk_g2s(sw, a.wt, TZ2_WBYTES, wbar);
+            }
+            if (blockIdx.x + pg * gridDim.x < n_work) issue_bits(0, blockIdx.x + pg * gridDim.x);
         }
-        named_sync_n(1, TZ2_NPT);
-        int k = 0, prev_y0[TZ2_NST] = {-1000, -1000};
-        for (int w = blockIdx.x; w < n_work; w += gridDim.x, k++) {
-            const int s = k & 1, y0 = (w % TZ2_STRIPS) * TZ2_R;
-            const uint32_t par = (uint32_t)((k >> 1) & 1);
-            uint4 *sa = reinterpret_cast<uint4 *>(smem + Tz2Smem::off_a + s * TZ2_ABYTES);
-            unsigned short *wl = reinterpret_cast<unsigned short *>(smem + Tz2Smem::off_wl) + s * TZ2_WL;
-            const uint32_t *sb = reinterpret_cast<const uint32_t *>(smem + Tz2Smem::off_bits) + s * 2 * TZ2_BITW;
-            if (k >= 2) {
+        named_sync_n(1 + pg, TZ2_NPT);
+        int j = 0, prev_y0 = -1000;                         // j = index among the group's work items
+        for (int w = blockIdx.x + pg * gridDim.x; w < n_work; w += wstep, j++) {
+            const int y0 = (w % TZ2_STRIPS) * TZ2_R;
+            const uint32_t par = (uint32_t)(j & 1);         // stage s is used once per group item: its barriers flip every item
+            const uint32_t *sb = reinterpret_cast<const uint32_t *>(smem + Tz2Smem::off_bits) + (s * 2 + (j & 1)) * 2 * TZ2_BITW;
+            if (j >= 1) {
                 // ---- the MMAs of the previous item in this stage are done: put the background back
                 mbar_wait(&a_empty[s], par ^ 1u);
                 const int n_old = misc[s];
@@ -926,18 +931,18 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
                     const int e = wl[i], r = e / TZ2_H, px = e % TZ2_H;
                     sa[(px & 7) * TZ2_PS + r * TZ2_P + (px >> 3) + 1] = bgq;
                 }
-                const int zr = prev_y0[s] == 0 ? 0 : (prev_y0[s] + TZ2_R >= TZ2_H ? TZ2_H - (prev_y0[s] - 1) : -1);
+                const int zr = prev_y0 == 0 ? 0 : (prev_y0 + TZ2_R >= TZ2_H ? TZ2_H - (prev_y0 - 1) : -1);
                 if (zr >= 0)
                     for (int i = pt; i < 8 * 25; i += TZ2_NPT) sa[(i / 25) * TZ2_PS + zr * TZ2_P + (i % 25) + 1] = bgq;
             }
-            prev_y0[s] = y0;
-            named_sync_n(1, TZ2_NPT);                          // every producer thread has left the previous item
+            prev_y0 = y0;
+            named_sync_n(1 + pg, TZ2_NPT);                  // every thread of the group has left the previous item
             if (pt == 0) {
                 misc[s] = 0;
-                if (w + gridDim.x < n_work) issue_bits(k + 1, w + gridDim.x);               // prefetch the next item's bit rows
+                if (w + wstep < n_work) issue_bits(j + 1, w + wstep);                        // prefetch the group's next bit rows
             }
-            mbar_wait(&bits_full[s], par);
-            named_sync_n(1, TZ2_NPT);
+            mbar_wait((j & 1) ? &bits_full2[s] : &bits_full[s], (uint32_t)((j >> 1) & 1));
+            named_sync_n(1 + pg, TZ2_NPT);
             // ---- scan: pooled pixels whose 4 x 4 map patch holds a set bit
             const int r0 = max(2 * y0 - 3, 0), bits_w0 = ((r0 * 50) & ~15) >> 2;
             const uint32_t *smap = sb - bits_w0, *lmap = sb + TZ2_BITW - bits_w0;
@@ -968,7 +973,7 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
                 for (int kk = 0; kk < 8; kk++)
                     if ((orr >> (2 * kk)) & 0xFu) wl[atomicAdd(&misc[s], 1)] = (unsigned short)(r * TZ2_H + gx * 8 + kk);
             }
-            named_sync_n(1, TZ2_NPT);
+            named_sync_n(1 + pg, TZ2_NPT);
             // ---- exact conv1 + pool for the dirty pixels; zero rows outside the image (conv2's padding)
             {
                 const int n_new = misc[s];
@@ -1054,7 +1059,7 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[s]);
-            named_sync_n(2 + grp, 128);
+            named_sync_n(3 + grp, 128);
             // ---- pooling along y and the NHWC store of the strip's rows_valid / 2 output rows
             __nv_bfloat16 *dst = a.out + (size_t)item * (100 * 100 * 8) + (size_t)(y0 / 2) * 100 * 8;
             for (int idx = gt; idx < (rows_valid / 2) * 100; idx += 128) {
@@ -1070,7 +1075,7 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
                 }
                 *reinterpret_cast<uint4 *>(dst + (size_t)idx * 8) = o;
             }
-            named_sync_n(2 + grp, 128);                    // the stage may be overwritten by the group's next item
+            named_sync_n(3 + grp, 128);                    // the stage may be overwritten by the group's next item
         }
     }
     tc_fence_before();
