@@ -225,8 +225,7 @@ def gpu_arm(args, wl):
                 bg.raster("bits", out=maps)        # Battleground.restart builds a fresh Observation
         if policy is not None:
             policy.act(bg, maps)                   # forward on the current maps -> the policy ship's ("external") action row
-        bg.frame()                                 # scripted bots + step in one launch
-        bg.raster("bits", out=maps)
+        bg.frame(maps=maps)                        # scripted bots + step + observation maps: one fused launch (ofb_frame_bots)
         launches[0] += bg.launch_count + (policy.launch_count if policy is not None else 0) - n0
 
     stream = torch.cuda.current_stream(dev)
@@ -312,8 +311,8 @@ def _ncu_traffic():
 
 
 def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
-    """Dominant kernel of the arena workloads = the raster (it writes >95 % of the step's bytes):
-    achieved = algorithmic bytes (the tensor it must produce: N * 2 * W*H/8) / mean launch time.
+    """Dominant kernel of the arena workloads = the fused frame kernel (step + raster; the maps are >95 % of its bytes):
+    achieved = algorithmic bytes (88 B/ship + 64 B/live laser + the maps it must produce: N * 2 * W*H/8) / mean launch time.
     Policy workloads: the dominant kernel is the phase-folded upconv4 + argmax (tcgen05); achieved =
     its algorithmic FLOPs (2 * 400*400*72 per ship, Appendix B) / its mean launch time, against the
     measured bf16 tensor peak; the whole forward is reported beside it in dense-equivalent FLOPs."""
@@ -356,7 +355,9 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
                                   "frac_of_peak": 155.3e6 * n / (total * 1e-3) / 1e12 / tpeak},
                 "layers": layers}
     res = {}
-    for name, fn, nbytes in (("k_raster", lambda: bg.raster("bits", out=maps), maps.numel() * 4),
+    map_bytes = maps.numel() * 4
+    for name, fn, nbytes in (("k_frame", lambda: bg.generate_frame(maps=maps), lambda: bg.algorithmic_step_bytes() + map_bytes),
+                             ("k_raster", lambda: bg.raster("bits", out=maps), map_bytes),
                              ("k_step", lambda: bg.generate_frame(), bg.algorithmic_step_bytes)):
         ts = []
         for _ in range(5):                                # warm-up (module load, clocks)
@@ -374,7 +375,7 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
         ms = sum(a.elapsed_time(b) for a, b, _ in ts) / iters
         nb = sum(x[2] for x in ts) / iters
         res[name] = {"us": ms * 1e3, "bytes": nb, "gbs": nb / (ms * 1e-3) / 1e9}
-    dom = "k_raster"
+    dom = "k_frame"
     tr = _ncu_traffic().get("arena%d" % bg.n_arenas, {}) if bg.ships_number == 7 else {}
     return {"bound": "hbm", "kernel": dom, "achieved": res[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": res[dom]["gbs"] / peak,
@@ -382,7 +383,9 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
             "traffic": tr.get(dom),
             "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_ncu_full_*): below the algorithmic bytes because "
                             "the last ~50 MB of the maps are still dirty in the 126 MB L2 when the kernel ends", "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
-            "other_kernels": {"k_step": res["k_step"]}}
+            "what": "k_frame = fused step + raster (one persistent launch per frame); algorithmic bytes = 88 B/ship + 64 B/live laser "
+                    "+ the 2 x W*H/8-byte maps it must produce, per arena (SURVEY 8(d)); 32-ship x 2048-slot arenas run as k_step + k_raster",
+            "other_kernels": {"k_step": res["k_step"], "k_raster": res["k_raster"]}}
 
 
 def _max_over_ranks(dt, world, dev):
@@ -481,8 +484,7 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
     def tape_step(k):
         if rep.time >= 200:
             rep.restart()
-        rep.step_host(tape[k], obs2[k & 1], wait=False)     # queue H2D(k) | step(k) | D2H(k) on three streams
-        rep.raster("bits", out=maps)
+        rep.step_host(tape[k], obs2[k & 1], wait=False, maps=maps)   # queue H2D(k) | fused step + raster (k) | D2H(k) on three streams
 
     for k in range(3):
         tape_step(k)
@@ -502,7 +504,7 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
     if not bool(torch.isfinite(last).all()):
         raise SystemExit("e2e: observation heads did not arrive")
     out.update(value=N * world * steps / dt, steps=steps, closed_loop=closed, replay_matches_device_run=same,
-               what="action-tape replay: pinned host int16[N,S,4] -> H2D -> step -> raster (maps stay in HBM) -> D2H of "
+               what="action-tape replay: pinned host int16[N,S,4] -> H2D -> fused step + raster (ofb_frame_host_async; maps stay in HBM) -> D2H of "
                     "the float32[N,S,8] obs heads into pinned host memory, every frame; copies on their own streams "
                     "overlap neighbouring frames' kernels (ofb_step_host_async); final state checked against the "
                     "device-bot run the tape was recorded from; wall clock")

@@ -128,6 +128,18 @@ int ofb_bot_actions(const ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev,
 int ofb_step_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed, int64_t arena0, uint32_t step,
                   const int16_t *actions_dev, float *obs_out_dev, void *stream);
 
+/* Battleground.frame (lib/battleground.py:163-166) as ONE launch: generate_frame followed by the new Observation's
+ * ship_map / laser_map (lib/observation.py:79-95) written to maps_bits_dev in OFB_MAP_BITS format.  A persistent,
+ * warp-specialised kernel steps the arenas and rasterises them from shared memory, so the state is read once and the
+ * step's latency hides behind the raster's HBM writes.  Results are bit-identical to ofb_step / ofb_step_bots followed
+ * by ofb_raster(OFB_MAP_BITS); configurations whose per-arena laser list does not fit the shared-memory ring (e.g. 32
+ * ships x 2048 slots) run as those two launches. */
+int ofb_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *maps_bits_dev, void *stream);
+int ofb_frame_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed, int64_t arena0, uint32_t step,
+                   const int16_t *actions_dev, float *obs_out_dev, void *maps_bits_dev, void *stream);
+/* ofb_step_host_async with the fused frame kernel (maps stay in HBM at maps_bits_dev). */
+int ofb_frame_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *maps_bits_dev, void *stream);
+
 /* randint(0, W) x randint(0, H) spawn draws of lib/battleground.py:79-81,114. */
 int ofb_random_spawn(int64_t n_arenas, int n_ships, int width, int height, uint64_t seed, int64_t arena0,
                      uint32_t episode, int32_t *spawn_dev, void *stream);

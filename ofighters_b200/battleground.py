@@ -164,8 +164,16 @@ class BatchedBattleground:
             self.actions.copy_(acts)
         return self.actions
 
-    def generate_frame(self, actions=None):
-        """lib/battleground.py:153-160 for all arenas (K1).  Also refreshes ``obs_vec``."""
+    def _maps_arg(self, maps):
+        N, W, H = self.n_arenas, self.config.width, self.config.height
+        if tuple(maps.shape) != (N, 2, W * H // 32) or maps.dtype != torch.int32 or not maps.is_contiguous() \
+                or maps.device != self.device:
+            raise Exception("Invalid map buffer : expected {} {}.".format((N, 2, W * H // 32), torch.int32))
+        return _ptr(maps)
+
+    def generate_frame(self, actions=None, maps=None):
+        """lib/battleground.py:153-160 for all arenas (K1).  Also refreshes ``obs_vec``.  With ``maps`` (the "bits"
+        buffer of ``raster``) the step and the new observation maps are one fused launch (ofb_frame)."""
         if actions is None:
             actions = self.actions
         if actions.dtype != torch.int16 or not actions.is_contiguous() or actions.device != self.device:
@@ -173,19 +181,23 @@ class BatchedBattleground:
         if tuple(actions.shape) != (self.n_arenas, self.ships_number, 4):
             raise Exception("Invalid actions : expected shape {} but got shape {}.".format(
                 (self.n_arenas, self.ships_number, 4), tuple(actions.shape)))
-        _lib.check(self._lib.ofb_step(self._h, _ptr(actions), _ptr(self.obs_vec), self._stream()))
+        if maps is not None:
+            _lib.check(self._lib.ofb_frame(self._h, _ptr(actions), _ptr(self.obs_vec), self._maps_arg(maps), self._stream()))
+        else:
+            _lib.check(self._lib.ofb_step(self._h, _ptr(actions), _ptr(self.obs_vec), self._stream()))
         self.launch_count += 1
         self.time += 1
         self.total_steps += 1
 
-    def step_host(self, actions_host, obs_host=None, wait=True):
+    def step_host(self, actions_host, obs_host=None, wait=True, maps=None):
         """``generate_frame`` for a host-side bot loop: ``actions_host`` int16 [N,S,4] and
         ``obs_host`` float32 [N,S,8] are (pinned) HOST tensors -- the batched form of one
         ``Battleground.frame()`` with Python bots.  ``wait=True``: the copies ride the same stream as
         the step (ofb_step_host) and the call returns once ``obs_host`` holds the next observation
         heads.  ``wait=False``: pipelined (ofb_step_host_async) -- the call only queues the frame; the
         H2D / D2H copies overlap the kernels of neighbouring frames, ``obs_host`` is valid after
-        ``wait_host()``.  Meant for replaying an action tape (lib/record.py) or open-loop bots."""
+        ``wait_host()``.  Meant for replaying an action tape (lib/record.py) or open-loop bots.  ``maps`` (pipelined
+        form only): the frame also writes its observation maps there (fused launch, ofb_frame_host_async)."""
         if actions_host.dtype != torch.int16 or tuple(actions_host.shape) != (self.n_arenas, self.ships_number, 4) \
                 or actions_host.is_cuda or not actions_host.is_contiguous():
             raise Exception("Invalid actions : expected a contiguous host int16 tensor of shape {}.".format(
@@ -194,9 +206,15 @@ class BatchedBattleground:
                                      or tuple(obs_host.shape) != (self.n_arenas, self.ships_number, 8)):
             raise Exception("Invalid observation buffer : expected host float32 {}.".format(
                 (self.n_arenas, self.ships_number, 8)))
-        fn = self._lib.ofb_step_host if wait else self._lib.ofb_step_host_async
-        _lib.check(fn(self._h, C.c_void_p(actions_host.data_ptr()),
-                      C.c_void_p(obs_host.data_ptr()) if obs_host is not None else None, self._stream()))
+        obs_p = C.c_void_p(obs_host.data_ptr()) if obs_host is not None else None
+        if maps is not None:
+            if wait:
+                raise Exception("maps= is only supported by the pipelined form (wait=False).")
+            _lib.check(self._lib.ofb_frame_host_async(self._h, C.c_void_p(actions_host.data_ptr()), obs_p,
+                                                      self._maps_arg(maps), self._stream()))
+        else:
+            fn = self._lib.ofb_step_host if wait else self._lib.ofb_step_host_async
+            _lib.check(fn(self._h, C.c_void_p(actions_host.data_ptr()), obs_p, self._stream()))
         self.launch_count += 1
         self.time += 1
         self.total_steps += 1
@@ -212,22 +230,28 @@ class BatchedBattleground:
         live = int(self.state(("n_lasers",))["n_lasers"].sum().item())
         return 88 * self.n_arenas * self.ships_number + 64 * live
 
-    def frame(self):
-        """lib/battleground.py:163-166; the raster (absolute_state) is produced on demand by
-        ``raster()`` / consumed directly by the policy.  With the built-in device bots the
-        request_actions + generate_frame pair is one fused launch (ofb_step_bots): non-external ships
-        draw their action inside the step kernel, external ships (policy, host bots) use the rows
-        already present in ``self.actions``."""
+    def frame(self, maps=None):
+        """lib/battleground.py:163-166.  Without ``maps`` the raster (absolute_state) is produced on demand by
+        ``raster()``; with ``maps`` (the "bits" buffer of ``raster``) the frame writes the new Observation's
+        ship_map / laser_map there in the same launch (ofb_frame_bots / ofb_frame).  With the built-in device
+        bots request_actions + generate_frame (+ the maps) is one fused launch: non-external ships draw their
+        action inside the kernel, external ships (policy, host bots) use the rows already in ``self.actions``."""
         if isinstance(self.bot, ScriptedBots):
             self.bot._ensure_kinds(self)
-            _lib.check(self._lib.ofb_step_bots(self._h, 0, _ptr(self.bot._kinds_dev), self.bot.seed, self.arena0,
-                                               self.total_steps, _ptr(self.actions), _ptr(self.obs_vec), self._stream()))
+            if maps is not None:
+                _lib.check(self._lib.ofb_frame_bots(self._h, 0, _ptr(self.bot._kinds_dev), self.bot.seed, self.arena0,
+                                                    self.total_steps, _ptr(self.actions), _ptr(self.obs_vec),
+                                                    self._maps_arg(maps), self._stream()))
+            else:
+                _lib.check(self._lib.ofb_step_bots(self._h, 0, _ptr(self.bot._kinds_dev), self.bot.seed, self.arena0,
+                                                   self.total_steps, _ptr(self.actions), _ptr(self.obs_vec),
+                                                   self._stream()))
             self.launch_count += 1
             self.time += 1
             self.total_steps += 1
             return
         self.actions = self.request_actions()
-        self.generate_frame(self.actions)
+        self.generate_frame(self.actions, maps=maps)
 
     def tick(self):
         """One controller tick with the MAX_TIME rule of lib/ofighters.py:684-688: after

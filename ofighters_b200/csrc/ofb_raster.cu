@@ -14,17 +14,7 @@
 // expanded to the dense NHWC bf16 / u8 tensor Keras' predict() takes (qlearnIA_V2.py:208).
 #include <cuda_bf16.h>
 #include "ofb_common.cuh"
-
-__device__ __forceinline__ void set_bit_range(uint32_t *bits, unsigned b0, unsigned b1) {
-    const unsigned w0 = b0 >> 5, w1 = b1 >> 5;
-    const uint32_t lo = ~0u << (b0 & 31u), hi = (2u << (b1 & 31u)) - 1u;
-    if (w0 == w1) atomicOr(&bits[w0], lo & hi);
-    else {
-        atomicOr(&bits[w0], lo);
-        for (unsigned w = w0 + 1; w < w1; w++) atomicOr(&bits[w], ~0u);
-        atomicOr(&bits[w1], hi);
-    }
-}
+#include "ofb_raster_dev.cuh"
 
 __global__ void __launch_bounds__(256)
 k_raster(const char *__restrict__ state, const ArenaLayout lay, void *__restrict__ out, int format,
@@ -46,40 +36,12 @@ k_raster(const char *__restrict__ state, const ArenaLayout lay, void *__restrict
 
     // ships: one thread per (ship, row)
     const int rows = 2 * OFB_R_SHIP - 1;
-    for (int t = threadIdx.x; t < lay.S * rows; t += blockDim.x) {
-        const int i = t / rows, dr = t % rows - (OFB_R_SHIP - 1);
-        const unsigned sxy = ship[i].x;                      // x | y << 16 | alive << 31
-        if (!(sxy >> 31)) continue;
-        const int cx = (int)(sxy & 0xffffu), y = (int)((sxy >> 16) & 0x7fffu) + dr;
-        if (y < 0 || y >= H) continue;
-        int hw = -1;
-        for (int dc = 0; dc < OFB_R_SHIP; dc++)
-            if (dr * dr + dc * dc < OFB_R_SHIP * OFB_R_SHIP) hw = dc;
-        const int c0 = max(0, cx - hw), c1 = min(W - 1, cx + hw);
-        if (hw >= 0 && c0 <= c1) set_bit_range(bits, (unsigned)(y * W + c0), (unsigned)(y * W + c1));
-    }
-    // lasers: one thread per laser, <= 5x5 candidate pixels in fp64
+    for (int t = threadIdx.x; t < lay.S * rows; t += blockDim.x)
+        raster_ship_row(bits, W, H, ship[t / rows].x, t % rows - (OFB_R_SHIP - 1));
+    // lasers: one thread per laser
     for (int k = threadIdx.x; k < n; k += blockDim.x) {
         const double *lp = reinterpret_cast<const double *>(base + laser_off(lay.off_laser, k));
-        const double cx = lp[0], cy = lp[OFB_G_Y / 8], R = (double)OFB_R_LASER;
-        long long ulr = (long long)ceil(__dsub_rn(cy, R)), ulc = (long long)ceil(__dsub_rn(cx, R));
-        long long lrr = (long long)floor(__dadd_rn(cy, R)), lrc = (long long)floor(__dadd_rn(cx, R));
-        ulr = ulr < 0 ? 0 : ulr;
-        ulc = ulc < 0 ? 0 : ulc;
-        lrr = lrr > H - 1 ? H - 1 : lrr;
-        lrc = lrc > W - 1 ? W - 1 : lrc;
-        const double scr = __dsub_rn(cy, (double)ulr), scc = __dsub_rn(cx, (double)ulc);
-        for (long long i = 0; i <= lrr - ulr; i++) {
-            const double dr = __dsub_rn((double)i, scr);
-            const double dr2 = __dmul_rn(dr, dr);
-            for (long long j = 0; j <= lrc - ulc; j++) {
-                const double dc = __dsub_rn((double)j, scc);
-                if (__dadd_rn(dr2, __dmul_rn(dc, dc)) < R * R) {
-                    const unsigned b = (unsigned)((ulr + i) * W + (ulc + j));
-                    atomicOr(&bits[words + (b >> 5)], 1u << (b & 31u));
-                }
-            }
-        }
+        raster_laser(bits + words, W, H, lp[0], lp[OFB_G_Y / 8]);
     }
 
     if (format == OFB_MAP_BITS) {
@@ -128,6 +90,10 @@ k_raster(const char *__restrict__ state, const ArenaLayout lay, void *__restrict
             __stcs(&o[q], make_uint4(r[0], r[1], r[2], r[3]));
         }
     }
+}
+
+int ofb_raster_bits_launch(const ofb_arenas *h, void *out_dev, cudaStream_t st) {
+    return ofb_raster(h, out_dev, OFB_MAP_BITS, (void *)st);
 }
 
 extern "C" int ofb_raster(const ofb_arenas *h, void *out_dev, int format, void *stream) {

@@ -13,7 +13,9 @@
 //     and later lasers pass through it (laser.py:52-62);
 //   * ship i's shoot-rewards read ships j<i after their thrust and j>i before it (ship.py:158-177
 //     inside the loop of battleground.py:159-160).
+#include <stdlib.h>
 #include "ofb_common.cuh"
+#include "ofb_raster_dev.cuh"
 
 #define FULL 0xffffffffu
 
@@ -104,6 +106,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
 #define STEP_THREADS 128
 #define STEP_BAR_BYTES 128               // 4 warp mbarriers in front of the tiles
 
+// Post-step entity list of one arena, kept in shared memory for the fused frame kernel's raster warps (k_frame):
+//   +0   uint32 n            lasers in the list after the step (just-destroyed ones included, lib/observation.py:89-93)
+//   +16  uint32 ship_xy[SP]  x | y << 16 | alive << 31
+//   +16 + 4 * SP             double2 lxy[L]
+__host__ __device__ __forceinline__ int post_slot_bytes(int SP, int L) { return 16 + 4 * SP + 16 * L; }
+
+
 // One LPA-lane tile per arena.  The arena's header, ships and the LIVE prefix of its laser list reach shared memory
 // as bulk asynchronous copies counted on the warp's mbarrier:
 //   phase 0        header + ships + the first C0 = LPA/4 laser groups (issued before anything is known about the arena)
@@ -113,35 +122,25 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
 // Everything the loop reads comes from the shared-memory snapshot; results go straight to HBM (only the fields that
 // changed: x, y, meta of live lasers; dx, dy only for entries the compaction moved), so a tile never waits on a global
 // load inside the loop and the in-place compaction cannot race with its own reads.
-template <int LPA, int PIT, int MINB>
-__global__ void __launch_bounds__(STEP_THREADS, MINB)
-k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions,
-       float4 *__restrict__ obs_out, long long n_arenas, const BotSpec bots, const int tile_bytes) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int APW = 32 / LPA;
+template <int LPA, int PIT, bool POST>
+__device__ __forceinline__ void step_tile(char *__restrict__ state, const ArenaLayout &lay, const int2 *__restrict__ actions,
+                                          float4 *__restrict__ obs_out, const long long arena, const bool ok, const BotSpec &bots,
+                                          unsigned char *tb, uint64_t *mbar, const uint32_t ph, uint32_t &ph_used,
+                                          unsigned char *post) {
     constexpr int CH = PIT * LPA / 8;                    // laser groups staged per pass = PIT chunk iterations
     constexpr int C0 = LPA / 4;                          // groups copied with the header = 2 chunk iterations
     static_assert(PIT > 2, "the second copy is awaited before chunk iteration 2");
     constexpr unsigned GM = (LPA == 32) ? 0xffffffffu : ((1u << LPA) - 1u);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int g = lane / LPA, gl = lane % LPA;
     const unsigned gshift = g * LPA;
     const unsigned tmask = GM << gshift;                 // lanes of this arena's tile
-    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long arena = warp_global * APW + g;
-    const bool ok = arena < n_arenas;
     const bool leader = gl == 0;
     const int S = lay.S, L = lay.L, off_l = lay.off_laser;
     char *base = state + (ok ? arena : 0) * (long long)lay.stride;
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem) + warp;
-    unsigned char *tb = smem + STEP_BAR_BYTES + (warp * APW + g) * tile_bytes;
     const int G_cap = L >> 3;
+    double2 *post_lxy = reinterpret_cast<double2 *>(post + 16 + 4 * lay.SP);
 
-    if (lane == 0) {
-        mbar_init(mbar, APW);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
     if (leader) {
         if (ok) {
             const unsigned bytes0 = (unsigned)(off_l + OFB_GROUP_BYTES * min(C0, G_cap));
@@ -165,7 +164,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         if (kind == OFB_BOT_EXTERNAL) act = actions[arena * S + gl];
     }
 
-    mbar_wait(mbar, 0);
+    mbar_wait(mbar, ph & 1u);
     int n = ok ? reinterpret_cast<const int *>(tb)[HDR_NLASERS] : 0;     // the other header words are re-read at the end
     int dk = 0;                                          // kills (= deaths: hull is 1 and never restored) of this frame
     const int G_live = min((n + 7) >> 3, G_cap);
@@ -213,10 +212,11 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     // reference computes -- and the ballots that recover the list order run only when a mask is non-zero.
     int iters = (n + LPA - 1) / LPA;
     iters = __reduce_max_sync(FULL, iters);
+    ph_used = 2u + (uint32_t)max(0, (iters + PIT - 1) / PIT - 1);      // mbarrier phases this call completes (warp-uniform)
     int w = 0;                                           // compaction write cursor
     for (int it = 0; it < iters; it++) {
         const int pit = it % PIT;                        // chunk iteration within the pass
-        if (it == 2) mbar_wait(mbar, 1);
+        if (it == 2) mbar_wait(mbar, (ph + 1u) & 1u);
         else if (pit == 0 && it > 0) {                   // pass p: restage groups [p * CH, (p + 1) * CH)
             const int p = it / PIT;
             __syncwarp();
@@ -229,7 +229,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
                     bulk_g2s(tb + off_l, base + off_l + OFB_GROUP_BYTES * lo, bytes, mbar);
                 } else mbar_arrive(mbar);
             }
-            mbar_wait(mbar, (uint32_t)((p + 1) & 1));
+            mbar_wait(mbar, (ph + (uint32_t)p + 1u) & 1u);
         }
         const int k = it * LPA + gl;
         const unsigned char *lp = tb + off_l + ((pit * LPA + gl) >> 3) * OFB_GROUP_BYTES + (gl & 7) * 8;
@@ -285,6 +285,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
             *reinterpret_cast<double *>(gp) = x;
             *reinterpret_cast<double *>(gp + OFB_G_Y) = y;
             *reinterpret_cast<unsigned *>(base + laser_meta_off(off_l, pos)) = (meta & 0xffu) | (destroyed ? 0x100u : 0u);
+            if (POST) post_lxy[pos] = make_double2(x, y);
             if (pos != k) {
                 *reinterpret_cast<double *>(gp + OFB_G_DX) = dx;
                 *reinterpret_cast<double *>(gp + OFB_G_DY) = dy;
@@ -374,6 +375,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
             *reinterpret_cast<double *>(gp + OFB_G_DX) = ndx;
             *reinterpret_cast<double *>(gp + OFB_G_DY) = ndy;
             *reinterpret_cast<unsigned *>(base + laser_meta_off(off_l, slot)) = (unsigned)gl;
+            if (POST) post_lxy[slot] = make_double2(nlx, nly);
         }
         const int want = w + __popc(sh);
         n_shots = __popc(sh);
@@ -386,7 +388,9 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     if (is_ship) {
         ShipRec o;
         o.x = sx; o.y = sy; o.px = spx; o.py = spy; o.score = score; o.reward = rew; o.hull = hull; o.alive = alive;
-        reinterpret_cast<uint4 *>(base + lay.off_ship)[gl] = ship_pack(o);
+        const uint4 packed = ship_pack(o);
+        reinterpret_cast<uint4 *>(base + lay.off_ship)[gl] = packed;
+        if (POST) reinterpret_cast<unsigned *>(post + 16)[gl] = packed.x;
         if (obs_out) {                                   // lib/observation.py:113-123
             float4 *ob = obs_out + (arena * S + gl) * 2;
             ob[0] = make_float4((float)rew, 1.0f, (float)spx, (float)spy);
@@ -398,7 +402,132 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
         int4 *h4 = reinterpret_cast<int4 *>(base);
         h4[0] = make_int4(h0.x + 1, n, h0.z + dk, h0.w + dk);
         h4[1] = make_int4(h1.x + n_shots, h1.y + n_over, h1.z, h1.w + nt);
+        if (POST) *reinterpret_cast<unsigned *>(post) = (unsigned)n;
     }
+}
+
+template <int LPA, int PIT, int MINB>
+__global__ void __launch_bounds__(STEP_THREADS, MINB)
+k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions,
+       float4 *__restrict__ obs_out, long long n_arenas, const BotSpec bots, const int tile_bytes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int APW = 32 / LPA;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane / LPA;
+    const long long warp_global = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long arena = warp_global * APW + g;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem) + warp;
+    unsigned char *tb = smem + STEP_BAR_BYTES + (warp * APW + g) * tile_bytes;
+    if (lane == 0) {
+        mbar_init(mbar, APW);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t ph_used;
+    step_tile<LPA, PIT, false>(state, lay, actions, obs_out, arena, arena < n_arenas, bots, tb, mbar, 0u, ph_used, nullptr);
+}
+
+
+// ---- K1 + K2 fused: Battleground.frame (lib/battleground.py:163-166) = generate_frame + the new Observation ----------------
+// Persistent, warp-specialised, one CTA per SM over a contiguous range of arenas:
+//   * SW stepper warps run step_tile over the range (unit u = 32/LPA arenas -> warp u % SW) and leave every arena's
+//     post-step entity list in a ring of K shared-memory slots (full / empty mbarriers per slot);
+//   * NG raster groups of 8 warps consume the ring (group q takes arenas i = q mod NG, in order): zero one of the
+//     group's NBUF bitmap buffers, compose both disk maps from the slot (one thread per ship row / per laser pixel),
+//     hand the 2 * W*H/8 bytes to one bulk store, and move on while that store drains.
+// The step's latency chain (two dependent bulk loads + the fp64 loop) therefore hides behind the raster's HBM writes,
+// the arena state is read once per frame, and a frame is one launch.
+#define FR_RASTER_WARPS 8                // per raster group
+#define FR_BAR_BYTES 1024                // tile mbarriers [8] at +0, full[K] at +64, empty[K] behind them (K <= 56)
+#define FR_MAX_K 56
+
+template <int LPA, int PIT, int SW, int NG, int NBUF>
+__global__ void __launch_bounds__((SW + NG * FR_RASTER_WARPS) * 32, 1)
+k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions, float4 *__restrict__ obs_out,
+        long long n_arenas, const BotSpec bots, const int tile_bytes, const int slot_bytes, const int K,
+        uint32_t *__restrict__ maps_out) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int APW = 32 / LPA;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t *tile_bar = reinterpret_cast<uint64_t *>(smem);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 64), *empty = full + K;
+    unsigned char *tiles = smem + FR_BAR_BYTES;
+    unsigned char *slots = tiles + SW * APW * tile_bytes;
+    const int words = (lay.W * lay.H) >> 5;
+    const unsigned map_bytes = (unsigned)(2 * words * 4);
+    unsigned char *bitmaps = smem + ((FR_BAR_BYTES + SW * APW * tile_bytes + K * slot_bytes + 127) & ~127);
+    const long long a0 = n_arenas * blockIdx.x / gridDim.x, a1 = n_arenas * (blockIdx.x + 1) / gridDim.x;
+    const int cnt = (int)(a1 - a0);
+
+    if (threadIdx.x == 0) {
+        for (int w = 0; w < SW; w++) mbar_init(&tile_bar[w], APW);
+        for (int k = 0; k < K; k++) { mbar_init(&full[k], 1); mbar_init(&empty[k], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < SW) {
+        // ---------------- stepper warps
+        const int g = lane / LPA, gl = lane % LPA;
+        uint32_t ph = 0;
+        for (int u = warp; u * APW < cnt; u += SW) {
+            const int i = u * APW + g;
+            const bool ok = i < cnt;
+            const int slot = i % K, r = i / K;
+            if (ok && r > 0) mbar_wait(&empty[slot], (uint32_t)((r - 1) & 1));      // the raster has left arena i - K
+            __syncwarp();
+            uint32_t used;
+            step_tile<LPA, PIT, true>(state, lay, actions, obs_out, a0 + i, ok, bots, tiles + (warp * APW + g) * tile_bytes,
+                                      &tile_bar[warp], ph, used, slots + slot * slot_bytes);
+            ph += used;
+            __syncwarp();
+            if (ok && gl == 0) mbar_arrive(&full[slot]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // tile reads before the next unit's bulk copy
+        }
+        return;
+    }
+
+    // ---------------- raster groups
+    constexpr int RT = FR_RASTER_WARPS * 32;
+    const int q = (warp - SW) / FR_RASTER_WARPS;
+    const int rt = threadIdx.x - (SW + q * FR_RASTER_WARPS) * 32;
+    const int W = lay.W, H = lay.H, S = lay.S;
+    const int rows = 2 * OFB_R_SHIP - 1;
+    unsigned char *gbuf = bitmaps + (size_t)q * NBUF * map_bytes;
+    int use = 0;                                         // arenas this group has rasterised
+    for (int i = q; i < cnt; i += NG, use++) {
+        const int slot = i % K, r = i / K;
+        uint32_t *bits = reinterpret_cast<uint32_t *>(gbuf + (size_t)(use % NBUF) * map_bytes);
+        if (rt == 0 && use >= NBUF)                      // the store that last used this buffer has read it out
+            asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(RT) : "memory");
+        {
+            uint4 *b4 = reinterpret_cast<uint4 *>(bits);
+            for (int x = rt; x < (int)(map_bytes / 16); x += RT) b4[x] = make_uint4(0, 0, 0, 0);
+        }
+        asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(RT) : "memory");
+        mbar_wait(&full[slot], (uint32_t)(r & 1));
+        const unsigned char *post = slots + slot * slot_bytes;
+        const int n = (int)*reinterpret_cast<const unsigned *>(post);
+        const unsigned *sxy = reinterpret_cast<const unsigned *>(post + 16);
+        const double2 *lxy = reinterpret_cast<const double2 *>(post + 16 + 4 * lay.SP);
+        // laser rows from the top thread down, ship rows from thread 0 up: both kinds start in the first round
+        for (int t = RT - 1 - rt; t < n * 5; t += RT) {
+            const double2 c = lxy[t / 5];
+            raster_laser_row(bits + words, W, H, c.x, c.y, t % 5);
+        }
+        for (int t = rt; t < S * rows; t += RT) raster_ship_row(bits, W, H, sxy[t / rows], t % rows - (OFB_R_SHIP - 1));
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(RT) : "memory");
+        if (rt == 0) {
+            char *dst = reinterpret_cast<char *>(maps_out) + (a0 + i) * (long long)map_bytes;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(bits)), "r"(map_bytes)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            mbar_arrive(&empty[slot]);
+        }
+    }
+    if (rt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 // lanes per arena: the smallest tile that holds the ships, widened while the batch is too small to fill the GPU
@@ -467,6 +596,101 @@ extern "C" int ofb_step_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_d
     return launch_step(h, actions_dev, obs_out_dev, b, stream);
 }
 
+// ---- fused frame: launch ------------------------------------------------------------------------------------------
+int ofb_raster_bits_launch(const ofb_arenas *h, void *out_dev, cudaStream_t st);     // ofb_raster.cu
+
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+template <int LPA, int PIT, int SW, int NG, int NBUF>
+static int launch_frame_t(ofb_arenas *h, const int2 *act, float4 *obs, const BotSpec &bots, uint32_t *maps, cudaStream_t st,
+                          int n_sm, int smem_max, bool *fits) {
+    constexpr int APW = 32 / LPA;
+    const int tile = step_tile_bytes(h->lay, LPA, PIT);
+    const int slot = post_slot_bytes(h->lay.SP, h->lay.L);
+    const int map_bytes = (h->lay.W * h->lay.H / 32) * 8;
+    const int fixed = FR_BAR_BYTES + SW * APW * tile + 128 + NG * NBUF * map_bytes;
+    int K = (smem_max - fixed) / slot;
+    K = min(K, min(FR_MAX_K, env_int("OFB_FRAME_K", 3 * SW * APW)));
+    // Every slot must have ONE producer (stepper warp, tile) and ONE consumer (raster group) for the phase parities of
+    // its full / empty barriers to be sound: arenas i and i + K share a slot, so K is a multiple of both the arenas in
+    // flight per stepper round (SW * APW) and the number of raster groups.
+    int unit = SW * APW;
+    while (unit % NG) unit += SW * APW;
+    K -= K % unit;
+    *fits = K >= unit && (map_bytes % 16) == 0;
+    if (!*fits) return OFB_OK;
+    const int smem = fixed + K * slot;
+    static thread_local int configured = 0;
+    if (smem > configured) {
+        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_frame<LPA, PIT, SW, NG, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = smem;
+    }
+    const unsigned grid = (unsigned)(h->n_arenas < (int64_t)n_sm ? h->n_arenas : (int64_t)n_sm);
+    k_frame<LPA, PIT, SW, NG, NBUF><<<grid, (SW + NG * FR_RASTER_WARPS) * 32, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas,
+                                                                                         bots, tile, slot, K, maps);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+// One launch when the arena's post-step list fits the shared-memory ring (default arenas); otherwise (e.g. 32 ships x 2048
+// laser slots) the same result as two launches, K1 then K2.
+static int launch_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, const BotSpec &bots, void *maps_dev,
+                        void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int2 *act = reinterpret_cast<const int2 *>(actions_dev);
+    float4 *obs = reinterpret_cast<float4 *>(obs_out_dev);
+    uint32_t *maps = reinterpret_cast<uint32_t *>(maps_dev);
+    if (h->n_arenas == 0) return OFB_OK;
+    static thread_local int n_sm = 0, smem_max = 0, dev_cached = -1;
+    if (dev_cached != h->device) {
+        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));
+        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+        dev_cached = h->device;
+    }
+    const int S = h->lay.S;
+    const int lpa = env_int("OFB_FRAME_LPA", S <= 16 ? 16 : 32);
+    const int sw = env_int("OFB_FRAME_SW", 4), ng = env_int("OFB_FRAME_NG", 2), nbuf = env_int("OFB_FRAME_NBUF", 2);
+    bool fits = false;
+    int rc = OFB_OK;
+    if (!env_int("OFB_FRAME_SPLIT", 0) && lpa >= S) {
+#define FR_CASE(L_, P_, W_, G_, B_) \
+        if (lpa == L_ && sw == W_ && ng == G_ && nbuf == B_) \
+            rc = launch_frame_t<L_, P_, W_, G_, B_>(h, act, obs, bots, maps, st, n_sm, smem_max, &fits);
+        FR_CASE(8, 6, 4, 2, 2) FR_CASE(8, 6, 4, 1, 3) FR_CASE(8, 6, 4, 3, 1)
+        FR_CASE(16, 4, 4, 2, 2) FR_CASE(16, 4, 4, 1, 3) FR_CASE(16, 4, 4, 3, 1) FR_CASE(16, 4, 8, 2, 2)
+        FR_CASE(32, 3, 4, 2, 2) FR_CASE(32, 3, 4, 1, 3) FR_CASE(32, 3, 4, 3, 1) FR_CASE(32, 3, 8, 2, 2)
+#undef FR_CASE
+        if (rc != OFB_OK) return rc;
+    }
+    if (fits) return OFB_OK;
+    rc = launch_step(h, actions_dev, obs_out_dev, bots, stream);
+    if (rc != OFB_OK) return rc;
+    return ofb_raster_bits_launch(h, maps_dev, st);
+}
+
+extern "C" int ofb_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *maps_bits_dev, void *stream) {
+    if (!h || !actions_dev || !maps_bits_dev) { ofb_set_error("ofb_frame: null argument"); return OFB_E_ARG; }
+    BotSpec none = {};
+    return launch_frame(h, actions_dev, obs_out_dev, none, maps_bits_dev, stream);
+}
+
+extern "C" int ofb_frame_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed, int64_t arena0, uint32_t step,
+                              const int16_t *actions_dev, float *obs_out_dev, void *maps_bits_dev, void *stream) {
+    if (!h || !maps_bits_dev || bot_kind < 0 || (bot_kind > OFB_BOT_STRESS && bot_kind != OFB_BOT_EXTERNAL)) {
+        ofb_set_error("ofb_frame_bots: bad argument");
+        return OFB_E_ARG;
+    }
+    if (!actions_dev && (kinds_dev || bot_kind == OFB_BOT_EXTERNAL)) {
+        ofb_set_error("ofb_frame_bots: ships of kind 'external' need an actions buffer");
+        return OFB_E_ARG;
+    }
+    BotSpec b = {1, bot_kind, kinds_dev, seed, (long long)arena0, step};
+    return launch_frame(h, actions_dev, obs_out_dev, b, maps_bits_dev, stream);
+}
+
 // Host-buffer form of ofb_step: the drop-in call for a host-side bot loop (Battleground.frame with
 // Python bots).  actions_host / obs_host should be pinned; everything is asynchronous on `stream`.
 extern "C" int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream) {
@@ -491,7 +715,7 @@ extern "C" int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *
 // obs_host is valid after ofb_host_wait(); actions_host may be reused after the same call (or after the next
 // ofb_step_host_async returns two frames later).
 int ofb_pipe_init(ofb_arenas *h);
-extern "C" int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream) {
+static int step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *maps_bits_dev, void *stream) {
     if (!h || !actions_host) { ofb_set_error("ofb_step_host_async: null argument"); return OFB_E_ARG; }
     int rc = ofb_pipe_init(h);
     if (rc != OFB_OK) return rc;
@@ -503,7 +727,8 @@ extern "C" int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, f
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
     OFB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_h2d[i], 0));
     if (obs_host && h->host_seq >= 2) OFB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_d2h[i], 0));   // pipe_obs[i] has left
-    rc = ofb_step(h, h->pipe_actions[i], obs_host ? h->pipe_obs[i] : nullptr, st);
+    rc = maps_bits_dev ? ofb_frame(h, h->pipe_actions[i], obs_host ? h->pipe_obs[i] : nullptr, maps_bits_dev, st)
+                       : ofb_step(h, h->pipe_actions[i], obs_host ? h->pipe_obs[i] : nullptr, st);
     if (rc != OFB_OK) return rc;
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_step[i], st));
     if (obs_host) {
@@ -513,6 +738,15 @@ extern "C" int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, f
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
     h->host_seq++;
     return OFB_OK;
+}
+
+extern "C" int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream) {
+    return step_host_async(h, actions_host, obs_host, nullptr, stream);
+}
+// Same pipeline with the fused frame kernel: the frame's observation maps (OFB_MAP_BITS) are written to maps_bits_dev.
+extern "C" int ofb_frame_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *maps_bits_dev, void *stream) {
+    if (!maps_bits_dev) { ofb_set_error("ofb_frame_host_async: null maps buffer"); return OFB_E_ARG; }
+    return step_host_async(h, actions_host, obs_host, maps_bits_dev, stream);
 }
 
 // Block until every copy queued by ofb_step_host_async has completed (obs_host readable, actions_host reusable).

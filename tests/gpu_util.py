@@ -26,3 +26,22 @@ class GpuEngine:
 
     def raster_bits(self):
         return self.bg.raster("bits").cpu().numpy().view(np.uint32)
+
+
+class GpuEngineFused(GpuEngine):
+    """Same protocol through the fused frame kernel (ofb_frame): every step also writes the observation maps."""
+
+    def __init__(self, spawn, lcap=0, **kw):
+        super().__init__(spawn, lcap=lcap, **kw)
+        self.maps = self.bg.raster("bits")
+
+    def step(self, actions):
+        self.bg.generate_frame(torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int16)).to(self.bg.device),
+                               maps=self.maps)
+
+    def reset(self, spawn):
+        super().reset(spawn)
+        self.bg.raster("bits", out=self.maps)
+
+    def raster_bits(self):
+        return self.maps.cpu().numpy().view(np.uint32)

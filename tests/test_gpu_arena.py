@@ -28,6 +28,62 @@ def test_cuda_path_matches_reference_trace(path):
     assert bad == []
 
 
+@pytest.mark.parametrize("path", tu.golden_files(), ids=lambda p: p.split("/")[-1][:-4])
+def test_fused_frame_matches_reference_trace(path):
+    """The fused frame kernel (ofb_frame: step + observation maps in one launch) against the real reference's traces."""
+    from tests.gpu_util import GpuEngineFused
+    gold = tu.load_golden(path)
+    bad = tu.run_engine(GpuEngineFused, gold, n_copies=5)
+    assert bad == []
+
+
+@pytest.mark.parametrize("N,S,kind,T,lcap", [(4096, 7, "random", 230, 0), (20000, 7, "random", 60, 0), (700, 7, "turret", 120, 0),
+                                             (333, 12, "random", 90, 0), (150, 32, "stress", 40, 2048),
+                                             (3000, 32, "stress", 40, 0), (5, 1, "random", 30, 0)])
+def test_fused_frame_equals_step_then_raster(N, S, kind, T, lcap):
+    _fused_vs_split(N, S, kind, T, lcap)
+
+
+@pytest.mark.parametrize("knobs", [dict(OFB_FRAME_K="19"), dict(OFB_FRAME_K="9"), dict(OFB_FRAME_LPA="32", OFB_FRAME_SW="8"),
+                                   dict(OFB_FRAME_LPA="8", OFB_FRAME_NG="3", OFB_FRAME_NBUF="1"),
+                                   dict(OFB_FRAME_NG="1", OFB_FRAME_NBUF="3", OFB_FRAME_K="56")],
+                         ids=lambda d: ",".join("%s=%s" % (k[10:], v) for k, v in d.items()))
+def test_fused_frame_ring_geometries(knobs, monkeypatch):
+    """The shared-memory ring of the fused kernel under other geometries (slots, stepper warps, raster groups)."""
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    _fused_vs_split(9000, 7, "random", 50, 0)
+
+
+def _fused_vs_split(N, S, kind, T, lcap):
+    """ofb_frame_bots == ofb_step_bots + ofb_raster bit for bit (state, observation heads, maps), incl. the episode
+    restart, arena ranges longer than the shared-memory ring, saturated laser lists (overflow counted identically) and
+    the two-launch form taken when an arena's list does not fit the ring."""
+    from ofighters_b200 import ArenaConfig, BatchedBattleground
+    mk = lambda: BatchedBattleground(N, ships={kind: S}, config=ArenaConfig(laser_cap=lcap), seed=4242, arena0=17)
+    a, b = mk(), mk()
+    maps_a = a.raster("bits")
+    maps_b = torch.zeros_like(maps_a)
+    for t in range(T):
+        if t == 200 or (T < 200 and t == T // 2):
+            a.restart()
+            b.restart()
+        a.frame()
+        a.raster("bits", out=maps_a)
+        b.frame(maps=maps_b)
+        if t % 9 == 0 or t == T - 1:
+            assert torch.equal(maps_a, maps_b), "maps t %d" % t
+            assert torch.equal(a.obs_vec, b.obs_vec), "obs t %d" % t
+    sa, sb = a.state(), b.state()
+    live = torch.arange(a.laser_cap, device=a.device)[None, :] < sa["n_lasers"].long()[:, None]
+    for k in sa:
+        if k.startswith("laser_"):
+            assert torch.equal(torch.where(live, sa[k], torch.zeros_like(sa[k])),
+                               torch.where(live, sb[k], torch.zeros_like(sb[k]))), k
+        else:
+            assert torch.equal(sa[k], sb[k]), k
+
+
 def _compare_states(g, c, tag):
     from oracle.step_c import ArenasC  # noqa: F401  (oracle = checker only)
     ga = g.arrays()
@@ -179,10 +235,13 @@ def test_host_tape_replay_matches_c_restatement(wait):
         tape[t].copy_(torch.from_numpy(a))
         c.step(a)
         want_obs[t] = c.obs_vec()
-    maps = None
+    maps = bg.raster("bits")
     for t in range(T):
-        bg.step_host(tape[t], obs[t], wait=wait)
-        maps = bg.raster("bits", out=maps)
+        if wait:
+            bg.step_host(tape[t], obs[t], wait=True)
+            bg.raster("bits", out=maps)
+        else:                                            # pipelined copies around the fused frame kernel
+            bg.step_host(tape[t], obs[t], wait=False, maps=maps)
     bg.wait_host()
     torch.cuda.synchronize()
     _compare_states(g, c, "after host tape")
