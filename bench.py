@@ -356,7 +356,10 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
                 "layers": layers}
     res = {}
     map_bytes = maps.numel() * 4
-    for name, fn, nbytes in (("k_frame", lambda: bg.generate_frame(maps=maps), lambda: bg.algorithmic_step_bytes() + map_bytes),
+    bg.restart()
+    for _ in range(40):                                   # back to the steady-state laser population of a running episode
+        bg.frame(maps=maps)
+    for name, fn, nbytes in (("k_frame", lambda: bg.frame(maps=maps), lambda: bg.algorithmic_step_bytes() + map_bytes),
                              ("k_raster", lambda: bg.raster("bits", out=maps), map_bytes),
                              ("k_step", lambda: bg.generate_frame(), bg.algorithmic_step_bytes)):
         ts = []
@@ -381,8 +384,8 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
             "frac": res[dom]["gbs"] / peak,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
             "traffic": tr.get(dom),
-            "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_ncu_full_*): below the algorithmic bytes because "
-                            "the last ~50 MB of the maps are still dirty in the 126 MB L2 when the kernel ends", "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
+            "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_ncu_full_frame*_v4.md): below the algorithmic bytes "
+                            "at 4096 arenas because the last ~50 MB of the maps are still dirty in the 126 MB L2 when the kernel ends", "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
             "what": "k_frame = fused step + raster (one persistent launch per frame); algorithmic bytes = 88 B/ship + 64 B/live laser "
                     "+ the 2 x W*H/8-byte maps it must produce, per arena (SURVEY 8(d)); 32-ship x 2048-slot arenas run as k_step + k_raster",
             "other_kernels": {"k_step": res["k_step"], "k_raster": res["k_raster"]}}

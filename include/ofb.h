@@ -140,6 +140,10 @@ int ofb_frame_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64
 /* ofb_step_host_async with the fused frame kernel (maps stay in HBM at maps_bits_dev). */
 int ofb_frame_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *maps_bits_dev, void *stream);
 
+/* Debug aid for profiling the fused frame kernel: when buf_dev != NULL every following ofb_frame* launch writes
+ * per-warp-role cycle counters to it (int64 [grid][32][8]); NULL switches it off. */
+int ofb_debug_frame_prof(long long *buf_dev);
+
 /* randint(0, W) x randint(0, H) spawn draws of lib/battleground.py:79-81,114. */
 int ofb_random_spawn(int64_t n_arenas, int n_ships, int width, int height, uint64_t seed, int64_t arena0,
                      uint32_t episode, int32_t *spawn_dev, void *stream);

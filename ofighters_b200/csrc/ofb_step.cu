@@ -109,8 +109,10 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32
 // Post-step entity list of one arena, kept in shared memory for the fused frame kernel's raster warps (k_frame):
 //   +0   uint32 n            lasers in the list after the step (just-destroyed ones included, lib/observation.py:89-93)
 //   +16  uint32 ship_xy[SP]  x | y << 16 | alive << 31
-//   +16 + 4 * SP             double2 lxy[L]
-__host__ __device__ __forceinline__ int post_slot_bytes(int SP, int L) { return 16 + 4 * SP + 16 * L; }
+//   +16 + 4 * SP             double2 lxy[PC]   the first PC = min(L, 64) lasers; the raster reads the rare ones beyond
+//                                              from the arena's block in HBM (written by the same CTA just before)
+#define FR_POST_CAP 64
+__host__ __device__ __forceinline__ int post_slot_bytes(int SP, int PC) { return 16 + 4 * SP + 16 * PC; }
 
 
 // One LPA-lane tile per arena.  The arena's header, ships and the LIVE prefix of its laser list reach shared memory
@@ -122,11 +124,24 @@ __host__ __device__ __forceinline__ int post_slot_bytes(int SP, int L) { return 
 // Everything the loop reads comes from the shared-memory snapshot; results go straight to HBM (only the fields that
 // changed: x, y, meta of live lasers; dx, dy only for entries the compaction moved), so a tile never waits on a global
 // load inside the loop and the in-place compaction cannot race with its own reads.
+// phase 0 of a tile: header + ships + the first LPA/4 laser groups of `arena` -> tb, counted on mbar
+template <int LPA>
+__device__ __forceinline__ void step_tile_load0(char *__restrict__ state, const ArenaLayout &lay, const long long arena, const bool ok,
+                                                unsigned char *tb, uint64_t *mbar) {
+    if ((threadIdx.x & 31) % LPA == 0) {
+        if (ok) {
+            const unsigned bytes0 = (unsigned)(lay.off_laser + OFB_GROUP_BYTES * min(LPA / 4, lay.L >> 3));
+            mbar_expect_tx(mbar, bytes0);
+            bulk_g2s(tb, state + arena * (long long)lay.stride, bytes0, mbar);
+        } else mbar_arrive(mbar);
+    }
+}
+
 template <int LPA, int PIT, bool POST>
 __device__ __forceinline__ void step_tile(char *__restrict__ state, const ArenaLayout &lay, const int2 *__restrict__ actions,
                                           float4 *__restrict__ obs_out, const long long arena, const bool ok, const BotSpec &bots,
                                           unsigned char *tb, uint64_t *mbar, const uint32_t ph, uint32_t &ph_used,
-                                          unsigned char *post) {
+                                          unsigned char *post, const int post_cap) {
     constexpr int CH = PIT * LPA / 8;                    // laser groups staged per pass = PIT chunk iterations
     constexpr int C0 = LPA / 4;                          // groups copied with the header = 2 chunk iterations
     static_assert(PIT > 2, "the second copy is awaited before chunk iteration 2");
@@ -141,13 +156,7 @@ __device__ __forceinline__ void step_tile(char *__restrict__ state, const ArenaL
     const int G_cap = L >> 3;
     double2 *post_lxy = reinterpret_cast<double2 *>(post + 16 + 4 * lay.SP);
 
-    if (leader) {
-        if (ok) {
-            const unsigned bytes0 = (unsigned)(off_l + OFB_GROUP_BYTES * min(C0, G_cap));
-            mbar_expect_tx(mbar, bytes0);
-            bulk_g2s(tb, base, bytes0, mbar);
-        } else mbar_arrive(mbar);
-    }
+    if (!POST) step_tile_load0<LPA>(state, lay, arena, ok, tb, mbar);      // k_frame issues it one unit ahead
 
     // ---- while the state is in flight: the action row, or the scripted bot's random words (they need nothing from the
     //      arena; the kind byte is loaded first and interpreted after the Philox rounds)
@@ -285,7 +294,7 @@ __device__ __forceinline__ void step_tile(char *__restrict__ state, const ArenaL
             *reinterpret_cast<double *>(gp) = x;
             *reinterpret_cast<double *>(gp + OFB_G_Y) = y;
             *reinterpret_cast<unsigned *>(base + laser_meta_off(off_l, pos)) = (meta & 0xffu) | (destroyed ? 0x100u : 0u);
-            if (POST) post_lxy[pos] = make_double2(x, y);
+            if (POST && pos < post_cap) post_lxy[pos] = make_double2(x, y);
             if (pos != k) {
                 *reinterpret_cast<double *>(gp + OFB_G_DX) = dx;
                 *reinterpret_cast<double *>(gp + OFB_G_DY) = dy;
@@ -375,7 +384,7 @@ __device__ __forceinline__ void step_tile(char *__restrict__ state, const ArenaL
             *reinterpret_cast<double *>(gp + OFB_G_DX) = ndx;
             *reinterpret_cast<double *>(gp + OFB_G_DY) = ndy;
             *reinterpret_cast<unsigned *>(base + laser_meta_off(off_l, slot)) = (unsigned)gl;
-            if (POST) post_lxy[slot] = make_double2(nlx, nly);
+            if (POST && slot < post_cap) post_lxy[slot] = make_double2(nlx, nly);
         }
         const int want = w + __popc(sh);
         n_shots = __popc(sh);
@@ -424,7 +433,7 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
     }
     __syncwarp();
     uint32_t ph_used;
-    step_tile<LPA, PIT, false>(state, lay, actions, obs_out, arena, arena < n_arenas, bots, tb, mbar, 0u, ph_used, nullptr);
+    step_tile<LPA, PIT, false>(state, lay, actions, obs_out, arena, arena < n_arenas, bots, tb, mbar, 0u, ph_used, nullptr, 0);
 }
 
 
@@ -438,19 +447,19 @@ k_step(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__
 // The step's latency chain (two dependent bulk loads + the fp64 loop) therefore hides behind the raster's HBM writes,
 // the arena state is read once per frame, and a frame is one launch.
 #define FR_RASTER_WARPS 8                // per raster group
-#define FR_BAR_BYTES 1024                // tile mbarriers [8] at +0, full[K] at +64, empty[K] behind them (K <= 56)
-#define FR_MAX_K 56
+#define FR_BAR_BYTES 1024                // tile mbarriers [SW <= 32] at +0, full[K] at +256, empty[K] behind them (K <= 48)
+#define FR_MAX_K 48
 
 template <int LPA, int PIT, int SW, int NG, int NBUF>
 __global__ void __launch_bounds__((SW + NG * FR_RASTER_WARPS) * 32, 1)
 k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions, float4 *__restrict__ obs_out,
-        long long n_arenas, const BotSpec bots, const int tile_bytes, const int slot_bytes, const int K,
-        uint32_t *__restrict__ maps_out) {
+        long long n_arenas, const BotSpec bots, const int tile_bytes, const int slot_bytes, const int post_cap, const int K,
+        uint32_t *__restrict__ maps_out, long long *__restrict__ prof) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int APW = 32 / LPA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t *tile_bar = reinterpret_cast<uint64_t *>(smem);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 64), *empty = full + K;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + 256), *empty = full + K;
     unsigned char *tiles = smem + FR_BAR_BYTES;
     unsigned char *slots = tiles + SW * APW * tile_bytes;
     const int words = (lay.W * lay.H) >> 5;
@@ -459,30 +468,37 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
     const long long a0 = n_arenas * blockIdx.x / gridDim.x, a1 = n_arenas * (blockIdx.x + 1) / gridDim.x;
     const int cnt = (int)(a1 - a0);
 
-    if (threadIdx.x == 0) {
-        for (int w = 0; w < SW; w++) mbar_init(&tile_bar[w], APW);
-        for (int k = 0; k < K; k++) { mbar_init(&full[k], 1); mbar_init(&empty[k], 1); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if ((int)threadIdx.x < SW) mbar_init(&tile_bar[threadIdx.x], APW);
+    else if ((int)threadIdx.x - SW < 2 * K) mbar_init(&full[threadIdx.x - SW], 1);      // full[K] and empty[K] are contiguous
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
     if (warp < SW) {
         // ---------------- stepper warps
         const int g = lane / LPA, gl = lane % LPA;
         uint32_t ph = 0;
+        long long t_wait = 0, t_begin = clock64();
+        unsigned char *tb = tiles + (warp * APW + g) * tile_bytes;
         for (int u = warp; u * APW < cnt; u += SW) {
             const int i = u * APW + g;
             const bool ok = i < cnt;
             const int slot = i % K, r = i / K;
+            step_tile_load0<LPA>(state, lay, a0 + i, ok, tb, &tile_bar[warp]);
+            const long long tw = clock64();
             if (ok && r > 0) mbar_wait(&empty[slot], (uint32_t)((r - 1) & 1));      // the raster has left arena i - K
             __syncwarp();
+            t_wait += clock64() - tw;
             uint32_t used;
-            step_tile<LPA, PIT, true>(state, lay, actions, obs_out, a0 + i, ok, bots, tiles + (warp * APW + g) * tile_bytes,
-                                      &tile_bar[warp], ph, used, slots + slot * slot_bytes);
+            step_tile<LPA, PIT, true>(state, lay, actions, obs_out, a0 + i, ok, bots, tb, &tile_bar[warp], ph, used,
+                                      slots + slot * slot_bytes, post_cap);
             ph += used;
             __syncwarp();
             if (ok && gl == 0) mbar_arrive(&full[slot]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // tile reads before the next unit's bulk copy
+        }
+        if (prof && lane == 0) {                         // debug: cycles this stepper warp spent in total / waiting for a slot
+            prof[((long long)blockIdx.x * 32 + warp) * 8 + 0] = clock64() - t_begin;
+            prof[((long long)blockIdx.x * 32 + warp) * 8 + 1] = t_wait;
         }
         return;
     }
@@ -494,31 +510,76 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
     const int W = lay.W, H = lay.H, S = lay.S;
     const int rows = 2 * OFB_R_SHIP - 1;
     unsigned char *gbuf = bitmaps + (size_t)q * NBUF * map_bytes;
+    for (int x = rt; x < NBUF * (int)(map_bytes / 16); x += RT) reinterpret_cast<uint4 *>(gbuf)[x] = make_uint4(0, 0, 0, 0);
+    // this thread's first ship-row and laser-row items are the same for every arena
+    const int s_i = rt / rows, s_dr = rt % rows - (OFB_R_SHIP - 1);
+    const int l_t = RT - 1 - rt, l_k = l_t / 5, l_i = l_t % 5;       // laser rows from the top thread down
+    // Re-zeroing: a buffer comes back after NBUF arenas of this group.  Each thread remembers the (at most two + two) words
+    // its items of that arena touched and clears just those; an arena with more items than threads asks for a full wipe.
+    int zs[NBUF], zl[NBUF];
+    bool zfull[NBUF];
+#pragma unroll
+    for (int j = 0; j < NBUF; j++) { zs[j] = -1; zl[j] = -1; zfull[j] = false; }
     int use = 0;                                         // arenas this group has rasterised
+    long long pt[6] = {0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+#define FR_PROF(j) do { if (prof) { const long long now = clock64(); pt[j] += now - tp; tp = now; } } while (0)
     for (int i = q; i < cnt; i += NG, use++) {
+        long long tp = prof ? clock64() : 0;
         const int slot = i % K, r = i / K;
         uint32_t *bits = reinterpret_cast<uint32_t *>(gbuf + (size_t)(use % NBUF) * map_bytes);
         if (rt == 0 && use >= NBUF)                      // the store that last used this buffer has read it out
             asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(NBUF - 1) : "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(RT) : "memory");
-        {
+        FR_PROF(0);
+        if (zfull[0]) {
             uint4 *b4 = reinterpret_cast<uint4 *>(bits);
             for (int x = rt; x < (int)(map_bytes / 16); x += RT) b4[x] = make_uint4(0, 0, 0, 0);
+        } else {
+            if (zs[0] >= 0) { bits[zs[0]] = 0u; bits[zs[0] + 1] = 0u; }            // (word + 1 may belong to the laser map: also zero)
+            if (zl[0] >= 0) { bits[zl[0]] = 0u; if (zl[0] + 1 < 2 * words) bits[zl[0] + 1] = 0u; }
         }
         asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(RT) : "memory");
+        FR_PROF(1);
         mbar_wait(&full[slot], (uint32_t)(r & 1));
+        FR_PROF(2);
         const unsigned char *post = slots + slot * slot_bytes;
         const int n = (int)*reinterpret_cast<const unsigned *>(post);
         const unsigned *sxy = reinterpret_cast<const unsigned *>(post + 16);
         const double2 *lxy = reinterpret_cast<const double2 *>(post + 16 + 4 * lay.SP);
-        // laser rows from the top thread down, ship rows from thread 0 up: both kinds start in the first round
-        for (int t = RT - 1 - rt; t < n * 5; t += RT) {
-            const double2 c = lxy[t / 5];
-            raster_laser_row(bits + words, W, H, c.x, c.y, t % 5);
+        int ws = -1, wl = -1;
+        if (l_t < n * 5) {
+            double2 c;
+            if (l_k < post_cap) c = lxy[l_k];
+            else {                                       // beyond the slot: the stepper's own store to the arena block
+                const double *lp = reinterpret_cast<const double *>(state + (a0 + i) * (long long)lay.stride + laser_off(lay.off_laser, l_k));
+                c = make_double2(lp[0], lp[OFB_G_Y / 8]);
+            }
+            wl = raster_laser_row(bits + words, W, H, c.x, c.y, l_i);
+            if (wl >= 0) wl += words;
         }
-        for (int t = rt; t < S * rows; t += RT) raster_ship_row(bits, W, H, sxy[t / rows], t % rows - (OFB_R_SHIP - 1));
+        if (rt < S * rows) ws = raster_ship_row(bits, W, H, sxy[s_i], s_dr);
+        const bool many = n * 5 > RT || S * rows > RT;   // (group-uniform) more items than threads: generic loops, full wipe later
+        if (many) {
+            for (int t = l_t + RT; t < n * 5; t += RT) {
+                const int k = t / 5;
+                double2 c;
+                if (k < post_cap) c = lxy[k];
+                else {
+                    const double *lp = reinterpret_cast<const double *>(state + (a0 + i) * (long long)lay.stride + laser_off(lay.off_laser, k));
+                    c = make_double2(lp[0], lp[OFB_G_Y / 8]);
+                }
+                raster_laser_row(bits + words, W, H, c.x, c.y, t % 5);
+            }
+            for (int t = rt + RT; t < S * rows; t += RT) raster_ship_row(bits, W, H, sxy[t / rows], t % rows - (OFB_R_SHIP - 1));
+        }
+#pragma unroll
+        for (int j = 0; j + 1 < NBUF; j++) { zs[j] = zs[j + 1]; zl[j] = zl[j + 1]; zfull[j] = zfull[j + 1]; }
+        zs[NBUF - 1] = ws; zl[NBUF - 1] = wl; zfull[NBUF - 1] = many;
+        FR_PROF(3);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync %0, %1;" ::"r"(q + 1), "n"(RT) : "memory");
+        FR_PROF(4);
         if (rt == 0) {
             char *dst = reinterpret_cast<char *>(maps_out) + (a0 + i) * (long long)map_bytes;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(bits)), "r"(map_bytes)
@@ -528,6 +589,13 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
         }
     }
     if (rt == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (prof && rt == 0) {                               // debug: cycles of this group's leader per phase of the loop
+        long long *o = prof + ((long long)blockIdx.x * 32 + SW + q) * 8;
+        o[0] = clock64() - t_begin;
+        for (int j = 0; j < 5; j++) o[1 + j] = pt[j];
+        o[6] = use;
+    }
+#undef FR_PROF
 }
 
 // lanes per arena: the smallest tile that holds the ships, widened while the batch is too small to fill the GPU
@@ -604,16 +672,21 @@ static int env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// debug: when set (ofb_debug_frame_prof), k_frame writes per-warp-role cycle counters there: long long [grid][32][8]
+static long long *g_frame_prof = nullptr;
+extern "C" int ofb_debug_frame_prof(long long *buf_dev) { g_frame_prof = buf_dev; return OFB_OK; }
+
 template <int LPA, int PIT, int SW, int NG, int NBUF>
 static int launch_frame_t(ofb_arenas *h, const int2 *act, float4 *obs, const BotSpec &bots, uint32_t *maps, cudaStream_t st,
                           int n_sm, int smem_max, bool *fits) {
     constexpr int APW = 32 / LPA;
     const int tile = step_tile_bytes(h->lay, LPA, PIT);
-    const int slot = post_slot_bytes(h->lay.SP, h->lay.L);
+    const int post_cap = min(h->lay.L, env_int("OFB_FRAME_POSTCAP", FR_POST_CAP));
+    const int slot = post_slot_bytes(h->lay.SP, post_cap);
     const int map_bytes = (h->lay.W * h->lay.H / 32) * 8;
     const int fixed = FR_BAR_BYTES + SW * APW * tile + 128 + NG * NBUF * map_bytes;
     int K = (smem_max - fixed) / slot;
-    K = min(K, min(FR_MAX_K, env_int("OFB_FRAME_K", 3 * SW * APW)));
+    K = min(K, min(FR_MAX_K, env_int("OFB_FRAME_K", 4 * SW * APW)));
     // Every slot must have ONE producer (stepper warp, tile) and ONE consumer (raster group) for the phase parities of
     // its full / empty barriers to be sound: arenas i and i + K share a slot, so K is a multiple of both the arenas in
     // flight per stepper round (SW * APW) and the number of raster groups.
@@ -630,7 +703,7 @@ static int launch_frame_t(ofb_arenas *h, const int2 *act, float4 *obs, const Bot
     }
     const unsigned grid = (unsigned)(h->n_arenas < (int64_t)n_sm ? h->n_arenas : (int64_t)n_sm);
     k_frame<LPA, PIT, SW, NG, NBUF><<<grid, (SW + NG * FR_RASTER_WARPS) * 32, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas,
-                                                                                         bots, tile, slot, K, maps);
+                                                                                         bots, tile, slot, post_cap, K, maps, g_frame_prof);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }
@@ -659,9 +732,9 @@ static int launch_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_ou
 #define FR_CASE(L_, P_, W_, G_, B_) \
         if (lpa == L_ && sw == W_ && ng == G_ && nbuf == B_) \
             rc = launch_frame_t<L_, P_, W_, G_, B_>(h, act, obs, bots, maps, st, n_sm, smem_max, &fits);
-        FR_CASE(8, 6, 4, 2, 2) FR_CASE(8, 6, 4, 1, 3) FR_CASE(8, 6, 4, 3, 1)
-        FR_CASE(16, 4, 4, 2, 2) FR_CASE(16, 4, 4, 1, 3) FR_CASE(16, 4, 4, 3, 1) FR_CASE(16, 4, 8, 2, 2)
-        FR_CASE(32, 3, 4, 2, 2) FR_CASE(32, 3, 4, 1, 3) FR_CASE(32, 3, 4, 3, 1) FR_CASE(32, 3, 8, 2, 2)
+        FR_CASE(8, 6, 8, 2, 2) FR_CASE(8, 6, 8, 1, 3)
+        FR_CASE(16, 4, 4, 2, 2) FR_CASE(16, 4, 8, 1, 3) FR_CASE(16, 4, 4, 3, 1)
+        FR_CASE(32, 3, 4, 2, 2) FR_CASE(32, 3, 8, 2, 2) FR_CASE(32, 3, 12, 1, 3)
 #undef FR_CASE
         if (rc != OFB_OK) return rc;
     }
