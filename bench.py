@@ -11,6 +11,7 @@ Workloads (BASELINE.json configs):
     arena4096    configs[1]: 4096 default arenas (7 ships), random bots, step + raster   [default]
     stress       configs[3]: 16384 arenas x 32 ships, max fire rate, step + raster
     policy       configs[2]: 65536 arenas, ship 0 policy-driven (conv+dense bi-head forward, bf16)
+    policy7      configs[2] variant: 16384 arenas, all 7 ships policy-driven (trunk once per arena, heads x7)
     sharded1m    configs[4]: 131072 arenas per GPU, policy forward, per-episode stat all-reduce
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB memset)
@@ -42,6 +43,9 @@ WORKLOADS = {
     "policy": dict(n=65536, ships=7, bot="random", lcap=0, policy=1,
                    desc="configs[2]: 65536 default arenas, ship 0 driven by the bi-head policy forward (bf16), "
                         "ships 1-6 random bots"),
+    "policy7": dict(n=16384, ships=7, bot="random", lcap=0, policy=7,
+                    desc="configs[2] variant of SURVEY 8(d): 16384 default arenas, ALL 7 ships policy-driven "
+                         "(trunk once per arena, heads x7 -> 114688 forwards per frame), bf16"),
     "sharded1m": dict(n=131072, ships=7, bot="random", lcap=0, policy=1,
                       desc="configs[4]: 131072 arenas per GPU (1M over 8), policy forward, per-episode stats all-reduce"),
 }
@@ -202,6 +206,7 @@ def gpu_arm(args, wl):
     max_time = 200
 
     ships = {wl["bot"]: S} if not wl["policy"] else {"QlearnIA": wl["policy"], wl["bot"]: S - wl["policy"]}
+    ships = {k: v for k, v in ships.items() if v > 0}
     bg = BatchedBattleground(N, ships=ships, config=ArenaConfig(laser_cap=wl["lcap"]), device=dev, seed=SEED,
                              arena0=rank * N)
     policy = None
@@ -327,14 +332,15 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
     stream = torch.cuda.current_stream(dev)
     if policy is not None:
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        vec = bg.obs_vec[:, 0, :].contiguous()
+        P = wl["policy"]                                  # policy ships per arena: the trunk runs once per arena, the heads P times
+        vec = bg.obs_vec[:, :P, :].contiguous().reshape(-1, 8)
         policy.profile(True)
         for _ in range(3):
-            policy.forward_argmax(maps, vec)
+            policy.forward_argmax(maps, vec, P)
         prof = policy.profile(False)                      # {layer: ms per forward of the whole batch}
         n = bg.n_arenas
         fl = {"trunk12": 2 * (23.04e6 + 23.04e6), "conv3": 2 * 5.76e6, "conv4": 2 * 1.44e6, "dense1": 2 * 0.5e6,
-              "heads": 2 * (5.1e3 + 62.5e3 + 45e3 + 720e3 + 800), "up3": 2 * 11.52e6, "up4": 2 * 11.52e6, "argmax": 0.0}
+              "heads": P * 2 * (5.1e3 + 62.5e3 + 45e3 + 720e3 + 800), "up3": P * 2 * 11.52e6, "up4": P * 2 * 11.52e6, "argmax": 0.0}
         layers = {k: {"ms": v, "alg_tflops": fl.get(k, 0.0) * n / (v * 1e-3) / 1e12 if v > 0 else None}
                   for k, v in prof.items()}
         dom = max(prof, key=prof.get)
@@ -345,14 +351,16 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
         return {"bound": "tensor", "kernel": kname.get(dom, dom), "achieved": layers[dom]["alg_tflops"], "peak": tpeak,
                 "unit": "TFLOP/s", "frac": layers[dom]["alg_tflops"] / tpeak,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM loop)" if peaks else "fallback",
-                "traffic": (per_item[kname.get(dom, dom).split(" ")[0]] * min(n, policy.max_ships)
+                "traffic": (per_item[kname.get(dom, dom).split(" ")[0]] * min(n * P, policy.max_ships)
                             if kname.get(dom, dom).split(" ")[0] in per_item else None),
-                "us_per_launch": prof[dom] * 1e3 / max(1, -(-n // policy.max_ships)),
+                "us_per_launch": prof[dom] * 1e3 / max(1, -(-n * P // policy.max_ships)),
                 "note": "algorithmic FLOPs of the layer (Appendix B MACs x 2) / its device time; these layers have 8 or fewer "
                         "channels, so the tensor pipe is bound by operand reads and the kernels by HBM / epilogue, not by math",
-                "whole_forward": {"ms": total, "forwards_per_s": n / (total * 1e-3),
-                                  "dense_equiv_tflops": 155.3e6 * n / (total * 1e-3) / 1e12,
-                                  "frac_of_peak": 155.3e6 * n / (total * 1e-3) / 1e12 / tpeak},
+                "whole_forward": {"ms": total, "forwards_per_s": n * P / (total * 1e-3), "policy_ships_per_arena": P,
+                                  "dense_equiv_tflops": 155.3e6 * n * P / (total * 1e-3) / 1e12,
+                                  "frac_of_peak": 155.3e6 * n * P / (total * 1e-3) / 1e12 / tpeak,
+                                  "note": "dense-equivalent = 155.3 MFLOP per ship-forward (Appendix B), the trunk counted once per SHIP "
+                                          "as the reference's batch-1 predict does; the library runs it once per arena"},
                 "layers": layers}
     res = {}
     map_bytes = maps.numel() * 4

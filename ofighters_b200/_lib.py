@@ -43,6 +43,12 @@ class OfbPolicyWeights(C.Structure):
                 ("output1", OfbDenseWeights), ("updense1", OfbDenseWeights), ("upconv", OfbConvWeights * 4)]
 
 
+class OfbTrainConfig(C.Structure):
+    _fields_ = [("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+                ("bn_momentum", C.c_float), ("bn_eps", C.c_float), ("bn_unbiased_moving_var", C.c_int32),
+                ("max_batch", C.c_int32), ("reserved", C.c_int32 * 8)]
+
+
 ENGINE_TENSOR, ENGINE_CUDA_CORE = 0, 1
 
 
@@ -105,6 +111,20 @@ def load():
     lib.ofb_policy_debug_tap.argtypes = [vp, i32, i64, vp, vp]
     lib.ofb_policy_profile.argtypes = [vp, i32, vp]
     lib.ofb_policy_profile.restype = i32
+    lib.ofb_train_default_config.argtypes = [C.POINTER(OfbTrainConfig)]
+    lib.ofb_train_default_config.restype = None
+    lib.ofb_trainer_create.argtypes = [vp, i64, C.POINTER(OfbTrainConfig), i32, C.POINTER(vp)]
+    lib.ofb_trainer_destroy.argtypes = [vp]
+    lib.ofb_trainer_fit.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.ofb_trainer_forward.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.ofb_trainer_td_targets.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, i32, vp, vp, vp]
+    lib.ofb_trainer_get_weights.argtypes = [vp, vp, vp]
+    lib.ofb_trainer_get_grads.argtypes = [vp, vp, vp]
+    lib.ofb_trainer_steps.argtypes = [vp]
+    lib.ofb_trainer_steps.restype = i64
+    for name in ("ofb_trainer_create", "ofb_trainer_destroy", "ofb_trainer_fit", "ofb_trainer_forward",
+                 "ofb_trainer_td_targets", "ofb_trainer_get_weights", "ofb_trainer_get_grads"):
+        getattr(lib, name).restype = i32
     for name in ("ofb_policy_create", "ofb_policy_destroy", "ofb_policy_set_engine", "ofb_policy_forward",
                  "ofb_policy_write_actions", "ofb_policy_pack_image", "ofb_policy_debug_tap"):
         getattr(lib, name).restype = i32

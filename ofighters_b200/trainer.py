@@ -1,0 +1,282 @@
+"""B200 counterpart of the reference's ``Trainer`` update path (agents/qlearnIA_V2.py:47-299) and its epsilon
+schedules (lib/epsilon.py:18-86) -- SURVEY.md 8(f) rank 1.
+
+    reference                                             here
+    ----------------------------------------------------  ---------------------------------------------------
+    Trainer(learning_rate, epsilon, batch_size, memory)   TrainerB200(weights=None, learning_rate=..., ...)
+    .remember(state, iaction, ipointer, reward, next, d)  .remember(...)   state = (maps_bits [2,5000], vec [8])
+    .replay(batch_size) -> History (loss)                 .replay(batch_size) -> History-like (.history["loss"])
+    .get_best_action(obs, rand=True)                      .get_best_action(maps_bits, vec, rand=True)
+    .decay_epsilon()                                      .decay_epsilon()
+    model.fit(x, y, epochs=1, batch_size=B)               .fit(maps_bits, vec, target_act, target_ptr)
+    Epsilon_cos(period) / Epsilon_decay()                 Epsilon_cos / Epsilon_decay (same arithmetic)
+
+``predict`` runs on the inference engine (PolicyB200: tcgen05 kernels, BN folded, moving statistics); ``fit`` runs
+libofb's training kernels (fp32, BatchNormalization on batch statistics, Keras' Adam) through include/ofb_train.h and
+then refreshes the inference engine's weights.  There is no torch / CPU fallback for either.
+"""
+import ctypes as C
+import math
+import random
+from collections import deque
+from types import SimpleNamespace
+
+import torch
+
+from . import _lib
+from .policy import WEIGHT_SPEC, PolicyB200, keras_default_weights
+
+
+def cos_P_u(time, period_time, amplitude):
+    """lib/epsilon.py:18-19"""
+    return amplitude * ((math.cos((time / period_time) * 2 * math.pi) + 1) / 2)
+
+
+def reverse_cos_P_u(value, period_time, amplitude):
+    """lib/epsilon.py:27-28"""
+    return period_time * math.acos(((2 * value) / amplitude) - 1) / (2 * math.pi)
+
+
+class Epsilon_cos:
+    """lib/epsilon.py:36-59"""
+
+    def __init__(self, period):
+        self.t = 0
+        self.amplitude = 1
+        self.period = period
+        self.epsilon = cos_P_u(self.t, self.period, self.amplitude)
+
+    def next(self):
+        self.t = (self.t + 1) % self.period
+        self.epsilon = cos_P_u(self.t, self.period, self.amplitude)
+        return self.epsilon
+
+    def get(self):
+        return self.epsilon
+
+    def set(self, value):
+        if value > 1.0 or value < 0.0:
+            raise Exception("Value must me in range [0,1]")
+        self.epsilon = value
+        self.t = reverse_cos_P_u(value, self.period, self.amplitude)
+
+
+class Epsilon_decay:
+    """lib/epsilon.py:62-86"""
+
+    def __init__(self):
+        self.epsilon = 1
+        self.epsilon_min = 0.01
+        self.decay = 0.99990
+
+    def next(self):
+        if self.epsilon > self.epsilon_min:
+            self.epsilon *= self.decay
+        return self.epsilon
+
+    def get(self):
+        return self.epsilon
+
+    def set(self, value):
+        if value > 1.0 or value < 0.0:
+            raise Exception("Value must me in range [0,1]")
+        self.epsilon = value
+
+
+def flatten_weights(weights):
+    """Keras-layout dict -> the flat fp32 array of include/ofb_train.h (WEIGHT_SPEC order)."""
+    parts = []
+    for name, shape in WEIGHT_SPEC:
+        if name not in weights:
+            raise Exception("missing weight " + name)
+        t = torch.as_tensor(weights[name]).detach().to("cpu", torch.float32).contiguous()
+        if tuple(t.shape) != tuple(shape):
+            raise Exception("weight {} : expected shape {} but got shape {}.".format(name, shape, tuple(t.shape)))
+        parts.append(t.reshape(-1))
+    return torch.cat(parts).contiguous()
+
+
+def unflatten_weights(flat):
+    out, off = {}, 0
+    for name, shape in WEIGHT_SPEC:
+        n = 1
+        for d in shape:
+            n *= d
+        out[name] = flat[off:off + n].reshape(shape).clone()
+        off += n
+    return out
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+
+
+class TrainerB200:
+    def __init__(self, weights=None, name=None, learning_rate=0.001, epsilon=None, batch_size=30, memory_size=400,
+                 device=None, seed=0, max_ships=64, bn_unbiased_moving_var=False):
+        """Defaults are the reference constructor's (qlearnIA_V2.py:48); the module-level TRAINER is built with
+        ``learning_rate=0.0001, epsilon=Epsilon_cos(period=110*400), batch_size=8`` (:304-310)."""
+        if not torch.cuda.is_available():
+            raise _lib.OfbError("TrainerB200 needs a CUDA device: fit and predict are hand-written sm_100a kernels "
+                                "and have no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self._lib = _lib.load()
+        self.state_size = 320008
+        self.action_size = 2
+        self.gamma = 0.9                                 # :51
+        self.epsilon = epsilon if epsilon is not None else Epsilon_decay()
+        self.learning_rate = learning_rate
+        self.memory = deque(maxlen=memory_size)
+        self.batch_size = batch_size
+        self.name = name
+        self.ptr_values = None
+        self.act_values = None
+        self.launch_count = 0
+        weights = weights if weights is not None else keras_default_weights(seed)
+        flat = flatten_weights(weights)
+        cfg = _lib.OfbTrainConfig()
+        self._lib.ofb_train_default_config(C.byref(cfg))
+        cfg.lr = float(learning_rate)
+        cfg.max_batch = max(int(batch_size), 1)
+        cfg.bn_unbiased_moving_var = 1 if bn_unbiased_moving_var else 0
+        h = C.c_void_p()
+        _lib.check(self._lib.ofb_trainer_create(C.c_void_p(flat.data_ptr()), flat.numel(), C.byref(cfg),
+                                                self.device.index or 0, C.byref(h)))
+        self._h = h
+        self.max_batch = cfg.max_batch
+        self.model = PolicyB200(weights, device=self.device, max_ships=max_ships)   # the predict() side
+        self._loss = torch.zeros(3, dtype=torch.float32, device=self.device)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            try:
+                self._lib.ofb_trainer_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ weights
+    def get_weights(self):
+        flat = torch.empty(len_flat(), dtype=torch.float32)
+        _lib.check(self._lib.ofb_trainer_get_weights(self._h, C.c_void_p(flat.data_ptr()), self._stream()))
+        return unflatten_weights(flat)
+
+    def get_grads(self):
+        flat = torch.empty(len_flat(), dtype=torch.float32)
+        _lib.check(self._lib.ofb_trainer_get_grads(self._h, C.c_void_p(flat.data_ptr()), self._stream()))
+        return unflatten_weights(flat)
+
+    @property
+    def steps(self):
+        return int(self._lib.ofb_trainer_steps(self._h))
+
+    def sync_model(self):
+        """Hand the trained weights to the inference engine (BN folded from the moving statistics)."""
+        self.model.load_weights(self.get_weights())
+
+    # ------------------------------------------------------------------ fit / predict
+    def _check_batch(self, maps_bits, vec):
+        B = maps_bits.shape[0]
+        if maps_bits.dtype != torch.int32 or tuple(maps_bits.shape) != (B, 2, 5000) or not maps_bits.is_contiguous() \
+                or maps_bits.device != self.device:
+            raise Exception("Invalid maps : expected contiguous int32 [B, 2, 5000] bit maps on {}.".format(self.device))
+        if B < 1 or B > self.max_batch:
+            raise Exception("Invalid batch : {} samples but the trainer was sized for {}.".format(B, self.max_batch))
+        vec = vec.to(device=self.device, dtype=torch.float32).contiguous().reshape(-1, 8)
+        if vec.shape[0] != B:
+            raise Exception("Invalid vector input : expected shape {} but got shape {}.".format((B, 8), tuple(vec.shape)))
+        return B, vec
+
+    def fit(self, maps_bits, vec, target_act, target_ptr, sync_model=True):
+        """``model.fit(x=[img, vec], y=[act, ptr], epochs=1, batch_size=B)`` (:286): one Adam step.  Returns the loss
+        tensor (total, mse(output1), mse(output2)) of the batch before the update (device, float32 [3])."""
+        B, vec = self._check_batch(maps_bits, vec)
+        target_act = target_act.to(device=self.device, dtype=torch.float32).contiguous()
+        target_ptr = target_ptr.to(device=self.device, dtype=torch.float32).contiguous()
+        if tuple(target_act.shape) != (B, 2) or target_ptr.numel() != B * 160000:
+            raise Exception("Invalid targets : expected shapes {} and {}.".format((B, 2), (B, 400, 400, 1)))
+        _lib.check(self._lib.ofb_trainer_fit(self._h, _ptr(maps_bits), _ptr(vec), _ptr(target_act), _ptr(target_ptr), B,
+                                             _ptr(self._loss), self._stream()))
+        self.launch_count += self.KERNELS_PER_FIT
+        loss = self._loss.clone()
+        if sync_model:
+            self.sync_model()
+        return loss
+
+    KERNELS_PER_FIT = 96          # forward 33 + backward 62 + Adam (memsets not counted)
+
+    def forward_train(self, maps_bits, vec):
+        """Training-mode predictions (batch statistics) -- what ``fit`` differentiates.  -> act [B,2], ptr [B,400,400]."""
+        B, vec = self._check_batch(maps_bits, vec)
+        act = torch.empty((B, 2), dtype=torch.float32, device=self.device)
+        ptr = torch.empty((B, 400, 400), dtype=torch.float32, device=self.device)
+        _lib.check(self._lib.ofb_trainer_forward(self._h, _ptr(maps_bits), _ptr(vec), B, _ptr(act), _ptr(ptr), self._stream()))
+        return act, ptr
+
+    def predict(self, maps_bits, vec):
+        """``model.predict`` on bit maps: (act [B,2], ptr [B,400,400]) from the inference engine."""
+        r = self.model.forward(maps_bits, vec, 1, want_ptr=True)
+        return r["act"], r["ptr"]
+
+    # ------------------------------------------------------------------ reference surface
+    def decay_epsilon(self):
+        self.epsilon.next()
+
+    def random_play(self):
+        """qlearnIA_V2.py:317-321"""
+        iaction = random.randint(0, self.action_size - 1)
+        return [iaction, (random.randint(0, 400 - 1), random.randint(0, 400 - 1))]
+
+    def get_best_action(self, maps_bits, vec, rand=True):
+        """:199-235 for one observation: maps_bits [2,5000] (or [1,2,5000]), vec [8] -> [iaction, (x, y)]."""
+        if rand and random.random() <= self.epsilon.get():
+            return self.random_play()
+        r = self.model.forward(maps_bits.reshape(1, 2, 5000).contiguous(), vec.reshape(1, 8), 1, want_ptr=True)
+        self.act_values = r["act"][0]
+        self.ptr_values = r["ptr"][0]
+        xy = r["xy"][0].tolist()
+        return [int(r["iaction"][0]), (int(xy[0]), int(xy[1]))]
+
+    def remember(self, state, iaction, ipointer, reward, next_state, done):
+        """:237-238.  ``state`` / ``next_state`` = (maps_bits int32 [2,5000], vec float32 [8]) device tensors."""
+        self.memory.append([state, iaction, ipointer, reward, next_state, done])
+
+    def replay(self, batch_size):
+        """:240-287.  Targets from predictions on obs and next_obs; like the reference, the fitted INPUTS are the
+        next observations (``inputs1[i] = img_input`` is evaluated after img_input was rebuilt from next_obs, :281-282)."""
+        batch_size = min(batch_size, len(self.memory))
+        if batch_size < 1:
+            raise Exception("replay on an empty memory")
+        minibatch = random.sample(self.memory, batch_size)
+        dev = self.device
+        maps_o = torch.stack([m[0][0] for m in minibatch]).to(dev).contiguous()
+        vec_o = torch.stack([m[0][1] for m in minibatch]).to(dev).contiguous()
+        maps_n = torch.stack([m[4][0] for m in minibatch]).to(dev).contiguous()
+        vec_n = torch.stack([m[4][1] for m in minibatch]).to(dev).contiguous()
+        iaction = torch.tensor([int(m[1]) for m in minibatch], dtype=torch.int32, device=dev)
+        pointer = torch.tensor([[int(m[2][0]), int(m[2][1])] for m in minibatch], dtype=torch.int32, device=dev)
+        reward = torch.tensor([float(m[3]) for m in minibatch], dtype=torch.float32, device=dev)
+        done = torch.tensor([1 if m[5] else 0 for m in minibatch], dtype=torch.uint8, device=dev)
+        act_o, ptr_o = self.predict(maps_o, vec_o)
+        act_n, ptr_n = self.predict(maps_n, vec_n)
+        _lib.check(self._lib.ofb_trainer_td_targets(_ptr(act_o), _ptr(ptr_o), _ptr(act_n), _ptr(ptr_n), _ptr(iaction),
+                                                    _ptr(pointer), _ptr(reward), _ptr(done), float(self.gamma), batch_size,
+                                                    _ptr(act_o), _ptr(ptr_o), self._stream()))
+        self.launch_count += 1
+        loss = self.fit(maps_n, vec_n, act_o, ptr_o)
+        host = loss.cpu().tolist()
+        return SimpleNamespace(history={"loss": [host[0]], "output1_loss": [host[1]], "output2_loss": [host[2]]})
+
+
+def len_flat():
+    n = 0
+    for _, shape in WEIGHT_SPEC:
+        k = 1
+        for d in shape:
+            k *= d
+        n += k
+    return n

@@ -1,0 +1,147 @@
+"""Parity of the Q-learning update kernels (include/ofb_train.h) with the torch-autograd oracle -- runs on the B200 box.
+
+Tolerances (fp32 on both sides, different summation orders; sums over up to 1.28 M elements):
+  * training-mode predictions and losses: 2e-4 relative to the tensor's max;
+  * gradients, per tensor, against the oracle run in fp64: max |difference| <= 2e-3 * max |gradient|;
+  * weights after Adam steps: the first steps move every weight by ~lr * sign(g), so elements whose gradient is below
+    the noise of the sum may step the other way -- the update must match within 5 % of lr on at least 99 % of every
+    tensor's elements and never differ by more than 2.2 * lr * steps;
+  * BatchNormalization moving statistics: 1e-5 absolute.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _arena_batch(B, frames=35, seed=11):
+    from ofighters_b200 import BatchedBattleground
+    bg = BatchedBattleground(B, ships={"random": 7}, seed=seed)
+    for _ in range(frames):
+        bg.frame()
+    maps = bg.raster("bits")
+    vec = bg.obs_vec[:, 0, :].contiguous()
+    return bg, maps, vec
+
+
+def _dense_image(maps):
+    b = maps.cpu().numpy().view(np.uint32)
+    n = b.shape[0]
+    img = np.unpackbits(b.view(np.uint8).reshape(n, 2, -1), axis=2, bitorder="little").reshape(n, 2, 400, 400)
+    return torch.from_numpy(img.transpose(0, 2, 3, 1).astype(np.float32))
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("B", [8, 3])
+def test_fit_matches_the_autograd_oracle(B):
+    from oracle import policy_torch as po
+    from oracle import policy_train_torch as pt
+    from ofighters_b200.trainer import TrainerB200
+    w = po.init_weights(4, randomize_bn=True)
+    _, maps, vec = _arena_batch(B)
+    g = torch.Generator().manual_seed(B)
+    ta = torch.randn((B, 2), generator=g) * 3
+    tp = torch.randn((B, 400, 400), generator=g) * 0.5
+    tr = TrainerB200(weights=w, learning_rate=1e-4, batch_size=8)
+    img, vec_h = _dense_image(maps), vec.cpu()
+
+    # training-mode forward
+    act, ptr = tr.forward_train(maps, vec)
+    oact, optr, _ = pt.forward_train(w, img, vec_h)
+    assert _rel(act.cpu(), oact) <= 2e-4 and _rel(ptr.cpu(), optr) <= 2e-4
+
+    # one fit: loss, gradients, moving statistics, weights.  The checker runs in fp64: torch's own fp32 backward is the
+    # noisier of the two (e.g. conv2/kernel: 8e-3 absolute vs 5e-5 for the kernels here, scripts/train_debug.py).
+    wd = {k: v.double() for k, v in w.items()}
+    imgd, vecd, tad, tpd = img.double(), vec_h.double(), ta.double(), tp.double()
+    opt = pt.KerasAdam(lr=1e-4)
+    (olosses, ograds, _) = pt.loss_and_grads(wd, imgd, vecd, tad, tpd)
+    loss = tr.fit(maps, vec, ta.cuda(), tp.cuda()).cpu()
+    pt.fit(wd, opt, imgd, vecd, tad, tpd)
+    assert np.allclose(loss.numpy(), np.array(olosses), rtol=2e-4)
+    grads = tr.get_grads()
+    # a conv bias in front of a BatchNormalization has an analytically zero gradient (the batch mean removes it): both sides
+    # hold rounding noise there, so the scale is the layer's kernel gradient
+    zero_grad = [k for k in ograds if k.endswith("/bias") and "conv" in k and k != "upconv4/bias"]
+    for k, og in ograds.items():
+        scale = max(float(og.abs().max()), float(ograds[k.replace("/bias", "/kernel")].abs().max()) if k in zero_grad else 0.0)
+        err = float((grads[k].double() - og).abs().max())
+        assert err <= 2e-3 * scale + 1e-9, (k, err, scale)
+        if k in zero_grad:
+            assert float(og.abs().max()) <= 1e-9 and float(grads[k].abs().max()) <= 1e-3 * scale
+    for steps in (1, 3):
+        if steps == 3:
+            for _ in range(2):
+                tr.fit(maps, vec, ta.cuda(), tp.cuda())
+                pt.fit(wd, opt, imgd, vecd, tad, tpd)
+        got = tr.get_weights()
+        assert tr.steps == steps
+        for k in wd:
+            if k.endswith("/mean") or k.endswith("/var"):
+                assert float((got[k].double() - wd[k]).abs().max()) <= 1e-5, k
+                continue
+            diff = ((got[k].double() - w[k].double()) - (wd[k] - w[k].double())).abs()
+            assert float(diff.max()) <= 2.2e-4 * steps, (k, float(diff.max()))
+            if k not in zero_grad:                       # (there Adam turns the rounding noise into +-lr steps on either side)
+                assert float((diff <= 5e-6 * steps).float().mean()) >= 0.99, (k, float((diff <= 5e-6 * steps).float().mean()))
+    got = {k: v.float() for k, v in got.items()}
+    # the inference engine was refreshed with the trained weights (BN folded from the moving statistics)
+    r = tr.model.forward(maps, vec, 1, want_ptr=True)
+    iact, iptr = po.forward(got, img, vec_h)
+    assert _rel(r["act"].cpu(), iact) <= 2.5e-2 and _rel(r["ptr"].cpu(), iptr) <= 2.5e-2
+
+
+def test_td_targets_kernel_is_exact_and_replay_runs():
+    import random
+    from oracle import policy_train_torch as pt
+    from ofighters_b200 import _lib
+    from ofighters_b200.trainer import Epsilon_cos, TrainerB200
+    import ctypes as C
+    B = 5
+    g = torch.Generator().manual_seed(9)
+    act_o, act_n = torch.randn((B, 2), generator=g), torch.randn((B, 2), generator=g)
+    ptr_o, ptr_n = torch.randn((B, 400, 400), generator=g), torch.randn((B, 400, 400), generator=g)
+    ia = torch.tensor([0, 1, 1, 0, 1], dtype=torch.int32)
+    pointer = torch.tensor([[10, 20], [399, 0], [7, 7], [0, 399], [200, 123]], dtype=torch.int32)
+    reward = torch.tensor([2.0, 0.0, 3.0, 1.0, 0.0])
+    done = torch.tensor([0, 1, 0, 0, 1], dtype=torch.uint8)
+    want_a, want_p = pt.td_targets(act_o, ptr_o, act_n, ptr_n, ia, pointer, reward, done)
+    d = [t.cuda() for t in (act_o, ptr_o, act_n, ptr_n, ia, pointer, reward, done)]
+    ta, tp = torch.empty_like(d[0]), torch.empty_like(d[1])
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(_lib.load().ofb_trainer_td_targets(*[p(t) for t in d], 0.9, B, p(ta), p(tp), None))
+    torch.cuda.synchronize()
+    assert torch.equal(ta.cpu(), want_a) and torch.equal(tp.cpu(), want_p)
+
+    # Trainer surface: remember / replay / get_best_action on observations of a running arena batch
+    random.seed(3)
+    bg, maps, vec = _arena_batch(16, frames=10, seed=5)
+    tr = TrainerB200(learning_rate=1e-4, epsilon=Epsilon_cos(period=110 * 400), batch_size=8, memory_size=400)
+    prev = None
+    for t in range(12):
+        maps = bg.raster("bits")
+        obs = [(maps[k].clone(), bg.obs_vec[k, 0].clone()) for k in range(16)]
+        if prev is not None:
+            for k in range(16):
+                tr.remember(prev[k][0], prev[k][1], prev[k][2], float(bg.obs_vec[k, 0, 0]), obs[k], False)
+        acts = [tr.random_play() for _ in range(16)]
+        prev = [(obs[k], acts[k][0], acts[k][1]) for k in range(16)]
+        bg.frame()
+    assert len(tr.memory) == 11 * 16
+    w0 = tr.get_weights()
+    hist = tr.replay(tr.batch_size)
+    assert np.isfinite(hist.history["loss"][0]) and tr.steps == 1
+    w1 = tr.get_weights()
+    assert any(not torch.equal(w0[k], w1[k]) for k in w0)
+    tr.epsilon.set(0.0)
+    ia_, (x, y) = tr.get_best_action(maps[0], bg.obs_vec[0, 0], rand=True)
+    assert ia_ in (0, 1) and 0 <= x < 400 and 0 <= y < 400
+    k = int(torch.argmax(tr.ptr_values.reshape(-1)))
+    assert (x, y) == (k % 400, k // 400)
+    with pytest.raises(Exception, match="Invalid batch"):
+        tr.fit(torch.zeros((9, 2, 5000), dtype=torch.int32, device="cuda"), torch.zeros((9, 8)), torch.zeros((9, 2)),
+               torch.zeros((9, 400, 400)))
