@@ -57,6 +57,9 @@ enum { OFB_ENGINE_TENSOR = 0,      /* tcgen05 kernels (product path) */
  * loops over chunks of that size); workspace = about 1 MB per ship.  0 = default (1024). */
 int ofb_policy_create(const ofb_policy_weights *w_host, int device, int max_ships, ofb_policy **out);
 int ofb_policy_destroy(ofb_policy *p);
+/* load new weights into an existing handle (Trainer.fit refreshed them; load_model, agents/qlearnIA_V2.py:70): folds like
+ * ofb_policy_create and overwrites the resident copy after `stream` has drained; the workspace is kept. */
+int ofb_policy_set_weights(ofb_policy *p, const ofb_policy_weights *w_host, void *stream);
 int ofb_policy_set_engine(ofb_policy *p, int engine);
 
 /* model.predict + decode for n_arenas arenas with ships_per_arena policy-driven ships each.

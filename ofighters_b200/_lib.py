@@ -104,6 +104,8 @@ def load():
     lib.ofb_state_import.argtypes = [vp, C.POINTER(OfbStateView), vp]
     lib.ofb_policy_create.argtypes = [C.POINTER(OfbPolicyWeights), i32, i32, C.POINTER(vp)]
     lib.ofb_policy_destroy.argtypes = [vp]
+    lib.ofb_policy_set_weights.argtypes = [vp, C.POINTER(OfbPolicyWeights), vp]
+    lib.ofb_policy_set_weights.restype = i32
     lib.ofb_policy_set_engine.argtypes = [vp, i32]
     lib.ofb_policy_forward.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
     lib.ofb_policy_write_actions.argtypes = [vp, vp, i64, i32, vp, i32, C.c_float, u64, i64, u32, vp, vp]

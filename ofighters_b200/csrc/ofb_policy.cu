@@ -98,26 +98,9 @@ struct Uploader {
     template <class T> void add(T **dst, const std::vector<T> &v) { add(dst, v.data(), v.size()); }
 };
 
-extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int max_ships, ofb_policy **out) {
-    if (!wh || !out) { ofb_set_error("ofb_policy_create: null argument"); return OFB_E_ARG; }
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        ofb_set_error("ofb_policy_create: no CUDA device (libofb has no CPU fallback)");
-        return OFB_E_CUDA;
-    }
-    OFB_CUDA_CHECK(cudaSetDevice(device));
-    if (max_ships <= 0) max_ships = 1024;
-    ofb_policy *p = new (std::nothrow) ofb_policy();
-    if (!p) return OFB_E_NOMEM;
-    memset(p, 0, sizeof(*p));
-    p->device = device;
-    p->max_ships = max_ships;
-    p->engine = OFB_ENGINE_TENSOR;
-    p->prof = new std::vector<ProfEvent>();
-
-    Uploader up;
-    PolicyDev &d = p->w;
+// Folds the Keras weights (BN into the convs, bilinear x2 into output phases, operand packs of the tensor-core kernels) into
+// the upload blob.  The blob's layout depends only on the architecture, so ofb_policy_set_weights can rebuild it in place.
+static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, PolicyDev &d, float &u4_bias) {
     std::vector<float> w, b;
     // trunk
     fold_conv(wh->conv[0], 2, 8, w, b);
@@ -170,8 +153,33 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     { const std::vector<float> pf = fold_phase(w, 8, 1);
       up.add(&d.u4_pw, pack_taps(pf, 8, 4, 16));
       up.add(&d.u4_tz, pack_toeplitz(pf, 8, 4, 8)); }
-    p->u4_bias = b[0];
+    u4_bias = b[0];
     { std::vector<float> pb(16, 0.f); for (int n = 0; n < 4; n++) pb[n] = b[0]; up.add(&d.u4_pb, pb); }
+
+}
+
+extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int max_ships, ofb_policy **out) {
+    if (!wh || !out) { ofb_set_error("ofb_policy_create: null argument"); return OFB_E_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        ofb_set_error("ofb_policy_create: no CUDA device (libofb has no CPU fallback)");
+        return OFB_E_CUDA;
+    }
+    OFB_CUDA_CHECK(cudaSetDevice(device));
+    if (max_ships <= 0) max_ships = 1024;
+    ofb_policy *p = new (std::nothrow) ofb_policy();
+    if (!p) return OFB_E_NOMEM;
+    memset(p, 0, sizeof(*p));
+    p->device = device;
+    p->max_ships = max_ships;
+    p->engine = OFB_ENGINE_TENSOR;
+    p->prof = new std::vector<ProfEvent>();
+
+    Uploader up;
+    PolicyDev &d = p->w;
+    build_weight_blob(wh, up, d, p->u4_bias);
+    p->arena_bytes = up.host.size();
 
     cudaError_t e = cudaMalloc(&p->arena_blob, up.host.size());
     if (e == cudaSuccess) e = cudaMemcpy(p->arena_blob, up.host.data(), up.host.size(), cudaMemcpyHostToDevice);
@@ -221,6 +229,22 @@ extern "C" int ofb_policy_destroy(ofb_policy *p) {
         delete static_cast<std::vector<ProfEvent> *>(p->prof);
     }
     delete p;
+    return OFB_OK;
+}
+
+// New weights into an existing handle (after a Trainer.fit step): same folding as ofb_policy_create, copied over the
+// resident blob once `stream` has drained.  The workspace is untouched.
+extern "C" int ofb_policy_set_weights(ofb_policy *p, const ofb_policy_weights *wh, void *stream) {
+    if (!p || !wh) { ofb_set_error("ofb_policy_set_weights: null argument"); return OFB_E_ARG; }
+    OFB_CUDA_CHECK(cudaSetDevice(p->device));
+    Uploader up;
+    PolicyDev scratch;
+    float u4_bias = 0.f;
+    build_weight_blob(wh, up, scratch, u4_bias);
+    if (up.host.size() != p->arena_bytes) { ofb_set_error("ofb_policy_set_weights: blob size mismatch"); return OFB_E_STATE; }
+    OFB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    OFB_CUDA_CHECK(cudaMemcpy(p->arena_blob, up.host.data(), up.host.size(), cudaMemcpyHostToDevice));
+    p->u4_bias = u4_bias;
     return OFB_OK;
 }
 

@@ -69,6 +69,7 @@ struct ofb_policy {
     int profiling;            // when set, forward brackets every kernel with CUDA events
     void *prof;               // std::vector<ProfEvent>*
     void *arena_blob;         // single allocation holding all weights
+    size_t arena_bytes;
     void *work_blob;          // single allocation holding the workspace
 };
 

@@ -98,6 +98,36 @@ __device__ __forceinline__ void block_accumulate(const double (&v)[NV], double *
     __syncthreads();
 }
 
+// N consecutive floats of one pixel: 16-byte accesses when the channel count allows (pixels are N * 4-byte aligned)
+template <int N>
+__device__ __forceinline__ void load_vec(const float *__restrict__ p, float (&v)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < N / 4; j++) {
+            const float4 t = reinterpret_cast<const float4 *>(p)[j];
+            v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+        }
+    } else if constexpr (N == 2) {
+        const float2 t = *reinterpret_cast<const float2 *>(p);
+        v[0] = t.x; v[1] = t.y;
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) v[j] = p[j];
+    }
+}
+template <int N>
+__device__ __forceinline__ void store_vec(float *__restrict__ p, const float (&v)[N]) {
+    if constexpr (N % 4 == 0) {
+#pragma unroll
+        for (int j = 0; j < N / 4; j++) reinterpret_cast<float4 *>(p)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else if constexpr (N == 2) {
+        *reinterpret_cast<float2 *>(p) = make_float2(v[0], v[1]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = v[j];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- forward kernels
 __global__ void k_tr_unpack(const uint32_t *__restrict__ bits, float *__restrict__ x0, long long n_px_total) {
     // x0[b, y, x, c] = bit (y*400 + x) of bits[b, c]
@@ -132,17 +162,16 @@ __global__ void k_tr_conv_fwd(const float *__restrict__ x, const float *__restri
             for (int kx = 0; kx < 3; kx++) {
                 const int sx = xx + kx - 1;
                 if (sx < 0 || sx >= W) continue;
-                const float *xp = x + ((b * H + sy) * W + sx) * CIN;
+                float xv[CIN];
+                load_vec<CIN>(x + ((b * H + sy) * W + sx) * CIN, xv);
 #pragma unroll
                 for (int ci = 0; ci < CIN; ci++) {
-                    const float v = xp[ci];
 #pragma unroll
-                    for (int co = 0; co < COUT; co++) acc[co] = fmaf(v, ws[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[co]);
+                    for (int co = 0; co < COUT; co++) acc[co] = fmaf(xv[ci], ws[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[co]);
                 }
             }
         }
-#pragma unroll
-        for (int co = 0; co < COUT; co++) y[i * COUT + co] = acc[co];
+        store_vec<COUT>(y + i * COUT, acc);
     }
 }
 
@@ -247,6 +276,25 @@ __global__ void k_tr_dense_fwd(const float *__restrict__ x, const float *__restr
     for (int k = 0; k < fin; k++) acc = fmaf(xp[k], W[(long long)k * fout + o], acc);
     y[i] = relu ? fmaxf(acc, 0.0f) : acc;
 }
+// the same for a long reduction (dense1: 5008 inputs): grid (slices, B), thread o sums its slice of k and adds it to y, which
+// k_tr_bias_fill initialised with the bias; k_tr_relu applies the activation afterwards
+__global__ void k_tr_dense_fwd_splitk(const float *__restrict__ x, const float *__restrict__ W, float *__restrict__ y, int fin, int fout) {
+    const int o = threadIdx.x, b = blockIdx.y;
+    const int per = (fin + gridDim.x - 1) / gridDim.x, k0 = blockIdx.x * per, k1 = min(fin, k0 + per);
+    if (o >= fout) return;
+    const float *xp = x + (long long)b * fin;
+    float acc = 0.0f;
+    for (int k = k0; k < k1; k++) acc = fmaf(xp[k], W[(long long)k * fout + o], acc);
+    atomicAdd(&y[b * fout + o], acc);
+}
+__global__ void k_tr_bias_fill(const float *__restrict__ bias, float *__restrict__ y, int B, int fout) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B * fout) y[i] = bias[i % fout];
+}
+__global__ void k_tr_relu(float *__restrict__ y, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fmaxf(y[i], 0.0f);
+}
 __global__ void k_tr_set_vec(const float *__restrict__ vec, float *__restrict__ cat, int B) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B * 8) cat[(long long)(i / 8) * 5008 + (i % 8)] = vec[i];
@@ -297,17 +345,16 @@ __global__ void k_tr_conv_bwd_data(const float *__restrict__ dy, const float *__
             for (int kx = 0; kx < 3; kx++) {
                 const int ox = xx + 1 - kx;
                 if (ox < 0 || ox >= W) continue;
-                const float *dp = dy + ((b * H + oy) * W + ox) * COUT;
+                float gv[COUT];
+                load_vec<COUT>(dy + ((b * H + oy) * W + ox) * COUT, gv);
 #pragma unroll
                 for (int co = 0; co < COUT; co++) {
-                    const float g = dp[co];
 #pragma unroll
-                    for (int ci = 0; ci < CIN; ci++) acc[ci] = fmaf(g, ws[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[ci]);
+                    for (int ci = 0; ci < CIN; ci++) acc[ci] = fmaf(gv[co], ws[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[ci]);
                 }
             }
         }
-#pragma unroll
-        for (int ci = 0; ci < CIN; ci++) dx[i * CIN + ci] = acc[ci];
+        store_vec<CIN>(dx + i * CIN, acc);
     }
 }
 
@@ -315,14 +362,21 @@ __global__ void k_tr_conv_bwd_data(const float *__restrict__ dy, const float *__
 // One thread per weight; a block walks row segments of TW pixels staged in shared memory and adds its partial sums once.
 #define TR_TW 64
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(9 * CIN * COUT < 64 ? 64 : 9 * CIN * COUT)
+struct BwdW {
+    static constexpr int NW = 9 * CIN * COUT;
+    static constexpr int PG = NW >= 288 ? 1 : (576 / NW > 16 ? 16 : 576 / NW);      // pixel groups sharing a tile
+    static constexpr int NT = NW * PG < 64 ? 64 : NW * PG;
+};
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(BwdW<CIN, COUT>::NT)
 k_tr_conv_bwd_weight(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, float *__restrict__ db, int B,
                      int H, int W) {
-    constexpr int NW = 9 * CIN * COUT;
+    constexpr int NW = BwdW<CIN, COUT>::NW, PG = BwdW<CIN, COUT>::PG;
     __shared__ float xs[3][TR_TW + 2][CIN];
     __shared__ float dys[TR_TW][COUT];
     const int t = threadIdx.x;
-    const int co = t % COUT, ci = (t / COUT) % CIN, kx = (t / (COUT * CIN)) % 3, ky = t / (COUT * CIN * 3);
+    const int wi = t % NW, pg = t / NW;                 // weight index, pixel group (threads beyond NW * PG only help staging)
+    const int co = wi % COUT, ci = (wi / COUT) % CIN, kx = (wi / (COUT * CIN)) % 3, ky = wi / (COUT * CIN * 3);
     const int segs = (W + TR_TW - 1) / TR_TW;
     const long long tiles = (long long)B * H * segs;
     double acc = 0.0, accb = 0.0;
@@ -341,10 +395,10 @@ k_tr_conv_bwd_weight(const float *__restrict__ x, const float *__restrict__ dy, 
             dys[px][c] = px < tw ? dy[((b * H + yy) * W + xbeg + px) * COUT + c] : 0.0f;
         }
         __syncthreads();
-        if (t < NW) {
+        if (pg < PG) {
             float s = 0.0f;
 #pragma unroll 8
-            for (int px = 0; px < TR_TW; px++) s = fmaf(xs[ky][px + kx][ci], dys[px][co], s);
+            for (int px = pg; px < TR_TW; px += PG) s = fmaf(xs[ky][px + kx][ci], dys[px][co], s);
             acc += (double)s;
         }
         if (t < COUT) {
@@ -353,7 +407,7 @@ k_tr_conv_bwd_weight(const float *__restrict__ x, const float *__restrict__ dy, 
             accb += (double)s;
         }
     }
-    if (t < NW) atomicAdd(&dw[t], (float)acc);
+    if (pg < PG) atomicAdd(&dw[wi], (float)acc);
     if (t < COUT) atomicAdd(&db[t], (float)accb);
 }
 
@@ -391,7 +445,7 @@ __global__ void k_tr_bnpool_bwd_apply(const float *__restrict__ y, const float *
                                       const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                                       const float *__restrict__ dp, long long dp_stride, const double *__restrict__ sums,
                                       float *__restrict__ dy, int B, int H, int W, int C) {
-    const int Ho = H / 2, Wo = W / 2;
+    const int Wo = W / 2;
     const long long n = (long long)B * H * W * C;
     const double inv_n = 1.0 / (double)((long long)B * H * W);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -639,7 +693,7 @@ static void conv_fwd(const float *x, const float *w, const float *b, float *y, i
 }
 template <int CIN, int COUT>
 static void conv_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int H, int W, cudaStream_t st) {
-    constexpr int NT = 9 * CIN * COUT < 64 ? 64 : 9 * CIN * COUT;
+    constexpr int NT = BwdW<CIN, COUT>::NT;
     const long long tiles = (long long)B * H * ((W + TR_TW - 1) / TR_TW);
     k_tr_conv_bwd_weight<CIN, COUT><<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), NT, 0, st>>>(x, dy, dw, db, B, H, W);
     if (dx) k_tr_conv_bwd_data<CIN, COUT><<<blocks_for((long long)B * H * W, 256), 256, 0, st>>>(dy, w, dx, B, H, W);
@@ -668,7 +722,9 @@ static int forward_train(ofb_trainer *t, const uint32_t *maps, const float *vec,
     }
     k_tr_set_vec<<<blocks_for(B * 8, 64), 64, 0, st>>>(vec, t->cat, B);
     k_tr_flat_to_cat<<<blocks_for((long long)B * 5000, 256), 256, 0, st>>>(t->p[3], t->cat, B);
-    k_tr_dense_fwd<<<blocks_for(B * 100, 64), 64, 0, st>>>(t->cat, P + T.d1.k.off, P + T.d1.b.off, t->h1, B, 5008, 100, 1);
+    k_tr_bias_fill<<<blocks_for(B * 100, 128), 128, 0, st>>>(P + T.d1.b.off, t->h1, B, 100);
+    k_tr_dense_fwd_splitk<<<dim3(40, B), 128, 0, st>>>(t->cat, P + T.d1.k.off, t->h1, 5008, 100);
+    k_tr_relu<<<blocks_for(B * 100, 128), 128, 0, st>>>(t->h1, B * 100);
     k_tr_dense_fwd<<<blocks_for(B * 50, 64), 64, 0, st>>>(t->h1, P + T.d2.k.off, P + T.d2.b.off, t->d2, B, 100, 50, 1);
     k_tr_dense_fwd<<<blocks_for(B * 2, 64), 64, 0, st>>>(t->d2, P + T.o1.k.off, P + T.o1.b.off, t->act, B, 50, 2, 0);
     k_tr_dense_fwd<<<blocks_for(B * 625, 128), 128, 0, st>>>(t->h1, P + T.ud.k.off, P + T.ud.b.off, t->u0, B, 100, 625, 1);

@@ -99,11 +99,12 @@ class PolicyB200:
         for n in ("dense1", "dense2", "output1", "updense1"):
             d = getattr(w, n)
             d.kernel, d.bias = host[n + "/kernel"].data_ptr(), host[n + "/bias"].data_ptr()
-        if self._h:
-            self._lib.ofb_policy_destroy(self._h)
-        h = C.c_void_p()
-        _lib.check(self._lib.ofb_policy_create(C.byref(w), self.device.index or 0, self.max_ships, C.byref(h)))
-        self._h = h
+        if self._h:                                       # same architecture: refresh the resident weights in place
+            _lib.check(self._lib.ofb_policy_set_weights(self._h, C.byref(w), self._stream()))
+        else:
+            h = C.c_void_p()
+            _lib.check(self._lib.ofb_policy_create(C.byref(w), self.device.index or 0, self.max_ships, C.byref(h)))
+            self._h = h
         self.weights = host
 
     def set_engine(self, name):
