@@ -210,9 +210,21 @@ def gpu_arm(args, wl):
     bg = BatchedBattleground(N, ships=ships, config=ArenaConfig(laser_cap=wl["lcap"]), device=dev, seed=SEED,
                              arena0=rank * N)
     policy = None
-    if wl["policy"]:
+    learner = trainer = None
+    learn = wl["policy"] and (args.learn == "on" or (args.learn == "auto" and args.workload == "sharded1m"))
+    loss_stats = torch.zeros(2, dtype=torch.float64, device=dev)
+    if wl["policy"] and learn:
+        # ONE shared trainer (agents/qlearnIA_V2.py:308): rank 0 learns from the policy ships of its first 8 arenas and
+        # broadcasts the weights after every scheduled replay; the episode's [sum loss, replays] rides the K7 all-reduce
+        from ofighters_b200.trainer import Epsilon_cos, QLearner, TrainerB200, flatten_weights, unflatten_weights
+        trainer = TrainerB200(learning_rate=1e-4, epsilon=Epsilon_cos(period=110 * 400), batch_size=8, device=dev, seed=0,
+                              max_ships=8192)
+        policy = trainer.model
+        learner = QLearner(trainer, track=8, replay_every=50) if rank == 0 else None
+    elif wl["policy"]:
         from ofighters_b200.policy import PolicyB200
         policy = PolicyB200.random_init(device=dev, seed=0, max_ships=8192)
+    trainer_len = 571730
     maps = torch.empty((N, 2, 400 * 400 // 32), dtype=torch.int32, device=dev)
     bg.raster("bits", out=maps)
     state_bytes = N * bg.state_stride
@@ -221,17 +233,33 @@ def gpu_arm(args, wl):
     launches = [0]
 
     def one_step():
-        n0 = bg.launch_count + (policy.launch_count if policy is not None else 0)
+        n0 = bg.launch_count + (policy.launch_count if policy is not None else 0) + (trainer.launch_count if trainer is not None else 0)
         if bg.time >= max_time:
             bg.restart()
+            if learner is not None:
+                loss_stats[0] += sum(learner.losses)
+                loss_stats[1] += len(learner.losses)
+                learner.losses.clear()
+                learner.reset()
             if world > 1:
                 sharding.reduce_episode_stats(bg.stats)   # K7: per-episode [score, kills, deaths, shots, ships, arenas]
+                if trainer is not None:
+                    sharding.reduce_loss_stats(loss_stats)     # ... and [sum of replay losses, replays]
             if policy is not None:
                 bg.raster("bits", out=maps)        # Battleground.restart builds a fresh Observation
         if policy is not None:
-            policy.act(bg, maps)                   # forward on the current maps -> the policy ship's ("external") action row
+            iact, xy = policy.act(bg, maps)        # forward on the current maps -> the policy ship's ("external") action row
+            if learner is not None:
+                learner.observe(bg, maps, iact, xy)            # remember / replay (fit) on rank 0
+            if trainer is not None and world > 1 and (bg.total_steps + 1) % 50 == 0:
+                flat = flatten_weights(trainer.get_weights()).to(dev) if rank == 0 else \
+                    torch.empty(trainer_len, dtype=torch.float32, device=dev)
+                sharding.broadcast_weights(flat, src=0)        # the single shared trainer's weights reach every rank
+                if rank != 0:
+                    policy.load_weights(unflatten_weights(flat.cpu()))
         bg.frame(maps=maps)                        # scripted bots + step + observation maps: one fused launch (ofb_frame_bots)
-        launches[0] += bg.launch_count + (policy.launch_count if policy is not None else 0) - n0
+        launches[0] += bg.launch_count + (policy.launch_count if policy is not None else 0) + \
+            (trainer.launch_count if trainer is not None else 0) - n0
 
     stream = torch.cuda.current_stream(dev)
     for _ in range(warmup):
@@ -289,7 +317,16 @@ def gpu_arm(args, wl):
                    "episode": "restart every 200 frames inside the timed region",
                    "l2": (flush_buf.describe() if flush_needed
                           else "working set %.0f MB > L2" % ((state_bytes + maps.numel() * 4) / 1e6)),
-                   "wall_s_timed_region": wall},
+                   "wall_s_timed_region": wall,
+                   **({"learning": {"replays_reduced": float(loss_stats[1].item()),
+                                    "pending_replays": len(learner.losses) if learner is not None else 0,
+                                    "mean_replay_loss": ((float(loss_stats[0].item()) + (sum(learner.losses) if learner is not None else 0.0))
+                                                         / max(1.0, float(loss_stats[1].item()) + (len(learner.losses) if learner is not None else 0))),
+                                    "trainer_steps": trainer.steps,
+                                    "what": "rank 0 runs Trainer.replay (batch 8, Adam 1e-4) every 50 frames on transitions of "
+                                            "its first 8 arenas' policy ships; weights broadcast to all ranks after each; "
+                                            "[sum loss, replays] all-reduced with the episode statistics"}}
+                      if trainer is not None else {})},
         "gpu_launches": launches[0], "clocks": clocks, "e2e": e2e, "roofline": roof,
     }
     if rank == 0:
@@ -530,6 +567,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--workload", default="arena4096", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--learn", default="auto", choices=["auto", "on", "off"],
+                    help="policy workloads: Q-learning replay (fit) every 50 frames on rank 0, weights broadcast, loss in the "
+                         "per-episode reduction (auto = on for sharded1m)")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
                     help="L2 flush between timed steps when the working set is L2-sized")
     args = ap.parse_args()

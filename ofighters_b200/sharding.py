@@ -5,7 +5,9 @@ hot path shards with no data-path collective: rank g of G owns the contiguous gl
 ``[g*N/G, (g+1)*N/G)`` and keys its device RNG by GLOBAL arena id (``arena0``), which makes every
 arena's trajectory independent of G.  The only exchange is the per-episode statistics vector
 ``[sum score, kills, deaths, shots, ships, arenas]`` (what the reference accumulates in
-``agent.scores`` / ``last_x_time_rewards``): one all-reduce(sum) of 6 int64 per 200-frame episode.
+``agent.scores`` / ``last_x_time_rewards``): one all-reduce(sum) of 6 int64 per 200-frame episode -- plus, when a rank
+learns (trainer.QLearner), the episode's [sum of replay losses, replays] pair and a broadcast of the single shared
+trainer's weights (572 k floats) after each scheduled replay.
 Works with any ``torch.distributed`` backend: NCCL over NVLink on the GPU box, gloo in CPU tests.
 """
 import torch
@@ -30,6 +32,26 @@ def reduce_episode_stats(stats, group=None, async_op=False):
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return None
     return dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
+def reduce_loss_stats(loss_stats, group=None):
+    """In-place sum over all ranks of the float64 [sum of replay losses, replays] pair of an episode -- the "loss" half of
+    the per-episode score/loss reduction (only ranks that learn contribute non-zero entries)."""
+    if loss_stats.dtype != torch.float64 or loss_stats.numel() != 2:
+        raise Exception("Invalid loss statistics tensor : expected float64 [2].")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    return dist.all_reduce(loss_stats, op=dist.ReduceOp.SUM, group=group)
+
+
+def broadcast_weights(flat, src=0, group=None):
+    """The reference has ONE trainer shared by every bot (agents/qlearnIA_V2.py:308, "All bots share the same trainer" :362):
+    the learning rank's flat fp32 weights (include/ofb_train.h order) replace everyone's, in place.  No-op without a group."""
+    if flat.dtype != torch.float32 or flat.dim() != 1:
+        raise Exception("Invalid weights tensor : expected flat float32.")
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return None
+    return dist.broadcast(flat, src=src, group=group)
 
 
 def stats_dict(stats):

@@ -280,3 +280,65 @@ def len_flat():
             k *= d
         n += k
     return n
+
+
+class QLearner:
+    """Batched counterpart of ``QlearnIA.play``'s learning bookkeeping (agents/qlearnIA_V2.py:372-417) on top of one shared
+    ``TrainerB200`` ("All bots share the same trainer", :362): the policy ship of each of the first ``track`` arenas is a
+    QlearnIA bot -- every frame it remembers (previous_obs, previous_action, previous_pointer, obs.reward, obs, obs.done) until
+    it has seen its own death (:376-392), and bot id 1 (arena 0) replays every ``replay_every`` total steps (:403-405) and
+    once when it dies (:378-385).  Observations stay on the device: obs = (maps_bits [2,5000], head [8])."""
+
+    def __init__(self, trainer, track=8, replay_every=50):
+        self.trainer = trainer
+        self.track = int(track)
+        self.replay_every = int(replay_every)
+        self.total_steps = 0
+        self.losses = []
+        self.epsilons = []
+        self.reset()
+
+    def reset(self):
+        """``QlearnIA.reset`` (:359-369): forget the previous action at an episode restart."""
+        self.epsilons.append(self.trainer.epsilon.get())
+        self.previous = [None] * self.track
+        self.done = [False] * self.track
+
+    def observe(self, bg, maps_bits, iaction, xy, ship=None):
+        """Call once per frame right after the policy chose (iaction [A*P], xy [A*P,2]) on the current observation."""
+        if ship is None:
+            ship = int(bg._policy_ship_idx[0]) if getattr(bg, "_policy_ship_idx", None) is not None else 0
+        K = min(self.track, bg.n_arenas)
+        P = iaction.numel() // bg.n_arenas
+        heads = bg.obs_vec[:K, ship, :]
+        alive = bg.state(("ship_alive",))["ship_alive"][:K, ship].tolist()
+        rewards = heads[:, 0].tolist()
+        ia = iaction.reshape(bg.n_arenas, P)[:K, 0].tolist()
+        pt = xy.reshape(bg.n_arenas, P, 2)[:K, 0].tolist()
+        self.total_steps += 1
+        replayed = False
+        for k in range(K):
+            if self.done[k]:
+                continue
+            obs = (maps_bits[k].clone(), heads[k].clone())
+            done = not alive[k]
+            if done:
+                if k == 0:
+                    self._replay()
+                    replayed = True
+                self.done[k] = True
+            if self.previous[k] is not None:
+                po, pa, pp = self.previous[k]
+                self.trainer.remember(po, pa, pp, rewards[k], obs, done)
+            self.previous[k] = (obs, int(ia[k]), (int(pt[k][0]), int(pt[k][1])))
+        self.trainer.decay_epsilon()
+        if self.total_steps % self.replay_every == 0 and len(self.trainer.memory) > 0:
+            self._replay()
+            replayed = True
+        return replayed
+
+    def _replay(self):
+        if len(self.trainer.memory) == 0:
+            return
+        h = self.trainer.replay(self.trainer.batch_size)
+        self.losses.append(h.history["loss"][0])

@@ -145,3 +145,45 @@ def test_td_targets_kernel_is_exact_and_replay_runs():
     with pytest.raises(Exception, match="Invalid batch"):
         tr.fit(torch.zeros((9, 2, 5000), dtype=torch.int32, device="cuda"), torch.zeros((9, 8)), torch.zeros((9, 2)),
                torch.zeros((9, 400, 400)))
+
+
+def test_qlearner_follows_qlearnia_bookkeeping():
+    """QlearnIA.play's remember / replay schedule on a batch: one transition per live tracked policy ship and frame, none
+    after the ship has seen its own death, a replay every 50 total steps (and at the death of bot 1), previous_* forgotten
+    at a restart, and the inference engine tracks the trained weights."""
+    import random
+    from ofighters_b200 import BatchedBattleground
+    from ofighters_b200.trainer import Epsilon_cos, QLearner, TrainerB200
+    random.seed(1)
+    bg = BatchedBattleground(32, ships={"QlearnIA": 1, "random": 6}, seed=21)
+    maps = bg.raster("bits")
+    tr = TrainerB200(learning_rate=1e-4, epsilon=Epsilon_cos(period=110 * 400), batch_size=8, max_ships=32)
+    ql = QLearner(tr, track=4, replay_every=50)
+    w0 = tr.get_weights()
+    expect, alive_prev = 0, [True] * 4
+    for t in range(120):
+        if t == 100:
+            bg.restart()
+            bg.raster("bits", out=maps)
+            ql.reset()
+            alive_prev = [True] * 4
+            had_prev = [False] * 4
+        iact, xy = tr.model.act(bg, maps)
+        alive = bg.state(("ship_alive",))["ship_alive"][:4, 0].tolist()
+        if t == 0:
+            had_prev = [False] * 4
+        for k in range(4):
+            if alive_prev[k]:                            # the ship had not yet seen its death before this frame
+                expect += 1 if had_prev[k] else 0
+                had_prev[k] = True
+            alive_prev[k] = alive_prev[k] and bool(alive[k])
+        n_before = len(tr.memory)
+        ql.observe(bg, maps, iact, xy)
+        assert min(len(tr.memory), 400) == min(expect, 400), (t, len(tr.memory), expect, n_before)
+        bg.frame()
+        bg.raster("bits", out=maps)
+    assert ql.total_steps == 120 and tr.steps >= 2 and len(ql.losses) == tr.steps and all(np.isfinite(ql.losses))
+    w1 = tr.get_weights()
+    assert not torch.equal(w0["upconv4/kernel"], w1["upconv4/kernel"])
+    assert torch.equal(tr.model.weights["dense2/kernel"], w1["dense2/kernel"])      # inference engine refreshed after each fit
+    assert tr.epsilon.t == 120                           # decay_epsilon once per decision of bot 1 (:399-401)

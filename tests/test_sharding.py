@@ -29,8 +29,12 @@ c.reset(c.random_spawn(seed, 1, arena0=lo))                  # episode end: stat
 stats = torch.from_numpy(c.arr["stats"].copy())
 local = stats.clone()
 sharding.reduce_episode_stats(stats)                         # K7: the path's only collective
+flat = torch.full((10,), float(rank + 3), dtype=torch.float32)     # the shared trainer's weights live on rank 0
+sharding.broadcast_weights(flat, src=0)
+ls = torch.tensor([1.5 * (rank + 1), rank + 1.0], dtype=torch.float64)
+sharding.reduce_loss_stats(ls)
 np.savez(os.environ["OFB_OUT"] + ".%d.npz" % rank, lo=lo, hi=hi, local=local.numpy(), total=stats.numpy(),
-         x=c.arr["ship_x"], y=c.arr["ship_y"], score=c.arr["ship_reward"])
+         x=c.arr["ship_x"], y=c.arr["ship_y"], score=c.arr["ship_reward"], flat=flat.numpy(), ls=ls.numpy())
 dist.destroy_process_group()
 '''
 
@@ -77,6 +81,8 @@ def test_world_size_2_gloo_matches_single_process(tmp_path):
         c.step(c.bot_actions("random", seed, t))
     c.reset(c.random_spawn(seed, 1))
     assert [int(p["lo"]) for p in parts] == [0, 19] and int(parts[1]["hi"]) == N
+    for p in parts:                                      # weights broadcast from rank 0; [sum loss, replays] summed
+        assert np.array_equal(p["flat"], np.full(10, 3.0, np.float32)) and np.array_equal(p["ls"], np.array([4.5, 3.0]))
     for k in ("x", "y", "score"):
         whole = {"x": "ship_x", "y": "ship_y", "score": "ship_reward"}[k]
         assert np.array_equal(np.concatenate([p[k] for p in parts]), c.arr[whole]), k
