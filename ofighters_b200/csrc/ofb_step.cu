@@ -454,7 +454,7 @@ template <int LPA, int PIT, int SW, int NG, int NBUF>
 __global__ void __launch_bounds__((SW + NG * FR_RASTER_WARPS) * 32, 1)
 k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict__ actions, float4 *__restrict__ obs_out,
         long long n_arenas, const BotSpec bots, const int tile_bytes, const int slot_bytes, const int post_cap, const int K,
-        uint32_t *__restrict__ maps_out, long long *__restrict__ prof) {
+        uint32_t *__restrict__ maps_out, long long *__restrict__ prof, const int dbg) {
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int APW = 32 / LPA;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -477,7 +477,8 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
         // ---------------- stepper warps
         const int g = lane / LPA, gl = lane % LPA;
         uint32_t ph = 0;
-        long long t_wait = 0, t_begin = clock64();
+        long long t_wait = 0, t_begin = clock64(), t_unit_max = 0;
+        int n_units = 0;
         unsigned char *tb = tiles + (warp * APW + g) * tile_bytes;
         for (int u = warp; u * APW < cnt; u += SW) {
             const int i = u * APW + g;
@@ -487,11 +488,14 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
             const long long tw = clock64();
             if (ok && r > 0) mbar_wait(&empty[slot], (uint32_t)((r - 1) & 1));      // the raster has left arena i - K
             __syncwarp();
-            t_wait += clock64() - tw;
+            const long long tu = clock64();
+            t_wait += tu - tw;
             uint32_t used;
             step_tile<LPA, PIT, true>(state, lay, actions, obs_out, a0 + i, ok, bots, tb, &tile_bar[warp], ph, used,
                                       slots + slot * slot_bytes, post_cap);
             ph += used;
+            t_unit_max = max(t_unit_max, clock64() - tu);
+            n_units++;
             __syncwarp();
             if (ok && gl == 0) mbar_arrive(&full[slot]);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // tile reads before the next unit's bulk copy
@@ -499,6 +503,8 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
         if (prof && lane == 0) {                         // debug: cycles this stepper warp spent in total / waiting for a slot
             prof[((long long)blockIdx.x * 32 + warp) * 8 + 0] = clock64() - t_begin;
             prof[((long long)blockIdx.x * 32 + warp) * 8 + 1] = t_wait;
+            prof[((long long)blockIdx.x * 32 + warp) * 8 + 2] = t_unit_max;
+            prof[((long long)blockIdx.x * 32 + warp) * 8 + 3] = n_units;
         }
         return;
     }
@@ -548,7 +554,7 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
         const unsigned *sxy = reinterpret_cast<const unsigned *>(post + 16);
         const double2 *lxy = reinterpret_cast<const double2 *>(post + 16 + 4 * lay.SP);
         int ws = -1, wl = -1;
-        if (l_t < n * 5) {
+        if (l_t < n * 5 && !(dbg & 1)) {
             double2 c;
             if (l_k < post_cap) c = lxy[l_k];
             else {                                       // beyond the slot: the stepper's own store to the arena block
@@ -558,7 +564,7 @@ k_frame(char *__restrict__ state, const ArenaLayout lay, const int2 *__restrict_
             wl = raster_laser_row(bits + words, W, H, c.x, c.y, l_i);
             if (wl >= 0) wl += words;
         }
-        if (rt < S * rows) ws = raster_ship_row(bits, W, H, sxy[s_i], s_dr);
+        if (rt < S * rows && !(dbg & 2)) ws = raster_ship_row(bits, W, H, sxy[s_i], s_dr);
         const bool many = n * 5 > RT || S * rows > RT;   // (group-uniform) more items than threads: generic loops, full wipe later
         if (many) {
             for (int t = l_t + RT; t < n * 5; t += RT) {
@@ -703,7 +709,8 @@ static int launch_frame_t(ofb_arenas *h, const int2 *act, float4 *obs, const Bot
     }
     const unsigned grid = (unsigned)(h->n_arenas < (int64_t)n_sm ? h->n_arenas : (int64_t)n_sm);
     k_frame<LPA, PIT, SW, NG, NBUF><<<grid, (SW + NG * FR_RASTER_WARPS) * 32, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas,
-                                                                                         bots, tile, slot, post_cap, K, maps, g_frame_prof);
+                                                                                         bots, tile, slot, post_cap, K, maps, g_frame_prof,
+                                                                                         g_frame_prof ? env_int("OFB_FRAME_DBG", 0) : 0);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }
@@ -733,7 +740,7 @@ static int launch_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_ou
         if (lpa == L_ && sw == W_ && ng == G_ && nbuf == B_) \
             rc = launch_frame_t<L_, P_, W_, G_, B_>(h, act, obs, bots, maps, st, n_sm, smem_max, &fits);
         FR_CASE(8, 6, 8, 2, 2) FR_CASE(8, 6, 8, 1, 3)
-        FR_CASE(16, 4, 4, 2, 2) FR_CASE(16, 4, 8, 1, 3) FR_CASE(16, 4, 4, 3, 1)
+        FR_CASE(16, 4, 4, 2, 2) FR_CASE(16, 4, 8, 2, 2) FR_CASE(16, 4, 8, 1, 3) FR_CASE(16, 4, 4, 3, 1)
         FR_CASE(32, 3, 4, 2, 2) FR_CASE(32, 3, 8, 2, 2) FR_CASE(32, 3, 12, 1, 3)
 #undef FR_CASE
         if (rc != OFB_OK) return rc;

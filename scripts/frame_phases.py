@@ -27,6 +27,11 @@ sw = int(os.environ.get("OFB_FRAME_SW", "4"))
 ng = int(os.environ.get("OFB_FRAME_NG", "2"))
 st = p[:, :sw, :2]
 print("N", N, "stepper warps: total cycles mean %.0f max %d, waiting for a slot mean %.0f" % (st[..., 0].mean(), st[..., 0].max(), st[..., 1].mean()))
+import numpy as np
+tot, umax, nun = p[:, :sw, 0].reshape(-1), p[:, :sw, 2].reshape(-1), p[:, :sw, 3].reshape(-1)
+print("  stepper total cycles percentiles 50/90/99/max:", [int(np.percentile(tot, q)) for q in (50, 90, 99, 100)],
+      " longest unit 50/90/99/max:", [int(np.percentile(umax, q)) for q in (50, 90, 99, 100)],
+      " units per warp min/max:", int(nun.min()), int(nun.max()), " mean unit cycles:", round(float((tot - p[:, :sw, 1].reshape(-1)).sum() / nun.sum())))
 ra = p[:, sw:sw + ng, :7].astype(float)
 names = ["total", "drain+bar1", "zero+bar2", "wait full", "compose", "fence+bar3", "arenas"]
 print("raster groups (mean over CTAs x groups):", {n: round(ra[..., j].mean(), 0) for j, n in enumerate(names)})
