@@ -432,7 +432,7 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
             "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_ncu_full_frame*_v4.md): below the algorithmic bytes "
                             "at 4096 arenas because the last ~50 MB of the maps are still dirty in the 126 MB L2 when the kernel ends", "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
             "what": "k_frame = fused step + raster (one persistent launch per frame); algorithmic bytes = 88 B/ship + 64 B/live laser "
-                    "+ the 2 x W*H/8-byte maps it must produce, per arena (SURVEY 8(d)); 32-ship x 2048-slot arenas run as k_step + k_raster",
+                    "+ the 2 x W*H/8-byte maps it must produce, per arena (SURVEY 8(d))",
             "other_kernels": {"k_step": res["k_step"], "k_raster": res["k_raster"]}}
 
 

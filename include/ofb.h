@@ -132,8 +132,8 @@ int ofb_step_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_
  * ship_map / laser_map (lib/observation.py:79-95) written to maps_bits_dev in OFB_MAP_BITS format.  A persistent,
  * warp-specialised kernel steps the arenas and rasterises them from shared memory, so the state is read once and the
  * step's latency hides behind the raster's HBM writes.  Results are bit-identical to ofb_step / ofb_step_bots followed
- * by ofb_raster(OFB_MAP_BITS); configurations whose per-arena laser list does not fit the shared-memory ring (e.g. 32
- * ships x 2048 slots) run as those two launches. */
+ * by ofb_raster(OFB_MAP_BITS); a configuration that does not fit the kernel's shared-memory ring runs as those two
+ * launches (ofb_debug_last_frame_fused tells which). */
 int ofb_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, void *maps_bits_dev, void *stream);
 int ofb_frame_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64_t seed, int64_t arena0, uint32_t step,
                    const int16_t *actions_dev, float *obs_out_dev, void *maps_bits_dev, void *stream);
@@ -143,6 +143,8 @@ int ofb_frame_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_
 /* Debug aid for profiling the fused frame kernel: when buf_dev != NULL every following ofb_frame* launch writes
  * per-warp-role cycle counters to it (int64 [grid][32][8]); NULL switches it off. */
 int ofb_debug_frame_prof(long long *buf_dev);
+/* 1 if the calling thread's last ofb_frame* call ran as the single fused launch, 0 if as the two-launch form, -1 before. */
+int ofb_debug_last_frame_fused(void);
 
 /* randint(0, W) x randint(0, H) spawn draws of lib/battleground.py:79-81,114. */
 int ofb_random_spawn(int64_t n_arenas, int n_ships, int width, int height, uint64_t seed, int64_t arena0,

@@ -92,6 +92,8 @@ def load():
     lib.ofb_frame_host_async.argtypes = [vp, vp, vp, vp, vp]
     lib.ofb_debug_frame_prof.argtypes = [vp]
     lib.ofb_debug_frame_prof.restype = i32
+    lib.ofb_debug_last_frame_fused.argtypes = []
+    lib.ofb_debug_last_frame_fused.restype = i32
     for name in ("ofb_frame", "ofb_frame_bots", "ofb_frame_host_async"):
         getattr(lib, name).restype = i32
     lib.ofb_reset.argtypes = [vp, vp, vp, vp, vp]

@@ -678,6 +678,9 @@ static int env_int(const char *name, int dflt) {
     return (v && *v) ? atoi(v) : dflt;
 }
 
+// debug: 1 if the calling thread's last ofb_frame* call ran as the single fused launch, 0 if as k_step + k_raster
+static thread_local int g_last_frame_fused = -1;
+extern "C" int ofb_debug_last_frame_fused(void) { return g_last_frame_fused; }
 // debug: when set (ofb_debug_frame_prof), k_frame writes per-warp-role cycle counters there: long long [grid][32][8]
 static long long *g_frame_prof = nullptr;
 extern "C" int ofb_debug_frame_prof(long long *buf_dev) { g_frame_prof = buf_dev; return OFB_OK; }
@@ -739,12 +742,13 @@ static int launch_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_ou
 #define FR_CASE(L_, P_, W_, G_, B_) \
         if (lpa == L_ && sw == W_ && ng == G_ && nbuf == B_) \
             rc = launch_frame_t<L_, P_, W_, G_, B_>(h, act, obs, bots, maps, st, n_sm, smem_max, &fits);
-        FR_CASE(8, 6, 8, 2, 2) FR_CASE(8, 6, 8, 1, 3)
+        FR_CASE(8, 6, 8, 2, 2) FR_CASE(8, 6, 8, 1, 3) FR_CASE(8, 6, 8, 2, 1)
         FR_CASE(16, 4, 4, 2, 2) FR_CASE(16, 4, 8, 2, 2) FR_CASE(16, 4, 8, 1, 3) FR_CASE(16, 4, 4, 3, 1)
         FR_CASE(32, 3, 4, 2, 2) FR_CASE(32, 3, 8, 2, 2) FR_CASE(32, 3, 12, 1, 3)
 #undef FR_CASE
         if (rc != OFB_OK) return rc;
     }
+    g_last_frame_fused = fits ? 1 : 0;
     if (fits) return OFB_OK;
     rc = launch_step(h, actions_dev, obs_out_dev, bots, stream);
     if (rc != OFB_OK) return rc;

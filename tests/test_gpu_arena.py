@@ -42,6 +42,8 @@ def test_fused_frame_matches_reference_trace(path):
                                              (3000, 32, "stress", 40, 0), (5, 1, "random", 30, 0)])
 def test_fused_frame_equals_step_then_raster(N, S, kind, T, lcap):
     _fused_vs_split(N, S, kind, T, lcap)
+    from ofighters_b200 import _lib
+    assert _lib.load().ofb_debug_last_frame_fused() == 1      # every shape here fits the ring: one launch per frame
 
 
 @pytest.mark.parametrize("knobs", [dict(OFB_FRAME_K="19"), dict(OFB_FRAME_K="9"), dict(OFB_FRAME_LPA="32", OFB_FRAME_SW="8"),
@@ -49,19 +51,22 @@ def test_fused_frame_equals_step_then_raster(N, S, kind, T, lcap):
                                    dict(OFB_FRAME_LPA="16", OFB_FRAME_SW="8", OFB_FRAME_NG="1", OFB_FRAME_NBUF="3"),
                                    dict(OFB_FRAME_LPA="8", OFB_FRAME_SW="8", OFB_FRAME_NG="1", OFB_FRAME_NBUF="3"),
                                    dict(OFB_FRAME_LPA="32", OFB_FRAME_SW="12", OFB_FRAME_NG="1", OFB_FRAME_NBUF="3"),
-                                   dict(OFB_FRAME_LPA="8", OFB_FRAME_SW="8"), dict(OFB_FRAME_POSTCAP="8")],
+                                   dict(OFB_FRAME_LPA="8", OFB_FRAME_SW="8"), dict(OFB_FRAME_POSTCAP="8"), dict(OFB_FRAME_SPLIT="1")],
                          ids=lambda d: ",".join("%s=%s" % (k[10:], v) for k, v in d.items()))
 def test_fused_frame_ring_geometries(knobs, monkeypatch):
     """The shared-memory ring of the fused kernel under other geometries (slots, stepper warps, raster groups)."""
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     _fused_vs_split(9000, 7, "random", 50, 0)
+    from ofighters_b200 import _lib
+    # the geometry is instantiated: this was the fused kernel (OFB_FRAME_SPLIT forces the two-launch form of ofb_frame)
+    assert _lib.load().ofb_debug_last_frame_fused() == (0 if "OFB_FRAME_SPLIT" in knobs else 1)
 
 
 def _fused_vs_split(N, S, kind, T, lcap):
     """ofb_frame_bots == ofb_step_bots + ofb_raster bit for bit (state, observation heads, maps), incl. the episode
     restart, arena ranges longer than the shared-memory ring, saturated laser lists (overflow counted identically) and
-    the two-launch form taken when an arena's list does not fit the ring."""
+    laser lists longer than a ring slot (read back from the arena block)."""
     from ofighters_b200 import ArenaConfig, BatchedBattleground
     mk = lambda: BatchedBattleground(N, ships={kind: S}, config=ArenaConfig(laser_cap=lcap), seed=4242, arena0=17)
     a, b = mk(), mk()
