@@ -51,7 +51,7 @@ def test_fused_frame_equals_step_then_raster(N, S, kind, T, lcap):
                                    dict(OFB_FRAME_LPA="16", OFB_FRAME_SW="8", OFB_FRAME_NG="1", OFB_FRAME_NBUF="3"),
                                    dict(OFB_FRAME_LPA="8", OFB_FRAME_SW="8", OFB_FRAME_NG="1", OFB_FRAME_NBUF="3"),
                                    dict(OFB_FRAME_LPA="32", OFB_FRAME_SW="12", OFB_FRAME_NG="1", OFB_FRAME_NBUF="3"),
-                                   dict(OFB_FRAME_LPA="8", OFB_FRAME_SW="8"), dict(OFB_FRAME_POSTCAP="8"), dict(OFB_FRAME_SPLIT="1")],
+                                   dict(OFB_FRAME_LPA="8", OFB_FRAME_SW="8", OFB_FRAME_NG="2", OFB_FRAME_NBUF="1"), dict(OFB_FRAME_POSTCAP="8"), dict(OFB_FRAME_SPLIT="1")],
                          ids=lambda d: ",".join("%s=%s" % (k[10:], v) for k, v in d.items()))
 def test_fused_frame_ring_geometries(knobs, monkeypatch):
     """The shared-memory ring of the fused kernel under other geometries (slots, stepper warps, raster groups)."""
