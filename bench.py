@@ -170,6 +170,40 @@ def cpu_arm(wl, steps, warmup, n_cap=4096):
         "%d arenas x %d frames of bots+step+raster, oracle/step_c.c (gcc -O2 -fopenmp, %d threads)" % (N, steps, cores)
 
 
+def cpu_policy_rate(cores, batch=8, reps=3):
+    """The policy forward on the host cores: the torch-fp32 restatement of the Keras model (oracle/policy_torch.py, the same
+    arithmetic as model.predict) on a bounded sample of `batch` forwards per call.  -> ship-forwards per second."""
+    import numpy as np  # noqa: F401
+    import torch
+    from oracle import policy_torch as po
+    torch.set_num_threads(cores)
+    w = po.init_weights(0)
+    g = torch.Generator().manual_seed(0)
+    img = (torch.rand((batch, 400, 400, 2), generator=g) < 0.01).float()
+    vec = torch.rand((batch, 8), generator=g) * 400
+    with torch.no_grad():
+        po.forward(w, img, vec)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            act, ptr = po.forward(w, img, vec)
+            po.decode(act, ptr)
+    return batch * reps / (time.perf_counter() - t0)
+
+
+def cpu_arm_with_policy(wl, steps, warmup):
+    """cpu_arm for the policy workloads: the arena rate and the forward rate are measured separately on bounded samples and
+    combined per frame (1 frame = 1 arena step + `policy` ship-forwards per arena), since one full-size CPU frame of 65 536
+    forwards would take minutes."""
+    v, ms, cores, sample = cpu_arm(wl, steps, warmup)
+    if not wl["policy"]:
+        return v, ms, cores, sample, None
+    fwd = cpu_policy_rate(cores)
+    combined = 1.0 / (1.0 / v + wl["policy"] / fwd)
+    sample += "; policy forward: oracle/policy_torch.py (torch fp32, %d threads) on batches of 8 = %.1f ship-forwards/s; " \
+              "combined per frame as 1 / (1 / arena rate + %d / forward rate)" % (cores, fwd, wl["policy"])
+    return combined, 1e3 * min(wl["n"], 4096) / combined, cores, sample, fwd
+
+
 def python_port_rate(ships, frames=100):
     """The pure-Python restatement (same language and structure as the reference) on one core."""
     import numpy as np
@@ -331,13 +365,15 @@ def gpu_arm(args, wl):
     }
     if rank == 0:
         if world == 1:
-            v, ms, cores, sample = cpu_arm(wl, 100, 5)
+            v, ms, cores, sample, fwd = cpu_arm_with_policy(wl, 100, 5)
             try:
                 py = python_port_rate(S)
             except Exception:
                 py = None
             out["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                    "sample": sample, "python_port_env_steps_per_s_1core": py}
+            if fwd is not None:
+                out["cpu_baseline"]["policy_ship_forwards_per_s"] = fwd
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -578,15 +614,17 @@ def main():
         if int(os.environ.get("RANK", "0")) != 0:
             return
         steps = min(args.steps, 400)
-        v, ms, cores, sample = cpu_arm(wl, steps, min(max(args.warmup, 3), 10))
+        v, ms, cores, sample, fwd = cpu_arm_with_policy(wl, steps, min(max(args.warmup, 3), 10))
         print(json.dumps({
-            "impl": "reference", "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster)",
+            "impl": "reference", "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster%s)" %
+                                           (" + policy fwd" if wl["policy"] else ""),
             "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64 laser physics / i32 ship state / u32 bit maps", "data": "synthetic (Philox-seeded)",
             "config": {"workload": args.workload, "desc": wl["desc"],
                        "note": "CPU restatement of the reference's algorithm (the reference is pure Python under "
-                               "/root/reference and is absent on the GPU box); policy forward not included"},
+                               "/root/reference and is absent on the GPU box)" +
+                               ("; policy forward = torch-fp32 restatement of the Keras model" if wl["policy"] else "")},
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return

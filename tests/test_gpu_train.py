@@ -187,3 +187,34 @@ def test_qlearner_follows_qlearnia_bookkeeping():
     assert not torch.equal(w0["upconv4/kernel"], w1["upconv4/kernel"])
     assert torch.equal(tr.model.weights["dense2/kernel"], w1["dense2/kernel"])      # inference engine refreshed after each fit
     assert tr.epsilon.t == 120                           # decay_epsilon once per decision of bot 1 (:399-401)
+
+
+def test_viewer_bridge_streams_one_arena():
+    """what the Tk controller and ActionMapGraph read, pulled from one arena of a GPU-stepped batch."""
+    from ofighters_b200 import BatchedBattleground
+    from ofighters_b200.trainer import TrainerB200
+    from ofighters_b200.viewer import ViewerBridge
+    bg = BatchedBattleground(24, ships={"QlearnIA": 1, "random": 6}, seed=33)
+    tr = TrainerB200(learning_rate=1e-4, batch_size=8, max_ships=32)
+    maps = bg.raster("bits")
+    for _ in range(25):
+        tr.model.act(bg, maps)
+        bg.frame(maps=maps)
+    v = ViewerBridge(bg, arena=5, trainer=tr).refresh(maps)
+    st = {k: t[5].cpu().numpy() for k, t in bg.state().items()}
+    assert [s.body.x for s in v.battleground.ships] == st["ship_x"].tolist()
+    assert len(v.battleground.lasers) == int(st["n_lasers"])
+    # maps: [row = y, col = x] like Observation.ship_map; every live ship's centre pixel is set
+    assert v.ship_map.shape == (400, 400) and v.laser_map.shape == (400, 400)
+    for s in v.battleground.ships:
+        if s.state == "flying" and 0 <= s.body.x < 400 and 0 <= s.body.y < 400:
+            assert v.ship_map[s.body.y, s.body.x] == 1.0
+    assert int(v.ship_map.sum()) == int(np.unpackbits(maps[5, 0].cpu().numpy().view(np.uint8)).sum())
+    # ActionMapGraph's inputs: the attached trainer's act_values (2,) / ptr_values (400, 400) of this arena's policy ship
+    assert tr.act_values.shape == (2,) and tr.ptr_values.shape == (400, 400)
+    r = tr.model.forward(maps[5:6].contiguous(), bg.obs_vec[5, 0].reshape(1, 8), 1, want_ptr=True)
+    assert np.array_equal(v.ptr_values, r["ptr"][0].cpu().numpy())
+    o = v.observation()
+    assert o["pos"] == (v.battleground.ships[0].body.x, v.battleground.ships[0].body.y) and o["dim"] == (400, 400)
+    with pytest.raises(Exception, match="Invalid arena"):
+        ViewerBridge(bg, arena=24)
