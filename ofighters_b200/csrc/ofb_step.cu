@@ -734,8 +734,14 @@ static int launch_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_ou
         dev_cached = h->device;
     }
     const int S = h->lay.S;
-    const int lpa = env_int("OFB_FRAME_LPA", S <= 16 ? 16 : 32);
-    const int sw = env_int("OFB_FRAME_SW", 4), ng = env_int("OFB_FRAME_NG", 2), nbuf = env_int("OFB_FRAME_NBUF", 2);
+    // Geometry (profiles/r01_step_tuning.md): up to a few hundred arenas per SM the kernel is bound by one step latency plus
+    // the per-SM store rate and two raster groups with 4 stepper warps are best (4 096 arenas: 36.8 us); long ranges are
+    // HBM-bound and want stepper throughput instead: one arena per warp, 12 stepper warps, one raster group with three
+    // buffers (131 072 arenas: 917 vs 975 us).
+    const bool long_range = h->n_arenas >= 256ll * n_sm;
+    const int lpa = env_int("OFB_FRAME_LPA", (S <= 16 && !long_range) ? 16 : 32);
+    const int sw = env_int("OFB_FRAME_SW", long_range ? 12 : 4), ng = env_int("OFB_FRAME_NG", long_range ? 1 : 2);
+    const int nbuf = env_int("OFB_FRAME_NBUF", long_range ? 3 : 2);
     bool fits = false;
     int rc = OFB_OK;
     if (!env_int("OFB_FRAME_SPLIT", 0) && lpa >= S) {
