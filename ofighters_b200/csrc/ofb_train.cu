@@ -360,11 +360,12 @@ __global__ void k_tr_conv_bwd_data(const float *__restrict__ dy, const float *__
 
 // dw[ky][kx][ci][co] += sum_{b,y,x} x[b, y+ky-1, x+kx-1, ci] * dy[b, y, x, co];  db[co] += sum dy.
 // One thread per weight; a block walks row segments of TW pixels staged in shared memory and adds its partial sums once.
-#define TR_TW 64
+// One thread per weight x pixel group; a block walks whole image rows staged in (dynamic) shared memory -- the three input
+// rows a 3x3 stencil needs plus the row of output gradients -- and adds its partial sums once at the end.
 template <int CIN, int COUT>
 struct BwdW {
     static constexpr int NW = 9 * CIN * COUT;
-    static constexpr int PG = NW >= 288 ? 1 : (576 / NW > 16 ? 16 : 576 / NW);      // pixel groups sharing a tile
+    static constexpr int PG = NW >= 288 ? 1 : (576 / NW > 16 ? 16 : 576 / NW);      // pixel groups sharing a row
     static constexpr int NT = NW * PG < 64 ? 64 : NW * PG;
 };
 template <int CIN, int COUT>
@@ -372,38 +373,39 @@ __global__ void __launch_bounds__(BwdW<CIN, COUT>::NT)
 k_tr_conv_bwd_weight(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ dw, float *__restrict__ db, int B,
                      int H, int W) {
     constexpr int NW = BwdW<CIN, COUT>::NW, PG = BwdW<CIN, COUT>::PG;
-    __shared__ float xs[3][TR_TW + 2][CIN];
-    __shared__ float dys[TR_TW][COUT];
+    extern __shared__ __align__(16) float tr_smem[];
+    float *xs = tr_smem;                                 // [3][W + 2][CIN]
+    float *dys = tr_smem + 3 * (W + 2) * CIN;            // [W][COUT]
     const int t = threadIdx.x;
     const int wi = t % NW, pg = t / NW;                 // weight index, pixel group (threads beyond NW * PG only help staging)
     const int co = wi % COUT, ci = (wi / COUT) % CIN, kx = (wi / (COUT * CIN)) % 3, ky = wi / (COUT * CIN * 3);
-    const int segs = (W + TR_TW - 1) / TR_TW;
-    const long long tiles = (long long)B * H * segs;
+    const long long rows = (long long)B * H;
     double acc = 0.0, accb = 0.0;
-    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int seg = (int)(tile % segs), yy = (int)((tile / segs) % H);
-        const long long b = tile / ((long long)segs * H);
-        const int xbeg = seg * TR_TW, tw = min(TR_TW, W - xbeg);
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const int yy = (int)(row % H);
+        const long long b = row / H;
         __syncthreads();
-        for (int i = t; i < 3 * (TR_TW + 2) * CIN; i += blockDim.x) {
-            const int c = i % CIN, px = (i / CIN) % (TR_TW + 2), r = i / (CIN * (TR_TW + 2));
-            const int sy = yy + r - 1, sx = xbeg + px - 1;
-            xs[r][px][c] = (sy >= 0 && sy < H && sx >= 0 && sx < W && px < tw + 2) ? x[((b * H + sy) * W + sx) * CIN + c] : 0.0f;
+        for (int i = t; i < 3 * (W + 2) * CIN; i += blockDim.x) {
+            const int c = i % CIN, px = (i / CIN) % (W + 2), r = i / (CIN * (W + 2));
+            const int sy = yy + r - 1, sx = px - 1;
+            xs[i] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? x[((b * H + sy) * W + sx) * CIN + c] : 0.0f;
         }
-        for (int i = t; i < TR_TW * COUT; i += blockDim.x) {
-            const int c = i % COUT, px = i / COUT;
-            dys[px][c] = px < tw ? dy[((b * H + yy) * W + xbeg + px) * COUT + c] : 0.0f;
-        }
+        for (int i = t; i < W * COUT; i += blockDim.x) dys[i] = dy[(b * H + yy) * (long long)W * COUT + i];
         __syncthreads();
         if (pg < PG) {
-            float s = 0.0f;
-#pragma unroll 8
-            for (int px = pg; px < TR_TW; px += PG) s = fmaf(xs[ky][px + kx][ci], dys[px][co], s);
-            acc += (double)s;
+            float s0 = 0.0f, s1 = 0.0f;                  // two chains: the sum over a 400-pixel row stays short in fp32
+            const float *xr = xs + (ky * (W + 2) + kx) * CIN + ci;
+            int px = pg;
+            for (; px + PG < W; px += 2 * PG) {
+                s0 = fmaf(xr[px * CIN], dys[px * COUT + co], s0);
+                s1 = fmaf(xr[(px + PG) * CIN], dys[(px + PG) * COUT + co], s1);
+            }
+            if (px < W) s0 = fmaf(xr[px * CIN], dys[px * COUT + co], s0);
+            acc += (double)s0 + (double)s1;
         }
         if (t < COUT) {
             float s = 0.0f;
-            for (int px = 0; px < TR_TW; px++) s += dys[px][t];
+            for (int px = 0; px < W; px++) s += dys[px * COUT + t];
             accb += (double)s;
         }
     }
@@ -694,8 +696,9 @@ static void conv_fwd(const float *x, const float *w, const float *b, float *y, i
 template <int CIN, int COUT>
 static void conv_bwd(const float *x, const float *dy, const float *w, float *dw, float *db, float *dx, int B, int H, int W, cudaStream_t st) {
     constexpr int NT = BwdW<CIN, COUT>::NT;
-    const long long tiles = (long long)B * H * ((W + TR_TW - 1) / TR_TW);
-    k_tr_conv_bwd_weight<CIN, COUT><<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), NT, 0, st>>>(x, dy, dw, db, B, H, W);
+    const long long rows = (long long)B * H;
+    const size_t smem = (size_t)(3 * (W + 2) * CIN + W * COUT) * sizeof(float);      // <= 40.2 KB (upconv4: 8 -> 1 at W = 400)
+    k_tr_conv_bwd_weight<CIN, COUT><<<(unsigned)(rows < 148 * 4 ? rows : 148 * 4), NT, smem, st>>>(x, dy, dw, db, B, H, W);
     if (dx) k_tr_conv_bwd_data<CIN, COUT><<<blocks_for((long long)B * H * W, 256), 256, 0, st>>>(dy, w, dx, B, H, W);
 }
 
