@@ -109,6 +109,11 @@ int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *obs_host, v
 int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream);
 int ofb_host_wait(ofb_arenas *h);
 
+/* Running statistics of the CURRENT episode, without resetting anything: [sum over ships of score + pending reward, kills,
+ * deaths, shots, ships, arenas] is ADDED into stats_dev[6] (int64; zero it first for totals) -- what the reference's score
+ * consumers read mid-episode (agent.score, battleground.last_x_time_rewards: lib/laser.py:58, lib/ship.py:229). */
+int ofb_stats(const ofb_arenas *h, int64_t *stats_dev, void *stream);
+
 /* Observation.analyse_ship head for every ship (lib/observation.py:101-123). */
 int ofb_obs_vec(const ofb_arenas *h, float *out_dev, void *stream);
 

@@ -99,6 +99,8 @@ def load():
     lib.ofb_reset.argtypes = [vp, vp, vp, vp, vp]
     lib.ofb_step.argtypes = [vp, vp, vp, vp]
     lib.ofb_obs_vec.argtypes = [vp, vp, vp]
+    lib.ofb_stats.argtypes = [vp, vp, vp]
+    lib.ofb_stats.restype = i32
     lib.ofb_raster.argtypes = [vp, vp, i32, vp]
     lib.ofb_bot_actions.argtypes = [vp, i32, vp, u64, i64, u32, vp, vp]
     lib.ofb_random_spawn.argtypes = [i64, i32, i32, i32, u64, i64, u32, vp, vp]

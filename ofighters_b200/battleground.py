@@ -300,6 +300,20 @@ class BatchedBattleground:
         self.launch_count += 1
         return out
 
+    @property
+    def absolute_state(self):
+        """lib/battleground.py:105,117,166: the Observation of the whole battleground built after every frame -- here the
+        two bit maps of every arena plus the per-ship heads (``.maps`` int32 [N,2,W*H/32], ``.obs_vec`` float32 [N,S,8])."""
+        return SimpleNamespace(maps=self.raster("bits"), obs_vec=self.obs_vec, dim=self.dim, time=self.time)
+
+    def running_stats(self):
+        """The current episode's [sum score, kills, deaths, shots, ships, arenas] so far (int64 [6] on the device), without
+        ending the episode -- ``restart`` adds the same six numbers of the finished episode into ``self.stats``."""
+        out = torch.zeros(6, dtype=torch.int64, device=self.device)
+        _lib.check(self._lib.ofb_stats(self._h, _ptr(out), self._stream()))
+        self.launch_count += 1
+        return out
+
     # ------------------------------------------------------------------ state access
     def state(self, fields=None):
         """Export the arena state as a dict of device tensors (names of include/ofb.h)."""

@@ -112,6 +112,41 @@ k_reset(char *state, ArenaLayout lay, const uint8_t *mask, const int32_t *spawn,
     }
 }
 
+// Read-only twin of k_reset's statistics: the RUNNING episode's [sum of score + pending reward, kills, deaths, shots, ships,
+// arenas] added into stats[6] (what the reference's ScoreGraph / last_x_time_rewards consumers read mid-episode).
+__global__ void __launch_bounds__(256)
+k_stats(const char *state, ArenaLayout lay, unsigned long long *stats, long long n_arenas) {
+    __shared__ long long s_acc[6];
+    if (threadIdx.x < 6) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long a = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const bool ok = a < n_arenas;
+    long long acc_score = 0;
+    int k = 0, d = 0, sh = 0;
+    if (ok) {
+        const char *base = state + a * (long long)lay.stride;
+        const int *hdr = reinterpret_cast<const int *>(base);
+        if (lane < lay.S) {
+            const ShipRec r = ship_unpack(reinterpret_cast<const uint4 *>(base + lay.off_ship)[lane]);
+            acc_score = (long long)r.score + r.reward;        // the pending reward folds into the score at the next Agent.step
+        }
+        k = hdr[HDR_KILLS]; d = hdr[HDR_DEATHS]; sh = hdr[HDR_SHOTS];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc_score += __shfl_xor_sync(0xffffffffu, acc_score, o);
+    if (lane == 0 && ok) {
+        atomicAdd((unsigned long long *)&s_acc[0], (unsigned long long)acc_score);
+        atomicAdd((unsigned long long *)&s_acc[1], (unsigned long long)k);
+        atomicAdd((unsigned long long *)&s_acc[2], (unsigned long long)d);
+        atomicAdd((unsigned long long *)&s_acc[3], (unsigned long long)sh);
+        atomicAdd((unsigned long long *)&s_acc[4], (unsigned long long)lay.S);
+        atomicAdd((unsigned long long *)&s_acc[5], 1ull);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && s_acc[threadIdx.x] != 0) atomicAdd(&stats[threadIdx.x], (unsigned long long)s_acc[threadIdx.x]);
+}
+
 // ---------------------------------------------------------------- observation head
 __global__ void k_obs_vec(const char *state, ArenaLayout lay, float4 *out, long long n_ships_total) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,6 +359,15 @@ extern "C" int ofb_reset(ofb_arenas *h, const uint8_t *mask_dev, const int32_t *
     if (!h || !spawn_dev) { ofb_set_error("ofb_reset: null argument"); return OFB_E_ARG; }
     k_reset<<<nblocks(h->n_arenas * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         h->state, h->lay, mask_dev, spawn_dev, reinterpret_cast<unsigned long long *>(stats_dev), h->n_arenas);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+extern "C" int ofb_stats(const ofb_arenas *h, int64_t *stats_dev, void *stream) {
+    if (!h || !stats_dev) { ofb_set_error("ofb_stats: null argument"); return OFB_E_ARG; }
+    if (h->n_arenas == 0) return OFB_OK;
+    k_stats<<<nblocks(h->n_arenas * 32, 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->lay,
+                                                                             reinterpret_cast<unsigned long long *>(stats_dev), h->n_arenas);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

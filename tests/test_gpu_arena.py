@@ -187,6 +187,23 @@ def test_partial_reset_mask_and_arena_view():
     assert view.ships[0].state in ("flying", "destroyed")
 
 
+def test_running_stats_equal_the_episode_end_stats():
+    """ofb_stats mid-episode == what ofb_reset adds at the episode's end (plus the rewards still pending)."""
+    from ofighters_b200 import BatchedBattleground
+    bg = BatchedBattleground(300, ships={"turret": 7}, seed=12)
+    for _ in range(80):
+        bg.frame()
+    run = bg.running_stats().cpu()
+    st = bg.state()
+    assert int(run[0]) == int(st["ship_score"].sum() + st["ship_reward"].sum())
+    assert run[1:].tolist() == [int(st["kills"].sum()), int(st["deaths"].sum()), int(st["shots"].sum()), 300 * 7, 300]
+    bg.restart()
+    end = bg.stats.cpu()
+    assert end[1:].tolist() == run[1:].tolist() and int(end[0]) == int(st["ship_score"].sum())
+    a = bg.absolute_state
+    assert tuple(a.maps.shape) == (300, 2, 5000) and a.obs_vec is bg.obs_vec
+
+
 def test_errors_are_loud():
     from ofighters_b200 import BatchedBattleground
     with pytest.raises(Exception, match="ships argument must be int or dict"):
