@@ -15,14 +15,17 @@ maps = torch.empty((N, 2, 5000), dtype=torch.int32, device=bg.device)
 for _ in range(40):
     bg.frame(maps=maps)
 flush = L2Flush(bg.device)
-prof = torch.zeros((148, 32, 8), dtype=torch.int64, device=bg.device)
+prof = torch.zeros(148 * 32 * 8 + 8, dtype=torch.int64, device=bg.device)
 lib = _lib.load()
 lib.ofb_debug_frame_prof(C.c_void_p(prof.data_ptr()))
 flush()
 bg.frame(maps=maps)
 torch.cuda.synchronize()
 lib.ofb_debug_frame_prof(None)
-p = prof.cpu().numpy()
+sec = prof[148 * 32 * 8:].cpu().numpy()
+p = prof[:148 * 32 * 8].reshape(148, 32, 8).cpu().numpy()
+if sec[7] > 0:
+    print("step_tile sections, cycles per unit (issue+bot | wait load0 | setup | laser loop | ship move | rewards+append | store):", [int(x / sec[7]) for x in sec[:7]], "units", int(sec[7]))
 sw = int(os.environ.get("OFB_FRAME_SW", "4"))
 ng = int(os.environ.get("OFB_FRAME_NG", "2"))
 st = p[:, :sw, :2]
