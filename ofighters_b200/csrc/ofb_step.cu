@@ -360,38 +360,15 @@ __device__ __forceinline__ void step_tile(char *__restrict__ state, const ArenaL
         const unsigned alive_now = (__ballot_sync(FULL, alive) >> gshift) & GM;
         const unsigned any_shooter = __ballot_sync(FULL, shooter) & tmask;
         bool aimed = false, traj = false;
-        // The (shooter, enemy) pairs of the tile are spread over its lanes -- item w = (k-th shooter, enemy j) -- instead of
-        // every shooter walking the S enemies in turn: with the random bots a third of the ships shoot, so one round of LPA
-        // lanes covers the tile and on_trajectory runs once instead of S times under divergence.  "any enemy" is an OR, so the
-        // order does not matter; near_ties counts every borderline pair (no short-circuit after the first touch).
-        const unsigned shm = any_shooter >> gshift;        // bit i = ship i shoots
-        const int n_sh = __popc(shm);
-        const int rounds = __reduce_max_sync(FULL, (n_sh * S + LPA - 1) / LPA);
-        const int my_rank = __popc(shm & ((1u << gl) - 1u));
-        for (int r = 0; r < rounds; r++) {
-            const int wq = r * LPA + gl;
-            const int k = wq / S, j = wq - k * S;
-            const bool item = wq < n_sh * S;
-            const int i = item ? (int)__fns(shm, 0, k + 1) : 0;
-            const int isx = __shfl_sync(FULL, sx, gshift + i), isy = __shfl_sync(FULL, sy, gshift + i);
-            const int ipx = __shfl_sync(FULL, spx, gshift + i), ipy = __shfl_sync(FULL, spy, gshift + i);
-            const int jnx = __shfl_sync(FULL, sx, gshift + j), jny = __shfl_sync(FULL, sy, gshift + j);
-            const int jox = __shfl_sync(FULL, old_x, gshift + j), joy = __shfl_sync(FULL, old_y, gshift + j);
-            bool a_p = false, t_p = false;
-            if (item && j != i && ((alive_now >> j) & 1u)) {
-                const int ox = j < i ? jnx : jox, oy = j < i ? jny : joy;     // j < i has already moved this frame
-                const int ax = ox - ipx, ay = oy - ipy;
-                a_p = ax * ax + ay * ay <= OFB_R_SHIP * OFB_R_SHIP;           // lib/ship.py:165-169
-                t_p = on_trajectory(ipx - isx, ipy - isy, ox - isx, oy - isy, near_ties);
-            }
-            const unsigned ba = (__ballot_sync(FULL, a_p) >> gshift) & GM, bt = (__ballot_sync(FULL, t_p) >> gshift) & GM;
-            if (shooter) {                                 // my items of this round sit on tile lanes [lo, lo + S)
-                const int lo = my_rank * S - r * LPA;
-                const int l0 = max(lo, 0), l1 = min(lo + S, LPA);
-                if (l0 < l1) {
-                    const unsigned m = ((l1 - l0 >= 32) ? 0xffffffffu : ((1u << (l1 - l0)) - 1u)) << l0;
-                    aimed = aimed || (ba & m) != 0u;
-                    traj = traj || (bt & m) != 0u;
+        if (any_shooter) {
+            for (int j = 0; j < S; j++) {
+                const int jnx = __shfl_sync(tmask, sx, gshift + j), jny = __shfl_sync(tmask, sy, gshift + j);
+                const int jox = __shfl_sync(tmask, old_x, gshift + j), joy = __shfl_sync(tmask, old_y, gshift + j);
+                if (shooter && j != gl && ((alive_now >> j) & 1u)) {
+                    const int ox = j < gl ? jnx : jox, oy = j < gl ? jny : joy;
+                    const int ax = ox - spx, ay = oy - spy;
+                    if (ax * ax + ay * ay <= OFB_R_SHIP * OFB_R_SHIP) aimed = true;     // lib/ship.py:165-169
+                    if (!traj && on_trajectory(spx - sx, spy - sy, ox - sx, oy - sy, near_ties)) traj = true;
                 }
             }
         }
