@@ -447,10 +447,12 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
         for _ in range(5):                                # warm-up (module load, clocks)
             fn()
         for _ in range(iters):
-            if flush_buf is not None:
+            nb = nbytes() if callable(nbytes) else nbytes    # (reads the live laser count: a host sync -- before the flush, so
+            if flush_buf is not None:                        #  that the timed launch is queued behind it like in the step loop)
                 flush_buf()
+            else:
+                torch.cuda._sleep(200000)                    # ~100 us of queued work for the same reason
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            nb = nbytes() if callable(nbytes) else nbytes
             a.record(stream)
             fn()
             b.record(stream)
