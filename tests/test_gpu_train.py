@@ -218,3 +218,50 @@ def test_viewer_bridge_streams_one_arena():
     assert o["pos"] == (v.battleground.ships[0].body.x, v.battleground.ships[0].body.y) and o["dim"] == (400, 400)
     with pytest.raises(Exception, match="Invalid arena"):
         ViewerBridge(bg, arena=24)
+
+
+def test_replay_is_the_references_sequence_of_calls():
+    """Trainer.replay (:240-287) spelled out call by call on a twin trainer: sample the minibatch with the same ``random``
+    state, predict on obs and next_obs, build the targets with the oracle's td_targets, then fit on the NEXT observations
+    (``inputs1[i] = img_input`` is evaluated after img_input was rebuilt from next_obs) -- the two trainers must end up with the
+    same weights (fp32 atomics aside) and the same reported loss."""
+    import random
+    from oracle import policy_torch as po
+    from oracle import policy_train_torch as pt
+    from ofighters_b200.trainer import TrainerB200
+    w = po.init_weights(6, randomize_bn=True)
+    bg, _, _ = _arena_batch(12, frames=8, seed=2)
+    a, b = TrainerB200(weights=w, learning_rate=1e-4, batch_size=8), TrainerB200(weights=w, learning_rate=1e-4, batch_size=8)
+    g = torch.Generator().manual_seed(4)
+    prev = None
+    for t in range(6):
+        maps = bg.raster("bits")
+        obs = [(maps[k].clone(), bg.obs_vec[k, 0].clone()) for k in range(12)]
+        if prev is not None:
+            for k in range(12):
+                tr_args = (prev[k][0], prev[k][1], prev[k][2], float(bg.obs_vec[k, 0, 0]), obs[k], bool(t == 5 and k % 3 == 0))
+                a.remember(*tr_args)
+                b.remember(*tr_args)
+        prev = [(obs[k], int(torch.randint(0, 2, (1,), generator=g)), (int(torch.randint(0, 400, (1,), generator=g)),
+                                                                         int(torch.randint(0, 400, (1,), generator=g)))) for k in range(12)]
+        bg.frame()
+    random.seed(7)
+    hist = a.replay(8)
+    # the same thing by hand on the twin
+    random.seed(7)
+    mb = random.sample(b.memory, 8)
+    maps_o, vec_o = torch.stack([m[0][0] for m in mb]), torch.stack([m[0][1] for m in mb])
+    maps_n, vec_n = torch.stack([m[4][0] for m in mb]), torch.stack([m[4][1] for m in mb])
+    act_o, ptr_o = b.predict(maps_o.contiguous(), vec_o)
+    act_n, ptr_n = b.predict(maps_n.contiguous(), vec_n)
+    ta, tp = pt.td_targets(act_o.cpu(), ptr_o.cpu(), act_n.cpu(), ptr_n.cpu(), torch.tensor([m[1] for m in mb]),
+                           torch.tensor([list(m[2]) for m in mb]), torch.tensor([m[3] for m in mb], dtype=torch.float32),
+                           torch.tensor([1 if m[5] else 0 for m in mb]))
+    loss = b.fit(maps_n.contiguous(), vec_n, ta.cuda(), tp.cuda()).cpu()
+    assert hist.history["loss"][0] == pytest.approx(float(loss[0]), rel=1e-5)
+    wa, wb = a.get_weights(), b.get_weights()
+    for k in wa:
+        # conv biases in front of a BatchNormalization: zero gradient, Adam turns the atomics' rounding noise into +-lr steps
+        noise_driven = k.endswith("/bias") and "conv" in k and k != "upconv4/bias"
+        tol = 2.2e-4 if noise_driven else 2e-6 + 1e-5 * float(wb[k].abs().max())
+        assert float((wa[k] - wb[k]).abs().max()) <= tol, k
