@@ -16,6 +16,8 @@ Only the selected arena crosses PCIe (a few KB of state + two 20 KB bit maps + o
 itself never leaves the GPU.  No compute happens here: the state comes from ofb_state_export, the maps from ofb_raster's bit
 planes, the pointer map from ofb_policy_forward.
 """
+from types import SimpleNamespace
+
 import numpy as np
 import torch
 
@@ -68,3 +70,60 @@ class ViewerBridge:
         return dict(reward=float(v[0]), can_shoot=float(v[1]), pointing=(int(v[2]), int(v[3])), dim=(int(v[4]), int(v[5])),
                     pos=(int(v[6]), int(v[7])), done=(s.state != "flying") if s is not None else None,
                     ship_map=self.ship_map, laser_map=self.laser_map)
+
+
+class PlayerBridge:
+    """Human ``Player`` passthrough (lib/player.py:6-63, Ship.read_keys lib/ship.py:233-242): the
+    same event handlers as the reference's Player (without the Tk bindings -- bind them to any event source), and
+    ``write_action`` = ``read_keys``: the pending keys become the int16 action row (shoot, thrust, pointing) of one
+    "external" ship of one arena, the pointing staying where it was unless the cursor moved, then the keys are cleared."""
+
+    def __init__(self, bg, arena=0, ship=0):
+        if not 0 <= arena < bg.n_arenas or not 0 <= ship < bg.ships_number:
+            raise Exception("Invalid arena / ship : ({}, {}).".format(arena, ship))
+        if bg.behaviors[ship] not in ("external", "QlearnIA"):
+            raise Exception("Ship {} is driven by the '{}' device bot: give the player an 'external' ship.".format(
+                ship, bg.behaviors[ship]))
+        self.bg, self.arena, self.ship = bg, int(arena), int(ship)
+        self.shoot = False
+        self.clear_keys()
+
+    # ---- lib/player.py:33-63, event = anything with .x / .y for the cursor
+    def press_shoot(self, event=None):
+        self.actions_set.add("shoot")
+        self.shoot = True
+
+    def unpress_shoot(self, event=None):
+        self.actions_set.discard("shoot")
+        self.shoot = False
+
+    def request_thrust(self, event=None):
+        self.actions_set.add("thrust")
+        self.thrust = True
+
+    def request_turn(self, event):
+        self.actions_set.add("pointing")
+        self.turn = True
+        self.cursor = SimpleNamespace(x=int(event.x), y=int(event.y))
+
+    def clear_keys(self):
+        self.actions_set = set()
+        if self.shoot:
+            self.actions_set.add("shoot")
+        self.thrust = False
+        self.turn = False
+        self.cursor = None
+
+    def write_action(self):
+        """``Ship.read_keys`` (lib/ship.py:233-242) into ``bg.actions[arena, ship]``; call before ``bg.frame()``."""
+        bg = self.bg
+        shoot = "shoot" in self.actions_set
+        thrust = "thrust" in self.actions_set
+        if "pointing" in self.actions_set:
+            px, py = self.cursor.x, self.cursor.y
+        else:                                            # keep the ship's pointing (obs head: pointing_x, pointing_y)
+            px, py = [int(v) for v in bg.obs_vec[self.arena, self.ship, 2:4].tolist()]
+        row = torch.tensor([int(shoot), int(thrust), px, py], dtype=torch.int16, device=bg.device)
+        bg.actions[self.arena, self.ship] = row
+        self.clear_keys()
+        return row

@@ -265,3 +265,27 @@ def test_replay_is_the_references_sequence_of_calls():
         noise_driven = k.endswith("/bias") and "conv" in k and k != "upconv4/bias"
         tol = 2.2e-4 if noise_driven else 2e-6 + 1e-5 * float(wb[k].abs().max())
         assert float((wa[k] - wb[k]).abs().max()) <= tol, k
+
+
+def test_player_bridge_is_read_keys():
+    """Human Player passthrough (lib/player.py, Ship.read_keys): pending keys -> the external ship's action row."""
+    from ofighters_b200 import BatchedBattleground
+    from ofighters_b200.viewer import PlayerBridge
+    from types import SimpleNamespace
+    bg = BatchedBattleground(6, ships={"external": 1, "random": 6}, seed=8)
+    pl = PlayerBridge(bg, arena=2, ship=0)
+    x0, y0 = [int(v) for v in bg.obs_vec[2, 0, 6:8].tolist()]
+    row = pl.write_action().tolist()                     # nothing pressed: no shot, no thrust, pointing unchanged (= own position)
+    assert row == [0, 0, x0, y0]
+    pl.press_shoot()
+    pl.request_thrust()
+    pl.request_turn(SimpleNamespace(x=123, y=45))
+    assert pl.write_action().tolist() == [1, 1, 123, 45]
+    bg.frame()                                           # the six device bots draw their own rows; row (2, 0) is the player's
+    assert [int(v) for v in bg.obs_vec[2, 0, 2:4].tolist()] == [123, 45]
+    assert int(bg.state(("shots",))["shots"][2]) >= 1
+    assert pl.write_action().tolist() == [1, 0, 123, 45]     # the button is still held, thrust was a key press, cursor did not move
+    pl.unpress_shoot()
+    assert pl.write_action().tolist() == [0, 0, 123, 45]
+    with pytest.raises(Exception, match="device bot"):
+        PlayerBridge(bg, arena=0, ship=3)
