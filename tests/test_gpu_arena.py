@@ -63,6 +63,13 @@ def test_fused_frame_ring_geometries(knobs, monkeypatch):
     assert _lib.load().ofb_debug_last_frame_fused() == (0 if "OFB_FRAME_SPLIT" in knobs else 1)
 
 
+@pytest.mark.parametrize("N", [1, 2, 31, 147, 148, 149, 443])
+@pytest.mark.parametrize("S", [2, 7, 20])
+def test_fused_frame_ragged_batches(N, S):
+    """Arena counts around the SM count (one CTA per SM: ranges of 0, 1, 2 and 3 arenas) and other ship counts."""
+    _fused_vs_split(N, S, "turret", 25, 0)
+
+
 def _fused_vs_split(N, S, kind, T, lcap):
     """ofb_frame_bots == ofb_step_bots + ofb_raster bit for bit (state, observation heads, maps), incl. the episode
     restart, arena ranges longer than the shared-memory ring, saturated laser lists (overflow counted identically) and
