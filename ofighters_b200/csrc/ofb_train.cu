@@ -151,24 +151,28 @@ __global__ void k_tr_conv_fwd(const float *__restrict__ x, const float *__restri
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int xx = (int)(i % W), yy = (int)((i / W) % H);
         const long long b = i / ((long long)W * H);
-        float acc[COUT];
+        float acc[COUT], xv[9][CIN];
 #pragma unroll
         for (int co = 0; co < COUT; co++) acc[co] = ws[9 * CIN * COUT + co];
+        // all nine taps are loaded (zeros outside the image) before the first multiply, so their latencies overlap
 #pragma unroll
         for (int ky = 0; ky < 3; ky++) {
-            const int sy = yy + ky - 1;
-            if (sy < 0 || sy >= H) continue;
 #pragma unroll
             for (int kx = 0; kx < 3; kx++) {
-                const int sx = xx + kx - 1;
-                if (sx < 0 || sx >= W) continue;
-                float xv[CIN];
-                load_vec<CIN>(x + ((b * H + sy) * W + sx) * CIN, xv);
+                const int sy = yy + ky - 1, sx = xx + kx - 1;
+                if (sy >= 0 && sy < H && sx >= 0 && sx < W) load_vec<CIN>(x + ((b * H + sy) * W + sx) * CIN, xv[ky * 3 + kx]);
+                else {
 #pragma unroll
-                for (int ci = 0; ci < CIN; ci++) {
-#pragma unroll
-                    for (int co = 0; co < COUT; co++) acc[co] = fmaf(xv[ci], ws[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[co]);
+                    for (int ci = 0; ci < CIN; ci++) xv[ky * 3 + kx][ci] = 0.0f;
                 }
+            }
+        }
+#pragma unroll
+        for (int tp = 0; tp < 9; tp++) {
+#pragma unroll
+            for (int ci = 0; ci < CIN; ci++) {
+#pragma unroll
+                for (int co = 0; co < COUT; co++) acc[co] = fmaf(xv[tp][ci], ws[(tp * CIN + ci) * COUT + co], acc[co]);
             }
         }
         store_vec<COUT>(y + i * COUT, acc);
@@ -181,10 +185,13 @@ __global__ void k_tr_chan_sums(const float *__restrict__ y, long long n_px, int 
 #pragma unroll
     for (int j = 0; j < 16; j++) v[j] = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
-        for (int c = 0; c < C; c++) {
-            const double t = (double)y[i * C + c];
-            v[c] += t;
-            v[8 + c] += t * t;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {                    // fixed trip count: the accumulators stay in registers
+            if (c < C) {
+                const double t = (double)y[i * C + c];
+                v[c] += t;
+                v[8 + c] += t * t;
+            }
         }
     }
     block_accumulate<16>(v, sums, 16);
@@ -239,29 +246,47 @@ __global__ void k_tr_bn_relu_pool(const float *__restrict__ y, const float *__re
     }
 }
 
-// a[b, Y, X, c] = bilinear x2 (TF2 half-pixel centres, edge clamp) of relu(bn(src)) (or of src itself when mean == NULL)
+// The 2 x 2 source pixels and weights of output pixel (Y, X) of a bilinear x2 (TF2 half-pixel centres, edge clamp):
+// Y = 2i: rows i-1 (1/4), i (3/4);  Y = 2i+1: rows i (3/4), i+1 (1/4); clamped to the image
+struct UpTap { int ia, ib, ja, jb; float wy, wx; };
+__device__ __forceinline__ UpTap up_tap(int Y, int X, int h, int w) {
+    UpTap t;
+    t.ia = (Y & 1) ? (Y >> 1) : max((Y >> 1) - 1, 0);
+    t.ib = (Y & 1) ? min((Y >> 1) + 1, h - 1) : (Y >> 1);
+    t.wy = (Y & 1) ? 0.75f : 0.25f;
+    t.ja = (X & 1) ? (X >> 1) : max((X >> 1) - 1, 0);
+    t.jb = (X & 1) ? min((X >> 1) + 1, w - 1) : (X >> 1);
+    t.wx = (X & 1) ? 0.75f : 0.25f;
+    return t;
+}
+// a[b, Y, X, :] = bilinear x2 of relu(bn(src)) (or of src itself when mean == NULL); one thread per output pixel
+template <int C>
 __global__ void k_tr_upsample(const float *__restrict__ src, const float *__restrict__ mean, const float *__restrict__ var,
                               const float *__restrict__ gamma, const float *__restrict__ beta, float eps, float *__restrict__ a,
-                              int B, int h, int w, int C) {
+                              int B, int h, int w) {
     const int H = 2 * h, W = 2 * w;
-    const long long n = (long long)B * H * W * C;
+    const long long n = (long long)B * H * W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C), X = (int)((i / C) % W), Y = (int)((i / ((long long)C * W)) % H);
-        const long long b = i / ((long long)C * W * H);
-        // Y = 2i: rows i-1 (1/4), i (3/4);  Y = 2i+1: rows i (3/4), i+1 (1/4); clamped
-        const int ia = (Y & 1) ? (Y >> 1) : max((Y >> 1) - 1, 0), ib = (Y & 1) ? min((Y >> 1) + 1, h - 1) : (Y >> 1);
-        const float wa_y = (Y & 1) ? 0.75f : 0.25f;
-        const int ja = (X & 1) ? (X >> 1) : max((X >> 1) - 1, 0), jb = (X & 1) ? min((X >> 1) + 1, w - 1) : (X >> 1);
-        const float wa_x = (X & 1) ? 0.75f : 0.25f;
-        float v00 = src[((b * h + ia) * w + ja) * C + c], v01 = src[((b * h + ia) * w + jb) * C + c];
-        float v10 = src[((b * h + ib) * w + ja) * C + c], v11 = src[((b * h + ib) * w + jb) * C + c];
-        if (mean) {
-            const float m = mean[c], r = rsqrtf(var[c] + eps), g = gamma[c], be = beta[c];
-            v00 = bn_relu(v00, m, r, g, be); v01 = bn_relu(v01, m, r, g, be);
-            v10 = bn_relu(v10, m, r, g, be); v11 = bn_relu(v11, m, r, g, be);
+        const int X = (int)(i % W), Y = (int)((i / W) % H);
+        const long long b = i / ((long long)W * H);
+        const UpTap t = up_tap(Y, X, h, w);
+        float v00[C], v01[C], v10[C], v11[C], o[C];
+        load_vec<C>(src + ((b * h + t.ia) * w + t.ja) * C, v00);
+        load_vec<C>(src + ((b * h + t.ia) * w + t.jb) * C, v01);
+        load_vec<C>(src + ((b * h + t.ib) * w + t.ja) * C, v10);
+        load_vec<C>(src + ((b * h + t.ib) * w + t.jb) * C, v11);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            float p00 = v00[c], p01 = v01[c], p10 = v10[c], p11 = v11[c];
+            if (mean) {
+                const float m = mean[c], r = rsqrtf(var[c] + eps), g = gamma[c], be = beta[c];
+                p00 = bn_relu(p00, m, r, g, be); p01 = bn_relu(p01, m, r, g, be);
+                p10 = bn_relu(p10, m, r, g, be); p11 = bn_relu(p11, m, r, g, be);
+            }
+            const float top = p00 * t.wx + p01 * (1.0f - t.wx), bot = p10 * t.wx + p11 * (1.0f - t.wx);
+            o[c] = top * t.wy + bot * (1.0f - t.wy);
         }
-        const float top = v00 * wa_x + v01 * (1.0f - wa_x), bot = v10 * wa_x + v11 * (1.0f - wa_x);
-        a[i] = top * wa_y + bot * (1.0f - wa_y);
+        store_vec<C>(a + i * C, o);
     }
 }
 
@@ -334,24 +359,27 @@ __global__ void k_tr_conv_bwd_data(const float *__restrict__ dy, const float *__
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int xx = (int)(i % W), yy = (int)((i / W) % H);
         const long long b = i / ((long long)W * H);
-        float acc[CIN];
+        float acc[CIN], gv[9][COUT];
 #pragma unroll
         for (int ci = 0; ci < CIN; ci++) acc[ci] = 0.0f;
 #pragma unroll
         for (int ky = 0; ky < 3; ky++) {
-            const int oy = yy + 1 - ky;
-            if (oy < 0 || oy >= H) continue;
 #pragma unroll
             for (int kx = 0; kx < 3; kx++) {
-                const int ox = xx + 1 - kx;
-                if (ox < 0 || ox >= W) continue;
-                float gv[COUT];
-                load_vec<COUT>(dy + ((b * H + oy) * W + ox) * COUT, gv);
+                const int oy = yy + 1 - ky, ox = xx + 1 - kx;
+                if (oy >= 0 && oy < H && ox >= 0 && ox < W) load_vec<COUT>(dy + ((b * H + oy) * W + ox) * COUT, gv[ky * 3 + kx]);
+                else {
 #pragma unroll
-                for (int co = 0; co < COUT; co++) {
-#pragma unroll
-                    for (int ci = 0; ci < CIN; ci++) acc[ci] = fmaf(gv[co], ws[((ky * 3 + kx) * CIN + ci) * COUT + co], acc[ci]);
+                    for (int co = 0; co < COUT; co++) gv[ky * 3 + kx][co] = 0.0f;
                 }
+            }
+        }
+#pragma unroll
+        for (int tp = 0; tp < 9; tp++) {
+#pragma unroll
+            for (int co = 0; co < COUT; co++) {
+#pragma unroll
+                for (int ci = 0; ci < CIN; ci++) acc[ci] = fmaf(gv[tp][co], ws[(tp * CIN + ci) * COUT + co], acc[ci]);
             }
         }
         store_vec<CIN>(dx + i * CIN, acc);
@@ -366,7 +394,8 @@ template <int CIN, int COUT>
 struct BwdW {
     static constexpr int NW = 9 * CIN * COUT;
     static constexpr int PG = NW >= 288 ? 1 : (576 / NW > 16 ? 16 : 576 / NW);      // pixel groups sharing a row
-    static constexpr int NT = NW * PG < 64 ? 64 : NW * PG;
+    static constexpr int NT0 = NW * PG < 64 ? 64 : NW * PG;
+    static constexpr int NT = NT0 < 32 * COUT ? 32 * COUT : (NT0 + 31) / 32 * 32;       // whole warps, one per bias channel at least
 };
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(BwdW<CIN, COUT>::NT)
@@ -385,12 +414,36 @@ k_tr_conv_bwd_weight(const float *__restrict__ x, const float *__restrict__ dy, 
         const int yy = (int)(row % H);
         const long long b = row / H;
         __syncthreads();
-        for (int i = t; i < 3 * (W + 2) * CIN; i += blockDim.x) {
-            const int c = i % CIN, px = (i / CIN) % (W + 2), r = i / (CIN * (W + 2));
-            const int sy = yy + r - 1, sx = px - 1;
-            xs[i] = (sy >= 0 && sy < H && sx >= 0 && sx < W) ? x[((b * H + sy) * W + sx) * CIN + c] : 0.0f;
+        // stage the three input rows (zero halo pixel on either side, zero rows outside the image) and the gradient row in
+        // 16 / 8 / 4-byte chunks, several loads in flight per thread
+        constexpr int CHX = (CIN % 4 == 0) ? 4 : ((CIN % 2 == 0) ? 2 : 1), CHY = (COUT % 4 == 0) ? 4 : ((COUT % 2 == 0) ? 2 : 1);
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const int sy = yy + r - 1;
+            float *dst = xs + (r * (W + 2) + 1) * CIN;
+            const float *src = x + ((b * H + sy) * W) * CIN;
+            const bool inside = sy >= 0 && sy < H;
+#pragma unroll 4
+            for (int q = t; q < W * CIN / CHX; q += blockDim.x) {
+                float v[CHX];
+                if (inside) load_vec<CHX>(src + q * CHX, v);
+                else {
+#pragma unroll
+                    for (int e = 0; e < CHX; e++) v[e] = 0.0f;
+                }
+                store_vec<CHX>(dst + q * CHX, v);
+            }
+            if (t < CIN) { xs[r * (W + 2) * CIN + t] = 0.0f; xs[(r * (W + 2) + W + 1) * CIN + t] = 0.0f; }
         }
-        for (int i = t; i < W * COUT; i += blockDim.x) dys[i] = dy[(b * H + yy) * (long long)W * COUT + i];
+        {
+            const float *src = dy + (b * H + yy) * (long long)W * COUT;
+#pragma unroll 4
+            for (int q = t; q < W * COUT / CHY; q += blockDim.x) {
+                float v[CHY];
+                load_vec<CHY>(src + q * CHY, v);
+                store_vec<CHY>(dys + q * CHY, v);
+            }
+        }
         __syncthreads();
         if (pg < PG) {
             float s0 = 0.0f, s1 = 0.0f;                  // two chains: the sum over a 400-pixel row stays short in fp32
@@ -403,14 +456,18 @@ k_tr_conv_bwd_weight(const float *__restrict__ x, const float *__restrict__ dy, 
             if (px < W) s0 = fmaf(xr[px * CIN], dys[px * COUT + co], s0);
             acc += (double)s0 + (double)s1;
         }
-        if (t < COUT) {
+        if ((t >> 5) < COUT) {                           // warp co sums channel co of the row, lane-strided
+            const int cb = t >> 5;
             float s = 0.0f;
-            for (int px = 0; px < W; px++) s += dys[px * COUT + t];
+            for (int px = t & 31; px < W; px += 32) s += dys[px * COUT + cb];
             accb += (double)s;
         }
     }
     if (pg < PG) atomicAdd(&dw[wi], (float)acc);
-    if (t < COUT) atomicAdd(&db[t], (float)accb);
+    if ((t >> 5) < COUT) {
+        accb = warp_sum(accb);
+        if ((t & 31) == 0) atomicAdd(&db[t >> 5], (float)accb);
+    }
 }
 
 // BatchNormalization + ReLU + MaxPool backward, pass 1: s1 = sum dz, s2 = sum dz * xhat over the layer, where dz is the
@@ -428,7 +485,9 @@ __global__ void k_tr_bnpool_bwd_reduce(const float *__restrict__ y, const float 
         const int xo = (int)(i % Wo), yo = (int)((i / Wo) % Ho);
         const long long b = i / ((long long)Wo * Ho);
         const long long base = ((b * H + 2 * yo) * W + 2 * xo) * C;
-        for (int c = 0; c < C; c++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            if (c >= C) continue;
             const float m = mean[c], r = rsqrtf(var[c] + eps);
             float zmax;
             const int k = pool_argmax(y, base, W, C, c, m, r, gamma[c], beta[c], zmax);
@@ -442,26 +501,51 @@ __global__ void k_tr_bnpool_bwd_reduce(const float *__restrict__ y, const float 
     }
     block_accumulate<16>(v, sums, 16);
 }
-// pass 2: dy[b, y, x, c] = gamma * rstd * (dz - s1 / N - xhat * s2 / N)
+// pass 2: dy[b, y, x, c] = gamma * rstd * (dz - s1 / N - xhat * s2 / N).  One thread per 2x2 window and all 8 channels (the
+// trunk's convolutions all have 8): the window's 4 pixels are read and written as float4 pairs.
 __global__ void k_tr_bnpool_bwd_apply(const float *__restrict__ y, const float *__restrict__ mean, const float *__restrict__ var,
                                       const float *__restrict__ gamma, const float *__restrict__ beta, float eps,
                                       const float *__restrict__ dp, long long dp_stride, const double *__restrict__ sums,
-                                      float *__restrict__ dy, int B, int H, int W, int C) {
-    const int Wo = W / 2;
-    const long long n = (long long)B * H * W * C;
+                                      float *__restrict__ dy, int B, int H, int W) {
+    constexpr int C = 8;
+    __shared__ float cm[C], cr[C], cg[C], cb[C], c1[C], c2[C];
     const double inv_n = 1.0 / (double)((long long)B * H * W);
+    if (threadIdx.x < C) {
+        const int c = threadIdx.x;
+        cm[c] = mean[c]; cr[c] = rsqrtf(var[c] + eps); cg[c] = gamma[c]; cb[c] = beta[c];
+        c1[c] = (float)(sums[c] * inv_n); c2[c] = (float)(sums[8 + c] * inv_n);
+    }
+    __syncthreads();
+    const int Ho = H / 2, Wo = W / 2;
+    const long long n = (long long)B * Ho * Wo;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C), xx = (int)((i / C) % W), yy = (int)((i / ((long long)C * W)) % H);
-        const long long b = i / ((long long)C * W * H);
-        const int yo = yy >> 1, xo = xx >> 1;
+        const int xo = (int)(i % Wo), yo = (int)((i / Wo) % Ho);
+        const long long b = i / ((long long)Wo * Ho);
         const long long base = ((b * H + 2 * yo) * W + 2 * xo) * C;
-        const float m = mean[c], r = rsqrtf(var[c] + eps);
-        float zmax;
-        const int k = pool_argmax(y, base, W, C, c, m, r, gamma[c], beta[c], zmax);
-        float dz = 0.0f;
-        if (zmax > 0.0f && k == ((yy & 1) * 2 + (xx & 1))) dz = dp[b * dp_stride + ((long long)yo * Wo + xo) * C + c];
-        const float xhat = (y[i] - m) * r;
-        dy[i] = gamma[c] * r * (dz - (float)(sums[c] * inv_n) - xhat * (float)(sums[8 + c] * inv_n));
+        const long long off[4] = {base, base + C, base + (long long)W * C, base + (long long)W * C + C};
+        float v[4][C], g[C];
+#pragma unroll
+        for (int q = 0; q < 4; q++) load_vec<C>(y + off[q], v[q]);
+        load_vec<C>(dp + b * dp_stride + ((long long)yo * Wo + xo) * C, g);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            const float m = cm[c], r = cr[c], ga = cg[c], be = cb[c];
+            float zmax = bn_relu(v[0][c], m, r, ga, be);
+            int k = 0;
+#pragma unroll
+            for (int q = 1; q < 4; q++) {                // first maximum in window order, like pool_argmax
+                const float z = bn_relu(v[q][c], m, r, ga, be);
+                if (z > zmax) { zmax = z; k = q; }
+            }
+            const float dz = zmax > 0.0f ? g[c] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const float xhat = (v[q][c] - m) * r;
+                v[q][c] = ga * r * ((q == k ? dz : 0.0f) - c1[c] - xhat * c2[c]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) store_vec<C>(dy + off[q], v[q]);
     }
 }
 // BatchNormalization + ReLU backward (no pooling; the pointer head), in place on dz [n_px, C]
@@ -472,7 +556,9 @@ __global__ void k_tr_bn_bwd_reduce(const float *__restrict__ y, const float *__r
 #pragma unroll
     for (int j = 0; j < 16; j++) v[j] = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_px; i += (long long)gridDim.x * blockDim.x) {
-        for (int c = 0; c < C; c++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            if (c >= C) continue;
             const float m = mean[c], r = rsqrtf(var[c] + eps);
             const float xhat = (y[i * C + c] - m) * r;
             if (fmaf(xhat, gamma[c], beta[c]) > 0.0f) {
@@ -502,22 +588,42 @@ __global__ void k_tr_bn_param_grads(const double *__restrict__ sums, int C, floa
     if (c < C) { dgamma[c] = (float)sums[8 + c]; dbeta[c] = (float)sums[c]; }
 }
 
-// transpose of k_tr_upsample's stencil: dsrc[b, i, j, c] += weights * da[b, Y, X, c]   (dsrc zeroed by the caller)
-__global__ void k_tr_upsample_bwd(const float *__restrict__ da, float *__restrict__ dsrc, int B, int h, int w, int C) {
+// transpose of k_tr_upsample's stencil as a gather: source row i feeds output rows 2i-1 (1/4), 2i (3/4), 2i+1 (3/4),
+// 2i+2 (1/4); at the edges the clamped tap folds its 1/4 onto the edge row (2i resp. 2i+1).  One thread per source pixel.
+__device__ __forceinline__ void up_bwd_w(int i, int h, float (&wt)[4]) {
+    wt[0] = i > 0 ? 0.25f : 0.0f;
+    wt[1] = i == 0 ? 1.0f : 0.75f;
+    wt[2] = i == h - 1 ? 1.0f : 0.75f;
+    wt[3] = i < h - 1 ? 0.25f : 0.0f;
+}
+template <int C>
+__global__ void k_tr_upsample_bwd(const float *__restrict__ da, float *__restrict__ dsrc, int B, int h, int w) {
     const int H = 2 * h, W = 2 * w;
-    const long long n = (long long)B * H * W * C;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % C), X = (int)((i / C) % W), Y = (int)((i / ((long long)C * W)) % H);
-        const long long b = i / ((long long)C * W * H);
-        const int ia = (Y & 1) ? (Y >> 1) : max((Y >> 1) - 1, 0), ib = (Y & 1) ? min((Y >> 1) + 1, h - 1) : (Y >> 1);
-        const float wa_y = (Y & 1) ? 0.75f : 0.25f;
-        const int ja = (X & 1) ? (X >> 1) : max((X >> 1) - 1, 0), jb = (X & 1) ? min((X >> 1) + 1, w - 1) : (X >> 1);
-        const float wa_x = (X & 1) ? 0.75f : 0.25f;
-        const float g = da[i];
-        atomicAdd(&dsrc[((b * h + ia) * w + ja) * C + c], g * wa_y * wa_x);
-        atomicAdd(&dsrc[((b * h + ia) * w + jb) * C + c], g * wa_y * (1.0f - wa_x));
-        atomicAdd(&dsrc[((b * h + ib) * w + ja) * C + c], g * (1.0f - wa_y) * wa_x);
-        atomicAdd(&dsrc[((b * h + ib) * w + jb) * C + c], g * (1.0f - wa_y) * (1.0f - wa_x));
+    const long long n = (long long)B * h * w;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx % w), i = (int)((idx / w) % h);
+        const long long b = idx / ((long long)w * h);
+        float wr[4], wc[4], acc[C];
+        up_bwd_w(i, h, wr);
+        up_bwd_w(j, w, wc);
+#pragma unroll
+        for (int c = 0; c < C; c++) acc[c] = 0.0f;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            const int Y = 2 * i - 1 + a;
+            if (wr[a] == 0.0f) continue;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int X = 2 * j - 1 + e;
+                if (wc[e] == 0.0f) continue;
+                float g[C];
+                load_vec<C>(da + ((b * H + Y) * W + X) * C, g);
+                const float wgt = wr[a] * wc[e];
+#pragma unroll
+                for (int c = 0; c < C; c++) acc[c] = fmaf(g[c], wgt, acc[c]);
+            }
+        }
+        store_vec<C>(dsrc + idx * C, acc);
     }
 }
 
@@ -736,14 +842,15 @@ static int forward_train(ofb_trainer *t, const uint32_t *maps, const float *vec,
         const ConvP &c = T.up[j];
         const int h = hs[j], H = 2 * h;
         // input of stage j: u0 (already activated) or relu(bn(yu[j-1]))
-        if (j == 0)
-            k_tr_upsample<<<blocks_for((long long)B * H * H * cin[j], 256), 256, 0, st>>>(t->u0, nullptr, nullptr, nullptr, nullptr, eps,
-                                                                                          t->a[j], B, h, h, cin[j]);
-        else {
-            const ConvP &pc = T.up[j - 1];
-            k_tr_upsample<<<blocks_for((long long)B * H * H * cin[j], 256), 256, 0, st>>>(
-                t->yu[j - 1], t->bn_mean + (4 + j - 1) * 8, t->bn_var + (4 + j - 1) * 8, P + pc.g.off, P + pc.be.off, eps, t->a[j], B, h, h,
-                cin[j]);
+        {
+            const float *src = j == 0 ? t->u0 : t->yu[j - 1];
+            const float *mean = j == 0 ? nullptr : t->bn_mean + (4 + j - 1) * 8, *var = j == 0 ? nullptr : t->bn_var + (4 + j - 1) * 8;
+            const float *ga = j == 0 ? nullptr : P + T.up[j - 1].g.off, *be = j == 0 ? nullptr : P + T.up[j - 1].be.off;
+            const unsigned nb = blocks_for((long long)B * H * H, 256);
+            if (cin[j] == 1) k_tr_upsample<1><<<nb, 256, 0, st>>>(src, mean, var, ga, be, eps, t->a[j], B, h, h);
+            else if (cin[j] == 2) k_tr_upsample<2><<<nb, 256, 0, st>>>(src, mean, var, ga, be, eps, t->a[j], B, h, h);
+            else if (cin[j] == 4) k_tr_upsample<4><<<nb, 256, 0, st>>>(src, mean, var, ga, be, eps, t->a[j], B, h, h);
+            else k_tr_upsample<8><<<nb, 256, 0, st>>>(src, mean, var, ga, be, eps, t->a[j], B, h, h);
         }
         if (j == 0) conv_fwd<1, 2>(t->a[j], P + c.k.off, P + c.b.off, t->yu[j], B, H, H, st);
         else if (j == 1) conv_fwd<2, 4>(t->a[j], P + c.k.off, P + c.b.off, t->yu[j], B, H, H, st);
@@ -825,8 +932,11 @@ extern "C" int ofb_trainer_fit(ofb_trainer *t, const uint32_t *maps, const float
         else conv_bwd<1, 2>(t->a[j], t->g0, P + c.k.off, G + c.k.off, G + c.b.off, t->g1, B, H, H, st);
         // g1 = d a[j] [B,H,H,cin] -> gradient w.r.t. the stage input [B,h,h,cin] (for j = 0: u0 [B,625])
         float *dst = j == 0 ? t->gu : t->g0;
-        TR_CHECK(cudaMemsetAsync(dst, 0, (size_t)B * h * h * cin[j] * sizeof(float), st));
-        k_tr_upsample_bwd<<<blocks_for(npx * cin[j], 256), 256, 0, st>>>(t->g1, dst, B, h, h, cin[j]);
+        const unsigned nb = blocks_for((long long)B * h * h, 128);
+        if (cin[j] == 1) k_tr_upsample_bwd<1><<<nb, 128, 0, st>>>(t->g1, dst, B, h, h);
+        else if (cin[j] == 2) k_tr_upsample_bwd<2><<<nb, 128, 0, st>>>(t->g1, dst, B, h, h);
+        else if (cin[j] == 4) k_tr_upsample_bwd<4><<<nb, 128, 0, st>>>(t->g1, dst, B, h, h);
+        else k_tr_upsample_bwd<8><<<nb, 128, 0, st>>>(t->g1, dst, B, h, h);
     }
     // ---- dense part
     k_tr_relu_mask<<<blocks_for((long long)B * 625, 128), 128, 0, st>>>(t->u0, t->gu, (long long)B * 625);
@@ -852,8 +962,8 @@ extern "C" int ofb_trainer_fit(ofb_trainer *t, const uint32_t *maps, const float
         const float *mean = t->bn_mean + i * 8, *var = t->bn_var + i * 8;
         k_tr_bnpool_bwd_reduce<<<blocks_for(npx / 4, 256, 148 * 4), 256, 0, st>>>(t->y[i], mean, var, P + c.g.off, P + c.be.off, eps, dp,
                                                                                   dp_stride, B, H, H, 8, s);
-        k_tr_bnpool_bwd_apply<<<blocks_for(npx * 8, 256), 256, 0, st>>>(t->y[i], mean, var, P + c.g.off, P + c.be.off, eps, dp, dp_stride, s,
-                                                                        t->g1, B, H, H, 8);
+        k_tr_bnpool_bwd_apply<<<blocks_for(npx / 4, 128), 128, 0, st>>>(t->y[i], mean, var, P + c.g.off, P + c.be.off, eps, dp, dp_stride, s,
+                                                                        t->g1, B, H, H);
         k_tr_bn_param_grads<<<1, 32, 0, st>>>(s, 8, G + c.g.off, G + c.be.off);
         if (i == 0) conv_bwd<2, 8>(t->x0, t->g1, P + c.k.off, G + c.k.off, G + c.b.off, nullptr, B, H, H, st);
         else conv_bwd<8, 8>(t->p[i - 1], t->g1, P + c.k.off, G + c.k.off, G + c.b.off, t->g0, B, H, H, st);
