@@ -87,6 +87,8 @@ class ClockSampler:
             self._stop.wait(0.05)
 
     def start(self):
+        if os.environ.get("OFB_BENCH_NO_SAMPLER"):        # diagnostic: is the NVML polling visible in the step times?
+            return
         if self.nv is not None:
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
@@ -323,7 +325,11 @@ def gpu_arm(args, wl):
     clocks = sampler.stop()
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    per_rank_ms = [total_ms / steps]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) / steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     bg.check_overflow()
@@ -351,7 +357,7 @@ def gpu_arm(args, wl):
                    "episode": "restart every 200 frames inside the timed region",
                    "l2": (flush_buf.describe() if flush_needed
                           else "working set %.0f MB > L2" % ((state_bytes + maps.numel() * 4) / 1e6)),
-                   "wall_s_timed_region": wall,
+                   "wall_s_timed_region": wall, "ms_per_step_by_rank": per_rank_ms,
                    **({"learning": {"replays_reduced": float(loss_stats[1].item()),
                                     "pending_replays": len(learner.losses) if learner is not None else 0,
                                     "mean_replay_loss": ((float(loss_stats[0].item()) + (sum(learner.losses) if learner is not None else 0.0))
@@ -374,7 +380,7 @@ def gpu_arm(args, wl):
                                    "sample": sample, "python_port_env_steps_per_s_1core": py}
             if fwd is not None:
                 out["cpu_baseline"]["policy_ship_forwards_per_s"] = fwd
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -598,7 +604,30 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
 
 
 # ----------------------------------------------------------------------------- main
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout: libraries print there too (NCCL's version banner, torchrun notices), so
+    everything but the final line is sent to stderr at the file-descriptor level."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _JSON_FD is None:
+        os.write(1, line)
+    else:
+        os.write(_JSON_FD, line)
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -617,7 +646,7 @@ def main():
             return
         steps = min(args.steps, 400)
         v, ms, cores, sample, fwd = cpu_arm_with_policy(wl, steps, min(max(args.warmup, 3), 10))
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster%s)" %
                                            (" + policy fwd" if wl["policy"] else ""),
             "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
