@@ -673,7 +673,11 @@ extern "C" int ofb_step_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_d
 // ---- fused frame: launch ------------------------------------------------------------------------------------------
 int ofb_raster_bits_launch(const ofb_arenas *h, void *out_dev, cudaStream_t st);     // ofb_raster.cu
 
+// Tuning knobs of the fused frame kernel (experiments and the geometry tests): only looked at when OFB_FRAME_TUNE is set, so
+// that a production launch costs one getenv.
+static thread_local bool g_frame_tune = false;
 static int env_int(const char *name, int dflt) {
+    if (!g_frame_tune) return dflt;
     const char *v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
@@ -727,6 +731,10 @@ static int launch_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_ou
     float4 *obs = reinterpret_cast<float4 *>(obs_out_dev);
     uint32_t *maps = reinterpret_cast<uint32_t *>(maps_dev);
     if (h->n_arenas == 0) return OFB_OK;
+    {
+        const char *tune = getenv("OFB_FRAME_TUNE");
+        g_frame_tune = tune && *tune && *tune != '0';
+    }
     static thread_local int n_sm = 0, smem_max = 0, dev_cached = -1;
     if (dev_cached != h->device) {
         OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, h->device));

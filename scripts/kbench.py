@@ -47,7 +47,7 @@ def run(N, S, bot, lcap, warm_frames):
     out = {"flush": FLUSH_MODE, "N": N, "S": S, "bot": bot, "live_lasers_per_arena": live / N, "stride": bg.state_stride,
            "us": {"bots": t_bot, "step_cold": t_step, "step_hot_l2": t_step_hot, "raster": t_ras, "frame+raster": t_frame, "fused_frame": t_fused},
            "fused_env_steps_per_s": N / t_fused * 1e6, "fused_frac": (step_bytes + N * 40000) / t_fused / 1e3 / PEAK,
-           "frame_knobs": {k: os.environ.get(k) for k in ("OFB_FRAME_LPA", "OFB_FRAME_SW", "OFB_FRAME_NG", "OFB_FRAME_NBUF", "OFB_FRAME_K")},
+           "frame_knobs": {k: os.environ.get(k) for k in ("OFB_FRAME_TUNE", "OFB_FRAME_LPA", "OFB_FRAME_SW", "OFB_FRAME_NG", "OFB_FRAME_NBUF", "OFB_FRAME_K")},
            "step_alg_GBs": step_bytes / t_step / 1e3, "step_frac": step_bytes / t_step / 1e3 / PEAK,
            "raster_alg_GBs": N * 40000 / t_ras / 1e3, "raster_frac": N * 40000 / t_ras / 1e3 / PEAK,
            "env_steps_per_s": N / t_frame * 1e6}

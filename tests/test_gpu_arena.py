@@ -55,6 +55,7 @@ def test_fused_frame_equals_step_then_raster(N, S, kind, T, lcap):
                          ids=lambda d: ",".join("%s=%s" % (k[10:], v) for k, v in d.items()))
 def test_fused_frame_ring_geometries(knobs, monkeypatch):
     """The shared-memory ring of the fused kernel under other geometries (slots, stepper warps, raster groups)."""
+    monkeypatch.setenv("OFB_FRAME_TUNE", "1")            # the knobs are only read when tuning is switched on
     for k, v in knobs.items():
         monkeypatch.setenv(k, v)
     _fused_vs_split(9000, 7, "random", 50, 0)
