@@ -293,3 +293,23 @@ def test_player_bridge_is_read_keys():
     assert pl.write_action().tolist() == [0, 0, 123, 45]
     with pytest.raises(Exception, match="device bot"):
         PlayerBridge(bg, arena=0, ship=3)
+
+
+def test_repeated_fit_descends_on_the_device():
+    """Ten Adam steps on one fixed batch: the loss the kernels report goes down (and keeps tracking the oracle's trajectory)."""
+    from oracle import policy_torch as po
+    from oracle import policy_train_torch as pt
+    from ofighters_b200.trainer import TrainerB200
+    w = po.init_weights(9)
+    _, maps, vec = _arena_batch(4, frames=20, seed=31)
+    g = torch.Generator().manual_seed(2)
+    ta, tp = torch.randn((4, 2), generator=g), torch.randn((4, 400, 400), generator=g) * 0.3
+    tr = TrainerB200(weights=w, learning_rate=1e-3, batch_size=4, max_ships=8)
+    img, vec_h = _dense_image(maps), vec.cpu()
+    wo, opt = {k: v.clone() for k, v in w.items()}, pt.KerasAdam(lr=1e-3)
+    losses, olosses = [], []
+    for _ in range(10):
+        losses.append(float(tr.fit(maps, vec, ta.cuda(), tp.cuda(), sync_model=False)[0]))
+        olosses.append(pt.fit(wo, opt, img, vec_h, ta, tp)[0])
+    assert losses[-1] < 0.8 * losses[0] and all(np.isfinite(losses))
+    assert np.allclose(losses, olosses, rtol=2e-2), (losses, olosses)      # two fp32 trajectories of a 10-step descent
