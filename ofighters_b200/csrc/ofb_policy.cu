@@ -117,8 +117,35 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
                 }
         up.add(&d.c1_lut, lut);
     }
+    std::vector<float> bg1(8);                            // pool1 of an empty arena: conv1 of zeros is its bias whatever the padding
+    for (int co = 0; co < 8; co++) bg1[co] = __bfloat162float(__float2bfloat16(std::max(b[co], 0.f)));
+    up.add(&d.sp_bg1, bg1);
     for (int l = 0; l < 3; l++) {
         fold_conv(wh->conv[l + 1], 8, 8, w, b);
+        if (l == 0) {
+            // pool2 of an empty arena per border class: a cell covers conv2 pixels (2Y + i, 2X + j); the taps that fall outside
+            // the 200 x 200 grid read the zero padding.  bf16 weights and activations, fp32 sums, like the kernels.
+            std::vector<__nv_bfloat16> bg2((size_t)9 * 8);
+            for (int cy = 0; cy < 3; cy++)
+                for (int cx = 0; cx < 3; cx++)
+                    for (int co = 0; co < 8; co++) {
+                        float best = 0.f;                      // ReLU
+                        for (int i = 0; i < 2; i++)
+                            for (int j = 0; j < 2; j++) {
+                                const int y = (cy == 0 ? 0 : (cy == 2 ? 198 : 100)) + i, x = (cx == 0 ? 0 : (cx == 2 ? 198 : 100)) + j;
+                                float s = b[co];
+                                for (int dy = 0; dy < 3; dy++)
+                                    for (int dx = 0; dx < 3; dx++) {
+                                        if (y + dy - 1 < 0 || y + dy - 1 > 199 || x + dx - 1 < 0 || x + dx - 1 > 199) continue;
+                                        for (int ci = 0; ci < 8; ci++)
+                                            s += bg1[ci] * __bfloat162float(__float2bfloat16(w[((size_t)(dy * 3 + dx) * 8 + ci) * 8 + co]));
+                                    }
+                                best = std::max(best, s);
+                            }
+                        bg2[(size_t)(cy * 3 + cx) * 8 + co] = __float2bfloat16(best);
+                    }
+            up.add(&d.sp_bg2, bg2);
+        }
         b.resize(16, 0.f);
         up.add(&d.cw[l], pack_taps(w, 8, 8, 16));
         if (l == 0) up.add(&d.c2_tz, pack_toeplitz(w, 8, 8, 8));
@@ -174,6 +201,9 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     p->device = device;
     p->max_ships = max_ships;
     p->engine = OFB_ENGINE_TENSOR;
+    // the sparse CUDA-core trunk12 (ofb_policy_sp.cu) is parity-green but measured slower than the dense tcgen05 one
+    // (5.7 vs 4.6 ms per 16 384 arenas, profiles/r01_step_tuning.md): opt-in
+    { const char *e = getenv("OFB_POLICY_SPARSE_TRUNK"); p->dense_trunk = (e && *e && *e != '0') ? 0 : 1; }
     p->prof = new std::vector<ProfEvent>();
 
     Uploader up;
@@ -715,7 +745,8 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     const bool tc = p->engine == OFB_ENGINE_TENSOR;
     int rc;
     if (tc) {
-        { ProfScope ps(p, L_TRUNK12, st); if ((rc = pol_tz_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc; }
+        { ProfScope ps(p, L_TRUNK12, st);
+          if ((rc = p->dense_trunk ? pol_tz_trunk12(p, maps, ws.pool2, A, st) : pol_sp_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc; }
         { ProfScope ps(p, L_CONV3, st); if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc; }
         { ProfScope ps(p, L_CONV4, st); if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc; }
     } else {

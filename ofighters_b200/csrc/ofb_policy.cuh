@@ -39,6 +39,8 @@ struct PolicyDev {
     float *u4_w, *u4_b;       // [9][8][1], [1]
     __nv_bfloat16 *u4_pw;     // [10][16][8]      (tap, n = phase (4 used), cin)
     float *u4_pb;             // [16]
+    float *sp_bg1;            // [8]     pool1 of an empty arena = bf16(relu(conv1 bias)), as fp32          (sparse trunk)
+    __nv_bfloat16 *sp_bg2;    // [9][8]  pool2 of an empty arena per border class (Y in {0, mid, 99}) x (X in {0, mid, 99})
     __nv_bfloat16 *c2_tz;     // block-Toeplitz B operand of conv2: [3 u][5 k-steps][2 chunks][64 n = xo*8 + cout][8 cin]
     __nv_bfloat16 *u3_tz;     // block-Toeplitz B operand of upconv3: [3 u][3 k-steps][2 chunks][128 n = xo*32 + phase*8 + cout][8 cin]
     __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
@@ -66,6 +68,7 @@ struct ofb_policy {
     float u4_bias;            // upconv4's (single) bias, host copy
     PolicyDev w;
     PolicyWork ws;
+    int dense_trunk;          // 1 = always the dense tcgen05 trunk12 (k_tz_trunk12); 0 = the sparse one (k_sp_trunk12)
     int profiling;            // when set, forward brackets every kernel with CUDA events
     void *prof;               // std::vector<ProfEvent>*
     void *arena_blob;         // single allocation holding all weights
@@ -84,6 +87,8 @@ int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, flo
 int pol_tz_up4_parts();
 int pol_tc_dense1(const ofb_policy *p, const __nv_bfloat16 *flat, float *hflat, int n_items, cudaStream_t st);
 int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
+// sparse trunk12 on CUDA cores, ofb_policy_sp.cu
+int pol_sp_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 // element offset of pixel (y, x) of a 100 x 100 x 8 image in plane layout (4 planes of x mod 4)
 __host__ __device__ __forceinline__ int pol_plane100_off(int y, int x) { return (((x & 3) * 100 + y) * 26 + (x >> 2) + 1) * 8; }

@@ -1,0 +1,179 @@
+// Sparse trunk12 (sm_100a, CUDA cores): conv1 + BN + ReLU + pool -> conv2 + BN + ReLU + pool (agents/qlearnIA_V2.py:129-139),
+// 400 x 400 x 2 bits -> 100 x 100 x 8 bf16, evaluated only where it can differ from the empty-arena answer.
+//
+// The maps are >96 % zeros (7 radius-8 disks and a few dozen radius-2 disks), conv1 of a zero input is its bias whatever the
+// padding, so pool1 equals one constant vector bg1 everywhere except under the entities, and a pooled conv2 output (one
+// "cell" of the 100 x 100 grid) can only differ from the precomputed empty-arena value bg2[class] -- 9 classes: interior and
+// the 8 border positions, where zero padding removes taps -- if its 10 x 10-pixel receptive field holds a set bit.  Per
+// arena about 600 of the 10 000 cells are such "dirty" cells; the dense tcgen05 kernel (k_tz_trunk12) spends 46 MFLOP per
+// arena on all of them, this one 2.8 MFLOP:
+//   1. both bit maps -> shared memory; for every cell row Y the OR of the 10 map rows 4Y-3 .. 4Y+6 ("rowor", 13 words);
+//   2. per cell: 10 bits of rowor[Y] decide clean / dirty; a clean cell stores bg2[class], a dirty one joins a list;
+//   3. dirty cells in batches of 64: (A) the 4 x 4 pool1 vectors a cell reads are evaluated from the bits exactly like the
+//      dense engines do (9-bit stencil LUT, rounded to bf16; zeros outside the map = the convolution's padding) into a
+//      shared-memory cache, 4 evaluations per thread; (B) 8 threads per cell, one output channel each with its 72 conv2
+//      weights in registers, accumulate the 4 conv2 pixels in fp32, ReLU, max, bf16.
+// Arithmetic is that of the CUDA-core twin (k_trunk1_cc + k_conv_pool_cc): bf16 weights and activations, fp32 sums.
+//
+// STATUS (round 1): parity-green against the dense trunk on four scenes (tests/test_gpu_policy.py) but SLOWER on the bench
+// scenes -- 5.7 ms vs 4.6 ms per 16 384 arenas: with ~45 live lasers an arena has ~1 000 dirty cells, step (A) re-evaluates
+// every pool1 vector for each of the 4 cells that read it (~100 instructions per evaluation), and step (B)'s 288 FMAs per
+// thread carry 16 shared-memory loads + 64 bf16 unpacks.  Opt-in (OFB_POLICY_SPARSE_TRUNK=1) until a banded pool1 buffer
+// removes the redundancy; the FMA floor of step (B) alone is ~1.0 ms.
+#include "ofb_policy.cuh"
+#include "ofb_policy_dev.cuh"
+
+#define SP_NT 256
+#define SP_BATCH 64                       // dirty cells per batch: cache = 64 x 16 pool1 vectors x 16 B = 16 KB
+#define SP_BAND 25                        // cell rows per detection pass (2 500 cells -> list of at most 2 500 entries)
+#define SP_RW 13                          // words of one 400-bit row
+
+struct SpSmem {
+    static constexpr int off_bs = 0;                                  // ship map   5000 words
+    static constexpr int off_bl = off_bs + POL_WORDS * 4;             // laser map  5000 words
+    static constexpr int off_ro = off_bl + POL_WORDS * 4;             // rowor [100][13]
+    static constexpr int off_list = off_ro + 100 * SP_RW * 4;         // u16 [2500]
+    static constexpr int off_cache = (off_list + SP_BAND * 100 * 2 + 15) & ~15;      // uint4 [SP_BATCH][16]
+    static constexpr int off_misc = off_cache + SP_BATCH * 16 * 16;   // c1 bias [8] f32, bg1 [8] f32, counter
+    static constexpr int bytes = off_misc + 8 * 4 + 8 * 4 + 16;
+};
+
+// 32 bits of map row r starting at column 32 c (rows are 400 bits = 12.5 words: odd rows start mid-word)
+__device__ __forceinline__ uint32_t sp_row_chunk(const uint32_t *__restrict__ m, int r, int c) {
+    const int b = r * POL_W + 32 * c, w = b >> 5;
+    const uint32_t v = __funnelshift_r(m[w], m[min(w + 1, POL_WORDS - 1)], b & 31);
+    return c == SP_RW - 1 ? (v & 0xFFFFu) : v;                        // the 13th chunk holds the row's last 16 columns
+}
+
+__global__ void __launch_bounds__(SP_NT, 2)
+k_sp_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16 *__restrict__ out, const int n_items) {
+    extern __shared__ __align__(16) uint8_t sp_smem[];
+    uint32_t *bs = reinterpret_cast<uint32_t *>(sp_smem + SpSmem::off_bs), *bl = reinterpret_cast<uint32_t *>(sp_smem + SpSmem::off_bl);
+    uint32_t *rowor = reinterpret_cast<uint32_t *>(sp_smem + SpSmem::off_ro);
+    uint16_t *list = reinterpret_cast<uint16_t *>(sp_smem + SpSmem::off_list);
+    uint4 *cache = reinterpret_cast<uint4 *>(sp_smem + SpSmem::off_cache);
+    float *c1b = reinterpret_cast<float *>(sp_smem + SpSmem::off_misc), *bg1 = c1b + 8;
+    int *counter = reinterpret_cast<int *>(bg1 + 8);
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    // this thread's output channel and its conv2 weights [tap][cin] (bf16 in HBM, fp32 in registers), bias
+    const int co = tid & 7;
+    float wreg[72];
+#pragma unroll
+    for (int t = 0; t < 9; t++) {
+        float v[8];
+        unpack_bf8(*reinterpret_cast<const uint4 *>(w.cw[0] + ((size_t)t * 16 + co) * 8), v);
+#pragma unroll
+        for (int ci = 0; ci < 8; ci++) wreg[t * 8 + ci] = v[ci];
+    }
+    const float bias2 = w.cb[0][co];
+    if (tid < 8) { c1b[tid] = w.c1_b[tid]; bg1[tid] = w.sp_bg1[tid]; }
+    const uint4 *bg2 = reinterpret_cast<const uint4 *>(w.sp_bg2);    // [9 classes] bf16 x 8
+
+    for (int a = blockIdx.x; a < n_items; a += gridDim.x) {
+        __syncthreads();                                               // the previous arena's reads of the maps are over
+        {   // ---- 1a. maps -> shared memory
+            const uint4 *src = reinterpret_cast<const uint4 *>(maps + (size_t)a * 2 * POL_WORDS);
+            uint4 *dst = reinterpret_cast<uint4 *>(bs);                // bs and bl are contiguous
+#pragma unroll 4
+            for (int i = tid; i < 2 * POL_WORDS / 4; i += SP_NT) dst[i] = src[i];
+        }
+        __syncthreads();
+        // ---- 1b. rowor[Y][c] = OR over map rows 4Y-3 .. 4Y+6 (both maps) of the row's 32-bit chunk c
+        for (int i = tid; i < 100 * SP_RW; i += SP_NT) {
+            const int Y = i / SP_RW, c = i % SP_RW;
+            const int r0 = max(4 * Y - 3, 0), r1 = min(4 * Y + 6, POL_W - 1);
+            uint32_t v = 0;
+            for (int r = r0; r <= r1; r++) v |= sp_row_chunk(bs, r, c) | sp_row_chunk(bl, r, c);
+            rowor[i] = v;
+        }
+        __nv_bfloat16 *dsta = out + (size_t)a * 100 * 100 * 8;
+        for (int band = 0; band < 100 / SP_BAND; band++) {
+            if (tid == 0) *counter = 0;
+            __syncthreads();
+            // ---- 2. clean cells get the empty-arena value of their border class, dirty ones are listed
+            for (int i = tid; i < SP_BAND * 100; i += SP_NT) {
+                const int Y = band * SP_BAND + i / 100, X = i % 100;
+                const int lo = max(4 * X - 3, 0), hi = min(4 * X + 6, POL_W - 1);
+                const uint32_t *ro = rowor + Y * SP_RW;
+                const uint32_t v = __funnelshift_r(ro[lo >> 5], ro[min((lo >> 5) + 1, SP_RW - 1)], lo & 31) & ((1u << (hi - lo + 1)) - 1u);
+                const bool dirty = v != 0u;
+                const unsigned bal = __ballot_sync(__activemask(), dirty);
+                if (dirty) {
+                    int base = 0;
+                    const int leader = __ffs(bal) - 1;
+                    if (lane == leader) base = atomicAdd(counter, __popc(bal));
+                    base = __shfl_sync(bal, base, leader);
+                    list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(Y * 100 + X);
+                } else {
+                    const int cls = (Y == 0 ? 0 : (Y == 99 ? 2 : 1)) * 3 + (X == 0 ? 0 : (X == 99 ? 2 : 1));
+                    *reinterpret_cast<uint4 *>(dsta + (size_t)(Y * 100 + X) * 8) = __ldg(bg2 + cls);
+                }
+            }
+            __syncthreads();
+            const int n_dirty = *counter;
+            __syncthreads();                                           // everyone has read the count before it is reset
+            // ---- 3. dirty cells, SP_BATCH at a time
+            for (int base = 0; base < n_dirty; base += SP_BATCH) {
+                const int nb = min(SP_BATCH, n_dirty - base);
+                // (A) the 4 x 4 pool1 vectors of every cell of the batch
+                for (int e = tid; e < nb * 16; e += SP_NT) {
+                    const int cell = list[base + (e >> 4)], pos = e & 15;
+                    const int py = 2 * (cell / 100) - 1 + (pos >> 2), px = 2 * (cell % 100) - 1 + (pos & 3);
+                    uint4 q = make_uint4(0u, 0u, 0u, 0u);             // outside the 200 x 200 grid: conv2's zero padding
+                    if (py >= 0 && py < 200 && px >= 0 && px < 200) {
+                        const uint32_t ps = conv1_patch(bs, py, px), pl = conv1_patch(bl, py, px);
+                        float v[8];
+                        if ((ps | pl) == 0u) {
+#pragma unroll
+                            for (int k = 0; k < 8; k++) v[k] = bg1[k];
+                        } else conv1_pool_pixel(ps, pl, w.c1_lut, c1b, v);
+                        q = pack_bf8(v);
+                    }
+                    cache[e] = q;
+                }
+                __syncthreads();
+                // (B) 8 threads per cell (one output channel each), 32 cells per round
+                for (int b = tid >> 3; b < nb; b += SP_NT / 8) {
+                    float acc[4] = {bias2, bias2, bias2, bias2};
+#pragma unroll
+                    for (int pos = 0; pos < 16; pos++) {
+                        float v[8];
+                        unpack_bf8(cache[b * 16 + pos], v);
+                        const int r = pos >> 2, c = pos & 3;
+#pragma unroll
+                        for (int i = 0; i < 2; i++)
+#pragma unroll
+                            for (int j = 0; j < 2; j++) {
+                                const int dy = r - i, dx = c - j;
+                                if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
+#pragma unroll
+                                for (int ci = 0; ci < 8; ci++) acc[i * 2 + j] = fmaf(v[ci], wreg[(dy * 3 + dx) * 8 + ci], acc[i * 2 + j]);
+                            }
+                    }
+                    const float m = fmaxf(fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3])), 0.0f);       // ReLU, then the 2 x 2 max
+                    const __nv_bfloat16 hb = __float2bfloat16(m);
+                    dsta[(size_t)list[base + b] * 8 + co] = hb;       // the cell's 8 lanes write 16 contiguous bytes
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+int pol_sp_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
+    if (n_items <= 0) return OFB_OK;
+    static thread_local bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_sp_trunk12, cudaFuncAttributeMaxDynamicSharedMemorySize, SpSmem::bytes);
+        if (e != cudaSuccess) { ofb_set_error("pol_sp_trunk12: %s", cudaGetErrorString(e)); return OFB_E_CUDA; }
+        configured = true;
+    }
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);
+    const int grid = n_items < 3 * n_sm ? n_items : 3 * n_sm;
+    k_sp_trunk12<<<grid, SP_NT, SpSmem::bytes, st>>>(maps, p->w, out, n_items);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { ofb_set_error("k_sp_trunk12 launch: %s", cudaGetErrorString(e)); return OFB_E_CUDA; }
+    return OFB_OK;
+}

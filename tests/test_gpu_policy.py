@@ -111,6 +111,49 @@ def test_engines_agree_tightly(setup):
     assert errs["act"] <= TOL_ENGINES and errs["ptr"] <= 5e-3, errs
 
 
+@pytest.mark.parametrize("scene", ["default", "stress32", "empty", "borders"])
+def test_sparse_trunk_equals_dense_trunk(setup, scene, monkeypatch):
+    """The opt-in sparse trunk12 (k_sp_trunk12: only the cells whose receptive field holds a set bit are evaluated, the rest
+    take the precomputed empty-arena value) against the dense tcgen05 trunk12 on the same weights: pool2 and everything
+    downstream.  Scenes: a running default arena, 32 ships at maximum fire rate (most cells dirty), empty maps (every cell
+    takes the background of its border class) and entities pushed against all four walls."""
+    from ofighters_b200 import ArenaConfig, BatchedBattleground
+    from ofighters_b200.policy import PolicyB200
+    s = setup
+    if scene == "default":
+        maps, vec = s["maps"], s["vec"]
+    elif scene == "stress32":
+        bg = BatchedBattleground(5, ships={"stress": 32}, config=ArenaConfig(laser_cap=2048), seed=3)
+        for _ in range(12):
+            bg.frame()
+        maps, vec = bg.raster("bits"), bg.obs_vec[:, 0, :].contiguous()
+    elif scene == "empty":
+        maps, vec = torch.zeros((3, 2, 5000), dtype=torch.int32, device="cuda"), s["vec"][:3].contiguous()
+    else:
+        spawn = torch.tensor([[[0, 0], [399, 0], [0, 399], [399, 399], [200, 0], [0, 200], [399, 200]]] * 4, dtype=torch.int32)
+        bg = BatchedBattleground(4, ships={"shoot": 7}, spawn_xy=spawn, seed=1)
+        for _ in range(3):
+            bg.frame()
+        maps, vec = bg.raster("bits"), bg.obs_vec[:, 0, :].contiguous()
+    n = maps.shape[0]
+    out = {}
+    for kind in ("dense", "sparse"):
+        if kind == "sparse":                             # read when the handle is created
+            monkeypatch.setenv("OFB_POLICY_SPARSE_TRUNK", "1")
+        else:
+            monkeypatch.delenv("OFB_POLICY_SPARSE_TRUNK", raising=False)
+        pol = PolicyB200(s["w"], max_ships=16)
+        r = pol.forward(maps, vec, 1, want_ptr=True)
+        out[kind] = dict(pool2=pol.debug_tap(1, n, (100, 100, 8)).clone(), act=r["act"].clone(), ptr=r["ptr"].clone(),
+                         xy=r["xy"].clone())
+    p_d, p_s = out["dense"]["pool2"].float(), out["sparse"]["pool2"].float()
+    # same bf16 operands, fp32 sums in another order: a value may land on the neighbouring bf16 (2^-8 relative) at most
+    assert float(((p_d - p_s).abs() / p_d.abs().clamp_min(1e-3)).max()) <= 2 ** -7, float((p_d - p_s).abs().max())
+    assert float((p_d != p_s).float().mean()) <= 2e-2
+    assert _relerr(out["sparse"]["act"], out["dense"]["act"]) <= TOL_ENGINES
+    assert _relerr(out["sparse"]["ptr"], out["dense"]["ptr"]) <= 5e-3
+
+
 def test_multi_ship_and_chunking(setup):
     """P policy ships per arena share the trunk; chunked calls equal one-shot calls."""
     from ofighters_b200.policy import PolicyB200
