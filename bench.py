@@ -425,7 +425,8 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
         dom = max(prof, key=prof.get)
         total = sum(prof.values())
         per_item = _ncu_traffic().get("policy_per_item", {})
-        kname = {"trunk12": "k_tz_trunk12 (conv1 from bits + block-Toeplitz conv2 + pools)", "conv3": "k_tc_conv_pool", "conv4": "k_tc_conv_pool",
+        kname = {"trunk12": ("k_tz_trunk12 (conv1 from bits + block-Toeplitz conv2 + pools)" if os.environ.get("OFB_POLICY_DENSE_TRUNK")
+                             else "k_sp_trunk12 (sparse conv1 + conv2 + pools on CUDA cores)"), "conv3": "k_tc_conv_pool", "conv4": "k_tc_conv_pool",
                  "dense1": "k_tc_dense1", "heads": "k_heads", "up3": "k_tz_up3", "up4": "k_tz_up4", "argmax": "k_argmax_final"}
         return {"bound": "tensor", "kernel": kname.get(dom, dom), "achieved": layers[dom]["alg_tflops"], "peak": tpeak,
                 "unit": "TFLOP/s", "frac": layers[dom]["alg_tflops"] / tpeak,

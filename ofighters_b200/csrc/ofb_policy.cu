@@ -201,9 +201,10 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     p->device = device;
     p->max_ships = max_ships;
     p->engine = OFB_ENGINE_TENSOR;
-    // the sparse CUDA-core trunk12 (ofb_policy_sp.cu) is parity-green but measured slower than the dense tcgen05 one
-    // (5.7 vs 4.6 ms per 16 384 arenas, profiles/r01_step_tuning.md): opt-in
-    { const char *e = getenv("OFB_POLICY_SPARSE_TRUNK"); p->dense_trunk = (e && *e && *e != '0') ? 0 : 1; }
+    // trunk12: the sparse CUDA-core kernel (ofb_policy_sp.cu) is the default -- 26 % faster than the dense tcgen05 one over a
+    // 200-frame episode of the default arena, 12 % slower at the laser peak around frame 30 (profiles/r01_step_tuning.md);
+    // OFB_POLICY_DENSE_TRUNK=1 selects the dense kernel when the handle is created
+    { const char *e = getenv("OFB_POLICY_DENSE_TRUNK"); p->dense_trunk = (e && *e && *e != '0') ? 1 : 0; }
     p->prof = new std::vector<ProfEvent>();
 
     Uploader up;

@@ -15,11 +15,10 @@
 //      weights in registers, accumulate the 4 conv2 pixels in fp32, ReLU, max, bf16.
 // Arithmetic is that of the CUDA-core twin (k_trunk1_cc + k_conv_pool_cc): bf16 weights and activations, fp32 sums.
 //
-// STATUS (round 1): parity-green against the dense trunk on four scenes (tests/test_gpu_policy.py) but SLOWER on the bench
-// scenes -- 5.7 ms vs 4.6 ms per 16 384 arenas: with ~45 live lasers an arena has ~1 000 dirty cells, step (A) re-evaluates
-// every pool1 vector for each of the 4 cells that read it (~100 instructions per evaluation), and step (B)'s 288 FMAs per
-// thread carry 16 shared-memory loads + 64 bf16 unpacks.  Opt-in (OFB_POLICY_SPARSE_TRUNK=1) until a banded pool1 buffer
-// removes the redundancy; the FMA floor of step (B) alone is ~1.0 ms.
+// STATUS (round 1): parity-green against the dense trunk on four scenes (tests/test_gpu_policy.py).  Per 8 192 default arenas
+// (scripts/trunk_episode.py): 0.96 ms late in an episode (8 lasers, 1 ship alive) to 2.6 ms at the laser peak (45 lasers),
+// episode mean 1.48 ms against 1.99 ms for the dense kernel (1.8 - 2.3 ms).  The floor is instruction count, not bytes: the
+// 40 KB map load, the 1 300 row-OR chunks, the 10 000 background stores and ~330 instructions per (dirty cell, channel).
 #include "ofb_policy.cuh"
 #include "ofb_policy_dev.cuh"
 
@@ -88,26 +87,25 @@ k_sp_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             rowor[i] = v;
         }
         __nv_bfloat16 *dsta = out + (size_t)a * 100 * 100 * 8;
+        // ---- 2a. every cell gets the empty-arena value of its border class; the dirty ones are overwritten in step 3
+        for (int i = tid; i < 100 * 100; i += SP_NT) {
+            const int Y = i / 100, X = i - Y * 100;
+            const int cls = (Y == 0 ? 0 : (Y == 99 ? 2 : 1)) * 3 + (X == 0 ? 0 : (X == 99 ? 2 : 1));
+            *reinterpret_cast<uint4 *>(dsta + (size_t)i * 8) = __ldg(bg2 + cls);
+        }
         for (int band = 0; band < 100 / SP_BAND; band++) {
             if (tid == 0) *counter = 0;
-            __syncthreads();
-            // ---- 2. clean cells get the empty-arena value of their border class, dirty ones are listed
-            for (int i = tid; i < SP_BAND * 100; i += SP_NT) {
-                const int Y = band * SP_BAND + i / 100, X = i % 100;
-                const int lo = max(4 * X - 3, 0), hi = min(4 * X + 6, POL_W - 1);
+            __syncthreads();                               // (also orders the background stores before the dirty cells' stores)
+            // ---- 2b. dirty cells of the band: a cell belongs to the 32-bit chunk of rowor[Y] its 10-bit window starts in
+            //          (cells 8c+1 .. 8c+8, and cell 0 with chunk 0); chunks that are zero -- most -- skip their cells at once
+            for (int i = tid; i < SP_BAND * SP_RW; i += SP_NT) {
+                const int Y = band * SP_BAND + i / SP_RW, c = i % SP_RW;
                 const uint32_t *ro = rowor + Y * SP_RW;
-                const uint32_t v = __funnelshift_r(ro[lo >> 5], ro[min((lo >> 5) + 1, SP_RW - 1)], lo & 31) & ((1u << (hi - lo + 1)) - 1u);
-                const bool dirty = v != 0u;
-                const unsigned bal = __ballot_sync(__activemask(), dirty);
-                if (dirty) {
-                    int base = 0;
-                    const int leader = __ffs(bal) - 1;
-                    if (lane == leader) base = atomicAdd(counter, __popc(bal));
-                    base = __shfl_sync(bal, base, leader);
-                    list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)(Y * 100 + X);
-                } else {
-                    const int cls = (Y == 0 ? 0 : (Y == 99 ? 2 : 1)) * 3 + (X == 0 ? 0 : (X == 99 ? 2 : 1));
-                    *reinterpret_cast<uint4 *>(dsta + (size_t)(Y * 100 + X) * 8) = __ldg(bg2 + cls);
+                const uint32_t w0 = ro[c], w1 = c + 1 < SP_RW ? ro[c + 1] : 0u;
+                if ((w0 | w1) == 0u) continue;
+                for (int X = (c == 0 ? 0 : 8 * c + 1); X <= min(8 * c + 8, 99); X++) {
+                    const int lo = max(4 * X - 3, 0), hi = min(4 * X + 6, POL_W - 1);
+                    if (__funnelshift_r(w0, w1, lo & 31) & ((1u << (hi - lo + 1)) - 1u)) list[atomicAdd(counter, 1)] = (uint16_t)(Y * 100 + X);
                 }
             }
             __syncthreads();

@@ -113,7 +113,7 @@ def test_engines_agree_tightly(setup):
 
 @pytest.mark.parametrize("scene", ["default", "stress32", "empty", "borders"])
 def test_sparse_trunk_equals_dense_trunk(setup, scene, monkeypatch):
-    """The opt-in sparse trunk12 (k_sp_trunk12: only the cells whose receptive field holds a set bit are evaluated, the rest
+    """The sparse trunk12 (the default; k_sp_trunk12: only the cells whose receptive field holds a set bit are evaluated, the rest
     take the precomputed empty-arena value) against the dense tcgen05 trunk12 on the same weights: pool2 and everything
     downstream.  Scenes: a running default arena, 32 ships at maximum fire rate (most cells dirty), empty maps (every cell
     takes the background of its border class) and entities pushed against all four walls."""
@@ -138,10 +138,10 @@ def test_sparse_trunk_equals_dense_trunk(setup, scene, monkeypatch):
     n = maps.shape[0]
     out = {}
     for kind in ("dense", "sparse"):
-        if kind == "sparse":                             # read when the handle is created
-            monkeypatch.setenv("OFB_POLICY_SPARSE_TRUNK", "1")
+        if kind == "dense":                              # read when the handle is created
+            monkeypatch.setenv("OFB_POLICY_DENSE_TRUNK", "1")
         else:
-            monkeypatch.delenv("OFB_POLICY_SPARSE_TRUNK", raising=False)
+            monkeypatch.delenv("OFB_POLICY_DENSE_TRUNK", raising=False)
         pol = PolicyB200(s["w"], max_ships=16)
         r = pol.forward(maps, vec, 1, want_ptr=True)
         out[kind] = dict(pool2=pol.debug_tap(1, n, (100, 100, 8)).clone(), act=r["act"].clone(), ptr=r["ptr"].clone(),
