@@ -88,10 +88,11 @@ k_sp_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
         }
         __nv_bfloat16 *dsta = out + (size_t)a * 100 * 100 * 8;
         // ---- 2a. every cell gets the empty-arena value of its border class; the dirty ones are overwritten in step 3
-        for (int i = tid; i < 100 * 100; i += SP_NT) {
-            const int Y = i / 100, X = i - Y * 100;
-            const int cls = (Y == 0 ? 0 : (Y == 99 ? 2 : 1)) * 3 + (X == 0 ? 0 : (X == 99 ? 2 : 1));
-            *reinterpret_cast<uint4 *>(dsta + (size_t)i * 8) = __ldg(bg2 + cls);
+        if ((tid & 127) < 100) {                           // a thread keeps its column and walks every other row
+            const int X = tid & 127, cx = X == 0 ? 0 : (X == 99 ? 2 : 1);
+            const uint4 top = __ldg(bg2 + cx), mid = __ldg(bg2 + 3 + cx), bot = __ldg(bg2 + 6 + cx);
+            uint4 *col = reinterpret_cast<uint4 *>(dsta) + X;
+            for (int Y = tid >> 7; Y < 100; Y += SP_NT / 128) col[Y * 100] = Y == 0 ? top : (Y == 99 ? bot : mid);
         }
         for (int band = 0; band < 100 / SP_BAND; band++) {
             if (tid == 0) *counter = 0;
