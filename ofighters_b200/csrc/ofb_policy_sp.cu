@@ -7,7 +7,7 @@
 // the 8 border positions, where zero padding removes taps -- if its 10 x 10-pixel receptive field holds a set bit.  Per
 // arena about 600 of the 10 000 cells are such "dirty" cells; the dense tcgen05 kernel (k_tz_trunk12) spends 46 MFLOP per
 // arena on all of them, this one 2.8 MFLOP:
-//   1. both bit maps -> shared memory; for every cell row Y the OR of the 10 map rows 4Y-3 .. 4Y+6 ("rowor", 13 words);
+//   1. both bit maps -> shared memory (bulk async copy, double-buffered: the next arena's maps arrive meanwhile); for every cell row Y the OR of the 10 map rows 4Y-3 .. 4Y+6 ("rowor", 13 words);
 //   2. per cell: 10 bits of rowor[Y] decide clean / dirty; a clean cell stores bg2[class], a dirty one joins a list;
 //   3. dirty cells in batches of 64: (A) the 4 x 4 pool1 vectors a cell reads are evaluated from the bits exactly like the
 //      dense engines do (9-bit stencil LUT, rounded to bf16; zeros outside the map = the convolution's padding) into a
@@ -16,11 +16,12 @@
 // Arithmetic is that of the CUDA-core twin (k_trunk1_cc + k_conv_pool_cc): bf16 weights and activations, fp32 sums.
 //
 // STATUS (round 1): parity-green against the dense trunk on four scenes (tests/test_gpu_policy.py).  Per 8 192 default arenas
-// (scripts/trunk_episode.py): 0.96 ms late in an episode (8 lasers, 1 ship alive) to 2.6 ms at the laser peak (45 lasers),
-// episode mean 1.48 ms against 1.99 ms for the dense kernel (1.8 - 2.3 ms).  The floor is instruction count, not bytes: the
+// (scripts/trunk_episode.py): 0.88 ms late in an episode (8 lasers, 1 ship alive) to 2.5 ms at the laser peak (45 lasers),
+// episode mean 1.43 ms against 1.99 ms for the dense kernel (1.8 - 2.3 ms).  The floor is instruction count, not bytes: the
 // 40 KB map load, the 1 300 row-OR chunks, the 10 000 background stores and ~330 instructions per (dirty cell, channel).
 #include "ofb_policy.cuh"
 #include "ofb_policy_dev.cuh"
+#include "ofb_tc_ptx.cuh"
 
 #define SP_NT 256
 #define SP_BATCH 64                       // dirty cells per batch: cache = 64 x 16 pool1 vectors x 16 B = 16 KB
@@ -28,13 +29,13 @@
 #define SP_RW 13                          // words of one 400-bit row
 
 struct SpSmem {
-    static constexpr int off_bs = 0;                                  // ship map   5000 words
-    static constexpr int off_bl = off_bs + POL_WORDS * 4;             // laser map  5000 words
-    static constexpr int off_ro = off_bl + POL_WORDS * 4;             // rowor [100][13]
+    static constexpr int off_bs = 0;                                  // [2 buffers][ship map 5000 words | laser map 5000 words]:
+    static constexpr int map_bytes = 2 * POL_WORDS * 4;               // the next arena's maps arrive (bulk async copy) while
+    static constexpr int off_ro = off_bs + 2 * map_bytes;             // this one is evaluated;  rowor [100][13]
     static constexpr int off_list = off_ro + 100 * SP_RW * 4;         // u16 [2500]
     static constexpr int off_cache = (off_list + SP_BAND * 100 * 2 + 15) & ~15;      // uint4 [SP_BATCH][16]
-    static constexpr int off_misc = off_cache + SP_BATCH * 16 * 16;   // c1 bias [8] f32, bg1 [8] f32, counter
-    static constexpr int bytes = off_misc + 8 * 4 + 8 * 4 + 16;
+    static constexpr int off_misc = off_cache + SP_BATCH * 16 * 16;   // c1 bias [8] f32, bg1 [8] f32, counter, 2 mbarriers
+    static constexpr int bytes = off_misc + 8 * 4 + 8 * 4 + 16 + 16;
 };
 
 // 32 bits of map row r starting at column 32 c (rows are 400 bits = 12.5 words: odd rows start mid-word)
@@ -47,12 +48,12 @@ __device__ __forceinline__ uint32_t sp_row_chunk(const uint32_t *__restrict__ m,
 __global__ void __launch_bounds__(SP_NT, 2)
 k_sp_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16 *__restrict__ out, const int n_items) {
     extern __shared__ __align__(16) uint8_t sp_smem[];
-    uint32_t *bs = reinterpret_cast<uint32_t *>(sp_smem + SpSmem::off_bs), *bl = reinterpret_cast<uint32_t *>(sp_smem + SpSmem::off_bl);
     uint32_t *rowor = reinterpret_cast<uint32_t *>(sp_smem + SpSmem::off_ro);
     uint16_t *list = reinterpret_cast<uint16_t *>(sp_smem + SpSmem::off_list);
     uint4 *cache = reinterpret_cast<uint4 *>(sp_smem + SpSmem::off_cache);
     float *c1b = reinterpret_cast<float *>(sp_smem + SpSmem::off_misc), *bg1 = c1b + 8;
     int *counter = reinterpret_cast<int *>(bg1 + 8);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(sp_smem + SpSmem::off_misc + 8 * 4 + 8 * 4 + 16);
     const int tid = threadIdx.x, lane = tid & 31;
 
     // this thread's output channel and its conv2 weights [tap][cin] (bf16 in HBM, fp32 in registers), bias
@@ -69,15 +70,28 @@ k_sp_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     if (tid < 8) { c1b[tid] = w.c1_b[tid]; bg1[tid] = w.sp_bg1[tid]; }
     const uint4 *bg2 = reinterpret_cast<const uint4 *>(w.sp_bg2);    // [9 classes] bf16 x 8
 
-    for (int a = blockIdx.x; a < n_items; a += gridDim.x) {
-        __syncthreads();                                               // the previous arena's reads of the maps are over
-        {   // ---- 1a. maps -> shared memory
-            const uint4 *src = reinterpret_cast<const uint4 *>(maps + (size_t)a * 2 * POL_WORDS);
-            uint4 *dst = reinterpret_cast<uint4 *>(bs);                // bs and bl are contiguous
-#pragma unroll 4
-            for (int i = tid; i < 2 * POL_WORDS / 4; i += SP_NT) dst[i] = src[i];
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < n_items) {                               // first arena of this CTA -> buffer 0
+            mbar_expect_tx(&mbar[0], SpSmem::map_bytes);
+            bulk_g2s(sp_smem + SpSmem::off_bs, maps + (size_t)blockIdx.x * 2 * POL_WORDS, SpSmem::map_bytes, &mbar[0]);
         }
-        __syncthreads();
+    }
+    __syncthreads();
+    int it = 0;
+    for (int a = blockIdx.x; a < n_items; a += gridDim.x, it++) {
+        const int buf = it & 1;
+        const uint32_t *bs = reinterpret_cast<const uint32_t *>(sp_smem + SpSmem::off_bs + buf * SpSmem::map_bytes), *bl = bs + POL_WORDS;
+        __syncthreads();                                               // the arena before last has left the other buffer
+        if (tid == 0 && a + (int)gridDim.x < n_items) {                // ---- 1a. the next arena's maps -> the other buffer
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&mbar[buf ^ 1], SpSmem::map_bytes);
+            bulk_g2s(sp_smem + SpSmem::off_bs + (buf ^ 1) * SpSmem::map_bytes, maps + (size_t)(a + gridDim.x) * 2 * POL_WORDS,
+                     SpSmem::map_bytes, &mbar[buf ^ 1]);
+        }
+        mbar_wait(&mbar[buf], (uint32_t)((it >> 1) & 1));              // this arena's maps have landed
         // ---- 1b. rowor[Y][c] = OR over map rows 4Y-3 .. 4Y+6 (both maps) of the row's 32-bit chunk c
         for (int i = tid; i < 100 * SP_RW; i += SP_NT) {
             const int Y = i / SP_RW, c = i % SP_RW;
