@@ -519,6 +519,12 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
 
     def host_step(k):
         t = k % T
+        decided = None
+        if policy is not None:
+            if bg.time >= 200:
+                bg.restart()
+                bg.raster("bits", out=maps)
+            decided = policy.decide(bg, maps)               # the forward is queued first: the host bot below overlaps it
         if wl["bot"] == "stress":
             act_np[..., 0] = 1
             act_np[..., 1] = kind[t] & 1
@@ -528,19 +534,17 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
             act_np[..., 1] = kind[t] == 1
             rep = (kind[t] == 2)[..., None]
             act_np[..., 2:] = np.where(rep, newp[t], obs_np[..., 2:4].astype(np.int16))
-        if bg.time >= 200:
-            bg.restart()
-            if policy is not None:
-                bg.raster("bits", out=maps)
         if policy is None:
+            if bg.time >= 200:
+                bg.restart()
             bg.step_host(act_host, obs_host)                # H2D actions, K1, D2H obs heads (synchronises)
+            bg.raster("bits", out=maps)
         else:
-            bg.actions.copy_(act_host, non_blocking=True)   # host bots' rows
-            policy.act(bg, maps)                            # policy ship's row from the forward
-            bg.generate_frame()
+            bg.actions.copy_(act_host, non_blocking=True)   # host bots' rows (stream-ordered behind the forward)
+            policy.write(bg, *decided)                      # policy ship's row from the forward
+            bg.generate_frame(maps=maps)                    # fused step + maps
             obs_host.copy_(bg.obs_vec, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
-        bg.raster("bits", out=maps)
 
     cl_steps = min(steps, 100 if policy is None else 20)
     for k in range(3):
@@ -554,7 +558,8 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
     closed = {"value": N * world * cl_steps / dt, "steps": cl_steps,
               "what": "host numpy bot reads frame k's obs heads before sending frame k+1: pinned actions -> H2D -> "
                       "step -> D2H obs heads -> sync -> raster (maps stay in HBM)%s; bot CPU time inside the timed "
-                      "region; wall clock" % (" -> policy forward" if policy is not None else "")}
+                      "region; wall clock" % (" [policy workloads: the forward of the policy ship is queued first and the host "
+                                              "bot's numpy runs while it executes; step + raster fused]" if policy is not None else "")}
     if policy is not None or make_bg is None:
         out.update(value=closed["value"], steps=cl_steps, what=closed["what"])
         return out

@@ -196,6 +196,13 @@ class PolicyB200:
         """Drive the "QlearnIA"/"external" ships of ``bg`` for the coming frame: forward on the
         current maps + observation heads, then QlearnIA.play's action vector (:447-456) straight into
         ``bg.actions``.  ``epsilon`` > 0 enables the eps-greedy random branch (:199-204)."""
+        iact, xy = self.decide(bg, maps_bits)
+        self.write(bg, iact, xy, epsilon)
+        return iact, xy
+
+    def decide(self, bg, maps_bits):
+        """First half of ``act``: queue the forward (asynchronous) -> (iaction [A*P], xy [A*P,2]) on the device.  A host-side
+        bot can compute the other ships' rows while it runs."""
         idx = getattr(bg, "_policy_ship_idx", None)
         if idx is None:
             ids = [i for i, b in enumerate(bg.behaviors) if b in ("QlearnIA", "external")]
@@ -205,12 +212,15 @@ class PolicyB200:
             bg._policy_ship_idx_long = idx.long()
         P = idx.numel()
         vec = bg.obs_vec.index_select(1, bg._policy_ship_idx_long).reshape(-1, 8)
-        iact, xy = self.forward_argmax(maps_bits, vec, P)
-        _lib.check(self._lib.ofb_policy_write_actions(_ptr(iact), _ptr(xy), bg.n_arenas, P, _ptr(idx), bg.ships_number,
+        return self.forward_argmax(maps_bits, vec, P)
+
+    def write(self, bg, iact, xy, epsilon=0.0):
+        """Second half of ``act``: the decoded actions become the policy ships' rows of ``bg.actions``."""
+        idx = bg._policy_ship_idx
+        _lib.check(self._lib.ofb_policy_write_actions(_ptr(iact), _ptr(xy), bg.n_arenas, idx.numel(), _ptr(idx), bg.ships_number,
                                                       float(epsilon), bg.seed, bg.arena0, bg.total_steps, _ptr(bg.actions),
                                                       self._stream()))
         self.launch_count += 1
-        return iact, xy
 
     _TAP_STRIDE = {0: 320000, 1: 80000, 2: 20000, 3: 5120, 4: 100, 5: 80000, 6: 320000}
 
