@@ -8,11 +8,16 @@ MAX_TIME=200 episode restart when due.  One process per GPU; arenas are sharded 
 collective (weak scaling: the per-GPU batch is fixed), NCCL only all-reduces the per-episode stats.
 
 Workloads (BASELINE.json configs):
-    arena4096    configs[1]: 4096 default arenas (7 ships), random bots, step + raster   [default]
+    policy       configs[2]: 65536 arenas, ship 0 policy-driven (conv+dense bi-head forward, bf16)   [default at --gpus 1]
+    sharded1m    configs[4]: 131072 arenas per GPU, policy forward, learning, per-episode score/loss all-reduce
+                 and weight broadcast                                                                 [default at --gpus N > 1]
+    arena4096    configs[1]: 4096 default arenas (7 ships), random bots, step + raster
     stress       configs[3]: 16384 arenas x 32 ships, max fire rate, step + raster
-    policy       configs[2]: 65536 arenas, ship 0 policy-driven (conv+dense bi-head forward, bf16)
     policy7      configs[2] variant: 16384 arenas, all 7 ships policy-driven (trunk once per arena, heads x7)
-    sharded1m    configs[4]: 131072 arenas per GPU, policy forward, per-episode stat all-reduce
+
+The metric BASELINE.json names is "env-steps/sec (batched arenas + policy fwd)", so the default workload is the one
+with the forward.  The un-timed pre-roll places the MAX_TIME=200 episode restart -- `restart()`, the per-episode
+all-reduces and (when learning) a replay + weight broadcast -- INSIDE the K timed steps.
 
 Timing: CUDA events on the launching stream around every step, L2 flushed (256 MiB memset)
 between steps when the working set is smaller than L2, barrier + synchronize on both sides of the
@@ -220,8 +225,35 @@ def python_port_rate(ships, frames=100):
     return frames / (time.perf_counter() - t0)
 
 
+# ----------------------------------------------------------------------------- shared by both arms
+METRIC = "env-steps/sec (batched arenas: bots + fused step + observation raster%s)"
+
+
+def resolve_workload(args):
+    """No --workload: the metric's own config -- configs[2] on one GPU, configs[4] (1M arenas over 8 GPUs: 131072 each,
+    learning + per-episode all-reduce) on several."""
+    name = args.workload
+    if name == "auto":
+        name = "policy" if args.gpus <= 1 else "sharded1m"
+    return name, WORKLOADS[name]
+
+
+def workload_config(name, wl, world, learn):
+    """The `config` object: identical in the `ours` and the `reference` arm (only static facts of the workload)."""
+    return {"workload": name, "desc": wl["desc"], "arenas_per_gpu": wl["n"], "arenas_total": wl["n"] * world,
+            "ships_per_arena": wl["ships"], "policy_ships_per_arena": wl["policy"], "bots": wl["bot"],
+            "map_format": "bits u32[N,2,5000]", "max_time": 200, "learning": bool(learn),
+            "episode": "the un-timed pre-roll ends half of the timed steps before frame 200, so the MAX_TIME restart (restart + "
+                       "per-episode all-reduces%s) runs inside the timed region" %
+                       (" + replay / weight broadcast" if learn else "")}
+
+
+def wants_learning(args, name, wl):
+    return bool(wl["policy"]) and (args.learn == "on" or (args.learn == "auto" and name == "sharded1m"))
+
+
 # ----------------------------------------------------------------------------- GPU arm
-def gpu_arm(args, wl):
+def gpu_arm(args, name, wl):
     import torch
     import torch.distributed as dist
     from ofighters_b200 import ArenaConfig, BatchedBattleground
@@ -247,19 +279,22 @@ def gpu_arm(args, wl):
                              arena0=rank * N)
     policy = None
     learner = trainer = None
-    learn = wl["policy"] and (args.learn == "on" or (args.learn == "auto" and args.workload == "sharded1m"))
+    learn = wants_learning(args, name, wl)
     loss_stats = torch.zeros(2, dtype=torch.float64, device=dev)
-    if wl["policy"] and learn:
-        # ONE shared trainer (agents/qlearnIA_V2.py:308): rank 0 learns from the policy ships of its first 8 arenas and
-        # broadcasts the weights after every scheduled replay; the episode's [sum loss, replays] rides the K7 all-reduce
-        from ofighters_b200.trainer import Epsilon_cos, QLearner, TrainerB200, flatten_weights, unflatten_weights
-        trainer = TrainerB200(learning_rate=1e-4, epsilon=Epsilon_cos(period=110 * 400), batch_size=8, device=dev, seed=0,
-                              max_ships=8192)
-        policy = trainer.model
-        learner = QLearner(trainer, track=8, replay_every=50) if rank == 0 else None
-    elif wl["policy"]:
+    max_ships = int(os.environ.get("OFB_BENCH_MAX_SHIPS", "8192"))
+    if wl["policy"]:
         from ofighters_b200.policy import PolicyB200
-        policy = PolicyB200.random_init(device=dev, seed=0, max_ships=8192)
+        policy = PolicyB200.random_init(device=dev, seed=0, max_ships=max_ships)       # the actor of every rank
+    if learn:
+        # ONE shared trainer (agents/qlearnIA_V2.py:308): rank 0 learns from the policy ships of its first 8 arenas
+        # (QlearnIA.play's bookkeeping: collecting phase, eps-greedy with the trainer's schedule, replay at deaths and every
+        # 50 steps); every rank's actor takes the trainer's weights at common points (every 50 frames and at the episode
+        # end), the episode's [sum loss, replays] rides the K7 all-reduce
+        from ofighters_b200.trainer import Epsilon_cos, QLearner, TrainerB200, flatten_weights, unflatten_weights
+        schedule = Epsilon_cos(period=110 * 400)
+        if rank == 0:
+            trainer = TrainerB200(learning_rate=1e-4, epsilon=schedule, batch_size=8, device=dev, seed=0, max_ships=16)
+            learner = QLearner(trainer, track=8, replay_every=50, collecting_steps=20, snapshot=0, actor=policy)
     trainer_len = 571730
     maps = torch.empty((N, 2, 400 * 400 // 32), dtype=torch.int32, device=dev)
     bg.raster("bits", out=maps)
@@ -267,11 +302,35 @@ def gpu_arm(args, wl):
     flush_needed = state_bytes + maps.numel() * 4 < 2 * 126 * 2 ** 20
     flush_buf = L2Flush(dev, args.flush) if flush_needed else None
     launches = [0]
+    coll = {"all_reduce": 0, "broadcast": 0, "restarts": 0, "replays": 0}
+    frame_no = [0]                                        # frames since construction (identical on every rank)
+    weights_dirty = [False]
+
+    def n_launched():
+        return bg.launch_count + (policy.launch_count if policy is not None else 0) + \
+            (trainer.launch_count + trainer.model.launch_count if trainer is not None else 0)
+
+    def sync_actor_weights():
+        """Every rank's actor <- the shared trainer's weights (a broadcast over NCCL when there are several ranks)."""
+        if world > 1:
+            # the shared trainer's weights + the step of its epsilon schedule (exact in fp32: t < 44000)
+            flat = torch.cat([flatten_weights(trainer.get_weights()), torch.tensor([trainer.epsilon.t])]).to(dev) if rank == 0 else \
+                torch.empty(trainer_len + 1, dtype=torch.float32, device=dev)
+            sharding.broadcast_weights(flat, src=0)
+            coll["broadcast"] += 1
+            host = flat.cpu()
+            policy.load_weights(unflatten_weights(host[:trainer_len]))
+            if rank != 0:
+                schedule.t = float(host[-1])
+        elif weights_dirty[0]:
+            policy.load_weights(trainer.get_weights())
+        weights_dirty[0] = False
 
     def one_step():
-        n0 = bg.launch_count + (policy.launch_count if policy is not None else 0) + (trainer.launch_count if trainer is not None else 0)
+        n0 = n_launched()
         if bg.time >= max_time:
             bg.restart()
+            coll["restarts"] += 1
             if learner is not None:
                 loss_stats[0] += sum(learner.losses)
                 loss_stats[1] += len(learner.losses)
@@ -279,28 +338,41 @@ def gpu_arm(args, wl):
                 learner.reset()
             if world > 1:
                 sharding.reduce_episode_stats(bg.stats)   # K7: per-episode [score, kills, deaths, shots, ships, arenas]
-                if trainer is not None:
+                coll["all_reduce"] += 1
+                if learn:
                     sharding.reduce_loss_stats(loss_stats)     # ... and [sum of replay losses, replays]
+                    coll["all_reduce"] += 1
+            if learn:
+                sync_actor_weights()
             if policy is not None:
                 bg.raster("bits", out=maps)        # Battleground.restart builds a fresh Observation
         if policy is not None:
-            iact, xy = policy.act(bg, maps)        # forward on the current maps -> the policy ship's ("external") action row
-            if learner is not None:
-                learner.observe(bg, maps, iact, xy)            # remember / replay (fit) on rank 0
-            if trainer is not None and world > 1 and (bg.total_steps + 1) % 50 == 0:
-                flat = flatten_weights(trainer.get_weights()).to(dev) if rank == 0 else \
-                    torch.empty(trainer_len, dtype=torch.float32, device=dev)
-                sharding.broadcast_weights(flat, src=0)        # the single shared trainer's weights reach every rank
-                if rank != 0:
-                    policy.load_weights(unflatten_weights(flat.cpu()))
+            if learn:
+                sched = learner.trainer.epsilon if learner is not None else schedule
+                collecting = frame_no[0] + 1 < 20
+                if learner is not None:
+                    _, _, replayed = learner.act(bg, maps)     # choose (collecting / eps-greedy), write rows, remember / replay
+                    coll["replays"] += 1 if replayed else 0
+                    weights_dirty[0] |= replayed
+                else:                                          # the other ranks follow the shared schedule between broadcasts
+                    policy.act(bg, maps, epsilon=sched, collecting=collecting)
+                    if not collecting:
+                        sched.next()
+                if (frame_no[0] + 1) % 50 == 0:
+                    sync_actor_weights()
+            else:
+                policy.act(bg, maps)               # forward on the current maps -> the policy ship's ("external") action row
         bg.frame(maps=maps)                        # scripted bots + step + observation maps: one fused launch (ofb_frame_bots)
-        launches[0] += bg.launch_count + (policy.launch_count if policy is not None else 0) + \
-            (trainer.launch_count if trainer is not None else 0) - n0
+        frame_no[0] += 1
+        launches[0] += n_launched() - n0
 
     stream = torch.cuda.current_stream(dev)
-    for _ in range(warmup):
+    # un-timed pre-roll: the episode is advanced so that frame 200 (the restart) falls in the middle of the timed steps
+    preroll = max(0, max_time - steps // 2 - warmup) if steps < 2 * max_time else 0
+    for _ in range(preroll + warmup):
         one_step()
     torch.cuda.synchronize(dev)
+    time_at_start = bg.time
 
     # ---- timed region: exactly K steps, per-step CUDA events, optional L2 flush between steps
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
@@ -310,6 +382,8 @@ def gpu_arm(args, wl):
     torch.cuda.synchronize(dev)
     sampler.start()
     launches[0] = 0
+    for k in coll:
+        coll[k] = 0
     wall0 = time.perf_counter()
     for k in range(steps):
         if flush_buf is not None:
@@ -323,7 +397,9 @@ def gpu_arm(args, wl):
     torch.cuda.synchronize(dev)
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
-    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    coll_timed = dict(coll)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     per_rank_ms = [total_ms / steps]
     if world > 1:
@@ -332,10 +408,16 @@ def gpu_arm(args, wl):
         per_rank_ms = [float(x.item()) / steps for x in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    st = bg.state(("overflow", "near_ties", "n_lasers"))
+    counters = torch.stack([st["overflow"].sum(), st["near_ties"].sum(), st["n_lasers"].sum()]).to(torch.int64)
+    if world > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    overflow, near_ties, live_lasers = [int(x) for x in counters.tolist()]
     bg.check_overflow()
     value = N * world * steps / (total_ms * 1e-3)
+    episode_stats = sharding.stats_dict(bg.stats)
 
-    # ---- dominant kernel alone (raster for the arena workloads), same events + flush
+    # ---- dominant kernel alone, same events + flush
     roof = kernel_roofline(bg, maps, flush_buf, wl, dev, policy)
 
     # ---- end-to-end through the public API with HOST buffers
@@ -345,29 +427,37 @@ def gpu_arm(args, wl):
 
     e2e = e2e_arm(bg, maps, wl, dev, min(steps, 400 if policy is None else 20), world, policy, make_bg)
 
+    extra = {"ship_steps_per_s": value * S,
+             "l2": (flush_buf.describe() if flush_needed else "working set %.0f MB > L2" % ((state_bytes + maps.numel() * 4) / 1e6)),
+             "wall_s_timed_region": wall, "ms_per_step_by_rank": per_rank_ms,
+             "frames_timed": "episode frames %d..%d, restart, frames 0..%d" % (time_at_start, max_time - 1, bg.time - 1)
+                             if coll_timed["restarts"] else "episode frames %d..%d" % (time_at_start, bg.time - 1),
+             "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
+             "preroll_frames": preroll, "live_lasers_at_end": live_lasers, "episode_stats_reduced": episode_stats}
+    if learn:
+        extra["learning"] = {
+            "replays_in_timed_region_rank0": coll_timed["replays"], "replays_reduced": float(loss_stats[1].item()),
+            "mean_replay_loss": ((float(loss_stats[0].item()) + (sum(learner.losses) if learner is not None else 0.0))
+                                 / max(1.0, float(loss_stats[1].item()) + (len(learner.losses) if learner is not None else 0))),
+            "trainer_steps": trainer.steps if trainer is not None else None,
+            "epsilon": learner.trainer.epsilon.get() if learner is not None else None,
+            "what": "rank 0 runs QlearnIA.play's bookkeeping for the policy ships of its first 8 arenas (20 random collecting steps, "
+                    "eps-greedy with Epsilon_cos(110*400) evaluated on the device, Trainer.replay = batch 8, Adam 1e-4, at "
+                    "every tracked death and every 50 steps of bot 1); every rank's actor takes the trainer's weights every 50 "
+                    "frames and at the episode end (NCCL broadcast of 571730 floats); [sum loss, replays] all-reduced with the "
+                    "episode statistics"}
+    if wl["policy"] and rank == 0 and world == 1 and not os.environ.get("OFB_BENCH_NO_EXTRA"):
+        extra["other_workloads"] = side_workloads(dev)
     out = {
-        "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster%s)" %
-                  (" + policy fwd" if wl["policy"] else ""),
+        "metric": METRIC % (" + policy fwd" if wl["policy"] else ""),
         "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 laser physics / i32 ship state / u32 bit maps" + (" / bf16 policy" if wl["policy"] else ""),
         "data": "synthetic (Philox-seeded spawns and bot actions)",
-        "config": {"workload": args.workload, "desc": wl["desc"], "arenas_per_gpu": N, "arenas_total": N * world,
-                   "ships_per_arena": S, "ship_steps_per_s": value * S, "map_format": "bits u32[N,2,5000]",
-                   "episode": "restart every 200 frames inside the timed region",
-                   "l2": (flush_buf.describe() if flush_needed
-                          else "working set %.0f MB > L2" % ((state_bytes + maps.numel() * 4) / 1e6)),
-                   "wall_s_timed_region": wall, "ms_per_step_by_rank": per_rank_ms,
-                   **({"learning": {"replays_reduced": float(loss_stats[1].item()),
-                                    "pending_replays": len(learner.losses) if learner is not None else 0,
-                                    "mean_replay_loss": ((float(loss_stats[0].item()) + (sum(learner.losses) if learner is not None else 0.0))
-                                                         / max(1.0, float(loss_stats[1].item()) + (len(learner.losses) if learner is not None else 0))),
-                                    "trainer_steps": trainer.steps,
-                                    "what": "rank 0 runs Trainer.replay (batch 8, Adam 1e-4) every 50 frames on transitions of "
-                                            "its first 8 arenas' policy ships; weights broadcast to all ranks after each; "
-                                            "[sum loss, replays] all-reduced with the episode statistics"}}
-                      if trainer is not None else {})},
-        "gpu_launches": launches[0], "clocks": clocks, "e2e": e2e, "roofline": roof,
+        "config": workload_config(name, wl, world, learn),
+        "gpu_launches": launches[0], "collectives_in_timed_region": coll_timed["all_reduce"] + coll_timed["broadcast"],
+        "collectives": coll_timed, "near_ties": near_ties, "overflow": overflow,
+        "clocks": clocks, "e2e": e2e, "roofline": roof, "extra": extra,
     }
     if rank == 0:
         if world == 1:
@@ -385,21 +475,95 @@ def gpu_arm(args, wl):
         dist.destroy_process_group()
 
 
+def side_workloads(dev):
+    """configs[1] and configs[3] (the forward-less arena workloads) in short form, for the `extra` of the default line:
+    event-timed fused frame kernel with the L2 flushed between launches."""
+    import torch
+    from ofighters_b200 import ArenaConfig, BatchedBattleground
+    res = {}
+    for wname in ("arena4096", "stress"):
+        w = WORKLOADS[wname]
+        b = BatchedBattleground(w["n"], ships={w["bot"]: w["ships"]}, config=ArenaConfig(laser_cap=w["lcap"]), device=dev, seed=SEED)
+        m = torch.empty((w["n"], 2, 5000), dtype=torch.int32, device=dev)
+        fl = L2Flush(dev)
+        st = torch.cuda.current_stream(dev)
+        for _ in range(12 if wname == "stress" else 30):
+            b.frame(maps=m)
+        ts = []
+        for _ in range(20 if wname == "arena4096" else 8):
+            fl()
+            a, c = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            b.frame(maps=m)
+            c.record(st)
+            ts.append((a, c))
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(c) for a, c in ts) / len(ts)
+        res[wname] = {"env_steps_per_s": w["n"] / (ms * 1e-3), "ms_per_step": ms, "arenas": w["n"], "ships": w["ships"],
+                      "frames": "%d..%d of an episode" % (b.time - len(ts), b.time - 1)}
+        del b, m, fl
+    return res
+
+
 def _ncu_traffic():
-    """DRAM bytes per launch of the dominant kernels, from the committed `ncu --set full` captures (profiles/)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            return json.load(f)
-    except Exception:
-        return {}
+    """DRAM bytes per launch / per item of the dominant kernels, from the committed `ncu --set full` captures (profiles/)."""
+    out = {}
+    for fn in ("r01_traffic.json", "r02_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                out.update(json.load(f))
+        except Exception:
+            pass
+    return out
+
+
+# Forward layers: kernel, what bounds it, algorithmic bytes and FLOPs per item (DESIGN.md section 4; Appendix B MACs x 2).
+# "per": the trunk runs once per ARENA, the heads once per policy SHIP.
+POLICY_LAYERS = {
+    "trunk12": dict(kernel_sparse="k_sp_trunk12", kernel_dense="k_tz_trunk12", per="arena", bytes=40000 + 160000, flops=2 * (23.04e6 + 23.04e6)),
+    "conv3": dict(kernel="k_tc_conv_pool", per="arena", bytes=160000 + 40000, flops=2 * 5.76e6),
+    "conv4": dict(kernel="k_tc_conv_pool", per="arena", bytes=40000 + 10240, flops=2 * 1.44e6),
+    "dense1": dict(kernel="k_tc_dense1", per="arena", bytes=10240 + 400, flops=2 * 0.5e6),
+    "heads": dict(kernel="k_heads", per="ship", bytes=400 + 32 + 80000, flops=2 * (5.1e3 + 62.5e3 + 45e3 + 720e3 + 800)),
+    "up3": dict(kernel="k_tz_up3", per="ship", bytes=80000 + 640000, flops=2 * 11.52e6),
+    "up4": dict(kernel="k_tz_up4", per="ship", bytes=640000 + 8, flops=2 * 11.52e6),
+    "tail": dict(kernel="k_tz_tail", per="ship", bytes=80000 + 8, flops=2 * (11.52e6 + 11.52e6)),
+    "argmax": dict(kernel="k_argmax_final", per="ship", bytes=8, flops=0.0),
+}
+TENSOR_LAYERS = ("conv3", "conv4", "up3", "up4", "tail")      # tcgen05 kernels: reported against the tensor peak
+
+
+def time_frame_kernel(bg, maps, flush_buf, dev, iters):
+    """k_frame alone (CUDA events, flush or queued work before every launch) -> (mean us, algorithmic bytes per launch)."""
+    import torch
+    stream = torch.cuda.current_stream(dev)
+    map_bytes = maps.numel() * 4
+    ts = []
+    for _ in range(3):
+        bg.frame(maps=maps)
+    for _ in range(iters):
+        nb = bg.algorithmic_step_bytes() + map_bytes
+        if flush_buf is not None:
+            flush_buf()
+        else:
+            torch.cuda._sleep(200000)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        bg.frame(maps=maps)
+        b.record(stream)
+        ts.append((a, b, nb))
+    torch.cuda.synchronize(dev)
+    return sum(a.elapsed_time(b) for a, b, _ in ts) / iters * 1e3, sum(x[2] for x in ts) / iters
 
 
 def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
-    """Dominant kernel of the arena workloads = the fused frame kernel (step + raster; the maps are >95 % of its bytes):
+    """Arena workloads: the dominant kernel is the fused frame kernel (step + raster; the maps are >95 % of its bytes):
     achieved = algorithmic bytes (88 B/ship + 64 B/live laser + the maps it must produce: N * 2 * W*H/8) / mean launch time.
-    Policy workloads: the dominant kernel is the phase-folded upconv4 + argmax (tcgen05); achieved =
-    its algorithmic FLOPs (2 * 400*400*72 per ship, Appendix B) / its mean launch time, against the
-    measured bf16 tensor peak; the whole forward is reported beside it in dense-equivalent FLOPs."""
+    Policy workloads: the forward's slowest kernel, each kernel against the roofline that really bounds it -- the tcgen05
+    kernels as algorithmic FLOPs (Appendix B MACs x 2) / time against the measured bf16 peak, the CUDA-core kernels as
+    algorithmic bytes / time against the measured HBM peak (with a note when the kernel is issue-bound rather than
+    HBM-bound) -- with the per-layer table, the whole forward in dense-equivalent FLOPs and the frame kernel (HBM) at this
+    arena count beside it."""
     import torch
     peaks = {}
     try:
@@ -408,40 +572,77 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s"
     stream = torch.cuda.current_stream(dev)
     if policy is not None:
         tpeak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         P = wl["policy"]                                  # policy ships per arena: the trunk runs once per arena, the heads P times
-        vec = bg.obs_vec[:, :P, :].contiguous().reshape(-1, 8)
-        policy.profile(True)
-        for _ in range(3):
-            policy.forward_argmax(maps, vec, P)
-        prof = policy.profile(False)                      # {layer: ms per forward of the whole batch}
         n = bg.n_arenas
-        fl = {"trunk12": 2 * (23.04e6 + 23.04e6), "conv3": 2 * 5.76e6, "conv4": 2 * 1.44e6, "dense1": 2 * 0.5e6,
-              "heads": P * 2 * (5.1e3 + 62.5e3 + 45e3 + 720e3 + 800), "up3": P * 2 * 11.52e6, "up4": P * 2 * 11.52e6, "argmax": 0.0}
-        layers = {k: {"ms": v, "alg_tflops": fl.get(k, 0.0) * n / (v * 1e-3) / 1e12 if v > 0 else None}
-                  for k, v in prof.items()}
-        dom = max(prof, key=prof.get)
+        traffic = _ncu_traffic().get("policy_per_item", {})
+        dense_trunk = bool(os.environ.get("OFB_POLICY_DENSE_TRUNK"))
+
+        def profile_now():
+            vec = bg.obs_vec[:, :P, :].contiguous().reshape(-1, 8)
+            policy.profile(True)
+            for _ in range(3):
+                policy.forward_argmax(maps, vec, P)
+            prof = policy.profile(False)                  # {layer: ms per forward of the whole batch}
+            layers = {}
+            for k, ms in prof.items():
+                if ms <= 0 or k not in POLICY_LAYERS:
+                    continue
+                L = POLICY_LAYERS[k]
+                items = n * (P if L["per"] == "ship" else 1)
+                kern = L.get("kernel") or (L["kernel_dense"] if dense_trunk else L["kernel_sparse"])
+                tens = k in TENSOR_LAYERS or (k == "trunk12" and dense_trunk)
+                ent = {"kernel": kern, "ms": ms, "bound": "tensor" if tens else "hbm",
+                       "alg_tflops": L["flops"] * items / (ms * 1e-3) / 1e12, "alg_gbs": L["bytes"] * items / (ms * 1e-3) / 1e9}
+                ent["frac"] = ent["alg_tflops"] / tpeak if tens else ent["alg_gbs"] / peak
+                if kern in traffic:
+                    ent["ncu_dram_bytes_per_item"] = traffic[kern]
+                layers[k] = ent
+            return prof, layers
+
+        prof, layers = profile_now()
+        dom = max(layers, key=lambda k: layers[k]["ms"])
         total = sum(prof.values())
-        per_item = _ncu_traffic().get("policy_per_item", {})
-        kname = {"trunk12": ("k_tz_trunk12 (conv1 from bits + block-Toeplitz conv2 + pools)" if os.environ.get("OFB_POLICY_DENSE_TRUNK")
-                             else "k_sp_trunk12 (sparse conv1 + conv2 + pools on CUDA cores)"), "conv3": "k_tc_conv_pool", "conv4": "k_tc_conv_pool",
-                 "dense1": "k_tc_dense1", "heads": "k_heads", "up3": "k_tz_up3", "up4": "k_tz_up4", "argmax": "k_argmax_final"}
-        return {"bound": "tensor", "kernel": kname.get(dom, dom), "achieved": layers[dom]["alg_tflops"], "peak": tpeak,
-                "unit": "TFLOP/s", "frac": layers[dom]["alg_tflops"] / tpeak,
-                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM loop)" if peaks else "fallback",
-                "traffic": (per_item[kname.get(dom, dom).split(" ")[0]] * min(n * P, policy.max_ships)
-                            if kname.get(dom, dom).split(" ")[0] in per_item else None),
-                "us_per_launch": prof[dom] * 1e3 / max(1, -(-n * P // policy.max_ships)),
-                "note": "algorithmic FLOPs of the layer (Appendix B MACs x 2) / its device time; these layers have 8 or fewer "
-                        "channels, so the tensor pipe is bound by operand reads and the kernels by HBM / epilogue, not by math",
+        D = layers[dom]
+        chunks = max(1, -(-n * P // policy.max_ships))
+        items_per_launch = min(n * (P if POLICY_LAYERS[dom]["per"] == "ship" else 1), policy.max_ships)
+        fus, fbytes = time_frame_kernel(bg, maps, flush_buf, dev, 10)
+        ftr = _ncu_traffic().get("arena%d" % n, {})
+        roof = {"bound": D["bound"], "kernel": D["kernel"],
+                "achieved": D["alg_tflops"] if D["bound"] == "tensor" else D["alg_gbs"],
+                "peak": tpeak if D["bound"] == "tensor" else peak, "unit": "TFLOP/s" if D["bound"] == "tensor" else "GB/s",
+                "frac": D["frac"],
+                "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 GEMM loop)" if D["bound"] == "tensor" else hbm_src)
+                               if peaks else "fallback",
+                "traffic": traffic[D["kernel"]] * items_per_launch if D["kernel"] in traffic else None,
+                "us_per_launch": D["ms"] * 1e3 / chunks,
+                "note": "slowest kernel of the forward at the state the timed region ended in; tcgen05 kernels = algorithmic FLOPs "
+                        "(Appendix B MACs x 2) / device time vs the measured bf16 peak; CUDA-core kernels = algorithmic bytes / device "
+                        "time vs the measured HBM peak (k_sp_trunk12 and k_heads are issue-bound, not HBM-bound: the fraction says "
+                        "how far above their HBM floor they run)",
                 "whole_forward": {"ms": total, "forwards_per_s": n * P / (total * 1e-3), "policy_ships_per_arena": P,
                                   "dense_equiv_tflops": 155.3e6 * n * P / (total * 1e-3) / 1e12,
                                   "frac_of_peak": 155.3e6 * n * P / (total * 1e-3) / 1e12 / tpeak,
+                                  "pointer_head_floor_ms": 47.7e6 * n * P / (tpeak * 1e12) * 1e3,
                                   "note": "dense-equivalent = 155.3 MFLOP per ship-forward (Appendix B), the trunk counted once per SHIP "
-                                          "as the reference's batch-1 predict does; the library runs it once per arena"},
-                "layers": layers}
+                                          "as the reference's batch-1 predict does; the library runs it once per arena; "
+                                          "pointer_head_floor_ms = 47.7 MFLOP x ships / measured bf16 peak (SURVEY 8(d))"},
+                "layers": layers,
+                "frame_kernel": {"bound": "hbm", "kernel": "k_frame", "us_per_launch": fus, "algorithmic_bytes_per_launch": fbytes,
+                                 "achieved": fbytes / (fus * 1e-6) / 1e9, "peak": peak, "unit": "GB/s",
+                                 "frac": fbytes / (fus * 1e-6) / 1e9 / peak, "traffic": ftr.get("k_frame"), "peak_source": hbm_src}}
+        # the same table at the laser peak of an episode (around frame 30), where the sparse trunk is at its slowest
+        if not os.environ.get("OFB_BENCH_NO_EXTRA"):
+            bg.restart()
+            bg.raster("bits", out=maps)
+            for _ in range(30):
+                bg.frame(maps=maps)
+            prof30, layers30 = profile_now()
+            roof["at_laser_peak_frame30"] = {"ms": sum(prof30.values()), "layers_ms": {k: v["ms"] for k, v in layers30.items()}}
+        return roof
     res = {}
     map_bytes = maps.numel() * 4
     bg.restart()
@@ -472,7 +673,7 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
     tr = _ncu_traffic().get("arena%d" % bg.n_arenas, {}) if bg.ships_number == 7 else {}
     return {"bound": "hbm", "kernel": dom, "achieved": res[dom]["gbs"], "peak": peak, "unit": "GB/s",
             "frac": res[dom]["gbs"] / peak,
-            "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+            "peak_source": hbm_src,
             "traffic": tr.get(dom),
             "traffic_note": "ncu dram__bytes_read+write per launch (profiles/r01_ncu_full_frame*_v4.md): below the algorithmic bytes "
                             "at 4096 arenas because the last ~50 MB of the maps are still dirty in the 126 MB L2 when the kernel ends", "us_per_launch": res[dom]["us"], "algorithmic_bytes_per_launch": res[dom]["bytes"],
@@ -638,34 +839,37 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--workload", default="arena4096", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="auto", choices=["auto"] + sorted(WORKLOADS),
+                    help="auto = the metric's config: policy (configs[2]) on one GPU, sharded1m (configs[4]) on several")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--learn", default="auto", choices=["auto", "on", "off"],
-                    help="policy workloads: Q-learning replay (fit) every 50 frames on rank 0, weights broadcast, loss in the "
-                         "per-episode reduction (auto = on for sharded1m)")
+                    help="policy workloads: QlearnIA.play's learning loop on rank 0 (replay = fit at tracked deaths and every 50 "
+                         "frames), weights broadcast, loss in the per-episode reduction (auto = on for sharded1m)")
     ap.add_argument("--flush", default="write+read", choices=["write", "write+read"],
                     help="L2 flush between timed steps when the working set is L2-sized")
     args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
+    name, wl = resolve_workload(args)
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
         steps = min(args.steps, 400)
         v, ms, cores, sample, fwd = cpu_arm_with_policy(wl, steps, min(max(args.warmup, 3), 10))
         emit(({
-            "impl": "reference", "metric": "env-steps/sec (batched arenas: bots + fused step + observation raster%s)" %
-                                           (" + policy fwd" if wl["policy"] else ""),
+            "impl": "reference", "metric": METRIC % (" + policy fwd" if wl["policy"] else ""),
             "value": v, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64 laser physics / i32 ship state / u32 bit maps", "data": "synthetic (Philox-seeded)",
-            "config": {"workload": args.workload, "desc": wl["desc"],
-                       "note": "CPU restatement of the reference's algorithm (the reference is pure Python under "
-                               "/root/reference and is absent on the GPU box)" +
-                               ("; policy forward = torch-fp32 restatement of the Keras model" if wl["policy"] else "")},
+            "dtype": "f64 laser physics / i32 ship state / u32 bit maps" + (" / fp32 policy" if wl["policy"] else ""),
+            "data": "synthetic (Philox-seeded)",
+            "config": workload_config(name, wl, max(1, args.gpus), wants_learning(args, name, wl)),
+            "reference_class": "cpu-port",
+            "note": "CPU restatement of the reference's algorithm on a bounded sample of the workload (the reference is pure "
+                    "Python under /root/reference and is absent on the GPU box)" +
+                    ("; policy forward = torch-fp32 restatement of the Keras model; learning is not part of the CPU sample"
+                     if wl["policy"] else ""),
             "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
-    gpu_arm(args, wl)
+    gpu_arm(args, name, wl)
 
 
 if __name__ == "__main__":

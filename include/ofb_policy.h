@@ -75,6 +75,19 @@ int ofb_policy_forward(ofb_policy *p, const uint32_t *maps_bits_dev, const float
                        int ships_per_arena, float *act_dev, float *ptr_dev, int32_t *iaction_dev, int32_t *xy_dev,
                        void *stream);
 
+/* Exploration schedule of the shared trainer (lib/epsilon.py:36-86 behind Trainer.epsilon, agents/qlearnIA_V2.py:53,195-201)
+ * as a closed-form function of the number t of decay_epsilon() calls made so far, so that the device evaluates it itself:
+ *   OFB_EPS_CONST   eps(t) = start
+ *   OFB_EPS_COSINE  eps(t) = start * (cos(2 pi (t mod period) / period) + 1) / 2          (Epsilon_cos, amplitude = start)
+ *   OFB_EPS_DECAY   eps(t) = start * decay^min(t, n),  n = first step count with start * decay^n <= floor  (Epsilon_decay:
+ *                   the reference stops multiplying once epsilon is at or below its soft minimum)                        */
+enum { OFB_EPS_CONST = 0, OFB_EPS_COSINE = 1, OFB_EPS_DECAY = 2 };
+typedef struct ofb_eps_schedule {
+    int32_t kind;
+    int32_t reserved;
+    double start, period, decay, floor;  /* doubles: 0.9999^t must not drift from the host's value over 10^5 steps */
+} ofb_eps_schedule;
+
 /* QlearnIA.play's action vector (agents/qlearnIA_V2.py:447-456): row (shoot, thrust, x, y) =
  * (iaction == 0, iaction == 1, x, y) written to actions[arena, ship_index[p], :] (int16 [A,S,4]).
  * With epsilon > 0 a ship acts randomly (iaction U{0,1}, x,y U{0..399}; :199-204,317-321) when its
@@ -82,6 +95,18 @@ int ofb_policy_forward(ofb_policy *p, const uint32_t *maps_bits_dev, const float
 int ofb_policy_write_actions(const int32_t *iaction_dev, const int32_t *xy_dev, int64_t n_arenas, int ships_per_arena,
                              const int32_t *ship_index_dev, int n_ships_total, float epsilon, uint64_t seed,
                              int64_t arena0, uint32_t step, int16_t *actions_dev, void *stream);
+
+/* The same with the trainer's schedule evaluated on the device at schedule step t, and with the action that is PLAYED
+ * written back over iaction_dev / xy_dev (in / out), which is what QlearnIA.play remembers as previous_action /
+ * previous_pointer (:399-401).  force_random != 0 = the collecting phase (total_steps < collecting_steps, :394-396):
+ * every row is random_play() and iaction_dev / xy_dev need not hold a prediction.  eps_out_dev (optional, float[1])
+ * receives the epsilon that was used. */
+int ofb_policy_play_actions(int32_t *iaction_dev, int32_t *xy_dev, int64_t n_arenas, int ships_per_arena,
+                            const int32_t *ship_index_dev, int n_ships_total, const ofb_eps_schedule *sched, double t,
+                            int force_random, uint64_t seed, int64_t arena0, uint32_t step, int16_t *actions_dev,
+                            float *eps_out_dev, void *stream);
+/* eps(t) evaluated on the host by the same code (logging: QlearnIA.epsilons, agents/qlearnIA_V2.py:364). */
+float ofb_eps_value(const ofb_eps_schedule *sched, double t);
 
 /* Dense image [B,400,400,2] (NHWC; fmt OFB_MAP_BF16 / OFB_MAP_U8 / 3 = float32) -> bit maps, for
  * predict([img, vec]) callers that hold Keras-style images.  A pixel is set iff it is non-zero. */

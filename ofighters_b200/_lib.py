@@ -49,6 +49,12 @@ class OfbTrainConfig(C.Structure):
                 ("max_batch", C.c_int32), ("reserved", C.c_int32 * 8)]
 
 
+class OfbEpsSchedule(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("start", C.c_double), ("period", C.c_double),
+                ("decay", C.c_double), ("floor", C.c_double)]
+
+
+EPS_CONST, EPS_COSINE, EPS_DECAY = 0, 1, 2
 ENGINE_TENSOR, ENGINE_CUDA_CORE = 0, 1
 
 
@@ -113,6 +119,11 @@ def load():
     lib.ofb_policy_set_engine.argtypes = [vp, i32]
     lib.ofb_policy_forward.argtypes = [vp, vp, vp, i64, i32, vp, vp, vp, vp, vp]
     lib.ofb_policy_write_actions.argtypes = [vp, vp, i64, i32, vp, i32, C.c_float, u64, i64, u32, vp, vp]
+    lib.ofb_policy_play_actions.argtypes = [vp, vp, i64, i32, vp, i32, C.POINTER(OfbEpsSchedule), C.c_double, i32, u64, i64, u32,
+                                            vp, vp, vp]
+    lib.ofb_policy_play_actions.restype = i32
+    lib.ofb_eps_value.argtypes = [C.POINTER(OfbEpsSchedule), C.c_double]
+    lib.ofb_eps_value.restype = C.c_float
     lib.ofb_policy_pack_image.argtypes = [vp, i32, i64, vp, vp]
     lib.ofb_policy_debug_tap.argtypes = [vp, i32, i64, vp, vp]
     lib.ofb_policy_profile.argtypes = [vp, i32, vp]

@@ -36,18 +36,32 @@ def _deps():
     return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(inc, f) for f in os.listdir(inc)]
 
 
+def _compile(src, extra, obj, verbose):
+    cmd = ["nvcc"] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-c", os.path.join(CSRC, src), "-o", obj]
+    subprocess.check_call(cmd)
+    return obj
+
+
 def build(force=False, verbose=False):
+    """Compiles the translation units that are older than any source / header (in parallel) and links libofb.so."""
+    from concurrent.futures import ThreadPoolExecutor
     newest = max(os.path.getmtime(p) for p in _deps())
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= newest:
         return LIB
     os.makedirs(OUT_DIR, exist_ok=True)
-    objs = []
+    hdr_newest = max(os.path.getmtime(p) for p in _deps() if not p.endswith(".cu"))
+    jobs, objs = [], []
     for src, extra in UNITS:
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = ["nvcc"] + ARCH + COMMON + extra + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-c", os.path.join(CSRC, src), "-o", obj]
-        subprocess.check_call(cmd)
         objs.append(obj)
+        stale = force or not os.path.exists(obj) or \
+            os.path.getmtime(obj) < max(hdr_newest, os.path.getmtime(os.path.join(CSRC, src)))
+        if stale:
+            jobs.append((src, extra, obj))
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for f in [ex.submit(_compile, s, e, o, verbose) for s, e, o in jobs]:
+            f.result()
     subprocess.check_call(["nvcc"] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcuda"])
     return LIB
 

@@ -357,6 +357,7 @@ extern "C" int64_t ofb_state_stride(const ofb_arenas *h) { return h ? (int64_t)h
 extern "C" int ofb_reset(ofb_arenas *h, const uint8_t *mask_dev, const int32_t *spawn_dev, int64_t *stats_dev,
                          void *stream) {
     if (!h || !spawn_dev) { ofb_set_error("ofb_reset: null argument"); return OFB_E_ARG; }
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
     k_reset<<<nblocks(h->n_arenas * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         h->state, h->lay, mask_dev, spawn_dev, reinterpret_cast<unsigned long long *>(stats_dev), h->n_arenas);
     OFB_CUDA_CHECK(cudaGetLastError());
@@ -365,6 +366,7 @@ extern "C" int ofb_reset(ofb_arenas *h, const uint8_t *mask_dev, const int32_t *
 
 extern "C" int ofb_stats(const ofb_arenas *h, int64_t *stats_dev, void *stream) {
     if (!h || !stats_dev) { ofb_set_error("ofb_stats: null argument"); return OFB_E_ARG; }
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
     if (h->n_arenas == 0) return OFB_OK;
     k_stats<<<nblocks(h->n_arenas * 32, 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->lay,
                                                                              reinterpret_cast<unsigned long long *>(stats_dev), h->n_arenas);
@@ -374,6 +376,7 @@ extern "C" int ofb_stats(const ofb_arenas *h, int64_t *stats_dev, void *stream) 
 
 extern "C" int ofb_obs_vec(const ofb_arenas *h, float *out_dev, void *stream) {
     if (!h || !out_dev) { ofb_set_error("ofb_obs_vec: null argument"); return OFB_E_ARG; }
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
     const long long nt = h->n_arenas * h->lay.S;
     k_obs_vec<<<nblocks(nt, 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->lay, reinterpret_cast<float4 *>(out_dev), nt);
     OFB_CUDA_CHECK(cudaGetLastError());
@@ -386,6 +389,7 @@ extern "C" int ofb_bot_actions(const ofb_arenas *h, int bot_kind, const uint8_t 
         ofb_set_error("ofb_bot_actions: bad argument");
         return OFB_E_ARG;
     }
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
     const long long nt = h->n_arenas * h->lay.S;
     k_bot_actions<<<nblocks(nt, 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->lay, bot_kind, kinds_dev, seed, arena0, step,
                                                                        reinterpret_cast<int2 *>(actions_dev), nt);
@@ -405,6 +409,7 @@ extern "C" int ofb_random_spawn(int64_t n_arenas, int n_ships, int width, int he
 
 extern "C" int ofb_state_export(const ofb_arenas *h, const ofb_state_view *view, void *stream) {
     if (!h || !view) { ofb_set_error("ofb_state_export: null argument"); return OFB_E_ARG; }
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
     k_xfer<false><<<(unsigned)h->n_arenas, 128, 0, (cudaStream_t)stream>>>(h->state, h->lay, *view, h->n_arenas);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
@@ -412,6 +417,7 @@ extern "C" int ofb_state_export(const ofb_arenas *h, const ofb_state_view *view,
 
 extern "C" int ofb_state_import(ofb_arenas *h, const ofb_state_view *view, void *stream) {
     if (!h || !view) { ofb_set_error("ofb_state_import: null argument"); return OFB_E_ARG; }
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
     k_xfer<true><<<(unsigned)h->n_arenas, 128, 0, (cudaStream_t)stream>>>(h->state, h->lay, *view, h->n_arenas);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;

@@ -178,3 +178,18 @@ void ofb_set_error(const char *fmt, ...);
             return OFB_E_CUDA;                                                            \
         }                                                                                 \
     } while (0)
+
+// Opt-in dynamic shared memory is a per-device (per-context) attribute of a kernel: a call site remembers, per calling thread
+// AND per device, the largest size it has configured, so that one thread driving handles on several GPUs configures each.
+struct SmemAttrCache {
+    int sz[32];
+    template <class K> cudaError_t ensure(K kernel, int bytes) {
+        int d = 0;
+        cudaGetDevice(&d);
+        int &c = sz[d & 31];
+        if (bytes <= c) return cudaSuccess;
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e == cudaSuccess) c = bytes;
+        return e;
+    }
+};

@@ -786,12 +786,9 @@ extern "C" int ofb_policy_forward(ofb_policy *p, const uint32_t *maps, const flo
         ofb_set_error("ofb_policy_forward: bad argument");
         return OFB_E_ARG;
     }
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_heads, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(HEADS_SMEM_FLOATS * sizeof(float))));
-        attr_set = true;
-    }
+    OFB_CUDA_CHECK(cudaSetDevice(p->device));
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_heads, (int)(HEADS_SMEM_FLOATS * sizeof(float))));
     const int64_t chunk = p->max_ships / P;                     // arenas per chunk
     for (int64_t a0 = 0; a0 < n_arenas; a0 += chunk) {
         const int A = (int)((n_arenas - a0) < chunk ? (n_arenas - a0) : chunk);
@@ -807,21 +804,41 @@ extern "C" int ofb_policy_forward(ofb_policy *p, const uint32_t *maps, const flo
 // ------------------------------------------------------------------------------------------------
 // action vector of QlearnIA.play (+ eps-greedy random_play), image packing, debug taps
 // ------------------------------------------------------------------------------------------------
-__global__ void k_write_actions(const int *__restrict__ iact, const int *__restrict__ xy, long long n_rows, int P,
-                                const int *__restrict__ ship_index, int S, float eps, uint64_t seed, long long arena0, uint32_t step,
-                                int2 *__restrict__ actions) {
+// eps(t) of include/ofb_policy.h (double precision: t reaches 10^5..10^6 and the cosine's argument must not lose it)
+__host__ __device__ inline float eps_at(const ofb_eps_schedule &s, double t) {
+    if (s.kind == OFB_EPS_COSINE) {
+        const double ph = fmod(t, s.period) / s.period;
+        return (float)(s.start * (cos(ph * 6.283185307179586) + 1.0) * 0.5);
+    }
+    if (s.kind == OFB_EPS_DECAY) {
+        double n = 0.0;
+        if (s.start > s.floor && s.decay > 0.0 && s.decay < 1.0) n = ceil(log(s.floor / s.start) / log(s.decay));
+        return (float)(s.start * pow(s.decay, fmin(t, n)));
+    }
+    return (float)s.start;
+}
+
+// WRITEBACK: the played action replaces the prediction in iact / xy (what QlearnIA.play remembers, :399-401)
+template <bool WRITEBACK>
+__global__ void k_write_actions(int *__restrict__ iact, int *__restrict__ xy, long long n_rows, int P,
+                                const int *__restrict__ ship_index, int S, ofb_eps_schedule sched, double t, int force_random,
+                                uint64_t seed, long long arena0, uint32_t step, int2 *__restrict__ actions, float *__restrict__ eps_out) {
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float eps = force_random ? 1.0f : eps_at(sched, t);
+    if (r == 0 && eps_out) *eps_out = eps;
     if (r >= n_rows) return;
     const long long a = r / P;
     const int ship = ship_index[r % P];
-    int ia = iact[r], x = xy[r * 2], y = xy[r * 2 + 1];
+    int ia = 0, x = 0, y = 0;
+    if (!force_random) { ia = iact[r]; x = xy[r * 2]; y = xy[r * 2 + 1]; }
     if (eps > 0.f) {
         uint32_t c[4] = {(uint32_t)(arena0 + a), (uint32_t)ship, step, 2u};
         philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-        if ((float)(c[0] >> 8) * (1.0f / 16777216.0f) <= eps) {     // np.random.rand() <= epsilon  (:201)
+        if (force_random || (float)(c[0] >> 8) * (1.0f / 16777216.0f) <= eps) {     // np.random.rand() <= epsilon  (:201)
             ia = (int)(c[1] & 1u);                                   // random.randint(0, action_size - 1)
             x = (int)mulhi32(c[2], POL_W);                           // randint(0, DEFAULT_WIDTH - 1)
             y = (int)mulhi32(c[3], POL_W);
+            if (WRITEBACK) { iact[r] = ia; xy[r * 2] = x; xy[r * 2 + 1] = y; }
         }
     }
     const int shoot = ia == 0, thrust = ia == 1;                     // act_vector[iaction] = 1   (:449)
@@ -834,11 +851,33 @@ extern "C" int ofb_policy_write_actions(const int32_t *iact, const int32_t *xy, 
     if (!iact || !xy || !ship_index || !actions || P < 1 || S < P) { ofb_set_error("ofb_policy_write_actions: bad argument"); return OFB_E_ARG; }
     const long long n = n_arenas * P;
     if (n == 0) return OFB_OK;
-    k_write_actions<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(iact, xy, n, P, ship_index, S, eps, seed, arena0, step,
-                                                                                  reinterpret_cast<int2 *>(actions));
+    ofb_eps_schedule sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.kind = OFB_EPS_CONST; sc.start = (double)eps;
+    k_write_actions<false><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        const_cast<int *>(iact), const_cast<int *>(xy), n, P, ship_index, S, sc, 0.0, 0, seed, arena0, step, reinterpret_cast<int2 *>(actions), nullptr);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }
+
+extern "C" int ofb_policy_play_actions(int32_t *iact, int32_t *xy, int64_t n_arenas, int P, const int32_t *ship_index, int S,
+                                       const ofb_eps_schedule *sched, double t, int force_random, uint64_t seed, int64_t arena0,
+                                       uint32_t step, int16_t *actions, float *eps_out, void *stream) {
+    if (!iact || !xy || !ship_index || !actions || !sched || P < 1 || S < P || t < 0.0 || sched->kind < OFB_EPS_CONST ||
+        sched->kind > OFB_EPS_DECAY || (sched->kind == OFB_EPS_COSINE && !(sched->period > 0.0))) {
+        ofb_set_error("ofb_policy_play_actions: bad argument");
+        return OFB_E_ARG;
+    }
+    const long long n = n_arenas * P;
+    if (n == 0) return OFB_OK;
+    k_write_actions<true><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        iact, xy, n, P, ship_index, S, *sched, t, force_random, seed, arena0, step, reinterpret_cast<int2 *>(actions), eps_out);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+// host-side evaluation of the same closed form (tests / logging use it through ofb_eps_value)
+extern "C" float ofb_eps_value(const ofb_eps_schedule *sched, double t) { return sched ? eps_at(*sched, t) : 0.f; }
 
 template <class T>
 __global__ void k_pack_image(const T *__restrict__ img, long long n_words, uint32_t *__restrict__ maps) {

@@ -19,6 +19,7 @@
 // (scripts/trunk_episode.py): 0.88 ms late in an episode (8 lasers, 1 ship alive) to 2.5 ms at the laser peak (45 lasers),
 // episode mean 1.43 ms against 1.99 ms for the dense kernel (1.8 - 2.3 ms).  The floor is instruction count, not bytes: the
 // 40 KB map load, the 1 300 row-OR chunks, the 10 000 background stores and ~330 instructions per (dirty cell, channel).
+#include "ofb_common.cuh"
 #include "ofb_policy.cuh"
 #include "ofb_policy_dev.cuh"
 #include "ofb_tc_ptx.cuh"
@@ -176,11 +177,10 @@ k_sp_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
 
 int pol_sp_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
     if (n_items <= 0) return OFB_OK;
-    static thread_local bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_sp_trunk12, cudaFuncAttributeMaxDynamicSharedMemorySize, SpSmem::bytes);
+    static thread_local SmemAttrCache attr = {};
+    {
+        cudaError_t e = attr.ensure(k_sp_trunk12, (int)SpSmem::bytes);
         if (e != cudaSuccess) { ofb_set_error("pol_sp_trunk12: %s", cudaGetErrorString(e)); return OFB_E_CUDA; }
-        configured = true;
     }
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device);

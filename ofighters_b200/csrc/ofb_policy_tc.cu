@@ -181,11 +181,8 @@ k_tc_conv_pool(const TcArgs a) {
 int pol_tc_conv_pool(const ofb_policy *p, int layer, const __nv_bfloat16 *in, __nv_bfloat16 *out, int hin, int n_items,
                      long long out_item_stride, cudaStream_t st) {
     const TcPlan pl = tc_plan(hin);
-    static thread_local unsigned configured = 0;
-    if (pl.total > configured) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tc_conv_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.total));
-        configured = pl.total;
-    }
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_tc_conv_pool, (int)pl.total));
     if (n_items == 0) return OFB_OK;
     TcArgs a = {};
     a.in = in; a.wt = p->w.cw[layer]; a.bias = p->w.cb[layer]; a.out = out;

@@ -764,11 +764,10 @@ extern "C" int ofb_policy_tz_debug(long long *dev_buf) { g_tz_dbg = dev_buf; ret
 
 int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, float *amax_val, int *amax_idx, int n_items,
                cudaStream_t st) {
-    static thread_local int n_sm = 0;
-    if (!n_sm) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tz_up4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tz4Smem::total));
-        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
-    }
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_tz_up4, (int)Tz4Smem::total));
+    int n_sm = 148;
+    OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
     if (n_items == 0) return OFB_OK;
     Tz4Args a = {};
     a.in = in; a.wt = p->w.u4_tz; a.ring_w = p->w.u4_w; a.bias = p->u4_bias;
@@ -783,11 +782,10 @@ int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, flo
 int pol_tz_up4_parts() { return TZ4_STRIPS; }
 
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
-    static thread_local int n_sm = 0;
-    if (!n_sm) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tz_up3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tz3Smem::total));
-        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
-    }
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_tz_up3, (int)Tz3Smem::total));
+    int n_sm = 148;
+    OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
     if (n_items == 0) return OFB_OK;
     Tz3Args a = {};
     a.in = in; a.wt = p->w.u3_tz; a.bias = p->w.u3_pb; a.ring_w = p->w.u3_w; a.out = out;
@@ -1084,11 +1082,10 @@ k_tz_trunk12(const Tz2Args a, const int n_work) {
 }
 
 int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
-    static thread_local int n_sm = 0;
-    if (!n_sm) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tz_trunk12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Tz2Smem::total));
-        OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
-    }
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_tz_trunk12, (int)Tz2Smem::total));
+    int n_sm = 148;
+    OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
     if (n_items == 0) return OFB_OK;
     Tz2Args a = {};
     a.maps = maps; a.wt = p->w.c2_tz; a.bias = p->w.cb[0]; a.c1_lut = p->w.c1_lut; a.c1_b = p->w.c1_b; a.out = out;
@@ -1204,11 +1201,8 @@ k_tc_dense1(const __nv_bfloat16 *__restrict__ flat, const __nv_bfloat16 *__restr
 
 int pol_tc_dense1(const ofb_policy *p, const __nv_bfloat16 *flat, float *hflat, int n_items, cudaStream_t st) {
     const int smem = D1_NST * 2 * D1_OPBYTES + (2 * D1_NST + 1) * 8 + 16;
-    static thread_local bool configured = false;
-    if (!configured) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_tc_dense1, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_tc_dense1, smem));
     if (n_items == 0) return OFB_OK;
     k_tc_dense1<<<(n_items + 127) / 128, D1_NT, smem, st>>>(flat, p->w.d1_wt, hflat, n_items);
     OFB_CUDA_CHECK(cudaGetLastError());

@@ -102,11 +102,9 @@ extern "C" int ofb_raster(const ofb_arenas *h, void *out_dev, int format, void *
         return OFB_E_ARG;
     }
     const size_t smem = (size_t)(h->lay.W * h->lay.H / 32) * 2 * sizeof(uint32_t);
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
+    static thread_local SmemAttrCache attr = {};
+    if (smem > 48 * 1024) OFB_CUDA_CHECK(attr.ensure(k_raster, (int)smem));
     k_raster<<<(unsigned)h->n_arenas, 256, smem, (cudaStream_t)stream>>>(h->state, h->lay, out_dev, format, h->n_arenas);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;

@@ -628,17 +628,15 @@ static int launch_step_t(ofb_arenas *h, const int2 *act, float4 *obs, const BotS
     if (blocks == 0) return OFB_OK;
     const int tile = step_tile_bytes(h->lay, LPA, PIT);
     const int smem = STEP_BAR_BYTES + (STEP_THREADS / 32) * apw * tile;
-    static thread_local int configured = 0;
-    if (smem > configured) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_step<LPA, PIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_step<LPA, PIT, MINB>, smem));
     k_step<LPA, PIT, MINB><<<(unsigned)blocks, STEP_THREADS, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas, bots, tile);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }
 
 static int launch_step(ofb_arenas *h, const int16_t *actions_dev, float *obs_out_dev, const BotSpec &bots, void *stream) {
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));           // a thread may drive handles on several GPUs
     cudaStream_t st = (cudaStream_t)stream;
     const int lpa = lpa_for(h->lay.S, h->n_arenas);
     const int2 *act = reinterpret_cast<const int2 *>(actions_dev);
@@ -709,11 +707,8 @@ static int launch_frame_t(ofb_arenas *h, const int2 *act, float4 *obs, const Bot
     *fits = K >= unit && (map_bytes % 16) == 0;
     if (!*fits) return OFB_OK;
     const int smem = fixed + K * slot;
-    static thread_local int configured = 0;
-    if (smem > configured) {
-        OFB_CUDA_CHECK(cudaFuncSetAttribute(k_frame<LPA, PIT, SW, NG, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    static thread_local SmemAttrCache attr = {};
+    OFB_CUDA_CHECK(attr.ensure(k_frame<LPA, PIT, SW, NG, NBUF>, smem));
     const unsigned grid = (unsigned)(h->n_arenas < (int64_t)n_sm ? h->n_arenas : (int64_t)n_sm);
     k_frame<LPA, PIT, SW, NG, NBUF><<<grid, (SW + NG * FR_RASTER_WARPS) * 32, smem, st>>>(h->state, h->lay, act, obs, h->n_arenas,
                                                                                          bots, tile, slot, post_cap, K, maps, g_frame_prof,
@@ -731,6 +726,7 @@ static int launch_frame(ofb_arenas *h, const int16_t *actions_dev, float *obs_ou
     float4 *obs = reinterpret_cast<float4 *>(obs_out_dev);
     uint32_t *maps = reinterpret_cast<uint32_t *>(maps_dev);
     if (h->n_arenas == 0) return OFB_OK;
+    OFB_CUDA_CHECK(cudaSetDevice(h->device));
     {
         const char *tune = getenv("OFB_FRAME_TUNE");
         g_frame_tune = tune && *tune && *tune != '0';
@@ -829,10 +825,11 @@ static int step_host_async(ofb_arenas *h, const int16_t *actions_host, float *ob
                        : ofb_step(h, h->pipe_actions[i], obs_host ? h->pipe_obs[i] : nullptr, st);
     if (rc != OFB_OK) return rc;
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_step[i], st));
-    if (obs_host) {
-        OFB_CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_step[i], 0));
+    // ev_d2h[i] also stands for "actions_host of frame k has been consumed" (ofb_host_wait): it must follow the step -- and
+    // with it the H2D copy the step waited for -- even when no observation heads are copied back
+    OFB_CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_step[i], 0));
+    if (obs_host)
         OFB_CUDA_CHECK(cudaMemcpyAsync(obs_host, h->pipe_obs[i], n_ship * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
-    }
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
     h->host_seq++;
     return OFB_OK;

@@ -882,6 +882,7 @@ extern "C" int ofb_trainer_forward(ofb_trainer *t, const uint32_t *maps, const f
     int rc = check_batch(t, B, "ofb_trainer_forward");
     if (rc != OFB_OK) return rc;
     if (!maps || !vec) { ofb_set_error("ofb_trainer_forward: null input"); return OFB_E_ARG; }
+    TR_CHECK(cudaSetDevice(t->device));
     cudaStream_t st = (cudaStream_t)stream;
     rc = forward_train(t, maps, vec, B, 0, st);
     if (rc != OFB_OK) return rc;
@@ -895,6 +896,7 @@ extern "C" int ofb_trainer_fit(ofb_trainer *t, const uint32_t *maps, const float
     int rc = check_batch(t, B, "ofb_trainer_fit");
     if (rc != OFB_OK) return rc;
     if (!maps || !vec || !target_act || !target_ptr) { ofb_set_error("ofb_trainer_fit: null argument"); return OFB_E_ARG; }
+    TR_CHECK(cudaSetDevice(t->device));
     cudaStream_t st = (cudaStream_t)stream;
     const Table &T = t->tab;
     float *P = t->params, *G = t->grads;

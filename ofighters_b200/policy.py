@@ -192,17 +192,22 @@ class PolicyB200:
         return self.forward_argmax(maps_bits, vec)
 
     # ------------------------------------------------------------------ env glue
-    def act(self, bg, maps_bits, epsilon=0.0):
+    def act(self, bg, maps_bits, epsilon=0.0, collecting=False):
         """Drive the "QlearnIA"/"external" ships of ``bg`` for the coming frame: forward on the
         current maps + observation heads, then QlearnIA.play's action vector (:447-456) straight into
-        ``bg.actions``.  ``epsilon`` > 0 enables the eps-greedy random branch (:199-204)."""
-        iact, xy = self.decide(bg, maps_bits)
-        self.write(bg, iact, xy, epsilon)
+        ``bg.actions``.  ``epsilon``: a float or an ``EpsilonSchedule`` (evaluated on the device at its current step) for
+        the eps-greedy random branch (:199-204); ``collecting``: the random phase of :394-396 (no forward at all, like
+        the reference).  Returns the (iaction, xy) that are PLAYED (what QlearnIA.play remembers, :399-401)."""
+        if collecting:
+            n = bg.n_arenas * self._ship_idx(bg).numel()
+            iact = torch.zeros((n,), dtype=torch.int32, device=self.device)
+            xy = torch.zeros((n, 2), dtype=torch.int32, device=self.device)
+        else:
+            iact, xy = self.decide(bg, maps_bits)
+        self.write(bg, iact, xy, epsilon, collecting)
         return iact, xy
 
-    def decide(self, bg, maps_bits):
-        """First half of ``act``: queue the forward (asynchronous) -> (iaction [A*P], xy [A*P,2]) on the device.  A host-side
-        bot can compute the other ships' rows while it runs."""
+    def _ship_idx(self, bg):
         idx = getattr(bg, "_policy_ship_idx", None)
         if idx is None:
             ids = [i for i, b in enumerate(bg.behaviors) if b in ("QlearnIA", "external")]
@@ -210,16 +215,29 @@ class PolicyB200:
                 raise Exception("no policy-driven ship in this battleground")
             idx = bg._policy_ship_idx = torch.tensor(ids, dtype=torch.int32, device=bg.device)
             bg._policy_ship_idx_long = idx.long()
+        return idx
+
+    def decide(self, bg, maps_bits):
+        """First half of ``act``: queue the forward (asynchronous) -> (iaction [A*P], xy [A*P,2]) on the device.  A host-side
+        bot can compute the other ships' rows while it runs."""
+        idx = self._ship_idx(bg)
         P = idx.numel()
         vec = bg.obs_vec.index_select(1, bg._policy_ship_idx_long).reshape(-1, 8)
         return self.forward_argmax(maps_bits, vec, P)
 
-    def write(self, bg, iact, xy, epsilon=0.0):
-        """Second half of ``act``: the decoded actions become the policy ships' rows of ``bg.actions``."""
-        idx = bg._policy_ship_idx
-        _lib.check(self._lib.ofb_policy_write_actions(_ptr(iact), _ptr(xy), bg.n_arenas, idx.numel(), _ptr(idx), bg.ships_number,
-                                                      float(epsilon), bg.seed, bg.arena0, bg.total_steps, _ptr(bg.actions),
-                                                      self._stream()))
+    def write(self, bg, iact, xy, epsilon=0.0, collecting=False):
+        """Second half of ``act``: the decoded actions become the policy ships' rows of ``bg.actions``; where the eps-greedy
+        branch (or the collecting phase) replaced a prediction by ``random_play()``, ``iact`` / ``xy`` are overwritten with
+        the action that is played."""
+        idx = self._ship_idx(bg)
+        if hasattr(epsilon, "as_struct"):
+            sched, t = epsilon.as_struct(), float(epsilon.t)
+        else:
+            sched, t = _lib.OfbEpsSchedule(), 0.0
+            sched.kind, sched.start = _lib.EPS_CONST, float(epsilon)
+        _lib.check(self._lib.ofb_policy_play_actions(_ptr(iact), _ptr(xy), bg.n_arenas, idx.numel(), _ptr(idx), bg.ships_number,
+                                                     C.byref(sched), t, 1 if collecting else 0, bg.seed, bg.arena0,
+                                                     bg.total_steps, _ptr(bg.actions), None, self._stream()))
         self.launch_count += 1
 
     _TAP_STRIDE = {0: 320000, 1: 80000, 2: 20000, 3: 5120, 4: 100, 5: 80000, 6: 320000}

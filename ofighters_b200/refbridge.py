@@ -72,7 +72,9 @@ class ArenaView:
         obs = self.observations()
         for i, bot in bots.items():
             o = obs[i]
-            act = None if o.done else bot.play(o)
+            act = bot.play(o)                 # called for wreckage too: Ship.get_action (lib/ship.py:253-262) asks the agent
+            if o.done:                        # and only then discards the answer -- a learning bot sees its own death there
+                act = None
             row = action_row(act, (o.pointing.x, o.pointing.y))
             self.bg.actions[self.k, i].copy_(torch.from_numpy(row))
         return obs

@@ -9,78 +9,25 @@ schedules (lib/epsilon.py:18-86) -- SURVEY.md 8(f) rank 1.
     .get_best_action(obs, rand=True)                      .get_best_action(maps_bits, vec, rand=True)
     .decay_epsilon()                                      .decay_epsilon()
     model.fit(x, y, epochs=1, batch_size=B)               .fit(maps_bits, vec, target_act, target_ptr)
-    Epsilon_cos(period) / Epsilon_decay()                 Epsilon_cos / Epsilon_decay (same arithmetic)
+    Epsilon_cos(period) / Epsilon_decay()                 epsilon.EpsilonSchedule (closed form in t, evaluated on the device)
+    .save(id)  /  load_model(name)                        .save(id) -> .npz of Keras-layout arrays / TrainerB200.load(path)
 
 ``predict`` runs on the inference engine (PolicyB200: tcgen05 kernels, BN folded, moving statistics); ``fit`` runs
 libofb's training kernels (fp32, BatchNormalization on batch statistics, Keras' Adam) through include/ofb_train.h and
 then refreshes the inference engine's weights.  There is no torch / CPU fallback for either.
 """
 import ctypes as C
-import math
+import os
 import random
+import time
 from collections import deque
 from types import SimpleNamespace
 
 import torch
 
 from . import _lib
+from .epsilon import Epsilon_cos, Epsilon_decay, EpsilonSchedule  # noqa: F401  (re-exported: Trainer(epsilon=Epsilon_cos(...)))
 from .policy import WEIGHT_SPEC, PolicyB200, keras_default_weights
-
-
-def cos_P_u(time, period_time, amplitude):
-    """lib/epsilon.py:18-19"""
-    return amplitude * ((math.cos((time / period_time) * 2 * math.pi) + 1) / 2)
-
-
-def reverse_cos_P_u(value, period_time, amplitude):
-    """lib/epsilon.py:27-28"""
-    return period_time * math.acos(((2 * value) / amplitude) - 1) / (2 * math.pi)
-
-
-class Epsilon_cos:
-    """lib/epsilon.py:36-59"""
-
-    def __init__(self, period):
-        self.t = 0
-        self.amplitude = 1
-        self.period = period
-        self.epsilon = cos_P_u(self.t, self.period, self.amplitude)
-
-    def next(self):
-        self.t = (self.t + 1) % self.period
-        self.epsilon = cos_P_u(self.t, self.period, self.amplitude)
-        return self.epsilon
-
-    def get(self):
-        return self.epsilon
-
-    def set(self, value):
-        if value > 1.0 or value < 0.0:
-            raise Exception("Value must me in range [0,1]")
-        self.epsilon = value
-        self.t = reverse_cos_P_u(value, self.period, self.amplitude)
-
-
-class Epsilon_decay:
-    """lib/epsilon.py:62-86"""
-
-    def __init__(self):
-        self.epsilon = 1
-        self.epsilon_min = 0.01
-        self.decay = 0.99990
-
-    def next(self):
-        if self.epsilon > self.epsilon_min:
-            self.epsilon *= self.decay
-        return self.epsilon
-
-    def get(self):
-        return self.epsilon
-
-    def set(self, value):
-        if value > 1.0 or value < 0.0:
-            raise Exception("Value must me in range [0,1]")
-        self.epsilon = value
 
 
 def flatten_weights(weights):
@@ -177,6 +124,28 @@ class TrainerB200:
     def sync_model(self):
         """Hand the trained weights to the inference engine (BN folded from the moving statistics)."""
         self.model.load_weights(self.get_weights())
+
+    def save(self, id=None, overwrite=False, folder="networks"):
+        """``Trainer.save`` (:289-298): same naming -- ``keras-model[-<name> | -<timestamp>][-<id>]`` under ``folder`` -- but
+        the file is an ``.npz`` of the Keras-layout arrays of WEIGHT_SPEC (what ``PolicyB200.load_weights`` / ``load`` take);
+        Keras' HDF5 container is out of scope.  Returns the path."""
+        import numpy as np
+        name = "keras-model-" + (self.name if self.name else time.strftime("%Y-%m-%d_%H-%M-%S"))
+        if id:
+            name += "-" + str(id)
+        os.makedirs(folder, exist_ok=True)
+        path = os.path.join(folder, name + ".npz")
+        if os.path.exists(path) and not overwrite:
+            raise Exception("{} exists and overwrite is False.".format(path))
+        np.savez(path, **{k.replace("/", "."): v.numpy() for k, v in self.get_weights().items()})
+        return path
+
+    @staticmethod
+    def load_weights_file(path):
+        """Inverse of ``save``: the Keras-layout dict (``load_model`` of :70 for this format)."""
+        import numpy as np
+        with np.load(path) as f:
+            return {k.replace(".", "/"): torch.from_numpy(f[k]) for k in f.files}
 
     # ------------------------------------------------------------------ fit / predict
     def _check_batch(self, maps_bits, vec):
@@ -284,28 +253,60 @@ def len_flat():
 
 class QLearner:
     """Batched counterpart of ``QlearnIA.play``'s learning bookkeeping (agents/qlearnIA_V2.py:372-417) on top of one shared
-    ``TrainerB200`` ("All bots share the same trainer", :362): the policy ship of each of the first ``track`` arenas is a
-    QlearnIA bot -- every frame it remembers (previous_obs, previous_action, previous_pointer, obs.reward, obs, obs.done) until
-    it has seen its own death (:376-392), and bot id 1 (arena 0) replays every ``replay_every`` total steps (:403-405) and
-    once when it dies (:378-385).  Observations stay on the device: obs = (maps_bits [2,5000], head [8])."""
+    ``TrainerB200`` ("All bots share the same trainer", :362).  The policy ship of each of the first ``track`` arenas is a
+    QlearnIA bot with ids 1..track (bot id 1 = arena 0): every frame it remembers (previous_obs, previous_action,
+    previous_pointer, obs.reward, obs, obs.done) until it has seen its own death (:376-392); ANY bot replays when it dies
+    (:378-385); bot id 1 alone advances epsilon -- once per decision it takes, i.e. not after its death and not during the
+    collecting phase (:394-401) -- replays every ``replay_every`` total steps (:403-405) and snapshots the model every
+    ``snapshot`` episodes (:416-417).  During the first ``collecting_steps`` total steps every policy ship plays
+    ``random_play()`` (:394-396).  Observations stay on the device: obs = (maps_bits [2,5000], head [8]).
 
-    def __init__(self, trainer, track=8, replay_every=50):
+    ``actor``: the inference engine that drives the arenas (default: the trainer's own ``model``).  With a separate actor
+    (multi-GPU: every rank's actor is refreshed from the broadcast weights at common points) the trainer's own small
+    ``model`` keeps serving ``replay``'s predictions with the latest weights."""
+
+    def __init__(self, trainer, track=8, replay_every=50, collecting_steps=20, snapshot=50, actor=None, snapshot_folder="networks"):
         self.trainer = trainer
+        self.actor = actor if actor is not None else trainer.model
         self.track = int(track)
         self.replay_every = int(replay_every)
-        self.total_steps = 0
+        self.collecting_steps = int(collecting_steps)
+        self.snapshot = int(snapshot)
+        self.snapshot_folder = snapshot_folder
+        self.total_steps = 0          # Agent.total_steps of bot 1 (never reset, agents/agent.py:66-68)
+        self.steps = 0                # Agent.steps: frames since the last reset
+        self.episode = 0
         self.losses = []
         self.epsilons = []
-        self.reset()
+        self.saved = []
+        self.previous = [None] * self.track
+        self.done = [False] * self.track
+
+    @property
+    def collecting(self):
+        """True while the NEXT decision belongs to the random collecting phase (``total_steps < collecting_steps`` is
+        evaluated after Agent.step incremented the counter)."""
+        return self.total_steps + 1 < self.collecting_steps
 
     def reset(self):
-        """``QlearnIA.reset`` (:359-369): forget the previous action at an episode restart."""
+        """``QlearnIA.reset`` (:359-369) + ``Agent.reset`` (agents/agent.py:59-64): log epsilon, forget the previous action."""
+        self.episode += 1
+        self.steps = 0
         self.epsilons.append(self.trainer.epsilon.get())
         self.previous = [None] * self.track
         self.done = [False] * self.track
 
+    def act(self, bg, maps_bits):
+        """One frame of every QlearnIA ship: choose (collecting phase / eps-greedy with the trainer's schedule on the
+        device), write the action rows, then the bookkeeping of ``observe`` with the actions that are PLAYED.
+        -> (iaction, xy, replayed)"""
+        collecting = self.collecting
+        iact, xy = self.actor.act(bg, maps_bits, epsilon=self.trainer.epsilon, collecting=collecting)
+        return iact, xy, self.observe(bg, maps_bits, iact, xy)
+
     def observe(self, bg, maps_bits, iaction, xy, ship=None):
-        """Call once per frame right after the policy chose (iaction [A*P], xy [A*P,2]) on the current observation."""
+        """Call once per frame right after the policy ships' PLAYED actions (iaction [A*P], xy [A*P,2]) were written for
+        the current observation.  Returns True when the trainer's weights changed (a replay ran)."""
         if ship is None:
             ship = int(bg._policy_ship_idx[0]) if getattr(bg, "_policy_ship_idx", None) is not None else 0
         K = min(self.track, bg.n_arenas)
@@ -316,29 +317,34 @@ class QLearner:
         ia = iaction.reshape(bg.n_arenas, P)[:K, 0].tolist()
         pt = xy.reshape(bg.n_arenas, P, 2)[:K, 0].tolist()
         self.total_steps += 1
+        self.steps += 1
+        collecting = self.total_steps < self.collecting_steps
         replayed = False
         for k in range(K):
-            if self.done[k]:
+            if self.done[k]:                              # `if self.done: return None` (:375)
                 continue
             obs = (maps_bits[k].clone(), heads[k].clone())
             done = not alive[k]
-            if done:
-                if k == 0:
-                    self._replay()
-                    replayed = True
+            if done:                                      # every bot replays on its own death (:376-385)
+                replayed |= self._replay()
                 self.done[k] = True
             if self.previous[k] is not None:
                 po, pa, pp = self.previous[k]
                 self.trainer.remember(po, pa, pp, rewards[k], obs, done)
             self.previous[k] = (obs, int(ia[k]), (int(pt[k][0]), int(pt[k][1])))
-        self.trainer.decay_epsilon()
-        if self.total_steps % self.replay_every == 0 and len(self.trainer.memory) > 0:
-            self._replay()
-            replayed = True
+            if k == 0:                                    # "All bots share the same trainer so we only save it once"
+                if not collecting:
+                    self.trainer.decay_epsilon()          # (:398-401)
+                if self.total_steps % self.replay_every == 0:
+                    replayed |= self._replay()            # (:403-405)
+                if self.snapshot > 0 and self.episode > 0 and self.episode % self.snapshot == 0 and self.steps < 2:
+                    self.saved.append(self.trainer.save(id="iteration-%s" % self.episode, overwrite=True,
+                                                        folder=self.snapshot_folder))     # (:416-417)
         return replayed
 
     def _replay(self):
         if len(self.trainer.memory) == 0:
-            return
+            return False
         h = self.trainer.replay(self.trainer.batch_size)
         self.losses.append(h.history["loss"][0])
+        return True

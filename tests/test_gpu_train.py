@@ -148,45 +148,90 @@ def test_td_targets_kernel_is_exact_and_replay_runs():
 
 
 def test_qlearner_follows_qlearnia_bookkeeping():
-    """QlearnIA.play's remember / replay schedule on a batch: one transition per live tracked policy ship and frame, none
-    after the ship has seen its own death, a replay every 50 total steps (and at the death of bot 1), previous_* forgotten
-    at a restart, and the inference engine tracks the trained weights."""
+    """QlearnIA.play's bookkeeping on a batch (agents/qlearnIA_V2.py:372-417): one transition per live tracked policy ship
+    and frame, none after the ship has seen its own death; a replay at the death of ANY tracked bot and, while bot 1 is
+    still playing, every 50 total steps; epsilon advanced once per decision of bot 1 outside the 20-step collecting phase;
+    previous_* forgotten at a restart; a snapshot at the first frame of every `snapshot`-th episode; and the inference
+    engine tracks the trained weights."""
     import random
+    import tempfile
     from ofighters_b200 import BatchedBattleground
     from ofighters_b200.trainer import Epsilon_cos, QLearner, TrainerB200
     random.seed(1)
     bg = BatchedBattleground(32, ships={"QlearnIA": 1, "random": 6}, seed=21)
     maps = bg.raster("bits")
-    tr = TrainerB200(learning_rate=1e-4, epsilon=Epsilon_cos(period=110 * 400), batch_size=8, max_ships=32)
-    ql = QLearner(tr, track=4, replay_every=50)
+    tr = TrainerB200(learning_rate=1e-4, epsilon=Epsilon_cos(period=110 * 400), batch_size=8, max_ships=32, name="t")
+    folder = tempfile.mkdtemp()
+    ql = QLearner(tr, track=4, replay_every=50, collecting_steps=20, snapshot=1, snapshot_folder=folder)
     w0 = tr.get_weights()
-    expect, alive_prev = 0, [True] * 4
+    expect, alive_prev, had_prev = 0, [True] * 4, [False] * 4
+    exp_replays, exp_eps_t = 0, 0
     for t in range(120):
         if t == 100:
             bg.restart()
             bg.raster("bits", out=maps)
             ql.reset()
-            alive_prev = [True] * 4
-            had_prev = [False] * 4
-        iact, xy = tr.model.act(bg, maps)
+            alive_prev, had_prev = [True] * 4, [False] * 4
+        assert ql.collecting == (t + 1 < 20)
         alive = bg.state(("ship_alive",))["ship_alive"][:4, 0].tolist()
-        if t == 0:
-            had_prev = [False] * 4
+        mem_nonempty = len(tr.memory) > 0
         for k in range(4):
-            if alive_prev[k]:                            # the ship had not yet seen its death before this frame
+            if alive_prev[k]:                            # the bot had not yet seen its death before this frame
+                if not alive[k] and (mem_nonempty or expect > 0):
+                    exp_replays += 1                     # replay on its own death (before this frame's remember)
                 expect += 1 if had_prev[k] else 0
                 had_prev[k] = True
+                if k == 0:
+                    exp_eps_t += 0 if t + 1 < 20 else 1
+                    if (t + 1) % 50 == 0:
+                        exp_replays += 1
             alive_prev[k] = alive_prev[k] and bool(alive[k])
-        n_before = len(tr.memory)
-        ql.observe(bg, maps, iact, xy)
-        assert min(len(tr.memory), 400) == min(expect, 400), (t, len(tr.memory), expect, n_before)
+        iact, xy, _ = ql.act(bg, maps)
+        assert min(len(tr.memory), 400) == min(expect, 400), (t, len(tr.memory), expect)
+        # the remembered previous action is the row that was written (eps-greedy / collecting included)
+        row = bg.actions[0, 0].tolist()
+        if ql.previous[0] is not None and alive[0]:
+            _, pa, pp = ql.previous[0]
+            assert row == [1 if pa == 0 else 0, 1 if pa == 1 else 0, pp[0], pp[1]], (t, row, pa, pp)
         bg.frame()
         bg.raster("bits", out=maps)
-    assert ql.total_steps == 120 and tr.steps >= 2 and len(ql.losses) == tr.steps and all(np.isfinite(ql.losses))
+    assert ql.total_steps == 120 and tr.steps == exp_replays and len(ql.losses) == tr.steps and all(np.isfinite(ql.losses))
+    assert tr.steps >= 1
     w1 = tr.get_weights()
     assert not torch.equal(w0["upconv4/kernel"], w1["upconv4/kernel"])
     assert torch.equal(tr.model.weights["dense2/kernel"], w1["dense2/kernel"])      # inference engine refreshed after each fit
-    assert tr.epsilon.t == 120                           # decay_epsilon once per decision of bot 1 (:399-401)
+    assert tr.epsilon.t == exp_eps_t                     # decay_epsilon once per decision of bot 1 (:398-401)
+    assert len(ql.saved) == 1 and ql.epsilons and ql.episode == 1
+    back = TrainerB200.load_weights_file(ql.saved[0])
+    assert set(back) == set(w1) and all(back[k].shape == w1[k].shape for k in w1)
+
+
+def test_remembered_action_is_the_row_played():
+    """with epsilon = 1 every policy row is random_play(); the (iaction, pointer) handed back by act() -- what
+    QLearner remembers -- must be exactly what landed in bg.actions, and differ from the greedy prediction."""
+    from ofighters_b200 import BatchedBattleground
+    from ofighters_b200.policy import PolicyB200
+    from ofighters_b200.epsilon import EpsilonSchedule
+    bg = BatchedBattleground(256, ships={"QlearnIA": 1, "random": 6}, seed=5)
+    pol = PolicyB200.random_init(max_ships=256)
+    maps = bg.raster("bits")
+    gi, gxy = pol.decide(bg, maps)
+    gi, gxy = gi.clone(), gxy.clone()
+    for eps, collecting in ((EpsilonSchedule.constant(1.0), False), (1.0, False), (0.0, True)):
+        iact, xy = pol.act(bg, maps, epsilon=eps, collecting=collecting)
+        rows = bg.actions[:, 0, :].cpu().long()
+        ia, p = iact.cpu().long(), xy.cpu().long()
+        assert torch.equal(rows[:, 0], (ia == 0).long()) and torch.equal(rows[:, 1], (ia == 1).long())
+        assert torch.equal(rows[:, 2:], p)
+        assert int(p.min()) >= 0 and int(p.max()) <= 399 and set(ia.tolist()) == {0, 1}
+        assert not torch.equal(p, gxy.cpu().long())      # 256 uniform draws do not reproduce the prediction
+    iact, xy = pol.act(bg, maps, epsilon=0.0)            # greedy: untouched
+    assert torch.equal(iact, gi) and torch.equal(xy, gxy)
+    half = EpsilonSchedule.cosine(400)
+    half.set(0.5)
+    iact, xy = pol.act(bg, maps, epsilon=half)
+    changed = float(((xy != gxy).any(dim=1)).float().mean())
+    assert 0.3 < changed < 0.7, changed                  # about half the rows explore at eps(t) = 0.5
 
 
 def test_viewer_bridge_streams_one_arena():

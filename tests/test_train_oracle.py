@@ -101,19 +101,45 @@ def test_td_targets_follow_replay_including_its_transposed_pointer_index():
 
 
 def test_epsilon_schedules_follow_lib_epsilon():
-    from ofighters_b200.trainer import Epsilon_cos, Epsilon_decay, cos_P_u
+    """EpsilonSchedule's closed forms against the recurrences of lib/epsilon.py:36-86, stated here independently:
+    cosine  eps_k = (cos(2 pi (k mod P) / P) + 1) / 2;  decay  eps_{k+1} = eps_k * 0.9999 while eps_k > 0.01."""
+    import math
+    from ofighters_b200.trainer import Epsilon_cos, Epsilon_decay
     e = Epsilon_cos(period=200)
     assert e.get() == 1.0
     vals = [e.next() for _ in range(200)]
-    assert vals[49] == pytest.approx(cos_P_u(50, 200, 1)) and vals[99] == pytest.approx(0.0, abs=1e-12) and vals[199] == 1.0
+    for k in (1, 50, 99, 100, 150, 199):
+        assert vals[k - 1] == pytest.approx((math.cos(2 * math.pi * k / 200) + 1) / 2, abs=1e-12)
+    assert vals[99] == pytest.approx(0.0, abs=1e-12) and vals[199] == 1.0 and e.t == 0      # t wraps at the period
+    e.set(0.5)
+    assert e.t == pytest.approx(50.0) and e.get() == pytest.approx(0.5)                     # reverse_cos_P_u
     d = Epsilon_decay()
+    ref = 1.0
+    for k in range(1, 60000):
+        if ref > 0.01:
+            ref *= 0.9999
+        if k in (1, 3, 1000, 46049, 46052, 59999):
+            assert d.value_at(k) == pytest.approx(ref, rel=1e-9), k
     for _ in range(3):
         d.next()
     assert d.get() == pytest.approx(0.9999 ** 3)
     d.set(0.005)
     assert d.next() == 0.005                                            # below the soft minimum: left alone
-    with pytest.raises(Exception, match="range"):
+    with pytest.raises(Exception, match=r"\[0, 1\]"):
         d.set(1.5)
+
+
+def test_epsilon_device_formula_matches_python():
+    """ofb_eps_value runs the SAME eps_at() the action kernel evaluates on the device (ofb_policy.cu)."""
+    import ctypes as C
+    from ofighters_b200 import _lib
+    from ofighters_b200.epsilon import EpsilonSchedule
+    lib = _lib.load()
+    for sch in (EpsilonSchedule.cosine(110 * 400), EpsilonSchedule.cosine(200, 0.8), EpsilonSchedule.decaying(),
+                EpsilonSchedule.decaying(0.5, 0.999, 0.05), EpsilonSchedule.constant(0.25)):
+        st = sch.as_struct()
+        for t in (0, 1, 17, 199, 200, 4400, 21999.5, 46051, 46052, 10 ** 6):
+            assert float(lib.ofb_eps_value(C.byref(st), float(t))) == pytest.approx(sch.value_at(t), abs=2e-7), (sch.kind, t)
 
 
 def test_trainer_has_no_cpu_fallback():
