@@ -398,6 +398,7 @@ def gpu_arm(args, name, wl):
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     coll_timed = dict(coll)
+    time_at_end = bg.time
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(step_ms)
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -430,8 +431,8 @@ def gpu_arm(args, name, wl):
     extra = {"ship_steps_per_s": value * S,
              "l2": (flush_buf.describe() if flush_needed else "working set %.0f MB > L2" % ((state_bytes + maps.numel() * 4) / 1e6)),
              "wall_s_timed_region": wall, "ms_per_step_by_rank": per_rank_ms,
-             "frames_timed": "episode frames %d..%d, restart, frames 0..%d" % (time_at_start, max_time - 1, bg.time - 1)
-                             if coll_timed["restarts"] else "episode frames %d..%d" % (time_at_start, bg.time - 1),
+             "frames_timed": "episode frames %d..%d, restart, frames 0..%d" % (time_at_start, max_time - 1, time_at_end - 1)
+                             if coll_timed["restarts"] else "episode frames %d..%d" % (time_at_start, time_at_end - 1),
              "ms_per_step_min_median_max": [min(step_ms), sorted(step_ms)[len(step_ms) // 2], max(step_ms)],
              "preroll_frames": preroll, "live_lasers_at_end": live_lasers, "episode_stats_reduced": episode_stats}
     if learn:
