@@ -16,7 +16,7 @@
  * the 5000-wide flat slice of dense1 and upconv3-4 run as bf16 x bf16 -> fp32 tensor-core
  * contractions (tcgen05) with bf16 activations between layers; conv1 (binary input), the 8-value
  * vector slice of dense1, dense2, output1, updense1, upconv1 and upconv2 stay in fp32.  Bilinear x2 upsampling uses TF2 half-pixel
- * centres with edge clamp.
+ * centres with edge clamp by default (ofb_policy_create_opts offers the TF1.x legacy kernel).
  */
 #ifndef OFB_POLICY_H
 #define OFB_POLICY_H
@@ -56,11 +56,21 @@ enum { OFB_ENGINE_TENSOR = 0,      /* tcgen05 kernels (product path) */
 /* max_ships = largest n_arenas * ships_per_arena a forward call may carry per chunk (the library
  * loops over chunks of that size); workspace = about 1 MB per ship.  0 = default (1024). */
 int ofb_policy_create(const ofb_policy_weights *w_host, int device, int max_ships, ofb_policy **out);
+/* The same with options (flags, OR-ed):
+ *   OFB_POLICY_BILINEAR_TF1   UpSampling2D(interpolation='bilinear') (agents/qlearnIA_V2.py:166,171,177,183) with the TF1.x /
+ *                             standalone-Keras legacy kernel (out[2i] = in[i], out[2i+1] = (in[i] + in[i+1]) / 2) instead of TF2's
+ *                             half-pixel centres: the reference pins no Keras / TensorFlow version, so both are offered
+ *   OFB_POLICY_UNFUSED_TAIL   upconv3 and upconv4 as two kernels through HBM (measurement aid; default = one fused kernel)
+ *   OFB_POLICY_DENSE_TRUNK    conv1 + conv2 on the dense tcgen05 kernel instead of the sparse one                              */
+enum { OFB_POLICY_BILINEAR_TF1 = 1, OFB_POLICY_UNFUSED_TAIL = 2, OFB_POLICY_DENSE_TRUNK = 4 };
+int ofb_policy_create_opts(const ofb_policy_weights *w_host, int device, int max_ships, int flags, ofb_policy **out);
 int ofb_policy_destroy(ofb_policy *p);
 /* load new weights into an existing handle (Trainer.fit refreshed them; load_model, agents/qlearnIA_V2.py:70): folds like
  * ofb_policy_create and overwrites the resident copy after `stream` has drained; the workspace is kept. */
 int ofb_policy_set_weights(ofb_policy *p, const ofb_policy_weights *w_host, void *stream);
 int ofb_policy_set_engine(ofb_policy *p, int engine);
+/* validation taps: when enabled the fused tail kernel also writes upconv3's output for ofb_policy_debug_tap(6) */
+int ofb_policy_set_taps(ofb_policy *p, int enable);
 
 /* model.predict + decode for n_arenas arenas with ships_per_arena policy-driven ships each.
  *   maps_bits_dev  uint32 [A, 2, 5000]   bit y*400+x, ch0 ship_map, ch1 laser_map (ofb_raster OFB_MAP_BITS)
@@ -114,7 +124,7 @@ int ofb_policy_pack_image(const void *img_dev, int fmt, int64_t n, uint32_t *map
 
 /* Per-layer device times (measurement aid): enable = 1 brackets every kernel of the following forward
  * calls with CUDA events; enable = 0 stops, synchronises and writes the accumulated milliseconds per
- * layer to ms_out[8] = (trunk12, conv3, conv4, dense1, heads, up3, up4, argmax). */
+ * layer to ms_out[9] = (trunk12, conv3, conv4, dense1, heads, up3, up4, argmax, tail = fused up3 + up4 + argmax). */
 int ofb_policy_profile(ofb_policy *p, int enable, float *ms_out);
 
 /* Debug / validation tap: copies the first n_items entries of an intermediate activation of the

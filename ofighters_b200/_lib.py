@@ -56,6 +56,7 @@ class OfbEpsSchedule(C.Structure):
 
 EPS_CONST, EPS_COSINE, EPS_DECAY = 0, 1, 2
 ENGINE_TENSOR, ENGINE_CUDA_CORE = 0, 1
+POLICY_BILINEAR_TF1, POLICY_UNFUSED_TAIL, POLICY_DENSE_TRUNK = 1, 2, 4
 
 
 class OfbError(RuntimeError):
@@ -113,6 +114,10 @@ def load():
     lib.ofb_state_export.argtypes = [vp, C.POINTER(OfbStateView), vp]
     lib.ofb_state_import.argtypes = [vp, C.POINTER(OfbStateView), vp]
     lib.ofb_policy_create.argtypes = [C.POINTER(OfbPolicyWeights), i32, i32, C.POINTER(vp)]
+    lib.ofb_policy_create_opts.argtypes = [C.POINTER(OfbPolicyWeights), i32, i32, i32, C.POINTER(vp)]
+    lib.ofb_policy_create_opts.restype = i32
+    lib.ofb_policy_set_taps.argtypes = [vp, i32]
+    lib.ofb_policy_set_taps.restype = i32
     lib.ofb_policy_destroy.argtypes = [vp]
     lib.ofb_policy_set_weights.argtypes = [vp, C.POINTER(OfbPolicyWeights), vp]
     lib.ofb_policy_set_weights.restype = i32

@@ -26,6 +26,7 @@ UNITS = [
     ("ofb_policy.cu", []),
     ("ofb_policy_tc.cu", []),
     ("ofb_policy_tz.cu", []),
+    ("ofb_policy_tail.cu", []),
     ("ofb_policy_sp.cu", []),
     ("ofb_train.cu", []),
 ]

@@ -7,9 +7,10 @@
 #include <vector>
 #include "ofb_common.cuh"
 #include "ofb_policy_dev.cuh"
+#include "ofb_policy_tail.cuh"
 
 struct ProfEvent { cudaEvent_t a, b; int layer; };
-enum { L_TRUNK12 = 0, L_CONV3, L_CONV4, L_DENSE1, L_HEADS, L_UP3, L_UP4, L_ARGMAX, L_COUNT };
+enum { L_TRUNK12 = 0, L_CONV3, L_CONV4, L_DENSE1, L_HEADS, L_UP3, L_UP4, L_ARGMAX, L_TAIL, L_COUNT };
 
 // ------------------------------------------------------------------------------------------------
 // host-side folding (BN into conv, bilinear x2 into 4 output phases) and upload
@@ -38,13 +39,40 @@ static std::vector<__nv_bfloat16> pack_taps(const std::vector<float> &w, int cin
     return o;
 }
 
-// coefficient of L[i+u-1] in U[2i + a + d - 1]  (TF2 half-pixel bilinear x2), a = phase, d = conv tap
-static const float PHASE_C[2][3][3] = {
-    {{0.75f, 0.25f, 0.f}, {0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}},
-    {{0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}, {0.f, 0.25f, 0.75f}}};
+// c[a][d][u] = coefficient of L[i+u-1] in U[2i + a + d - 1] for a bilinear x2 upsampling U of L: a = output phase, d = conv
+// tap, on a replicate-extended L.  TF2 / Keras >= 2.2.? half-pixel centres: U[2i] = .25 L[i-1] + .75 L[i], U[2i+1] = .75 L[i] +
+// .25 L[i+1];  TF1.x legacy (asymmetric, align_corners=False): U[2i] = L[i], U[2i+1] = .5 (L[i] + L[i+1]).
+struct PhaseTab { float c[2][3][3]; };
+static PhaseTab phase_tab(int legacy) {
+    static const PhaseTab tf2 = {{{{0.75f, 0.25f, 0.f}, {0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}},
+                                  {{0.25f, 0.75f, 0.f}, {0.f, 0.75f, 0.25f}, {0.f, 0.25f, 0.75f}}}};
+    static const PhaseTab tf1 = {{{{0.5f, 0.5f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.5f, 0.5f}},
+                                  {{0.f, 1.f, 0.f}, {0.f, 0.5f, 0.5f}, {0.f, 0.f, 1.f}}}};
+    return legacy ? tf1 : tf2;
+}
+// The same for the FIRST row / column of the image (phase 0): tap 0 reads the convolution's zero padding, and the edge
+// clamp of the upsampling folds L[-1] onto L[0].
+static PhaseTab low_border(PhaseTab t) {
+    for (int d = 0; d < 3; d++) {
+        if (d == 0) { t.c[0][0][0] = t.c[0][0][1] = t.c[0][0][2] = 0.f; continue; }
+        t.c[0][d][1] += t.c[0][d][0];
+        t.c[0][d][0] = 0.f;
+    }
+    return t;
+}
+// ... and for the LAST row / column (phase 1): tap 2 reads the padding, L[n] folds onto L[n-1].
+static PhaseTab high_border(PhaseTab t) {
+    for (int d = 0; d < 3; d++) {
+        if (d == 2) { t.c[1][2][0] = t.c[1][2][1] = t.c[1][2][2] = 0.f; continue; }
+        t.c[1][d][1] += t.c[1][d][2];
+        t.c[1][d][2] = 0.f;
+    }
+    return t;
+}
 
-// [9][cin][cout] -> bilinear-x2 phase-folded fp32 [9 (u, v)][cin][4 * cout], column = (a*2+b)*cout + co
-static std::vector<float> fold_phase(const std::vector<float> &w, int cin, int cout) {
+// [9][cin][cout] -> bilinear-x2 phase-folded fp32 [9 (u, v)][cin][4 * cout], column = (a*2+b)*cout + co; ty / tx = the
+// coefficient tables of the vertical / horizontal direction
+static std::vector<float> fold_phase(const std::vector<float> &w, int cin, int cout, const PhaseTab &ty, const PhaseTab &tx) {
     std::vector<float> o((size_t)9 * cin * 4 * cout, 0.f);
     for (int a = 0; a < 2; a++)
         for (int b = 0; b < 2; b++)
@@ -55,7 +83,7 @@ static std::vector<float> fold_phase(const std::vector<float> &w, int cin, int c
                             double s = 0.0;
                             for (int dy = 0; dy < 3; dy++)
                                 for (int dx = 0; dx < 3; dx++)
-                                    s += (double)w[((size_t)(dy * 3 + dx) * cin + ci) * cout + co] * PHASE_C[a][dy][u] * PHASE_C[b][dx][v];
+                                    s += (double)w[((size_t)(dy * 3 + dx) * cin + ci) * cout + co] * ty.c[a][dy][u] * tx.c[b][dx][v];
                             o[((size_t)(u * 3 + v) * cin + ci) * 4 * cout + (a * 2 + b) * cout + co] = (float)s;
                         }
     return o;
@@ -86,6 +114,106 @@ static std::vector<__nv_bfloat16> pack_toeplitz(const std::vector<float> &pf, in
     return o;
 }
 
+// Operands of the fused tail kernel (layouts: ofb_policy_tail.cuh / .cu).  w3 = upconv3 [9][4][8] and w4 = upconv4 [9][8][1],
+// BN folded; b3 = upconv3's bias.
+static std::vector<uint8_t> pack_tail(const std::vector<float> &w3, const std::vector<float> &b3, const std::vector<float> &w4,
+                                      int legacy) {
+    std::vector<uint8_t> blob(TL_WBYTES, 0);
+    auto put = [&](size_t byte_off, float v) { *reinterpret_cast<__nv_bfloat16 *>(blob.data() + byte_off) = __float2bfloat16(v); };
+    const PhaseTab T = phase_tab(legacy), TLo = low_border(T), THi = high_border(T);
+    // ---- upconv3: K lanes of chunk cc < 3 = pixel offsets p = 2 cc + (l >> 2) (input x = 4 xb + p - 1), channel l & 3; chunk 3 =
+    //      spare lanes: l < 4 -> L[i][0] (M rows xb = 0), l >= 4 -> L[i][99] (xb = 24), weights = minus the out-of-range taps
+    auto pack3 = [&](size_t base, const PhaseTab &ty, int u, int ks, int n_cols, bool only_a, int a_sel) {
+        const std::vector<float> pf = fold_phase(w3, 4, 8, ty, T);
+        for (int c = 0; c < 2; c++) {
+            const int cc = 2 * ks + c;
+            for (int n = 0; n < n_cols; n++) {
+                int xo, a, b, co;
+                if (only_a) { xo = n >> 4; a = a_sel; b = (n >> 3) & 1; co = n & 7; }
+                else { xo = n >> 5; a = (n >> 4) & 1; b = (n >> 3) & 1; co = n & 7; }
+                for (int l = 0; l < 8; l++) {
+                    float val = 0.f;
+                    const int ci = l & 3;
+                    if (cc < 3) {
+                        const int v = 2 * cc + (l >> 2) - xo;
+                        if (v >= 0 && v <= 2) val = pf[((size_t)(u * 3 + v) * 4 + ci) * 32 + (a * 2 + b) * 8 + co];
+                    } else if ((l < 4 && xo == 0 && b == 0) || (l >= 4 && xo == 3 && b == 1)) {
+                        const int dx = l < 4 ? 0 : 2;
+                        double sacc = 0.0;
+                        for (int dy = 0; dy < 3; dy++) sacc += (double)w3[((size_t)(dy * 3 + dx) * 4 + ci) * 8 + co] * ty.c[a][dy][u];
+                        val = (float)-sacc;
+                    }
+                    put(base + ((size_t)c * n_cols + n) * 16 + l * 2, val);
+                }
+            }
+        }
+    };
+    for (int u = 0; u < 3; u++)
+        for (int ks = 0; ks < 2; ks++) pack3(TL_OFF_B3 + (size_t)(u * 2 + ks) * 2 * 128 * 16, T, u, ks, 128, false, 0);
+    for (int set = 0; set < 2; set++)                       // top: phase a = 0 of row 0, taps u = 1, 2; bottom: a = 1 of row 99, u = 0, 1
+        for (int ui = 0; ui < 2; ui++)
+            for (int ks = 0; ks < 2; ks++)
+                pack3(TL_OFF_B3V + (size_t)(((set * 2 + ui) * 2) + ks) * 2 * 64 * 16, set == 0 ? TLo : THi, set == 0 ? ui + 1 : ui, ks, 64,
+                      true, set);
+    // ---- upconv4 (2-row form): output row r of the pair uses tap u = dy - r; pixel offset p of (ks, chunk): input X = 8 xb + p - 1
+    const std::vector<float> pf4 = fold_phase(w4, 8, 1, T, T), pfL = fold_phase(w4, 8, 1, T, TLo), pfR = fold_phase(w4, 8, 1, T, THi);
+    const std::vector<float> pfT = fold_phase(w4, 8, 1, TLo, T), pfB = fold_phase(w4, 8, 1, THi, T);
+    auto pix_of = [](int ks, int c) { return ks == 0 ? (c == 0 ? 1 : 0) : (ks == 4 ? (c == 0 ? 9 : 8) : 2 * ks + c); };
+    const size_t b4off[4] = {0, 480, 1280, 2080};
+    for (int dy = 0; dy < 4; dy++) {
+        const int nn = (dy == 0 || dy == 3) ? 48 : 80, n0 = dy == 3 ? 32 : 0;
+        for (int ks = 0; ks < 5; ks++)
+            for (int c = 0; c < 2; c++) {
+                const int p = pix_of(ks, c);
+                for (int j = 0; j < nn; j++) {
+                    const int n = n0 + j;
+                    for (int ci = 0; ci < 8; ci++) {
+                        float val = 0.f;
+                        int r = -1, cph = 0, xo = 0, d = 0;
+                        const std::vector<float> *src = &pf4;
+                        if (n < 4) { r = 0; cph = n >> 1; if (n & 1) { xo = 7; d = 1; src = &pfR; } else { xo = 0; d = 0; src = &pfL; } }
+                        else if (n >= 8 && n < 72) { r = (n - 8) >> 5; const int rem = (n - 8) & 31; xo = rem >> 2; cph = (rem >> 1) & 1; d = rem & 1; }
+                        else if (n >= 72 && n < 76) { r = 1; cph = (n - 72) >> 1; if (n & 1) { xo = 7; d = 1; src = &pfR; } else { xo = 0; d = 0; src = &pfL; } }
+                        if (r >= 0) {
+                            const int u = dy - r, v = p - xo;
+                            if (u >= 0 && u <= 2 && v >= 0 && v <= 2) val = (*src)[((size_t)(u * 3 + v) * 8 + ci) * 4 + cph * 2 + d];
+                        }
+                        put(TL_OFF_B4 + (b4off[dy] + (size_t)(ks * 2 + c) * nn + j) * 16 + ci * 2, val);
+                    }
+                }
+            }
+    }
+    for (int set = 0; set < 2; set++)                       // V = 0: row r = 0, phase c = 0, taps u = dy = 1, 2; V = 399: r = 1, c = 1, u = dy - 1 = 0, 1
+        for (int dyi = 0; dyi < 2; dyi++)
+            for (int ks = 0; ks < 5; ks++)
+                for (int c = 0; c < 2; c++) {
+                    const int p = pix_of(ks, c), u = set == 0 ? dyi + 1 : dyi;
+                    const std::vector<float> &src = set == 0 ? pfT : pfB;
+                    for (int n = 0; n < 16; n++)
+                        for (int ci = 0; ci < 8; ci++) {
+                            const int xo = n >> 1, d = n & 1, v = p - xo;
+                            const float val = (v >= 0 && v <= 2) ? src[((size_t)(u * 3 + v) * 8 + ci) * 4 + set * 2 + d] : 0.f;
+                            put(TL_OFF_B4V + ((size_t)((((set * 2 + dyi) * 5) + ks) * 2 + c) * 16 + n) * 16 + ci * 2, val);
+                        }
+                }
+    // ---- floats: upconv3's bias, then the 4 corner pixels' weights [corner][uu][vv][ci] (bf16-rounded like the operands):
+    //      the corner reads upconv3 pixels (Y0 + uu, X0 + vv), (Y0, X0) = (0 | 198, 0 | 198)
+    float *aux = reinterpret_cast<float *>(blob.data() + TL_OFF_AUX);
+    for (int c = 0; c < 8; c++) aux[c] = b3[c];
+    for (int cid = 0; cid < 4; cid++) {
+        const bool bottom = cid >= 2, right = cid & 1;
+        const std::vector<float> pfc = fold_phase(w4, 8, 1, bottom ? THi : TLo, right ? THi : TLo);
+        for (int uu = 0; uu < 2; uu++)
+            for (int vv = 0; vv < 2; vv++)
+                for (int ci = 0; ci < 8; ci++) {
+                    const int u = bottom ? uu : uu + 1, v = right ? vv : vv + 1;
+                    const float val = pfc[((size_t)(u * 3 + v) * 8 + ci) * 4 + (bottom ? 2 : 0) + (right ? 1 : 0)];
+                    aux[8 + ((cid * 2 + uu) * 2 + vv) * 8 + ci] = __bfloat162float(__float2bfloat16(val));
+                }
+    }
+    return blob;
+}
+
 struct Uploader {
     std::vector<char> host;
     std::vector<std::pair<void **, size_t>> fix;
@@ -100,8 +228,9 @@ struct Uploader {
 
 // Folds the Keras weights (BN into the convs, bilinear x2 into output phases, operand packs of the tensor-core kernels) into
 // the upload blob.  The blob's layout depends only on the architecture, so ofb_policy_set_weights can rebuild it in place.
-static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, PolicyDev &d, float &u4_bias) {
+static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, PolicyDev &d, float &u4_bias, int legacy) {
     std::vector<float> w, b;
+    const PhaseTab PT = phase_tab(legacy);
     // trunk
     fold_conv(wh->conv[0], 2, 8, w, b);
     up.add(&d.c1_w, w); up.add(&d.c1_b, b);
@@ -167,26 +296,35 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
     up.add(&d.d2_w, wh->dense2.kernel, 100 * 50); up.add(&d.d2_b, wh->dense2.bias, 50);
     up.add(&d.o1_w, wh->output1.kernel, 50 * 2); up.add(&d.o1_b, wh->output1.bias, 2);
     up.add(&d.ud_w, wh->updense1.kernel, 100 * 625); up.add(&d.ud_b, wh->updense1.bias, 625);
-    fold_conv(wh->upconv[0], 1, 2, w, b); up.add(&d.u1_w, w); up.add(&d.u1_b, b); up.add(&d.u1_pw, fold_phase(w, 1, 2));
-    fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b); up.add(&d.u2_pw, fold_phase(w, 2, 4));
+    fold_conv(wh->upconv[0], 1, 2, w, b); up.add(&d.u1_w, w); up.add(&d.u1_b, b); up.add(&d.u1_pw, fold_phase(w, 1, 2, PT, PT));
+    fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b); up.add(&d.u2_pw, fold_phase(w, 2, 4, PT, PT));
     fold_conv(wh->upconv[2], 4, 8, w, b);
+    const std::vector<float> w3 = w, b3 = b;
     up.add(&d.u3_w, w); up.add(&d.u3_b, b);
-    { const std::vector<float> pf = fold_phase(w, 4, 8);
+    { const std::vector<float> pf = fold_phase(w, 4, 8, PT, PT);
       up.add(&d.u3_pw, pack_taps(pf, 4, 32, 32));
       up.add(&d.u3_tz, pack_toeplitz(pf, 4, 32, 4)); }
     { std::vector<float> pb(32); for (int n = 0; n < 32; n++) pb[n] = b[n % 8]; up.add(&d.u3_pb, pb); }
     fold_conv(wh->upconv[3], 8, 1, w, b);
     up.add(&d.u4_w, w); up.add(&d.u4_b, b);
-    { const std::vector<float> pf = fold_phase(w, 8, 1);
+    { const std::vector<float> pf = fold_phase(w, 8, 1, PT, PT);
       up.add(&d.u4_pw, pack_taps(pf, 8, 4, 16));
       up.add(&d.u4_tz, pack_toeplitz(pf, 8, 4, 8)); }
+    up.add(&d.tail_blob, pack_tail(w3, b3, w, legacy));
     u4_bias = b[0];
     { std::vector<float> pb(16, 0.f); for (int n = 0; n < 4; n++) pb[n] = b[0]; up.add(&d.u4_pb, pb); }
 
 }
 
 extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int max_ships, ofb_policy **out) {
-    if (!wh || !out) { ofb_set_error("ofb_policy_create: null argument"); return OFB_E_ARG; }
+    return ofb_policy_create_opts(wh, device, max_ships, 0, out);
+}
+
+extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, int max_ships, int flags, ofb_policy **out) {
+    if (!wh || !out || (flags & ~(OFB_POLICY_BILINEAR_TF1 | OFB_POLICY_UNFUSED_TAIL | OFB_POLICY_DENSE_TRUNK))) {
+        ofb_set_error("ofb_policy_create: bad argument");
+        return OFB_E_ARG;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
@@ -204,12 +342,15 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     // trunk12: the sparse CUDA-core kernel (ofb_policy_sp.cu) is the default -- 26 % faster than the dense tcgen05 one over a
     // 200-frame episode of the default arena, 12 % slower at the laser peak around frame 30 (profiles/r01_step_tuning.md);
     // OFB_POLICY_DENSE_TRUNK=1 selects the dense kernel when the handle is created
-    { const char *e = getenv("OFB_POLICY_DENSE_TRUNK"); p->dense_trunk = (e && *e && *e != '0') ? 1 : 0; }
+    { const char *e = getenv("OFB_POLICY_DENSE_TRUNK"); p->dense_trunk = ((e && *e && *e != '0') || (flags & OFB_POLICY_DENSE_TRUNK)) ? 1 : 0; }
+    // the tail: fused upconv3 -> upconv4 -> argmax by default; the two-kernel form is kept for A / B measurements
+    { const char *e = getenv("OFB_POLICY_UNFUSED_TAIL"); p->unfused_tail = ((e && *e && *e != '0') || (flags & OFB_POLICY_UNFUSED_TAIL)) ? 1 : 0; }
+    p->bilinear_legacy = (flags & OFB_POLICY_BILINEAR_TF1) ? 1 : 0;
     p->prof = new std::vector<ProfEvent>();
 
     Uploader up;
     PolicyDev &d = p->w;
-    build_weight_blob(wh, up, d, p->u4_bias);
+    build_weight_blob(wh, up, d, p->u4_bias, p->bilinear_legacy);
     p->arena_bytes = up.host.size();
 
     cudaError_t e = cudaMalloc(&p->arena_blob, up.host.size());
@@ -219,6 +360,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
         cudaFree(p->arena_blob); delete p; return OFB_E_CUDA;
     }
     for (auto &f : up.fix) *f.first = static_cast<char *>(p->arena_blob) + f.second;
+    d.bil_legacy = p->bilinear_legacy;
 
     // workspace
     const size_t C = (size_t)max_ships;
@@ -235,7 +377,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
     }
     char *wb = static_cast<char *>(p->work_blob);
     cudaMemset(wb + o_fl, 0, C * POL_FLAT_PITCH * 2);            // K padding of dense1 must read as zero
-    cudaMemset(wb + o_u2, 0, C * POL_UP2_ITEM * 2);              // channels 4..7 of up2 stay zero
+    cudaMemset(wb + o_u2, 0, C * POL_UP2_ITEM * 2);              // channels 4..7 of up2 (plane layout) / the never-written entries of the pairs layout stay zero
     p->ws.pool1 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p1);
     p->ws.pool2 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p2);
     p->ws.pool3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p3);
@@ -271,7 +413,7 @@ extern "C" int ofb_policy_set_weights(ofb_policy *p, const ofb_policy_weights *w
     Uploader up;
     PolicyDev scratch;
     float u4_bias = 0.f;
-    build_weight_blob(wh, up, scratch, u4_bias);
+    build_weight_blob(wh, up, scratch, u4_bias, p->bilinear_legacy);
     if (up.host.size() != p->arena_bytes) { ofb_set_error("ofb_policy_set_weights: blob size mismatch"); return OFB_E_STATE; }
     OFB_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
     OFB_CUDA_CHECK(cudaMemcpy(p->arena_blob, up.host.data(), up.host.size(), cudaMemcpyHostToDevice));
@@ -280,8 +422,8 @@ extern "C" int ofb_policy_set_weights(ofb_policy *p, const ofb_policy_weights *w
 }
 
 // Per-layer device times: enable = 1 starts collecting (CUDA events around every kernel of forward);
-// enable = 0 stops, synchronises and returns the accumulated milliseconds per layer in ms_out[8]
-// (trunk12, conv3, conv4, dense1, heads, up3, up4, argmax) together with the number of forward calls' chunks.
+// enable = 0 stops, synchronises and returns the accumulated milliseconds per layer in ms_out[9]
+// (trunk12, conv3, conv4, dense1, heads, up3, up4, argmax, tail = the fused up3 + up4 + argmax kernel).
 extern "C" int ofb_policy_profile(ofb_policy *p, int enable, float *ms_out) {
     if (!p) { ofb_set_error("ofb_policy_profile: null handle"); return OFB_E_ARG; }
     auto *v = static_cast<std::vector<ProfEvent> *>(p->prof);
@@ -297,6 +439,12 @@ extern "C" int ofb_policy_profile(ofb_policy *p, int enable, float *ms_out) {
     }
     v->clear();
     if (ms_out) for (int i = 0; i < L_COUNT; i++) ms_out[i] = acc[i];
+    return OFB_OK;
+}
+
+extern "C" int ofb_policy_set_taps(ofb_policy *p, int enable) {
+    if (!p) { ofb_set_error("ofb_policy_set_taps: null handle"); return OFB_E_ARG; }
+    p->taps = enable ? 1 : 0;
     return OFB_OK;
 }
 
@@ -444,15 +592,16 @@ __device__ __forceinline__ float4 lds128_volatile(const float *p) {
 // Border-ring correction of a phase-folded [bilinear x2 -> conv3x3 'same'] for an fp32 [n][n][CIN] source in shared memory
 // (see up_ring_correct in ofb_policy_dev.cuh): v[co] -= sum over the taps outside [0, 2n) of w[dy][dx][:, co] . U~.
 template <int CIN, int COUT>
-__device__ __forceinline__ void ring_correct_f32(const float *__restrict__ src, int n, int Y, int X, const float *__restrict__ w, float *v) {
+__device__ __forceinline__ void ring_correct_f32(const float *__restrict__ src, int n, int Y, int X, const float *__restrict__ w, float *v,
+                                                 int legacy) {
     for (int dy = 0; dy < 3; dy++) {
         const int YY = Y + dy - 1;
         for (int dx = 0; dx < 3; dx++) {
             const int XX = X + dx - 1;
             if (YY >= 0 && YY < 2 * n && XX >= 0 && XX < 2 * n) continue;
             int ylo, yhi, xlo, xhi; float wyl, wyh, wxl, wxh;
-            bil_tap_ext(YY, ylo, yhi, wyl, wyh);
-            bil_tap_ext(XX, xlo, xhi, wxl, wxh);
+            bil_tap_ext(YY, ylo, yhi, wyl, wyh, legacy);
+            bil_tap_ext(XX, xlo, xhi, wxl, wxh, legacy);
             ylo = min(max(ylo, 0), n - 1); yhi = min(max(yhi, 0), n - 1);
             xlo = min(max(xlo, 0), n - 1); xhi = min(max(xhi, 0), n - 1);
 #pragma unroll
@@ -470,6 +619,29 @@ __device__ __forceinline__ void ring_correct_f32(const float *__restrict__ src, 
 // dense1 (vector slice + bias + ReLU), dense2, output1 (+ argmax), updense1, upsampling1 + upconv1, upsampling2 + upconv2.
 // The two small up-convolutions run in the phase-folded form on their low-res grids (25 x 25 and 50 x 50), so no upsampled
 // map is materialised and the block needs ~26 KB of shared memory (8 blocks per SM instead of 2).
+// upconv2's output pixel (y, x) (4 channels = 8 bytes) in the "pairs" layout the fused tail stages with bulk copies
+// (ofb_policy_tail.cu): plane A entry (y+1)*26 + s = pixels (4s-1, 4s), plane B = pixels (4s+1, 4s+2), plane S (spare K
+// lanes) = L[y][0] in the low half of entry s = 0 and L[y][99] in the high half of entry s = 24; rows -1 / 100 and columns
+// -1 / 100 replicate the edge.
+__device__ __forceinline__ void up2_pairs_store_row(uint8_t *item, int row, int x, uint2 v) {
+    const int s = (x + 1) >> 2, rr = (x + 1) & 3;
+    uint8_t *e = item + ((size_t)(rr >> 1) * TL_UP2_PLANE + (size_t)row * TL_P + s) * 16 + (rr & 1) * 8;
+    *reinterpret_cast<uint2 *>(e) = v;
+    if (x == 0) {
+        *reinterpret_cast<uint2 *>(item + ((size_t)row * TL_P) * 16) = v;                                   // x = -1 := x = 0
+        *reinterpret_cast<uint2 *>(item + ((size_t)2 * TL_UP2_PLANE + (size_t)row * TL_P) * 16) = v;        // spare, left
+    }
+    if (x == 99) {
+        *reinterpret_cast<uint2 *>(item + ((size_t)row * TL_P + 25) * 16 + 8) = v;                          // x = 100 := x = 99
+        *reinterpret_cast<uint2 *>(item + ((size_t)2 * TL_UP2_PLANE + (size_t)row * TL_P + 24) * 16 + 8) = v;   // spare, right
+    }
+}
+__device__ __forceinline__ void up2_pairs_store(uint8_t *item, int y, int x, uint2 v) {
+    up2_pairs_store_row(item, y + 1, x, v);
+    if (y == 0) up2_pairs_store_row(item, 0, x, v);
+    if (y == 99) up2_pairs_store_row(item, 101, x, v);
+}
+
 #define HEADS_SMEM_FLOATS (128 + 64 + 640 + 5000 + 80 + 304 + 32 + 80)
 __global__ void __launch_bounds__(256, 3)
 k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, float *__restrict__ act_out,
@@ -548,14 +720,15 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
             o[0] += x * w1p[t * 8 + ph * 2];
             o[1] += x * w1p[t * 8 + ph * 2 + 1];
         }
-        ring_correct_f32<1, 2>(u, 25, Y, X, w1r, o);
+        ring_correct_f32<1, 2>(u, 25, Y, X, w1r, o, w.bil_legacy);
         a1[(Y * 50 + X) * 2] = fmaxf(o[0], 0.f);
         a1[(Y * 50 + X) * 2 + 1] = fmaxf(o[1], 0.f);
     }
     __syncthreads();
     // upsampling2 + upconv2 2 -> 4 + BN + ReLU (:172-175): one thread per pixel of the 50 x 50 grid, 4 phases x 4 channels
     // -> bf16 with channels padded to 8
-    __nv_bfloat16 *dst = up2_out + (size_t)s * POL_UP2_ITEM;   // tensor engine: de-interleaved by x mod 4 for k_tz_up3
+    __nv_bfloat16 *dst = up2_out + (size_t)s * POL_UP2_ITEM;   // plane_layout 1: de-interleaved by x mod 4 for k_tz_up3; 2: pairs for k_tz_tail
+    uint8_t *dstp = reinterpret_cast<uint8_t *>(up2_out) + (size_t)s * TL_UP2_ITEM_BYTES;
     for (int p = tid; p < 2500; p += nt) {
         const int i = p / 50, j = p % 50;
         float acc[16];
@@ -581,10 +754,11 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         for (int ph = 0; ph < 4; ph++) {
             const int y = 2 * i + (ph >> 1), x = 2 * j + (ph & 1);
             if (y == 0 || y == 99 || x == 0 || x == 99) continue;        // border ring: second loop
+            const uint2 px = make_uint2(pack_bf2(fmaxf(acc[ph * 4], 0.f), fmaxf(acc[ph * 4 + 1], 0.f)),
+                                        pack_bf2(fmaxf(acc[ph * 4 + 2], 0.f), fmaxf(acc[ph * 4 + 3], 0.f)));
+            if (plane_layout == 2) { up2_pairs_store(dstp, y, x, px); continue; }
             // full 16-byte pixels (channels 4..7 = 0): partial 32-byte sectors would turn into read-modify-writes in DRAM
-            *reinterpret_cast<uint4 *>(dst + (plane_layout ? pol_plane100_off(y, x) : (y * 100 + x) * 8)) =
-                make_uint4(pack_bf2(fmaxf(acc[ph * 4], 0.f), fmaxf(acc[ph * 4 + 1], 0.f)),
-                           pack_bf2(fmaxf(acc[ph * 4 + 2], 0.f), fmaxf(acc[ph * 4 + 3], 0.f)), 0u, 0u);
+            *reinterpret_cast<uint4 *>(dst + (plane_layout ? pol_plane100_off(y, x) : (y * 100 + x) * 8)) = make_uint4(px.x, px.y, 0u, 0u);
         }
     }
 #pragma unroll 1
@@ -601,12 +775,16 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
             c[2] += v.x * wa.z + v.y * wb.z;
             c[3] += v.x * wa.w + v.y * wb.w;
         }
-        ring_correct_f32<2, 4>(a1, 50, y, x, w2r, c);
+        ring_correct_f32<2, 4>(a1, 50, y, x, w2r, c, w.bil_legacy);
+        if (plane_layout == 2) {
+            up2_pairs_store(dstp, y, x, make_uint2(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f))));
+            continue;
+        }
         __nv_bfloat16 *q16 = dst + (plane_layout ? pol_plane100_off(y, x) : (y * 100 + x) * 8);
         *reinterpret_cast<uint4 *>(q16) = make_uint4(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f)), 0u, 0u);
-        if (plane_layout && x == 0) *reinterpret_cast<uint4 *>(q16 - 8) = make_uint4(0u, 0u, 0u, 0u);     // the row's halo slot
+        if (plane_layout == 1 && x == 0) *reinterpret_cast<uint4 *>(q16 - 8) = make_uint4(0u, 0u, 0u, 0u);     // the row's halo slot
     }
-    if (plane_layout)                                                    // halo slots of planes 1..3 (x = 1..3 are interior pixels)
+    if (plane_layout == 1)                                               // halo slots of planes 1..3 (x = 1..3 are interior pixels)
         for (int rp = tid; rp < 3 * 100; rp += nt)
             *reinterpret_cast<uint4 *>(dst + pol_plane100_off(rp % 100, 1 + rp / 100) - 8) = make_uint4(0u, 0u, 0u, 0u);
 }
@@ -647,7 +825,7 @@ k_up3_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, __nv_bfloat16 *__res
         float o[8];
 #pragma unroll
         for (int co = 0; co < 8; co++) o[co] = acc[ph * 8 + co];
-        if (Y == 0 || Y == 199 || X == 0 || X == 199) up_ring_correct<4, 8>(GlobalImage{L, 100}, 100, Y, X, rw, o);
+        if (Y == 0 || Y == 199 || X == 0 || X == 199) up_ring_correct<4, 8>(GlobalImage{L, 100}, 100, Y, X, rw, o, w.bil_legacy);
 #pragma unroll
         for (int co = 0; co < 8; co++) o[co] = fmaxf(o[co], 0.f);
         *reinterpret_cast<uint4 *>(dst + ((size_t)Y * 200 + X) * 8) = pack_bf8(o);
@@ -688,7 +866,7 @@ k_up4_cc(const __nv_bfloat16 *__restrict__ in, PolicyDev w, float *__restrict__ 
         for (int ph = 0; ph < 4; ph++) {
             const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
             float o = acc[ph];
-            if (Y == 0 || Y == 399 || X == 0 || X == 399) up_ring_correct<8, 1>(GlobalImage{L, 200}, 200, Y, X, rw, &o);
+            if (Y == 0 || Y == 399 || X == 0 || X == 399) up_ring_correct<8, 1>(GlobalImage{L, 200}, 200, Y, X, rw, &o, w.bil_legacy);
             const int idx = Y * 400 + X;
             if (ptr_out) ptr_out[(size_t)blockIdx.y * 160000 + idx] = o;
             if (amax_better(o, idx, bv, bi)) { bv = o; bi = idx; }
@@ -763,9 +941,17 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
       if (tc) { if ((rc = pol_tc_dense1(p, ws.flat, ws.hflat, A, st)) != OFB_OK) return rc; }
       else k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A); }
     { ProfScope ps(p, L_HEADS, st);
-      k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2, tc ? 1 : 0); }
+      k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2,
+                                                                 tc ? (p->unfused_tail ? 1 : 2) : 0); }
     if (!xy && !ptr) { OFB_CUDA_CHECK(cudaGetLastError()); return OFB_OK; }
     int parts;
+    if (tc && !p->unfused_tail) {
+        // fused tail: upconv3 never reaches HBM, (x, y) comes straight out of the kernel
+        ProfScope ps(p, L_TAIL, st);
+        if ((rc = pol_tz_tail(p, ws.up2, ptr, xy, p->taps ? ws.up3 : nullptr, S, st)) != OFB_OK) return rc;
+        OFB_CUDA_CHECK(cudaGetLastError());
+        return OFB_OK;
+    }
     if (tc) {
         { ProfScope ps(p, L_UP3, st); if ((rc = pol_tz_up3(p, ws.up2, ws.up3, S, st)) != OFB_OK) return rc; }
         { ProfScope ps(p, L_UP4, st); if ((rc = pol_tz_up4(p, ws.up3, ptr, ws.amax_val, ws.amax_idx, S, st)) != OFB_OK) return rc; }
@@ -926,8 +1112,33 @@ __global__ void k_plane100_to_nhwc(const __nv_bfloat16 *__restrict__ src, __nv_b
     *reinterpret_cast<uint4 *>(dst + t * 8) = *reinterpret_cast<const uint4 *>(src + item * POL_UP2_ITEM + pol_plane100_off(y, x));
 }
 
+// pairs layout (see up2_pairs_store) -> NHWC [item][100][100][8] (channels 4..7 = 0)
+__global__ void k_pairs_to_nhwc(const uint8_t *__restrict__ src, __nv_bfloat16 *__restrict__ dst, long long n_pixels) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_pixels) return;
+    const long long item = t / 10000;
+    const int p = (int)(t % 10000), y = p / 100, x = p % 100;
+    const int s = (x + 1) >> 2, rr = (x + 1) & 3;
+    const uint2 v = *reinterpret_cast<const uint2 *>(src + item * TL_UP2_ITEM_BYTES +
+                                                     ((size_t)(rr >> 1) * TL_UP2_PLANE + (size_t)(y + 1) * TL_P + s) * 16 + (rr & 1) * 8);
+    *reinterpret_cast<uint4 *>(dst + t * 8) = make_uint4(v.x, v.y, 0u, 0u);
+}
+
 extern "C" int ofb_policy_debug_tap(ofb_policy *p, int which, int64_t n_items, void *dst_dev, void *stream) {
     if (!p || !dst_dev || n_items < 0 || n_items > p->max_ships) { ofb_set_error("ofb_policy_debug_tap: bad argument"); return OFB_E_ARG; }
+    const bool fused = p->engine == OFB_ENGINE_TENSOR && !p->unfused_tail;
+    if (which == 5 && fused) {                                   // the fused tail takes upconv2's output in the pairs layout
+        const long long np = n_items * 10000;
+        if (np) k_pairs_to_nhwc<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const uint8_t *>(p->ws.up2), static_cast<__nv_bfloat16 *>(dst_dev), np);
+        OFB_CUDA_CHECK(cudaGetLastError());
+        return OFB_OK;
+    }
+    if (which == 6 && fused) {                                   // ... and writes upconv3's output (NHWC) only when taps are enabled
+        if (!p->taps) { ofb_set_error("ofb_policy_debug_tap: enable taps (ofb_policy_set_taps) before the forward to see upconv3's output"); return OFB_E_STATE; }
+        OFB_CUDA_CHECK(cudaMemcpyAsync(dst_dev, p->ws.up3, (size_t)n_items * 320000 * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return OFB_OK;
+    }
     if (which == 5 && p->engine == OFB_ENGINE_TENSOR) {          // ... and upconv2's in the 4-plane layout
         const long long np = n_items * 10000;
         if (np) k_plane100_to_nhwc<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

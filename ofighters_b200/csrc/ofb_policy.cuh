@@ -44,6 +44,8 @@ struct PolicyDev {
     __nv_bfloat16 *c2_tz;     // block-Toeplitz B operand of conv2: [3 u][5 k-steps][2 chunks][64 n = xo*8 + cout][8 cin]
     __nv_bfloat16 *u3_tz;     // block-Toeplitz B operand of upconv3: [3 u][3 k-steps][2 chunks][128 n = xo*32 + phase*8 + cout][8 cin]
     __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
+    int bil_legacy;           // 1 = TF1.x legacy bilinear in the scalar border code (the folded operands carry it themselves)
+    uint8_t *tail_blob;       // operands + constants of the fused tail kernel (ofb_policy_tail.cuh: TL_WBYTES)
 };
 
 struct PolicyWork {
@@ -69,6 +71,9 @@ struct ofb_policy {
     PolicyDev w;
     PolicyWork ws;
     int dense_trunk;          // 1 = always the dense tcgen05 trunk12 (k_tz_trunk12); 0 = the sparse one (k_sp_trunk12)
+    int unfused_tail;         // 1 = upconv3 / upconv4 as two kernels through HBM (k_tz_up3, k_tz_up4); 0 = the fused tail (k_tz_tail)
+    int taps;                 // 1 = the fused tail also writes upconv3's output (validation taps)
+    int bilinear_legacy;      // 0 = TF2 half-pixel bilinear x2 (default), 1 = TF1.x legacy (asymmetric) UpSampling2D
     int profiling;            // when set, forward brackets every kernel with CUDA events
     void *prof;               // std::vector<ProfEvent>*
     void *arena_blob;         // single allocation holding all weights
@@ -90,6 +95,9 @@ int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out
 // sparse trunk12 on CUDA cores, ofb_policy_sp.cu
 int pol_sp_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
+// fused upconv3 -> upconv4 -> argmax, ofb_policy_tail.cu (input: upconv2's output in the pairs layout)
+int pol_tz_tail(const ofb_policy *p, const __nv_bfloat16 *up2_pairs, float *ptr_out, int32_t *xy, __nv_bfloat16 *up3_dbg, int n_items,
+                cudaStream_t st);
 // element offset of pixel (y, x) of a 100 x 100 x 8 image in plane layout (4 planes of x mod 4)
 __host__ __device__ __forceinline__ int pol_plane100_off(int y, int x) { return (((x & 3) * 100 + y) * 26 + (x >> 2) + 1) * 8; }
 // element offset of pixel (Y, X) of a 200 x 200 x 8 image in plane layout (ofb_policy_tz.cu)

@@ -94,18 +94,24 @@ __device__ __forceinline__ void bil_tap(int Y, int n, int &lo, int &hi, float &w
 //     out_true = out_folded - sum_{(dy,dx) out of range} w[dy][dx] . U~[Y+dy-1][X+dx-1]
 // with U~ the same half-pixel interpolation evaluated on the replicate-extended input.
 // `L(y, x)` returns the 8 bf16 channels of low-res pixel (y, x) for y, x in [-1, n] (replicated).
-__device__ __forceinline__ void bil_tap_ext(int Y, int &lo, int &hi, float &wlo, float &whi) {
+// legacy != 0: TF1.x UpSampling2D (U[2i] = L[i], U[2i+1] = (L[i] + L[i+1]) / 2) instead of TF2's half-pixel centres
+__device__ __forceinline__ void bil_tap_ext(int Y, int &lo, int &hi, float &wlo, float &whi, int legacy = 0) {
     const int i = Y >> 1;                                   // arithmetic shift: -1 -> -1
+    if (legacy) {
+        lo = i; hi = i + (Y & 1); wlo = (Y & 1) ? 0.5f : 1.0f; whi = (Y & 1) ? 0.5f : 0.0f;
+        return;
+    }
     if (Y & 1) { lo = i; hi = i + 1; wlo = 0.75f; whi = 0.25f; }
     else { lo = i - 1; hi = i; wlo = 0.25f; whi = 0.75f; }
 }
 
 // contribution of ONE out-of-range tap (dy, dx) of output pixel (Y, X): acc[co] += w[dy][dx][:, co] . U~[Y+dy-1][X+dx-1]
 template <int CIN, int COUT, class Acc>
-__device__ __forceinline__ void up_ring_tap(const Acc &L, int Y, int X, int dy, int dx, const float *__restrict__ w, float *acc) {
+__device__ __forceinline__ void up_ring_tap(const Acc &L, int Y, int X, int dy, int dx, const float *__restrict__ w, float *acc,
+                                            int legacy = 0) {
     int ylo, yhi, xlo, xhi; float wyl, wyh, wxl, wxh;
-    bil_tap_ext(Y + dy - 1, ylo, yhi, wyl, wyh);
-    bil_tap_ext(X + dx - 1, xlo, xhi, wxl, wxh);
+    bil_tap_ext(Y + dy - 1, ylo, yhi, wyl, wyh, legacy);
+    bil_tap_ext(X + dx - 1, xlo, xhi, wxl, wxh, legacy);
     float a[8], c[8], d[8], e[8];
     unpack_bf8(L(ylo, xlo), a);
     unpack_bf8(L(ylo, xhi), c);
@@ -121,7 +127,7 @@ __device__ __forceinline__ void up_ring_tap(const Acc &L, int Y, int X, int dy, 
 }
 
 template <int CIN, int COUT, class Acc>
-__device__ __forceinline__ void up_ring_correct(const Acc &L, int n, int Y, int X, const float *__restrict__ w, float *v) {
+__device__ __forceinline__ void up_ring_correct(const Acc &L, int n, int Y, int X, const float *__restrict__ w, float *v, int legacy = 0) {
     float acc[COUT];
 #pragma unroll
     for (int co = 0; co < COUT; co++) acc[co] = 0.f;
@@ -130,7 +136,7 @@ __device__ __forceinline__ void up_ring_correct(const Acc &L, int n, int Y, int 
         for (int dx = 0; dx < 3; dx++) {
             const int XX = X + dx - 1;
             if (YY >= 0 && YY < 2 * n && XX >= 0 && XX < 2 * n) continue;
-            up_ring_tap<CIN, COUT>(L, Y, X, dy, dx, w, acc);
+            up_ring_tap<CIN, COUT>(L, Y, X, dy, dx, w, acc, legacy);
         }
     }
 #pragma unroll

@@ -43,6 +43,7 @@ struct Tz4Args {
     float *amax_val;                  // [item][TZ4_STRIPS]
     int *amax_idx;
     long long *dbg;                   // optional: clock64 stamps of CTA (5, 0) at the phase boundaries
+    int legacy;                       // TF1.x legacy bilinear in the ring corrections
 };
 
 #define TZ4_NG 3                      // draining groups of 4 warps; group g owns stage g (TZ4_NG == TZ4_NST)
@@ -258,7 +259,7 @@ k_tz_up4(const Tz4Args a, const int n_work) {
                 float *cdots = reinterpret_cast<float *>(smem + Tz4Smem::off_scr) + grp * TZ4_SCR, *rdots = cdots + 2 * (TZ4_R + 2) * 3;
                 const int dye = first ? 0 : 2, Yedge = first ? 0 : Wo - 1;
                 int rlo = 0, rhi = 0; float rwl = 0.f, rwh = 0.f;
-                bil_tap_ext(Yedge + dye - 1, rlo, rhi, rwl, rwh);
+                bil_tap_ext(Yedge + dye - 1, rlo, rhi, rwl, rwh, a.legacy);
                 if (gt < 2 * (TZ4_R + 2) * 3) {
                     const int side = gt / ((TZ4_R + 2) * 3), rem = gt % ((TZ4_R + 2) * 3), r = rem / 3, dy = rem % 3;
                     float x[8];
@@ -292,7 +293,7 @@ k_tz_up4(const Tz4Args a, const int n_work) {
 #pragma unroll
                         for (int dy = 0; dy < 3; dy++) {
                             int lo, hi; float wlo, whi;
-                            bil_tap_ext(Y + dy - 1, lo, hi, wlo, whi);
+                            bil_tap_ext(Y + dy - 1, lo, hi, wlo, whi, a.legacy);
                             c += wlo * ds[(lo - y0 + 1) * 3 + dy] + whi * ds[(hi - y0 + 1) * 3 + dy];
                         }
                         if ((first || last) && Y == Yedge) {        // corner: the two taps of the border row outside its column
@@ -301,7 +302,7 @@ k_tz_up4(const Tz4Args a, const int n_work) {
                             for (int dx = 0; dx < 3; dx++) {
                                 if (dx == (side ? 2 : 0)) continue;
                                 int lo, hi; float wlo, whi;
-                                bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                                bil_tap_ext(X + dx - 1, lo, hi, wlo, whi, a.legacy);
                                 c += wlo * rdots[(lo + 1) * 3 + dx] + whi * rdots[(hi + 1) * 3 + dx];
                             }
                         }
@@ -310,7 +311,7 @@ k_tz_up4(const Tz4Args a, const int n_work) {
 #pragma unroll
                         for (int dx = 0; dx < 3; dx++) {
                             int lo, hi; float wlo, whi;
-                            bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                            bil_tap_ext(X + dx - 1, lo, hi, wlo, whi, a.legacy);
                             c += wlo * rdots[(lo + 1) * 3 + dx] + whi * rdots[(hi + 1) * 3 + dx];
                         }
                     }
@@ -439,6 +440,7 @@ struct Tz3Args {
     const float *ring_w;              // un-phased fp32 weights [9][4][8]
     __nv_bfloat16 *out;               // plane layout [item][8][200][26][8]
     long long *dbg;                   // optional per-work clock stamps of CTA 5
+    int legacy;
 };
 
 struct Tz3Smem {
@@ -593,7 +595,7 @@ k_tz_up3(const Tz3Args a, const int n_work) {
             mbar_wait(&halo[s], par);
             const int dye = first ? 0 : 2, Yedge = first ? 0 : Wo - 1;
             int rlo = 0, rhi = 0; float rwl = 0.f, rwh = 0.f;
-            bil_tap_ext(Yedge + dye - 1, rlo, rhi, rwl, rwh);
+            bil_tap_ext(Yedge + dye - 1, rlo, rhi, rwl, rwh, a.legacy);
             for (int q = lane; q < 2 * (TZ3_R + 2) * 3; q += 32) {
                 const int side = q / ((TZ3_R + 2) * 3), rem = q % ((TZ3_R + 2) * 3), r = rem / 3, dy = rem % 3;
                 float x[8], d[8];
@@ -640,7 +642,7 @@ k_tz_up3(const Tz3Args a, const int n_work) {
 #pragma unroll
                     for (int dy = 0; dy < 3; dy++) {
                         int lo, hi; float wlo, whi;
-                        bil_tap_ext(Y + dy - 1, lo, hi, wlo, whi);
+                        bil_tap_ext(Y + dy - 1, lo, hi, wlo, whi, a.legacy);
                         const float *dl = ds + ((lo - y0 + 1) * 3 + dy) * 8, *dh = ds + ((hi - y0 + 1) * 3 + dy) * 8;
 #pragma unroll
                         for (int co = 0; co < 8; co++) c[co] += wlo * dl[co] + whi * dh[co];
@@ -650,7 +652,7 @@ k_tz_up3(const Tz3Args a, const int n_work) {
                         for (int dx = 0; dx < 3; dx++) {
                             if (dx == (side ? 2 : 0)) continue;
                             int lo, hi; float wlo, whi;
-                            bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                            bil_tap_ext(X + dx - 1, lo, hi, wlo, whi, a.legacy);
                             const float *dl = rdots + ((lo + 1) * 3 + dx) * 8, *dh = rdots + ((hi + 1) * 3 + dx) * 8;
 #pragma unroll
                             for (int co = 0; co < 8; co++) c[co] += wlo * dl[co] + whi * dh[co];
@@ -661,7 +663,7 @@ k_tz_up3(const Tz3Args a, const int n_work) {
 #pragma unroll
                     for (int dx = 0; dx < 3; dx++) {
                         int lo, hi; float wlo, whi;
-                        bil_tap_ext(X + dx - 1, lo, hi, wlo, whi);
+                        bil_tap_ext(X + dx - 1, lo, hi, wlo, whi, a.legacy);
                         const float *dl = rdots + ((lo + 1) * 3 + dx) * 8, *dh = rdots + ((hi + 1) * 3 + dx) * 8;
 #pragma unroll
                         for (int co = 0; co < 8; co++) c[co] += wlo * dl[co] + whi * dh[co];
@@ -771,7 +773,7 @@ int pol_tz_up4(const ofb_policy *p, const __nv_bfloat16 *in, float *ptr_out, flo
     if (n_items == 0) return OFB_OK;
     Tz4Args a = {};
     a.in = in; a.wt = p->w.u4_tz; a.ring_w = p->w.u4_w; a.bias = p->u4_bias;
-    a.ptr_out = ptr_out; a.amax_val = amax_val; a.amax_idx = amax_idx;
+    a.ptr_out = ptr_out; a.amax_val = amax_val; a.amax_idx = amax_idx; a.legacy = p->w.bil_legacy;
     a.dbg = g_tz_dbg;
     const int n_work = n_items * TZ4_STRIPS;
     k_tz_up4<<<n_work < n_sm ? n_work : n_sm, TZ4_NTP, Tz4Smem::total, st>>>(a, n_work);     // one persistent CTA per SM
@@ -788,7 +790,7 @@ int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out,
     OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
     if (n_items == 0) return OFB_OK;
     Tz3Args a = {};
-    a.in = in; a.wt = p->w.u3_tz; a.bias = p->w.u3_pb; a.ring_w = p->w.u3_w; a.out = out;
+    a.in = in; a.wt = p->w.u3_tz; a.bias = p->w.u3_pb; a.ring_w = p->w.u3_w; a.out = out; a.legacy = p->w.bil_legacy;
     a.dbg = g_tz_dbg3;
     const int n_work = n_items * TZ3_STRIPS;
     k_tz_up3<<<n_work < n_sm ? n_work : n_sm, TZ3_NTP, Tz3Smem::total, st>>>(a, n_work);

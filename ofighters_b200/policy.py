@@ -13,6 +13,7 @@ libofb.so (tcgen05 tensor-core kernels + CUDA-core glue); there is no torch / CP
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -56,9 +57,16 @@ def _ptr(t):
 
 
 class PolicyB200:
-    KERNELS_PER_CHUNK = 8         # trunk12, conv3, conv4, dense1, heads, up3, up4, argmax
-
-    def __init__(self, weights, device=None, max_ships=1024):
+    def __init__(self, weights, device=None, max_ships=1024, bilinear="tf2", fused_tail=True, dense_trunk=False):
+        """``bilinear``: "tf2" (half-pixel centres, the default of every TF2 / Keras >= 2.3 UpSampling2D) or "tf1" (the legacy
+        asymmetric kernel of TF1.x / standalone Keras 2.2) -- the reference pins no version (requirements.txt:1-2), so the
+        choice is the caller's.  ``fused_tail=False`` / ``dense_trunk=True`` select the alternative kernels (measurement aids)."""
+        if bilinear not in ("tf2", "tf1"):
+            raise Exception("bilinear must be 'tf2' or 'tf1'")
+        self.bilinear = bilinear
+        self._flags = (_lib.POLICY_BILINEAR_TF1 if bilinear == "tf1" else 0) | (0 if fused_tail else _lib.POLICY_UNFUSED_TAIL) | \
+            (_lib.POLICY_DENSE_TRUNK if dense_trunk else 0)
+        self.fused_tail = bool(fused_tail) and not os.environ.get("OFB_POLICY_UNFUSED_TAIL", "").strip("0")
         if not torch.cuda.is_available():
             raise _lib.OfbError("PolicyB200 needs a CUDA device: the forward is made of hand-written "
                                 "sm_100a kernels and has no CPU fallback")
@@ -66,6 +74,7 @@ class PolicyB200:
         self._lib = _lib.load()
         self.max_ships = int(max_ships)
         self._h = None
+        self._engine = "tensor"
         self.launch_count = 0         # kernels of libofb launched by this object so far
         self.act_values = None        # Trainer.act_values / ptr_values of the last predict (qlearnIA_V2.py:214-215)
         self.ptr_values = None
@@ -103,15 +112,25 @@ class PolicyB200:
             _lib.check(self._lib.ofb_policy_set_weights(self._h, C.byref(w), self._stream()))
         else:
             h = C.c_void_p()
-            _lib.check(self._lib.ofb_policy_create(C.byref(w), self.device.index or 0, self.max_ships, C.byref(h)))
+            _lib.check(self._lib.ofb_policy_create_opts(C.byref(w), self.device.index or 0, self.max_ships, self._flags, C.byref(h)))
             self._h = h
         self.weights = host
 
     def set_engine(self, name):
         """"tensor" (tcgen05, default) or "cuda_core" (same arithmetic on CUDA cores; validation twin)."""
         _lib.check(self._lib.ofb_policy_set_engine(self._h, {"tensor": 0, "cuda_core": 1}[name]))
+        self._engine = name
 
-    LAYERS = ("trunk12", "conv3", "conv4", "dense1", "heads", "up3", "up4", "argmax")
+    LAYERS = ("trunk12", "conv3", "conv4", "dense1", "heads", "up3", "up4", "argmax", "tail")
+
+    @property
+    def kernels_per_chunk(self):
+        """trunk12, conv3, conv4, dense1, heads + the fused tail (or up3, up4, argmax)."""
+        return 6 if (self.fused_tail and self._engine == "tensor") else 8
+
+    def set_taps(self, enable):
+        """Validation only: the fused tail kernel also writes upconv3's output so that ``debug_tap(6, ...)`` can read it."""
+        _lib.check(self._lib.ofb_policy_set_taps(self._h, 1 if enable else 0))
 
     def profile(self, enable):
         """enable=True: start bracketing every kernel with CUDA events.  enable=False: stop and return
@@ -120,7 +139,7 @@ class PolicyB200:
             self._prof_calls = 0
             _lib.check(self._lib.ofb_policy_profile(self._h, 1, None))
             return None
-        ms = (C.c_float * 8)()
+        ms = (C.c_float * 9)()
         _lib.check(self._lib.ofb_policy_profile(self._h, 0, ms))
         calls = max(1, getattr(self, "_prof_calls", 1))
         return {k: float(ms[i]) / calls for i, k in enumerate(self.LAYERS)}
@@ -156,7 +175,7 @@ class PolicyB200:
                                                 _ptr(ptr), _ptr(iact), _ptr(xy), self._stream()))
         self._prof_calls = getattr(self, "_prof_calls", 0) + 1
         per_chunk = max(1, self.max_ships // ships_per_arena)
-        self.launch_count += self.KERNELS_PER_CHUNK * ((A + per_chunk - 1) // per_chunk)
+        self.launch_count += self.kernels_per_chunk * ((A + per_chunk - 1) // per_chunk)
         return {"act": act, "ptr": ptr, "iaction": iact, "xy": xy}
 
     def forward_argmax(self, maps_bits, vec, ships_per_arena=1):

@@ -7,8 +7,10 @@ PARITY UNPINNED: Keras / TensorFlow are un-pinned third-party dependencies that 
 the reference ships no trained weights and its tests hold no expected outputs for the model, so
 this file is pinned only by the layer list itself (and by the hand-checked bilinear / flatten /
 argmax conventions in tests/test_policy_oracle.py).  Choices where Keras versions differ:
-  * UpSampling2D(interpolation='bilinear') = TF2 half-pixel centres with edge clamp
-    (== F.interpolate(scale_factor=2, mode='bilinear', align_corners=False));
+  * UpSampling2D(interpolation='bilinear'): bilinear="tf2" (default) = TF2 half-pixel centres with edge clamp
+    (== F.interpolate(scale_factor=2, mode='bilinear', align_corners=False)); bilinear="tf1" = the TF1.x / standalone
+    Keras 2.2 legacy kernel tf.image.resize_bilinear(align_corners=False): source coordinate = dst / 2, i.e.
+    out[2i] = in[i], out[2i+1] = (in[i] + in[min(i+1, n-1)]) / 2 per axis;
   * BatchNormalization epsilon = 1e-3, inference mode (moving statistics).
 
 Weights are a flat ``dict name -> tensor`` in Keras layer order with Keras layouts:
@@ -73,7 +75,23 @@ def _conv_bn_relu(x, w, conv, bn):
     return y
 
 
-def forward(w, image, vector, return_intermediates=False):
+def upsample2x(u, bilinear="tf2"):
+    """UpSampling2D(size=2, interpolation='bilinear') on NCHW (see the module docstring for the two kernels)."""
+    if bilinear == "tf2":
+        return F.interpolate(u, scale_factor=2, mode="bilinear", align_corners=False)
+    if bilinear != "tf1":
+        raise ValueError("bilinear must be 'tf2' or 'tf1'")
+    for dim in (2, 3):
+        n = u.shape[dim]
+        nxt = torch.index_select(u, dim, torch.clamp(torch.arange(n) + 1, max=n - 1))
+        u = torch.stack([u, 0.5 * (u + nxt)], dim=dim + 1)            # interleave: even outputs = in[i], odd = the mean
+        shape = list(u.shape)
+        shape[dim:dim + 2] = [2 * n]
+        u = u.reshape(shape)
+    return u
+
+
+def forward(w, image, vector, return_intermediates=False, bilinear="tf2"):
     """image [B,400,400,2] (NHWC, ch0 ship_map, ch1 laser_map), vector [B,8]
     -> act [B,2], ptr [B,400,400]   (qlearnIA_V2.py:123-190)."""
     x = image.to(torch.float32).permute(0, 3, 1, 2).contiguous()
@@ -92,7 +110,7 @@ def forward(w, image, vector, return_intermediates=False):
     u = u.reshape(-1, 25, 25, 1).permute(0, 3, 1, 2)                   # Reshape((25,25,1)) :164
     inter["updense1"] = u
     for i in range(1, 5):                                              # :166-186
-        u = F.interpolate(u, scale_factor=2, mode="bilinear", align_corners=False)
+        u = upsample2x(u, bilinear)
         u = _conv_bn_relu(u, w, "upconv%d" % i, "upnorm%d" % i if i < 4 else None)
         inter["up%d" % i] = u
     ptr = u[:, 0]

@@ -47,6 +47,7 @@ def setup():
     from ofighters_b200.policy import PolicyB200
     w = po.init_weights(5, randomize_bn=True)
     pol = PolicyB200(w, max_ships=16)
+    pol.set_taps(True)                                   # the fused tail keeps upconv3's output on the SM unless asked
     bg, maps = _scene(6)
     img = _dense_image(maps)
     vec = bg.obs_vec[:, 0, :].contiguous()
