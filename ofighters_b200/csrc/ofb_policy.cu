@@ -198,6 +198,8 @@ static std::vector<uint8_t> pack_tail(const std::vector<float> &w3, const std::v
                 }
     // ---- floats: upconv3's bias, then the 4 corner pixels' weights [corner][uu][vv][ci] (bf16-rounded like the operands):
     //      the corner reads upconv3 pixels (Y0 + uu, X0 + vv), (Y0, X0) = (0 | 198, 0 | 198)
+    // upconv3's bias rides the tensor pipe: one extra MMA per tile whose A operand is a column of ones (K lane 0)
+    for (int n = 0; n < 128; n++) put(TL_OFF_BIAS3 + (size_t)n * 16, b3[n & 7]);
     float *aux = reinterpret_cast<float *>(blob.data() + TL_OFF_AUX);
     for (int c = 0; c < 8; c++) aux[c] = b3[c];
     for (int cid = 0; cid < 4; cid++) {

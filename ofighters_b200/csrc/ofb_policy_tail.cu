@@ -50,14 +50,19 @@ struct TlArgs {
     float *ptr_out;                   // optional dense pointer map [item][400][400]
     int *xy;                          // [item][2]
     __nv_bfloat16 *up3_dbg;           // optional: upconv3's output NHWC [item][200][200][8] (validation taps)
+    long long *stamps;                // optional: clock64 stamps of CTA 0, [tile < TL_STAMP_TILES][8] (scripts/tail_stamps.py)
 };
+#define TL_STAMP_TILES 64
+#define TL_STAMP(g, j) do { if (a.stamps && blockIdx.x == 0 && (g) < TL_STAMP_TILES) a.stamps[(g) * 8 + (j)] = clock64(); } while (0)
 
 // shared memory (bytes)
 struct TlSmem {
-    static constexpr unsigned off_ring = 0;                                          // 16 planes x TL_RING rows x 16 B
+    static constexpr unsigned off_ones = 0;                                          // 128 rows x 16 B: K lane 0 = 1.0 (bias MMA's A operand;
+                                                                                     // its second K chunk = the ring rows behind it, x 0)
+    static constexpr unsigned off_ring = off_ones + 128 * 16;                        // 16 planes x TL_RING rows x 16 B
     static constexpr unsigned off_w = off_ring + 16 * TL_RING * 16;                  // the weight blob, verbatim
     static constexpr unsigned off_a3 = off_w + TL_WBYTES;                            // 2 stages x 3 planes x TL_A3_SLOTS x 16 B
-    static constexpr unsigned off_misc = off_a3 + 2 * 3 * TL_A3_SLOTS * 16;          // corners[2][4], vship, sv[4], si[4]
+    static constexpr unsigned off_misc = off_a3 + 2 * 3 * TL_A3_SLOTS * 16;          // corners[2][4], vship, si[4]
     static constexpr unsigned off_bar = off_misc + 32 * 4;
     // barriers: wbar, a3_full[2], a3_empty[2], d3_full[2], d3_empty[2], d3v_empty, ring_full[3], ring_free[3], d4_full[2], d4_empty[2]
     static constexpr unsigned n_bar = 1 + 2 + 2 + 2 + 2 + 1 + 3 + 3 + 2 + 2;
@@ -95,6 +100,7 @@ k_tz_tail(const TlArgs a, const int n_ships) {
     // the ring starts out as zeros: rows nobody has written yet are read (by M rows whose outputs are discarded) and must
     // not hold NaN patterns
     for (int i = tid; i < 16 * TL_RING; i += TL_NT) ring[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid < 128) reinterpret_cast<uint4 *>(smem + TlSmem::off_ones)[tid] = make_uint4(0x3F80u, 0u, 0u, 0u);   // bf16 1.0 in K lane 0
     if (tid == 0) {
         mbar_init(wbar, 1);
         for (int s = 0; s < 2; s++) {
@@ -146,6 +152,8 @@ k_tz_tail(const TlArgs a, const int n_ships) {
         mbar_wait(wbar, 0);
         const bool leader = elect_one();
         const uint32_t b3 = smem_u32(smem + TlSmem::off_w + TL_OFF_B3) >> 4, b3v = smem_u32(smem + TlSmem::off_w + TL_OFF_B3V) >> 4;
+        const uint32_t ones16 = smem_u32(smem + TlSmem::off_ones) >> 4, ring16 = smem_u32(ring) >> 4;
+        const uint32_t bias16 = smem_u32(smem + TlSmem::off_w + TL_OFF_BIAS3) >> 4;
         constexpr uint32_t ID128 = instr_desc(128), ID64 = instr_desc(64);
         int vq = 0;
         for (int g = 0; g < n_tiles; g++) {
@@ -154,6 +162,9 @@ k_tz_tail(const TlArgs a, const int n_ships) {
             if (g >= 2) { mbar_wait(&d3_empty[s], (uint32_t)(((g >> 1) - 1) & 1)); tc_fence_after(); }
             const uint32_t a16 = smem_u32(smem + TlSmem::off_a3 + s * (3 * TL_A3_SLOTS * 16)) >> 4;
             const uint32_t d = tmem_base + (uint32_t)(s * 128);
+            // bias: A = a column of ones in K lane 0 (the second K chunk reads ring rows against zero weights)
+            const uint64_t ones_d = smem_desc(ones16, ring16 - ones16, 8), bias_d = smem_desc(bias16, 128, 8);
+            if (leader) tc_mma(d, ones_d, bias_d, ID128, 0u);
 #pragma unroll
             for (int u = 0; u < 3; u++)
 #pragma unroll
@@ -161,12 +172,13 @@ k_tz_tail(const TlArgs a, const int n_ships) {
                     // ks 0: chunks (PA[e], PB[e]); ks 1: (PA[e + 1], spare[e])
                     const uint64_t ad = smem_desc(a16 + (uint32_t)(26 * u + ks), ks ? 2u * TL_A3_SLOTS - 1u : (uint32_t)TL_A3_SLOTS, 8);
                     const uint64_t bd = smem_desc(b3 + (uint32_t)((u * 2 + ks) * 2 * 128), 128, 8);
-                    if (leader) tc_mma(d, ad, bd, ID128, (u | ks) ? 1u : 0u);
+                    if (leader) tc_mma(d, ad, bd, ID128, 1u);
                 }
             if (t == 0 || t == TL_TILES - 1) {
                 // top / bottom image row: the true (zero-padded) phase a = 0 / 1 of row i = 0 / 99 into their own columns
                 const int set = t == 0 ? 0 : 1;
                 if (vq >= 1) { mbar_wait(d3v_empty, (uint32_t)((vq - 1) & 1)); tc_fence_after(); }
+                if (leader) tc_mma(tmem_base + TL_TM_D3V, ones_d, bias_d, ID64, 0u);       // column n of the variant has channel n & 7 too
 #pragma unroll
                 for (int ui = 0; ui < 2; ui++)
 #pragma unroll
@@ -174,7 +186,7 @@ k_tz_tail(const TlArgs a, const int n_ships) {
                         const int u = set == 0 ? ui + 1 : ui;
                         const uint64_t ad = smem_desc(a16 + (uint32_t)(26 * u + ks), ks ? 2u * TL_A3_SLOTS - 1u : (uint32_t)TL_A3_SLOTS, 8);
                         const uint64_t bd = smem_desc(b3v + (uint32_t)((((set * 2 + ui) * 2) + ks) * 2 * 64), 64, 8);
-                        if (leader) tc_mma(tmem_base + TL_TM_D3V, ad, bd, ID64, (ui | ks) ? 1u : 0u);
+                        if (leader) tc_mma(tmem_base + TL_TM_D3V, ad, bd, ID64, 1u);
                     }
                 vq++;
             }
@@ -191,7 +203,9 @@ k_tz_tail(const TlArgs a, const int n_ships) {
         for (int g = 0; g < n_tiles; g++) {
             const int s = g & 1, t = g % TL_TILES, slot = t % 3;
             mbar_wait(&ring_full[slot], (uint32_t)((g / 3) & 1));
+            if (lane == 0) TL_STAMP(g, 4);
             if (g >= 2) { mbar_wait(&d4_empty[s], (uint32_t)(((g >> 1) - 1) & 1)); tc_fence_after(); }
+            if (lane == 0) TL_STAMP(g, 5);
             const uint32_t base = ring16 + (uint32_t)(TL_MARGIN - TL_UP4_LAG + 128 * slot);       // ring row of M row 128 t - 32
             const uint32_t d = tmem_base + (uint32_t)(TL_TM_D4 + 96 * s);
             // vertical tap dy reads upconv3 row 2i - 1 + dy: parity a = (dy + 1) & 1, ring row m + {-26, 0, 0, +26}
@@ -232,12 +246,11 @@ k_tz_tail(const TlArgs a, const int n_ships) {
             __syncwarp();
         }
     } else if (warp < 8) {
-        // ------------------------------------------------------------ upconv3 drain: group grp takes the tiles g = grp (mod 2)
+        // ------------------------------------------------------------ upconv3 drain: group grp takes the tiles g = grp (mod 2).
+        // TMEM -> ReLU -> bf16 happens BEFORE the wait for the ring slot (the 16 chunks of an M row sit in 64 registers), so
+        // that only the stores are in the dependency chain  MMAs of upconv4 (g - 2) -> ring slot free -> MMAs of upconv4 (g).
         mbar_wait(wbar, 0);
         const int grp = warp >> 2, gw = warp & 3, r = tid & 127;
-        float bias[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) bias[c] = wf[c];
         for (int g = grp; g < n_tiles; g += 2) {
             const int s = grp, k = g / TL_TILES, t = g - k * TL_TILES, slot = t % 3;
             const size_t ship = (size_t)blockIdx.x + (size_t)k * gridDim.x;
@@ -245,71 +258,96 @@ k_tz_tail(const TlArgs a, const int n_ships) {
             const bool valid = xb < 25 && i < 100;
             mbar_wait(&d3_full[s], (uint32_t)((g >> 1) & 1));
             tc_fence_after();
-            // Ring slot `slot` (tile g - 3's) is free once upconv4's MMAs of tile g - 2 have completed.  A tile of slot 2 also
-            // writes the mirror rows in front of slot 0, which the MMAs of tile g - 2 (slot 0) read: it waits even the first time.
-            if (slot == 2) mbar_wait(&ring_free[2], (uint32_t)((g / 3) & 1));
-            else if (g >= 3) mbar_wait(&ring_free[slot], (uint32_t)(((g / 3) - 1) & 1));
+            if (r == 0) TL_STAMP(g, 0);
             const uint32_t lane_base = tmem_base + ((uint32_t)(gw * 32) << 16);
             const bool var_tile = t == 0 || t == TL_TILES - 1;
             const bool var_warp = (t == 0 && gw == 0) || (t == TL_TILES - 1 && gw < 2);     // warps that hold M rows of i = 0 / 99
             const int var_a = t == 0 ? 0 : 1;
             const bool use_var = var_warp && valid && i == (t == 0 ? 0 : 99);
-            float corner = 0.f;
-            const int cid = (i == 0 ? 0 : 2) + (xb == 0 ? 0 : 1);
-            const bool is_corner = valid && (i == 0 || i == 99) && (xb == 0 || xb == 24);
+            uint4 px[16];                                 // chunk xo * 4 + a * 2 + b = pixel (2i + a, 8 xb + 2 xo + b)
 #pragma unroll
             for (int xo = 0; xo < 4; xo++) {
                 uint32_t rr[32], rv[16];
                 tc_ld32(lane_base + (uint32_t)(s * 128 + xo * 32), rr);
                 if (var_warp) tc_ld16(lane_base + (uint32_t)(TL_TM_D3V + xo * 16), rv);
                 tc_wait_ld();
-                if (xo == 3) {                            // all of this warp's accumulator reads are done: hand the stage back
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) { mbar_arrive(&d3_empty[s]); if (var_tile) mbar_arrive(d3v_empty); }
+                if (var_warp && use_var) {                 // compile-time register indices: no local-memory array
+                    if (var_a == 0) {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) rr[j] = rv[j];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j++) rr[16 + j] = rv[j];
+                    }
                 }
-                if (!valid) continue;
 #pragma unroll
-                for (int ph = 0; ph < 4; ph++) {
-                    const int pa = ph >> 1, pb = ph & 1, q = 2 * xo + pb;
-                    float o[8];
+                for (int ph = 0; ph < 4; ph++)
+                    px[xo * 4 + ph] = make_uint4(pack_relu_bf2(__uint_as_float(rr[ph * 8]), __uint_as_float(rr[ph * 8 + 1])),
+                                                 pack_relu_bf2(__uint_as_float(rr[ph * 8 + 2]), __uint_as_float(rr[ph * 8 + 3])),
+                                                 pack_relu_bf2(__uint_as_float(rr[ph * 8 + 4]), __uint_as_float(rr[ph * 8 + 5])),
+                                                 pack_relu_bf2(__uint_as_float(rr[ph * 8 + 6]), __uint_as_float(rr[ph * 8 + 7])));
+            }
+            tc_fence_before();                            // all of this warp's accumulator reads are done: hand the stage back
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&d3_empty[s]); if (var_tile) mbar_arrive(d3v_empty); }
+            if (r == 0) TL_STAMP(g, 1);
+            // Ring slot `slot` (tile g - 3's) is free once upconv4's MMAs of tile g - 2 have completed.  A tile of slot 2 also
+            // writes the mirror rows in front of slot 0, which the MMAs of tile g - 2 (slot 0) read: it waits even the first time.
+            if (slot == 2) mbar_wait(&ring_free[2], (uint32_t)((g / 3) & 1));
+            else if (g >= 3) mbar_wait(&ring_free[slot], (uint32_t)(((g / 3) - 1) & 1));
+            if (r == 0) TL_STAMP(g, 2);
+            if (valid) {
+                uint4 *dst = ring + TL_MARGIN + 128 * slot + r;
 #pragma unroll
-                    for (int c = 0; c < 8; c++) {
-                        float acc = __uint_as_float(rr[ph * 8 + c]);
-                        if (var_warp) { if (use_var && pa == var_a) acc = __uint_as_float(rv[pb * 8 + c]); }
-                        o[c] = acc + bias[c];
-                    }
-                    const uint4 px = pack_relu_bf8(o);
-                    const int pl = pa * 8 + q;
-                    ring_store(ring, pl, slot, r, px);
-                    if (xb == 0 && q == 0) ring_store(ring, pa * 8 + 7, slot, r - 1, px);            // X = -1 := X = 0
-                    if (xb == 24 && q == 7) ring_store(ring, pa * 8 + 0, slot, r + 1, px);           // X = 200 := X = 199
-                    if (i == 0 && pa == 0) {                                                         // Y = -1 := Y = 0
-                        ring_store(ring, 8 + q, slot, r - TL_P, px);
-                        if (xb == 0 && q == 0) ring_store(ring, 8 + 7, slot, r - TL_P - 1, px);
-                        if (xb == 24 && q == 7) ring_store(ring, 8 + 0, slot, r - TL_P + 1, px);
-                    }
-                    if (i == 99 && pa == 1) {                                                        // Y = 200 := Y = 199
-                        ring_store(ring, q, slot, r + TL_P, px);
-                        if (xb == 0 && q == 0) ring_store(ring, 7, slot, r + TL_P - 1, px);
-                        if (xb == 24 && q == 7) ring_store(ring, 0, slot, r + TL_P + 1, px);
-                    }
-                    if (a.up3_dbg)
-                        *reinterpret_cast<uint4 *>(a.up3_dbg + ((ship * 200 + (size_t)(2 * i + pa)) * 200 + (size_t)(8 * xb + q)) * 8) = px;
-                    if (is_corner && xo == (xb == 0 ? 0 : 3)) {
-                        // corner pixel of the 400 x 400 map: 2 x 2 upconv3 pixels x 8 channels with both borders' weights
+                for (int c = 0; c < 16; c++) dst[(((c >> 1) & 1) * 8 + 2 * (c >> 2) + (c & 1)) * TL_RING] = px[c];
+                if (slot == 2 && r >= 64) {               // mirror in front of slot 0
+#pragma unroll
+                    for (int c = 0; c < 16; c++) dst[(((c >> 1) & 1) * 8 + 2 * (c >> 2) + (c & 1)) * TL_RING - 384] = px[c];
+                }
+                // replicated edges (rare lanes): X = -1 := X = 0, X = 200 := X = 199, Y = -1 := Y = 0, Y = 200 := Y = 199
+                if (xb == 0) { ring_store(ring, 7, slot, r - 1, px[0]); ring_store(ring, 15, slot, r - 1, px[2]); }
+                if (xb == 24) { ring_store(ring, 0, slot, r + 1, px[13]); ring_store(ring, 8, slot, r + 1, px[15]); }
+                if (i == 0) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        if (((c >> 1) & 1) == 0) ring_store(ring, 8 + 2 * (c >> 2) + (c & 1), slot, r - TL_P, px[c]);
+                    if (xb == 0) ring_store(ring, 15, slot, r - TL_P - 1, px[0]);
+                    if (xb == 24) ring_store(ring, 8, slot, r - TL_P + 1, px[13]);
+                }
+                if (i == 99) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        if (((c >> 1) & 1) == 1) ring_store(ring, 2 * (c >> 2) + (c & 1), slot, r + TL_P, px[c]);
+                    if (xb == 0) ring_store(ring, 7, slot, r + TL_P - 1, px[2]);
+                    if (xb == 24) ring_store(ring, 0, slot, r + TL_P + 1, px[15]);
+                }
+                if ((i == 0 || i == 99) && (xb == 0 || xb == 24)) {
+                    // corner pixel of the 400 x 400 map: 2 x 2 upconv3 pixels x 8 channels with both borders' weights
+                    const int cid = (i == 0 ? 0 : 2) + (xb == 0 ? 0 : 1);
+                    float corner = 0.f;
+#pragma unroll
+                    for (int ph = 0; ph < 4; ph++) {
+                        const uint4 lo = px[ph], hi = px[12 + ph];
+                        const uint4 sel = make_uint4(xb == 0 ? lo.x : hi.x, xb == 0 ? lo.y : hi.y, xb == 0 ? lo.z : hi.z, xb == 0 ? lo.w : hi.w);
                         float u3[8];
-                        unpack_bf8(px, u3);
-                        const float *cw = wf + 8 + ((cid * 2 + pa) * 2 + pb) * 8;
+                        unpack_bf8(sel, u3);
+                        const float *cw = wf + 8 + ((cid * 2 + (ph >> 1)) * 2 + (ph & 1)) * 8;
 #pragma unroll
                         for (int c = 0; c < 8; c++) corner += u3[c] * cw[c];
                     }
+                    corners[(k & 1) * 4 + cid] = corner;
+                }
+                if (a.up3_dbg) {
+#pragma unroll
+                    for (int c = 0; c < 16; c++)
+                        *reinterpret_cast<uint4 *>(a.up3_dbg + ((ship * 200 + (size_t)(2 * i + ((c >> 1) & 1))) * 200 +
+                                                                (size_t)(8 * xb + 2 * (c >> 2) + (c & 1))) * 8) = px[c];
                 }
             }
-            if (is_corner) corners[(k & 1) * 4 + cid] = corner;
             fence_async_smem();                           // generic-proxy stores -> visible to the MMAs' operand reads
             __syncwarp();
             if (lane == 0) mbar_arrive(&ring_full[slot]);
+            if (r == 0) TL_STAMP(g, 3);
         }
     } else if (warp < 12) {
         // ------------------------------------------------------------ upconv4 drain + argmax
@@ -325,6 +363,7 @@ k_tz_tail(const TlArgs a, const int n_ships) {
             const bool var_tile = t == 0 || t == TL_TILES - 1;
             mbar_wait(&d4_full[s], (uint32_t)((g >> 1) & 1));
             tc_fence_after();
+            if (l == 0) TL_STAMP(g, 6);
             uint32_t ra[32], rb[32], rc[16], rv[16];
             const uint32_t tm = lane_base + (uint32_t)(TL_TM_D4 + 96 * s);
             tc_ld32(tm, ra);
@@ -398,6 +437,7 @@ k_tz_tail(const TlArgs a, const int n_ships) {
                     atomicMax(vship, key);
                 }
             }
+            if (l == 0) TL_STAMP(g, 7);
             if (t == TL_TILES - 1) {
                 // the ship is complete: the lowest flat index among the threads that hold its maximum
                 named_sync(1, 128);
@@ -426,6 +466,9 @@ k_tz_tail(const TlArgs a, const int n_ships) {
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
+static long long *g_tail_stamps = nullptr;
+extern "C" int ofb_policy_tail_stamps(long long *dev_buf) { g_tail_stamps = dev_buf; return OFB_OK; }
+
 int pol_tz_tail(const ofb_policy *p, const __nv_bfloat16 *up2_pairs, float *ptr_out, int32_t *xy, __nv_bfloat16 *up3_dbg, int n_items,
                 cudaStream_t st) {
     static thread_local SmemAttrCache attr = {};
@@ -440,6 +483,7 @@ int pol_tz_tail(const ofb_policy *p, const __nv_bfloat16 *up2_pairs, float *ptr_
     a.ptr_out = ptr_out;
     a.xy = xy;
     a.up3_dbg = up3_dbg;
+    a.stamps = g_tail_stamps;
     k_tz_tail<<<n_items < n_sm ? n_items : n_sm, TL_NT, TlSmem::total, st>>>(a, n_items);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;

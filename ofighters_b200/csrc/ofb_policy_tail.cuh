@@ -10,11 +10,12 @@
 #define TL_UP2_ITEM_BYTES (3 * TL_UP2_PLANE * 16)
 // the weight blob (bytes): upconv3 B operand [3 u][2 ks][2 chunks][128 n][16 B]; its top / bottom variants
 // [2 sets][2 u][2 ks][2 chunks][64 n][16 B]; upconv4 B operand dy 0: [5 ks][2][48 n], dy 1, 2: [5][2][80], dy 3: [5][2][48];
-// its top / bottom variants [2 sets][2 dy][5 ks][2][16 n]; floats: upconv3 bias [8], corner weights [4][2][2][8]
+// its top / bottom variants [2 sets][2 dy][5 ks][2][16 n]; upconv3's bias operand; floats: upconv3 bias [8], corner weights [4][2][2][8]
 #define TL_OFF_B3 0
 #define TL_OFF_B3V 24576
 #define TL_OFF_B4 (TL_OFF_B3V + 16384)
 #define TL_OFF_B4V (TL_OFF_B4 + 40960)
-#define TL_OFF_AUX (TL_OFF_B4V + 10240)
+#define TL_OFF_BIAS3 (TL_OFF_B4V + 10240) /* upconv3's bias as a B operand [2 chunks][128 n][16 B]: K lane 0 = bias, the rest 0 */
+#define TL_OFF_AUX (TL_OFF_BIAS3 + 4096)
 #define TL_AUX_FLOATS (8 + 128)
 #define TL_WBYTES (TL_OFF_AUX + TL_AUX_FLOATS * 4)
