@@ -455,6 +455,13 @@ extern "C" int ofb_policy_set_engine(ofb_policy *p, int engine) {
         ofb_set_error("ofb_policy_set_engine: bad argument");
         return OFB_E_ARG;
     }
+    if (engine != p->engine) {
+        // the engines keep upconv2's output in different layouts; the entries of the pairs layout that k_heads never writes
+        // (spare K lanes, plane tails) must read as zero for the fused tail
+        OFB_CUDA_CHECK(cudaSetDevice(p->device));
+        OFB_CUDA_CHECK(cudaDeviceSynchronize());
+        OFB_CUDA_CHECK(cudaMemset(p->ws.up2, 0, (size_t)p->max_ships * POL_UP2_ITEM * 2));
+    }
     p->engine = engine;
     return OFB_OK;
 }

@@ -91,17 +91,20 @@ def upsample2x(u, bilinear="tf2"):
     return u
 
 
-def forward(w, image, vector, return_intermediates=False, bilinear="tf2"):
+def forward(w, image, vector, return_intermediates=False, bilinear="tf2", dtype=torch.float32):
     """image [B,400,400,2] (NHWC, ch0 ship_map, ch1 laser_map), vector [B,8]
-    -> act [B,2], ptr [B,400,400]   (qlearnIA_V2.py:123-190)."""
-    x = image.to(torch.float32).permute(0, 3, 1, 2).contiguous()
+    -> act [B,2], ptr [B,400,400]   (qlearnIA_V2.py:123-190).  ``dtype=torch.float64`` runs the same graph in double
+    precision (cross-check against oracle/policy_numpy.py)."""
+    if dtype != torch.float32:
+        w = {k: v.to(dtype) for k, v in w.items()}
+    x = image.to(dtype).permute(0, 3, 1, 2).contiguous()
     inter = {}
     for i in range(1, 5):                                              # :129-147
         x = _conv_bn_relu(x, w, "conv%d" % i, "norm%d" % i)
         x = F.max_pool2d(x, 2)
         inter["pool%d" % i] = x
     flat = x.permute(0, 2, 3, 1).reshape(x.shape[0], -1)               # Flatten() on NHWC  :150
-    cat = torch.cat([vector.to(torch.float32), flat], dim=1)           # [vector, flat]     :154
+    cat = torch.cat([vector.to(dtype), flat], dim=1)                   # [vector, flat]     :154
     h = F.relu(cat @ w["dense1/kernel"] + w["dense1/bias"])            # :155
     inter["dense1"] = h
     d2 = F.relu(h @ w["dense2/kernel"] + w["dense2/bias"])             # :158

@@ -109,7 +109,9 @@ def test_engines_agree_tightly(setup):
     print({k: "%.2e" % v for k, v in errs.items()})
     # bf16 storage can flip one ulp (2^-8 relative) where the fp32 sums differ in the last bits
     assert all(v <= 8e-3 for v in errs.values()), errs
-    assert errs["act"] <= TOL_ENGINES and errs["ptr"] <= 5e-3, errs
+    # the fused tail rounds upconv3's bias to bf16 (it rides the tensor pipe) and takes its border pixels from weight variants,
+    # the CUDA-core twin keeps fp32 biases and corrects the ring: one more bf16 ulp on a few upconv3 pixels
+    assert errs["act"] <= TOL_ENGINES and errs["ptr"] <= 8e-3, errs
 
 
 @pytest.mark.parametrize("scene", ["default", "stress32", "empty", "borders"])

@@ -68,3 +68,45 @@ def test_random_bn_weights_give_finite_outputs():
     img = (torch.rand(2, 400, 400, 2) < 0.01).float()
     act, ptr = po.forward(w, img, torch.rand(2, 8) * 400)
     assert act.shape == (2, 2) and ptr.shape == (2, 400, 400) and torch.isfinite(ptr).all()
+
+
+def test_tf1_legacy_bilinear_kernel():
+    """TF1.x resize_bilinear(align_corners=False): source = dst / 2 -> out[2i] = in[i], out[2i+1] = (in[i] + in[i+1]) / 2,
+    the last odd sample clamps onto in[n-1]."""
+    x = torch.arange(5, dtype=torch.float32).reshape(1, 1, 1, 5) ** 2
+    y = po.upsample2x(x.expand(1, 1, 2, 5).contiguous(), "tf1")
+    v = x[0, 0, 0]
+    assert y.shape == (1, 1, 4, 10)
+    for i in range(5):
+        assert float(y[0, 0, 0, 2 * i]) == float(v[i])
+        assert float(y[0, 0, 0, 2 * i + 1]) == float(0.5 * (v[i] + v[min(i + 1, 4)]))
+    assert torch.equal(y[0, 0, 0], y[0, 0, 3])            # rows: both input rows are equal
+
+
+def test_two_independent_restatements_agree():
+    """oracle/policy_numpy.py (numpy float64, NHWC, explicit index arithmetic, written from the Keras layer semantics) against
+    oracle/policy_torch.py run in float64: every tapped tensor and both outputs within 1e-6 of the tensor's scale, for both
+    bilinear kernels and for fresh as well as randomised BatchNormalization statistics; and the fp32 run the GPU tests use
+    stays within 2e-5 of them.  Removes single-author risk; parity with Keras itself stays unpinned."""
+    from oracle import policy_numpy as pn
+    g = torch.Generator().manual_seed(7)
+    img = (torch.rand((2, 400, 400, 2), generator=g) < 0.02).float()
+    img[0, 100:117, 200:217, 0] = 1.0                       # a blob, like a ship disk
+    vec = torch.rand((2, 8), generator=g) * 400
+    for seed, rbn in ((0, False), (5, True)):
+        w = po.init_weights(seed, randomize_bn=rbn)
+        for mode in ("tf2", "tf1"):
+            a64, p64, i64 = po.forward(w, img, vec, return_intermediates=True, bilinear=mode, dtype=torch.float64)
+            an, pn_, inn = pn.forward({k: v.numpy() for k, v in w.items()}, img.numpy(), vec.numpy(), bilinear=mode,
+                                      return_intermediates=True)
+            for name in ("pool1", "pool2", "pool3", "pool4", "up1", "up2", "up3", "up4"):
+                ref = i64[name].permute(0, 2, 3, 1).numpy()
+                assert np.abs(inn[name] - ref).max() <= 1e-6 * max(1.0, np.abs(ref).max()), (seed, mode, name)
+            assert np.abs(an - a64.numpy()).max() <= 1e-6 * max(1.0, np.abs(an).max())
+            assert np.abs(pn_ - p64.numpy()).max() <= 1e-6 * max(1.0, np.abs(pn_).max())
+            a32, p32 = po.forward(w, img, vec, bilinear=mode)
+            assert np.abs(p32.numpy() - pn_).max() <= 2e-5 * max(1.0, np.abs(pn_).max())
+            assert np.abs(a32.numpy() - an).max() <= 2e-5 * max(1.0, np.abs(an).max())
+            ia, xy = po.decode(a64, p64)
+            dec = pn.decode(an, pn_)
+            assert [(int(ia[b]), (int(xy[b, 0]), int(xy[b, 1]))) for b in range(2)] == dec
