@@ -92,8 +92,12 @@ class ArenasC:
         self._lib.ofo_reset(C.byref(self.st), C.c_void_p(m.ctypes.data if m is not None else None),
                             C.c_void_p(spawn.ctypes.data))
 
-    def raster_bits(self):
-        out = np.zeros((self.N, 2, self.W * self.H // 32), np.uint32)
+    def raster_bits(self, out=None):
+        if out is None:
+            out = np.zeros((self.N, 2, self.W * self.H // 32), np.uint32)
+        else:
+            assert out.shape == (self.N, 2, self.W * self.H // 32) and out.dtype == np.uint32 and out.flags.c_contiguous
+            out[...] = 0
         self._lib.ofo_raster_bits(C.byref(self.st), C.c_void_p(out.ctypes.data))
         return out
 

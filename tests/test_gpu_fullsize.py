@@ -1,8 +1,13 @@
-"""BASELINE.json's full sizes on the B200 box, checked through size-independent properties (the oracles finish such sizes
-in minutes, not seconds): arenas are independent and keyed by global id, so any window of a full-size batch must equal a
-small batch of the same global ids (which the other GPU tests pin to the oracle); discrete counters obey the reference's
-bookkeeping identities; the fused frame kernel equals the two-launch form; the chunked policy forward equals the forward
-of a window."""
+"""BASELINE.json's full sizes on the B200 box.
+
+(1) DIRECT oracle parity: the C restatement (oracle/step_c.c, pinned bit-for-bit to traces of the unmodified reference)
+steps the same 65 536 x 7 default arenas, a 4 096-arena batch across the MAX_TIME restart and the 16 384 x 32 stress batch
+on the host cores (it does ~10^6 env-steps/s on 16 threads), and every frame's ship state, observation heads and laser
+counts -- plus the laser lists and the bit maps at sampled frames -- must be IDENTICAL to what the fused frame kernel
+produced (test_full_size_matches_the_c_oracle_directly).
+(2) Size-independent properties: arenas are independent and keyed by global id, so any window of a full-size batch must
+equal a small batch of the same global ids; discrete counters obey the reference's bookkeeping identities; the fused
+frame kernel equals the two-launch form; the chunked policy forward equals the forward of a window."""
 import numpy as np
 import pytest
 import torch
@@ -86,3 +91,69 @@ def test_chunked_policy_forward_at_configs2_size_equals_window_forwards():
     rows = bg.actions[:, 0, :].long()
     assert torch.equal(rows[:, 0], (ia == 0).long()) and torch.equal(rows[:, 1], (ia == 1).long())
     assert torch.equal(rows[:, 2:], xy.long())
+
+
+SHIP_KEYS = ("time", "n_lasers", "kills", "deaths", "shots", "overflow", "ship_x", "ship_y", "ship_px", "ship_py", "ship_alive",
+             "ship_hull", "ship_reward", "ship_score", "ship_steps")
+
+
+@pytest.mark.parametrize("N,S,kind,lcap,T,heavy_every,restart", [
+    (65536, 7, "random", 0, 41, 8, False),               # configs[2]'s arena batch, frames 0-40
+    (4096, 7, "random", 0, 216, 12, True),                # a batch across the MAX_TIME = 200 restart
+    (16384, 32, "stress", 2048, 30, 10, False)],          # configs[3]: laser lists of up to ~250 entries
+    ids=["65536x7-frames0-40", "4096x7-across-restart", "16384x32-stress-30-frames"])
+def test_full_size_matches_the_c_oracle_directly(N, S, kind, lcap, T, heavy_every, restart):
+    """lib/battleground.py:153-166, lib/laser.py:36-62, lib/ship.py:92-339, lib/observation.py:79-133 for every arena of a
+    BASELINE-sized batch: fused frame kernel (device bots + step + maps in one launch) against oracle/step_c.c on identical
+    Philox-drawn spawns and actions.  Every frame: observation heads (incl. dead ships), all per-arena counters and all
+    per-ship integers.  Every `heavy_every` frames and on the last one (and around the restart): the laser lists (fp64
+    positions bit-for-bit, owners, destroyed flags) and both bit maps of EVERY arena."""
+    from oracle.step_c import ArenasC
+    from ofighters_b200 import ArenaConfig, BatchedBattleground
+    seed, arena0 = 0x0F16, 3
+    bg = BatchedBattleground(N, ships={kind: S}, config=ArenaConfig(laser_cap=lcap), seed=seed, arena0=arena0)
+    c0 = ArenasC(np.zeros((N, S, 2), np.int32))
+    c = ArenasC(c0.random_spawn(seed, 0, arena0), lcap=bg.laser_cap)
+    maps = bg.raster("bits")
+    host_maps = torch.empty(maps.shape, dtype=torch.int32).pin_memory()
+    ref_maps = np.zeros((N, 2, 5000), np.uint32)
+    # `enemy_on_trajectory` (lib/ship.py:179-210) compares libm atan2 / atan values; the kernel decides it with an exact integer
+    # predicate and only within 1e-10 rad of a decision boundary -- where the reference's own answer hangs on libm's last bit --
+    # falls back to the device's atan2, counting the event per arena (SURVEY 7, hard part 2).  An arena that has seen such a
+    # near-tie may legitimately differ by one trajectory reward from a glibc run: it leaves the comparison (and is counted).
+    clean = np.ones(N, bool)
+    flagged_and_different = 0
+    t_ep, ep = 0, 0
+    for t in range(T):
+        if restart and t_ep == 200:
+            ep += 1
+            bg.restart()
+            c.reset(c.random_spawn(seed, ep, arena0))
+            t_ep = 0
+        assert np.array_equal(bg.obs_vec.cpu().numpy()[clean], c.obs_vec()[clean]), "observation heads differ before frame %d" % t
+        bg.frame(maps=maps)
+        c.step(c.bot_actions(kind, seed, t, arena0))
+        t_ep += 1
+        heavy = t % heavy_every == 0 or t == T - 1 or (restart and 198 <= t <= 203)
+        st = bg.state(SHIP_KEYS + ("near_ties",) + (("laser_x", "laser_y", "laser_owner", "laser_destroyed") if heavy else ()))
+        clean &= st["near_ties"].cpu().numpy() == 0
+        for k in SHIP_KEYS:
+            got, ref = st[k].cpu().numpy().astype(np.int64), c.arr[k].astype(np.int64)
+            assert np.array_equal(got[clean], ref[clean]), (k, t)
+        if heavy:
+            live = (np.arange(bg.laser_cap)[None, :] < c.arr["n_lasers"][:, None]) & clean[:, None]
+            for k in ("laser_x", "laser_y", "laser_owner", "laser_destroyed"):
+                got = st[k].cpu().numpy()
+                assert np.array_equal(got[live], c.arr[k][live]), (k, t)          # fp64 positions: bit-for-bit
+            host_maps.copy_(maps)
+            c.raster_bits(out=ref_maps)
+            assert np.array_equal(host_maps.numpy().view(np.uint32)[clean], ref_maps[clean]), "bit maps differ at frame %d" % t
+        if t == T - 1:
+            sc = st["ship_score"].cpu().numpy().astype(np.int64) + st["ship_reward"].cpu().numpy().astype(np.int64)
+            flagged_and_different = int(((sc != c.arr["ship_score"].astype(np.int64) + c.arr["ship_reward"].astype(np.int64)).any(axis=1) & ~clean).sum())
+    n_flagged = int((~clean).sum())
+    assert n_flagged <= max(2, N * T * S * S // 2000000), n_flagged      # measured: < 1 per 10^7 (shooter, target) pairs
+    assert int(c.arr["overflow"].sum()) == 0
+    print("%d x %d %s: %d frames identical to oracle/step_c.c on %d arenas; %d arenas left the comparison after a near-tie of the "
+          "trajectory test, %d of them ended with a different reward than glibc's atan2 gives" % (N, S, kind, T, N - n_flagged, n_flagged,
+                                                                                                  flagged_and_different))
