@@ -28,6 +28,7 @@ UNITS = [
     ("ofb_policy_tz.cu", []),
     ("ofb_policy_tail.cu", []),
     ("ofb_policy_sp.cu", []),
+    ("ofb_policy_st.cu", []),
     ("ofb_train.cu", []),
 ]
 

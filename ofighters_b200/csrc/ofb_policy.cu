@@ -280,6 +280,19 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
         b.resize(16, 0.f);
         up.add(&d.cw[l], pack_taps(w, 8, 8, 16));
         if (l == 0) up.add(&d.c2_tz, pack_toeplitz(w, 8, 8, 8));
+        if (l == 0) {
+            // sparse tensor trunk (ofb_policy_st.cu): one M row per pool2 cell, K = its 4 x 4 pool1 patch (position r * 4 + c) x 8
+            // channels, N = the cell's 2 x 2 conv2 pixels (i * 2 + j) x 8 channels: pixel (i, j) reads patch (r, c) with tap (r - i, c - j)
+            std::vector<__nv_bfloat16> st((size_t)16 * 32 * 8, __float2bfloat16(0.f));
+            for (int pos = 0; pos < 16; pos++)
+                for (int n = 0; n < 32; n++)
+                    for (int ci = 0; ci < 8; ci++) {
+                        const int dy = (pos >> 2) - ((n >> 3) >> 1), dx = (pos & 3) - ((n >> 3) & 1), co = n & 7;
+                        if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
+                        st[((size_t)pos * 32 + n) * 8 + ci] = __float2bfloat16(w[((size_t)(dy * 3 + dx) * 8 + ci) * 8 + co]);
+                    }
+            up.add(&d.c2_st, st);
+        }
         up.add(&d.cb[l], b);
     }
     // dense1: rows 0..7 = vector slice (fp32), rows 8..5007 = flat slice (bf16)
@@ -323,7 +336,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
 }
 
 extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, int max_ships, int flags, ofb_policy **out) {
-    if (!wh || !out || (flags & ~(OFB_POLICY_BILINEAR_TF1 | OFB_POLICY_UNFUSED_TAIL | OFB_POLICY_DENSE_TRUNK))) {
+    if (!wh || !out || (flags & ~(OFB_POLICY_BILINEAR_TF1 | OFB_POLICY_UNFUSED_TAIL | OFB_POLICY_DENSE_TRUNK | OFB_POLICY_CC_SPARSE_TRUNK))) {
         ofb_set_error("ofb_policy_create: bad argument");
         return OFB_E_ARG;
     }
@@ -345,6 +358,7 @@ extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, 
     // 200-frame episode of the default arena, 12 % slower at the laser peak around frame 30 (profiles/r01_step_tuning.md);
     // OFB_POLICY_DENSE_TRUNK=1 selects the dense kernel when the handle is created
     { const char *e = getenv("OFB_POLICY_DENSE_TRUNK"); p->dense_trunk = ((e && *e && *e != '0') || (flags & OFB_POLICY_DENSE_TRUNK)) ? 1 : 0; }
+    { const char *e = getenv("OFB_POLICY_CC_SPARSE_TRUNK"); if (!p->dense_trunk && ((e && *e && *e != '0') || (flags & OFB_POLICY_CC_SPARSE_TRUNK))) p->dense_trunk = 2; }
     // the tail: fused upconv3 -> upconv4 -> argmax by default; the two-kernel form is kept for A / B measurements
     { const char *e = getenv("OFB_POLICY_UNFUSED_TAIL"); p->unfused_tail = ((e && *e && *e != '0') || (flags & OFB_POLICY_UNFUSED_TAIL)) ? 1 : 0; }
     p->bilinear_legacy = (flags & OFB_POLICY_BILINEAR_TF1) ? 1 : 0;
@@ -934,7 +948,9 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     int rc;
     if (tc) {
         { ProfScope ps(p, L_TRUNK12, st);
-          if ((rc = p->dense_trunk ? pol_tz_trunk12(p, maps, ws.pool2, A, st) : pol_sp_trunk12(p, maps, ws.pool2, A, st)) != OFB_OK) return rc; }
+          rc = p->dense_trunk == 1 ? pol_tz_trunk12(p, maps, ws.pool2, A, st)
+                                   : (p->dense_trunk == 2 ? pol_sp_trunk12(p, maps, ws.pool2, A, st) : pol_st_trunk12(p, maps, ws.pool2, A, st));
+          if (rc != OFB_OK) return rc; }
         { ProfScope ps(p, L_CONV3, st); if ((rc = pol_tc_conv_pool(p, 1, ws.pool2, ws.pool3, 100, A, 50 * 50 * 8, st)) != OFB_OK) return rc; }
         { ProfScope ps(p, L_CONV4, st); if ((rc = pol_tc_conv_pool(p, 2, ws.pool3, ws.flat, 50, A, POL_FLAT_PITCH, st)) != OFB_OK) return rc; }
     } else {

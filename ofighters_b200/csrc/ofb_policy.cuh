@@ -45,6 +45,7 @@ struct PolicyDev {
     __nv_bfloat16 *u3_tz;     // block-Toeplitz B operand of upconv3: [3 u][3 k-steps][2 chunks][128 n = xo*32 + phase*8 + cout][8 cin]
     __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
     int bil_legacy;           // 1 = TF1.x legacy bilinear in the scalar border code (the folded operands carry it themselves)
+    __nv_bfloat16 *c2_st;     // conv2 as the B operand of the sparse tensor trunk: [8 k-steps][2 chunks][32 n = px*8 + cout][8 cin]
     uint8_t *tail_blob;       // operands + constants of the fused tail kernel (ofb_policy_tail.cuh: TL_WBYTES)
 };
 
@@ -70,7 +71,7 @@ struct ofb_policy {
     float u4_bias;            // upconv4's (single) bias, host copy
     PolicyDev w;
     PolicyWork ws;
-    int dense_trunk;          // 1 = always the dense tcgen05 trunk12 (k_tz_trunk12); 0 = the sparse one (k_sp_trunk12)
+    int dense_trunk;          // 1 = the dense tcgen05 trunk12 (k_tz_trunk12); 2 = the CUDA-core sparse one (k_sp_trunk12); 0 = sparse + tcgen05 (k_st_trunk12)
     int unfused_tail;         // 1 = upconv3 / upconv4 as two kernels through HBM (k_tz_up3, k_tz_up4); 0 = the fused tail (k_tz_tail)
     int taps;                 // 1 = the fused tail also writes upconv3's output (validation taps)
     int bilinear_legacy;      // 0 = TF2 half-pixel bilinear x2 (default), 1 = TF1.x legacy (asymmetric) UpSampling2D
@@ -94,6 +95,8 @@ int pol_tc_dense1(const ofb_policy *p, const __nv_bfloat16 *flat, float *hflat, 
 int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 // sparse trunk12 on CUDA cores, ofb_policy_sp.cu
 int pol_sp_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
+// sparse trunk12 with conv2 on tensor cores (one MMA row per dirty cell), ofb_policy_st.cu
+int pol_st_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 // fused upconv3 -> upconv4 -> argmax, ofb_policy_tail.cu (input: upconv2's output in the pairs layout)
 int pol_tz_tail(const ofb_policy *p, const __nv_bfloat16 *up2_pairs, float *ptr_out, int32_t *xy, __nv_bfloat16 *up3_dbg, int n_items,
