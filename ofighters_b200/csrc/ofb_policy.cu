@@ -228,6 +228,52 @@ struct Uploader {
     template <class T> void add(T **dst, const std::vector<T> &v) { add(dst, v.data(), v.size()); }
 };
 
+// conv (8 -> 8, 3x3 'same') + bias + ReLU + 2x2 max-pool of a field that only depends on the border class of a pixel --
+// lower[(cy * 3 + cx) * 8 + c] for class (first / middle / last row, first / middle / last column) of an n x n grid -- gives a
+// field of the same kind on the n/2 x n/2 grid.  bf16 weights and activations, fp32 sums, like the kernels.
+static std::vector<__nv_bfloat16> pool_of_class_field(const std::vector<float> &lower, int n, const std::vector<float> &w,
+                                                      const std::vector<float> &b) {
+    std::vector<__nv_bfloat16> up((size_t)9 * 8);
+    auto cls = [&](int i) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); };
+    const int no = n / 2;
+    for (int cy = 0; cy < 3; cy++)
+        for (int cx = 0; cx < 3; cx++)
+            for (int co = 0; co < 8; co++) {
+                float best = 0.f;                          // ReLU
+                for (int i = 0; i < 2; i++)
+                    for (int j = 0; j < 2; j++) {
+                        const int y = 2 * (cy == 0 ? 0 : (cy == 2 ? no - 1 : no / 2)) + i, x = 2 * (cx == 0 ? 0 : (cx == 2 ? no - 1 : no / 2)) + j;
+                        float sacc = b[co];
+                        for (int dy = 0; dy < 3; dy++)
+                            for (int dx = 0; dx < 3; dx++) {
+                                const int yy = y + dy - 1, xx = x + dx - 1;
+                                if (yy < 0 || yy >= n || xx < 0 || xx >= n) continue;
+                                for (int ci = 0; ci < 8; ci++)
+                                    sacc += lower[(size_t)(cls(yy) * 3 + cls(xx)) * 8 + ci] *
+                                            __bfloat162float(__float2bfloat16(w[((size_t)(dy * 3 + dx) * 8 + ci) * 8 + co]));
+                            }
+                        best = std::max(best, sacc);
+                    }
+                up[(size_t)(cy * 3 + cx) * 8 + co] = __float2bfloat16(best);
+            }
+    return up;
+}
+
+// conv (8 -> 8) as the B operand of the sparse tensor trunk (ofb_policy_st.cu): one M row per pooled cell, K = its 4 x 4 input
+// patch (position r * 4 + c) x 8 channels, N = the cell's 2 x 2 conv pixels (i * 2 + j) x 8 channels: pixel (i, j) reads patch
+// entry (r, c) with tap (r - i, c - j).  [16 pos][32 n][8 cin] = [8 k-steps][2 chunks][32][8]
+static std::vector<__nv_bfloat16> pack_cell_patch(const std::vector<float> &w) {
+    std::vector<__nv_bfloat16> st((size_t)16 * 32 * 8, __float2bfloat16(0.f));
+    for (int pos = 0; pos < 16; pos++)
+        for (int n = 0; n < 32; n++)
+            for (int ci = 0; ci < 8; ci++) {
+                const int dy = (pos >> 2) - ((n >> 3) >> 1), dx = (pos & 3) - ((n >> 3) & 1), co = n & 7;
+                if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
+                st[((size_t)pos * 32 + n) * 8 + ci] = __float2bfloat16(w[((size_t)(dy * 3 + dx) * 8 + ci) * 8 + co]);
+            }
+    return st;
+}
+
 // Folds the Keras weights (BN into the convs, bilinear x2 into output phases, operand packs of the tensor-core kernels) into
 // the upload blob.  The blob's layout depends only on the architecture, so ofb_policy_set_weights can rebuild it in place.
 static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, PolicyDev &d, float &u4_bias, int legacy) {
@@ -251,6 +297,7 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
     std::vector<float> bg1(8);                            // pool1 of an empty arena: conv1 of zeros is its bias whatever the padding
     for (int co = 0; co < 8; co++) bg1[co] = __bfloat162float(__float2bfloat16(std::max(b[co], 0.f)));
     up.add(&d.sp_bg1, bg1);
+    std::vector<float> bg_lower;
     for (int l = 0; l < 3; l++) {
         fold_conv(wh->conv[l + 1], 8, 8, w, b);
         if (l == 0) {
@@ -280,18 +327,19 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
         b.resize(16, 0.f);
         up.add(&d.cw[l], pack_taps(w, 8, 8, 16));
         if (l == 0) up.add(&d.c2_tz, pack_toeplitz(w, 8, 8, 8));
-        if (l == 0) {
-            // sparse tensor trunk (ofb_policy_st.cu): one M row per pool2 cell, K = its 4 x 4 pool1 patch (position r * 4 + c) x 8
-            // channels, N = the cell's 2 x 2 conv2 pixels (i * 2 + j) x 8 channels: pixel (i, j) reads patch (r, c) with tap (r - i, c - j)
-            std::vector<__nv_bfloat16> st((size_t)16 * 32 * 8, __float2bfloat16(0.f));
-            for (int pos = 0; pos < 16; pos++)
-                for (int n = 0; n < 32; n++)
-                    for (int ci = 0; ci < 8; ci++) {
-                        const int dy = (pos >> 2) - ((n >> 3) >> 1), dx = (pos & 3) - ((n >> 3) & 1), co = n & 7;
-                        if (dy < 0 || dy > 2 || dx < 0 || dx > 2) continue;
-                        st[((size_t)pos * 32 + n) * 8 + ci] = __float2bfloat16(w[((size_t)(dy * 3 + dx) * 8 + ci) * 8 + co]);
-                    }
-            up.add(&d.c2_st, st);
+        {
+            // sparse tensor trunk: the three 8 -> 8 convolutions as cell-patch operands, and the empty-arena value of a pooled
+            // cell per border class at every level (each level's classes follow from the level below; level 2 = sp_bg2 above)
+            if (l == 0) {
+                bg_lower.assign((size_t)9 * 8, 0.f);
+                for (int k = 0; k < 9; k++)
+                    for (int c = 0; c < 8; c++) bg_lower[(size_t)k * 8 + c] = bg1[c];
+            }
+            const std::vector<__nv_bfloat16> bgu = pool_of_class_field(bg_lower, 200 >> l, w, b);
+            for (size_t k = 0; k < bgu.size(); k++) bg_lower[k] = __bfloat162float(bgu[k]);
+            if (l == 1) up.add(&d.sp_bg3, bgu);
+            if (l == 2) up.add(&d.sp_bg4, bgu);
+            up.add(l == 0 ? &d.c2_st : (l == 1 ? &d.c3_st : &d.c4_st), pack_cell_patch(w));
         }
         up.add(&d.cb[l], b);
     }
@@ -336,7 +384,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
 }
 
 extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, int max_ships, int flags, ofb_policy **out) {
-    if (!wh || !out || (flags & ~(OFB_POLICY_BILINEAR_TF1 | OFB_POLICY_UNFUSED_TAIL | OFB_POLICY_DENSE_TRUNK | OFB_POLICY_CC_SPARSE_TRUNK))) {
+    if (!wh || !out || (flags & ~(OFB_POLICY_BILINEAR_TF1 | OFB_POLICY_UNFUSED_TAIL | OFB_POLICY_DENSE_TRUNK | OFB_POLICY_CC_SPARSE_TRUNK | OFB_POLICY_UNFUSED_TRUNK))) {
         ofb_set_error("ofb_policy_create: bad argument");
         return OFB_E_ARG;
     }
@@ -360,6 +408,7 @@ extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, 
     { const char *e = getenv("OFB_POLICY_DENSE_TRUNK"); p->dense_trunk = ((e && *e && *e != '0') || (flags & OFB_POLICY_DENSE_TRUNK)) ? 1 : 0; }
     { const char *e = getenv("OFB_POLICY_CC_SPARSE_TRUNK"); if (!p->dense_trunk && ((e && *e && *e != '0') || (flags & OFB_POLICY_CC_SPARSE_TRUNK))) p->dense_trunk = 2; }
     // the tail: fused upconv3 -> upconv4 -> argmax by default; the two-kernel form is kept for A / B measurements
+    { const char *e = getenv("OFB_POLICY_UNFUSED_TRUNK"); p->unfused_trunk = ((e && *e && *e != '0') || (flags & OFB_POLICY_UNFUSED_TRUNK)) ? 1 : 0; }
     { const char *e = getenv("OFB_POLICY_UNFUSED_TAIL"); p->unfused_tail = ((e && *e && *e != '0') || (flags & OFB_POLICY_UNFUSED_TAIL)) ? 1 : 0; }
     p->bilinear_legacy = (flags & OFB_POLICY_BILINEAR_TF1) ? 1 : 0;
     p->prof = new std::vector<ProfEvent>();
@@ -386,6 +435,7 @@ extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, 
     const size_t o_fl = take(C * POL_FLAT_PITCH * 2), o_hf = take(C * 100 * 4);
     const size_t o_u2 = take(C * POL_UP2_ITEM * 2), o_u3 = take(C * POL_UP3_ITEM * 2);
     const size_t o_av = take(C * AMAX_PARTS * 4), o_ai = take(C * AMAX_PARTS * 4);
+    const size_t o_sc = take((size_t)ST_MAX_CTAS * ST_SCRATCH_CELLS * 16);
     e = cudaMalloc(&p->work_blob, off);
     if (e != cudaSuccess) {
         ofb_set_error("ofb_policy_create: cudaMalloc(workspace %zu bytes for %d ships) failed: %s", off, max_ships, cudaGetErrorString(e));
@@ -403,6 +453,7 @@ extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, 
     p->ws.up3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_u3);
     p->ws.amax_val = reinterpret_cast<float *>(wb + o_av);
     p->ws.amax_idx = reinterpret_cast<int *>(wb + o_ai);
+    p->ws.st_scratch = reinterpret_cast<uint4 *>(wb + o_sc);
     OFB_CUDA_CHECK(cudaDeviceSynchronize());
     *out = p;
     return OFB_OK;
@@ -946,7 +997,11 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     const int S = A * P;
     const bool tc = p->engine == OFB_ENGINE_TENSOR;
     int rc;
-    if (tc) {
+    if (tc && !p->dense_trunk && !p->unfused_trunk) {
+        // the whole trunk (conv1 .. conv4 + pools) in one sparse kernel: pool2 / pool3 never reach HBM (unless taps are on)
+        ProfScope ps(p, L_TRUNK12, st);
+        if ((rc = pol_st_trunk(p, maps, ws.flat, p->taps ? ws.pool2 : nullptr, p->taps ? ws.pool3 : nullptr, A, st)) != OFB_OK) return rc;
+    } else if (tc) {
         { ProfScope ps(p, L_TRUNK12, st);
           rc = p->dense_trunk == 1 ? pol_tz_trunk12(p, maps, ws.pool2, A, st)
                                    : (p->dense_trunk == 2 ? pol_sp_trunk12(p, maps, ws.pool2, A, st) : pol_st_trunk12(p, maps, ws.pool2, A, st));

@@ -45,7 +45,8 @@ struct PolicyDev {
     __nv_bfloat16 *u3_tz;     // block-Toeplitz B operand of upconv3: [3 u][3 k-steps][2 chunks][128 n = xo*32 + phase*8 + cout][8 cin]
     __nv_bfloat16 *u4_tz;     // block-Toeplitz B operand of upconv4: [3 u][5 k-steps][2 chunks][32 n = xo*4 + phase][8 cin]
     int bil_legacy;           // 1 = TF1.x legacy bilinear in the scalar border code (the folded operands carry it themselves)
-    __nv_bfloat16 *c2_st;     // conv2 as the B operand of the sparse tensor trunk: [8 k-steps][2 chunks][32 n = px*8 + cout][8 cin]
+    __nv_bfloat16 *c2_st, *c3_st, *c4_st;   // conv2..4 as B operands of the sparse tensor trunk: [8 k-steps][2 chunks][32 n = px*8 + cout][8 cin]
+    __nv_bfloat16 *sp_bg3, *sp_bg4;         // [9][8] pool3 / pool4 of an empty arena per border class
     uint8_t *tail_blob;       // operands + constants of the fused tail kernel (ofb_policy_tail.cuh: TL_WBYTES)
 };
 
@@ -57,10 +58,13 @@ struct PolicyWork {
     float *hflat;             // [Ca][100]   dense1 flat-part pre-activation
     __nv_bfloat16 *up2;       // [Cs][POL_UP2_ITEM]: tensor engine = plane layout [4][100][26][8], CUDA-core engine = NHWC [100][100][8]
     __nv_bfloat16 *up3;       // [Cs][POL_UP3_ITEM]: tensor engine = plane layout [8][200][26][8], CUDA-core engine = NHWC [200][200][8]
+    uint4 *st_scratch;        // sparse tensor trunk: per CTA a dense pool2 (100 x 100) + pool3 (50 x 50) image, [ST_MAX_CTAS][12500]
     float *amax_val;          // [Cs][AMAX_PARTS]
     int *amax_idx;            // [Cs][AMAX_PARTS]
 };
 #define AMAX_PARTS 160
+#define ST_MAX_CTAS 320                // upper bound of the sparse tensor trunk's grid (2 CTAs per SM)
+#define ST_SCRATCH_CELLS (100 * 100 + 50 * 50)
 #define POL_UP2_ITEM (4 * 100 * 26 * 8)   // elements of one upconv2 output in plane layout (>= 100*100*8)
 #define POL_UP3_ITEM (8 * 200 * 26 * 8)   // elements of one upconv3 output in plane layout (>= 200*200*8)
 
@@ -72,6 +76,7 @@ struct ofb_policy {
     PolicyDev w;
     PolicyWork ws;
     int dense_trunk;          // 1 = the dense tcgen05 trunk12 (k_tz_trunk12); 2 = the CUDA-core sparse one (k_sp_trunk12); 0 = sparse + tcgen05 (k_st_trunk12)
+    int unfused_trunk;        // 1 = trunk12, conv3, conv4 as three kernels through HBM; 0 = the whole trunk in k_st_trunk
     int unfused_tail;         // 1 = upconv3 / upconv4 as two kernels through HBM (k_tz_up3, k_tz_up4); 0 = the fused tail (k_tz_tail)
     int taps;                 // 1 = the fused tail also writes upconv3's output (validation taps)
     int bilinear_legacy;      // 0 = TF2 half-pixel bilinear x2 (default), 1 = TF1.x legacy (asymmetric) UpSampling2D
@@ -97,6 +102,9 @@ int pol_tz_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out
 int pol_sp_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 // sparse trunk12 with conv2 on tensor cores (one MMA row per dirty cell), ofb_policy_st.cu
 int pol_st_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st);
+// ... the whole trunk (conv1 .. conv4 + pools) in the same kernel: bit maps -> flat [item][POL_FLAT_PITCH]; tap2 / tap3 (optional) receive pool2 / pool3
+int pol_st_trunk(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *flat, __nv_bfloat16 *tap2, __nv_bfloat16 *tap3, int n_items,
+                 cudaStream_t st);
 int pol_tz_up3(const ofb_policy *p, const __nv_bfloat16 *in, __nv_bfloat16 *out, int n_items, cudaStream_t st);
 // fused upconv3 -> upconv4 -> argmax, ofb_policy_tail.cu (input: upconv2's output in the pairs layout)
 int pol_tz_tail(const ofb_policy *p, const __nv_bfloat16 *up2_pairs, float *ptr_out, int32_t *xy, __nv_bfloat16 *up3_dbg, int n_items,

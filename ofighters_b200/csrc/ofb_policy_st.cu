@@ -22,7 +22,7 @@
 #include "ofb_tc_ptx.cuh"
 
 #define ST_NT 256
-#define ST_CAP1 1536                      // dirty pool1 pixels per band
+#define ST_CAP1 1280                      // dirty pool1 pixels per band
 #define ST_CAP2 2048                      // dirty cells per band
 #define ST_RW 13                          // 32-bit words of one 400-bit map row
 
@@ -39,11 +39,14 @@ struct StSmem {
     static constexpr int off_rb1 = off_p2 + 100 * 4 * 4;               // int [201] prefix of dirty pool1 pixels per row
     static constexpr int off_rb2 = off_rb1 + 202 * 4;                  // int [101] prefix of dirty cells per row
     static constexpr int off_b = (off_rb2 + 102 * 4 + 15) & ~15;       // conv2 as B operand [8 ks][2 chunks][32 n][8 k] bf16
-    static constexpr int off_misc = off_b + 8 * 2 * 32 * 16;           // c1 bias [8] f32, conv2 bias [8] f32, bg1 (uint4), band ints [8], scan [16]
-    static constexpr int off_bar = off_misc + 32 + 32 + 16 + 32 + 64;  // 2 mbarriers, tmem slot
+    static constexpr int b_bytes = 8 * 2 * 32 * 16;                    //   x 3: conv2, conv3, conv4
+    static constexpr int off_misc = off_b + 3 * b_bytes;               // c1 bias [8] f32, conv2 bias [8] f32, bg1 (uint4), band ints [8], scan [16],
+    static constexpr int off_bar = off_misc + 32 + 32 + 16 + 32 + 64 + 64;   // conv3 / conv4 bias [16] f32; then 2 mbarriers, tmem slot
     static constexpr int bytes = off_bar + 16 + 16;
 };
-static_assert(StSmem::a_bytes <= 40000 && ST_CAP1 * 16 >= 201 * ST_RW * 4, "k_st_trunk12: aliasing");
+// levels 3 / 4 (fused trunk) keep their bitmaps and lists where V1 was: D3 [50][2], P3 [50][2], L3 u16 [2500], D4 [25], P4 [25], L4 u16 [625]
+static_assert(StSmem::a_bytes <= 40000 && ST_CAP1 * 16 >= 201 * ST_RW * 4 && ST_CAP1 * 16 >= 400 + 400 + 5000 + 128 + 128 + 1280,
+              "k_st_trunk12: aliasing");
 static_assert(StSmem::bytes <= 113 * 1024, "k_st_trunk12: two CTAs per SM");
 
 // 32 bits of map row r starting at column 32 c (rows are 400 bits = 12.5 words: odd rows start mid-word)
@@ -72,8 +75,76 @@ __device__ __forceinline__ uint32_t st_window4(uint32_t wa, uint32_t wb, uint32_
     return st_even_bits(g | (g >> 2) | (g64 << 62));                   // bit 2p': g[2p'] | g[2p' + 2]
 }
 
+// The whole trunk in this kernel (fz.fuse): pool2 and pool3 live in per-CTA dense images in global memory (L2-resident scratch,
+// initialised with the empty-arena values; only the dirty cells are written and put back afterwards), levels 3 and 4 are the
+// same cell-patch MMAs on the dirty cells of D3 = window(D2) / D4 = window(D3), and only `flat` (25 x 25 x 8) reaches HBM.
+struct StFuse {
+    int fuse;
+    __nv_bfloat16 *flat;               // [item][POL_FLAT_PITCH]
+    uint4 *scratch;                    // [gridDim.x][ST_SCRATCH_CELLS]
+    __nv_bfloat16 *tap2, *tap3;        // optional dense copies of pool2 / pool3 (validation taps)
+};
+__device__ __forceinline__ int st_cls(int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); }
+
+// One level of the fused trunk: the `n` cells of `list` (cell = Y * NDST + X on the NDST x NDST output grid) from the dense
+// NSRC x NSRC image `src` (global; written by this CTA before the last barrier -> read through L2), 128 cells per MMA tile.
+template <int NSRC, int NDST>
+__device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list, int n, uint4 *atile, uint32_t b16, const float *bias,
+                                         uint4 *dst, uint32_t tmem_base, uint64_t *mma_bar, uint32_t &n_mma) {
+    const int tid = threadIdx.x, warp = tid >> 5;
+    constexpr uint32_t IDESC = instr_desc(32);
+    for (int tb = 0; tb < n; tb += 128) {
+        const int nb = min(128, n - tb), c = tid & 127;
+        if (c < nb) {
+            const int cell = list[tb + c], Y = cell / NDST, X = cell - Y * NDST;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int pos = (tid >> 7) + 2 * k, qy = 2 * Y - 1 + (pos >> 2), qx = 2 * X - 1 + (pos & 3);
+                uint4 val = make_uint4(0u, 0u, 0u, 0u);                                 // outside the grid: the convolution's zero padding
+                if (qy >= 0 && qy < NSRC && qx >= 0 && qx < NSRC) val = __ldcg(src + qy * NSRC + qx);
+                atile[pos * 128 + c] = val;
+            }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        if (warp == 4) {
+            tc_fence_after();
+            const bool leader = elect_one();
+            const uint32_t a16 = smem_u32(atile) >> 4;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++) {
+                const uint64_t ad = smem_desc(a16 + (uint32_t)(2 * ks * 128), 128, 8);
+                const uint64_t bd = smem_desc(b16 + (uint32_t)(ks * 2 * 32), 32, 8);
+                if (leader) tc_mma(tmem_base, ad, bd, IDESC, ks ? 1u : 0u);
+            }
+            if (leader) tc_commit(mma_bar);
+            __syncwarp();
+        }
+        mbar_wait(mma_bar, n_mma & 1u);
+        n_mma++;
+        tc_fence_after();
+        if (warp < 4) {
+            uint32_t r[32];
+            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
+            tc_wait_ld();
+            if (tid < nb) {
+                float o[8];
+#pragma unroll
+                for (int co = 0; co < 8; co++)
+                    o[co] = fmaxf(fmaxf(__uint_as_float(r[co]), __uint_as_float(r[8 + co])),
+                                  fmaxf(__uint_as_float(r[16 + co]), __uint_as_float(r[24 + co]))) + bias[co];
+                dst[list[tb + tid]] = pack_relu_bf8(o);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(ST_NT, 2)
-k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16 *__restrict__ out, const int n_items, long long *stamps) {
+k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16 *__restrict__ out, const int n_items, long long *stamps,
+             const StFuse fz) {
 #define ST_STAMP(j) do { if (stamps && blockIdx.x == 0 && tid == 0 && it < 8) stamps[it * 16 + (j)] = clock64(); } while (0)
     extern __shared__ __align__(128) uint8_t st_smem[];
     const uint32_t *bs = reinterpret_cast<const uint32_t *>(st_smem + StSmem::off_maps), *bl = bs + POL_WORDS;
@@ -103,8 +174,22 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 8 * 2 * 32; i += ST_NT)
+    for (int i = tid; i < 8 * 2 * 32; i += ST_NT) {
         reinterpret_cast<uint4 *>(st_smem + StSmem::off_b)[i] = reinterpret_cast<const uint4 *>(w.c2_st)[i];
+        if (fz.fuse) {
+            reinterpret_cast<uint4 *>(st_smem + StSmem::off_b + StSmem::b_bytes)[i] = reinterpret_cast<const uint4 *>(w.c3_st)[i];
+            reinterpret_cast<uint4 *>(st_smem + StSmem::off_b + 2 * StSmem::b_bytes)[i] = reinterpret_cast<const uint4 *>(w.c4_st)[i];
+        }
+    }
+    float *b34 = reinterpret_cast<float *>(st_smem + StSmem::off_misc + 176);      // conv3 bias [8], conv4 bias [8]
+    if (tid < 8) { b34[tid] = w.cb[1][tid]; b34[8 + tid] = w.cb[2][tid]; }
+    uint4 *scr2 = fz.scratch + (size_t)blockIdx.x * ST_SCRATCH_CELLS, *scr3 = scr2 + 100 * 100;
+    const uint4 *bg3 = reinterpret_cast<const uint4 *>(w.sp_bg3), *bg4 = reinterpret_cast<const uint4 *>(w.sp_bg4);
+    if (fz.fuse) {                                          // this CTA's pool2 / pool3 images start out as the empty arena's
+        const uint4 *bg2i = reinterpret_cast<const uint4 *>(w.sp_bg2);
+        for (int i = tid; i < 100 * 100; i += ST_NT) scr2[i] = __ldg(bg2i + st_cls(i / 100, 100) * 3 + st_cls(i % 100, 100));
+        for (int i = tid; i < 50 * 50; i += ST_NT) scr3[i] = __ldg(bg3 + st_cls(i / 50, 50) * 3 + st_cls(i % 50, 50));
+    }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -130,7 +215,10 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             mbar_expect_tx(&mbar[0], 2 * POL_WORDS * 4);
             bulk_g2s(st_smem + StSmem::off_maps, src, 2 * POL_WORDS * 4, &mbar[0]);
         }
-        if ((tid & 127) < 100) {                           // a thread keeps its column and walks every other row
+        if (fz.fuse) {                                     // only `flat` leaves the kernel: its empty-arena values first
+            uint4 *fl = reinterpret_cast<uint4 *>(fz.flat + (size_t)a * POL_FLAT_PITCH);
+            for (int i = tid; i < 625; i += ST_NT) fl[i] = __ldg(bg4 + st_cls(i / 25, 25) * 3 + st_cls(i % 25, 25));
+        } else if ((tid & 127) < 100) {                    // a thread keeps its column and walks every other row
             const int X = tid & 127, cx = X == 0 ? 0 : (X == 99 ? 2 : 1);
             const uint4 top = __ldg(bg2 + cx), mid = __ldg(bg2 + 3 + cx), bot = __ldg(bg2 + 6 + cx);
             uint4 *col = reinterpret_cast<uint4 *>(dsta) + X;
@@ -322,7 +410,8 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
                             for (int co = 0; co < 8; co++)
                                 o[co] = fmaxf(fmaxf(__uint_as_float(r[co]), __uint_as_float(r[8 + co])),
                                               fmaxf(__uint_as_float(r[16 + co]), __uint_as_float(r[24 + co]))) + b2[co];
-                            *reinterpret_cast<uint4 *>(dsta + (size_t)l2[tb + tid] * 8) = pack_relu_bf8(o);
+                            if (fz.fuse) scr2[l2[tb + tid]] = pack_relu_bf8(o);
+                            else *reinterpret_cast<uint4 *>(dsta + (size_t)l2[tb + tid] * 8) = pack_relu_bf8(o);
                         }
                     }
                     tc_fence_before();
@@ -334,6 +423,91 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             __syncthreads();                               // everyone has read the band's bounds before thread 0 writes the next ones
         }
         __syncthreads();                                   // nobody still reads this arena's lists / bitmaps
+        if (fz.fuse) {
+            // ---- 5. level 3: D3 = dirty pool3 cells (50 x 50), from D2; lists by popcount prefix (one warp); conv3 on the dirty cells
+            uint32_t *d3 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_v1), *d4 = d3 + 100;
+            int *p3 = reinterpret_cast<int *>(d4 + 32), *p4 = p3 + 100;
+            uint16_t *l3 = reinterpret_cast<uint16_t *>(p4 + 32), *l4 = l3 + 2500;
+            int *cnt = band;                               // n3, n4
+            if (tid < 100) {
+                const int Y = tid >> 1, wd = tid & 1, c0 = 2 * wd;
+                uint32_t wa = 0u, wb = 0u, wc = 0u, we = 0u;
+                for (int r = max(2 * Y - 1, 0); r <= min(2 * Y + 2, 99); r++) {
+                    const uint32_t *dr = d2 + r * 4;
+                    if (c0 > 0) wa |= dr[c0 - 1];
+                    wb |= dr[c0];
+                    wc |= dr[c0 + 1];
+                    if (c0 + 2 < 4) we |= dr[c0 + 2];
+                }
+                uint32_t dd = st_window4(wa, wb, wc, we);
+                if (wd == 1) dd &= 0x3FFFFu;               // 50 cells per row
+                d3[tid] = dd;
+            }
+            __syncthreads();
+            if (tid < 25) {                                // D4 = dirty pool4 cells (25 x 25), from D3
+                uint32_t wb = 0u, wc = 0u;
+                for (int r = max(2 * tid - 1, 0); r <= min(2 * tid + 2, 49); r++) { wb |= d3[r * 2]; wc |= d3[r * 2 + 1]; }
+                d4[tid] = st_window4(0u, wb, wc, 0u) & 0x1FFFFFFu;
+            }
+            __syncthreads();
+            if (warp == 0) {                               // row-major prefixes of D3 (100 words) and D4 (25 words)
+                int run = 0;
+                for (int base = 0; base < 100; base += 32) {
+                    const int i = base + lane, c = i < 100 ? __popc(d3[i]) : 0;
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                    if (i < 100) p3[i] = run + inc - c;
+                    run += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                const int c4 = lane < 25 ? __popc(d4[lane]) : 0;
+                int inc = c4;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                if (lane < 25) p4[lane] = inc - c4;
+                if (lane == 31) { cnt[0] = run; cnt[1] = inc; }
+            }
+            __syncthreads();
+            if (tid < 100) {
+                uint32_t bits = d3[tid];
+                int k = p3[tid];
+                while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; l3[k++] = (uint16_t)((tid >> 1) * 50 + 32 * (tid & 1) + b); }
+            } else if (tid >= 128 && tid < 153) {
+                const int Y = tid - 128;
+                uint32_t bits = d4[Y];
+                int k = p4[Y];
+                while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; l4[k++] = (uint16_t)(Y * 25 + b); }
+            }
+            __syncthreads();
+            const int n3 = cnt[0], n4 = cnt[1];
+            const uint32_t b16 = smem_u32(st_smem + StSmem::off_b) >> 4;
+            st_level<100, 50>(scr2, l3, n3, atile, b16 + StSmem::b_bytes / 16, b34, scr3, tmem_base, &mbar[1], n_mma);
+            // ---- 6. level 4: conv4 on the dirty pool4 cells, straight into `flat` (NHWC flatten = 16 bytes per cell, raster order)
+            st_level<50, 25>(scr3, l4, n4, atile, b16 + 2 * StSmem::b_bytes / 16, b34 + 8,
+                             reinterpret_cast<uint4 *>(fz.flat + (size_t)a * POL_FLAT_PITCH), tmem_base, &mbar[1], n_mma);
+            // ---- 7. validation taps, then the dirty cells of both images go back to their empty-arena values
+            if (fz.tap2) {
+                uint4 *t2 = reinterpret_cast<uint4 *>(fz.tap2) + (size_t)a * 10000, *t3 = reinterpret_cast<uint4 *>(fz.tap3) + (size_t)a * 2500;
+                for (int i = tid; i < 10000; i += ST_NT) t2[i] = __ldcg(scr2 + i);
+                for (int i = tid; i < 2500; i += ST_NT) t3[i] = __ldcg(scr3 + i);
+                __syncthreads();
+            }
+            const uint4 *bg2i = reinterpret_cast<const uint4 *>(w.sp_bg2);
+            for (int i = tid; i < 100 * 4; i += ST_NT) {
+                uint32_t bits = d2[i];
+                const int Y = i >> 2;
+                while (bits) {
+                    const int X = 32 * (i & 3) + __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    scr2[Y * 100 + X] = __ldg(bg2i + st_cls(Y, 100) * 3 + st_cls(X, 100));
+                }
+            }
+            for (int e = tid; e < n3; e += ST_NT) {
+                const int cell = l3[e];
+                scr3[cell] = __ldg(bg3 + st_cls(cell / 50, 50) * 3 + st_cls(cell % 50, 50));
+            }
+            __syncthreads();
+        }
         ST_STAMP(7);
     }
     tc_fence_before();
@@ -344,14 +518,27 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
 static long long *g_st_stamps = nullptr;
 extern "C" int ofb_policy_st_stamps(long long *dev_buf) { g_st_stamps = dev_buf; return OFB_OK; }
 
-int pol_st_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
+static int st_launch(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, const StFuse &fz, cudaStream_t st) {
     if (n_items <= 0) return OFB_OK;
     static thread_local SmemAttrCache attr = {};
     OFB_CUDA_CHECK(attr.ensure(k_st_trunk12, (int)StSmem::bytes));
     int n_sm = 148;
     OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
-    const int grid = n_items < 2 * n_sm ? n_items : 2 * n_sm;
-    k_st_trunk12<<<grid, ST_NT, StSmem::bytes, st>>>(maps, p->w, out, n_items, g_st_stamps);
+    int grid = n_items < 2 * n_sm ? n_items : 2 * n_sm;
+    if (grid > ST_MAX_CTAS) grid = ST_MAX_CTAS;
+    k_st_trunk12<<<grid, ST_NT, StSmem::bytes, st>>>(maps, p->w, out, n_items, g_st_stamps, fz);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
+}
+
+int pol_st_trunk12(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *out, int n_items, cudaStream_t st) {
+    StFuse fz = {};
+    return st_launch(p, maps, out, n_items, fz, st);
+}
+
+int pol_st_trunk(const ofb_policy *p, const uint32_t *maps, __nv_bfloat16 *flat, __nv_bfloat16 *tap2, __nv_bfloat16 *tap3, int n_items,
+                 cudaStream_t st) {
+    StFuse fz = {};
+    fz.fuse = 1; fz.flat = flat; fz.scratch = p->ws.st_scratch; fz.tap2 = tap2; fz.tap3 = tap2 ? tap3 : nullptr;
+    return st_launch(p, maps, nullptr, n_items, fz, st);
 }

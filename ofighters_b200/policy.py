@@ -57,7 +57,7 @@ def _ptr(t):
 
 
 class PolicyB200:
-    def __init__(self, weights, device=None, max_ships=1024, bilinear="tf2", fused_tail=True, dense_trunk=False, cc_sparse_trunk=False):
+    def __init__(self, weights, device=None, max_ships=1024, bilinear="tf2", fused_tail=True, dense_trunk=False, cc_sparse_trunk=False, fused_trunk=True):
         """``bilinear``: "tf2" (half-pixel centres, the default of every TF2 / Keras >= 2.3 UpSampling2D) or "tf1" (the legacy
         asymmetric kernel of TF1.x / standalone Keras 2.2) -- the reference pins no version (requirements.txt:1-2), so the
         choice is the caller's.  ``fused_tail=False`` / ``dense_trunk=True`` select the alternative kernels (measurement aids)."""
@@ -65,8 +65,10 @@ class PolicyB200:
             raise Exception("bilinear must be 'tf2' or 'tf1'")
         self.bilinear = bilinear
         self._flags = (_lib.POLICY_BILINEAR_TF1 if bilinear == "tf1" else 0) | (0 if fused_tail else _lib.POLICY_UNFUSED_TAIL) | \
-            (_lib.POLICY_DENSE_TRUNK if dense_trunk else 0) | (_lib.POLICY_CC_SPARSE_TRUNK if cc_sparse_trunk else 0)
+            (_lib.POLICY_DENSE_TRUNK if dense_trunk else 0) | (_lib.POLICY_CC_SPARSE_TRUNK if cc_sparse_trunk else 0) | (0 if fused_trunk else _lib.POLICY_UNFUSED_TRUNK)
         self.fused_tail = bool(fused_tail) and not os.environ.get("OFB_POLICY_UNFUSED_TAIL", "").strip("0")
+        self.fused_trunk = bool(fused_trunk) and not dense_trunk and not os.environ.get("OFB_POLICY_UNFUSED_TRUNK", "").strip("0") \
+            and not os.environ.get("OFB_POLICY_DENSE_TRUNK", "").strip("0")
         if not torch.cuda.is_available():
             raise _lib.OfbError("PolicyB200 needs a CUDA device: the forward is made of hand-written "
                                 "sm_100a kernels and has no CPU fallback")
@@ -126,7 +128,9 @@ class PolicyB200:
     @property
     def kernels_per_chunk(self):
         """trunk12, conv3, conv4, dense1, heads + the fused tail (or up3, up4, argmax)."""
-        return 6 if (self.fused_tail and self._engine == "tensor") else 8
+        if self._engine != "tensor":
+            return 9
+        return (1 if self.fused_trunk else 3) + 2 + (1 if self.fused_tail else 3)
 
     def set_taps(self, enable):
         """Validation only: the fused tail kernel also writes upconv3's output so that ``debug_tap(6, ...)`` can read it."""
