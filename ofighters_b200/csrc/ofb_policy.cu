@@ -716,13 +716,16 @@ __device__ __forceinline__ void up2_pairs_store(uint8_t *item, int y, int x, uin
     if (y == 99) up2_pairs_store_row(item, 101, x, v);
 }
 
-#define HEADS_SMEM_FLOATS (128 + 64 + 640 + 5000 + 80 + 304 + 32 + 80)
+#define HEADS_G 4                                        // ships per CTA: the dense layers' weights are read once per group
+#define HEADS_SMEM_FLOATS (HEADS_G * (128 + 64 + 640) + 5000 + 80 + 304 + 32 + 80)
 __global__ void __launch_bounds__(256, 3)
-k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, float *__restrict__ act_out,
+k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, int n_ships, float *__restrict__ act_out,
         int *__restrict__ iaction_out, __nv_bfloat16 *__restrict__ up2_out, int plane_layout) {
     extern __shared__ __align__(16) float sm[];
-    float *h = sm, *d2 = h + 128, *u = d2 + 64, *a1 = u + 640, *w1p = a1 + 5000, *w2p = w1p + 80, *w1r = w2p + 304, *w2r = w1r + 32;
-    const int s = blockIdx.x, arena = s / ships_per_arena, tid = threadIdx.x, nt = blockDim.x;
+    float *hh = sm, *dd2 = hh + HEADS_G * 128, *u_all = dd2 + HEADS_G * 64, *a1 = u_all + HEADS_G * 640, *w1p = a1 + 5000, *w2p = w1p + 80,
+          *w1r = w2p + 304, *w2r = w1r + 32;
+    const int s0 = blockIdx.x * HEADS_G, tid = threadIdx.x, nt = blockDim.x;
+    const int ng = min(HEADS_G, n_ships - s0);
     // folded weights: upconv1 [9][1][8] (+ un-phased [9][1][2] for the ring), upconv2 [9][2][16] (+ [9][2][4]), biases
     for (int i = tid; i < 72; i += nt) w1p[i] = w.u1_pw[i];
     for (int i = tid; i < 288; i += nt) w2p[i] = w.u2_pw[i];
@@ -732,35 +735,63 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
     if (tid < 4) w2p[288 + tid] = w.u2_b[tid];
     // dense1: [vector(8), flat(5000)] -> 100, ReLU      (qlearnIA_V2.py:154-155)
     if (tid < 100) {
-        float acc = w.d1_b[tid];
+        float wv[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) acc += vec[(size_t)s * 8 + i] * w.d1_wv[i * 100 + tid];
-        acc += hflat[(size_t)arena * 100 + tid];
-        h[tid] = fmaxf(acc, 0.f);
+        for (int i = 0; i < 8; i++) wv[i] = w.d1_wv[i * 100 + tid];
+        const float bias = w.d1_b[tid];
+#pragma unroll
+        for (int g = 0; g < HEADS_G; g++) {
+            if (g >= ng) break;
+            const int s = s0 + g;
+            float acc = bias;
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc += vec[(size_t)s * 8 + i] * wv[i];
+            acc += hflat[(size_t)(s / ships_per_arena) * 100 + tid];
+            hh[g * 128 + tid] = fmaxf(acc, 0.f);
+        }
     }
     __syncthreads();
-    // dense2 100 -> 50 ReLU (:158); updense1 100 -> 625 ReLU (:163)
+    // dense2 100 -> 50 ReLU (:158); updense1 100 -> 625 ReLU (:163): every weight is loaded once for the group's ships
     for (int j = tid; j < 50 + 625; j += nt) {
+        float acc[HEADS_G];
         if (j < 50) {
-            float acc = w.d2_b[j];
-            for (int i = 0; i < 100; i++) acc += h[i] * w.d2_w[i * 50 + j];
-            d2[j] = fmaxf(acc, 0.f);
+#pragma unroll
+            for (int g = 0; g < HEADS_G; g++) acc[g] = w.d2_b[j];
+            for (int i = 0; i < 100; i++) {
+                const float wt = w.d2_w[i * 50 + j];
+#pragma unroll
+                for (int g = 0; g < HEADS_G; g++) acc[g] += hh[g * 128 + i] * wt;
+            }
+#pragma unroll
+            for (int g = 0; g < HEADS_G; g++) dd2[g * 64 + j] = fmaxf(acc[g], 0.f);
         } else {
             const int q = j - 50;
-            float acc = w.ud_b[q];
+#pragma unroll
+            for (int g = 0; g < HEADS_G; g++) acc[g] = w.ud_b[q];
 #pragma unroll 10
-            for (int i = 0; i < 100; i++) acc += h[i] * w.ud_w[i * 625 + q];
-            u[q] = fmaxf(acc, 0.f);
+            for (int i = 0; i < 100; i++) {
+                const float wt = w.ud_w[i * 625 + q];
+#pragma unroll
+                for (int g = 0; g < HEADS_G; g++) acc[g] += hh[g * 128 + i] * wt;
+            }
+#pragma unroll
+            for (int g = 0; g < HEADS_G; g++) u_all[g * 640 + q] = fmaxf(acc[g], 0.f);
         }
     }
     __syncthreads();
     // output1 50 -> 2 linear (:160) and its argmax (:218, ties -> lowest index)
-    if (tid == 0) {
+    if (tid < ng) {
+        const int s = s0 + tid;
+        const float *d2 = dd2 + tid * 64;
         float a0 = w.o1_b[0], a1v = w.o1_b[1];
         for (int i = 0; i < 50; i++) { a0 += d2[i] * w.o1_w[i * 2]; a1v += d2[i] * w.o1_w[i * 2 + 1]; }
         if (act_out) { act_out[(size_t)s * 2] = a0; act_out[(size_t)s * 2 + 1] = a1v; }
         if (iaction_out) iaction_out[s] = a1v > a0 ? 1 : 0;
     }
+  for (int g = 0; g < ng; g++) {                          // the pointer head's small up-convolutions, one ship at a time
+    const int s = s0 + g;
+    const float *u = u_all + g * 640;
+    if (g > 0) __syncthreads();                           // the previous ship's a1 has been consumed
     // upsampling1 + upconv1 1 -> 2 + BN + ReLU (:166-169): one thread per pixel of the 25 x 25 grid, 4 phases x 2 channels
     for (int p = tid; p < 625; p += nt) {
         const int i = p / 25, j = p % 25;
@@ -861,6 +892,7 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
     if (plane_layout == 1)                                               // halo slots of planes 1..3 (x = 1..3 are interior pixels)
         for (int rp = tid; rp < 3 * 100; rp += nt)
             *reinterpret_cast<uint4 *>(dst + pol_plane100_off(rp % 100, 1 + rp / 100) - 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
 }
 
 // upconv3 (bilinear x2 folded into 4 phases) 4 -> 8 + BN + ReLU: one thread per low-res pixel
@@ -1021,7 +1053,7 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
       if (tc) { if ((rc = pol_tc_dense1(p, ws.flat, ws.hflat, A, st)) != OFB_OK) return rc; }
       else k_dense1_cc<<<(A + D1_ARENAS - 1) / D1_ARENAS, 256, 0, st>>>(ws.flat, w.d1_wf, ws.hflat, A); }
     { ProfScope ps(p, L_HEADS, st);
-      k_heads<<<S, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, act, iact, ws.up2,
+      k_heads<<<(S + HEADS_G - 1) / HEADS_G, 256, HEADS_SMEM_FLOATS * sizeof(float), st>>>(ws.hflat, vec, w, P, S, act, iact, ws.up2,
                                                                  tc ? (p->unfused_tail ? 1 : 2) : 0); }
     if (!xy && !ptr) { OFB_CUDA_CHECK(cudaGetLastError()); return OFB_OK; }
     int parts;
