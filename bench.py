@@ -521,7 +521,10 @@ def _ncu_traffic():
 # Forward layers: kernel, what bounds it, algorithmic bytes and FLOPs per item (Appendix B MACs x 2).
 # "per": the trunk runs once per ARENA, the heads once per policy SHIP.
 POLICY_LAYERS = {
-    "trunk12": dict(kernel_sparse="k_sp_trunk12", kernel_dense="k_tz_trunk12", per="arena", bytes=40000 + 160000, flops=2 * (23.04e6 + 23.04e6)),
+    "trunk12": dict(kernel_sparse="k_st_trunk12 (conv1 + conv2)", kernel_dense="k_tz_trunk12", per="arena", bytes=40000 + 160000,
+                    flops=2 * (23.04e6 + 23.04e6)),
+    # the default: conv1 .. conv4 + pools in one sparse tensor-core kernel, bit maps in, flat (25 x 25 x 8 bf16) out
+    "trunk": dict(kernel="k_st_trunk12 (fused conv1..conv4)", per="arena", bytes=40000 + 10240, flops=2 * (23.04e6 + 23.04e6 + 5.76e6 + 1.44e6)),
     "conv3": dict(kernel="k_tc_conv_pool", per="arena", bytes=160000 + 40000, flops=2 * 5.76e6),
     "conv4": dict(kernel="k_tc_conv_pool", per="arena", bytes=40000 + 10240, flops=2 * 1.44e6),
     "dense1": dict(kernel="k_tc_dense1", per="arena", bytes=10240 + 400, flops=2 * 0.5e6),
@@ -588,6 +591,8 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
             for _ in range(3):
                 policy.forward_argmax(maps, vec, P)
             prof = policy.profile(False)                  # {layer: ms per forward of the whole batch}
+            if getattr(policy, "fused_trunk", False) and prof.get("conv3", 0.0) == 0.0:
+                prof["trunk"] = prof.pop("trunk12")       # the fused trunk kernel is timed in the first slot
             layers = {}
             for k, ms in prof.items():
                 if ms <= 0 or k not in POLICY_LAYERS:
@@ -622,8 +627,9 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
                 "us_per_launch": D["ms"] * 1e3 / chunks,
                 "note": "slowest kernel of the forward at the state the timed region ended in; tcgen05 kernels = algorithmic FLOPs "
                         "(Appendix B MACs x 2) / device time vs the measured bf16 peak; CUDA-core kernels = algorithmic bytes / device "
-                        "time vs the measured HBM peak (k_sp_trunk12 and k_heads are issue-bound, not HBM-bound: the fraction says "
-                        "how far above their HBM floor they run)",
+                        "time vs the measured HBM peak (the sparse trunk k_st_trunk12 and k_heads are issue- / latency-bound, not HBM-bound: "
+                        "the fraction says how far above their HBM floor they run; the fused tail k_tz_tail is bound by shared-memory "
+                        "operand reads of its small-N MMAs, see DESIGN.md)",
                 "whole_forward": {"ms": total, "forwards_per_s": n * P / (total * 1e-3), "policy_ships_per_arena": P,
                                   "dense_equiv_tflops": 155.3e6 * n * P / (total * 1e-3) / 1e12,
                                   "frac_of_peak": 155.3e6 * n * P / (total * 1e-3) / 1e12 / tpeak,
@@ -693,24 +699,98 @@ def _max_over_ranks(dt, world, dev):
     return dt
 
 
+def e2e_policy_tape(wl, dev, steps, world, policy, make_bg):
+    """Policy workloads end to end with HOST buffers: every frame the scripted ships' action rows come from a pinned host tape
+    (H2D on a copy stream), the policy ship's row from the forward on the device, the fused frame kernel steps and rasterises,
+    and the compact int16 [N,S,5] observation heads (ofb_obs_pack_i16) go back to pinned host memory (D2H on a third
+    stream).  Copies of frame k +- 1 overlap the kernels of frame k.  Wall clock, max over ranks."""
+    import torch
+    twin = make_bg()
+    N, S = twin.n_arenas, twin.ships_number
+    T = steps + 3
+    tape = torch.empty((T, N, S, 4), dtype=torch.int16).pin_memory()
+    for k in range(T):                                     # what the device bots would play on a twin of the batch
+        tape[k].copy_(twin.request_actions())
+        twin.generate_frame()
+    del twin
+    torch.cuda.synchronize(dev)
+    main = torch.cuda.current_stream(dev)
+
+    def run(pipelined):
+        bg = make_bg()
+        maps = bg.raster("bits")
+        act_dev = [torch.empty((N, S, 4), dtype=torch.int16, device=dev) for _ in range(2)]
+        obs_dev = [torch.empty((N, S, 5), dtype=torch.int16, device=dev) for _ in range(2)]
+        obs_host = [torch.empty((N, S, 5), dtype=torch.int16).pin_memory() for _ in range(2)]
+        s_h2d, s_d2h = (torch.cuda.Stream(dev), torch.cuda.Stream(dev)) if pipelined else (main, main)
+        ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        ev_frame = [torch.cuda.Event() for _ in range(2)]
+        ev_d2h = [torch.cuda.Event() for _ in range(2)]
+
+        def step(k):
+            i = k & 1
+            if k >= 2:
+                s_h2d.wait_event(ev_frame[i])              # frame k - 2 has consumed act_dev[i]
+            with torch.cuda.stream(s_h2d):
+                act_dev[i].copy_(tape[k], non_blocking=True)
+                ev_h2d[i].record(s_h2d)
+            decided = policy.decide(bg, maps)              # the forward does not need the tape's rows: it overlaps the copy
+            main.wait_event(ev_h2d[i])
+            bg.actions = act_dev[i]
+            policy.write(bg, *decided)                     # the policy ship's row
+            if k >= 2:
+                main.wait_event(ev_d2h[i])                 # obs_dev[i] has left for the host
+            bg.generate_frame(act_dev[i], maps=maps)       # fused step + maps with every row taken from the buffer
+            bg.obs_compact(out=obs_dev[i])
+            ev_frame[i].record(main)
+            s_d2h.wait_event(ev_frame[i])
+            with torch.cuda.stream(s_d2h):
+                obs_host[i].copy_(obs_dev[i], non_blocking=True)
+                ev_d2h[i].record(s_d2h)
+
+        for k in range(3):
+            step(k)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(3, T):
+            step(k)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        st = {k: v.cpu() for k, v in bg.state(("ship_x", "ship_y", "ship_score", "ship_alive", "n_lasers", "kills")).items()}
+        return dt, st, obs_host[(T - 1) & 1].clone(), bg.obs_vec.cpu()
+
+    dt, st, last16, last_obs = run(True)
+    dt = _max_over_ranks(dt, world, dev)
+    _, st_sync, _, _ = run(False)                          # the same tape without the copy streams: the pipelining changes nothing
+    same = all(torch.equal(st[k], st_sync[k]) for k in st)
+    if not same:
+        raise SystemExit("e2e: the pipelined run diverged from the synchronous run of the same tape")
+    if not torch.equal(last16.to(torch.float32), last_obs[..., [0, 2, 3, 6, 7]]):
+        raise SystemExit("e2e: the compact observation heads on the host differ from the device's")
+    return {"unit": "env-steps/s", "h2d_bytes_per_step": N * S * 4 * 2, "d2h_bytes_per_step": N * S * 5 * 2,
+            "value": N * world * steps / dt, "steps": steps, "pipelined_equals_synchronous": same,
+            "what": "pinned host tape int16[N,S,4] of the scripted ships' actions -> H2D (copy stream) | policy forward + action row of the "
+                    "policy ship + fused step + raster (maps stay in HBM) | compact int16[N,S,5] observation heads -> D2H into pinned host "
+                    "memory (third stream), every frame; final state equal to a synchronous run of the same tape; wall clock"}
+
+
 def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
     """Same metric through BatchedBattleground with HOST buffers, wall clock, max over ranks.
 
-    Arena workloads -- headline `value`: replay of a HOST-resident action tape (the reference's record/replay
-    use, lib/record.py:32-39, and the parity mode of the tests): every frame the frame's int16 [N,S,4] actions
-    are copied from pinned host memory, step + raster run, and the float32 [N,S,8] observation heads (what every
-    bot is shown next, incl. its reward) are copied back to pinned host memory.  The copies are pipelined
-    against the kernels of neighbouring frames (ofb_step_host_async).  `closed_loop`: a host-side numpy bot
-    that reads frame k's observations before it sends frame k+1 (synchronous ofb_step_host; the numpy bot's
-    CPU time is inside the timed region).  Policy workloads: closed loop only (the forward dominates)."""
+    Headline `value`: replay of a HOST-resident action tape (the reference's record/replay use, lib/record.py:32-39, and
+    the parity mode of the tests): every frame the frame's int16 [N,S,4] actions are copied from pinned host memory, step +
+    raster run (+ the policy forward for the policy ship of the policy workloads), and the observation heads (what every bot
+    is shown next, incl. its reward; compact int16 [N,S,5] form) are copied back to pinned host memory.  The copies are
+    pipelined against the kernels of neighbouring frames.  `closed_loop`: a host-side numpy bot that reads frame k's
+    observations before it sends frame k+1 (the numpy bot's CPU time is inside the timed region)."""
     import numpy as np
     import torch
     N, S = bg.n_arenas, bg.ships_number
-    out = {"unit": "env-steps/s", "h2d_bytes_per_step": N * S * 4 * 2, "d2h_bytes_per_step": N * S * 8 * 4}
+    out = {"unit": "env-steps/s", "h2d_bytes_per_step": N * S * 4 * 2, "d2h_bytes_per_step": N * S * 5 * 2}
 
     # ---------------- closed loop (host numpy bot inside the timed region)
     rng = np.random.Generator(np.random.PCG64(7))
-    T = 64
+    T = 64 if policy is None else 16
     kind = rng.integers(0, 3, size=(T, N, S), dtype=np.int16)
     newp = rng.integers(0, 401, size=(T, N, S, 2), dtype=np.int16)
     act_host = torch.empty((N, S, 4), dtype=torch.int16).pin_memory()
@@ -748,7 +828,7 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
             obs_host.copy_(bg.obs_vec, non_blocking=True)
             torch.cuda.current_stream(dev).synchronize()
 
-    cl_steps = min(steps, 100 if policy is None else 20)
+    cl_steps = min(steps, 100 if policy is None else 10)
     for k in range(3):
         host_step(k)
     torch.cuda.synchronize(dev)
@@ -757,13 +837,17 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
         host_step(k)
     torch.cuda.synchronize(dev)
     dt = _max_over_ranks(time.perf_counter() - t0, world, dev)
-    closed = {"value": N * world * cl_steps / dt, "steps": cl_steps,
-              "what": "host numpy bot reads frame k's obs heads before sending frame k+1: pinned actions -> H2D -> "
+    closed = {"value": N * world * cl_steps / dt, "steps": cl_steps, "h2d_bytes_per_step": N * S * 4 * 2, "d2h_bytes_per_step": N * S * 8 * 4,
+              "what": "host numpy bot reads frame k's float32 obs heads before sending frame k+1: pinned actions -> H2D -> "
                       "step -> D2H obs heads -> sync -> raster (maps stay in HBM)%s; bot CPU time inside the timed "
                       "region; wall clock" % (" [policy workloads: the forward of the policy ship is queued first and the host "
                                               "bot's numpy runs while it executes; step + raster fused]" if policy is not None else "")}
-    if policy is not None or make_bg is None:
-        out.update(value=closed["value"], steps=cl_steps, what=closed["what"])
+    if make_bg is None:
+        out.update(value=closed["value"], steps=cl_steps, what=closed["what"], d2h_bytes_per_step=N * S * 8 * 4)
+        return out
+    if policy is not None:
+        out = e2e_policy_tape(wl, dev, steps, world, policy, make_bg)
+        out["closed_loop"] = closed
         return out
 
     # ---------------- action-tape replay, pipelined
@@ -777,14 +861,15 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
         tape[k].copy_(twin.request_actions())
         twin.generate_frame()
     want = {k: v.cpu() for k, v in twin.state(("ship_x", "ship_y", "ship_score", "ship_alive", "n_lasers", "kills")).items()}
+    want_obs = twin.obs_vec.cpu()
     del twin
     rep = make_bg()
-    obs2 = [torch.empty((N, S, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
+    obs2 = [torch.empty((N, S, 5), dtype=torch.int16).pin_memory() for _ in range(2)]
 
     def tape_step(k):
         if rep.time >= 200:
             rep.restart()
-        rep.step_host(tape[k], obs2[k & 1], wait=False, maps=maps)   # queue H2D(k) | fused step + raster (k) | D2H(k) on three streams
+        rep.step_host(tape[k], obs2[k & 1], wait=False, maps=maps)   # queue H2D(k) | fused step + raster (k) | pack + D2H(k) on three streams
 
     for k in range(3):
         tape_step(k)
@@ -801,13 +886,13 @@ def e2e_arm(bg, maps, wl, dev, steps, world, policy=None, make_bg=None):
     if not same:
         raise SystemExit("e2e: the tape replay diverged from the device-bot run it was recorded from")
     last = obs2[(steps + 2) & 1]
-    if not bool(torch.isfinite(last).all()):
-        raise SystemExit("e2e: observation heads did not arrive")
+    if not torch.equal(last.to(torch.float32), want_obs[..., [0, 2, 3, 6, 7]]):
+        raise SystemExit("e2e: the observation heads that arrived on the host differ from the recorded run's")
     out.update(value=N * world * steps / dt, steps=steps, closed_loop=closed, replay_matches_device_run=same,
-               what="action-tape replay: pinned host int16[N,S,4] -> H2D -> fused step + raster (ofb_frame_host_async; maps stay in HBM) -> D2H of "
-                    "the float32[N,S,8] obs heads into pinned host memory, every frame; copies on their own streams "
-                    "overlap neighbouring frames' kernels (ofb_step_host_async); final state checked against the "
-                    "device-bot run the tape was recorded from; wall clock")
+               what="action-tape replay: pinned host int16[N,S,4] -> H2D -> fused step + raster (ofb_frame_host_async_i16; maps stay in HBM) -> "
+                    "the 5 non-constant entries of every observation head as int16[N,S,5] (ofb_obs_pack_i16) -> D2H into pinned host "
+                    "memory, every frame; copies on their own streams overlap neighbouring frames' kernels; final state and last heads "
+                    "checked against the device-bot run the tape was recorded from; wall clock")
     return out
 
 

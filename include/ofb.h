@@ -144,6 +144,12 @@ int ofb_frame_bots(ofb_arenas *h, int bot_kind, const uint8_t *kinds_dev, uint64
                    const int16_t *actions_dev, float *obs_out_dev, void *maps_bits_dev, void *stream);
 /* ofb_step_host_async with the fused frame kernel (maps stay in HBM at maps_bits_dev). */
 int ofb_frame_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *maps_bits_dev, void *stream);
+/* The 5 entries of an observation head that are not constants (lib/observation.py:119-123: can_shoot is always 1, dim is the
+ * map's size) as int16 [n_rows, 5] = [reward, pointing.x, pointing.y, pos.x, pos.y] -- all exact small integers: 10 instead of
+ * 32 bytes per ship on the device -> host path. */
+int ofb_obs_pack_i16(const float *obs_dev, int16_t *out_dev, int64_t n_rows, void *stream);
+/* ofb_frame_host_async with the observation heads copied back in that compact form (obs16_host: pinned int16 [N, S, 5]). */
+int ofb_frame_host_async_i16(ofb_arenas *h, const int16_t *actions_host, int16_t *obs16_host, void *maps_bits_dev, void *stream);
 
 /* Debug aid for profiling the fused frame kernel: when buf_dev != NULL every following ofb_frame* launch writes
  * per-warp-role cycle counters to it (int64 [grid][32][8]); NULL switches it off. */

@@ -97,6 +97,10 @@ def load():
     lib.ofb_frame.argtypes = [vp, vp, vp, vp, vp]
     lib.ofb_frame_bots.argtypes = [vp, i32, vp, u64, i64, u32, vp, vp, vp, vp]
     lib.ofb_frame_host_async.argtypes = [vp, vp, vp, vp, vp]
+    lib.ofb_frame_host_async_i16.argtypes = [vp, vp, vp, vp, vp]
+    lib.ofb_frame_host_async_i16.restype = i32
+    lib.ofb_obs_pack_i16.argtypes = [vp, vp, i64, vp]
+    lib.ofb_obs_pack_i16.restype = i32
     lib.ofb_debug_frame_prof.argtypes = [vp]
     lib.ofb_debug_frame_prof.restype = i32
     lib.ofb_debug_last_frame_fused.argtypes = []

@@ -202,16 +202,20 @@ class BatchedBattleground:
                 or actions_host.is_cuda or not actions_host.is_contiguous():
             raise Exception("Invalid actions : expected a contiguous host int16 tensor of shape {}.".format(
                 (self.n_arenas, self.ships_number, 4)))
-        if obs_host is not None and (obs_host.dtype != torch.float32 or obs_host.is_cuda
-                                     or tuple(obs_host.shape) != (self.n_arenas, self.ships_number, 8)):
-            raise Exception("Invalid observation buffer : expected host float32 {}.".format(
-                (self.n_arenas, self.ships_number, 8)))
+        compact = obs_host is not None and obs_host.dtype == torch.int16
+        want = (self.n_arenas, self.ships_number, 5 if compact else 8)
+        if obs_host is not None and (obs_host.dtype not in (torch.float32, torch.int16) or obs_host.is_cuda or tuple(obs_host.shape) != want):
+            raise Exception("Invalid observation buffer : expected host float32 {} or int16 {}.".format(
+                (self.n_arenas, self.ships_number, 8), (self.n_arenas, self.ships_number, 5)))
         obs_p = C.c_void_p(obs_host.data_ptr()) if obs_host is not None else None
+        if compact and (maps is None or wait):
+            raise Exception("compact (int16) observation heads are only supported by the pipelined fused form (wait=False, maps=...).")
         if maps is not None:
             if wait:
                 raise Exception("maps= is only supported by the pipelined form (wait=False).")
-            _lib.check(self._lib.ofb_frame_host_async(self._h, C.c_void_p(actions_host.data_ptr()), obs_p,
-                                                      self._maps_arg(maps), self._stream()))
+            fn = self._lib.ofb_frame_host_async_i16 if compact else self._lib.ofb_frame_host_async
+            _lib.check(fn(self._h, C.c_void_p(actions_host.data_ptr()), obs_p, self._maps_arg(maps), self._stream()))
+            self.launch_count += 1 if compact else 0
         else:
             fn = self._lib.ofb_step_host if wait else self._lib.ofb_step_host_async
             _lib.check(fn(self._h, C.c_void_p(actions_host.data_ptr()), obs_p, self._stream()))
@@ -220,6 +224,25 @@ class BatchedBattleground:
         self.total_steps += 1
         if wait:
             torch.cuda.current_stream(self.device).synchronize()
+
+    OBS_COMPACT_COLUMNS = (0, 2, 3, 6, 7)      # reward, pointing.x, pointing.y, pos.x, pos.y (lib/observation.py:119-123)
+
+    def obs_compact(self, out=None):
+        """The observation heads without their constant entries (can_shoot = 1, dim = the map size), as int16 [N,S,5] on the
+        device: what a host-side consumer needs per frame at 10 instead of 32 bytes per ship."""
+        if out is None:
+            out = torch.empty((self.n_arenas, self.ships_number, 5), dtype=torch.int16, device=self.device)
+        _lib.check(self._lib.ofb_obs_pack_i16(_ptr(self.obs_vec), _ptr(out), self.n_arenas * self.ships_number, self._stream()))
+        self.launch_count += 1
+        return out
+
+    def expand_obs(self, obs16):
+        """Inverse of ``obs_compact`` / the int16 form of ``step_host``: float32 [..., 8] heads in the reference's order."""
+        o = torch.empty(tuple(obs16.shape[:-1]) + (8,), dtype=torch.float32, device=obs16.device)
+        f = obs16.to(torch.float32)
+        o[..., 0], o[..., 1], o[..., 2], o[..., 3] = f[..., 0], 1.0, f[..., 1], f[..., 2]
+        o[..., 4], o[..., 5], o[..., 6], o[..., 7] = float(self.config.width), float(self.config.height), f[..., 3], f[..., 4]
+        return o
 
     def wait_host(self):
         """Block until the copies queued by ``step_host(..., wait=False)`` have completed."""

@@ -317,6 +317,7 @@ int ofb_pipe_init(ofb_arenas *h) {
     for (int i = 0; i < 2; i++) {
         OFB_CUDA_CHECK(cudaMalloc(&h->pipe_actions[i], n_ship * 4 * sizeof(int16_t)));
         OFB_CUDA_CHECK(cudaMalloc(&h->pipe_obs[i], n_ship * 8 * sizeof(float)));
+        OFB_CUDA_CHECK(cudaMalloc(&h->pipe_obs16[i], n_ship * 5 * sizeof(int16_t)));
         OFB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
         OFB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming));
         OFB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_d2h[i], cudaEventDisableTiming));
@@ -337,6 +338,7 @@ extern "C" int ofb_destroy(ofb_arenas *h) {
         for (int i = 0; i < 2; i++) {
             cudaFree(h->pipe_actions[i]);
             cudaFree(h->pipe_obs[i]);
+            cudaFree(h->pipe_obs16[i]);
             cudaEventDestroy(h->ev_h2d[i]);
             cudaEventDestroy(h->ev_step[i]);
             cudaEventDestroy(h->ev_d2h[i]);
@@ -379,6 +381,24 @@ extern "C" int ofb_obs_vec(const ofb_arenas *h, float *out_dev, void *stream) {
     OFB_CUDA_CHECK(cudaSetDevice(h->device));
     const long long nt = h->n_arenas * h->lay.S;
     k_obs_vec<<<nblocks(nt, 256), 256, 0, (cudaStream_t)stream>>>(h->state, h->lay, reinterpret_cast<float4 *>(out_dev), nt);
+    OFB_CUDA_CHECK(cudaGetLastError());
+    return OFB_OK;
+}
+
+// The 5 entries of an observation head that are not constants (lib/observation.py:119-123: can_shoot = 1 and the map's
+// dimensions never change), as int16: [reward, pointing.x, pointing.y, pos.x, pos.y] -- all small exact integers.
+__global__ void k_obs_pack_i16(const float4 *__restrict__ obs, int16_t *__restrict__ out, long long n_rows) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const float4 a = obs[2 * r], b = obs[2 * r + 1];
+    int16_t *o = out + 5 * r;
+    o[0] = (int16_t)a.x; o[1] = (int16_t)a.z; o[2] = (int16_t)a.w; o[3] = (int16_t)b.z; o[4] = (int16_t)b.w;
+}
+
+extern "C" int ofb_obs_pack_i16(const float *obs_dev, int16_t *out_dev, int64_t n_rows, void *stream) {
+    if (!obs_dev || !out_dev || n_rows < 0) { ofb_set_error("ofb_obs_pack_i16: bad argument"); return OFB_E_ARG; }
+    if (n_rows == 0) return OFB_OK;
+    k_obs_pack_i16<<<nblocks(n_rows, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(obs_dev), out_dev, n_rows);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

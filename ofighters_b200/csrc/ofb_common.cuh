@@ -49,6 +49,7 @@ struct ofb_arenas {
     // pipelined host frames (ofb_step_host_async): double-buffered staging, one stream per copy direction
     int16_t *pipe_actions[2];
     float *pipe_obs[2];
+    int16_t *pipe_obs16[2];        // compact observation heads (ofb_obs_pack_i16) of the pipelined host loop
     cudaStream_t s_h2d, s_d2h;
     cudaEvent_t ev_h2d[2], ev_step[2], ev_d2h[2];
     unsigned long long host_seq;

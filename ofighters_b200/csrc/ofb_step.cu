@@ -809,39 +809,50 @@ extern "C" int ofb_step_host(ofb_arenas *h, const int16_t *actions_host, float *
 // obs_host is valid after ofb_host_wait(); actions_host may be reused after the same call (or after the next
 // ofb_step_host_async returns two frames later).
 int ofb_pipe_init(ofb_arenas *h);
-static int step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *maps_bits_dev, void *stream) {
+extern "C" int ofb_obs_pack_i16(const float *obs_dev, int16_t *out_dev, int64_t n_rows, void *stream);
+static int step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, int16_t *obs16_host, void *maps_bits_dev,
+                           void *stream) {
     if (!h || !actions_host) { ofb_set_error("ofb_step_host_async: null argument"); return OFB_E_ARG; }
     int rc = ofb_pipe_init(h);
     if (rc != OFB_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t n_ship = (size_t)h->n_arenas * h->lay.S;
     const int i = (int)(h->host_seq & 1ull);
+    const bool want_obs = obs_host || obs16_host;
     if (h->host_seq >= 2) OFB_CUDA_CHECK(cudaStreamWaitEvent(h->s_h2d, h->ev_step[i], 0));    // step k-2 has read pipe_actions[i]
     OFB_CUDA_CHECK(cudaMemcpyAsync(h->pipe_actions[i], actions_host, n_ship * 4 * sizeof(int16_t), cudaMemcpyHostToDevice, h->s_h2d));
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
     OFB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_h2d[i], 0));
-    if (obs_host && h->host_seq >= 2) OFB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_d2h[i], 0));   // pipe_obs[i] has left
-    rc = maps_bits_dev ? ofb_frame(h, h->pipe_actions[i], obs_host ? h->pipe_obs[i] : nullptr, maps_bits_dev, st)
-                       : ofb_step(h, h->pipe_actions[i], obs_host ? h->pipe_obs[i] : nullptr, st);
+    if (want_obs && h->host_seq >= 2) OFB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_d2h[i], 0));   // pipe_obs[i] has left
+    rc = maps_bits_dev ? ofb_frame(h, h->pipe_actions[i], want_obs ? h->pipe_obs[i] : nullptr, maps_bits_dev, st)
+                       : ofb_step(h, h->pipe_actions[i], want_obs ? h->pipe_obs[i] : nullptr, st);
     if (rc != OFB_OK) return rc;
+    if (obs16_host && (rc = ofb_obs_pack_i16(h->pipe_obs[i], h->pipe_obs16[i], (int64_t)n_ship, st)) != OFB_OK) return rc;
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_step[i], st));
     // ev_d2h[i] also stands for "actions_host of frame k has been consumed" (ofb_host_wait): it must follow the step -- and
     // with it the H2D copy the step waited for -- even when no observation heads are copied back
     OFB_CUDA_CHECK(cudaStreamWaitEvent(h->s_d2h, h->ev_step[i], 0));
     if (obs_host)
         OFB_CUDA_CHECK(cudaMemcpyAsync(obs_host, h->pipe_obs[i], n_ship * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->s_d2h));
+    if (obs16_host)
+        OFB_CUDA_CHECK(cudaMemcpyAsync(obs16_host, h->pipe_obs16[i], n_ship * 5 * sizeof(int16_t), cudaMemcpyDeviceToHost, h->s_d2h));
     OFB_CUDA_CHECK(cudaEventRecord(h->ev_d2h[i], h->s_d2h));
     h->host_seq++;
     return OFB_OK;
 }
 
 extern "C" int ofb_step_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *stream) {
-    return step_host_async(h, actions_host, obs_host, nullptr, stream);
+    return step_host_async(h, actions_host, obs_host, nullptr, nullptr, stream);
 }
 // Same pipeline with the fused frame kernel: the frame's observation maps (OFB_MAP_BITS) are written to maps_bits_dev.
 extern "C" int ofb_frame_host_async(ofb_arenas *h, const int16_t *actions_host, float *obs_host, void *maps_bits_dev, void *stream) {
     if (!maps_bits_dev) { ofb_set_error("ofb_frame_host_async: null maps buffer"); return OFB_E_ARG; }
-    return step_host_async(h, actions_host, obs_host, maps_bits_dev, stream);
+    return step_host_async(h, actions_host, obs_host, nullptr, maps_bits_dev, stream);
+}
+// ... and the observation heads copied back in the compact form of ofb_obs_pack_i16 (10 instead of 32 bytes per ship).
+extern "C" int ofb_frame_host_async_i16(ofb_arenas *h, const int16_t *actions_host, int16_t *obs16_host, void *maps_bits_dev, void *stream) {
+    if (!maps_bits_dev || !obs16_host) { ofb_set_error("ofb_frame_host_async_i16: null buffer"); return OFB_E_ARG; }
+    return step_host_async(h, actions_host, nullptr, obs16_host, maps_bits_dev, stream);
 }
 
 // Block until every copy queued by ofb_step_host_async has completed (obs_host readable, actions_host reusable).

@@ -331,3 +331,55 @@ def test_record_replay_roundtrip(tmp_path):
         assert np.array_equal(r2.obs_host.numpy(), bg.obs_vec.cpu().numpy()), tag
         with pytest.raises(Exception, match="end of record"):
             r2.nextFrame()
+
+
+def test_compact_observation_heads_roundtrip_and_pipelined_host_path():
+    """lib/observation.py:119-123: can_shoot is always 1 and dim is the map size, so the 5 remaining entries of a head (exact
+    small integers) travel to the host as int16 [N,S,5] (ofb_obs_pack_i16): expanding them gives the float32 heads back, and the
+    pipelined host loop (ofb_frame_host_async_i16) delivers exactly what the float32 path delivers."""
+    import torch
+    from ofighters_b200 import BatchedBattleground
+    N, S, T = 300, 7, 24
+    a = BatchedBattleground(N, ships={"random": S}, seed=9)
+    b = BatchedBattleground(N, ships={"external": S}, seed=9)
+    c = BatchedBattleground(N, ships={"external": S}, seed=9)
+    maps_b, maps_c = b.raster("bits"), c.raster("bits")
+    tape = torch.empty((T, N, S, 4), dtype=torch.int16).pin_memory()
+    obs16 = [torch.empty((N, S, 5), dtype=torch.int16).pin_memory() for _ in range(2)]
+    obs32 = [torch.empty((N, S, 8), dtype=torch.float32).pin_memory() for _ in range(2)]
+    for t in range(T):
+        tape[t].copy_(a.request_actions())
+        a.generate_frame()
+        assert torch.equal(a.expand_obs(a.obs_compact()), a.obs_vec)
+    for t in range(T):
+        b.step_host(tape[t], obs16[t & 1], wait=False, maps=maps_b)
+        c.step_host(tape[t], obs32[t & 1], wait=False, maps=maps_c)
+    b.wait_host()
+    c.wait_host()
+    torch.cuda.synchronize()
+    assert torch.equal(b.expand_obs(obs16[(T - 1) & 1]), obs32[(T - 1) & 1])
+    assert torch.equal(obs32[(T - 1) & 1], a.obs_vec.cpu()) and torch.equal(maps_b, maps_c)
+    with pytest.raises(Exception, match="compact"):
+        b.step_host(tape[0], obs16[0], wait=True)
+
+
+def test_host_wait_covers_the_action_copy_without_observation_buffer():
+    """step_host(obs_host=None, wait=False) followed by wait_host() must mean that the pinned action buffer has been
+    consumed: overwriting it afterwards may not change the replay."""
+    import torch
+    from ofighters_b200 import BatchedBattleground
+    N, S, T = 20000, 7, 12
+    src = BatchedBattleground(N, ships={"random": S}, seed=4)
+    tape = []
+    for t in range(T):
+        tape.append(src.request_actions().cpu().clone())
+        src.generate_frame()
+    rep = BatchedBattleground(N, ships={"external": S}, seed=4)
+    buf = torch.empty((N, S, 4), dtype=torch.int16).pin_memory()
+    for t in range(T):
+        buf.copy_(tape[t])
+        rep.step_host(buf, None, wait=False)
+        rep.wait_host()
+        buf.fill_(-1)                                    # scribble over the tape: the frame must already have its copy
+    want, got = src.state(("ship_x", "ship_y", "ship_score", "n_lasers")), rep.state(("ship_x", "ship_y", "ship_score", "n_lasers"))
+    assert all(torch.equal(want[k], got[k]) for k in want)
