@@ -198,7 +198,8 @@ static std::vector<uint8_t> pack_tail(const std::vector<float> &w3, const std::v
                 }
     // ---- floats: upconv3's bias, then the 4 corner pixels' weights [corner][uu][vv][ci] (bf16-rounded like the operands):
     //      the corner reads upconv3 pixels (Y0 + uu, X0 + vv), (Y0, X0) = (0 | 198, 0 | 198)
-    // upconv3's bias rides the tensor pipe: one extra MMA per tile whose A operand is a column of ones (K lane 0)
+    // upconv3's bias rides the tensor pipe: one extra MMA per tile whose A operand is a column of ones (K lane 0).  (Adding it in
+    // the drain instead was measured: 11.0 vs 10.3 ms per 65 536 ships -- the drain's instruction count is what the ring waits for.)
     for (int n = 0; n < 128; n++) put(TL_OFF_BIAS3 + (size_t)n * 16, b3[n & 7]);
     float *aux = reinterpret_cast<float *>(blob.data() + TL_OFF_AUX);
     for (int c = 0; c < 8; c++) aux[c] = b3[c];
@@ -359,8 +360,22 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
     up.add(&d.d2_w, wh->dense2.kernel, 100 * 50); up.add(&d.d2_b, wh->dense2.bias, 50);
     up.add(&d.o1_w, wh->output1.kernel, 50 * 2); up.add(&d.o1_b, wh->output1.bias, 2);
     up.add(&d.ud_w, wh->updense1.kernel, 100 * 625); up.add(&d.ud_b, wh->updense1.bias, 625);
+    // the folded weights per border class of the low-res pixel: on the image's first / last row or column the convolution's zero
+    // padding and the upsampling's edge clamp change the fold (low_border / high_border), not the code that applies it
+    auto class_folds = [&](const std::vector<float> &wc, int cin, int cout) {
+        std::vector<float> all;
+        const PhaseTab tabs[3] = {low_border(PT), PT, high_border(PT)};
+        for (int cy = 0; cy < 3; cy++)
+            for (int cx = 0; cx < 3; cx++) {
+                const std::vector<float> f = fold_phase(wc, cin, cout, tabs[cy], tabs[cx]);
+                all.insert(all.end(), f.begin(), f.end());
+            }
+        return all;
+    };
     fold_conv(wh->upconv[0], 1, 2, w, b); up.add(&d.u1_w, w); up.add(&d.u1_b, b); up.add(&d.u1_pw, fold_phase(w, 1, 2, PT, PT));
+    up.add(&d.u1_cw, class_folds(w, 1, 2));
     fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b); up.add(&d.u2_pw, fold_phase(w, 2, 4, PT, PT));
+    up.add(&d.u2_cw, class_folds(w, 2, 4));
     fold_conv(wh->upconv[2], 4, 8, w, b);
     const std::vector<float> w3 = w, b3 = b;
     up.add(&d.u3_w, w); up.add(&d.u3_b, b);
@@ -820,12 +835,12 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         const int Y = side == 0 ? 0 : (side == 1 ? 49 : (side == 2 ? q + 1 : q)), X = side == 0 ? q : (side == 1 ? q + 1 : (side == 2 ? 0 : 49));
         const int i = Y >> 1, j = X >> 1, ph = (Y & 1) * 2 + (X & 1);
         float o[2] = {w1p[72], w1p[73]};
+        const float *wc = w.u1_cw + ((i == 0 ? 0 : (i == 24 ? 2 : 1)) * 3 + (j == 0 ? 0 : (j == 24 ? 2 : 1))) * 72;    // border-class fold
         for (int t = 0; t < 9; t++) {
             const float x = u[min(max(i + t / 3 - 1, 0), 24) * 25 + min(max(j + t % 3 - 1, 0), 24)];
-            o[0] += x * w1p[t * 8 + ph * 2];
-            o[1] += x * w1p[t * 8 + ph * 2 + 1];
+            o[0] += x * __ldg(wc + t * 8 + ph * 2);
+            o[1] += x * __ldg(wc + t * 8 + ph * 2 + 1);
         }
-        ring_correct_f32<1, 2>(u, 25, Y, X, w1r, o, w.bil_legacy);
         a1[(Y * 50 + X) * 2] = fmaxf(o[0], 0.f);
         a1[(Y * 50 + X) * 2 + 1] = fmaxf(o[1], 0.f);
     }
@@ -872,15 +887,15 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         const int y = side == 0 ? 0 : (side == 1 ? 99 : (side == 2 ? q + 1 : q)), x = side == 0 ? q : (side == 1 ? q + 1 : (side == 2 ? 0 : 99));
         const int i = y >> 1, j = x >> 1, ph = (y & 1) * 2 + (x & 1);
         float c[4] = {w2p[288], w2p[289], w2p[290], w2p[291]};
+        const float *wc = w.u2_cw + ((i == 0 ? 0 : (i == 49 ? 2 : 1)) * 3 + (j == 0 ? 0 : (j == 49 ? 2 : 1))) * 288;   // border-class fold
         for (int t = 0; t < 9; t++) {
             const float2 v = *reinterpret_cast<const float2 *>(a1 + (min(max(i + t / 3 - 1, 0), 49) * 50 + min(max(j + t % 3 - 1, 0), 49)) * 2);
-            const float4 wa = *reinterpret_cast<const float4 *>(w2p + t * 32 + ph * 4), wb = *reinterpret_cast<const float4 *>(w2p + t * 32 + 16 + ph * 4);
+            const float4 wa = __ldg(reinterpret_cast<const float4 *>(wc + t * 32 + ph * 4)), wb = __ldg(reinterpret_cast<const float4 *>(wc + t * 32 + 16 + ph * 4));
             c[0] += v.x * wa.x + v.y * wb.x;
             c[1] += v.x * wa.y + v.y * wb.y;
             c[2] += v.x * wa.z + v.y * wb.z;
             c[3] += v.x * wa.w + v.y * wb.w;
         }
-        ring_correct_f32<2, 4>(a1, 50, y, x, w2r, c, w.bil_legacy);
         if (plane_layout == 2) {
             up2_pairs_store(dstp, y, x, make_uint2(pack_bf2(fmaxf(c[0], 0.f), fmaxf(c[1], 0.f)), pack_bf2(fmaxf(c[2], 0.f), fmaxf(c[3], 0.f))));
             continue;
