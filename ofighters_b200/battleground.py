@@ -285,9 +285,23 @@ class BatchedBattleground:
         self.frame()
         return True
 
+    def watch_scores(self, arena):
+        """``agent.scores`` for one arena (agents/agent.py:59-64: ``Agent.reset`` appends the finished episode's score): from now
+        on every ``restart`` records the scores of that arena's ships first.  Returns the (live) list of int [S] rows."""
+        if not 0 <= arena < self.n_arenas:
+            raise Exception("Invalid arena {} : the batch holds {} arenas.".format(arena, self.n_arenas))
+        if not hasattr(self, "_watched"):
+            self._watched = {}
+        return self._watched.setdefault(int(arena), [])
+
     def restart(self, mask=None, spawn_xy=None):
         """lib/battleground.py:108-117.  ``spawn_xy`` int [N,S,2] replaces the randint draws;
         ``mask`` bool [N] restricts the reset to some arenas (extension for vectorised envs)."""
+        if getattr(self, "_watched", None):
+            sc = self.state(("ship_score",))["ship_score"]
+            for a, rows in self._watched.items():
+                if mask is None or bool(torch.as_tensor(mask)[a]):
+                    rows.append(sc[a].cpu().tolist())
         self.episode += 1
         if spawn_xy is None:
             self._draw_spawn(self.episode)

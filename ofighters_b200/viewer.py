@@ -23,7 +23,7 @@ import torch
 
 
 class ViewerBridge:
-    def __init__(self, bg, arena=0, trainer=None, policy=None, ship=None):
+    def __init__(self, bg, arena=0, trainer=None, policy=None, ship=None, learner=None):
         if not 0 <= arena < bg.n_arenas:
             raise Exception("Invalid arena {} : the batch holds {} arenas.".format(arena, bg.n_arenas))
         self.bg = bg
@@ -35,12 +35,25 @@ class ViewerBridge:
         self.battleground = None
         self.ship_map = self.laser_map = None
         self.act_values = self.ptr_values = None
-        self.scores = []              # agent.scores of the selected ship, one entry per finished episode (agents/agent.py:61)
-        self._episode = 0
+        self.learner = learner        # trainer.QLearner: the producer of .losses / .epsilons (QlearnIA.losses / .epsilons)
+        # agent.scores of the selected arena's ships, one row per finished episode (agents/agent.py:59-64): the batch records them
+        # at every restart for the arenas somebody watches
+        self._scores = bg.watch_scores(self.arena)
+
+    @property
+    def scores(self):
+        """``agent.scores`` of the selected ship: one entry per finished episode (what ScoreGraph plots)."""
+        return [int(row[self.ship]) for row in self._scores]
+
+    @property
+    def epsilons(self):
+        """``QlearnIA.epsilons`` (agents/qlearnIA_V2.py:364): epsilon at every reset, when a learner is attached."""
+        return list(self.learner.epsilons) if self.learner is not None else []
 
     @property
     def losses(self):
-        return list(getattr(self.trainer, "losses", [])) if self.trainer is not None else []
+        """``QlearnIA.losses`` (:382,408): one entry per replay."""
+        return list(self.learner.losses) if self.learner is not None else []
 
     def refresh(self, maps_bits=None, with_pointer_map=True):
         """Pull the selected arena: state snapshot, the two observation maps and (when a policy is attached) the
@@ -58,9 +71,6 @@ class ViewerBridge:
             self.ptr_values = r["ptr"][0].cpu().numpy()
             if self.trainer is not None:              # what ActionMapGraph reads (lib/action_map_graph.py:87-91)
                 self.trainer.act_values, self.trainer.ptr_values = self.act_values, self.ptr_values
-        ep = int(bg.episode)
-        if ep != self._episode:                       # Agent.reset appended the finished episode's score (agents/agent.py:59-64)
-            self._episode = ep
         return self
 
     def observation(self):

@@ -263,6 +263,16 @@ def test_viewer_bridge_streams_one_arena():
     assert o["pos"] == (v.battleground.ships[0].body.x, v.battleground.ships[0].body.y) and o["dim"] == (400, 400)
     with pytest.raises(Exception, match="Invalid arena"):
         ViewerBridge(bg, arena=24)
+    # ScoreGraph / EpsilonGraph inputs: agent.scores gets the finished episode's score at every restart (agents/agent.py:59-64),
+    # QlearnIA.epsilons the trainer's epsilon at every reset (agents/qlearnIA_V2.py:364)
+    from ofighters_b200.trainer import QLearner
+    ql = QLearner(tr, track=2, snapshot=0)
+    v2 = ViewerBridge(bg, arena=5, trainer=tr, learner=ql)
+    assert v2.scores == [] and v2.epsilons == []
+    want = int(bg.state(("ship_score",))["ship_score"][5, 0])
+    bg.restart()
+    ql.reset()
+    assert v2.scores == [want] and v.scores == [] and v2.epsilons == [tr.epsilon.get()] and v2.losses == ql.losses
 
 
 def test_replay_is_the_references_sequence_of_calls():
