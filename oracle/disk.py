@@ -14,7 +14,7 @@ restated:
         ((i - shifted_r)/R)**2 + ((j - shifted_c)/R)**2 < 1  (strict, fp64)
 
 Known-answer vectors from the upstream docstrings are checked in
-tests/test_oracle_disk.py.
+tests/test_oracle.py.
 """
 import numpy as np
 
