@@ -8,6 +8,7 @@
 #include "ofb_common.cuh"
 #include "ofb_policy_dev.cuh"
 #include "ofb_policy_tail.cuh"
+#include "ofb_tc_ptx.cuh"
 
 struct ProfEvent { cudaEvent_t a, b; int layer; };
 enum { L_TRUNK12 = 0, L_CONV3, L_CONV4, L_DENSE1, L_HEADS, L_UP3, L_UP4, L_ARGMAX, L_TAIL, L_COUNT };
@@ -376,6 +377,28 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
     up.add(&d.u1_cw, class_folds(w, 1, 2));
     fold_conv(wh->upconv[1], 2, 4, w, b); up.add(&d.u2_w, w); up.add(&d.u2_b, b); up.add(&d.u2_pw, fold_phase(w, 2, 4, PT, PT));
     up.add(&d.u2_cw, class_folds(w, 2, 4));
+    {
+        // upconv2 as a tcgen05 kind::tf32 B operand (k_heads): [5 k-steps][2 chunks][32 n = xo * 16 + phase * 4 + co][4 lanes = pixel
+        // of the chunk * 2 + cin]; chunk (u, c) of the 3 x 3 chunk neighbourhood holds the input pixels 2k + 2c + p, the output pixel
+        // 2k + xo reads input pixel 2k + xo + v - 1  ->  v = 2c + p - xo + 1
+        const std::vector<float> pf2 = fold_phase(w, 2, 4, PT, PT);
+        std::vector<float> tf((size_t)5 * 2 * 32 * 4, 0.f);
+        for (int idx = 0; idx < 9; idx++) {
+            const int u = idx / 3, c = idx % 3 - 1, j = idx / 2, ch = idx % 2;
+            for (int n = 0; n < 32; n++)
+                for (int l = 0; l < 4; l++) {
+                    const int xo = n >> 4, ph = (n >> 2) & 3, co = n & 3, pp = l >> 1, ci = l & 1, v = 2 * c + pp - xo + 1;
+                    if (v < 0 || v > 2) continue;
+                    float wv = pf2[((size_t)(u * 3 + v) * 2 + ci) * 16 + ph * 4 + co];
+                    uint32_t bits;                        // round to tf32 (10 mantissa bits), nearest even: the pipe would truncate
+                    memcpy(&bits, &wv, 4);
+                    bits = (bits + 0xFFFu + ((bits >> 13) & 1u)) & ~0x1FFFu;
+                    memcpy(&wv, &bits, 4);
+                    tf[(((size_t)j * 2 + ch) * 32 + n) * 4 + l] = wv;
+                }
+        }
+        up.add(&d.u2_tf, tf);
+    }
     fold_conv(wh->upconv[2], 4, 8, w, b);
     const std::vector<float> w3 = w, b3 = b;
     up.add(&d.u3_w, w); up.add(&d.u3_b, b);
@@ -731,14 +754,31 @@ __device__ __forceinline__ void up2_pairs_store(uint8_t *item, int y, int x, uin
     if (y == 99) up2_pairs_store_row(item, 101, x, v);
 }
 
+__device__ __forceinline__ float to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
 #define HEADS_G 4                                        // ships per CTA: the dense layers' weights are read once per group
-#define HEADS_SMEM_FLOATS (HEADS_G * (128 + 64 + 640) + 5000 + 80 + 304 + 32 + 80)
+// upconv1's output a1 (50 x 50 x 2 fp32).  CUDA-core upconv2: plain [y][x][c].  Tensor-core upconv2 (tcgen05 kind::tf32, the product
+// path): a1 IS the A operand -- 16-byte chunks of 2 pixels x 2 channels, 27 chunks per row (one halo chunk on either side) and one
+// halo row above / below, replicated edges: chunk (y + 1) * 27 + (x >> 1) + 1.
+#define HEADS_A1_CHUNKS (52 * 27 + 32)
+#define HEADS_A1_FLOATS (HEADS_A1_CHUNKS * 4)
+#define HEADS_U2_TILES 11                                // 52 * 27 = 1404 M rows (chunks incl. halos) in tiles of 128
+#define HEADS_SMEM_FLOATS (HEADS_G * (128 + 64 + 640) + HEADS_A1_FLOATS + 80 + 304 + 32 + 80 + 5 * 2 * 32 * 4 + 16)
 __global__ void __launch_bounds__(256, 3)
 k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, int n_ships, float *__restrict__ act_out,
         int *__restrict__ iaction_out, __nv_bfloat16 *__restrict__ up2_out, int plane_layout) {
     extern __shared__ __align__(16) float sm[];
-    float *hh = sm, *dd2 = hh + HEADS_G * 128, *u_all = dd2 + HEADS_G * 64, *a1 = u_all + HEADS_G * 640, *w1p = a1 + 5000, *w2p = w1p + 80,
-          *w1r = w2p + 304, *w2r = w1r + 32;
+    float *hh = sm, *dd2 = hh + HEADS_G * 128, *u_all = dd2 + HEADS_G * 64, *a1 = u_all + HEADS_G * 640, *w1p = a1 + HEADS_A1_FLOATS,
+          *w2p = w1p + 80, *w1r = w2p + 304, *w2r = w1r + 32, *u2b = w2r + 80;       // u2b: upconv2 as a tf32 B operand (16-byte aligned)
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(u2b + 5 * 2 * 32 * 4);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(mbar + 1);
+    const bool tc2 = plane_layout == 2;                  // the fused-tail path: upconv2 on the tensor pipe
+    // (the tensor pipe reads fp32 operands as tf32 by dropping mantissa bits: round to nearest here instead)
+#define A1V(v) (tc2 ? to_tf32(v) : (v))
+#define A1I(Y, X) (tc2 ? ((((Y) + 1) * 27 + ((X) >> 1) + 1) * 4 + ((X) & 1) * 2) : (((Y) * 50 + (X)) * 2))
     const int s0 = blockIdx.x * HEADS_G, tid = threadIdx.x, nt = blockDim.x;
     const int ng = min(HEADS_G, n_ships - s0);
     // folded weights: upconv1 [9][1][8] (+ un-phased [9][1][2] for the ring), upconv2 [9][2][16] (+ [9][2][4]), biases
@@ -748,6 +788,21 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
     for (int i = tid; i < 72; i += nt) w2r[i] = w.u2_w[i];
     if (tid < 2) w1p[72 + tid] = w.u1_b[tid];
     if (tid < 4) w2p[288 + tid] = w.u2_b[tid];
+    uint32_t tmem_base = 0;
+    if (tc2) {
+        for (int i = tid; i < 5 * 2 * 32 * 4; i += nt) u2b[i] = w.u2_tf[i];
+        for (int i = 52 * 27 * 4 + tid; i < HEADS_A1_FLOATS; i += nt) a1[i] = 0.f;     // read (against zero weights) by the last rows' pad chunk
+        if (tid == 0) { mbar_init(mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        if (tid < 32) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        tmem_base = *tmem_slot;
+    }
+    uint32_t n_mma = 0;
     // dense1: [vector(8), flat(5000)] -> 100, ReLU      (qlearnIA_V2.py:154-155)
     if (tid < 100) {
         float wv[8];
@@ -825,8 +880,8 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         for (int ph = 0; ph < 4; ph++) {
             const int Y = 2 * i + (ph >> 1), X = 2 * j + (ph & 1);
             if (Y == 0 || Y == 49 || X == 0 || X == 49) continue;        // border ring: second loop
-            a1[(Y * 50 + X) * 2] = fmaxf(acc[ph * 2], 0.f);
-            a1[(Y * 50 + X) * 2 + 1] = fmaxf(acc[ph * 2 + 1], 0.f);
+            a1[A1I(Y, X)] = A1V(fmaxf(acc[ph * 2], 0.f));
+            a1[A1I(Y, X) + 1] = A1V(fmaxf(acc[ph * 2 + 1], 0.f));
         }
     }
 #pragma unroll 1
@@ -841,15 +896,84 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
             o[0] += x * __ldg(wc + t * 8 + ph * 2);
             o[1] += x * __ldg(wc + t * 8 + ph * 2 + 1);
         }
-        a1[(Y * 50 + X) * 2] = fmaxf(o[0], 0.f);
-        a1[(Y * 50 + X) * 2 + 1] = fmaxf(o[1], 0.f);
+        a1[A1I(Y, X)] = A1V(fmaxf(o[0], 0.f));
+        a1[A1I(Y, X) + 1] = A1V(fmaxf(o[1], 0.f));
     }
     __syncthreads();
     // upsampling2 + upconv2 2 -> 4 + BN + ReLU (:172-175): one thread per pixel of the 50 x 50 grid, 4 phases x 4 channels
     // -> bf16 with channels padded to 8
     __nv_bfloat16 *dst = up2_out + (size_t)s * POL_UP2_ITEM;   // plane_layout 1: de-interleaved by x mod 4 for k_tz_up3; 2: pairs for k_tz_tail
     uint8_t *dstp = reinterpret_cast<uint8_t *>(up2_out) + (size_t)s * TL_UP2_ITEM_BYTES;
-    for (int p = tid; p < 2500; p += nt) {
+    if (tc2) {
+        // ---- upconv2 on the tensor pipe (tcgen05 kind::tf32): one M row per 2-pixel chunk of a1, K = the 3 x 3 chunks around it
+        //      (9 x 4 values + 4 lanes of zero weights = 5 K-steps), N = 2 pixels x 4 phases x 4 channels.  a1 is the A operand as it
+        //      lies (its halo chunks / rows replicate the edges); the border ring of the output comes from the scalar loop below.
+        for (int q = tid; q < 100; q += nt) {             // halo chunks of rows 0 .. 49: x = -1 := x = 0, x = 50 := x = 49
+            const int r = 1 + (q >> 1), side = q & 1;
+            const float2 e = *reinterpret_cast<const float2 *>(a1 + A1I(r - 1, side ? 49 : 0));
+            *reinterpret_cast<float4 *>(a1 + (r * 27 + (side ? 26 : 0)) * 4) = make_float4(e.x, e.y, e.x, e.y);
+        }
+        __syncthreads();
+        for (int q = tid; q < 2 * 27; q += nt) {          // halo rows: row -1 := row 0, row 50 := row 49
+            const int side = q / 27, c = q % 27;
+            *reinterpret_cast<float4 *>(a1 + ((side ? 51 : 0) * 27 + c) * 4) = *reinterpret_cast<const float4 *>(a1 + ((side ? 50 : 1) * 27 + c) * 4);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        tc_fence_before();
+        __syncthreads();
+        const uint32_t a16 = smem_u32(a1) >> 4, b16 = smem_u32(u2b) >> 4;
+        constexpr uint32_t ID_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const int warp = tid >> 5, grp = warp >> 2;
+        for (int t0 = 0; t0 < HEADS_U2_TILES; t0 += 4) {  // rounds of 4 tiles = 4 x 32 TMEM columns
+            const int nt4 = min(4, HEADS_U2_TILES - t0);
+            if (warp == 0) {
+                tc_fence_after();
+                const bool leader = elect_one();
+                for (int tt = 0; tt < nt4; tt++) {
+                    const int m0 = 128 * (t0 + tt);
+#pragma unroll
+                    for (int j = 0; j < 5; j++) {
+                        // chunk pairs (u, c): (0,-1)(0,0) | (0,1)(1,-1) | (1,0)(1,1) | (2,-1)(2,0) | (2,1)(pad); offsets in chunks
+                        const int o0 = j == 0 ? -28 : (j == 1 ? -26 : (j == 2 ? 0 : (j == 3 ? 26 : 28)));
+                        const uint32_t lbo = j == 1 ? 25u : 1u;
+                        const uint64_t ad = smem_desc(a16 + (uint32_t)(m0 + o0), lbo, 8);
+                        const uint64_t bd = smem_desc(b16 + (uint32_t)(j * 2 * 32), 32, 8);
+                        if (leader)
+                            asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_base + (uint32_t)(tt * 32)),
+                                         "l"(ad), "l"(bd), "r"(ID_TF32), "r"(j ? 1u : 0u) : "memory");
+                    }
+                }
+                if (leader) tc_commit(mbar);
+                __syncwarp();
+            }
+            mbar_wait(mbar, n_mma & 1u);
+            n_mma++;
+            tc_fence_after();
+            for (int tt = grp; tt < nt4; tt += 2) {       // warps 0-3 drain the even tiles of the round, warps 4-7 the odd ones
+                uint32_t r[32];
+                tc_ld32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(tt * 32), r);
+                tc_wait_ld();
+                const int m = 128 * (t0 + tt) + (tid & 127), ip = m / 27, sc = m - ip * 27;
+                const bool valid = ip >= 1 && ip <= 50 && sc >= 1 && sc <= 25;     // not a halo chunk
+                const int i = ip - 1, k = sc - 1;
+#pragma unroll
+                for (int xo = 0; xo < 2; xo++)
+#pragma unroll
+                    for (int ph = 0; ph < 4; ph++) {
+                        const int y = 2 * i + (ph >> 1), x = 2 * (2 * k + xo) + (ph & 1);
+                        if (!valid || y == 0 || y == 99 || x == 0 || x == 99) continue;      // border ring: scalar loop below
+                        const float *bb = w2p + 288;
+                        const uint2 px = make_uint2(pack_relu_bf2(__uint_as_float(r[xo * 16 + ph * 4]) + bb[0], __uint_as_float(r[xo * 16 + ph * 4 + 1]) + bb[1]),
+                                                    pack_relu_bf2(__uint_as_float(r[xo * 16 + ph * 4 + 2]) + bb[2], __uint_as_float(r[xo * 16 + ph * 4 + 3]) + bb[3]));
+                        up2_pairs_store(dstp, y, x, px);
+                    }
+            }
+            tc_fence_before();
+            __syncthreads();
+        }
+    }
+    for (int p = tid; p < (tc2 ? 0 : 2500); p += nt) {
         const int i = p / 50, j = p % 50;
         float acc[16];
 #pragma unroll
@@ -858,7 +982,7 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         for (int uu = 0; uu < 3; uu++)
 #pragma unroll
             for (int vv = 0; vv < 3; vv++) {
-                const float2 x = *reinterpret_cast<const float2 *>(a1 + (min(max(i + uu - 1, 0), 49) * 50 + min(max(j + vv - 1, 0), 49)) * 2);
+                const float2 x = *reinterpret_cast<const float2 *>(a1 + A1I(min(max(i + uu - 1, 0), 49), min(max(j + vv - 1, 0), 49)));
                 // volatile: keeps the 288 loop-invariant weights in shared memory instead of (spilled) registers
                 const float *wp = w2p + (uu * 3 + vv) * 32;
 #pragma unroll
@@ -889,7 +1013,7 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         float c[4] = {w2p[288], w2p[289], w2p[290], w2p[291]};
         const float *wc = w.u2_cw + ((i == 0 ? 0 : (i == 49 ? 2 : 1)) * 3 + (j == 0 ? 0 : (j == 49 ? 2 : 1))) * 288;   // border-class fold
         for (int t = 0; t < 9; t++) {
-            const float2 v = *reinterpret_cast<const float2 *>(a1 + (min(max(i + t / 3 - 1, 0), 49) * 50 + min(max(j + t % 3 - 1, 0), 49)) * 2);
+            const float2 v = *reinterpret_cast<const float2 *>(a1 + A1I(min(max(i + t / 3 - 1, 0), 49), min(max(j + t % 3 - 1, 0), 49)));
             const float4 wa = __ldg(reinterpret_cast<const float4 *>(wc + t * 32 + ph * 4)), wb = __ldg(reinterpret_cast<const float4 *>(wc + t * 32 + 16 + ph * 4));
             c[0] += v.x * wa.x + v.y * wb.x;
             c[1] += v.x * wa.y + v.y * wb.y;
@@ -908,6 +1032,13 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
         for (int rp = tid; rp < 3 * 100; rp += nt)
             *reinterpret_cast<uint4 *>(dst + pol_plane100_off(rp % 100, 1 + rp / 100) - 8) = make_uint4(0u, 0u, 0u, 0u);
   }
+    if (tc2) {
+        tc_fence_before();
+        __syncthreads();
+        if (tid < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
+    }
+#undef A1I
+#undef A1V
 }
 
 // upconv3 (bilinear x2 folded into 4 phases) 4 -> 8 + BN + ReLU: one thread per low-res pixel

@@ -32,6 +32,7 @@ struct PolicyDev {
     float *u1_w, *u1_b;       // upconv1 [9][1][2], [2]
     float *u2_w, *u2_b;       // upconv2 [9][2][4], [4]
     float *u1_pw, *u2_pw;     // the same, bilinear x2 folded into 4 output phases: [9][1][8], [9][2][16] (n = phase * cout + co)
+    float *u2_tf;             // upconv2 (folded) as a tcgen05 kind::tf32 B operand: [5 k-steps][2 chunks][32 n][4 lanes]
     float *u1_cw, *u2_cw;     // ... per border class of the low-res pixel (first / middle / last row x column): [9 cls][9][1][8], [9 cls][9][2][16]
     // upconv3 / upconv4: bilinear x2 folded into 4 output phases on the low-res grid
     float *u3_w, *u3_b;       // [9][4][8], [8]   un-phased fp32 (ring pixels)

@@ -108,10 +108,12 @@ def test_engines_agree_tightly(setup):
     errs = {k: _relerr(out["tensor"][k], out["cuda_core"][k]) for k in out["tensor"]}
     print({k: "%.2e" % v for k, v in errs.items()})
     # bf16 storage can flip one ulp (2^-8 relative) where the fp32 sums differ in the last bits
-    assert all(v <= 8e-3 for v in errs.values()), errs
-    # the fused tail rounds upconv3's bias to bf16 (it rides the tensor pipe) and takes its border pixels from weight variants,
-    # the CUDA-core twin keeps fp32 biases and corrects the ring: one more bf16 ulp on a few upconv3 pixels
-    assert errs["act"] <= TOL_ENGINES and errs["ptr"] <= 8e-3, errs
+    assert all(v <= 8e-3 for k, v in errs.items() if k != "ptr"), errs
+    # the fused tail rounds upconv3's bias to bf16 (it rides the tensor pipe) and takes its border pixels from weight variants, and
+    # the product path runs upconv2 on the tensor pipe in tf32 while the CUDA-core twin keeps fp32: more bf16 values of upconv2 /
+    # upconv3 land on the neighbouring ulp, which the last two convolutions amplify (measured 1.1e-2; both engines sit at the same
+    # distance from the fp32 oracle, tests/test_gpu_policy_parity.py)
+    assert errs["act"] <= TOL_ENGINES and errs["ptr"] <= 1.5e-2, errs
 
 
 @pytest.mark.parametrize("scene", ["default", "stress32", "empty", "borders"])

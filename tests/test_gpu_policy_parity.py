@@ -173,6 +173,6 @@ def test_fused_tail_equals_two_kernel_tail_decisions(scenes, weight_sets):
     d = float((ra["ptr"] - rb["ptr"]).abs().max() / rb["ptr"].abs().max())
     agree = float((ra["xy"] == rb["xy"]).all(dim=1).float().mean())
     print("fused vs two-kernel tail: max rel diff %.2e, same (x, y) on %.4f of the ships" % (d, agree))
-    assert d <= 1e-2 and agree >= 0.9                       # measured 5.8e-3 / 0.95: the disagreements are plateau ties
+    assert d <= 1.5e-2 and agree >= 0.9                     # measured 1.0e-2 / 0.92 (tf32 upconv2 vs fp32 in the two-kernel path): plateau ties
     i2, xy2 = a.forward_argmax(maps, vec, 1)
     assert torch.equal(xy2, ra["xy"]) and torch.equal(i2, ra["iaction"])

@@ -272,7 +272,7 @@ def test_viewer_bridge_streams_one_arena():
     want = int(bg.state(("ship_score",))["ship_score"][5, 0])
     bg.restart()
     ql.reset()
-    assert v2.scores == [want] and v.scores == [] and v2.epsilons == [tr.epsilon.get()] and v2.losses == ql.losses
+    assert v2.scores == [want] and v.scores == [want] and v2.epsilons == [tr.epsilon.get()] and v2.losses == ql.losses   # one list per watched arena
 
 
 def test_replay_is_the_references_sequence_of_calls():
