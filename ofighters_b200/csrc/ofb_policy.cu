@@ -957,17 +957,27 @@ k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDe
                 const int m = 128 * (t0 + tt) + (tid & 127), ip = m / 27, sc = m - ip * 27;
                 const bool valid = ip >= 1 && ip <= 50 && sc >= 1 && sc <= 25;     // not a halo chunk
                 const int i = ip - 1, k = sc - 1;
+                const float *bb = w2p + 288;
+                // the chunk's 2 x 4 output pixels x = 4k .. 4k+3 of rows y = 2i, 2i+1 in the pairs layout: x = 4k -> plane A entry k
+                // (high half), 4k+1 / 4k+2 -> plane B entry k (one 16-byte store), 4k+3 -> plane A entry k+1 (low half).  The border
+                // ring (rows 0 / 99, columns 0 / 99) and its replicas belong to the scalar loop below.
 #pragma unroll
-                for (int xo = 0; xo < 2; xo++)
+                for (int pa = 0; pa < 2; pa++) {
+                    const int y = 2 * i + pa;
+                    uint2 px[4];
 #pragma unroll
-                    for (int ph = 0; ph < 4; ph++) {
-                        const int y = 2 * i + (ph >> 1), x = 2 * (2 * k + xo) + (ph & 1);
-                        if (!valid || y == 0 || y == 99 || x == 0 || x == 99) continue;      // border ring: scalar loop below
-                        const float *bb = w2p + 288;
-                        const uint2 px = make_uint2(pack_relu_bf2(__uint_as_float(r[xo * 16 + ph * 4]) + bb[0], __uint_as_float(r[xo * 16 + ph * 4 + 1]) + bb[1]),
-                                                    pack_relu_bf2(__uint_as_float(r[xo * 16 + ph * 4 + 2]) + bb[2], __uint_as_float(r[xo * 16 + ph * 4 + 3]) + bb[3]));
-                        up2_pairs_store(dstp, y, x, px);
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t *rv = r + (q >> 1) * 16 + (pa * 2 + (q & 1)) * 4;
+                        px[q] = make_uint2(pack_relu_bf2(__uint_as_float(rv[0]) + bb[0], __uint_as_float(rv[1]) + bb[1]),
+                                           pack_relu_bf2(__uint_as_float(rv[2]) + bb[2], __uint_as_float(rv[3]) + bb[3]));
                     }
+                    if (valid && y != 0 && y != 99) {
+                        uint8_t *e = dstp + ((size_t)(y + 1) * TL_P + k) * 16;
+                        if (k != 0) *reinterpret_cast<uint2 *>(e + 8) = px[0];
+                        *reinterpret_cast<uint4 *>(e + (size_t)TL_UP2_PLANE * 16) = make_uint4(px[1].x, px[1].y, px[2].x, px[2].y);
+                        if (k != 24) *reinterpret_cast<uint2 *>(e + 16) = px[3];
+                    }
+                }
             }
             tc_fence_before();
             __syncthreads();
