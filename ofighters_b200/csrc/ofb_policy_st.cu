@@ -21,7 +21,10 @@
 #include "ofb_policy_dev.cuh"
 #include "ofb_tc_ptx.cuh"
 
-#define ST_NT 256
+#ifndef ST_NT
+#define ST_NT 384
+#endif
+#define ST_NG (ST_NT / 128)                 // gather slices: thread = (cell of the tile, every ST_NG-th patch position)
 #define ST_CAP1 1280                      // dirty pool1 pixels per band
 #define ST_CAP2 2048                      // dirty cells per band
 #define ST_RW 13                          // 32-bit words of one 400-bit map row
@@ -44,9 +47,10 @@ struct StSmem {
     static constexpr int off_bar = off_misc + 32 + 32 + 16 + 32 + 64 + 64;   // conv3 / conv4 bias [16] f32; then 2 mbarriers, tmem slot
     static constexpr int bytes = off_bar + 16 + 16;
 };
-// levels 3 / 4 (fused trunk) keep their bitmaps and lists where V1 was: D3 [50][2], P3 [50][2], L3 u16 [2500], D4 [25], P4 [25], L4 u16 [625]
-static_assert(StSmem::a_bytes <= 40000 && ST_CAP1 * 16 >= 201 * ST_RW * 4 && ST_CAP1 * 16 >= 400 + 400 + 5000 + 128 + 128 + 1280,
-              "k_st_trunk12: aliasing");
+// levels 3 / 4 (fused trunk): D3 [50][2], P3 [50][2], L3 u16 [2500], L4 u16 [625] in the map region behind A tile 0; D4 / P4 [25] in RB1;
+// A tile 1 over V1 .. the head of D1 (D2 survives: the restore reads it)
+static_assert(StSmem::a_bytes <= 40000 && ST_CAP1 * 16 >= 201 * ST_RW * 4 && 40000 - StSmem::a_bytes >= 400 + 400 + 5000 + 1250 &&
+              StSmem::off_v1 + StSmem::a_bytes <= StSmem::off_d2, "k_st_trunk12: aliasing");
 static_assert(StSmem::bytes <= 113 * 1024, "k_st_trunk12: two CTAs per SM");
 
 // 32 bits of map row r starting at column 32 c (rows are 400 bits = 12.5 words: odd rows start mid-word)
@@ -87,27 +91,42 @@ struct StFuse {
 __device__ __forceinline__ int st_cls(int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); }
 
 // One level of the fused trunk: the `n` cells of `list` (cell = Y * NDST + X on the NDST x NDST output grid) from the dense
-// NSRC x NSRC image `src` (global; written by this CTA before the last barrier -> read through L2), 128 cells per MMA tile.
+// NSRC x NSRC image `src` (global; written by this CTA before the last barrier -> read at L2), 128 cells per MMA tile.
+// The A tile is double-buffered (atile0 / atile1): the gather of tile t + 1 -- cp.async straight from L2 into shared memory,
+// every patch position of a thread in flight together -- runs under the MMAs and the drain of tile t.
 template <int NSRC, int NDST>
-__device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list, int n, uint4 *atile, uint32_t b16, const float *bias,
-                                         uint4 *dst, uint32_t tmem_base, uint64_t *mma_bar, uint32_t &n_mma) {
+__device__ __forceinline__ void st_gather(const uint4 *src, const uint16_t *list, int tb, int n, uint4 *atile) {
+    // item = (patch row, cell, column j of the patch): 4 neighbouring lanes fetch the 64 contiguous bytes of one patch row, so a
+    // warp's 32 requests fall into a few 128-byte lines (the L1 -> L2 request rate is what this gather costs)
+    const int nb = min(128, n - tb);
+#pragma unroll
+    for (int k = 0; k < (2048 + ST_NT - 1) / ST_NT; k++) {
+        const int idx = threadIdx.x + ST_NT * k, j = idx & 3, c = (idx >> 2) & 127, row = idx >> 9;
+        if (idx >= 2048) break;
+        if (c < nb) {
+            const int cell = list[tb + c], Y = cell / NDST, X = cell - Y * NDST, qy = 2 * Y - 1 + row, qx = 2 * X - 1 + j;
+            uint4 *dst = atile + (row * 4 + j) * 128 + c;
+            if (qy >= 0 && qy < NSRC && qx >= 0 && qx < NSRC)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + qy * NSRC + qx) : "memory");
+            else
+                *dst = make_uint4(0u, 0u, 0u, 0u);                                      // outside the grid: the convolution's zero padding
+        }
+    }
+}
+template <int NSRC, int NDST>
+__device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list, int n, uint4 *atile0, uint4 *atile1, uint32_t b16,
+                                         const float *bias, uint4 *dst, uint32_t tmem_base, uint64_t *mma_bar, uint32_t &n_mma) {
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr uint32_t IDESC = instr_desc(32);
-    for (int tb = 0; tb < n; tb += 128) {
-        const int nb = min(128, n - tb), c = tid & 127;
-        if (c < nb) {
-            const int cell = list[tb + c], Y = cell / NDST, X = cell - Y * NDST;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const int pos = (tid >> 7) + 2 * k, qy = 2 * Y - 1 + (pos >> 2), qx = 2 * X - 1 + (pos & 3);
-                uint4 val = make_uint4(0u, 0u, 0u, 0u);                                 // outside the grid: the convolution's zero padding
-                if (qy >= 0 && qy < NSRC && qx >= 0 && qx < NSRC) val = __ldcg(src + qy * NSRC + qx);
-                atile[pos * 128 + c] = val;
-            }
-        }
+    if (n > 0) st_gather<NSRC, NDST>(src, list, 0, n, atile0);
+    int buf = 0;
+    for (int tb = 0; tb < n; tb += 128, buf ^= 1) {
+        const int nb = min(128, n - tb);
+        uint4 *atile = buf ? atile1 : atile0;
+        asm volatile("cp.async.wait_all;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
-        __syncthreads();
+        __syncthreads();                                   // tile tb is in shared memory; the previous tile's drain has left TMEM
         if (warp == 4) {
             tc_fence_after();
             const bool leader = elect_one();
@@ -121,6 +140,8 @@ __device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list,
             if (leader) tc_commit(mma_bar);
             __syncwarp();
         }
+        // the other buffer was last read by the MMAs of the tile before this one, whose completion every thread has waited for
+        if (tb + 128 < n) st_gather<NSRC, NDST>(src, list, tb + 128, n, buf ? atile0 : atile1);
         mbar_wait(mma_bar, n_mma & 1u);
         n_mma++;
         tc_fence_after();
@@ -137,9 +158,9 @@ __device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list,
                 dst[list[tb + tid]] = pack_relu_bf8(o);
             }
         }
-        tc_fence_before();
-        __syncthreads();
     }
+    tc_fence_before();
+    __syncthreads();                                       // the level's image is complete; TMEM and both A tiles are free
 }
 
 __global__ void __launch_bounds__(ST_NT, 2)
@@ -369,8 +390,9 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
                     if (c < nb) {
                         const int cell = l2[tb + c], Y = cell / 100, X = cell - Y * 100;
 #pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            const int pos = (tid >> 7) + 2 * k, qy = 2 * Y - 1 + (pos >> 2), qx = 2 * X - 1 + (pos & 3);
+                        for (int k = 0; k < (16 + ST_NG - 1) / ST_NG; k++) {
+                            const int pos = (tid >> 7) + ST_NG * k, qy = 2 * Y - 1 + (pos >> 2), qx = 2 * X - 1 + (pos & 3);
+                            if (pos >= 16) break;
                             uint4 val = make_uint4(0u, 0u, 0u, 0u);                     // outside the grid: conv2's zero padding
                             if (qy >= 0 && qy < 200 && qx >= 0 && qx < 200) {
                                 const uint32_t *dr = d1 + qy * 7;
@@ -425,9 +447,14 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
         __syncthreads();                                   // nobody still reads this arena's lists / bitmaps
         if (fz.fuse) {
             // ---- 5. level 3: D3 = dirty pool3 cells (50 x 50), from D2; lists by popcount prefix (one warp); conv3 on the dirty cells
-            uint32_t *d3 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_v1), *d4 = d3 + 100;
-            int *p3 = reinterpret_cast<int *>(d4 + 32), *p4 = p3 + 100;
-            uint16_t *l3 = reinterpret_cast<uint16_t *>(p4 + 32), *l4 = l3 + 2500;
+            // (shared memory in levels 3 / 4: A tile 0 = the first 32 KB of the map region, bitmaps and lists in the 7 232 B after
+            //  it, A tile 1 over V1 / L1 / L2 / the head of D1 -- all dead by now; D2 stays for the restore)
+            uint32_t *d3 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_maps + StSmem::a_bytes);
+            int *p3 = reinterpret_cast<int *>(d3 + 100);
+            uint16_t *l3 = reinterpret_cast<uint16_t *>(p3 + 100), *l4 = l3 + 2500;
+            uint32_t *d4 = reinterpret_cast<uint32_t *>(rb1);
+            int *p4 = rb1 + 32;
+            uint4 *atile1 = reinterpret_cast<uint4 *>(st_smem + StSmem::off_v1);
             int *cnt = band;                               // n3, n4
             if (tid < 100) {
                 const int Y = tid >> 1, wd = tid & 1, c0 = 2 * wd;
@@ -481,9 +508,9 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             __syncthreads();
             const int n3 = cnt[0], n4 = cnt[1];
             const uint32_t b16 = smem_u32(st_smem + StSmem::off_b) >> 4;
-            st_level<100, 50>(scr2, l3, n3, atile, b16 + StSmem::b_bytes / 16, b34, scr3, tmem_base, &mbar[1], n_mma);
+            st_level<100, 50>(scr2, l3, n3, atile, atile1, b16 + StSmem::b_bytes / 16, b34, scr3, tmem_base, &mbar[1], n_mma);
             // ---- 6. level 4: conv4 on the dirty pool4 cells, straight into `flat` (NHWC flatten = 16 bytes per cell, raster order)
-            st_level<50, 25>(scr3, l4, n4, atile, b16 + 2 * StSmem::b_bytes / 16, b34 + 8,
+            st_level<50, 25>(scr3, l4, n4, atile, atile1, b16 + 2 * StSmem::b_bytes / 16, b34 + 8,
                              reinterpret_cast<uint4 *>(fz.flat + (size_t)a * POL_FLAT_PITCH), tmem_base, &mbar[1], n_mma);
             // ---- 7. validation taps, then the dirty cells of both images go back to their empty-arena values
             if (fz.tap2) {
