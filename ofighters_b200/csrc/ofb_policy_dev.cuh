@@ -69,9 +69,12 @@ __device__ __forceinline__ void conv1_pool_pixel(uint32_t ps, uint32_t pl, const
     for (int i = 0; i < 2; i++)
 #pragma unroll
         for (int j = 0; j < 2; j++) {
-            const float4 *ls = reinterpret_cast<const float4 *>(lut + (size_t)conv1_pattern(ps, i, j) * 8);
-            const float4 *ll = reinterpret_cast<const float4 *>(lut + (size_t)(512 + conv1_pattern(pl, i, j)) * 8);
-            const float4 s0 = __ldg(ls), s1 = __ldg(ls + 1), l0 = __ldg(ll), l1 = __ldg(ll + 1);
+            // (entry 0 = no tap set = 0.0f: most dirty pixels see only one of the two maps, so half of the lookups are skipped)
+            const uint32_t qs = conv1_pattern(ps, i, j), ql = conv1_pattern(pl, i, j);
+            const float4 *ls = reinterpret_cast<const float4 *>(lut + (size_t)qs * 8);
+            const float4 *ll = reinterpret_cast<const float4 *>(lut + (size_t)(512 + ql) * 8);
+            const float4 zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const float4 s0 = qs ? __ldg(ls) : zero, s1 = qs ? __ldg(ls + 1) : zero, l0 = ql ? __ldg(ll) : zero, l1 = ql ? __ldg(ll + 1) : zero;
             const float sv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
             const float lv[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
 #pragma unroll
