@@ -1,20 +1,22 @@
-// Sparse trunk12 on tensor cores (sm_100a): conv1 + BN + ReLU + pool -> conv2 + BN + ReLU + pool (agents/qlearnIA_V2.py:129-139),
-// 400 x 400 x 2 bits -> 100 x 100 x 8 bf16, evaluated only where it can differ from the empty-arena answer.
+// Sparse trunk on tensor cores (sm_100a): conv1 + BN + ReLU + pool -> ... -> conv4 + BN + ReLU + pool (agents/qlearnIA_V2.py:129-147),
+// 400 x 400 x 2 bits -> 25 x 25 x 8 bf16 (`flat`), evaluated only where it can differ from the empty-arena answer.
 //
 // The maps are > 96 % zeros, so pool1 (200 x 200 x 8) equals one constant vector bg1 except at the "dirty" pixels whose
-// 4 x 4-bit receptive field holds a set bit, and a pool2 cell equals the precomputed empty-arena value of its border class
-// unless one of the 4 x 4 pool1 pixels it reads is dirty.  Per arena (default scene: 150 - 1 000 dirty cells of 10 000):
-//   1. both bit maps -> shared memory (one bulk async copy); meanwhile every cell of the output gets its empty-arena value;
-//   2. bit arithmetic only: M = ship | laser re-aligned to 13 words per row, D1 = dirty pool1 pixels (200 x 200 bits),
-//      D2 = dirty cells (100 x 100 bits), row prefix sums of both -> compact lists without atomics, in raster order;
+// 4 x 4-bit receptive field holds a set bit, and a pooled cell of any deeper level equals the precomputed empty-arena value of its
+// border class unless one of the 4 x 4 cells it reads is dirty.  Per arena (default scene: 150 - 1 000 dirty pool2 cells of 10 000):
+//   1. both bit maps -> shared memory (one bulk async copy); meanwhile `flat` gets its empty-arena values;
+//   2. bit arithmetic only: Q = pairwise OR of map rows re-aligned to 13 words per row, D1 = dirty pool1 pixels (200 x 200 bits),
+//      D2 / D3 / D4 = dirty cells of the levels above (a 4-wide window OR + even-bit compress of the level below), row-major
+//      popcount prefixes of every level -> compact lists without atomics, in raster order;
 //   3. conv1 for the dirty pool1 pixels only (9-bit stencil LUT exactly like the other engines) -> V1[k];
-//   4. dirty cells 128 at a time: ONE M row of a tcgen05 MMA per cell -- K = the cell's 4 x 4 pool1 patch x 8 channels
-//      (each patch entry is bg1, a V1 entry found by a popcount prefix, or zero outside the grid = conv2's padding),
-//      N = 4 conv2 pixels x 8 channels, B = conv2's weights scattered over the patch (8 K-steps); the draining thread owns
-//      a cell: + bias, max over its 4 pixels, ReLU, bf16, one 16-byte store.
-// So the only per-pixel CUDA-core work left is the LUT of step 3 (~1 200 pixels per arena) and the 16 patch lookups per
-// dirty cell; conv2's 2 304 MACs per dirty cell run on the tensor pipe.  Scenes with more dirty pixels than the lists hold
-// (32-ship stress arenas) are processed in bands of cell rows sized from the prefix sums.
+//   4. per level, dirty cells 128 at a time: ONE M row of a tcgen05 MMA per cell -- K = the cell's 4 x 4 input patch x 8 channels,
+//      N = 4 conv pixels x 8 channels, B = the conv's weights scattered over the patch (8 K-steps); the draining thread owns a cell:
+//      + bias, max over its 4 pixels, ReLU, bf16.  The computed cells of a level stay in shared memory as a compact list in raster
+//      order (V1 -> V2 -> V3); a patch row of the next level is 4 adjacent entries, found with ONE bitmap word pair and ONE prefix
+//      (entry = the empty-arena value of its border class, a V entry, or zero outside the grid = the convolution's padding).
+// Only `flat` reaches HBM.  Arenas whose dirty cells exceed the lists (32-ship stress scenes, all-ones maps) take the fallback:
+// level 2 in bands of cell rows sized from the prefix sums, pool2 / pool3 in per-CTA dense images in global memory (L2-resident
+// scratch, initialised on first use with the empty arena's values; only the dirty cells are written and put back afterwards).
 // Arithmetic: bf16 weights and activations, fp32 accumulation, like the twin engines (the summation order differs).
 #include "ofb_common.cuh"
 #include "ofb_policy.cuh"
@@ -24,33 +26,43 @@
 #ifndef ST_NT
 #define ST_NT 384
 #endif
-#define ST_NG (ST_NT / 128)                 // gather slices: thread = (cell of the tile, every ST_NG-th patch position)
 #define ST_CAP1 1280                      // dirty pool1 pixels per band
-#define ST_CAP2 2048                      // dirty cells per band
+#define ST_CAP2 2048                      // dirty pool2 cells per band
+#define ST_VCAP 1024                      // compact path: dirty pool2 / pool3 cells of an arena kept in shared memory
 #define ST_RW 13                          // 32-bit words of one 400-bit map row
 
 struct StSmem {
     static constexpr int off_maps = 0;                                 // ship map | laser map (40 000 B); later the MMA's A tile:
     static constexpr int a_bytes = 16 * 128 * 16;                      //   [16 patch positions][128 cells][8 ch bf16]
+    // V1 .. P1 are contiguous: all four are dead after level 2, when the region holds conv3's and conv4's B operands and V3
     static constexpr int off_v1 = 40000;                               // uint4 [CAP1]; before that Q [201][13] words (10 452 B)
     static constexpr int off_l1 = off_v1 + ST_CAP1 * 16;               // u32 [CAP1]: py << 16 | px
-    static constexpr int off_l2 = off_l1 + ST_CAP1 * 4;                // u16 [CAP2]: Y * 100 + X
-    static constexpr int off_d1 = off_l2 + ST_CAP2 * 2;                // u32 [200][7]
-    static constexpr int off_d2 = off_d1 + 200 * 7 * 4;                // u32 [100][4]
-    static constexpr int off_p1 = off_d2 + 100 * 4 * 4;                // int [200][7] dirty pool1 pixels before word (py, w), raster order
-    static constexpr int off_p2 = off_p1 + 200 * 7 * 4;                // int [100][4] dirty cells before word (Y, w)
-    static constexpr int off_rb1 = off_p2 + 100 * 4 * 4;               // int [201] prefix of dirty pool1 pixels per row
+    static constexpr int off_d1 = off_l1 + ST_CAP1 * 4;                // u32 [200][7]
+    static constexpr int off_p1 = off_d1 + 200 * 7 * 4;                // int [200][7] dirty pool1 pixels before word (py, w), raster order
+    static constexpr int off_l2 = off_p1 + 200 * 7 * 4;                // u16 [CAP2]: Y * 100 + X; compact path: L3 = the second half
+    static constexpr int off_d2 = off_l2 + ST_CAP2 * 2;                // u32 [100][4]
+    static constexpr int off_p2 = off_d2 + 100 * 4 * 4;                // int [100][4] dirty cells before word (Y, w)
+    static constexpr int off_d3 = off_p2 + 100 * 4 * 4;                // u32 [50][2]
+    static constexpr int off_p3 = off_d3 + 100 * 4;                    // int [50][2]
+    static constexpr int off_d4 = off_p3 + 100 * 4;                    // u32 [25] (+ 7)
+    static constexpr int off_p4 = off_d4 + 32 * 4;                     // int [25] (+ 7)
+    static constexpr int off_l4 = off_p4 + 32 * 4;                     // u16 [625] (+ 15): Y * 25 + X
+    static constexpr int off_rb1 = off_l4 + 640 * 2;                   // int [201] prefix of dirty pool1 pixels per row
     static constexpr int off_rb2 = off_rb1 + 202 * 4;                  // int [101] prefix of dirty cells per row
     static constexpr int off_b = (off_rb2 + 102 * 4 + 15) & ~15;       // conv2 as B operand [8 ks][2 chunks][32 n][8 k] bf16
-    static constexpr int b_bytes = 8 * 2 * 32 * 16;                    //   x 3: conv2, conv3, conv4
-    static constexpr int off_misc = off_b + 3 * b_bytes;               // c1 bias [8] f32, conv2 bias [8] f32, bg1 (uint4), band ints [8], scan [16],
-    static constexpr int off_bar = off_misc + 32 + 32 + 16 + 32 + 64 + 64;   // conv3 / conv4 bias [16] f32; then 2 mbarriers, tmem slot
-    static constexpr int bytes = off_bar + 16 + 16;
+    static constexpr int b_bytes = 8 * 2 * 32 * 16;
+    static constexpr int off_v2 = off_b + b_bytes;                     // uint4 [VCAP]: pool2's dirty cells, raster order
+    static constexpr int off_misc = off_v2 + ST_VCAP * 16;             // c1 bias [8], conv2 bias [8], conv3 / conv4 bias [16] f32, bg1 (uint4),
+                                                                       // band ints [8], scan [16], bg1 / bg2 / bg3 classes: 3 x uint4 [9 + a zero entry]
+    static constexpr int off_bar = off_misc + 32 + 32 + 64 + 16 + 32 + 64 + 160 + 160 + 160;    // 3 mbarriers, tmem slot
+    static constexpr int bytes = off_bar + 24 + 8;
+    // levels 3 / 4: conv3's and conv4's B operands and V3 over the dead V1 .. P1
+    static constexpr int off_b34 = off_v1;
+    static constexpr int off_v3 = off_v1 + 2 * b_bytes;
 };
-// levels 3 / 4 (fused trunk): D3 [50][2], P3 [50][2], L3 u16 [2500], L4 u16 [625] in the map region behind A tile 0; D4 / P4 [25] in RB1;
-// A tile 1 over V1 .. the head of D1 (D2 survives: the restore reads it)
-static_assert(StSmem::a_bytes <= 40000 && ST_CAP1 * 16 >= 201 * ST_RW * 4 && 40000 - StSmem::a_bytes >= 400 + 400 + 5000 + 1250 &&
-              StSmem::off_v1 + StSmem::a_bytes <= StSmem::off_d2, "k_st_trunk12: aliasing");
+// fallback path, levels 3 / 4: L3 u16 [2500], L4 u16 [625] in the map region behind the A tile
+static_assert(StSmem::a_bytes <= 40000 && ST_CAP1 * 16 >= 201 * ST_RW * 4 && 40000 - StSmem::a_bytes >= 5000 + 1250 &&
+              StSmem::off_v3 + ST_VCAP * 16 <= StSmem::off_l2 && 2 * ST_VCAP <= ST_CAP2, "k_st_trunk12: aliasing");
 static_assert(StSmem::bytes <= 113 * 1024, "k_st_trunk12: two CTAs per SM");
 
 // 32 bits of map row r starting at column 32 c (rows are 400 bits = 12.5 words: odd rows start mid-word)
@@ -79,56 +91,113 @@ __device__ __forceinline__ uint32_t st_window4(uint32_t wa, uint32_t wb, uint32_
     return st_even_bits(g | (g >> 2) | (g64 << 62));                   // bit 2p': g[2p'] | g[2p' + 2]
 }
 
-// The whole trunk in this kernel (fz.fuse): pool2 and pool3 live in per-CTA dense images in global memory (L2-resident scratch,
-// initialised with the empty-arena values; only the dirty cells are written and put back afterwards), levels 3 and 4 are the
-// same cell-patch MMAs on the dirty cells of D3 = window(D2) / D4 = window(D3), and only `flat` (25 x 25 x 8) reaches HBM.
 struct StFuse {
-    int fuse;
+    int fuse;                          // 1 = the whole trunk (levels 2 .. 4 -> flat); 0 = conv1 + conv2 only (dense pool2 -> `out`)
     __nv_bfloat16 *flat;               // [item][POL_FLAT_PITCH]
-    uint4 *scratch;                    // [gridDim.x][ST_SCRATCH_CELLS]
+    uint4 *scratch;                    // fallback path: [gridDim.x][ST_SCRATCH_CELLS]
     __nv_bfloat16 *tap2, *tap3;        // optional dense copies of pool2 / pool3 (validation taps)
 };
 __device__ __forceinline__ int st_cls(int i, int n) { return i == 0 ? 0 : (i == n - 1 ? 2 : 1); }
 
-// One level of the fused trunk: the `n` cells of `list` (cell = Y * NDST + X on the NDST x NDST output grid) from the dense
-// NSRC x NSRC image `src` (global; written by this CTA before the last barrier -> read at L2), 128 cells per MMA tile.
-// The A tile is double-buffered (atile0 / atile1): the gather of tile t + 1 -- cp.async straight from L2 into shared memory,
-// every patch position of a thread in flight together -- runs under the MMAs and the drain of tile t.
-template <int NSRC, int NDST>
-__device__ __forceinline__ void st_gather(const uint4 *src, const uint16_t *list, int tb, int n, uint4 *atile) {
-    // item = (patch row, cell, column j of the patch): 4 neighbouring lanes fetch the 64 contiguous bytes of one patch row, so a
-    // warp's 32 requests fall into a few 128-byte lines (the L1 -> L2 request rate is what this gather costs)
-    const int nb = min(128, n - tb);
+// The A tile of 128 cells of `list` (cell = Y * NDST + X on the NDST x NDST output grid; input grid NSRC = 2 NDST): item = (cell,
+// patch row) = the 4 adjacent input entries (2Y - 1 + r, 2X - 1 .. 2X + 2).  Compact source: bitmap D [NSRC][RW words] of the
+// computed ("dirty") entries, P = entries before each word in raster order, V = their values in raster order, every other entry
+// = the empty-arena value of its border class (bg[9]; one value when CONST_BG), zero outside the grid.
+template <int NSRC, int NDST, int RW, bool CONST_BG>
+struct StGatherCompact {
+    const uint32_t *D;
+    const int *P;
+    int base;
+    const uint4 *V, *bg;                                   // bg[9] classes (bg[0] only when CONST_BG), bg[9] = zeros
+    const uint16_t *list;
+    uint4 *atile;
+    // Straight-line code (no branches, every load's address is valid): the items of a thread overlap in the pipeline.  An entry
+    // is fetched through a shared-memory ADDRESS chosen among {V entry, class value, zeros}, not a value select.
+    __device__ __forceinline__ void operator()(int tb, int nb) const {
+        const uint32_t v16 = smem_u32(V), bg16 = smem_u32(bg), zero16 = bg16 + 9 * 16;
+        constexpr int NK = (512 + ST_NT - 1) / ST_NT;
+        uint32_t addr[NK][4];
+        uint4 val[NK][4];
 #pragma unroll
-    for (int k = 0; k < (2048 + ST_NT - 1) / ST_NT; k++) {
-        const int idx = threadIdx.x + ST_NT * k, j = idx & 3, c = (idx >> 2) & 127, row = idx >> 9;
-        if (idx >= 2048) break;
-        if (c < nb) {
-            const int cell = list[tb + c], Y = cell / NDST, X = cell - Y * NDST, qy = 2 * Y - 1 + row, qx = 2 * X - 1 + j;
-            uint4 *dst = atile + (row * 4 + j) * 128 + c;
-            if (qy >= 0 && qy < NSRC && qx >= 0 && qx < NSRC)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src + qy * NSRC + qx) : "memory");
-            else
-                *dst = make_uint4(0u, 0u, 0u, 0u);                                      // outside the grid: the convolution's zero padding
+        for (int k = 0; k < NK; k++) {
+            const int idx = (int)threadIdx.x + ST_NT * k, c = idx & 127, r = idx >> 7;
+            const bool on = idx < 512 && c < nb;
+            const int cell = list[tb + (on ? c : 0)], Y = cell / NDST, X = cell - Y * NDST, qy = 2 * Y - 1 + r, x0 = 2 * X - 1;
+            const bool row_in = qy >= 0 && qy < NSRC;
+            const int qc = min(max(qy, 0), NSRC - 1), start = max(x0, 0), w = start >> 5, sh = start & 31;
+            const uint32_t lo = D[qc * RW + w], hi = D[qc * RW + w + 1];        // (hi matters only inside the row: see the masks of D)
+            const int pw = P[qc * RW + w];
+            uint32_t m = __funnelshift_r(lo, hi, sh) & 0xFu;
+            if (x0 < 0) m = (m << 1) & 0xFu;
+            if (!row_in) m = 0u;
+            const uint32_t vi = v16 + (uint32_t)(pw - base + __popc(lo & ((1u << sh) - 1u))) * 16u;
+            const uint32_t cls16 = CONST_BG ? bg16 : bg16 + (uint32_t)(st_cls(qc, NSRC) * 3) * 16u;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int qx = x0 + j;
+                uint32_t ad = CONST_BG ? cls16 : cls16 + (qx <= 0 ? 0u : (qx >= NSRC - 1 ? 32u : 16u));
+                if (!row_in || qx < 0 || qx >= NSRC) ad = zero16;
+                if ((m >> j) & 1u) ad = vi + (uint32_t)__popc(m & ((1u << j) - 1u)) * 16u;
+                addr[k][j] = ad;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NK; k++)
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(val[k][j].x), "=r"(val[k][j].y), "=r"(val[k][j].z), "=r"(val[k][j].w) : "r"(addr[k][j]) : "memory");
+#pragma unroll
+        for (int k = 0; k < NK; k++) {
+            const int idx = (int)threadIdx.x + ST_NT * k, c = idx & 127, r = idx >> 7;
+            if (idx < 512 && c < nb) {
+                uint4 *dst = atile + (r * 4) * 128 + c;
+#pragma unroll
+                for (int j = 0; j < 4; j++) dst[j * 128] = val[k][j];
+            }
         }
     }
-}
+};
+// Fallback source: the dense NSRC x NSRC image `src` in global memory (written by this CTA before the last barrier -> read at L2)
 template <int NSRC, int NDST>
-__device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list, int n, uint4 *atile0, uint4 *atile1, uint32_t b16,
-                                         const float *bias, uint4 *dst, uint32_t tmem_base, uint64_t *mma_bar, uint32_t &n_mma) {
+struct StGatherDense {
+    const uint4 *src;
+    const uint16_t *list;
+    uint4 *atile;
+    __device__ __forceinline__ void operator()(int tb, int nb) const {
+        for (int idx = threadIdx.x; idx < 2048; idx += ST_NT) {
+            const int j = idx & 3, c = (idx >> 2) & 127, row = idx >> 9;
+            if (c >= nb) continue;
+            const int cell = list[tb + c], Y = cell / NDST, X = cell - Y * NDST, qy = 2 * Y - 1 + row, qx = 2 * X - 1 + j;
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);                                      // outside the grid: the convolution's zero padding
+            if (qy >= 0 && qy < NSRC && qx >= 0 && qx < NSRC) val = __ldcg(src + qy * NSRC + qx);
+            atile[(row * 4 + j) * 128 + c] = val;
+        }
+    }
+};
+
+// One level: the `n` cells of `list`, 128 per MMA tile: gather -> 8 MMAs (N = 32) -> drain (+ bias, max over the cell's 4 conv
+// pixels, ReLU, bf16) into dst[list[.]] (by_list) or dst[position in the list].  Only the draining warps wait for the MMAs;
+// everyone else goes on to the block barrier.  `pf_*`: after the gather of the level's LAST tile thread 0 may start a bulk
+// copy (the next levels' B operands into memory this level's gathers were the last readers of).
+template <class G>
+__device__ __forceinline__ void st_tiles(const G &gather, const uint16_t *list, int n, uint4 *atile, uint32_t b16, const float *bias,
+                                         uint4 *dst, bool by_list, uint32_t tmem_base, uint64_t *mma_bar, uint32_t &n_mma,
+                                         uint64_t *wait_bar, uint32_t wait_parity, uint64_t *pf_bar, void *pf_dst, const void *pf_src0,
+                                         const void *pf_src1, long long *stamp) {
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr uint32_t IDESC = instr_desc(32);
-    if (n > 0) st_gather<NSRC, NDST>(src, list, 0, n, atile0);
-    int buf = 0;
-    for (int tb = 0; tb < n; tb += 128, buf ^= 1) {
+    for (int tb = 0; tb < n; tb += 128) {
         const int nb = min(128, n - tb);
-        uint4 *atile = buf ? atile1 : atile0;
-        asm volatile("cp.async.wait_all;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        gather(tb, nb);
+        if (stamp && tb == 0) stamp[0] = clock64();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMAs
         tc_fence_before();
-        __syncthreads();                                   // tile tb is in shared memory; the previous tile's drain has left TMEM
+        __syncthreads();
+        if (stamp && tb == 0) stamp[1] = clock64();
         if (warp == 4) {
             tc_fence_after();
+            if (wait_bar && tb == 0) mbar_wait(wait_bar, wait_parity);     // this level's B operand has landed
             const bool leader = elect_one();
             const uint32_t a16 = smem_u32(atile) >> 4;
 #pragma unroll
@@ -140,12 +209,16 @@ __device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list,
             if (leader) tc_commit(mma_bar);
             __syncwarp();
         }
-        // the other buffer was last read by the MMAs of the tile before this one, whose completion every thread has waited for
-        if (tb + 128 < n) st_gather<NSRC, NDST>(src, list, tb + 128, n, buf ? atile0 : atile1);
-        mbar_wait(mma_bar, n_mma & 1u);
-        n_mma++;
-        tc_fence_after();
+        if (pf_bar && tb + 128 >= n && tid == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(pf_bar, 2 * StSmem::b_bytes);
+            bulk_g2s(pf_dst, pf_src0, StSmem::b_bytes, pf_bar);
+            bulk_g2s(reinterpret_cast<uint8_t *>(pf_dst) + StSmem::b_bytes, pf_src1, StSmem::b_bytes, pf_bar);
+        }
         if (warp < 4) {
+            mbar_wait(mma_bar, n_mma & 1u);
+            tc_fence_after();
+            if (stamp && tb == 0) stamp[2] = clock64();
             uint32_t r[32];
             tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
             tc_wait_ld();
@@ -155,12 +228,25 @@ __device__ __forceinline__ void st_level(const uint4 *src, const uint16_t *list,
                 for (int co = 0; co < 8; co++)
                     o[co] = fmaxf(fmaxf(__uint_as_float(r[co]), __uint_as_float(r[8 + co])),
                                   fmaxf(__uint_as_float(r[16 + co]), __uint_as_float(r[24 + co]))) + bias[co];
-                dst[list[tb + tid]] = pack_relu_bf8(o);
+                dst[by_list ? (int)list[tb + tid] : tb + tid] = pack_relu_bf8(o);
             }
         }
+        n_mma++;
+        tc_fence_before();
+        __syncthreads();                                   // TMEM and the A tile are free again; the drained cells are visible
+        if (stamp && tb == 0) stamp[3] = clock64();
     }
-    tc_fence_before();
-    __syncthreads();                                       // the level's image is complete; TMEM and both A tiles are free
+}
+
+// raster-order list of the set bits of bitmap word `wd` (NW words per row, NCOL cells per row), starting at entry k
+template <int NW, int NCOL>
+__device__ __forceinline__ void st_list_word(uint32_t bits, int wd, int k, uint16_t *list) {
+    const int Y = wd / NW, x0 = 32 * (wd - Y * NW);
+    while (bits) {
+        const int b = __ffs(bits) - 1;
+        bits &= bits - 1;
+        list[k++] = (uint16_t)(Y * NCOL + x0 + b);
+    }
 }
 
 __global__ void __launch_bounds__(ST_NT, 2)
@@ -171,46 +257,45 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     const uint32_t *bs = reinterpret_cast<const uint32_t *>(st_smem + StSmem::off_maps), *bl = bs + POL_WORDS;
     uint4 *atile = reinterpret_cast<uint4 *>(st_smem + StSmem::off_maps);
     uint4 *v1 = reinterpret_cast<uint4 *>(st_smem + StSmem::off_v1);
+    uint4 *v2 = reinterpret_cast<uint4 *>(st_smem + StSmem::off_v2), *v3 = reinterpret_cast<uint4 *>(st_smem + StSmem::off_v3);
     uint32_t *qrow = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_v1);       // Q [201][13], dead before V1 is written
     uint32_t *l1 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_l1);
     int *p1 = reinterpret_cast<int *>(st_smem + StSmem::off_p1), *p2 = reinterpret_cast<int *>(st_smem + StSmem::off_p2);
+    int *p3 = reinterpret_cast<int *>(st_smem + StSmem::off_p3), *p4 = reinterpret_cast<int *>(st_smem + StSmem::off_p4);
     uint16_t *l2 = reinterpret_cast<uint16_t *>(st_smem + StSmem::off_l2);
     uint32_t *d1 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_d1), *d2 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_d2);
+    uint32_t *d3 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_d3), *d4 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_d4);
     int *rb1 = reinterpret_cast<int *>(st_smem + StSmem::off_rb1), *rb2 = reinterpret_cast<int *>(st_smem + StSmem::off_rb2);
-    float *c1b = reinterpret_cast<float *>(st_smem + StSmem::off_misc), *b2 = c1b + 8;
-    uint4 *bg1v = reinterpret_cast<uint4 *>(st_smem + StSmem::off_misc + 64);
-    int *band = reinterpret_cast<int *>(st_smem + StSmem::off_misc + 80);         // Y1, p_lo, p_hi of the current band
-    int *scan = reinterpret_cast<int *>(st_smem + StSmem::off_misc + 112);        // warp totals of the row scan
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(st_smem + StSmem::off_bar);      // [0] maps landed, [1] MMAs done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_bar + 16);
+    float *c1b = reinterpret_cast<float *>(st_smem + StSmem::off_misc), *b2 = c1b + 8, *b34 = c1b + 16;   // conv3 bias [8], conv4 bias [8]
+    uint4 *bg1v = reinterpret_cast<uint4 *>(st_smem + StSmem::off_misc + 128);
+    int *band = reinterpret_cast<int *>(st_smem + StSmem::off_misc + 144);        // Y1, p_lo, p_hi of the current band; [4] n3, [5] n4
+    int *scan = reinterpret_cast<int *>(st_smem + StSmem::off_misc + 176);        // warp totals of the row scan
+    uint4 *bgc1 = reinterpret_cast<uint4 *>(st_smem + StSmem::off_misc + 240), *bgc2 = bgc1 + 10, *bgc3 = bgc2 + 10;   // [9] = zeros
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(st_smem + StSmem::off_bar);      // [0] maps landed, [1] MMAs done, [2] conv3 / conv4 operands landed
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_bar + 24);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    if (tid < 8) { c1b[tid] = w.c1_b[tid]; b2[tid] = w.cb[0][tid]; }
+    if (tid < 8) { c1b[tid] = w.c1_b[tid]; b2[tid] = w.cb[0][tid]; b34[tid] = w.cb[1][tid]; b34[8 + tid] = w.cb[2][tid]; }
+    if (tid >= 32 && tid < 41) bgc2[tid - 32] = reinterpret_cast<const uint4 *>(w.sp_bg2)[tid - 32];
+    if (tid >= 64 && tid < 73 && fz.fuse) bgc3[tid - 64] = reinterpret_cast<const uint4 *>(w.sp_bg3)[tid - 64];
+    if (tid >= 96 && tid < 99) bgc1[(tid - 96) * 10 + 9] = make_uint4(0u, 0u, 0u, 0u);
     if (tid == 0) {
         float v[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) v[k] = w.sp_bg1[k];
         *bg1v = pack_bf8(v);
+        bgc1[0] = *bg1v;
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 8 * 2 * 32; i += ST_NT) {
+    for (int i = tid; i < 8 * 2 * 32; i += ST_NT)
         reinterpret_cast<uint4 *>(st_smem + StSmem::off_b)[i] = reinterpret_cast<const uint4 *>(w.c2_st)[i];
-        if (fz.fuse) {
-            reinterpret_cast<uint4 *>(st_smem + StSmem::off_b + StSmem::b_bytes)[i] = reinterpret_cast<const uint4 *>(w.c3_st)[i];
-            reinterpret_cast<uint4 *>(st_smem + StSmem::off_b + 2 * StSmem::b_bytes)[i] = reinterpret_cast<const uint4 *>(w.c4_st)[i];
-        }
-    }
-    float *b34 = reinterpret_cast<float *>(st_smem + StSmem::off_misc + 176);      // conv3 bias [8], conv4 bias [8]
-    if (tid < 8) { b34[tid] = w.cb[1][tid]; b34[8 + tid] = w.cb[2][tid]; }
     uint4 *scr2 = fz.scratch + (size_t)blockIdx.x * ST_SCRATCH_CELLS, *scr3 = scr2 + 100 * 100;
-    const uint4 *bg3 = reinterpret_cast<const uint4 *>(w.sp_bg3), *bg4 = reinterpret_cast<const uint4 *>(w.sp_bg4);
-    if (fz.fuse) {                                          // this CTA's pool2 / pool3 images start out as the empty arena's
-        const uint4 *bg2i = reinterpret_cast<const uint4 *>(w.sp_bg2);
-        for (int i = tid; i < 100 * 100; i += ST_NT) scr2[i] = __ldg(bg2i + st_cls(i / 100, 100) * 3 + st_cls(i % 100, 100));
-        for (int i = tid; i < 50 * 50; i += ST_NT) scr3[i] = __ldg(bg3 + st_cls(i / 50, 50) * 3 + st_cls(i % 50, 50));
-    }
+    const uint4 *bg2g = reinterpret_cast<const uint4 *>(w.sp_bg2), *bg3g = reinterpret_cast<const uint4 *>(w.sp_bg3);
+    const uint4 *bg4g = reinterpret_cast<const uint4 *>(w.sp_bg4);
+    bool scratch_ready = false;                             // the fallback's dense images are initialised on first use
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -220,14 +305,14 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint4 *bg2 = reinterpret_cast<const uint4 *>(w.sp_bg2);      // [9 classes] bf16 x 8
-    constexpr uint32_t IDESC = instr_desc(32);
-    uint32_t n_loads = 0, n_mma = 0;
+    const uint32_t b16 = smem_u32(st_smem + StSmem::off_b) >> 4, b34_16 = smem_u32(st_smem + StSmem::off_b34) >> 4;
+    uint32_t n_loads = 0, n_mma = 0, n_b34 = 0;
 
     int it = -1;
     for (int a = blockIdx.x; a < n_items; a += gridDim.x) {
         it++;
         ST_STAMP(0);
+        long long *tstamp = (stamps && blockIdx.x == 0 && tid == 0 && it < 8) ? stamps + 128 + it * 32 : nullptr;
         const uint32_t *src = maps + (size_t)a * 2 * POL_WORDS;
         __nv_bfloat16 *dsta = out + (size_t)a * 100 * 100 * 8;
         // ---- 1. maps -> shared memory; the output's empty-arena values meanwhile
@@ -238,10 +323,10 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
         }
         if (fz.fuse) {                                     // only `flat` leaves the kernel: its empty-arena values first
             uint4 *fl = reinterpret_cast<uint4 *>(fz.flat + (size_t)a * POL_FLAT_PITCH);
-            for (int i = tid; i < 625; i += ST_NT) fl[i] = __ldg(bg4 + st_cls(i / 25, 25) * 3 + st_cls(i % 25, 25));
+            for (int i = tid; i < 625; i += ST_NT) fl[i] = __ldg(bg4g + st_cls(i / 25, 25) * 3 + st_cls(i % 25, 25));
         } else if ((tid & 127) < 100) {                    // a thread keeps its column and walks every other row
             const int X = tid & 127, cx = X == 0 ? 0 : (X == 99 ? 2 : 1);
-            const uint4 top = __ldg(bg2 + cx), mid = __ldg(bg2 + 3 + cx), bot = __ldg(bg2 + 6 + cx);
+            const uint4 top = __ldg(bg2g + cx), mid = __ldg(bg2g + 3 + cx), bot = __ldg(bg2g + 6 + cx);
             uint4 *col = reinterpret_cast<uint4 *>(dsta) + X;
             for (int Y = tid >> 7; Y < 100; Y += ST_NT / 128) col[Y * 100] = Y == 0 ? top : (Y == 99 ? bot : mid);
         }
@@ -287,8 +372,9 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             d2[i] = dd;
         }
         __syncthreads();
-        // ---- 2d. prefix sums in raster order, both levels in one block scan: thread t = pool1 row t (low 16 bits) and cell row t
-        //          (high 16 bits; the totals stay below 2^16); then the prefix in front of every word
+        // ---- 2d. prefix sums in raster order, levels 1 and 2 in one block scan: thread t = pool1 row t (low 16 bits) and cell row t
+        //          (high 16 bits; the totals stay below 2^16); then the prefix in front of every word.  Beside it (threads that
+        //          have no row): D3 = dirty pool3 cells (50 x 50) from D2, then D4 (25 x 25) from D3 and both their prefixes.
         {
             int c1 = 0, c2 = 0;
             if (tid < 200)
@@ -297,6 +383,20 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             if (tid < 100)
 #pragma unroll
                 for (int k = 0; k < 4; k++) c2 += __popc(d2[tid * 4 + k]);
+            if (fz.fuse && tid >= 256 && tid < 356) {
+                const int t = tid - 256, Y = t >> 1, wd = t & 1, c0 = 2 * wd;
+                uint32_t wa = 0u, wb = 0u, wc = 0u, we = 0u;
+                for (int r = max(2 * Y - 1, 0); r <= min(2 * Y + 2, 99); r++) {
+                    const uint32_t *dr = d2 + r * 4;
+                    if (c0 > 0) wa |= dr[c0 - 1];
+                    wb |= dr[c0];
+                    wc |= dr[c0 + 1];
+                    if (c0 + 2 < 4) we |= dr[c0 + 2];
+                }
+                uint32_t dd = st_window4(wa, wb, wc, we);
+                if (wd == 1) dd &= 0x3FFFFu;               // 50 cells per row
+                d3[t] = dd;
+            }
             const int mine = c1 | (c2 << 16);
             int inc = mine;
 #pragma unroll
@@ -320,9 +420,47 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
                 for (int k = 0; k < 4; k++) { p2[tid * 4 + k] = run; run += __popc(d2[tid * 4 + k]); }
                 if (tid == 99) rb2[100] = run;
             }
+            if (fz.fuse && warp == 8) {                    // D4, its prefix
+                uint32_t dd = 0u;
+                if (lane < 25) {
+                    uint32_t wb = 0u, wc = 0u;
+                    for (int r = max(2 * lane - 1, 0); r <= min(2 * lane + 2, 49); r++) { wb |= d3[r * 2]; wc |= d3[r * 2 + 1]; }
+                    dd = st_window4(0u, wb, wc, 0u) & 0x1FFFFFFu;
+                    d4[lane] = dd;
+                }
+                const int c4 = __popc(dd);
+                int i4 = c4;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, i4, o); if (lane >= o) i4 += t; }
+                if (lane < 25) p4[lane] = i4 - c4;
+                if (lane == 31) band[5] = i4;
+            } else if (fz.fuse && warp == 9) {             // row-major prefix of D3 (100 words)
+                int run = 0;
+                for (int base = 0; base < 100; base += 32) {
+                    const int i = base + lane, c = i < 100 ? __popc(d3[i]) : 0;
+                    int i3 = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, i3, o); if (lane >= o) i3 += t; }
+                    if (i < 100) p3[i] = run + i3 - c;
+                    run += __shfl_sync(0xffffffffu, i3, 31);
+                }
+                if (lane == 0) band[4] = run;
+            }
         }
         __syncthreads();
         ST_STAMP(4);
+        const int n3 = fz.fuse ? band[4] : 0, n4 = fz.fuse ? band[5] : 0;
+        // the compact path: every level's dirty cells fit the shared-memory lists (one band)
+        const bool compact = fz.fuse && rb1[200] <= ST_CAP1 && rb2[100] <= ST_VCAP && n3 <= ST_VCAP;
+        uint16_t *l3 = compact ? l2 + ST_VCAP : reinterpret_cast<uint16_t *>(st_smem + StSmem::off_maps + StSmem::a_bytes);
+        uint16_t *l4 = compact ? reinterpret_cast<uint16_t *>(st_smem + StSmem::off_l4) : l3 + 2500;
+        const bool need_b34 = n3 > 0;                       // (D4 is a window of D3: n3 == 0 implies n4 == 0)
+        bool b34_issued = false;
+        if (fz.fuse && !compact && !scratch_ready) {       // this CTA's pool2 / pool3 images start out as the empty arena's
+            for (int i = tid; i < 100 * 100; i += ST_NT) scr2[i] = __ldg(bg2g + st_cls(i / 100, 100) * 3 + st_cls(i % 100, 100));
+            for (int i = tid; i < 50 * 50; i += ST_NT) scr3[i] = __ldg(bg3g + st_cls(i / 50, 50) * 3 + st_cls(i % 50, 50));
+            scratch_ready = true;
+        }
         // ---- 3 / 4. bands of cell rows whose dirty pixels / cells fit the lists (one band for a default arena)
         int Y0 = 0, nband = 0;
         while (Y0 < 100) {
@@ -351,14 +489,8 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
                 }
                 // the band's dirty cells in raster order: entry index = prefix in front of the word + set bits before it in the word
                 for (int i = tid; i < (Y1 - Y0 + 1) * 4; i += ST_NT) {
-                    const int Y = Y0 + (i >> 2), wd = i & 3;
-                    uint32_t bits = d2[Y * 4 + wd];
-                    int k = p2[Y * 4 + wd] - base2;
-                    while (bits) {
-                        const int b = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        l2[k++] = (uint16_t)(Y * 100 + 32 * wd + b);
-                    }
+                    const int wd = Y0 * 4 + i;
+                    st_list_word<4, 100>(d2[wd], wd, p2[wd] - base2, l2);
                 }
                 for (int i = tid; i < (phi - plo + 1) * 7; i += ST_NT) {
                     const int py = plo + i / 7, wd = i % 7;
@@ -369,6 +501,11 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
                         bits &= bits - 1;
                         l1[k++] = ((uint32_t)py << 16) | (uint32_t)(32 * wd + b);
                     }
+                }
+                if (compact) {                             // the lists of levels 3 and 4, by the threads with the fewest items above
+                    const int t2 = ST_NT - 1 - tid;
+                    if (t2 < 100) st_list_word<2, 50>(d3[t2], t2, p3[t2], l3);
+                    else if (t2 < 125) st_list_word<1, 25>(d4[t2 - 100], t2 - 100, p4[t2 - 100], l4);
                 }
                 __syncthreads();
                 ST_STAMP(5);
@@ -383,159 +520,91 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
                 }
                 __syncthreads();                           // the maps are dead from here on: the A tile takes their place
                 ST_STAMP(6);
-                if (stamps && blockIdx.x == 0 && tid == 0 && it < 8) { stamps[it * 16 + 8] = n1; stamps[it * 16 + 9] = n2; }
-                // ---- 4. conv2 + pool on the tensor pipe, 128 dirty cells per MMA tile
-                for (int tb = 0; tb < n2; tb += 128) {
-                    const int nb = min(128, n2 - tb), c = tid & 127;
-                    if (c < nb) {
-                        const int cell = l2[tb + c], Y = cell / 100, X = cell - Y * 100;
-#pragma unroll
-                        for (int k = 0; k < (16 + ST_NG - 1) / ST_NG; k++) {
-                            const int pos = (tid >> 7) + ST_NG * k, qy = 2 * Y - 1 + (pos >> 2), qx = 2 * X - 1 + (pos & 3);
-                            if (pos >= 16) break;
-                            uint4 val = make_uint4(0u, 0u, 0u, 0u);                     // outside the grid: conv2's zero padding
-                            if (qy >= 0 && qy < 200 && qx >= 0 && qx < 200) {
-                                const uint32_t *dr = d1 + qy * 7;
-                                const int wd = qx >> 5, bit = qx & 31;
-                                if ((dr[wd] >> bit) & 1u) val = v1[p1[qy * 7 + wd] - base1 + __popc(dr[wd] & ((1u << bit) - 1u))];
-                                else val = *bg1v;
-                            }
-                            atile[pos * 128 + c] = val;
-                        }
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMAs
-                    tc_fence_before();
-                    __syncthreads();
-                    if (warp == 4) {
-                        tc_fence_after();
-                        const bool leader = elect_one();
-                        const uint32_t a16 = smem_u32(atile) >> 4, b16 = smem_u32(st_smem + StSmem::off_b) >> 4;
-#pragma unroll
-                        for (int ks = 0; ks < 8; ks++) {
-                            const uint64_t ad = smem_desc(a16 + (uint32_t)(2 * ks * 128), 128, 8);
-                            const uint64_t bd = smem_desc(b16 + (uint32_t)(ks * 2 * 32), 32, 8);
-                            if (leader) tc_mma(tmem_base, ad, bd, IDESC, ks ? 1u : 0u);
-                        }
-                        if (leader) tc_commit(&mbar[1]);
-                        __syncwarp();
-                    }
-                    mbar_wait(&mbar[1], n_mma & 1u);
-                    n_mma++;
-                    tc_fence_after();
-                    if (warp < 4) {                        // thread = cell: + bias, max over its 4 conv2 pixels, ReLU, bf16
-                        uint32_t r[32];
-                        tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
-                        tc_wait_ld();
-                        if (tid < nb) {
-                            float o[8];
-#pragma unroll
-                            for (int co = 0; co < 8; co++)
-                                o[co] = fmaxf(fmaxf(__uint_as_float(r[co]), __uint_as_float(r[8 + co])),
-                                              fmaxf(__uint_as_float(r[16 + co]), __uint_as_float(r[24 + co]))) + b2[co];
-                            if (fz.fuse) scr2[l2[tb + tid]] = pack_relu_bf8(o);
-                            else *reinterpret_cast<uint4 *>(dsta + (size_t)l2[tb + tid] * 8) = pack_relu_bf8(o);
-                        }
-                    }
-                    tc_fence_before();
-                    __syncthreads();                       // TMEM and the A tile are free again
+                if (stamps && blockIdx.x == 0 && tid == 0 && it < 8) {
+                    stamps[it * 16 + 8] = n1; stamps[it * 16 + 9] = n2; stamps[it * 16 + 10] = n3; stamps[it * 16 + 11] = n4;
                 }
+                // ---- 4. conv2 + pool on the tensor pipe, 128 dirty cells per MMA tile
+                const StGatherCompact<200, 100, 7, true> g2 = {d1, p1, base1, v1, bgc1, l2, atile};
+                uint4 *dst2 = compact ? v2 : (fz.fuse ? scr2 : reinterpret_cast<uint4 *>(dsta));
+                const bool pf = compact && need_b34;
+                st_tiles(g2, l2, n2, atile, b16, b2, dst2, !compact, tmem_base, &mbar[1], n_mma, nullptr, 0u, pf ? &mbar[2] : nullptr,
+                         st_smem + StSmem::off_b34, w.c3_st, w.c4_st, tstamp);
+                b34_issued = b34_issued || pf;
             }
             Y0 = Y1 + 1;
             nband++;
             __syncthreads();                               // everyone has read the band's bounds before thread 0 writes the next ones
         }
-        __syncthreads();                                   // nobody still reads this arena's lists / bitmaps
+        ST_STAMP(7);
         if (fz.fuse) {
-            // ---- 5. level 3: D3 = dirty pool3 cells (50 x 50), from D2; lists by popcount prefix (one warp); conv3 on the dirty cells
-            // (shared memory in levels 3 / 4: A tile 0 = the first 32 KB of the map region, bitmaps and lists in the 7 232 B after
-            //  it, A tile 1 over V1 / L1 / L2 / the head of D1 -- all dead by now; D2 stays for the restore)
-            uint32_t *d3 = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_maps + StSmem::a_bytes);
-            int *p3 = reinterpret_cast<int *>(d3 + 100);
-            uint16_t *l3 = reinterpret_cast<uint16_t *>(p3 + 100), *l4 = l3 + 2500;
-            uint32_t *d4 = reinterpret_cast<uint32_t *>(rb1);
-            int *p4 = rb1 + 32;
-            uint4 *atile1 = reinterpret_cast<uint4 *>(st_smem + StSmem::off_v1);
-            int *cnt = band;                               // n3, n4
-            if (tid < 100) {
-                const int Y = tid >> 1, wd = tid & 1, c0 = 2 * wd;
-                uint32_t wa = 0u, wb = 0u, wc = 0u, we = 0u;
-                for (int r = max(2 * Y - 1, 0); r <= min(2 * Y + 2, 99); r++) {
-                    const uint32_t *dr = d2 + r * 4;
-                    if (c0 > 0) wa |= dr[c0 - 1];
-                    wb |= dr[c0];
-                    wc |= dr[c0 + 1];
-                    if (c0 + 2 < 4) we |= dr[c0 + 2];
-                }
-                uint32_t dd = st_window4(wa, wb, wc, we);
-                if (wd == 1) dd &= 0x3FFFFu;               // 50 cells per row
-                d3[tid] = dd;
+            if (!compact) {
+                // fallback: the lists of levels 3 / 4 behind the A tile (the maps are dead)
+                if (tid < 100) st_list_word<2, 50>(d3[tid], tid, p3[tid], l3);
+                else if (tid >= 128 && tid < 153) st_list_word<1, 25>(d4[tid - 128], tid - 128, p4[tid - 128], l4);
+            }
+            if (need_b34 && !b34_issued && tid == 0) {     // conv3's and conv4's B operands over V1 (dead: the barrier above)
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&mbar[2], 2 * StSmem::b_bytes);
+                bulk_g2s(st_smem + StSmem::off_b34, w.c3_st, StSmem::b_bytes, &mbar[2]);
+                bulk_g2s(st_smem + StSmem::off_b34 + StSmem::b_bytes, w.c4_st, StSmem::b_bytes, &mbar[2]);
             }
             __syncthreads();
-            if (tid < 25) {                                // D4 = dirty pool4 cells (25 x 25), from D3
-                uint32_t wb = 0u, wc = 0u;
-                for (int r = max(2 * tid - 1, 0); r <= min(2 * tid + 2, 49); r++) { wb |= d3[r * 2]; wc |= d3[r * 2 + 1]; }
-                d4[tid] = st_window4(0u, wb, wc, 0u) & 0x1FFFFFFu;
+            uint4 *flat_a = reinterpret_cast<uint4 *>(fz.flat + (size_t)a * POL_FLAT_PITCH);
+            // ---- 5. level 3: conv3 on the dirty pool3 cells;  6. level 4: conv4 on the dirty pool4 cells, straight into `flat`
+            //         (NHWC flatten = 16 bytes per cell, raster order)
+            if (compact) {
+                const StGatherCompact<100, 50, 4, false> g3 = {d2, p2, 0, v2, bgc2, l3, atile};
+                st_tiles(g3, l3, n3, atile, b34_16, b34, v3, false, tmem_base, &mbar[1], n_mma, &mbar[2], n_b34 & 1u, nullptr, nullptr,
+                         nullptr, nullptr, tstamp ? tstamp + 4 : nullptr);
+                ST_STAMP(12);
+                const StGatherCompact<50, 25, 2, false> g4 = {d3, p3, 0, v3, bgc3, l4, atile};
+                st_tiles(g4, l4, n4, atile, b34_16 + StSmem::b_bytes / 16, b34 + 8, flat_a, true, tmem_base, &mbar[1], n_mma, nullptr, 0u,
+                         nullptr, nullptr, nullptr, nullptr, tstamp ? tstamp + 8 : nullptr);
+            } else {
+                const StGatherDense<100, 50> g3 = {scr2, l3, atile};
+                st_tiles(g3, l3, n3, atile, b34_16, b34, scr3, true, tmem_base, &mbar[1], n_mma, &mbar[2], n_b34 & 1u, nullptr, nullptr,
+                         nullptr, nullptr, nullptr);
+                ST_STAMP(12);
+                const StGatherDense<50, 25> g4 = {scr3, l4, atile};
+                st_tiles(g4, l4, n4, atile, b34_16 + StSmem::b_bytes / 16, b34 + 8, flat_a, true, tmem_base, &mbar[1], n_mma, nullptr, 0u,
+                         nullptr, nullptr, nullptr, nullptr, nullptr);
             }
-            __syncthreads();
-            if (warp == 0) {                               // row-major prefixes of D3 (100 words) and D4 (25 words)
-                int run = 0;
-                for (int base = 0; base < 100; base += 32) {
-                    const int i = base + lane, c = i < 100 ? __popc(d3[i]) : 0;
-                    int inc = c;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                    if (i < 100) p3[i] = run + inc - c;
-                    run += __shfl_sync(0xffffffffu, inc, 31);
-                }
-                const int c4 = lane < 25 ? __popc(d4[lane]) : 0;
-                int inc = c4;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                if (lane < 25) p4[lane] = inc - c4;
-                if (lane == 31) { cnt[0] = run; cnt[1] = inc; }
-            }
-            __syncthreads();
-            if (tid < 100) {
-                uint32_t bits = d3[tid];
-                int k = p3[tid];
-                while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; l3[k++] = (uint16_t)((tid >> 1) * 50 + 32 * (tid & 1) + b); }
-            } else if (tid >= 128 && tid < 153) {
-                const int Y = tid - 128;
-                uint32_t bits = d4[Y];
-                int k = p4[Y];
-                while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; l4[k++] = (uint16_t)(Y * 25 + b); }
-            }
-            __syncthreads();
-            const int n3 = cnt[0], n4 = cnt[1];
-            const uint32_t b16 = smem_u32(st_smem + StSmem::off_b) >> 4;
-            st_level<100, 50>(scr2, l3, n3, atile, atile1, b16 + StSmem::b_bytes / 16, b34, scr3, tmem_base, &mbar[1], n_mma);
-            // ---- 6. level 4: conv4 on the dirty pool4 cells, straight into `flat` (NHWC flatten = 16 bytes per cell, raster order)
-            st_level<50, 25>(scr3, l4, n4, atile, atile1, b16 + 2 * StSmem::b_bytes / 16, b34 + 8,
-                             reinterpret_cast<uint4 *>(fz.flat + (size_t)a * POL_FLAT_PITCH), tmem_base, &mbar[1], n_mma);
-            // ---- 7. validation taps, then the dirty cells of both images go back to their empty-arena values
+            if (need_b34) n_b34++;
+            ST_STAMP(13);
+            // ---- 7. validation taps (dense pool2 / pool3)
             if (fz.tap2) {
                 uint4 *t2 = reinterpret_cast<uint4 *>(fz.tap2) + (size_t)a * 10000, *t3 = reinterpret_cast<uint4 *>(fz.tap3) + (size_t)a * 2500;
-                for (int i = tid; i < 10000; i += ST_NT) t2[i] = __ldcg(scr2 + i);
-                for (int i = tid; i < 2500; i += ST_NT) t3[i] = __ldcg(scr3 + i);
+                if (compact) {
+                    const int n2 = rb2[100];
+                    for (int i = tid; i < 10000; i += ST_NT) t2[i] = bgc2[st_cls(i / 100, 100) * 3 + st_cls(i % 100, 100)];
+                    for (int i = tid; i < 2500; i += ST_NT) t3[i] = bgc3[st_cls(i / 50, 50) * 3 + st_cls(i % 50, 50)];
+                    __syncthreads();
+                    for (int e = tid; e < n2; e += ST_NT) t2[l2[e]] = v2[e];
+                    for (int e = tid; e < n3; e += ST_NT) t3[l3[e]] = v3[e];
+                } else {
+                    for (int i = tid; i < 10000; i += ST_NT) t2[i] = __ldcg(scr2 + i);
+                    for (int i = tid; i < 2500; i += ST_NT) t3[i] = __ldcg(scr3 + i);
+                }
                 __syncthreads();
             }
-            const uint4 *bg2i = reinterpret_cast<const uint4 *>(w.sp_bg2);
-            for (int i = tid; i < 100 * 4; i += ST_NT) {
-                uint32_t bits = d2[i];
-                const int Y = i >> 2;
-                while (bits) {
-                    const int X = 32 * (i & 3) + __ffs(bits) - 1;
-                    bits &= bits - 1;
-                    scr2[Y * 100 + X] = __ldg(bg2i + st_cls(Y, 100) * 3 + st_cls(X, 100));
+            if (!compact) {                                // fallback: the dirty cells of both images go back to their empty-arena values
+                for (int i = tid; i < 100 * 4; i += ST_NT) {
+                    uint32_t bits = d2[i];
+                    const int Y = i >> 2;
+                    while (bits) {
+                        const int X = 32 * (i & 3) + __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        scr2[Y * 100 + X] = __ldg(bg2g + st_cls(Y, 100) * 3 + st_cls(X, 100));
+                    }
+                }
+                for (int e = tid; e < n3; e += ST_NT) {
+                    const int cell = l3[e];
+                    scr3[cell] = __ldg(bg3g + st_cls(cell / 50, 50) * 3 + st_cls(cell % 50, 50));
                 }
             }
-            for (int e = tid; e < n3; e += ST_NT) {
-                const int cell = l3[e];
-                scr3[cell] = __ldg(bg3 + st_cls(cell / 50, 50) * 3 + st_cls(cell % 50, 50));
-            }
-            __syncthreads();
+            __syncthreads();                               // nobody still reads this arena's lists / bitmaps / V lists
         }
-        ST_STAMP(7);
+        ST_STAMP(14);
     }
     tc_fence_before();
     __syncthreads();
