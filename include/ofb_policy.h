@@ -63,9 +63,11 @@ int ofb_policy_create(const ofb_policy_weights *w_host, int device, int max_ship
  *   OFB_POLICY_UNFUSED_TAIL   upconv3 and upconv4 as two kernels through HBM (measurement aid; default = one fused kernel)
  *   OFB_POLICY_DENSE_TRUNK    conv1 + conv2 on the dense tcgen05 kernel instead of the sparse one
  *   OFB_POLICY_CC_SPARSE_TRUNK  the sparse trunk with conv2 on CUDA cores (round 1's kernel) instead of tensor cores
- *   OFB_POLICY_UNFUSED_TRUNK  conv1+conv2, conv3, conv4 as three kernels through HBM (default: one sparse kernel for the whole trunk) */
+ *   OFB_POLICY_UNFUSED_TRUNK  conv1+conv2, conv3, conv4 as three kernels through HBM (default: one sparse kernel for the whole trunk)
+ *   OFB_POLICY_TAIL_PAIR      the fused tail as CTA pairs (tcgen05 cta_group::2, M = 256 MMAs over two SMs that share the weight operand);
+ *                             identical results, measured no faster than one CTA per SM, kept as a selectable experiment */
 enum { OFB_POLICY_BILINEAR_TF1 = 1, OFB_POLICY_UNFUSED_TAIL = 2, OFB_POLICY_DENSE_TRUNK = 4, OFB_POLICY_CC_SPARSE_TRUNK = 8,
-       OFB_POLICY_UNFUSED_TRUNK = 16 };
+       OFB_POLICY_UNFUSED_TRUNK = 16, OFB_POLICY_TAIL_PAIR = 32 };
 int ofb_policy_create_opts(const ofb_policy_weights *w_host, int device, int max_ships, int flags, ofb_policy **out);
 int ofb_policy_destroy(ofb_policy *p);
 /* load new weights into an existing handle (Trainer.fit refreshed them; load_model, agents/qlearnIA_V2.py:70): folds like

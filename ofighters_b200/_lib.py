@@ -56,7 +56,7 @@ class OfbEpsSchedule(C.Structure):
 
 EPS_CONST, EPS_COSINE, EPS_DECAY = 0, 1, 2
 ENGINE_TENSOR, ENGINE_CUDA_CORE = 0, 1
-POLICY_BILINEAR_TF1, POLICY_UNFUSED_TAIL, POLICY_DENSE_TRUNK, POLICY_CC_SPARSE_TRUNK, POLICY_UNFUSED_TRUNK = 1, 2, 4, 8, 16
+POLICY_BILINEAR_TF1, POLICY_UNFUSED_TAIL, POLICY_DENSE_TRUNK, POLICY_CC_SPARSE_TRUNK, POLICY_UNFUSED_TRUNK, POLICY_TAIL_PAIR = 1, 2, 4, 8, 16, 32
 
 
 class OfbError(RuntimeError):

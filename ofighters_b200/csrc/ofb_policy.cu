@@ -218,6 +218,24 @@ static std::vector<uint8_t> pack_tail(const std::vector<float> &w3, const std::v
     return blob;
 }
 
+// The blob of pack_tail for CTA pairs: every B operand [blocks][2 chunks][N][16 B] sliced along N, rank r keeps the columns
+// [r N/2, (r + 1) N/2); the floats unchanged.  -> [2 ranks][TL_WBYTES_H]
+static std::vector<uint8_t> split_tail_blob(const std::vector<uint8_t> &blob) {
+    std::vector<uint8_t> out((size_t)2 * TL_WBYTES_H, 0);
+    struct Op { size_t off; int blocks, n; };
+    const Op ops[] = {{TL_OFF_B3, 6, 128}, {TL_OFF_B3V, 8, 64}, {TL_OFF_B4, 5, 48}, {TL_OFF_B4 + 480 * 16, 5, 80}, {TL_OFF_B4 + 1280 * 16, 5, 80},
+                      {TL_OFF_B4 + 2080 * 16, 5, 48}, {TL_OFF_B4V, 20, 16}, {TL_OFF_BIAS3, 1, 128}};
+    for (int r = 0; r < 2; r++) {
+        uint8_t *dst = out.data() + (size_t)r * TL_WBYTES_H;
+        for (const Op &o : ops)
+            for (int b = 0; b < o.blocks * 2; b++)          // (block, chunk)
+                memcpy(dst + o.off / 2 + (size_t)b * (o.n / 2) * 16, blob.data() + o.off + ((size_t)b * o.n + (size_t)r * (o.n / 2)) * 16,
+                       (size_t)(o.n / 2) * 16);
+        memcpy(dst + TL_OFF_AUX / 2, blob.data() + TL_OFF_AUX, TL_AUX_FLOATS * 4);
+    }
+    return out;
+}
+
 struct Uploader {
     std::vector<char> host;
     std::vector<std::pair<void **, size_t>> fix;
@@ -411,7 +429,11 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
     { const std::vector<float> pf = fold_phase(w, 8, 1, PT, PT);
       up.add(&d.u4_pw, pack_taps(pf, 8, 4, 16));
       up.add(&d.u4_tz, pack_toeplitz(pf, 8, 4, 8)); }
-    up.add(&d.tail_blob, pack_tail(w3, b3, w, legacy));
+    {
+        const std::vector<uint8_t> tb = pack_tail(w3, b3, w, legacy);
+        up.add(&d.tail_blob, tb);
+        up.add(&d.tail_blob2, split_tail_blob(tb));
+    }
     u4_bias = b[0];
     { std::vector<float> pb(16, 0.f); for (int n = 0; n < 4; n++) pb[n] = b[0]; up.add(&d.u4_pb, pb); }
 
@@ -422,7 +444,7 @@ extern "C" int ofb_policy_create(const ofb_policy_weights *wh, int device, int m
 }
 
 extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, int max_ships, int flags, ofb_policy **out) {
-    if (!wh || !out || (flags & ~(OFB_POLICY_BILINEAR_TF1 | OFB_POLICY_UNFUSED_TAIL | OFB_POLICY_DENSE_TRUNK | OFB_POLICY_CC_SPARSE_TRUNK | OFB_POLICY_UNFUSED_TRUNK))) {
+    if (!wh || !out || (flags & ~(OFB_POLICY_BILINEAR_TF1 | OFB_POLICY_UNFUSED_TAIL | OFB_POLICY_DENSE_TRUNK | OFB_POLICY_CC_SPARSE_TRUNK | OFB_POLICY_UNFUSED_TRUNK | OFB_POLICY_TAIL_PAIR))) {
         ofb_set_error("ofb_policy_create: bad argument");
         return OFB_E_ARG;
     }
@@ -448,6 +470,7 @@ extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, 
     // the tail: fused upconv3 -> upconv4 -> argmax by default; the two-kernel form is kept for A / B measurements
     { const char *e = getenv("OFB_POLICY_UNFUSED_TRUNK"); p->unfused_trunk = ((e && *e && *e != '0') || (flags & OFB_POLICY_UNFUSED_TRUNK)) ? 1 : 0; }
     { const char *e = getenv("OFB_POLICY_UNFUSED_TAIL"); p->unfused_tail = ((e && *e && *e != '0') || (flags & OFB_POLICY_UNFUSED_TAIL)) ? 1 : 0; }
+    { const char *e = getenv("OFB_POLICY_TAIL_PAIR"); p->tail_pair = ((e && *e && *e != '0') || (flags & OFB_POLICY_TAIL_PAIR)) ? 1 : 0; }
     p->bilinear_legacy = (flags & OFB_POLICY_BILINEAR_TF1) ? 1 : 0;
     p->prof = new std::vector<ProfEvent>();
 
@@ -469,9 +492,10 @@ extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, 
     const size_t C = (size_t)max_ships;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
-    const size_t o_p1 = take(C * 200 * 200 * 8 * 2), o_p2 = take(C * 100 * 100 * 8 * 2), o_p3 = take(C * 50 * 50 * 8 * 2);
+    // (pool1 / pool2 / pool3 / up3 -- 1.5 MB per ship, needed only by the alternative kernels and the validation taps -- are
+    //  allocated on first use: ensure_wide_workspace)
     const size_t o_fl = take(C * POL_FLAT_PITCH * 2), o_hf = take(C * 100 * 4);
-    const size_t o_u2 = take(C * POL_UP2_ITEM * 2), o_u3 = take(C * POL_UP3_ITEM * 2);
+    const size_t o_u2 = take(C * POL_UP2_ITEM * 2);
     const size_t o_av = take(C * AMAX_PARTS * 4), o_ai = take(C * AMAX_PARTS * 4);
     const size_t o_sc = take((size_t)ST_MAX_CTAS * ST_SCRATCH_CELLS * 16);
     e = cudaMalloc(&p->work_blob, off);
@@ -482,13 +506,11 @@ extern "C" int ofb_policy_create_opts(const ofb_policy_weights *wh, int device, 
     char *wb = static_cast<char *>(p->work_blob);
     cudaMemset(wb + o_fl, 0, C * POL_FLAT_PITCH * 2);            // K padding of dense1 must read as zero
     cudaMemset(wb + o_u2, 0, C * POL_UP2_ITEM * 2);              // channels 4..7 of up2 (plane layout) / the never-written entries of the pairs layout stay zero
-    p->ws.pool1 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p1);
-    p->ws.pool2 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p2);
-    p->ws.pool3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p3);
+    p->ws.pool1 = p->ws.pool2 = p->ws.pool3 = p->ws.up3 = nullptr;
+    p->wide_blob = nullptr;
     p->ws.flat = reinterpret_cast<__nv_bfloat16 *>(wb + o_fl);
     p->ws.hflat = reinterpret_cast<float *>(wb + o_hf);
     p->ws.up2 = reinterpret_cast<__nv_bfloat16 *>(wb + o_u2);
-    p->ws.up3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_u3);
     p->ws.amax_val = reinterpret_cast<float *>(wb + o_av);
     p->ws.amax_idx = reinterpret_cast<int *>(wb + o_ai);
     p->ws.st_scratch = reinterpret_cast<uint4 *>(wb + o_sc);
@@ -502,6 +524,7 @@ extern "C" int ofb_policy_destroy(ofb_policy *p) {
     cudaSetDevice(p->device);
     cudaFree(p->arena_blob);
     cudaFree(p->work_blob);
+    cudaFree(p->wide_blob);
     if (p->prof) {
         for (auto &e : *static_cast<std::vector<ProfEvent> *>(p->prof)) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
         delete static_cast<std::vector<ProfEvent> *>(p->prof);
@@ -1178,6 +1201,31 @@ struct ProfScope {
         }
     }
 };
+// The intermediates only the alternative kernels (dense / unfused trunk, two-kernel tail, CUDA-core engine) and the validation
+// taps need -- pool1, pool2, pool3, upconv3's output: 1.5 MB per ship -- live in a second allocation made on first use, so that
+// the default path can be created for 131 072 ships (24 GB) instead of 220 GB.
+static int ensure_wide_workspace(ofb_policy *p) {
+    if (p->wide_blob) return OFB_OK;
+    const size_t C = (size_t)p->max_ships;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) & ~(size_t)255; return o; };
+    const size_t o_p1 = take(C * 200 * 200 * 8 * 2), o_p2 = take(C * 100 * 100 * 8 * 2), o_p3 = take(C * 50 * 50 * 8 * 2);
+    const size_t o_u3 = take(C * POL_UP3_ITEM * 2);
+    const cudaError_t e = cudaMalloc(&p->wide_blob, off);
+    if (e != cudaSuccess) {
+        p->wide_blob = nullptr;
+        ofb_set_error("ofb_policy: cudaMalloc(%zu bytes of intermediates for %d ships: alternative kernels / taps) failed: %s", off, p->max_ships,
+                      cudaGetErrorString(e));
+        return OFB_E_NOMEM;
+    }
+    char *wb = static_cast<char *>(p->wide_blob);
+    p->ws.pool1 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p1);
+    p->ws.pool2 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p2);
+    p->ws.pool3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_p3);
+    p->ws.up3 = reinterpret_cast<__nv_bfloat16 *>(wb + o_u3);
+    return OFB_OK;
+}
+
 static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, int A, int P, float *act, float *ptr, int32_t *iact,
                          int32_t *xy, cudaStream_t st) {
     const PolicyDev &w = p->w;
@@ -1185,6 +1233,8 @@ static int forward_chunk(ofb_policy *p, const uint32_t *maps, const float *vec, 
     const int S = A * P;
     const bool tc = p->engine == OFB_ENGINE_TENSOR;
     int rc;
+    if (!tc || p->dense_trunk || p->unfused_trunk || p->unfused_tail || p->taps)
+        if ((rc = ensure_wide_workspace(p)) != OFB_OK) return rc;
     if (tc && !p->dense_trunk && !p->unfused_trunk) {
         // the whole trunk (conv1 .. conv4 + pools) in one sparse kernel: pool2 / pool3 never reach HBM (unless taps are on)
         ProfScope ps(p, L_TRUNK12, st);
@@ -1395,6 +1445,11 @@ __global__ void k_pairs_to_nhwc(const uint8_t *__restrict__ src, __nv_bfloat16 *
 extern "C" int ofb_policy_debug_tap(ofb_policy *p, int which, int64_t n_items, void *dst_dev, void *stream) {
     if (!p || !dst_dev || n_items < 0 || n_items > p->max_ships) { ofb_set_error("ofb_policy_debug_tap: bad argument"); return OFB_E_ARG; }
     const bool fused = p->engine == OFB_ENGINE_TENSOR && !p->unfused_tail;
+    if ((which == 0 || which == 1 || which == 2 || which == 6) && !p->wide_blob) {
+        ofb_set_error("ofb_policy_debug_tap: tap %d was not produced -- the default path keeps it on chip; enable taps (ofb_policy_set_taps) or "
+                      "select the alternative kernels before the forward", which);
+        return OFB_E_STATE;
+    }
     if (which == 5 && fused) {                                   // the fused tail takes upconv2's output in the pairs layout
         const long long np = n_items * 10000;
         if (np) k_pairs_to_nhwc<<<(unsigned)((np + 255) / 256), 256, 0, (cudaStream_t)stream>>>(

@@ -50,6 +50,7 @@ struct PolicyDev {
     __nv_bfloat16 *c2_st, *c3_st, *c4_st;   // conv2..4 as B operands of the sparse tensor trunk: [8 k-steps][2 chunks][32 n = px*8 + cout][8 cin]
     __nv_bfloat16 *sp_bg3, *sp_bg4;         // [9][8] pool3 / pool4 of an empty arena per border class
     uint8_t *tail_blob;       // operands + constants of the fused tail kernel (ofb_policy_tail.cuh: TL_WBYTES)
+    uint8_t *tail_blob2;      // the same for CTA pairs: [2 ranks][TL_WBYTES_H], each rank's half of every operand's columns
 };
 
 struct PolicyWork {
@@ -80,6 +81,7 @@ struct ofb_policy {
     int dense_trunk;          // 1 = the dense tcgen05 trunk12 (k_tz_trunk12); 2 = the CUDA-core sparse one (k_sp_trunk12); 0 = sparse + tcgen05 (k_st_trunk12)
     int unfused_trunk;        // 1 = trunk12, conv3, conv4 as three kernels through HBM; 0 = the whole trunk in k_st_trunk
     int unfused_tail;         // 1 = upconv3 / upconv4 as two kernels through HBM (k_tz_up3, k_tz_up4); 0 = the fused tail (k_tz_tail)
+    int tail_pair;            // 1 = the fused tail runs as CTA pairs (tcgen05 cta_group::2, M = 256); 0 = one CTA per SM on its own
     int taps;                 // 1 = the fused tail also writes upconv3's output (validation taps)
     int bilinear_legacy;      // 0 = TF2 half-pixel bilinear x2 (default), 1 = TF1.x legacy (asymmetric) UpSampling2D
     int profiling;            // when set, forward brackets every kernel with CUDA events
@@ -87,6 +89,7 @@ struct ofb_policy {
     void *arena_blob;         // single allocation holding all weights
     size_t arena_bytes;
     void *work_blob;          // single allocation holding the workspace
+    void *wide_blob;          // second allocation (on first use): pool1 / pool2 / pool3 / up3 of the alternative kernels and the taps
 };
 
 void ofb_set_error(const char *fmt, ...);

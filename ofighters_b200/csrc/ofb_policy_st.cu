@@ -113,7 +113,8 @@ struct StGatherCompact {
     uint4 *atile;
     // Straight-line code (no branches, every load's address is valid): the items of a thread overlap in the pipeline.  An entry
     // is fetched through a shared-memory ADDRESS chosen among {V entry, class value, zeros}, not a value select.
-    __device__ __forceinline__ void operator()(int tb, int nb) const {
+    __device__ __forceinline__ void operator()(int tb, int nb, long long *gst = nullptr) const {
+        if (gst) gst[0] = clock64();
         const uint32_t v16 = smem_u32(V), bg16 = smem_u32(bg), zero16 = bg16 + 9 * 16;
         constexpr int NK = (512 + ST_NT - 1) / ST_NT;
         uint32_t addr[NK][4];
@@ -141,12 +142,14 @@ struct StGatherCompact {
                 addr[k][j] = ad;
             }
         }
+        if (gst) gst[1] = clock64() + (addr[0][0] & 0u) + (addr[NK - 1][3] & 0u);
 #pragma unroll
         for (int k = 0; k < NK; k++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(val[k][j].x), "=r"(val[k][j].y), "=r"(val[k][j].z), "=r"(val[k][j].w) : "r"(addr[k][j]) : "memory");
+        if (gst) gst[2] = clock64() + (val[0][0].x & 0u) + (val[NK - 1][3].w & 0u);
 #pragma unroll
         for (int k = 0; k < NK; k++) {
             const int idx = (int)threadIdx.x + ST_NT * k, c = idx & 127, r = idx >> 7;
@@ -164,7 +167,7 @@ struct StGatherDense {
     const uint4 *src;
     const uint16_t *list;
     uint4 *atile;
-    __device__ __forceinline__ void operator()(int tb, int nb) const {
+    __device__ __forceinline__ void operator()(int tb, int nb, long long * = nullptr) const {
         for (int idx = threadIdx.x; idx < 2048; idx += ST_NT) {
             const int j = idx & 3, c = (idx >> 2) & 127, row = idx >> 9;
             if (c >= nb) continue;
@@ -189,7 +192,7 @@ __device__ __forceinline__ void st_tiles(const G &gather, const uint16_t *list, 
     constexpr uint32_t IDESC = instr_desc(32);
     for (int tb = 0; tb < n; tb += 128) {
         const int nb = min(128, n - tb);
-        gather(tb, nb);
+        gather(tb, nb, (stamp && tb == 0) ? stamp + 12 : nullptr);
         if (stamp && tb == 0) stamp[0] = clock64();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMAs
         tc_fence_before();
@@ -312,7 +315,7 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     for (int a = blockIdx.x; a < n_items; a += gridDim.x) {
         it++;
         ST_STAMP(0);
-        long long *tstamp = (stamps && blockIdx.x == 0 && tid == 0 && it < 8) ? stamps + 128 + it * 32 : nullptr;
+        long long *tstamp = (stamps && blockIdx.x == 0 && tid == 0 && it < 8) ? stamps + 128 + it * 48 : nullptr;
         const uint32_t *src = maps + (size_t)a * 2 * POL_WORDS;
         __nv_bfloat16 *dsta = out + (size_t)a * 100 * 100 * 8;
         // ---- 1. maps -> shared memory; the output's empty-arena values meanwhile
@@ -555,11 +558,11 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             if (compact) {
                 const StGatherCompact<100, 50, 4, false> g3 = {d2, p2, 0, v2, bgc2, l3, atile};
                 st_tiles(g3, l3, n3, atile, b34_16, b34, v3, false, tmem_base, &mbar[1], n_mma, &mbar[2], n_b34 & 1u, nullptr, nullptr,
-                         nullptr, nullptr, tstamp ? tstamp + 4 : nullptr);
+                         nullptr, nullptr, tstamp ? tstamp + 16 : nullptr);
                 ST_STAMP(12);
                 const StGatherCompact<50, 25, 2, false> g4 = {d3, p3, 0, v3, bgc3, l4, atile};
                 st_tiles(g4, l4, n4, atile, b34_16 + StSmem::b_bytes / 16, b34 + 8, flat_a, true, tmem_base, &mbar[1], n_mma, nullptr, 0u,
-                         nullptr, nullptr, nullptr, nullptr, tstamp ? tstamp + 8 : nullptr);
+                         nullptr, nullptr, nullptr, nullptr, tstamp ? tstamp + 32 : nullptr);
             } else {
                 const StGatherDense<100, 50> g3 = {scr2, l3, atile};
                 st_tiles(g3, l3, n3, atile, b34_16, b34, scr3, true, tmem_base, &mbar[1], n_mma, &mbar[2], n_b34 & 1u, nullptr, nullptr,

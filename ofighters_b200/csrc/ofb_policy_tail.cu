@@ -43,6 +43,54 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // order-preserving map float -> int (for an atomic maximum on values of either sign)
 __device__ __forceinline__ int okey(float v) { const int b = __float_as_int(v); return b >= 0 ? b : b ^ 0x7fffffff; }
 
+// ---- CTA pairs (cta_group::2): M = 256 MMAs over two CTAs of a cluster, each supplying its own 128 A rows and HALF of the B columns
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+// wait for a phase completed by an arrival from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        if (++spins > (1u << 24)) __trap();
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+template <bool PAIR>
+__device__ __forceinline__ void tl_commit(uint64_t *bar) {
+    if constexpr (PAIR)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                     "h"((uint16_t)3) : "memory");
+    else
+        tc_commit(bar);
+}
+template <bool PAIR>
+__device__ __forceinline__ void tl_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (PAIR)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        tc_mma(d_tmem, a_desc, b_desc, idesc, accumulate);
+}
+// kind::f16 instruction descriptor of the pair: M = 256
+__host__ __device__ constexpr uint32_t instr_desc_m(int n, int m) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
 struct TlArgs {
     const uint8_t *in;                // upconv2's output, pairs layout [item][3 planes][TL_UP2_PLANE][16 B]
     const uint8_t *wblob;             // TL_WBYTES of operands + constants (pack_tail in ofb_policy.cu)
@@ -65,7 +113,8 @@ struct TlSmem {
     static constexpr unsigned off_misc = off_a3 + 2 * 3 * TL_A3_SLOTS * 16;          // corners[2][4], vship, si[4]
     static constexpr unsigned off_bar = off_misc + 32 * 4;
     // barriers: wbar, a3_full[2], a3_empty[2], d3_full[2], d3_empty[2], d3v_empty, ring_full[3], ring_free[3], d4_full[2], d4_empty[2]
-    static constexpr unsigned n_bar = 1 + 2 + 2 + 2 + 2 + 1 + 3 + 3 + 2 + 2;
+    // ... and, for CTA pairs, peer3[2], peer4[2]: the peer's "tile g may be issued" of upconv3 / upconv4 (arrivals from the other CTA)
+    static constexpr unsigned n_bar = 1 + 2 + 2 + 2 + 2 + 1 + 3 + 3 + 2 + 2 + 4;
     static constexpr unsigned total = off_bar + n_bar * 8 + 16;
 };
 static_assert(TlSmem::total <= 232448, "k_tz_tail: shared memory over the 227 KB limit");
@@ -82,19 +131,26 @@ __device__ __forceinline__ void ring_store(uint4 *ring, int plane, int slot, int
     if (slot == 2 && rel >= 64 && rel < 128) ring[plane * TL_RING + phys - 384] = v;        // mirror in front of slot 0
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(TL_NT, 1)
 k_tz_tail(const TlArgs a, const int n_ships) {
+    // operand geometry: a CTA of a pair holds HALF of every B operand's N columns (its rank's half), so every operand offset,
+    // block stride and chunk distance (LBO) is halved; A operands, TMEM columns and every drain are unchanged
+    constexpr uint32_t H = PAIR ? 2u : 1u;
+    constexpr int MM = PAIR ? 256 : 128;
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;
+    const bool leader = !PAIR || rank == 0u;
     extern __shared__ __align__(128) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint4 *ring = reinterpret_cast<uint4 *>(smem + TlSmem::off_ring);
-    const float *wf = reinterpret_cast<const float *>(smem + TlSmem::off_w + TL_OFF_AUX);   // bias3[8], corner weights [4][2][2][8]
+    const float *wf = reinterpret_cast<const float *>(smem + TlSmem::off_w + TL_OFF_AUX / (PAIR ? 2 : 1));   // bias3[8], corner weights [4][2][2][8]
     float *corners = reinterpret_cast<float *>(smem + TlSmem::off_misc);                  // [2][4]
     int *vship = reinterpret_cast<int *>(smem + TlSmem::off_misc) + 8;
     int *si = reinterpret_cast<int *>(smem + TlSmem::off_misc) + 16;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + TlSmem::off_bar);
     uint64_t *wbar = bars, *a3_full = bars + 1, *a3_empty = a3_full + 2, *d3_full = a3_empty + 2, *d3_empty = d3_full + 2,
              *d3v_empty = d3_empty + 2, *ring_full = d3v_empty + 1, *ring_free = ring_full + 3, *d4_full = ring_free + 3,
-             *d4_empty = d4_full + 2;
+             *d4_empty = d4_full + 2, *peer3 = d4_empty + 2, *peer4 = peer3 + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + TlSmem::off_bar + TlSmem::n_bar * 8);
 
     // the ring starts out as zeros: rows nobody has written yet are read (by M rows whose outputs are discarded) and must
@@ -113,30 +169,41 @@ k_tz_tail(const TlArgs a, const int n_ships) {
         }
         mbar_init(d3v_empty, 4);
         for (int s = 0; s < 3; s++) { mbar_init(&ring_full[s], 4); mbar_init(&ring_free[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&peer3[s], 1); mbar_init(&peer4[s], 1); }
         *vship = (int)0x80000000;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {
+    fence_async_smem();                                   // the zeros above vs. the MMAs' (async proxy) reads
+    if constexpr (PAIR) {
+        __syncthreads();
+        cluster_sync_all();                               // both CTAs' barriers exist before anything can arrive on them
+        if (warp == 0) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        }
+    } else if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
-    fence_async_smem();                                   // the zeros above vs. the MMAs' (async proxy) reads
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int n_mine = (n_ships - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // ships of this CTA
+    // ships of this CTA; a pair works in lockstep, so both CTAs take the same count (a CTA past the end repeats the last ship)
+    const int n_mine = PAIR ? (n_ships + (int)gridDim.x - 1) / (int)gridDim.x : (n_ships - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int n_tiles = n_mine * TL_TILES;
+    auto ship_of = [&](int k) { return (size_t)min((long long)blockIdx.x + (long long)k * gridDim.x, (long long)n_ships - 1); };
 
     if (warp == 12) {
         // ------------------------------------------------------------ producer: weights once, then one input tile per step
         if (lane == 0) {
-            mbar_expect_tx(wbar, TL_WBYTES);
-            for (unsigned off = 0; off < TL_WBYTES; off += 30720)
-                bulk_g2s(smem + TlSmem::off_w + off, a.wblob + off, min(30720u, TL_WBYTES - off), wbar);
+            constexpr unsigned WB = PAIR ? TL_WBYTES_H : TL_WBYTES;
+            const uint8_t *wsrc = a.wblob + (PAIR ? (size_t)rank * TL_WBYTES_H : 0);
+            mbar_expect_tx(wbar, WB);
+            for (unsigned off = 0; off < WB; off += 30720) bulk_g2s(smem + TlSmem::off_w + off, wsrc + off, min(30720u, WB - off), wbar);
             for (int g = 0; g < n_tiles; g++) {
                 const int s = g & 1, k = g / TL_TILES, t = g - k * TL_TILES;
-                const size_t ship = (size_t)blockIdx.x + (size_t)k * gridDim.x;
+                const size_t ship = ship_of(k);
                 if (g >= 2) mbar_wait(&a3_empty[s], (uint32_t)(((g >> 1) - 1) & 1));
                 mbar_expect_tx(&a3_full[s], 3u * TL_A3_SLOTS * 16);
                 uint8_t *dst = smem + TlSmem::off_a3 + s * (3 * TL_A3_SLOTS * 16);
@@ -148,63 +215,86 @@ k_tz_tail(const TlArgs a, const int n_ships) {
         }
         __syncwarp();
     } else if (warp == 13) {
-        // ------------------------------------------------------------ upconv3 MMAs (converged warp, one elected lane issues)
+        // ------------------------------------------------------------ upconv3 MMAs (converged warp, one elected lane issues).
+        // CTA pairs: the leader issues for both CTAs; the peer's warp only reports "my tile g may be issued" (input landed,
+        // TMEM stage drained) to the leader; the commits arrive on both CTAs' barriers.
         mbar_wait(wbar, 0);
-        const bool leader = elect_one();
-        const uint32_t b3 = smem_u32(smem + TlSmem::off_w + TL_OFF_B3) >> 4, b3v = smem_u32(smem + TlSmem::off_w + TL_OFF_B3V) >> 4;
+        const bool elected = elect_one(), issue = elected && leader;
+        const uint32_t b3 = smem_u32(smem + TlSmem::off_w + TL_OFF_B3 / H) >> 4, b3v = smem_u32(smem + TlSmem::off_w + TL_OFF_B3V / H) >> 4;
         const uint32_t ones16 = smem_u32(smem + TlSmem::off_ones) >> 4, ring16 = smem_u32(ring) >> 4;
-        const uint32_t bias16 = smem_u32(smem + TlSmem::off_w + TL_OFF_BIAS3) >> 4;
-        constexpr uint32_t ID128 = instr_desc(128), ID64 = instr_desc(64);
+        const uint32_t bias16 = smem_u32(smem + TlSmem::off_w + TL_OFF_BIAS3 / H) >> 4;
+        constexpr uint32_t ID128 = instr_desc_m(128, MM), ID64 = instr_desc_m(64, MM);
         int vq = 0;
         for (int g = 0; g < n_tiles; g++) {
             const int s = g & 1, t = g % TL_TILES;
+            const bool var_tile = t == 0 || t == TL_TILES - 1;
             mbar_wait(&a3_full[s], (uint32_t)((g >> 1) & 1));
             if (g >= 2) { mbar_wait(&d3_empty[s], (uint32_t)(((g >> 1) - 1) & 1)); tc_fence_after(); }
+            if (PAIR && var_tile && vq >= 1) { mbar_wait(d3v_empty, (uint32_t)((vq - 1) & 1)); tc_fence_after(); }
+            if constexpr (PAIR) {
+                if (!leader) {
+                    if (elected) mbar_arrive_remote(&peer3[s], 0u);
+                    if (var_tile) vq++;
+                    __syncwarp();
+                    continue;
+                }
+                mbar_wait_cluster(&peer3[s], (uint32_t)((g >> 1) & 1));
+                tc_fence_after();
+            }
             const uint32_t a16 = smem_u32(smem + TlSmem::off_a3 + s * (3 * TL_A3_SLOTS * 16)) >> 4;
             const uint32_t d = tmem_base + (uint32_t)(s * 128);
             // bias: A = a column of ones in K lane 0 (the second K chunk reads ring rows against zero weights)
-            const uint64_t ones_d = smem_desc(ones16, ring16 - ones16, 8), bias_d = smem_desc(bias16, 128, 8);
-            if (leader) tc_mma(d, ones_d, bias_d, ID128, 0u);
+            const uint64_t ones_d = smem_desc(ones16, ring16 - ones16, 8), bias_d = smem_desc(bias16, 128 / H, 8);
+            if (issue) tl_mma<PAIR>(d, ones_d, bias_d, ID128, 0u);
 #pragma unroll
             for (int u = 0; u < 3; u++)
 #pragma unroll
                 for (int ks = 0; ks < 2; ks++) {
                     // ks 0: chunks (PA[e], PB[e]); ks 1: (PA[e + 1], spare[e])
                     const uint64_t ad = smem_desc(a16 + (uint32_t)(26 * u + ks), ks ? 2u * TL_A3_SLOTS - 1u : (uint32_t)TL_A3_SLOTS, 8);
-                    const uint64_t bd = smem_desc(b3 + (uint32_t)((u * 2 + ks) * 2 * 128), 128, 8);
-                    if (leader) tc_mma(d, ad, bd, ID128, 1u);
+                    const uint64_t bd = smem_desc(b3 + (uint32_t)((u * 2 + ks) * 2 * (128 / H)), 128 / H, 8);
+                    if (issue) tl_mma<PAIR>(d, ad, bd, ID128, 1u);
                 }
-            if (t == 0 || t == TL_TILES - 1) {
+            if (var_tile) {
                 // top / bottom image row: the true (zero-padded) phase a = 0 / 1 of row i = 0 / 99 into their own columns
                 const int set = t == 0 ? 0 : 1;
-                if (vq >= 1) { mbar_wait(d3v_empty, (uint32_t)((vq - 1) & 1)); tc_fence_after(); }
-                if (leader) tc_mma(tmem_base + TL_TM_D3V, ones_d, bias_d, ID64, 0u);       // column n of the variant has channel n & 7 too
+                if (!PAIR && vq >= 1) { mbar_wait(d3v_empty, (uint32_t)((vq - 1) & 1)); tc_fence_after(); }
+                if (issue) tl_mma<PAIR>(tmem_base + TL_TM_D3V, ones_d, bias_d, ID64, 0u);       // column n of the variant has channel n & 7 too
 #pragma unroll
                 for (int ui = 0; ui < 2; ui++)
 #pragma unroll
                     for (int ks = 0; ks < 2; ks++) {
                         const int u = set == 0 ? ui + 1 : ui;
                         const uint64_t ad = smem_desc(a16 + (uint32_t)(26 * u + ks), ks ? 2u * TL_A3_SLOTS - 1u : (uint32_t)TL_A3_SLOTS, 8);
-                        const uint64_t bd = smem_desc(b3v + (uint32_t)((((set * 2 + ui) * 2) + ks) * 2 * 64), 64, 8);
-                        if (leader) tc_mma(tmem_base + TL_TM_D3V, ad, bd, ID64, 1u);
+                        const uint64_t bd = smem_desc(b3v + (uint32_t)((((set * 2 + ui) * 2) + ks) * 2 * (64 / H)), 64 / H, 8);
+                        if (issue) tl_mma<PAIR>(tmem_base + TL_TM_D3V, ad, bd, ID64, 1u);
                     }
                 vq++;
             }
-            if (leader) { tc_commit(&d3_full[s]); tc_commit(&a3_empty[s]); }
+            if (issue) { tl_commit<PAIR>(&d3_full[s]); tl_commit<PAIR>(&a3_empty[s]); }
             __syncwarp();
         }
     } else if (warp == 14) {
         // ------------------------------------------------------------ upconv4 MMAs
         mbar_wait(wbar, 0);
-        const bool leader = elect_one();
+        const bool elected = elect_one(), issue = elected && leader;
         const uint32_t ring16 = smem_u32(ring) >> 4;
-        const uint32_t b4 = smem_u32(smem + TlSmem::off_w + TL_OFF_B4) >> 4, b4v = smem_u32(smem + TlSmem::off_w + TL_OFF_B4V) >> 4;
-        constexpr uint32_t ID80 = instr_desc(80), ID48 = instr_desc(48), ID16 = instr_desc(16);
+        const uint32_t b4 = smem_u32(smem + TlSmem::off_w + TL_OFF_B4 / H) >> 4, b4v = smem_u32(smem + TlSmem::off_w + TL_OFF_B4V / H) >> 4;
+        constexpr uint32_t ID80 = instr_desc_m(80, MM), ID48 = instr_desc_m(48, MM), ID16 = instr_desc_m(16, MM);
         for (int g = 0; g < n_tiles; g++) {
             const int s = g & 1, t = g % TL_TILES, slot = t % 3;
             mbar_wait(&ring_full[slot], (uint32_t)((g / 3) & 1));
             if (lane == 0) TL_STAMP(g, 4);
             if (g >= 2) { mbar_wait(&d4_empty[s], (uint32_t)(((g >> 1) - 1) & 1)); tc_fence_after(); }
+            if constexpr (PAIR) {
+                if (!leader) {
+                    if (elected) mbar_arrive_remote(&peer4[s], 0u);
+                    __syncwarp();
+                    continue;
+                }
+                mbar_wait_cluster(&peer4[s], (uint32_t)((g >> 1) & 1));
+                tc_fence_after();
+            }
             if (lane == 0) TL_STAMP(g, 5);
             const uint32_t base = ring16 + (uint32_t)(TL_MARGIN - TL_UP4_LAG + 128 * slot);       // ring row of M row 128 t - 32
             const uint32_t d = tmem_base + (uint32_t)(TL_TM_D4 + 96 * s);
@@ -214,14 +304,14 @@ k_tz_tail(const TlArgs a, const int n_ships) {
                 const int dy = o == 0 ? 1 : (o == 1 ? 2 : (o == 2 ? 0 : 3));       // the full-width taps first (they zero the accumulator)
                 const int par = (dy + 1) & 1, voff = dy == 0 ? -TL_P : (dy == 3 ? TL_P : 0);
                 const int nn = (dy == 0 || dy == 3) ? 48 : 80;
-                const uint32_t boff = dy == 0 ? 0u : (dy == 1 ? 480u : (dy == 2 ? 1280u : 2080u));
+                const uint32_t boff = (dy == 0 ? 0u : (dy == 1 ? 480u : (dy == 2 ? 1280u : 2080u))) / H;
 #pragma unroll
                 for (int ks = 0; ks < 5; ks++) {
                     const int q0 = (ks == 0 || ks == 4) ? 0 : 2 * ks - 1, o0 = ks == 4 ? 1 : 0;
                     const uint32_t lbo = (ks == 0 || ks == 4) ? 7u * TL_RING - 1u : (uint32_t)TL_RING;
                     const uint64_t ad = smem_desc(base + (uint32_t)((par * 8 + q0) * TL_RING + voff + o0), lbo, 8);
-                    const uint64_t bd = smem_desc(b4 + boff + (uint32_t)(ks * 2 * nn), (uint32_t)nn, 8);
-                    if (leader) tc_mma(d + (dy == 3 ? 32u : 0u), ad, bd, nn == 80 ? ID80 : ID48, (o | ks) ? 1u : 0u);
+                    const uint64_t bd = smem_desc(b4 + boff + (uint32_t)(ks * 2 * (nn / (int)H)), (uint32_t)nn / H, 8);
+                    if (issue) tl_mma<PAIR>(d + (dy == 3 ? 32u : 0u), ad, bd, nn == 80 ? ID80 : ID48, (o | ks) ? 1u : 0u);
                 }
             }
             if (t == 0 || t == TL_TILES - 1) {
@@ -235,13 +325,13 @@ k_tz_tail(const TlArgs a, const int n_ships) {
                         const int q0 = (ks == 0 || ks == 4) ? 0 : 2 * ks - 1, o0 = ks == 4 ? 1 : 0;
                         const uint32_t lbo = (ks == 0 || ks == 4) ? 7u * TL_RING - 1u : (uint32_t)TL_RING;
                         const uint64_t ad = smem_desc(base + (uint32_t)((par * 8 + q0) * TL_RING + o0), lbo, 8);
-                        const uint64_t bd = smem_desc(b4v + (uint32_t)((((set * 2 + dyi) * 5) + ks) * 2 * 16), 16, 8);
-                        if (leader) tc_mma(d + 80u, ad, bd, ID16, (dyi | ks) ? 1u : 0u);
+                        const uint64_t bd = smem_desc(b4v + (uint32_t)((((set * 2 + dyi) * 5) + ks) * 2 * (16 / H)), 16 / H, 8);
+                        if (issue) tl_mma<PAIR>(d + 80u, ad, bd, ID16, (dyi | ks) ? 1u : 0u);
                     }
             }
-            if (leader) {
-                tc_commit(&d4_full[s]);
-                tc_commit(&ring_free[(slot + 2) % 3]);      // tile g - 1's ring slot (and, for a tile of slot 0, the mirror rows): no reader left
+            if (issue) {
+                tl_commit<PAIR>(&d4_full[s]);
+                tl_commit<PAIR>(&ring_free[(slot + 2) % 3]);      // tile g - 1's ring slot (and, for a tile of slot 0, the mirror rows): no reader left
             }
             __syncwarp();
         }
@@ -253,7 +343,7 @@ k_tz_tail(const TlArgs a, const int n_ships) {
         const int grp = warp >> 2, gw = warp & 3, r = tid & 127;
         for (int g = grp; g < n_tiles; g += 2) {
             const int s = grp, k = g / TL_TILES, t = g - k * TL_TILES, slot = t % 3;
-            const size_t ship = (size_t)blockIdx.x + (size_t)k * gridDim.x;
+            const size_t ship = ship_of(k);
             const int m = 128 * t + r, i = m / TL_P, xb = m - i * TL_P;
             const bool valid = xb < 25 && i < 100;
             mbar_wait(&d3_full[s], (uint32_t)((g >> 1) & 1));
@@ -357,7 +447,7 @@ k_tz_tail(const TlArgs a, const int n_ships) {
         int best_key = (int)0x80000000, best_idx = 0x7fffffff;
         for (int g = 0; g < n_tiles; g++) {
             const int s = g & 1, k = g / TL_TILES, t = g - k * TL_TILES;
-            const size_t ship = (size_t)blockIdx.x + (size_t)k * gridDim.x;
+            const size_t ship = ship_of(k);
             const int m = 128 * t - TL_UP4_LAG + l, mm = max(m, 0), i = mm / TL_P, xb = mm - i * TL_P;
             const bool valid = m >= 0 && xb < 25 && i < 100;
             const bool var_tile = t == 0 || t == TL_TILES - 1;
@@ -463,7 +553,12 @@ k_tz_tail(const TlArgs a, const int n_ships) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    if constexpr (PAIR) {
+        cluster_sync_all();                               // the peer's MMAs / commits no longer touch this CTA
+        if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    } else if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
 }
 
 static long long *g_tail_stamps = nullptr;
@@ -471,8 +566,7 @@ extern "C" int ofb_policy_tail_stamps(long long *dev_buf) { g_tail_stamps = dev_
 
 int pol_tz_tail(const ofb_policy *p, const __nv_bfloat16 *up2_pairs, float *ptr_out, int32_t *xy, __nv_bfloat16 *up3_dbg, int n_items,
                 cudaStream_t st) {
-    static thread_local SmemAttrCache attr = {};
-    OFB_CUDA_CHECK(attr.ensure(k_tz_tail, (int)TlSmem::total));
+    static thread_local SmemAttrCache attr = {}, attr2 = {};
     int n_sm = 148;
     OFB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, p->device));
     if (n_items == 0) return OFB_OK;
@@ -484,7 +578,28 @@ int pol_tz_tail(const ofb_policy *p, const __nv_bfloat16 *up2_pairs, float *ptr_
     a.xy = xy;
     a.up3_dbg = up3_dbg;
     a.stamps = g_tail_stamps;
-    k_tz_tail<<<n_items < n_sm ? n_items : n_sm, TL_NT, TlSmem::total, st>>>(a, n_items);
+    if (p->tail_pair) {
+        // CTA pairs: clusters of 2 (one CTA per SM, both SMs of a TPC), an even grid
+        OFB_CUDA_CHECK(attr2.ensure(k_tz_tail<true>, (int)TlSmem::total));
+        a.wblob = reinterpret_cast<const uint8_t *>(p->w.tail_blob2);
+        int grid = n_items < n_sm ? n_items : n_sm;
+        grid = (grid + 1) & ~1;
+        if (grid > n_sm) grid -= 2;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(TL_NT);
+        cfg.dynamicSmemBytes = TlSmem::total;
+        cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        OFB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tz_tail<true>, a, n_items));
+        return OFB_OK;
+    }
+    OFB_CUDA_CHECK(attr.ensure(k_tz_tail<false>, (int)TlSmem::total));
+    k_tz_tail<false><<<n_items < n_sm ? n_items : n_sm, TL_NT, TlSmem::total, st>>>(a, n_items);
     OFB_CUDA_CHECK(cudaGetLastError());
     return OFB_OK;
 }

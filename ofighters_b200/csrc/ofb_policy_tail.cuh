@@ -19,3 +19,6 @@
 #define TL_OFF_AUX (TL_OFF_BIAS3 + 4096)
 #define TL_AUX_FLOATS (8 + 128)
 #define TL_WBYTES (TL_OFF_AUX + TL_AUX_FLOATS * 4)
+// CTA pairs (cta_group::2): each CTA of a pair holds HALF of every B operand's N columns -- rank r the columns [r N/2, (r + 1) N/2) --
+// in the same block order, so every operand offset above is halved; the floats follow at TL_OFF_AUX / 2.  Blob: [2 ranks][TL_WBYTES_H]
+#define TL_WBYTES_H (TL_OFF_AUX / 2 + TL_AUX_FLOATS * 4)

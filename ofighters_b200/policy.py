@@ -57,15 +57,16 @@ def _ptr(t):
 
 
 class PolicyB200:
-    def __init__(self, weights, device=None, max_ships=1024, bilinear="tf2", fused_tail=True, dense_trunk=False, cc_sparse_trunk=False, fused_trunk=True):
+    def __init__(self, weights, device=None, max_ships=1024, bilinear="tf2", fused_tail=True, dense_trunk=False, cc_sparse_trunk=False, fused_trunk=True, tail_pair=False):
         """``bilinear``: "tf2" (half-pixel centres, the default of every TF2 / Keras >= 2.3 UpSampling2D) or "tf1" (the legacy
         asymmetric kernel of TF1.x / standalone Keras 2.2) -- the reference pins no version (requirements.txt:1-2), so the
-        choice is the caller's.  ``fused_tail=False`` / ``dense_trunk=True`` select the alternative kernels (measurement aids)."""
+        choice is the caller's.  ``fused_tail=False`` / ``dense_trunk=True`` / ``tail_pair=True`` select the alternative kernels (measurement aids)."""
         if bilinear not in ("tf2", "tf1"):
             raise Exception("bilinear must be 'tf2' or 'tf1'")
         self.bilinear = bilinear
         self._flags = (_lib.POLICY_BILINEAR_TF1 if bilinear == "tf1" else 0) | (0 if fused_tail else _lib.POLICY_UNFUSED_TAIL) | \
-            (_lib.POLICY_DENSE_TRUNK if dense_trunk else 0) | (_lib.POLICY_CC_SPARSE_TRUNK if cc_sparse_trunk else 0) | (0 if fused_trunk else _lib.POLICY_UNFUSED_TRUNK)
+            (_lib.POLICY_DENSE_TRUNK if dense_trunk else 0) | (_lib.POLICY_CC_SPARSE_TRUNK if cc_sparse_trunk else 0) | (0 if fused_trunk else _lib.POLICY_UNFUSED_TRUNK) | \
+            (_lib.POLICY_TAIL_PAIR if tail_pair else 0)
         self.fused_tail = bool(fused_tail) and not os.environ.get("OFB_POLICY_UNFUSED_TAIL", "").strip("0")
         self.fused_trunk = bool(fused_trunk) and not dense_trunk and not os.environ.get("OFB_POLICY_UNFUSED_TRUNK", "").strip("0") \
             and not os.environ.get("OFB_POLICY_DENSE_TRUNK", "").strip("0")

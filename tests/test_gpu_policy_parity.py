@@ -176,3 +176,21 @@ def test_fused_tail_equals_two_kernel_tail_decisions(scenes, weight_sets):
     assert d <= 1.5e-2 and agree >= 0.9                     # measured 1.0e-2 / 0.92 (tf32 upconv2 vs fp32 in the two-kernel path): plateau ties
     i2, xy2 = a.forward_argmax(maps, vec, 1)
     assert torch.equal(xy2, ra["xy"]) and torch.equal(i2, ra["iaction"])
+
+
+@pytest.mark.parametrize("n", [1, 5, 149])
+def test_cta_pair_tail_equals_single_cta_tail(scenes, weight_sets, n):
+    """The fused tail as CTA pairs (tcgen05 cta_group::2: M = 256 MMAs over two SMs, each holding half of every weight operand's
+    columns) gives bit-identical pointer maps and decisions, for ship counts that leave a pair's second CTA without a ship of its
+    own (odd counts, fewer ships than CTAs)."""
+    from ofighters_b200.policy import PolicyB200
+    w = weight_sets["random_bn"]
+    maps, obs = scenes["frame40"]
+    maps, vec = maps[:n].contiguous(), obs[:n, 0, :].contiguous()
+    a = PolicyB200(w, max_ships=max(16, n))
+    b = PolicyB200(w, max_ships=max(16, n), tail_pair=True)
+    ra, rb = a.forward(maps, vec, 1, want_ptr=True), b.forward(maps, vec, 1, want_ptr=True)
+    assert torch.equal(ra["ptr"], rb["ptr"]) and torch.equal(ra["xy"], rb["xy"]) and torch.equal(ra["iaction"], rb["iaction"])
+    ia, xya = a.forward_argmax(maps, vec, 1)
+    ib, xyb = b.forward_argmax(maps, vec, 1)
+    assert torch.equal(xya, xyb) and torch.equal(ia, ib)
