@@ -54,8 +54,8 @@ struct StSmem {
     static constexpr int off_v2 = off_b + b_bytes;                     // uint4 [VCAP]: pool2's dirty cells, raster order
     static constexpr int off_misc = off_v2 + ST_VCAP * 16;             // c1 bias [8], conv2 bias [8], conv3 / conv4 bias [16] f32, bg1 (uint4),
                                                                        // band ints [8], scan [16], bg1 / bg2 / bg3 classes: 3 x uint4 [9 + a zero entry]
-    static constexpr int off_bar = off_misc + 32 + 32 + 64 + 16 + 32 + 64 + 160 + 160 + 160;    // 3 mbarriers, tmem slot
-    static constexpr int bytes = off_bar + 24 + 8;
+    static constexpr int off_bar = off_misc + 32 + 32 + 64 + 16 + 32 + 64 + 160 + 160 + 160;    // 6 mbarriers, tmem slot
+    static constexpr int bytes = off_bar + 48 + 8;
     // levels 3 / 4: conv3's and conv4's B operands and V3 over the dead V1 .. P1
     static constexpr int off_b34 = off_v1;
     static constexpr int off_v3 = off_v1 + 2 * b_bytes;
@@ -111,53 +111,63 @@ struct StGatherCompact {
     const uint4 *V, *bg;                                   // bg[9] classes (bg[0] only when CONST_BG), bg[9] = zeros
     const uint16_t *list;
     uint4 *atile;
-    // Straight-line code (no branches, every load's address is valid): the items of a thread overlap in the pipeline.  An entry
-    // is fetched through a shared-memory ADDRESS chosen among {V entry, class value, zeros}, not a value select.
-    __device__ __forceinline__ void operator()(int tb, int nb, long long *gst = nullptr) const {
-        if (gst) gst[0] = clock64();
+    // A thread of warps 4 .. (the draining warps 0 - 3 sit the gather out) takes TWO patch rows of one cell: the cell is decoded
+    // once, and the code is straight-line (no data-dependent branches, every load's address is valid) so that the two rows overlap
+    // in the pipeline.  An entry is fetched through a shared-memory ADDRESS chosen among {V entry, class value, zeros}.
+    __device__ __forceinline__ void operator()(int tb, int nb) const {
+        static_assert(ST_NT >= 384, "two rows per thread need 256 gathering threads");
+        const int t = (int)threadIdx.x - 128, c = t & 127, r0 = (t >> 7) * 2;
+        if (t < 0 || t >= 256 || (c & ~31) >= nb) return;                // (warp-uniform)
         const uint32_t v16 = smem_u32(V), bg16 = smem_u32(bg), zero16 = bg16 + 9 * 16;
-        constexpr int NK = (512 + ST_NT - 1) / ST_NT;
-        uint32_t addr[NK][4];
-        uint4 val[NK][4];
+        const bool on = c < nb;
+        const int cell = list[tb + (on ? c : 0)], Y = cell / NDST, X = cell - Y * NDST, x0 = 2 * X - 1;
+        const int start = max(x0, 0), w = start >> 5, sh = start & 31;
+        const uint32_t below = (1u << sh) - 1u;
+        uint32_t addr[2][4];
+        uint4 val[2][4];
 #pragma unroll
-        for (int k = 0; k < NK; k++) {
-            const int idx = (int)threadIdx.x + ST_NT * k, c = idx & 127, r = idx >> 7;
-            const bool on = idx < 512 && c < nb;
-            const int cell = list[tb + (on ? c : 0)], Y = cell / NDST, X = cell - Y * NDST, qy = 2 * Y - 1 + r, x0 = 2 * X - 1;
+        for (int k = 0; k < 2; k++) {
+            const int qy = 2 * Y - 1 + r0 + k;
             const bool row_in = qy >= 0 && qy < NSRC;
-            const int qc = min(max(qy, 0), NSRC - 1), start = max(x0, 0), w = start >> 5, sh = start & 31;
+            const int qc = min(max(qy, 0), NSRC - 1);
             const uint32_t lo = D[qc * RW + w], hi = D[qc * RW + w + 1];        // (hi matters only inside the row: see the masks of D)
             const int pw = P[qc * RW + w];
             uint32_t m = __funnelshift_r(lo, hi, sh) & 0xFu;
             if (x0 < 0) m = (m << 1) & 0xFu;
             if (!row_in) m = 0u;
-            const uint32_t vi = v16 + (uint32_t)(pw - base + __popc(lo & ((1u << sh) - 1u))) * 16u;
+            const uint32_t vi = v16 + (uint32_t)(pw - base + __popc(lo & below)) * 16u;
             const uint32_t cls16 = CONST_BG ? bg16 : bg16 + (uint32_t)(st_cls(qc, NSRC) * 3) * 16u;
+            // interior columns: a dirty entry = the next V entry of the row, anything else = the row's middle class (or zeros)
+            const uint32_t plain = !row_in ? zero16 : (CONST_BG ? cls16 : cls16 + 16u);
+            uint32_t nextv = vi;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const int qx = x0 + j;
-                uint32_t ad = CONST_BG ? cls16 : cls16 + (qx <= 0 ? 0u : (qx >= NSRC - 1 ? 32u : 16u));
-                if (!row_in || qx < 0 || qx >= NSRC) ad = zero16;
-                if ((m >> j) & 1u) ad = vi + (uint32_t)__popc(m & ((1u << j) - 1u)) * 16u;
-                addr[k][j] = ad;
+                const bool dirty = (m >> j) & 1u;
+                addr[k][j] = dirty ? nextv : plain;
+                nextv += dirty ? 16u : 0u;
+            }
+            if (X == 0 || X == NDST - 1) {                 // first / last cell of a row: the grid's border column and the padding
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int qx = x0 + j;
+                    if ((m >> j) & 1u) continue;
+                    if (!row_in || qx < 0 || qx >= NSRC) addr[k][j] = zero16;
+                    else if (!CONST_BG && (qx == 0 || qx == NSRC - 1)) addr[k][j] = cls16 + (qx == 0 ? 0u : 32u);
+                }
             }
         }
-        if (gst) gst[1] = clock64() + (addr[0][0] & 0u) + (addr[NK - 1][3] & 0u);
 #pragma unroll
-        for (int k = 0; k < NK; k++)
+        for (int k = 0; k < 2; k++)
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(val[k][j].x), "=r"(val[k][j].y), "=r"(val[k][j].z), "=r"(val[k][j].w) : "r"(addr[k][j]) : "memory");
-        if (gst) gst[2] = clock64() + (val[0][0].x & 0u) + (val[NK - 1][3].w & 0u);
+        if (on) {
+            uint4 *dst = atile + (r0 * 4) * 128 + c;
 #pragma unroll
-        for (int k = 0; k < NK; k++) {
-            const int idx = (int)threadIdx.x + ST_NT * k, c = idx & 127, r = idx >> 7;
-            if (idx < 512 && c < nb) {
-                uint4 *dst = atile + (r * 4) * 128 + c;
+            for (int k = 0; k < 2; k++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) dst[j * 128] = val[k][j];
-            }
+                for (int j = 0; j < 4; j++) dst[(k * 4 + j) * 128] = val[k][j];
         }
     }
 };
@@ -167,8 +177,8 @@ struct StGatherDense {
     const uint4 *src;
     const uint16_t *list;
     uint4 *atile;
-    __device__ __forceinline__ void operator()(int tb, int nb, long long * = nullptr) const {
-        for (int idx = threadIdx.x; idx < 2048; idx += ST_NT) {
+    __device__ __forceinline__ void operator()(int tb, int nb) const {
+        for (int idx = (int)threadIdx.x - 128; idx < 2048; idx += ST_NT - 128) {                 // (the gathering warps 4 ..)
             const int j = idx & 3, c = (idx >> 2) & 127, row = idx >> 9;
             if (c >= nb) continue;
             const int cell = list[tb + c], Y = cell / NDST, X = cell - Y * NDST, qy = 2 * Y - 1 + row, qx = 2 * X - 1 + j;
@@ -179,52 +189,59 @@ struct StGatherDense {
     }
 };
 
-// One level: the `n` cells of `list`, 128 per MMA tile: gather -> 8 MMAs (N = 32) -> drain (+ bias, max over the cell's 4 conv
-// pixels, ReLU, bf16) into dst[list[.]] (by_list) or dst[position in the list].  Only the draining warps wait for the MMAs;
-// everyone else goes on to the block barrier.  `pf_*`: after the gather of the level's LAST tile thread 0 may start a bulk
-// copy (the next levels' B operands into memory this level's gathers were the last readers of).
+// One level: the `n` cells of `list`, 128 per MMA tile, as a two-role pipeline.  Warps 4 .. gather tile t into the A tile (after the
+// MMAs of tile t - 1 have finished reading it), meet at a named barrier, and warp 4 issues the tile's 8 MMAs (N = 32) into TMEM
+// stage t & 1; warps 0 - 3 drain tile t - 1 meanwhile: + bias, max over the cell's 4 conv pixels, ReLU, bf16 into dst[list[.]]
+// (by_list) or dst[position in the list].  `gt` counts the tiles of the whole kernel (stage and barrier parities).  The level ends
+// with a block barrier: every drained cell is visible, TMEM and the A tile are free.  `pf_*`: after the gather of the level's LAST
+// tile one thread may start a bulk copy (the next levels' B operands into memory this level's gathers were the last readers of).
 template <class G>
 __device__ __forceinline__ void st_tiles(const G &gather, const uint16_t *list, int n, uint4 *atile, uint32_t b16, const float *bias,
-                                         uint4 *dst, bool by_list, uint32_t tmem_base, uint64_t *mma_bar, uint32_t &n_mma,
+                                         uint4 *dst, bool by_list, uint32_t tmem_base, uint64_t *mma_done, uint64_t *tfree, uint32_t &gt,
                                          uint64_t *wait_bar, uint32_t wait_parity, uint64_t *pf_bar, void *pf_dst, const void *pf_src0,
                                          const void *pf_src1, long long *stamp) {
     const int tid = threadIdx.x, warp = tid >> 5;
     constexpr uint32_t IDESC = instr_desc(32);
-    for (int tb = 0; tb < n; tb += 128) {
+    if (n <= 0) return;
+    for (int tb = 0; tb < n; tb += 128, gt++) {
         const int nb = min(128, n - tb);
-        gather(tb, nb, (stamp && tb == 0) ? stamp + 12 : nullptr);
-        if (stamp && tb == 0) stamp[0] = clock64();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMAs
-        tc_fence_before();
-        __syncthreads();
-        if (stamp && tb == 0) stamp[1] = clock64();
-        if (warp == 4) {
-            tc_fence_after();
-            if (wait_bar && tb == 0) mbar_wait(wait_bar, wait_parity);     // this level's B operand has landed
-            const bool leader = elect_one();
-            const uint32_t a16 = smem_u32(atile) >> 4;
+        const uint32_t stage = gt & 1u, use = gt >> 1;
+        if (warp >= 4) {
+            if (tb > 0) mbar_wait(&mma_done[stage ^ 1u], ((gt - 1u) >> 1) & 1u);       // the previous tile's MMAs have read the A tile
+            gather(tb, nb);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy writes -> visible to the MMAs
+            asm volatile("bar.sync 1, %0;" ::"n"(ST_NT - 128) : "memory");
+            if (warp == 4) {
+                if (wait_bar && tb == 0) mbar_wait(wait_bar, wait_parity);     // this level's B operand has landed
+                if (use >= 1u) { mbar_wait(&tfree[stage], (use - 1u) & 1u); tc_fence_after(); }   // the stage's last tile has been drained
+                const bool leader = elect_one();
+                const uint32_t a16 = smem_u32(atile) >> 4, d = tmem_base + stage * 32u;
 #pragma unroll
-            for (int ks = 0; ks < 8; ks++) {
-                const uint64_t ad = smem_desc(a16 + (uint32_t)(2 * ks * 128), 128, 8);
-                const uint64_t bd = smem_desc(b16 + (uint32_t)(ks * 2 * 32), 32, 8);
-                if (leader) tc_mma(tmem_base, ad, bd, IDESC, ks ? 1u : 0u);
+                for (int ks = 0; ks < 8; ks++) {
+                    const uint64_t ad = smem_desc(a16 + (uint32_t)(2 * ks * 128), 128, 8);
+                    const uint64_t bd = smem_desc(b16 + (uint32_t)(ks * 2 * 32), 32, 8);
+                    if (leader) tc_mma(d, ad, bd, IDESC, ks ? 1u : 0u);
+                }
+                if (leader) tc_commit(&mma_done[stage]);
+                __syncwarp();
+                if (pf_bar && tb + 128 >= n && elect_one()) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(pf_bar, 2 * StSmem::b_bytes);
+                    bulk_g2s(pf_dst, pf_src0, StSmem::b_bytes, pf_bar);
+                    bulk_g2s(reinterpret_cast<uint8_t *>(pf_dst) + StSmem::b_bytes, pf_src1, StSmem::b_bytes, pf_bar);
+                }
+                __syncwarp();
             }
-            if (leader) tc_commit(mma_bar);
-            __syncwarp();
-        }
-        if (pf_bar && tb + 128 >= n && tid == 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(pf_bar, 2 * StSmem::b_bytes);
-            bulk_g2s(pf_dst, pf_src0, StSmem::b_bytes, pf_bar);
-            bulk_g2s(reinterpret_cast<uint8_t *>(pf_dst) + StSmem::b_bytes, pf_src1, StSmem::b_bytes, pf_bar);
-        }
-        if (warp < 4) {
-            mbar_wait(mma_bar, n_mma & 1u);
+        } else {
+            mbar_wait(&mma_done[stage], use & 1u);
             tc_fence_after();
             if (stamp && tb == 0) stamp[2] = clock64();
             uint32_t r[32];
-            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16), r);
+            tc_ld32(tmem_base + stage * 32u + ((uint32_t)(warp * 32) << 16), r);
             tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&tfree[stage]);
             if (tid < nb) {
                 float o[8];
 #pragma unroll
@@ -233,12 +250,11 @@ __device__ __forceinline__ void st_tiles(const G &gather, const uint16_t *list, 
                                   fmaxf(__uint_as_float(r[16 + co]), __uint_as_float(r[24 + co]))) + bias[co];
                 dst[by_list ? (int)list[tb + tid] : tb + tid] = pack_relu_bf8(o);
             }
+            if (stamp && tb == 0) stamp[3] = clock64();
         }
-        n_mma++;
-        tc_fence_before();
-        __syncthreads();                                   // TMEM and the A tile are free again; the drained cells are visible
-        if (stamp && tb == 0) stamp[3] = clock64();
     }
+    tc_fence_before();
+    __syncthreads();
 }
 
 // raster-order list of the set bits of bitmap word `wd` (NW words per row, NCOL cells per row), starting at entry k
@@ -274,8 +290,9 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     int *band = reinterpret_cast<int *>(st_smem + StSmem::off_misc + 144);        // Y1, p_lo, p_hi of the current band; [4] n3, [5] n4
     int *scan = reinterpret_cast<int *>(st_smem + StSmem::off_misc + 176);        // warp totals of the row scan
     uint4 *bgc1 = reinterpret_cast<uint4 *>(st_smem + StSmem::off_misc + 240), *bgc2 = bgc1 + 10, *bgc3 = bgc2 + 10;   // [9] = zeros
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(st_smem + StSmem::off_bar);      // [0] maps landed, [1] MMAs done, [2] conv3 / conv4 operands landed
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_bar + 24);
+    // [0] maps landed, [1] [2] MMAs of TMEM stage 0 / 1 done, [3] [4] stage 0 / 1 drained, [5] conv3 / conv4 operands landed
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(st_smem + StSmem::off_bar);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(st_smem + StSmem::off_bar + 48);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (tid < 8) { c1b[tid] = w.c1_b[tid]; b2[tid] = w.cb[0][tid]; b34[tid] = w.cb[1][tid]; b34[8 + tid] = w.cb[2][tid]; }
@@ -291,6 +308,9 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         mbar_init(&mbar[2], 1);
+        mbar_init(&mbar[3], 4);
+        mbar_init(&mbar[4], 4);
+        mbar_init(&mbar[5], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < 8 * 2 * 32; i += ST_NT)
@@ -300,7 +320,7 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     const uint4 *bg4g = reinterpret_cast<const uint4 *>(w.sp_bg4);
     bool scratch_ready = false;                             // the fallback's dense images are initialised on first use
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(32u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(64u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // the B operand was written through the generic proxy
@@ -309,13 +329,13 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t b16 = smem_u32(st_smem + StSmem::off_b) >> 4, b34_16 = smem_u32(st_smem + StSmem::off_b34) >> 4;
-    uint32_t n_loads = 0, n_mma = 0, n_b34 = 0;
+    uint32_t n_loads = 0, gt = 0, n_b34 = 0;
 
     int it = -1;
     for (int a = blockIdx.x; a < n_items; a += gridDim.x) {
         it++;
         ST_STAMP(0);
-        long long *tstamp = (stamps && blockIdx.x == 0 && tid == 0 && it < 8) ? stamps + 128 + it * 48 : nullptr;
+        long long *tstamp = (stamps && blockIdx.x == 0 && tid == 0 && it < 8) ? stamps + 128 + it * 16 : nullptr;
         const uint32_t *src = maps + (size_t)a * 2 * POL_WORDS;
         __nv_bfloat16 *dsta = out + (size_t)a * 100 * 100 * 8;
         // ---- 1. maps -> shared memory; the output's empty-arena values meanwhile
@@ -530,7 +550,7 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
                 const StGatherCompact<200, 100, 7, true> g2 = {d1, p1, base1, v1, bgc1, l2, atile};
                 uint4 *dst2 = compact ? v2 : (fz.fuse ? scr2 : reinterpret_cast<uint4 *>(dsta));
                 const bool pf = compact && need_b34;
-                st_tiles(g2, l2, n2, atile, b16, b2, dst2, !compact, tmem_base, &mbar[1], n_mma, nullptr, 0u, pf ? &mbar[2] : nullptr,
+                st_tiles(g2, l2, n2, atile, b16, b2, dst2, !compact, tmem_base, &mbar[1], &mbar[3], gt, nullptr, 0u, pf ? &mbar[5] : nullptr,
                          st_smem + StSmem::off_b34, w.c3_st, w.c4_st, tstamp);
                 b34_issued = b34_issued || pf;
             }
@@ -547,9 +567,9 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             }
             if (need_b34 && !b34_issued && tid == 0) {     // conv3's and conv4's B operands over V1 (dead: the barrier above)
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&mbar[2], 2 * StSmem::b_bytes);
-                bulk_g2s(st_smem + StSmem::off_b34, w.c3_st, StSmem::b_bytes, &mbar[2]);
-                bulk_g2s(st_smem + StSmem::off_b34 + StSmem::b_bytes, w.c4_st, StSmem::b_bytes, &mbar[2]);
+                mbar_expect_tx(&mbar[5], 2 * StSmem::b_bytes);
+                bulk_g2s(st_smem + StSmem::off_b34, w.c3_st, StSmem::b_bytes, &mbar[5]);
+                bulk_g2s(st_smem + StSmem::off_b34 + StSmem::b_bytes, w.c4_st, StSmem::b_bytes, &mbar[5]);
             }
             __syncthreads();
             uint4 *flat_a = reinterpret_cast<uint4 *>(fz.flat + (size_t)a * POL_FLAT_PITCH);
@@ -557,19 +577,19 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
             //         (NHWC flatten = 16 bytes per cell, raster order)
             if (compact) {
                 const StGatherCompact<100, 50, 4, false> g3 = {d2, p2, 0, v2, bgc2, l3, atile};
-                st_tiles(g3, l3, n3, atile, b34_16, b34, v3, false, tmem_base, &mbar[1], n_mma, &mbar[2], n_b34 & 1u, nullptr, nullptr,
-                         nullptr, nullptr, tstamp ? tstamp + 16 : nullptr);
+                st_tiles(g3, l3, n3, atile, b34_16, b34, v3, false, tmem_base, &mbar[1], &mbar[3], gt, &mbar[5], n_b34 & 1u, nullptr, nullptr,
+                         nullptr, nullptr, tstamp ? tstamp + 4 : nullptr);
                 ST_STAMP(12);
                 const StGatherCompact<50, 25, 2, false> g4 = {d3, p3, 0, v3, bgc3, l4, atile};
-                st_tiles(g4, l4, n4, atile, b34_16 + StSmem::b_bytes / 16, b34 + 8, flat_a, true, tmem_base, &mbar[1], n_mma, nullptr, 0u,
-                         nullptr, nullptr, nullptr, nullptr, tstamp ? tstamp + 32 : nullptr);
+                st_tiles(g4, l4, n4, atile, b34_16 + StSmem::b_bytes / 16, b34 + 8, flat_a, true, tmem_base, &mbar[1], &mbar[3], gt, nullptr, 0u,
+                         nullptr, nullptr, nullptr, nullptr, tstamp ? tstamp + 8 : nullptr);
             } else {
                 const StGatherDense<100, 50> g3 = {scr2, l3, atile};
-                st_tiles(g3, l3, n3, atile, b34_16, b34, scr3, true, tmem_base, &mbar[1], n_mma, &mbar[2], n_b34 & 1u, nullptr, nullptr,
+                st_tiles(g3, l3, n3, atile, b34_16, b34, scr3, true, tmem_base, &mbar[1], &mbar[3], gt, &mbar[5], n_b34 & 1u, nullptr, nullptr,
                          nullptr, nullptr, nullptr);
                 ST_STAMP(12);
                 const StGatherDense<50, 25> g4 = {scr3, l4, atile};
-                st_tiles(g4, l4, n4, atile, b34_16 + StSmem::b_bytes / 16, b34 + 8, flat_a, true, tmem_base, &mbar[1], n_mma, nullptr, 0u,
+                st_tiles(g4, l4, n4, atile, b34_16 + StSmem::b_bytes / 16, b34 + 8, flat_a, true, tmem_base, &mbar[1], &mbar[3], gt, nullptr, 0u,
                          nullptr, nullptr, nullptr, nullptr, nullptr);
             }
             if (need_b34) n_b34++;
@@ -611,7 +631,7 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(32u));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u));
 }
 
 static long long *g_st_stamps = nullptr;
