@@ -65,12 +65,6 @@ static_assert(StSmem::a_bytes <= 40000 && ST_CAP1 * 16 >= 201 * ST_RW * 4 && 400
               StSmem::off_v3 + ST_VCAP * 16 <= StSmem::off_l2 && 2 * ST_VCAP <= ST_CAP2, "k_st_trunk12: aliasing");
 static_assert(StSmem::bytes <= 113 * 1024, "k_st_trunk12: two CTAs per SM");
 
-// 32 bits of map row r starting at column 32 c (rows are 400 bits = 12.5 words: odd rows start mid-word)
-__device__ __forceinline__ uint32_t st_row_chunk(const uint32_t *__restrict__ m, int r, int c) {
-    const int b = r * POL_W + 32 * c, w = b >> 5;
-    const uint32_t v = __funnelshift_r(m[w], m[min(w + 1, POL_WORDS - 1)], b & 31);
-    return c == ST_RW - 1 ? (v & 0xFFFFu) : v;                        // the 13th chunk holds the row's last 16 columns
-}
 // bit p of the result = bit 2p of x
 __device__ __forceinline__ uint32_t st_even_bits(uint64_t x) {
     x &= 0x5555555555555555ull;
@@ -359,11 +353,18 @@ k_st_trunk12(const uint32_t *__restrict__ maps, const PolicyDev w, __nv_bfloat16
         ST_STAMP(2);
         // ---- 2a. Q[j] = M[2j-1] | M[2j] (M = ship | laser; j = 0 .. 200), 13 aligned words per row: the 4 map rows a pool1 row
         //          depends on are Q[py] | Q[py + 1]
+        // (a map row is 12.5 words: row 2j starts at word 25 j, row 2j - 1 sixteen bits into word 25 j - 13)
         for (int i = tid; i < 201 * ST_RW; i += ST_NT) {
-            const int j = i / ST_RW, c = i - j * ST_RW;
+            const int j = i / ST_RW, c = i - j * ST_RW, we = 25 * j + c, wo = we - 13;
             uint32_t v = 0u;
-            if (j > 0) v = st_row_chunk(bs, 2 * j - 1, c) | st_row_chunk(bl, 2 * j - 1, c);
-            if (j < 200) v |= st_row_chunk(bs, 2 * j, c) | st_row_chunk(bl, 2 * j, c);
+            if (j < 200) {
+                v = bs[we] | bl[we];
+                if (c == ST_RW - 1) v &= 0xFFFFu;              // the 13th chunk holds the row's last 16 columns
+            }
+            if (j > 0) {
+                const uint32_t lo = bs[wo] | bl[wo], hi = c == ST_RW - 1 ? 0u : (bs[wo + 1] | bl[wo + 1]);
+                v |= __funnelshift_r(lo, hi, 16);
+            }
             qrow[i] = v;
         }
         __syncthreads();
