@@ -790,7 +790,7 @@ __device__ __forceinline__ float to_tf32(float v) {
 #define HEADS_A1_FLOATS (HEADS_A1_CHUNKS * 4)
 #define HEADS_U2_TILES 11                                // 52 * 27 = 1404 M rows (chunks incl. halos) in tiles of 128
 #define HEADS_SMEM_FLOATS (HEADS_G * (128 + 64 + 640) + HEADS_A1_FLOATS + 80 + 304 + 32 + 80 + 5 * 2 * 32 * 4 + 16)
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 4)
 k_heads(const float *__restrict__ hflat, const float *__restrict__ vec, PolicyDev w, int ships_per_arena, int n_ships, float *__restrict__ act_out,
         int *__restrict__ iaction_out, __nv_bfloat16 *__restrict__ up2_out, int plane_layout) {
     extern __shared__ __align__(16) float sm[];
