@@ -629,8 +629,9 @@ def kernel_roofline(bg, maps, flush_buf, wl, dev, policy=None, iters=50):
                 "note": "slowest kernel of the forward at the state the timed region ended in; tcgen05 kernels = algorithmic FLOPs "
                         "(Appendix B MACs x 2) / device time vs the measured bf16 peak; CUDA-core kernels = algorithmic bytes / device "
                         "time vs the measured HBM peak (the sparse trunk k_st_trunk12 and k_heads are issue- / latency-bound, not HBM-bound: "
-                        "the fraction says how far above their HBM floor they run; the fused tail k_tz_tail is bound by shared-memory "
-                        "operand reads of its small-N MMAs, see DESIGN.md)",
+                        "the fraction says how far above their HBM floor they run; the fused tail k_tz_tail is bound by the shared-memory "
+                        "port: an SS-mode tcgen05.mma below N = 128 costs max(N/2, 32 + N/4) cycles (measured, profiles/r02_mma_pace.md), "
+                        "ncu: tensor-operand + LSU wavefronts = 94 % of the shared-memory data pipe, tensor pipe 57 % active; see DESIGN.md)",
                 "whole_forward": {"ms": total, "forwards_per_s": n * P / (total * 1e-3), "policy_ships_per_arena": P,
                                   "dense_equiv_tflops": 155.3e6 * n * P / (total * 1e-3) / 1e12,
                                   "frac_of_peak": 155.3e6 * n * P / (total * 1e-3) / 1e12 / tpeak,
