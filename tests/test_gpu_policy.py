@@ -116,13 +116,15 @@ def test_engines_agree_tightly(setup):
     assert errs["act"] <= TOL_ENGINES and errs["ptr"] <= 1.5e-2, errs
 
 
-@pytest.mark.parametrize("scene", ["default", "stress32", "empty", "borders"])
+@pytest.mark.parametrize("scene", ["default", "stress32", "empty", "borders", "crowd16", "mixed"])
 def test_sparse_trunk_equals_dense_trunk(setup, scene):
     """The sparse trunks -- the default k_st_trunk12 in its fused form (conv1 .. conv4 in one kernel, only dirty cells evaluated on
     the tensor pipe, the rest take the precomputed empty-arena value of their border class), its three-kernel form, and round 1's
     CUDA-core sparse kernel -- against the dense tcgen05 trunk12 on the same weights: pool2, pool3, pool4 and everything
     downstream.  Scenes: a running default arena, 32 ships at maximum fire rate (most cells dirty), empty maps (every cell
-    takes the background of its border class) and entities pushed against all four walls."""
+    takes the background of its border class), entities pushed against all four walls, 16 ships at maximum fire rate (dirty-cell
+    counts around the capacity of the fused kernel's shared-memory lists) and a batch that interleaves default, stress and empty
+    arenas, so that one CTA alternates between the compact path and the fallback (scratch images, bands) from arena to arena."""
     from ofighters_b200 import ArenaConfig, BatchedBattleground
     from ofighters_b200.policy import PolicyB200
     s = setup
@@ -135,6 +137,21 @@ def test_sparse_trunk_equals_dense_trunk(setup, scene):
         maps, vec = bg.raster("bits"), bg.obs_vec[:, 0, :].contiguous()
     elif scene == "empty":
         maps, vec = torch.zeros((3, 2, 5000), dtype=torch.int32, device="cuda"), s["vec"][:3].contiguous()
+    elif scene == "crowd16":
+        bg = BatchedBattleground(8, ships={"stress": 16}, config=ArenaConfig(laser_cap=1024), seed=5)
+        for _ in range(14):
+            bg.frame()
+        maps, vec = bg.raster("bits"), bg.obs_vec[:, 0, :].contiguous()
+    elif scene == "mixed":
+        a = BatchedBattleground(5, ships={"stress": 32}, config=ArenaConfig(laser_cap=2048), seed=3)
+        for _ in range(12):
+            a.frame()
+        ma, va = a.raster("bits"), a.obs_vec[:, 0, :]
+        md, vd = s["maps"][:5], s["vec"][:5]
+        me = torch.zeros_like(md)
+        order = [(md, vd), (ma, va), (me, vd), (ma, va), (md, vd)]
+        maps = torch.stack([m[i] for i in range(5) for m, _ in order]).contiguous()      # default, stress, empty, stress, default, ...
+        vec = torch.stack([v[i] for i in range(5) for _, v in order]).contiguous()
     else:
         spawn = torch.tensor([[[0, 0], [399, 0], [0, 399], [399, 399], [200, 0], [0, 200], [399, 200]]] * 4, dtype=torch.int32)
         bg = BatchedBattleground(4, ships={"shoot": 7}, spawn_xy=spawn, seed=1)
@@ -145,7 +162,7 @@ def test_sparse_trunk_equals_dense_trunk(setup, scene):
     out = {}
     variants = {"dense": dict(dense_trunk=True), "fused": {}, "st12": dict(fused_trunk=False), "cc": dict(cc_sparse_trunk=True)}
     for kind, kw in variants.items():
-        pol = PolicyB200(s["w"], max_ships=16, **kw)
+        pol = PolicyB200(s["w"], max_ships=32, **kw)
         pol.set_taps(True)                               # the fused trunk keeps pool2 / pool3 off HBM unless asked
         r = pol.forward(maps, vec, 1, want_ptr=True)
         out[kind] = dict(pool2=pol.debug_tap(1, n, (100, 100, 8)).clone(), pool3=pol.debug_tap(2, n, (50, 50, 8)).clone(),
