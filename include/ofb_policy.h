@@ -54,7 +54,8 @@ enum { OFB_ENGINE_TENSOR = 0,      /* tcgen05 kernels (product path) */
                                       validate the tensor-core kernels layer by layer */
 
 /* max_ships = largest n_arenas * ships_per_arena a forward call may carry per chunk (the library
- * loops over chunks of that size); workspace = about 1 MB per ship.  0 = default (1024). */
+ * loops over chunks of that size); workspace = 0.18 MB per ship, plus 1.5 MB per ship allocated on the first use of
+ * an alternative kernel or of the validation taps.  0 = default (1024). */
 int ofb_policy_create(const ofb_policy_weights *w_host, int device, int max_ships, ofb_policy **out);
 /* The same with options (flags, OR-ed):
  *   OFB_POLICY_BILINEAR_TF1   UpSampling2D(interpolation='bilinear') (agents/qlearnIA_V2.py:166,171,177,183) with the TF1.x /

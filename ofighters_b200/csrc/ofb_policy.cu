@@ -298,6 +298,7 @@ static std::vector<__nv_bfloat16> pack_cell_patch(const std::vector<float> &w) {
 // the upload blob.  The blob's layout depends only on the architecture, so ofb_policy_set_weights can rebuild it in place.
 static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, PolicyDev &d, float &u4_bias, int legacy) {
     std::vector<float> w, b;
+    up.host.reserve((size_t)4 << 20);                       // (the blob is 2.9 MB: no reallocation while it grows)
     const PhaseTab PT = phase_tab(legacy);
     // trunk
     fold_conv(wh->conv[0], 2, 8, w, b);
@@ -367,12 +368,24 @@ static void build_weight_blob(const ofb_policy_weights *wh, Uploader &up, Policy
     {
         const float *k = wh->dense1.kernel;
         up.add(&d.d1_wv, k, 8 * 100);
-        std::vector<__nv_bfloat16> wf((size_t)POL_FLAT * 100), wt((size_t)128 * POL_FLAT_PITCH, __float2bfloat16(0.f));
-        for (int i = 0; i < POL_FLAT; i++)
-            for (int j = 0; j < 100; j++) {
-                wf[(size_t)i * 100 + j] = __float2bfloat16(k[(size_t)(8 + i) * 100 + j]);
-                wt[(size_t)j * POL_FLAT_PITCH + i] = wf[(size_t)i * 100 + j];
-            }
+        // (1.1 M values on the path of every weight refresh -- Trainer.replay -> ofb_policy_set_weights: the round-to-nearest-even
+        //  conversion inline on the bit pattern, the transpose in blocks of 64 rows that stay in L1)
+        auto bf16_bits = [](float f) -> uint16_t {
+            uint32_t u;
+            memcpy(&u, &f, 4);
+            if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);     // NaN stays NaN
+            return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+        };
+        std::vector<__nv_bfloat16> wf((size_t)POL_FLAT * 100), wt((size_t)128 * POL_FLAT_PITCH);
+        uint16_t *wf16 = reinterpret_cast<uint16_t *>(wf.data()), *wt16 = reinterpret_cast<uint16_t *>(wt.data());
+        memset(wt16, 0, wt.size() * 2);
+        const float *kf = k + 8 * 100;
+        for (size_t e = 0; e < (size_t)POL_FLAT * 100; e++) wf16[e] = bf16_bits(kf[e]);
+        for (int i0 = 0; i0 < POL_FLAT; i0 += 64) {
+            const int i1 = std::min(i0 + 64, (int)POL_FLAT);
+            for (int j = 0; j < 100; j++)
+                for (int i = i0; i < i1; i++) wt16[(size_t)j * POL_FLAT_PITCH + i] = wf16[(size_t)i * 100 + j];
+        }
         up.add(&d.d1_wf, wf); up.add(&d.d1_wt, wt);
         up.add(&d.d1_b, wh->dense1.bias, 100);
     }
