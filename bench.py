@@ -48,7 +48,7 @@ WORKLOADS = {
     "policy": dict(n=65536, ships=7, bot="random", lcap=0, policy=1,
                    desc="configs[2]: 65536 default arenas, ship 0 driven by the bi-head policy forward (bf16), "
                         "ships 1-6 random bots"),
-    "policy7": dict(n=16384, ships=7, bot="random", lcap=0, policy=7,
+    "policy7": dict(n=16384, ships=7, bot="random", lcap=512, policy=7,      # (seven ships that all shoot: more lasers in flight than the default 128 slots)
                     desc="configs[2] variant of SURVEY 8(d): 16384 default arenas, ALL 7 ships policy-driven "
                          "(trunk once per arena, heads x7 -> 114688 forwards per frame), bf16"),
     "sharded1m": dict(n=131072, ships=7, bot="random", lcap=0, policy=1,
